@@ -1,0 +1,160 @@
+/* mfem_b200.h -- C ABI of the B200 linear-elasticity assemble-and-solve path.
+ *
+ * MeshFEM has no plugin/FFI boundary of its own: its operator surface is C++
+ * templates.  This header is the seam a maintainer binds instead of the
+ * reference's CPU implementation; each entry point cites the reference
+ * interface it replaces (paths relative to src/lib/MeshFEM/ of MeshFEM).
+ * The host C++ mirror of the reference classes (include/MeshFEM/ in this repo)
+ * and the ctypes binding (meshfem_b200/capi.py) both call ONLY these
+ * functions.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative mfem_b200_status
+ *     otherwise; mfem_b200_last_error(h) describes the last failure.
+ *   - all pointers are HOST pointers to caller-owned buffers; device memory
+ *     is owned by the handle.  One handle <-> one CUDA device and stream;
+ *     a handle is not thread-safe (mirrors the reference's Simulator).
+ *   - Real is double everywhere (Types.hh:8).  Per-node / per-DoF vector
+ *     fields are flat, index N*node + c  (Fields.hh:46-50).
+ *   - there is NO CPU fallback: if no CUDA device is usable, create() fails.
+ */
+#ifndef MFEM_B200_H
+#define MFEM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mfem_b200_ctx *mfem_b200_handle;
+
+typedef enum {
+    MFEM_B200_OK = 0,
+    MFEM_B200_ERR_INVALID = -1,       /* bad argument / call order                     */
+    MFEM_B200_ERR_CUDA = -2,          /* CUDA runtime failure                          */
+    MFEM_B200_ERR_NEG_VOLUME = -3,    /* "Mesh has negatively oriented elements." LinearElasticity.hh:465-472 */
+    MFEM_B200_ERR_ALREADY_FIXED = -4, /* "Variable already fixed." SparseMatrices.hh:2432 */
+    MFEM_B200_ERR_BAD_RHS = -5,       /* "Bad RHS" SparseMatrices.hh:2521              */
+    MFEM_B200_ERR_NOT_SPD = -6,       /* PCG breakdown p'Ap <= 0 (CHOLMOD: not positive definite, SparseMatrices.hh:2010) */
+    MFEM_B200_ERR_NO_CONVERGE = -7,   /* max iterations reached                        */
+    MFEM_B200_ERR_NAN = -8,           /* NaN/Inf in the iteration                      */
+    MFEM_B200_ERR_COMM = -9           /* NCCL failure                                  */
+} mfem_b200_status;
+
+typedef struct {
+    int32_t iterations;       /* PCG iterations of the last right-hand side           */
+    int32_t converged;        /* 1 if ||r||_2 <= rtol ||b||_2                         */
+    double rel_residual;      /* final ||r||_2 / ||b||_2 (recurrence residual)        */
+    double seconds;           /* device time of the PCG loop (CUDA events)            */
+    double spmv_seconds;      /* device time of one stand-alone SpMV launch measured after the solve (0 if not measured) */
+} mfem_b200_solve_info;
+
+/* ---- lifetime ------------------------------------------------------------------- */
+/* Replaces constructing LinearElasticity::Simulator's device-side state.             */
+int mfem_b200_create(int device, mfem_b200_handle *out);
+int mfem_b200_destroy(mfem_b200_handle h);
+const char *mfem_b200_last_error(mfem_b200_handle h);
+/* number of CUDA devices visible, or a negative status                               */
+int mfem_b200_device_count(void);
+
+/* Multi-GPU: element-partitioned execution, one process per GPU.  nccl_unique_id is the
+ * 128-byte ncclUniqueId obtained on rank 0 (mfem_b200_comm_unique_id) and broadcast by the
+ * caller (torch.distributed / MPI / files).  Must be called before set_mesh; after it,
+ * set_mesh receives this rank's LOCAL sub-mesh plus the global ids of its nodes.       */
+int mfem_b200_comm_unique_id(void *out128);
+int mfem_b200_comm_init(mfem_b200_handle h, int n_ranks, int rank, const void *nccl_unique_id128);
+
+/* ---- options (before set_mesh) --------------------------------------------------- */
+/* "reorder": 1 (default) renumbers DoFs along a space-filling curve inside the handle;
+ *            every ABI function still speaks the caller's numbering.
+ * "assembly": 0 = owner-gather (default: every BSR block written exactly once),
+ *             1 = graph-coloured element scatter (read-modify-write, no atomics).       */
+int mfem_b200_set_option(mfem_b200_handle h, const char *name, int64_t value);
+
+/* ---- mesh ------------------------------------------------------------------------ */
+/* Replaces FEMMesh(elems, vertices) + Simulator ctor (FEMMesh.inl:11-82,
+ * LinearElasticity.hh:460-473).  dim in {2,3}, degree in {1,2}.  nodes: [n_nodes*dim].
+ * elem_nodes: [n_elems * nodesPerElem] in the reference local order (Simplex.hh:31-46:
+ * vertices, then edge nodes (0,1)(1,2)(2,0)(0,3)(2,3)(1,3)); only the first dim+1 nodes'
+ * coordinates define the (straight-sided) element (FEMMesh.hh:228-233).
+ * dof_for_node: NULL (identity) or PeriodicCondition::periodicDoFsForNodes()
+ * (BoundaryConditions.hh:457-561) with n_dofs distinct values 0..n_dofs-1.
+ * Fails with MFEM_B200_ERR_NEG_VOLUME if any element volume is < 0.                  */
+int mfem_b200_set_mesh(mfem_b200_handle h, int dim, int degree, int64_t n_nodes, const double *nodes,
+                       int64_t n_elems, const int32_t *elem_nodes, const int64_t *dof_for_node,
+                       int64_t n_dofs);
+/* Multi-GPU only: global DoF id of every local DoF (defines shared interface DoFs).    */
+int mfem_b200_set_global_dof_ids(mfem_b200_handle h, const int64_t *global_id_of_local_dof);
+
+/* ---- material -------------------------------------------------------------------- */
+/* D: flattened elasticity tensor, row-major flat x flat (flat = 3 in 2D, 6 in 3D),
+ * Voigt order xx,yy,zz,yz,xz,xy (Flattening.hh:47-60, ElasticityTensor.hh:274-289).
+ * constant  <-> _HMG static material (LinearElasticity.hh:31-44);
+ * per_element <-> ETensorStoreGetter (LinearElasticity.hh:20-29).                     */
+int mfem_b200_set_material_constant(mfem_b200_handle h, const double *D);
+int mfem_b200_set_material_per_element(mfem_b200_handle h, const double *D_per_elem);
+
+/* ---- assembly -------------------------------------------------------------------- */
+/* Replaces Simulator::m_assembleStiffnessMatrix + TripletMatrix::sumRepeated
+ * (LinearElasticity.hh:1408-1466, SparseMatrices.hh:280-374): K in DoF space, stored as
+ * full block-CSR (dim x dim blocks).  The sparsity pattern is built on first call and
+ * cached; later calls (new material / node positions) only recompute values.           */
+int mfem_b200_assemble(mfem_b200_handle h);
+int mfem_b200_get_bsr_sizes(mfem_b200_handle h, int64_t *n_block_rows, int64_t *nnz_blocks);
+/* Export in the CALLER's numbering: rowptr[nb+1], colidx[nnzb] sorted per row,
+ * vals[nnzb*dim*dim] row-major blocks.                                                */
+int mfem_b200_get_bsr(mfem_b200_handle h, int64_t *rowptr, int32_t *colidx, double *vals);
+/* TripletMatrix::dumpBinary layout of the summed upper triangle
+ * (SparseMatrices.hh:623-645: uint64 nnz | uint64 rows[] | uint64 cols[] | double vals[]);
+ * Simulate_cli --dumpMatrix.                                                           */
+int mfem_b200_dump_upper_triplets(mfem_b200_handle h, const char *path);
+/* Update node positions (Simulator::updateMeshNodePositions); pattern is kept.         */
+int mfem_b200_set_node_positions(mfem_b200_handle h, const double *nodes);
+
+/* ---- constraints + solve (SPSDSystem) -------------------------------------------- */
+/* SPSDSystem::fixVariables (SparseMatrices.hh:2389-2500): scalar variable indices
+ * dim*DoF+c and the values they are fixed to (values may be NULL = 0).  Cumulative;
+ * fixing a variable twice fails with MFEM_B200_ERR_ALREADY_FIXED.                      */
+int mfem_b200_fix_variables(mfem_b200_handle h, int64_t n, const int64_t *vars, const double *values);
+int mfem_b200_clear_fixed_variables(mfem_b200_handle h);
+/* SPSDSystem::solve (SparseMatrices.hh:2516-2606) with the CHOLMOD factorisation
+ * replaced by block-Jacobi PCG: for each of nrhs right-hand sides f (length dim*n_dofs,
+ * stored one after another) returns the full-length u with fixed variables at their
+ * values.  rtol on ||r||_2/||b||_2 of the reduced system; info may be NULL, else
+ * info[nrhs].                                                                          */
+int mfem_b200_solve(mfem_b200_handle h, int nrhs, const double *f, double *u, double rtol,
+                    int max_iters, mfem_b200_solve_info *info);
+
+/* ---- operators around the solve -------------------------------------------------- */
+/* Simulator::applyStiffnessMatrix (LinearElasticity.hh:801-823): raw K on per-NODE
+ * fields (ignores periodic DoFs and Dirichlet conditions).                              */
+int mfem_b200_apply_K(mfem_b200_handle h, const double *u_nodes, double *Ku_nodes);
+/* y = K x on per-DoF fields with the assembled block-CSR (no masking).                 */
+int mfem_b200_spmv(mfem_b200_handle h, const double *x_dofs, double *y_dofs);
+/* Simulator::constantStrainLoad (LinearElasticity.hh:551-562, 135-162); eps flattened. */
+int mfem_b200_const_strain_load(mfem_b200_handle h, const double *eps_flat, double *f_dofs);
+/* Simulator::averageStrainField / averageStressField (LinearElasticity.hh:528-549):
+ * per-element flattened averages [n_elems*flat]; either output may be NULL.           */
+int mfem_b200_avg_strain_stress(mfem_b200_handle h, const double *u_nodes, double *strain, double *stress);
+/* Per-element volumes and negative-volume count (Simulator ctor check).                */
+int mfem_b200_get_volumes(mfem_b200_handle h, double *vol);
+
+/* ---- timers (BENCHMARK_REPORT sections, GlobalBenchmark.hh:8-58) ------------------ */
+/* Seconds of device time (CUDA events) accumulated under a section name, e.g.
+ * "Pattern", "Assemble System", "Elasticity Solve", "SpMV".  Returns -1.0 if unknown.  */
+double mfem_b200_get_timer(mfem_b200_handle h, const char *section);
+int mfem_b200_reset_timers(mfem_b200_handle h);
+/* number of kernel launches issued by this handle since creation / last reset          */
+int64_t mfem_b200_launch_count(mfem_b200_handle h);
+
+/* ---- device-resident benchmarking hooks ------------------------------------------ */
+/* Run `iters` PCG iterations' worth of SpMV on the assembled matrix with device-resident
+ * vectors and return the mean device seconds per launch (CUDA events on the handle's
+ * stream).  Used by bench.py for the roofline of the dominant kernel.                  */
+int mfem_b200_time_spmv(mfem_b200_handle h, int iters, double *seconds_per_launch);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MFEM_B200_H */

@@ -1,0 +1,81 @@
+"""Build recipe for libmfem_b200.so (hand-written sm_100a CUDA behind the C ABI).
+
+In-tree build with nvcc; the .so travels to the GPU box with the repo snapshot.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(ROOT, "csrc")
+LIBDIR = os.path.join(ROOT, "lib")
+LIB = os.path.join(LIBDIR, "libmfem_b200.so")
+SOURCES = ["setup.cu", "assemble.cu", "solver.cu", "aux.cu", "comm.cu", "capi.cu"]
+HEADERS = ["core.cuh", "elem_math.cuh", os.path.join("..", "..", "include", "mfem_b200.h")]
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "--extended-lambda", "-Xcompiler", "-fPIC", "-Xcompiler", "-O3",
+]
+
+
+def _nccl_link_flags():
+    # Prefer the NCCL bundled with torch (the one torch.distributed loads); fall back to the system one.
+    cands = []
+    try:
+        import nvidia.nccl  # type: ignore
+        cands.append(os.path.join(os.path.dirname(nvidia.nccl.__file__), "lib"))
+    except Exception:
+        pass
+    for d in cands:
+        so = os.path.join(d, "libnccl.so.2")
+        if os.path.exists(so):
+            return ["-L" + d, "-l:libnccl.so.2", "-Xlinker", "-rpath=" + d]
+    return ["-lnccl"]
+
+
+def _stamp():
+    h = hashlib.sha256()
+    for f in SOURCES + HEADERS:
+        with open(os.path.join(CSRC, f), "rb") as fh:
+            h.update(fh.read())
+    h.update(" ".join(FLAGS).encode())
+    return h.hexdigest()
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    os.makedirs(LIBDIR, exist_ok=True)
+    stamp_file = LIB + ".stamp"
+    stamp = _stamp()
+    if not force and os.path.exists(LIB) and os.path.exists(stamp_file):
+        if open(stamp_file).read().strip() == stamp:
+            return LIB
+    objs = []
+    procs = []
+    for src in SOURCES:
+        obj = os.path.join(LIBDIR, src.replace(".cu", ".o"))
+        cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
+    failed = False
+    for src, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            failed = True
+            sys.stderr.write(f"--- nvcc {src} failed ---\n{out}\n")
+        elif verbose or out.strip():
+            sys.stderr.write(f"--- nvcc {src} ---\n{out}\n")
+    if failed:
+        raise RuntimeError("nvcc failed")
+    cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"] + _nccl_link_flags()
+    subprocess.check_call(cmd)
+    with open(stamp_file, "w") as f:
+        f.write(stamp)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

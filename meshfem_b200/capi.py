@@ -1,0 +1,306 @@
+"""ctypes binding of the C ABI in include/mfem_b200.h.
+
+This is the same binding a MeshFEM maintainer would write for the Python module
+(src/python_bindings/*.cc call the same entry points from C++).
+There is no CPU fallback: if libmfem_b200.so is missing or no CUDA device is
+usable, construction fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_int, c_int32, c_int64, c_void_p
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libmfem_b200.so")
+
+SYMBOLS = [
+    "mfem_b200_create", "mfem_b200_destroy", "mfem_b200_last_error", "mfem_b200_device_count",
+    "mfem_b200_comm_unique_id", "mfem_b200_comm_init", "mfem_b200_set_option", "mfem_b200_set_mesh",
+    "mfem_b200_set_global_dof_ids", "mfem_b200_set_material_constant", "mfem_b200_set_material_per_element",
+    "mfem_b200_assemble", "mfem_b200_get_bsr_sizes", "mfem_b200_get_bsr", "mfem_b200_dump_upper_triplets",
+    "mfem_b200_set_node_positions", "mfem_b200_fix_variables", "mfem_b200_clear_fixed_variables",
+    "mfem_b200_solve", "mfem_b200_apply_K", "mfem_b200_spmv", "mfem_b200_const_strain_load",
+    "mfem_b200_avg_strain_stress", "mfem_b200_get_volumes", "mfem_b200_get_timer", "mfem_b200_reset_timers",
+    "mfem_b200_launch_count", "mfem_b200_time_spmv",
+]
+
+STATUS_NAMES = {
+    0: "OK", -1: "ERR_INVALID", -2: "ERR_CUDA", -3: "ERR_NEG_VOLUME", -4: "ERR_ALREADY_FIXED",
+    -5: "ERR_BAD_RHS", -6: "ERR_NOT_SPD", -7: "ERR_NO_CONVERGE", -8: "ERR_NAN", -9: "ERR_COMM",
+}
+
+
+class SolveInfo(ctypes.Structure):
+    _fields_ = [("iterations", c_int32), ("converged", c_int32), ("rel_residual", c_double),
+                ("seconds", c_double), ("spmv_seconds", c_double)]
+
+
+class MfemB200Error(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__(f"[{STATUS_NAMES.get(status, status)}] {msg}")
+        self.status = status
+        self.message = msg
+
+
+_lib = None
+
+
+def load_library():
+    """Load libmfem_b200.so (building is the job of __graft_entry__.build / meshfem_b200.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `python -m meshfem_b200.build` "
+            "(there is no CPU fallback for the assemble-and-solve path)")
+    lib = ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_GLOBAL)
+    dp, ip, lp = POINTER(c_double), POINTER(c_int32), POINTER(c_int64)
+    lib.mfem_b200_create.argtypes = [c_int, POINTER(c_void_p)]
+    lib.mfem_b200_destroy.argtypes = [c_void_p]
+    lib.mfem_b200_last_error.argtypes = [c_void_p]
+    lib.mfem_b200_last_error.restype = c_char_p
+    lib.mfem_b200_device_count.argtypes = []
+    lib.mfem_b200_comm_unique_id.argtypes = [c_void_p]
+    lib.mfem_b200_comm_init.argtypes = [c_void_p, c_int, c_int, c_void_p]
+    lib.mfem_b200_set_option.argtypes = [c_void_p, c_char_p, c_int64]
+    lib.mfem_b200_set_mesh.argtypes = [c_void_p, c_int, c_int, c_int64, dp, c_int64, ip, lp, c_int64]
+    lib.mfem_b200_set_global_dof_ids.argtypes = [c_void_p, lp]
+    lib.mfem_b200_set_material_constant.argtypes = [c_void_p, dp]
+    lib.mfem_b200_set_material_per_element.argtypes = [c_void_p, dp]
+    lib.mfem_b200_assemble.argtypes = [c_void_p]
+    lib.mfem_b200_get_bsr_sizes.argtypes = [c_void_p, lp, lp]
+    lib.mfem_b200_get_bsr.argtypes = [c_void_p, lp, ip, dp]
+    lib.mfem_b200_dump_upper_triplets.argtypes = [c_void_p, c_char_p]
+    lib.mfem_b200_set_node_positions.argtypes = [c_void_p, dp]
+    lib.mfem_b200_fix_variables.argtypes = [c_void_p, c_int64, lp, dp]
+    lib.mfem_b200_clear_fixed_variables.argtypes = [c_void_p]
+    lib.mfem_b200_solve.argtypes = [c_void_p, c_int, dp, dp, c_double, c_int, POINTER(SolveInfo)]
+    lib.mfem_b200_apply_K.argtypes = [c_void_p, dp, dp]
+    lib.mfem_b200_spmv.argtypes = [c_void_p, dp, dp]
+    lib.mfem_b200_const_strain_load.argtypes = [c_void_p, dp, dp]
+    lib.mfem_b200_avg_strain_stress.argtypes = [c_void_p, dp, dp, dp]
+    lib.mfem_b200_get_volumes.argtypes = [c_void_p, dp]
+    lib.mfem_b200_get_timer.argtypes = [c_void_p, c_char_p]
+    lib.mfem_b200_get_timer.restype = c_double
+    lib.mfem_b200_reset_timers.argtypes = [c_void_p]
+    lib.mfem_b200_launch_count.argtypes = [c_void_p]
+    lib.mfem_b200_launch_count.restype = c_int64
+    lib.mfem_b200_time_spmv.argtypes = [c_void_p, c_int, dp]
+    for name in SYMBOLS:
+        fn = getattr(lib, name)
+        if fn.restype is c_int and name not in ("mfem_b200_device_count",):
+            fn.restype = c_int
+    _lib = lib
+    return lib
+
+
+def _dptr(a):
+    return a.ctypes.data_as(POINTER(c_double))
+
+
+def _f64(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape is not None:
+        a = a.reshape(shape)
+    return a
+
+
+def nodes_per_elem(dim, deg):
+    return dim + 1 if deg == 1 else (6 if dim == 2 else 10)
+
+
+def flat_len(dim):
+    return dim * (dim + 1) // 2
+
+
+class Handle:
+    """Thin object wrapper over an mfem_b200_handle."""
+
+    def __init__(self, device: int = 0, **options):
+        self.lib = load_library()
+        self._h = c_void_p()
+        st = self.lib.mfem_b200_create(device, ctypes.byref(self._h))
+        if st != 0:
+            msg = self.lib.mfem_b200_last_error(None).decode()
+            self._h = None
+            raise MfemB200Error(st, msg)
+        self.dim = self.deg = 0
+        self.n_nodes = self.n_elems = self.n_dofs = 0
+        for k, v in options.items():
+            self.set_option(k, v)
+
+    def _check(self, st):
+        if st != 0:
+            raise MfemB200Error(st, self.lib.mfem_b200_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.mfem_b200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # ---- configuration -----------------------------------------------------
+    def set_option(self, name, value):
+        self._check(self.lib.mfem_b200_set_option(self._h, name.encode(), int(value)))
+
+    def comm_init(self, n_ranks, rank, unique_id: bytes):
+        buf = ctypes.create_string_buffer(unique_id, 128)
+        self._check(self.lib.mfem_b200_comm_init(self._h, n_ranks, rank, buf))
+
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        lib = load_library()
+        buf = ctypes.create_string_buffer(128)
+        st = lib.mfem_b200_comm_unique_id(buf)
+        if st != 0:
+            raise MfemB200Error(st, "ncclGetUniqueId failed")
+        return buf.raw
+
+    def set_mesh(self, dim, deg, nodes, elem_nodes, dof_for_node=None, n_dofs=None):
+        nodes = _f64(nodes)
+        en = np.ascontiguousarray(elem_nodes, dtype=np.int32)
+        assert nodes.ndim == 2 and nodes.shape[1] == dim
+        assert en.ndim == 2 and en.shape[1] == nodes_per_elem(dim, deg)
+        dptr = None
+        nd = nodes.shape[0]
+        if dof_for_node is not None:
+            dof = np.ascontiguousarray(dof_for_node, dtype=np.int64)
+            dptr = dof.ctypes.data_as(POINTER(c_int64))
+            nd = int(n_dofs if n_dofs is not None else dof.max() + 1)
+        self._check(self.lib.mfem_b200_set_mesh(self._h, dim, deg, nodes.shape[0], _dptr(nodes), en.shape[0],
+                                                en.ctypes.data_as(POINTER(c_int32)), dptr, nd))
+        self.dim, self.deg = dim, deg
+        self.n_nodes, self.n_elems, self.n_dofs = nodes.shape[0], en.shape[0], nd
+
+    def set_global_dof_ids(self, ids):
+        ids = np.ascontiguousarray(ids, dtype=np.int64)
+        self._check(self.lib.mfem_b200_set_global_dof_ids(self._h, ids.ctypes.data_as(POINTER(c_int64))))
+
+    def set_node_positions(self, nodes):
+        nodes = _f64(nodes, (self.n_nodes, self.dim))
+        self._check(self.lib.mfem_b200_set_node_positions(self._h, _dptr(nodes)))
+
+    def set_material(self, D):
+        D = _f64(D)
+        F = flat_len(self.dim)
+        if D.shape == (F, F):
+            self._check(self.lib.mfem_b200_set_material_constant(self._h, _dptr(D)))
+        elif D.shape == (self.n_elems, F, F):
+            self._check(self.lib.mfem_b200_set_material_per_element(self._h, _dptr(D)))
+        else:
+            raise ValueError(f"material tensor has shape {D.shape}")
+
+    # ---- assembly ------------------------------------------------------------
+    def assemble(self):
+        self._check(self.lib.mfem_b200_assemble(self._h))
+
+    def bsr_sizes(self):
+        nb, nnzb = c_int64(), c_int64()
+        self._check(self.lib.mfem_b200_get_bsr_sizes(self._h, ctypes.byref(nb), ctypes.byref(nnzb)))
+        return nb.value, nnzb.value
+
+    def get_bsr(self, values=True):
+        nb, nnzb = self.bsr_sizes()
+        N = self.dim
+        rowptr = np.zeros(nb + 1, dtype=np.int64)
+        colidx = np.zeros(nnzb, dtype=np.int32)
+        vals = np.zeros((nnzb, N, N)) if values else None
+        self._check(self.lib.mfem_b200_get_bsr(self._h, rowptr.ctypes.data_as(POINTER(c_int64)),
+                                               colidx.ctypes.data_as(POINTER(c_int32)),
+                                               _dptr(vals) if values else None))
+        return rowptr, colidx, vals
+
+    def get_matrix(self):
+        """Assembled K as a scipy BSR matrix in the caller's numbering."""
+        import scipy.sparse as sp
+        rowptr, colidx, vals = self.get_bsr()
+        n = self.n_dofs * self.dim
+        return sp.bsr_matrix((vals, colidx, rowptr), shape=(n, n))
+
+    def dump_upper_triplets(self, path):
+        self._check(self.lib.mfem_b200_dump_upper_triplets(self._h, os.fsencode(path)))
+
+    # ---- constraints + solve ----------------------------------------------------
+    def fix_variables(self, vars_, values=None):
+        v = np.ascontiguousarray(vars_, dtype=np.int64)
+        x = None if values is None else _f64(values)
+        self._check(self.lib.mfem_b200_fix_variables(self._h, v.size, v.ctypes.data_as(POINTER(c_int64)),
+                                                     None if x is None else _dptr(x)))
+
+    def clear_fixed_variables(self):
+        self._check(self.lib.mfem_b200_clear_fixed_variables(self._h))
+
+    def solve(self, f, rtol=1e-10, max_iters=100000, return_info=False):
+        n = self.n_dofs * self.dim
+        f = _f64(f)
+        nrhs = f.size // n
+        assert f.size == nrhs * n and nrhs >= 1
+        u = np.zeros_like(f)
+        info = (SolveInfo * nrhs)()
+        st = self.lib.mfem_b200_solve(self._h, nrhs, _dptr(f), _dptr(u), rtol, max_iters, info)
+        self.last_info = [dict(iterations=i.iterations, converged=bool(i.converged), rel_residual=i.rel_residual,
+                               seconds=i.seconds) for i in info]
+        self._check(st)
+        return (u, self.last_info) if return_info else u
+
+    # ---- operators -----------------------------------------------------------------
+    def spmv(self, x):
+        x = _f64(x)
+        y = np.zeros_like(x)
+        self._check(self.lib.mfem_b200_spmv(self._h, _dptr(x), _dptr(y)))
+        return y
+
+    def apply_K(self, u_nodes):
+        u = _f64(u_nodes)
+        out = np.zeros_like(u)
+        self._check(self.lib.mfem_b200_apply_K(self._h, _dptr(u), _dptr(out)))
+        return out
+
+    def const_strain_load(self, eps_flat):
+        e = _f64(eps_flat)
+        out = np.zeros((self.n_dofs, self.dim))
+        self._check(self.lib.mfem_b200_const_strain_load(self._h, _dptr(e), _dptr(out)))
+        return out
+
+    def avg_strain_stress(self, u_nodes):
+        u = _f64(u_nodes)
+        F = flat_len(self.dim)
+        strain = np.zeros((self.n_elems, F))
+        stress = np.zeros((self.n_elems, F))
+        self._check(self.lib.mfem_b200_avg_strain_stress(self._h, _dptr(u), _dptr(strain), _dptr(stress)))
+        return strain, stress
+
+    def volumes(self):
+        v = np.zeros(self.n_elems)
+        self._check(self.lib.mfem_b200_get_volumes(self._h, _dptr(v)))
+        return v
+
+    # ---- bookkeeping ----------------------------------------------------------------
+    def timer(self, section):
+        return self.lib.mfem_b200_get_timer(self._h, section.encode())
+
+    def reset_timers(self):
+        self.lib.mfem_b200_reset_timers(self._h)
+
+    def launch_count(self):
+        return self.lib.mfem_b200_launch_count(self._h)
+
+    def time_spmv(self, iters=20):
+        s = c_double()
+        self._check(self.lib.mfem_b200_time_spmv(self._h, iters, ctypes.byref(s)))
+        return s.value

@@ -1,0 +1,375 @@
+// C ABI of libmfem_b200 (include/mfem_b200.h): argument checking, host<->device staging,
+// exception -> status translation.  No compute lives here.
+#include <cstring>
+#include <fstream>
+
+#include "core.cuh"
+
+using namespace mfem;
+
+namespace mfem {
+void comm_destroy(mfem_b200_ctx *c);   // comm.cu
+}
+
+#define API_BEGIN(h)                                   \
+    if (!(h)) return MFEM_B200_ERR_INVALID;            \
+    try {                                              \
+        MFEM_CUDA(cudaSetDevice((h)->device));
+#define API_END(h)                                     \
+        return MFEM_B200_OK;                           \
+    } catch (const CudaError &e) {                     \
+        (h)->err = e.what();                           \
+        return e.status;                               \
+    } catch (const std::exception &e) {                \
+        (h)->err = e.what();                           \
+        return MFEM_B200_ERR_INVALID;                  \
+    }
+
+static thread_local std::string g_createError;
+
+extern "C" {
+
+int mfem_b200_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return MFEM_B200_ERR_CUDA;
+    return n;
+}
+
+int mfem_b200_create(int device, mfem_b200_handle *out) {
+    if (!out) return MFEM_B200_ERR_INVALID;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        g_createError = std::string("no usable CUDA device (") + cudaGetErrorString(e) +
+                        "); this library has no CPU fallback";
+        return MFEM_B200_ERR_CUDA;
+    }
+    if (device < 0 || device >= n) { g_createError = "device index out of range"; return MFEM_B200_ERR_INVALID; }
+    if (cudaSetDevice(device) != cudaSuccess) { g_createError = "cudaSetDevice failed"; return MFEM_B200_ERR_CUDA; }
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    if (prop.major < 10) {
+        g_createError = "device compute capability " + std::to_string(prop.major) + "." + std::to_string(prop.minor) +
+                        " < 10.0: this library is built for sm_100a only";
+        return MFEM_B200_ERR_CUDA;
+    }
+    auto *c = new mfem_b200_ctx();
+    c->device = device;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete c;
+        g_createError = "cudaStreamCreate failed";
+        return MFEM_B200_ERR_CUDA;
+    }
+    *out = c;
+    return MFEM_B200_OK;
+}
+
+int mfem_b200_destroy(mfem_b200_handle h) {
+    if (!h) return MFEM_B200_ERR_INVALID;
+    cudaSetDevice(h->device);
+    comm_destroy(h);
+    if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+    delete h;
+    return MFEM_B200_OK;
+}
+
+const char *mfem_b200_last_error(mfem_b200_handle h) {
+    if (!h) return g_createError.c_str();
+    return h->err.c_str();
+}
+
+int mfem_b200_set_option(mfem_b200_handle h, const char *name, int64_t value) {
+    API_BEGIN(h)
+    MFEM_REQUIRE(name, MFEM_B200_ERR_INVALID, "null option name");
+    const std::string n(name);
+    if (n == "reorder") {
+        MFEM_REQUIRE(h->nElems == 0, MFEM_B200_ERR_INVALID, "option 'reorder' must be set before set_mesh");
+        h->opt_reorder = value != 0;
+    } else if (n == "assembly") {
+        MFEM_REQUIRE(value == 0 || value == 1, MFEM_B200_ERR_INVALID, "assembly must be 0 or 1");
+        h->opt_assembly = (int)value;
+    } else if (n == "graph") {
+        h->opt_graph = value != 0;
+    } else {
+        throw CudaError(MFEM_B200_ERR_INVALID, "unknown option " + n);
+    }
+    API_END(h)
+}
+
+int mfem_b200_set_mesh(mfem_b200_handle h, int dim, int degree, int64_t n_nodes, const double *nodes,
+                       int64_t n_elems, const int32_t *elem_nodes, const int64_t *dof_for_node, int64_t n_dofs) {
+    API_BEGIN(h)
+    setup_mesh(h, dim, degree, n_nodes, nodes, n_elems, elem_nodes, dof_for_node, n_dofs);
+    API_END(h)
+}
+
+int mfem_b200_set_node_positions(mfem_b200_handle h, const double *nodes) {
+    API_BEGIN(h)
+    MFEM_REQUIRE(h->nElems > 0 && nodes, MFEM_B200_ERR_INVALID, "set_node_positions: no mesh set");
+    MFEM_CUDA(cudaMemcpyAsync(h->nodes, nodes, h->nodes.bytes(), cudaMemcpyHostToDevice, h->stream));
+    compute_geometry(h);
+    h->precondValid = false;
+    API_END(h)
+}
+
+int mfem_b200_set_material_constant(mfem_b200_handle h, const double *D) {
+    API_BEGIN(h)
+    MFEM_REQUIRE(h->N > 0 && D, MFEM_B200_ERR_INVALID, "set_material: set the mesh first");
+    const int F = flat_len(h->N);
+    std::memset(&h->Dconst, 0, sizeof(h->Dconst));
+    for (int i = 0; i < F; ++i)
+        for (int j = 0; j < F; ++j) {
+            // symmetrise from the upper triangle, as every reference setter does
+            // (ElasticityTensor.hh:134 selfadjointView<Upper>)
+            h->Dconst.d[i * F + j] = (i <= j) ? D[i * F + j] : D[j * F + i];
+        }
+    h->perElemD = false;
+    h->Delem.free();
+    h->haveMaterial = true;
+    h->valuesValid = false;
+    h->precondValid = false;
+    API_END(h)
+}
+
+int mfem_b200_set_material_per_element(mfem_b200_handle h, const double *D) {
+    API_BEGIN(h)
+    MFEM_REQUIRE(h->nElems > 0 && D, MFEM_B200_ERR_INVALID, "set_material: set the mesh first");
+    const int F = flat_len(h->N);
+    std::vector<double> sym((size_t)h->nElems * F * F);
+    for (int64_t e = 0; e < h->nElems; ++e)
+        for (int i = 0; i < F; ++i)
+            for (int j = 0; j < F; ++j)
+                sym[(size_t)e * F * F + i * F + j] = (i <= j) ? D[e * F * F + i * F + j] : D[e * F * F + j * F + i];
+    h->Delem.alloc(sym.size());
+    MFEM_CUDA(cudaMemcpy(h->Delem, sym.data(), h->Delem.bytes(), cudaMemcpyHostToDevice));
+    h->perElemD = true;
+    h->haveMaterial = true;
+    h->valuesValid = false;
+    h->precondValid = false;
+    API_END(h)
+}
+
+int mfem_b200_assemble(mfem_b200_handle h) {
+    API_BEGIN(h)
+    assemble_values(h);
+    MFEM_CUDA(cudaStreamSynchronize(h->stream));
+    API_END(h)
+}
+
+int mfem_b200_get_bsr_sizes(mfem_b200_handle h, int64_t *n_block_rows, int64_t *nnz_blocks) {
+    API_BEGIN(h)
+    MFEM_REQUIRE(h->patternValid, MFEM_B200_ERR_INVALID, "get_bsr_sizes: matrix not assembled");
+    if (n_block_rows) *n_block_rows = h->nDofs;
+    if (nnz_blocks) *nnz_blocks = h->nnzb;
+    API_END(h)
+}
+
+int mfem_b200_get_bsr(mfem_b200_handle h, int64_t *rowptr, int32_t *colidx, double *vals) {
+    API_BEGIN(h)
+    MFEM_REQUIRE(rowptr, MFEM_B200_ERR_INVALID, "get_bsr: rowptr required");
+    MFEM_CUDA(cudaStreamSynchronize(h->stream));
+    export_bsr(h, rowptr, colidx, vals);
+    API_END(h)
+}
+
+int mfem_b200_dump_upper_triplets(mfem_b200_handle h, const char *path) {
+    API_BEGIN(h)
+    MFEM_REQUIRE(path && h->valuesValid, MFEM_B200_ERR_INVALID, "dump: matrix not assembled");
+    const int N = h->N, NN = N * N;
+    std::vector<int64_t> rp((size_t)h->nDofs + 1);
+    std::vector<int32_t> ci((size_t)h->nnzb);
+    std::vector<double> v((size_t)h->nnzb * NN);
+    export_bsr(h, rp.data(), ci.data(), v.data());
+    // column-major order like the reference's sorted CSC (SparseMatrices.hh:355-361)
+    std::vector<uint64_t> rows, cols;
+    std::vector<double> vv;
+    // K is symmetric: upper triangle of column j == lower triangle entries of row j transposed;
+    // emit by (col, row) using the row-major data of row `col`.
+    for (int64_t bj = 0; bj < h->nDofs; ++bj)
+        for (int cj = 0; cj < N; ++cj)
+            for (int64_t k = rp[(size_t)bj]; k < rp[(size_t)bj + 1]; ++k) {
+                const int64_t bi = ci[(size_t)k];
+                for (int cc = 0; cc < N; ++cc) {
+                    const uint64_t row = (uint64_t)(N * bi + cc), col = (uint64_t)(N * bj + cj);
+                    if (row > col) continue;
+                    const double val = v[(size_t)k * NN + cj * N + cc];   // K[col,row] == K[row,col]
+                    if (val * val <= 0.0) continue;                        // pruneTol = 0
+                    rows.push_back(row); cols.push_back(col); vv.push_back(val);
+                }
+            }
+    std::ofstream os(path, std::ios::binary);
+    MFEM_REQUIRE(os.is_open(), MFEM_B200_ERR_INVALID, std::string("cannot open ") + path);
+    const uint64_t nnz = rows.size();
+    os.write(reinterpret_cast<const char *>(&nnz), 8);
+    os.write(reinterpret_cast<const char *>(rows.data()), 8 * nnz);
+    os.write(reinterpret_cast<const char *>(cols.data()), 8 * nnz);
+    os.write(reinterpret_cast<const char *>(vv.data()), 8 * nnz);
+    API_END(h)
+}
+
+__global__ void k_set_fixed(int64_t n, int N, const int64_t *vars, const double *vals, const int32_t *ext2int,
+                            uint8_t *mask, double *fixedVals) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t v = vars[i];
+    const int64_t d = v / N;
+    const int cc = (int)(v - d * N);
+    const int64_t vi = (int64_t)ext2int[d] * N + cc;
+    mask[vi] = 1;
+    fixedVals[vi] = vals ? vals[i] : 0.0;
+}
+
+int mfem_b200_fix_variables(mfem_b200_handle h, int64_t n, const int64_t *vars, const double *values) {
+    API_BEGIN(h)
+    MFEM_REQUIRE(h->nElems > 0, MFEM_B200_ERR_INVALID, "fix_variables: no mesh set");
+    if (n == 0) return MFEM_B200_OK;
+    MFEM_REQUIRE(n > 0 && vars, MFEM_B200_ERR_INVALID, "fix_variables: bad arguments");
+    const int64_t nvar = h->nvar();
+    for (int64_t i = 0; i < n; ++i) {
+        MFEM_REQUIRE(vars[i] >= 0 && vars[i] < nvar, MFEM_B200_ERR_INVALID, "fix_variables: variable out of range");
+        MFEM_REQUIRE(!h->fixedHost[(size_t)vars[i]], MFEM_B200_ERR_ALREADY_FIXED, "Variable already fixed.");
+        h->fixedHost[(size_t)vars[i]] = 1;
+    }
+    h->nFixed += n;
+    ensure_work(h);
+    DevBuf<int64_t> dv((size_t)n);
+    DevBuf<double> dx;
+    MFEM_CUDA(cudaMemcpyAsync(dv, vars, dv.bytes(), cudaMemcpyHostToDevice, h->stream));
+    if (values) {
+        dx.alloc((size_t)n);
+        MFEM_CUDA(cudaMemcpyAsync(dx, values, dx.bytes(), cudaMemcpyHostToDevice, h->stream));
+    }
+    k_set_fixed<<<grid_for(n, 256), 256, 0, h->stream>>>(n, h->N, dv, values ? dx.p : nullptr, h->ext2int,
+                                                         h->fixedMask, h->fixedVals);
+    h->launches++;
+    MFEM_CUDA(cudaStreamSynchronize(h->stream));
+    MFEM_CUDA(cudaGetLastError());
+    h->precondValid = false;
+    API_END(h)
+}
+
+int mfem_b200_clear_fixed_variables(mfem_b200_handle h) {
+    API_BEGIN(h)
+    std::fill(h->fixedHost.begin(), h->fixedHost.end(), 0);
+    h->nFixed = 0;
+    if (h->fixedMask.n) {
+        MFEM_CUDA(cudaMemsetAsync(h->fixedMask, 0, h->fixedMask.bytes(), h->stream));
+        MFEM_CUDA(cudaMemsetAsync(h->fixedVals, 0, h->fixedVals.bytes(), h->stream));
+    }
+    h->precondValid = false;
+    API_END(h)
+}
+
+int mfem_b200_solve(mfem_b200_handle h, int nrhs, const double *f, double *u, double rtol, int max_iters,
+                    mfem_b200_solve_info *info) {
+    API_BEGIN(h)
+    MFEM_REQUIRE(nrhs >= 1 && f && u, MFEM_B200_ERR_BAD_RHS, "Bad RHS");
+    MFEM_REQUIRE(h->valuesValid, MFEM_B200_ERR_INVALID, "No system to solve");
+    MFEM_REQUIRE(rtol > 0 && max_iters > 0, MFEM_B200_ERR_INVALID, "solve: bad tolerance / iteration limit");
+    const size_t n = (size_t)h->nvar();
+    DevBuf<double> fext(n), fin(n), uin(n), uext(n);
+    int firstErr = MFEM_B200_OK;
+    std::string firstMsg;
+    for (int k = 0; k < nrhs; ++k) {
+        MFEM_CUDA(cudaMemcpyAsync(fext, f + (size_t)k * n, n * 8, cudaMemcpyHostToDevice, h->stream));
+        permute_to_internal(h, fext, fin);
+        try {
+            pcg_solve(h, fin, uin, rtol, max_iters, info ? info + k : nullptr);
+        } catch (const CudaError &e) {
+            if (e.status != MFEM_B200_ERR_NO_CONVERGE) throw;
+            if (firstErr == MFEM_B200_OK) { firstErr = e.status; firstMsg = e.what(); }
+        }
+        permute_to_external(h, uin, uext);
+        MFEM_CUDA(cudaMemcpyAsync(u + (size_t)k * n, uext, n * 8, cudaMemcpyDeviceToHost, h->stream));
+        MFEM_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    if (firstErr != MFEM_B200_OK) throw CudaError(firstErr, firstMsg);
+    API_END(h)
+}
+
+int mfem_b200_spmv(mfem_b200_handle h, const double *x, double *y) {
+    API_BEGIN(h)
+    MFEM_REQUIRE(x && y, MFEM_B200_ERR_INVALID, "spmv: null argument");
+    const size_t n = (size_t)h->nvar();
+    DevBuf<double> a(n), b(n);
+    MFEM_CUDA(cudaMemcpyAsync(a, x, n * 8, cudaMemcpyHostToDevice, h->stream));
+    permute_to_internal(h, a, b);
+    spmv_plain(h, b, a);
+    permute_to_external(h, a, b);
+    MFEM_CUDA(cudaMemcpyAsync(y, b, n * 8, cudaMemcpyDeviceToHost, h->stream));
+    MFEM_CUDA(cudaStreamSynchronize(h->stream));
+    API_END(h)
+}
+
+int mfem_b200_apply_K(mfem_b200_handle h, const double *u_nodes, double *Ku_nodes) {
+    API_BEGIN(h)
+    MFEM_REQUIRE(u_nodes && Ku_nodes, MFEM_B200_ERR_INVALID, "apply_K: null argument");
+    const size_t n = (size_t)h->nNodes * h->N;
+    DevBuf<double> a(n), b(n);
+    MFEM_CUDA(cudaMemcpyAsync(a, u_nodes, n * 8, cudaMemcpyHostToDevice, h->stream));
+    apply_K_nodes(h, a, b);
+    MFEM_CUDA(cudaMemcpyAsync(Ku_nodes, b, n * 8, cudaMemcpyDeviceToHost, h->stream));
+    MFEM_CUDA(cudaStreamSynchronize(h->stream));
+    API_END(h)
+}
+
+int mfem_b200_const_strain_load(mfem_b200_handle h, const double *eps_flat, double *f_dofs) {
+    API_BEGIN(h)
+    MFEM_REQUIRE(eps_flat && f_dofs, MFEM_B200_ERR_INVALID, "const_strain_load: null argument");
+    const size_t n = (size_t)h->nvar();
+    DevBuf<double> fext(n);
+    const_strain_load(h, eps_flat, fext);
+    MFEM_CUDA(cudaMemcpyAsync(f_dofs, fext, n * 8, cudaMemcpyDeviceToHost, h->stream));
+    MFEM_CUDA(cudaStreamSynchronize(h->stream));
+    API_END(h)
+}
+
+int mfem_b200_avg_strain_stress(mfem_b200_handle h, const double *u_nodes, double *strain, double *stress) {
+    API_BEGIN(h)
+    MFEM_REQUIRE(u_nodes && h->nElems > 0, MFEM_B200_ERR_INVALID, "avg_strain_stress: bad arguments");
+    const size_t n = (size_t)h->nNodes * h->N, m = (size_t)h->nElems * flat_len(h->N);
+    DevBuf<double> u(n), e, s;
+    if (strain) e.alloc(m);
+    if (stress) s.alloc(m);
+    MFEM_CUDA(cudaMemcpyAsync(u, u_nodes, n * 8, cudaMemcpyHostToDevice, h->stream));
+    avg_strain_stress(h, u, strain ? e.p : nullptr, stress ? s.p : nullptr);
+    if (strain) MFEM_CUDA(cudaMemcpyAsync(strain, e, m * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (stress) MFEM_CUDA(cudaMemcpyAsync(stress, s, m * 8, cudaMemcpyDeviceToHost, h->stream));
+    MFEM_CUDA(cudaStreamSynchronize(h->stream));
+    API_END(h)
+}
+
+int mfem_b200_get_volumes(mfem_b200_handle h, double *vol) {
+    API_BEGIN(h)
+    MFEM_REQUIRE(vol && h->geom.n, MFEM_B200_ERR_INVALID, "get_volumes: no mesh set");
+    const int GS = 1 + h->N * (h->N + 1);
+    MFEM_CUDA(cudaMemcpy2D(vol, sizeof(double), h->geom, GS * sizeof(double), sizeof(double), (size_t)h->nElems,
+                           cudaMemcpyDeviceToHost));
+    API_END(h)
+}
+
+double mfem_b200_get_timer(mfem_b200_handle h, const char *section) {
+    if (!h || !section) return -1.0;
+    auto it = h->timers.find(section);
+    return it == h->timers.end() ? -1.0 : it->second;
+}
+
+int mfem_b200_reset_timers(mfem_b200_handle h) {
+    if (!h) return MFEM_B200_ERR_INVALID;
+    h->timers.clear();
+    h->launches = 0;
+    return MFEM_B200_OK;
+}
+
+int64_t mfem_b200_launch_count(mfem_b200_handle h) { return h ? h->launches : -1; }
+
+int mfem_b200_time_spmv(mfem_b200_handle h, int iters, double *seconds_per_launch) {
+    API_BEGIN(h)
+    MFEM_REQUIRE(iters > 0 && seconds_per_launch, MFEM_B200_ERR_INVALID, "time_spmv: bad arguments");
+    *seconds_per_launch = time_spmv(h, iters);
+    API_END(h)
+}
+
+}  // extern "C"

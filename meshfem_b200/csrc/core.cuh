@@ -1,0 +1,195 @@
+// Shared state and helpers of libmfem_b200 (internal header; the public surface is
+// include/mfem_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/mfem_b200.h"
+#include "elem_math.cuh"
+
+namespace mfem {
+
+struct CudaError : std::runtime_error {
+    int status;
+    CudaError(int st, const std::string &m) : std::runtime_error(m), status(st) {}
+};
+
+#define MFEM_CUDA(call)                                                                          \
+    do {                                                                                         \
+        cudaError_t e_ = (call);                                                                 \
+        if (e_ != cudaSuccess)                                                                   \
+            throw mfem::CudaError(MFEM_B200_ERR_CUDA, std::string(#call) + " failed at " +        \
+                                                          __FILE__ + ":" + std::to_string(__LINE__) + \
+                                                          ": " + cudaGetErrorString(e_));        \
+    } while (0)
+
+#define MFEM_REQUIRE(cond, status, msg)                       \
+    do {                                                      \
+        if (!(cond)) throw mfem::CudaError((status), (msg));  \
+    } while (0)
+
+// Owning device buffer (plain cudaMalloc; lifetime = handle or a setup scope).
+template <class T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    explicit DevBuf(size_t count) { alloc(count); }
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DevBuf &operator=(DevBuf &&o) noexcept {
+        if (this != &o) { free(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+        return *this;
+    }
+    ~DevBuf() { free(); }
+    void alloc(size_t count) {
+        free();
+        n = count;
+        if (count) MFEM_CUDA(cudaMalloc(reinterpret_cast<void **>(&p), count * sizeof(T)));
+    }
+    void free() {
+        if (p) cudaFree(p);
+        p = nullptr; n = 0;
+    }
+    size_t bytes() const { return n * sizeof(T); }
+    operator T *() const { return p; }
+};
+
+struct MatD {            // constant material, lives in the kernel parameter (constant) bank
+    double d[36];
+};
+
+// One cached PCG workspace (vectors of length nvar).
+struct PcgWork {
+    DevBuf<double> x, r, z, p, Ap, b, ufix;
+    DevBuf<double> partials;     // per-CTA partial sums, 4 slots
+    DevBuf<double> scal;         // device scalars (see solver.cu)
+    DevBuf<unsigned> ticket;     // last-block tickets
+    DevBuf<int> status;          // [0]=iterations done, [1]=state (0 running, 1 converged, 2 breakdown, 3 nan)
+};
+
+struct Halo;   // multi-GPU interface exchange (comm.cu)
+
+}  // namespace mfem
+
+struct mfem_b200_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+
+    // options
+    int opt_reorder = 1;
+    int opt_assembly = 0;
+    int opt_graph = 1;
+
+    // mesh
+    int N = 0, deg = 0, npe = 0;
+    int64_t nNodes = 0, nElems = 0, nDofs = 0;
+    bool periodic = false;                 // dof_for_node given
+    mfem::DevBuf<double> nodes;            // [nNodes*N]   caller's node order
+    mfem::DevBuf<int32_t> elemNodes;       // [nElems*npe] caller's node ids
+    mfem::DevBuf<int32_t> elemDof;         // [nElems*npe] INTERNAL dof ids
+    mfem::DevBuf<int32_t> nodeDof;         // [nNodes]     internal dof of each node
+    mfem::DevBuf<int32_t> ext2int, int2ext;  // [nDofs]
+    mfem::DevBuf<double> geom;             // [nElems*(1+N*(N+1))]  vol, G
+    bool geomValid = false;
+
+    // material
+    bool haveMaterial = false, perElemD = false;
+    mfem::MatD Dconst{};
+    mfem::DevBuf<double> Delem;            // [nElems*flat*flat]
+
+    // block-CSR matrix (internal numbering)
+    bool patternValid = false, valuesValid = false;
+    int64_t nnzb = 0;
+    mfem::DevBuf<int64_t> rowptr;          // [nDofs+1]
+    mfem::DevBuf<int32_t> colidx;          // [nnzb]
+    mfem::DevBuf<double> vals;             // [nnzb*N*N]
+    // DoF -> incident (element, local node) lists
+    int64_t totalInc = 0;
+    mfem::DevBuf<int64_t> incPtr;          // [nDofs+1]
+    mfem::DevBuf<int32_t> incList;         // [totalInc]  e*npe + i
+    // element colouring (assembly mode 1)
+    int nColors = 0;
+    std::vector<int64_t> colorPtr;         // host: [nColors+1]
+    mfem::DevBuf<int32_t> colorElems;      // elements sorted by colour
+
+    // constraints
+    std::vector<uint8_t> fixedHost;        // [nDofs*N] caller's numbering
+    int64_t nFixed = 0;
+    mfem::DevBuf<uint8_t> fixedMask;       // [nDofs*N] internal numbering, 1 = fixed
+    mfem::DevBuf<double> fixedVals;        // [nDofs*N]
+    mfem::DevBuf<double> Minv;             // [nDofs*N*N] inverse diagonal blocks after masking
+    bool precondValid = false;
+
+    mfem::PcgWork work;
+    bool workValid = false;
+
+    // multi-GPU
+    int nRanks = 1, rank = 0;
+    void *ncclComm = nullptr;
+    mfem::Halo *halo = nullptr;
+
+    // bookkeeping
+    std::map<std::string, double> timers;
+    int64_t launches = 0;
+
+    int64_t nvar() const { return nDofs * N; }
+};
+
+namespace mfem {
+
+struct ScopedTimer {           // CUDA-event section timer accumulating into ctx->timers
+    mfem_b200_ctx *c;
+    std::string name;
+    cudaEvent_t e0, e1;
+    ScopedTimer(mfem_b200_ctx *ctx, const char *n) : c(ctx), name(n) {
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaEventRecord(e0, c->stream);
+    }
+    double stop() {
+        if (!e0) return 0.0;
+        cudaEventRecord(e1, c->stream);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        e0 = e1 = nullptr;
+        c->timers[name] += ms * 1e-3;
+        return ms * 1e-3;
+    }
+    ~ScopedTimer() { stop(); }
+};
+
+inline int grid_for(int64_t n, int block) { return static_cast<int>((n + block - 1) / block); }
+
+// setup.cu
+void setup_mesh(mfem_b200_ctx *c, int dim, int degree, int64_t nNodes, const double *nodes, int64_t nElems,
+                const int32_t *elemNodes, const int64_t *dofForNode, int64_t nDofs);
+void compute_geometry(mfem_b200_ctx *c);
+void build_pattern(mfem_b200_ctx *c);
+void build_coloring(mfem_b200_ctx *c);
+// assemble.cu
+void assemble_values(mfem_b200_ctx *c);
+// solver.cu
+void spmv_plain(mfem_b200_ctx *c, const double *x_int, double *y_int);
+void build_preconditioner(mfem_b200_ctx *c);
+void pcg_solve(mfem_b200_ctx *c, const double *f_ext_dev, double *u_ext_dev, double rtol, int maxIters,
+               mfem_b200_solve_info *info);
+void ensure_work(mfem_b200_ctx *c);
+double time_spmv(mfem_b200_ctx *c, int iters);
+// aux.cu
+void permute_to_internal(mfem_b200_ctx *c, const double *ext, double *in);   // per-DoF vectors
+void permute_to_external(mfem_b200_ctx *c, const double *in, double *ext);
+void apply_K_nodes(mfem_b200_ctx *c, const double *u_nodes_dev, double *Ku_nodes_dev);
+void const_strain_load(mfem_b200_ctx *c, const double *epsFlatHost, double *f_ext_dev);
+void avg_strain_stress(mfem_b200_ctx *c, const double *u_nodes_dev, double *strain_dev, double *stress_dev);
+void export_bsr(mfem_b200_ctx *c, int64_t *rowptr, int32_t *colidx, double *vals);
+
+}  // namespace mfem

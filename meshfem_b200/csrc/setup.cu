@@ -1,0 +1,398 @@
+// Mesh upload, DoF renumbering, element geometry, and the symbolic phase
+// (block-CSR pattern + DoF->element incidence lists) -- all on the device.
+//
+// Reference being replaced:
+//   FEMMesh ctor / Simulator ctor            FEMMesh.inl:11-82, LinearElasticity.hh:460-473
+//   LinearlyEmbeddedSimplex::embed           EmbeddedElement.hh:170-190, 211-231
+//   triplet reservation + sumRepeated's      LinearElasticity.hh:1441-1443,
+//   bucket/sort/unique (symbolic part)       SparseMatrices.hh:280-374
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <limits>
+
+#include "core.cuh"
+
+namespace mfem {
+
+// ---------------------------------------------------------------------------
+// small kernels
+// ---------------------------------------------------------------------------
+__global__ void k_check_elem_nodes(int64_t n, const int32_t *en, int64_t nNodes, int *bad) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n && (en[i] < 0 || en[i] >= nNodes)) atomicAdd(bad, 1);
+}
+
+__global__ void k_rep_node(int64_t nNodes, const int32_t *dofOfNode, int32_t *repNode) {
+    int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (n < nNodes) atomicMin(&repNode[dofOfNode[n]], (int32_t)n);
+}
+
+__device__ __forceinline__ uint64_t spread3(uint64_t v) {   // 21 bits -> every third bit
+    v &= 0x1fffffULL;
+    v = (v | (v << 32)) & 0x1f00000000ffffULL;
+    v = (v | (v << 16)) & 0x1f0000ff0000ffULL;
+    v = (v | (v << 8)) & 0x100f00f00f00f00fULL;
+    v = (v | (v << 4)) & 0x10c30c30c30c30c3ULL;
+    v = (v | (v << 2)) & 0x1249249249249249ULL;
+    return v;
+}
+__device__ __forceinline__ uint64_t spread2(uint64_t v) {   // 31 bits -> every second bit
+    v &= 0x7fffffffULL;
+    v = (v | (v << 16)) & 0x0000ffff0000ffffULL;
+    v = (v | (v << 8)) & 0x00ff00ff00ff00ffULL;
+    v = (v | (v << 4)) & 0x0f0f0f0f0f0f0f0fULL;
+    v = (v | (v << 2)) & 0x3333333333333333ULL;
+    v = (v | (v << 1)) & 0x5555555555555555ULL;
+    return v;
+}
+
+// Morton key of every DoF from the position of its representative node.  One common
+// scale for all axes keeps the curve's cells cubic on elongated domains.
+__global__ void k_morton_keys(int N, int64_t nDofs, const int32_t *repNode, const double *nodes, double mn0,
+                              double mn1, double mn2, double invScale, uint64_t *keys, int32_t *ids) {
+    int64_t d = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (d >= nDofs) return;
+    const int32_t n = repNode[d];
+    uint64_t key;
+    if (n == 0x7f7f7f7f) {   // memset marker: no node maps to this DoF
+        key = ~0ULL;                 // DoF without node (should not happen): park at the end
+    } else if (N == 3) {
+        const double s = 2097151.0;  // 2^21 - 1
+        uint64_t x = (uint64_t)(fmin(fmax((nodes[3 * (int64_t)n + 0] - mn0) * invScale, 0.0), 1.0) * s);
+        uint64_t y = (uint64_t)(fmin(fmax((nodes[3 * (int64_t)n + 1] - mn1) * invScale, 0.0), 1.0) * s);
+        uint64_t z = (uint64_t)(fmin(fmax((nodes[3 * (int64_t)n + 2] - mn2) * invScale, 0.0), 1.0) * s);
+        key = spread3(x) | (spread3(y) << 1) | (spread3(z) << 2);
+    } else {
+        const double s = 2147483647.0;   // 2^31 - 1
+        uint64_t x = (uint64_t)(fmin(fmax((nodes[2 * (int64_t)n + 0] - mn0) * invScale, 0.0), 1.0) * s);
+        uint64_t y = (uint64_t)(fmin(fmax((nodes[2 * (int64_t)n + 1] - mn1) * invScale, 0.0), 1.0) * s);
+        key = spread2(x) | (spread2(y) << 1);
+    }
+    keys[d] = key;
+    ids[d] = (int32_t)d;
+}
+
+__global__ void k_iota(int64_t n, int32_t *a) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) a[i] = (int32_t)i;
+}
+
+__global__ void k_invert_perm(int64_t n, const int32_t *int2ext, int32_t *ext2int) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) ext2int[int2ext[i]] = (int32_t)i;
+}
+
+__global__ void k_node_dof(int64_t nNodes, const int32_t *dofOfNode, const int32_t *ext2int, int32_t *nodeDof) {
+    int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (n < nNodes) nodeDof[n] = ext2int[dofOfNode[n]];
+}
+
+__global__ void k_elem_dof(int64_t n, const int32_t *elemNodes, const int32_t *nodeDof, int32_t *elemDof) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) elemDof[i] = nodeDof[elemNodes[i]];
+}
+
+// K1 elem_geom: one thread per element (EmbeddedElement.hh:170-190, 211-231).
+template <int N>
+__global__ void k_elem_geom(int64_t nElems, int npe, const int32_t *elemNodes, const double *nodes, double *geom,
+                            int *negCount) {
+    int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= nElems) return;
+    double p[N + 1][N];
+#pragma unroll
+    for (int v = 0; v <= N; ++v) {
+        const int64_t n = elemNodes[e * npe + v];
+#pragma unroll
+        for (int r = 0; r < N; ++r) p[v][r] = nodes[n * N + r];
+    }
+    ElemGeom<N> g;
+    embed(p, g);
+    constexpr int GS = 1 + N * (N + 1);
+    double *o = geom + e * GS;
+    o[0] = g.vol;
+#pragma unroll
+    for (int r = 0; r < N; ++r)
+#pragma unroll
+        for (int a = 0; a <= N; ++a) o[1 + r * (N + 1) + a] = g.G[r][a];
+    if (!(g.vol >= 0.0)) atomicAdd(negCount, 1);
+}
+
+// (row,col) block keys of every element: npe*npe per element.
+__global__ void k_pair_keys(int64_t nElems, int npe, const int32_t *elemDof, uint64_t *keys) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t per = (int64_t)npe * npe;
+    if (t >= nElems * per) return;
+    const int64_t e = t / per;
+    const int ij = (int)(t - e * per);
+    const int i = ij / npe, j = ij - i * npe;
+    keys[t] = ((uint64_t)(uint32_t)elemDof[e * npe + i] << 32) | (uint32_t)elemDof[e * npe + j];
+}
+
+__global__ void k_low32(int64_t n, const uint64_t *keys, int32_t *out) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (int32_t)(keys[i] & 0xffffffffULL);
+}
+
+// rowptr[r] = first index k with (keys[k] >> 32) >= r   (keys sorted)
+__global__ void k_rowptr_from_keys64(int64_t nRows, int64_t nKeys, const uint64_t *keys, int64_t *rowptr) {
+    int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r > nRows) return;
+    int64_t lo = 0, hi = nKeys;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if ((int64_t)(keys[mid] >> 32) < r) lo = mid + 1; else hi = mid;
+    }
+    rowptr[r] = lo;
+}
+
+__global__ void k_rowptr_from_keys32(int64_t nRows, int64_t nKeys, const uint32_t *keys, int64_t *rowptr) {
+    int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r > nRows) return;
+    int64_t lo = 0, hi = nKeys;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if ((int64_t)keys[mid] < r) lo = mid + 1; else hi = mid;
+    }
+    rowptr[r] = lo;
+}
+
+static int bits_for(int64_t n) {
+    int b = 1;
+    while ((int64_t(1) << b) < n) ++b;
+    return b;
+}
+
+// ---------------------------------------------------------------------------
+void setup_mesh(mfem_b200_ctx *c, int dim, int degree, int64_t nNodes, const double *nodes, int64_t nElems,
+                const int32_t *elemNodes, const int64_t *dofForNode, int64_t nDofs) {
+    MFEM_REQUIRE(dim == 2 || dim == 3, MFEM_B200_ERR_INVALID, "dim must be 2 or 3");
+    MFEM_REQUIRE(degree == 1 || degree == 2, MFEM_B200_ERR_INVALID, "degree must be 1 or 2");
+    MFEM_REQUIRE(nNodes > 0 && nElems > 0 && nodes && elemNodes, MFEM_B200_ERR_INVALID, "empty mesh");
+    MFEM_REQUIRE(nNodes < INT32_MAX && nElems * 16 < INT32_MAX, MFEM_B200_ERR_INVALID,
+                 "mesh too large for 32-bit node/element ids");
+    cudaStream_t s = c->stream;
+    c->N = dim; c->deg = degree; c->npe = nodes_per_elem(dim, degree);
+    c->nNodes = nNodes; c->nElems = nElems;
+    c->periodic = dofForNode != nullptr;
+    c->nDofs = c->periodic ? nDofs : nNodes;
+    MFEM_REQUIRE(c->nDofs > 0 && c->nDofs <= nNodes, MFEM_B200_ERR_INVALID, "bad n_dofs");
+    c->patternValid = c->valuesValid = c->geomValid = c->precondValid = c->workValid = false;
+    c->fixedHost.assign((size_t)c->nDofs * dim, 0);
+    c->nFixed = 0;
+
+    const int npe = c->npe;
+    c->nodes.alloc((size_t)nNodes * dim);
+    c->elemNodes.alloc((size_t)nElems * npe);
+    MFEM_CUDA(cudaMemcpyAsync(c->nodes, nodes, c->nodes.bytes(), cudaMemcpyHostToDevice, s));
+    MFEM_CUDA(cudaMemcpyAsync(c->elemNodes, elemNodes, c->elemNodes.bytes(), cudaMemcpyHostToDevice, s));
+
+    DevBuf<int> flag(1);
+    MFEM_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), s));
+    k_check_elem_nodes<<<grid_for(nElems * npe, 256), 256, 0, s>>>(nElems * npe, c->elemNodes, nNodes, flag);
+    c->launches++;
+    int bad = 0;
+    MFEM_CUDA(cudaMemcpyAsync(&bad, flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+    MFEM_CUDA(cudaStreamSynchronize(s));
+    MFEM_REQUIRE(bad == 0, MFEM_B200_ERR_INVALID, "Bad vertex index encountered.");
+
+    // DoF of every node in the caller's numbering
+    DevBuf<int32_t> dofOfNode((size_t)nNodes);
+    if (c->periodic) {
+        std::vector<int32_t> tmp((size_t)nNodes);
+        for (int64_t i = 0; i < nNodes; ++i) {
+            MFEM_REQUIRE(dofForNode[i] >= 0 && dofForNode[i] < c->nDofs, MFEM_B200_ERR_INVALID,
+                         "dof_for_node out of range");
+            tmp[(size_t)i] = (int32_t)dofForNode[i];
+        }
+        MFEM_CUDA(cudaMemcpyAsync(dofOfNode, tmp.data(), dofOfNode.bytes(), cudaMemcpyHostToDevice, s));
+        MFEM_CUDA(cudaStreamSynchronize(s));
+    } else {
+        k_iota<<<grid_for(nNodes, 256), 256, 0, s>>>(nNodes, dofOfNode);
+        c->launches++;
+    }
+
+    c->int2ext.alloc((size_t)c->nDofs);
+    c->ext2int.alloc((size_t)c->nDofs);
+    if (c->opt_reorder) {
+        // bounding box on the host (one pass over data the caller already holds)
+        double mn[3] = {std::numeric_limits<double>::max(), std::numeric_limits<double>::max(),
+                        std::numeric_limits<double>::max()};
+        double mx[3] = {-mn[0], -mn[0], -mn[0]};
+        for (int64_t i = 0; i < nNodes; ++i)
+            for (int r = 0; r < dim; ++r) {
+                const double v = nodes[i * dim + r];
+                mn[r] = std::min(mn[r], v); mx[r] = std::max(mx[r], v);
+            }
+        double ext = 0.0;
+        for (int r = 0; r < dim; ++r) ext = std::max(ext, mx[r] - mn[r]);
+        if (dim == 2) { mn[2] = 0.0; }
+        const double invScale = ext > 0 ? 1.0 / ext : 0.0;
+
+        DevBuf<int32_t> repNode((size_t)c->nDofs);
+        MFEM_CUDA(cudaMemsetAsync(repNode, 0x7f, repNode.bytes(), s));   // 0x7f7f7f7f > any id
+        k_rep_node<<<grid_for(nNodes, 256), 256, 0, s>>>(nNodes, dofOfNode, repNode);
+        DevBuf<uint64_t> keys((size_t)c->nDofs), keysOut((size_t)c->nDofs);
+        DevBuf<int32_t> ids((size_t)c->nDofs);
+        k_morton_keys<<<grid_for(c->nDofs, 256), 256, 0, s>>>(dim, c->nDofs, repNode, c->nodes, mn[0], mn[1], mn[2],
+                                                              invScale, keys, ids);
+        c->launches += 2;
+        size_t tmpBytes = 0;
+        MFEM_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmpBytes, keys.p, keysOut.p, ids.p, c->int2ext.p,
+                                                  c->nDofs, 0, 64, s));
+        DevBuf<uint8_t> tmp(tmpBytes);
+        MFEM_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmpBytes, keys.p, keysOut.p, ids.p, c->int2ext.p, c->nDofs,
+                                                  0, 64, s));
+        MFEM_CUDA(cudaStreamSynchronize(s));
+    } else {
+        k_iota<<<grid_for(c->nDofs, 256), 256, 0, s>>>(c->nDofs, c->int2ext);
+        c->launches++;
+    }
+    k_invert_perm<<<grid_for(c->nDofs, 256), 256, 0, s>>>(c->nDofs, c->int2ext, c->ext2int);
+    c->nodeDof.alloc((size_t)nNodes);
+    k_node_dof<<<grid_for(nNodes, 256), 256, 0, s>>>(nNodes, dofOfNode, c->ext2int, c->nodeDof);
+    c->elemDof.alloc((size_t)nElems * npe);
+    k_elem_dof<<<grid_for(nElems * npe, 256), 256, 0, s>>>(nElems * npe, c->elemNodes, c->nodeDof, c->elemDof);
+    c->launches += 3;
+    MFEM_CUDA(cudaStreamSynchronize(s));
+
+    compute_geometry(c);
+}
+
+void compute_geometry(mfem_b200_ctx *c) {
+    cudaStream_t s = c->stream;
+    const int GS = 1 + c->N * (c->N + 1);
+    if (c->geom.n != (size_t)c->nElems * GS) c->geom.alloc((size_t)c->nElems * GS);
+    DevBuf<int> neg(1);
+    MFEM_CUDA(cudaMemsetAsync(neg, 0, sizeof(int), s));
+    if (c->N == 3)
+        k_elem_geom<3><<<grid_for(c->nElems, 256), 256, 0, s>>>(c->nElems, c->npe, c->elemNodes, c->nodes, c->geom, neg);
+    else
+        k_elem_geom<2><<<grid_for(c->nElems, 256), 256, 0, s>>>(c->nElems, c->npe, c->elemNodes, c->nodes, c->geom, neg);
+    c->launches++;
+    int nneg = 0;
+    MFEM_CUDA(cudaMemcpyAsync(&nneg, neg, sizeof(int), cudaMemcpyDeviceToHost, s));
+    MFEM_CUDA(cudaStreamSynchronize(s));
+    MFEM_CUDA(cudaGetLastError());
+    c->geomValid = true;
+    c->valuesValid = false;
+    if (nneg > 0)
+        throw CudaError(MFEM_B200_ERR_NEG_VOLUME,
+                        "Found " + std::to_string(nneg) +
+                            " elements with negative volume...\nMesh has negatively oriented elements.\n"
+                            "Correct with: mesh_convert --reorientNegativeElements.");
+}
+
+// Symbolic phase: sorted unique (row, col) block keys -> rowptr / colidx, and the
+// DoF -> (element, local node) incidence lists the owner-gather assembly walks.
+void build_pattern(mfem_b200_ctx *c) {
+    if (c->patternValid) return;
+    ScopedTimer timer(c, "Pattern");
+    cudaStream_t s = c->stream;
+    const int npe = c->npe;
+    const int64_t nb = c->nDofs;
+    const int64_t nPairs = c->nElems * npe * npe;
+    MFEM_REQUIRE(nPairs < INT32_MAX, MFEM_B200_ERR_INVALID,
+                 "pattern build: more than 2^31 element block pairs on one device; partition the mesh");
+    const int dofBits = bits_for(nb + 1);
+
+    {   // ---- block pattern
+        DevBuf<uint64_t> keys((size_t)nPairs), keysSorted((size_t)nPairs);
+        k_pair_keys<<<grid_for(nPairs, 256), 256, 0, s>>>(c->nElems, npe, c->elemDof, keys);
+        c->launches++;
+        size_t tmpBytes = 0;
+        MFEM_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmpBytes, keys.p, keysSorted.p, nPairs, 0, 32 + dofBits, s));
+        {
+            DevBuf<uint8_t> tmp(tmpBytes);
+            MFEM_CUDA(cub::DeviceRadixSort::SortKeys(tmp.p, tmpBytes, keys.p, keysSorted.p, nPairs, 0, 32 + dofBits, s));
+            MFEM_CUDA(cudaStreamSynchronize(s));
+        }
+        // unique into `keys` (reused as output)
+        DevBuf<int> nSel(1);
+        tmpBytes = 0;
+        MFEM_CUDA(cub::DeviceSelect::Unique(nullptr, tmpBytes, keysSorted.p, keys.p, nSel.p, (int)nPairs, s));
+        {
+            DevBuf<uint8_t> tmp(tmpBytes);
+            MFEM_CUDA(cub::DeviceSelect::Unique(tmp.p, tmpBytes, keysSorted.p, keys.p, nSel.p, (int)nPairs, s));
+            int n = 0;
+            MFEM_CUDA(cudaMemcpyAsync(&n, nSel, sizeof(int), cudaMemcpyDeviceToHost, s));
+            MFEM_CUDA(cudaStreamSynchronize(s));
+            c->nnzb = n;
+        }
+        keysSorted.free();
+        c->colidx.alloc((size_t)c->nnzb);
+        c->rowptr.alloc((size_t)nb + 1);
+        k_low32<<<grid_for(c->nnzb, 256), 256, 0, s>>>(c->nnzb, keys, c->colidx);
+        k_rowptr_from_keys64<<<grid_for(nb + 1, 256), 256, 0, s>>>(nb, c->nnzb, keys, c->rowptr);
+        c->launches += 2;
+        MFEM_CUDA(cudaStreamSynchronize(s));
+    }
+    {   // ---- incidence lists (stable sort keeps (element, local node) order inside a row)
+        const int64_t nInc = c->nElems * npe;
+        DevBuf<uint32_t> keysOut((size_t)nInc);
+        DevBuf<int32_t> ids((size_t)nInc);
+        c->incList.alloc((size_t)nInc);
+        k_iota<<<grid_for(nInc, 256), 256, 0, s>>>(nInc, ids);
+        c->launches++;
+        size_t tmpBytes = 0;
+        const uint32_t *kin = reinterpret_cast<const uint32_t *>(c->elemDof.p);
+        MFEM_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmpBytes, kin, keysOut.p, ids.p, c->incList.p, nInc, 0,
+                                                  dofBits, s));
+        DevBuf<uint8_t> tmp(tmpBytes);
+        MFEM_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmpBytes, kin, keysOut.p, ids.p, c->incList.p, nInc, 0,
+                                                  dofBits, s));
+        c->incPtr.alloc((size_t)nb + 1);
+        k_rowptr_from_keys32<<<grid_for(nb + 1, 256), 256, 0, s>>>(nb, nInc, keysOut, c->incPtr);
+        c->launches++;
+        c->totalInc = nInc;
+        MFEM_CUDA(cudaStreamSynchronize(s));
+    }
+    MFEM_CUDA(cudaGetLastError());
+    c->vals.alloc((size_t)c->nnzb * c->N * c->N);
+    c->patternValid = true;
+    c->valuesValid = false;
+    c->precondValid = false;
+}
+
+}  // namespace mfem
+
+namespace mfem {
+
+// Greedy element colouring for assembly mode 1 (elements of one colour share no DoF).
+// Host-side first-fit over the element list; the colour classes are uploaded once and cached
+// with the pattern.
+void build_coloring(mfem_b200_ctx *c) {
+    if (c->nColors > 0 && c->colorElems.n == (size_t)c->nElems) return;
+    ScopedTimer timer(c, "Coloring");
+    const int npe = c->npe;
+    std::vector<int32_t> ed((size_t)c->nElems * npe);
+    MFEM_CUDA(cudaMemcpy(ed.data(), c->elemDof, ed.size() * 4, cudaMemcpyDeviceToHost));
+    constexpr int W = 4;                                   // up to 256 colours
+    std::vector<uint64_t> used((size_t)c->nDofs * W, 0);
+    std::vector<int32_t> color((size_t)c->nElems);
+    int nColors = 0;
+    for (int64_t e = 0; e < c->nElems; ++e) {
+        uint64_t forb[W] = {0, 0, 0, 0};
+        for (int j = 0; j < npe; ++j)
+            for (int w = 0; w < W; ++w) forb[w] |= used[(size_t)ed[(size_t)e * npe + j] * W + w];
+        int col = -1;
+        for (int w = 0; w < W && col < 0; ++w)
+            if (~forb[w]) col = w * 64 + __builtin_ctzll(~forb[w]);
+        MFEM_REQUIRE(col >= 0, MFEM_B200_ERR_INVALID, "colouring needs more than 256 colours");
+        color[(size_t)e] = col;
+        nColors = std::max(nColors, col + 1);
+        for (int j = 0; j < npe; ++j) used[(size_t)ed[(size_t)e * npe + j] * W + col / 64] |= (1ULL << (col % 64));
+    }
+    c->colorPtr.assign((size_t)nColors + 1, 0);
+    for (int64_t e = 0; e < c->nElems; ++e) c->colorPtr[(size_t)color[(size_t)e] + 1]++;
+    for (int k = 0; k < nColors; ++k) c->colorPtr[(size_t)k + 1] += c->colorPtr[(size_t)k];
+    std::vector<int32_t> sorted((size_t)c->nElems);
+    std::vector<int64_t> pos(c->colorPtr.begin(), c->colorPtr.end() - 1);
+    for (int64_t e = 0; e < c->nElems; ++e) sorted[(size_t)pos[(size_t)color[(size_t)e]]++] = (int32_t)e;
+    c->colorElems.alloc((size_t)c->nElems);
+    MFEM_CUDA(cudaMemcpy(c->colorElems, sorted.data(), sorted.size() * 4, cudaMemcpyHostToDevice));
+    c->nColors = nColors;
+}
+
+}  // namespace mfem

@@ -1,0 +1,535 @@
+// K3-K6: block-CSR SpMV, block-Jacobi preconditioner, fused PCG vector kernels.
+//
+// Replaces SPSDSystem::fixVariables / solve (SparseMatrices.hh:2389-2500, 2516-2606) and the
+// CholmodFactorizer behind it (SparseMatrices.hh:1984-2296): the reduced SPD system
+//     K_ff u_f = f_f - K_fc u_c ,  u_c = fixed values
+// is solved by preconditioned conjugate gradients on FULL-LENGTH vectors whose fixed
+// components are held at zero (CG on the free subspace); K itself is never modified, the
+// mask is applied where the SpMV writes its result.  The preconditioner is block-Jacobi on the
+// dim x dim diagonal blocks taken after masking.
+//
+// All reductions are two-stage with a fixed order (per-CTA partials, then the last CTA to
+// finish sums them in index order): results are bit-reproducible run to run.
+#include "core.cuh"
+
+namespace mfem {
+
+constexpr int kSpmvThreads = 256;
+constexpr int kVecThreads = 256;
+constexpr int kMaxPartials = 4096;      // upper bound on CTAs of any reducing kernel
+
+// device scalar slots (PcgWork::scal)
+enum {
+    S_RZ = 0,      // r.z of the current iterate
+    S_RZ_NEW = 1,  // r.z after the update
+    S_PAP = 2,     // p.Ap
+    S_RR = 3,      // r.r
+    S_BB = 4,      // b.b
+    S_TOL2 = 5,    // rtol^2
+    S_COUNT = 8
+};
+// status slots (PcgWork::status)
+enum { ST_ITERS = 0, ST_STATE = 1 };   // state: 0 running, 1 converged, 2 breakdown (p'Ap<=0), 3 nan
+
+// ---------------------------------------------------------------------------
+// Deterministic block reduction + "last block finalises" pattern.
+// ---------------------------------------------------------------------------
+template <int NV>
+__device__ __forceinline__ void block_reduce_store(double (&v)[NV], double *partials /* [NV][gridDim.x] */) {
+    __shared__ double red[NV][kVecThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        double x = v[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (lane == 0) red[k][warp] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        double s = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[threadIdx.x][w];
+        partials[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = s;
+    }
+}
+
+// returns true in exactly one block (the last to arrive); that block then sees all partials
+__device__ __forceinline__ bool last_block(unsigned *ticket) {
+    __shared__ bool isLast;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(ticket, 1u);
+        isLast = (t == gridDim.x - 1);
+        if (isLast) *ticket = 0u;        // re-arm for the next launch
+    }
+    __syncthreads();
+    if (isLast) __threadfence();
+    return isLast;
+}
+
+// sum partials[k][0..n) in fixed order with one warp-shaped tree (whole block participates)
+__device__ __forceinline__ double final_sum(const double *partials, int n) {
+    __shared__ double red2[kVecThreads / 32];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s += partials[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red2[threadIdx.x >> 5] = s;
+    __syncthreads();
+    double tot = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red2[w];
+    return tot;
+}
+
+// ---------------------------------------------------------------------------
+// K3  bsr_spmv: y = mask(K x) [, dot = x.y]
+// One warp per block row.  The row's values are a contiguous run of NN*nblk doubles; lanes
+// stride over that run ELEMENT-wise (not block-wise), so every value load is a fully
+// coalesced 256 B warp access at any block size, and x is gathered through L1/L2.
+// ---------------------------------------------------------------------------
+template <int N, bool MASKED, bool DOT>
+__global__ void __launch_bounds__(kSpmvThreads)
+k_bsr_spmv(int64_t nb, const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
+           const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y,
+           const uint8_t *__restrict__ fixedMask, double *partials, unsigned *ticket, double *scal,
+           const int *status) {
+    constexpr int NN = N * N;
+    if (status && status[ST_STATE] != 0) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t warpGlobal = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nWarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    double dot = 0.0;
+    for (int64_t row = warpGlobal; row < nb; row += nWarps) {
+        const int64_t b0 = rowptr[row], b1 = rowptr[row + 1];
+        const double *v = vals + b0 * NN;
+        const int32_t *ci = colidx + b0;
+        const int nE = (int)(b1 - b0) * NN;
+        double acc[N];
+#pragma unroll
+        for (int r = 0; r < N; ++r) acc[r] = 0.0;
+#pragma unroll 4
+        for (int f = lane; f < nE; f += 32) {
+            const int blk = f / NN;
+            const int rc = f - blk * NN;
+            const int r = rc / N, cc = rc - r * N;
+            const double a = __ldcs(v + f);                         // streamed once
+            const double xv = __ldg(x + (int64_t)__ldg(ci + blk) * N + cc);
+            const double p = a * xv;
+#pragma unroll
+            for (int k = 0; k < N; ++k) acc[k] += (r == k) ? p : 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < N; ++k)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+        if (lane < N) {
+            double out = acc[0];
+#pragma unroll
+            for (int k = 1; k < N; ++k) out = (lane == k) ? acc[k] : out;
+            if (MASKED && fixedMask[row * N + lane]) out = 0.0;
+            y[row * N + lane] = out;
+            if (DOT) dot += out * x[row * N + lane];
+        }
+    }
+    if (DOT) {
+        double v1[1] = {dot};
+        block_reduce_store<1>(v1, partials);
+        if (last_block(ticket)) {
+            const double s = final_sum(partials, gridDim.x);
+            if (threadIdx.x == 0) scal[S_PAP] = s;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K5  block-Jacobi: invert the masked diagonal blocks.
+// ---------------------------------------------------------------------------
+template <int N>
+__global__ void k_jacobi_setup(int64_t nb, const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
+                               const double *__restrict__ vals, const uint8_t *__restrict__ fixedMask,
+                               double *__restrict__ Minv, int *bad) {
+    constexpr int NN = N * N;
+    const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (row >= nb) return;
+    int64_t lo = rowptr[row], hi = rowptr[row + 1];
+    const int64_t end = hi;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (colidx[mid] < row) lo = mid + 1; else hi = mid;
+    }
+    double a[N][N];
+    const bool have = (lo < end) && (colidx[lo] == row);
+#pragma unroll
+    for (int r = 0; r < N; ++r)
+#pragma unroll
+        for (int c = 0; c < N; ++c) a[r][c] = have ? vals[lo * NN + r * N + c] : ((r == c) ? 1.0 : 0.0);
+    bool fx[N];
+#pragma unroll
+    for (int r = 0; r < N; ++r) fx[r] = fixedMask[row * N + r] != 0;
+#pragma unroll
+    for (int r = 0; r < N; ++r)
+#pragma unroll
+        for (int c = 0; c < N; ++c)
+            if (fx[r] || fx[c]) a[r][c] = (r == c) ? 1.0 : 0.0;
+    double inv[N][N];
+    double det;
+    if (N == 3) {
+        const double c00 = a[1][1] * a[2][2] - a[1][2] * a[2][1];
+        const double c01 = a[1][2] * a[2][0] - a[1][0] * a[2][2];
+        const double c02 = a[1][0] * a[2][1] - a[1][1] * a[2][0];
+        det = a[0][0] * c00 + a[0][1] * c01 + a[0][2] * c02;
+        const double id = 1.0 / det;
+        inv[0][0] = c00 * id;
+        inv[0][1] = (a[0][2] * a[2][1] - a[0][1] * a[2][2]) * id;
+        inv[0][2] = (a[0][1] * a[1][2] - a[0][2] * a[1][1]) * id;
+        inv[1][0] = c01 * id;
+        inv[1][1] = (a[0][0] * a[2][2] - a[0][2] * a[2][0]) * id;
+        inv[1][2] = (a[0][2] * a[1][0] - a[0][0] * a[1][2]) * id;
+        inv[2][0] = c02 * id;
+        inv[2][1] = (a[0][1] * a[2][0] - a[0][0] * a[2][1]) * id;
+        inv[2][2] = (a[0][0] * a[1][1] - a[0][1] * a[1][0]) * id;
+    } else {
+        det = a[0][0] * a[1][1] - a[0][1] * a[1][0];
+        const double id = 1.0 / det;
+        inv[0][0] = a[1][1] * id; inv[0][1] = -a[0][1] * id;
+        inv[1][0] = -a[1][0] * id; inv[1][1] = a[0][0] * id;
+    }
+    if (!(det > 0.0) || !isfinite(det)) atomicAdd(bad, 1);
+#pragma unroll
+    for (int r = 0; r < N; ++r)
+#pragma unroll
+        for (int c = 0; c < N; ++c) Minv[row * NN + r * N + c] = inv[r][c];
+}
+
+// ---------------------------------------------------------------------------
+// K4  fused vector kernels (one thread per DoF block, grid-stride)
+// ---------------------------------------------------------------------------
+// init: r = mask(b); z = Minv r; p = z; x = 0; rz = r.z, rr = r.r (= b.b of the reduced system)
+template <int N>
+__global__ void __launch_bounds__(kVecThreads)
+k_pcg_init(int64_t nb, const double *__restrict__ b, const uint8_t *__restrict__ fixedMask,
+           const double *__restrict__ Minv, double *__restrict__ x, double *__restrict__ r, double *__restrict__ z,
+           double *__restrict__ p, double *partials, unsigned *ticket, double *scal, int *status, double tol2) {
+    constexpr int NN = N * N;
+    double acc[2] = {0.0, 0.0};
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nb; i += (int64_t)gridDim.x * blockDim.x) {
+        double rv[N], zv[N];
+#pragma unroll
+        for (int k = 0; k < N; ++k) rv[k] = fixedMask[i * N + k] ? 0.0 : b[i * N + k];
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            double s = 0.0;
+#pragma unroll
+            for (int m = 0; m < N; ++m) s += Minv[i * NN + k * N + m] * rv[m];
+            zv[k] = s;
+        }
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            x[i * N + k] = 0.0; r[i * N + k] = rv[k]; z[i * N + k] = zv[k]; p[i * N + k] = zv[k];
+            acc[0] += rv[k] * zv[k];
+            acc[1] += rv[k] * rv[k];
+        }
+    }
+    block_reduce_store<2>(acc, partials);
+    if (last_block(ticket)) {
+        const double rz = final_sum(partials, gridDim.x);
+        const double rr = final_sum(partials + gridDim.x, gridDim.x);
+        if (threadIdx.x == 0) {
+            scal[S_RZ] = rz; scal[S_RR] = rr; scal[S_BB] = rr; scal[S_TOL2] = tol2;
+            status[ST_ITERS] = 0;
+            status[ST_STATE] = (rr == 0.0) ? 1 : ((rr != rr) ? 3 : 0);
+        }
+    }
+}
+
+// update: alpha = rz/pAp; x += alpha p; r -= alpha Ap; z = Minv r; rz_new = r.z; rr = r.r
+template <int N>
+__global__ void __launch_bounds__(kVecThreads)
+k_pcg_update(int64_t nb, const double *__restrict__ Minv, const double *__restrict__ p, const double *__restrict__ Ap,
+             double *__restrict__ x, double *__restrict__ r, double *__restrict__ z, double *partials,
+             unsigned *ticket, double *scal, int *status) {
+    constexpr int NN = N * N;
+    if (status[ST_STATE] != 0) return;
+    const double pAp = scal[S_PAP];
+    const double alpha = scal[S_RZ] / pAp;
+    double acc[2] = {0.0, 0.0};
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nb; i += (int64_t)gridDim.x * blockDim.x) {
+        double rv[N], zv[N];
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            x[i * N + k] += alpha * p[i * N + k];
+            rv[k] = r[i * N + k] - alpha * Ap[i * N + k];
+        }
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            double s = 0.0;
+#pragma unroll
+            for (int m = 0; m < N; ++m) s += Minv[i * NN + k * N + m] * rv[m];
+            zv[k] = s;
+        }
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            r[i * N + k] = rv[k]; z[i * N + k] = zv[k];
+            acc[0] += rv[k] * zv[k];
+            acc[1] += rv[k] * rv[k];
+        }
+    }
+    block_reduce_store<2>(acc, partials);
+    if (last_block(ticket)) {
+        const double rz = final_sum(partials, gridDim.x);
+        const double rr = final_sum(partials + gridDim.x, gridDim.x);
+        if (threadIdx.x == 0) {
+            scal[S_RZ_NEW] = rz; scal[S_RR] = rr;
+            status[ST_ITERS] += 1;
+            int st = 0;
+            if (!(pAp > 0.0)) st = 2;
+            if (rr != rr || rz != rz || pAp != pAp) st = 3;
+            if (st == 0 && rr <= scal[S_TOL2] * scal[S_BB]) st = 1;
+            status[ST_STATE] = st;     // written last; kernels of later iterations read it first
+        }
+    }
+}
+
+// direction: beta = rz_new/rz; p = z + beta p; rz <- rz_new
+template <int N>
+__global__ void __launch_bounds__(kVecThreads)
+k_pcg_direction(int64_t n, const double *__restrict__ z, double *__restrict__ p, double *scal, const int *status,
+                unsigned *ticket) {
+    if (status[ST_STATE] != 0) return;
+    const double beta = scal[S_RZ_NEW] / scal[S_RZ];
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        p[i] = z[i] + beta * p[i];
+    // the last CTA rotates the scalar once every CTA has read it
+    if (last_block(ticket)) {
+        if (threadIdx.x == 0) scal[S_RZ] = scal[S_RZ_NEW];
+    }
+}
+
+// b = f - K ufix on free rows (ufix carries the fixed values, zero elsewhere); u = x + ufix
+__global__ void k_axpby(int64_t n, double a, const double *__restrict__ x, double bcoef, const double *__restrict__ y,
+                        double *__restrict__ out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = a * x[i] + bcoef * y[i];
+}
+
+// ---------------------------------------------------------------------------
+static int sm_count(mfem_b200_ctx *c) {
+    static int n = 0;
+    if (!n) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, c->device);
+    return n > 0 ? n : 148;
+}
+
+static int spmv_grid(mfem_b200_ctx *c) {
+    // persistent-style launch: 8 CTAs of 256 threads per SM (full occupancy), rows grid-strided by warp
+    const int64_t warpsNeeded = c->nDofs;
+    const int64_t ctas = (warpsNeeded + (kSpmvThreads / 32) - 1) / (kSpmvThreads / 32);
+    return (int)std::min<int64_t>(ctas, (int64_t)sm_count(c) * 8);
+}
+
+static int vec_grid(mfem_b200_ctx *c, int64_t n) {
+    const int64_t ctas = (n + kVecThreads - 1) / kVecThreads;
+    return (int)std::max<int64_t>(1, std::min<int64_t>(ctas, std::min<int64_t>(kMaxPartials, (int64_t)sm_count(c) * 8)));
+}
+
+void ensure_work(mfem_b200_ctx *c) {
+    if (c->workValid) return;
+    const size_t n = (size_t)c->nvar();
+    PcgWork &w = c->work;
+    w.x.alloc(n); w.r.alloc(n); w.z.alloc(n); w.p.alloc(n); w.Ap.alloc(n); w.b.alloc(n); w.ufix.alloc(n);
+    w.partials.alloc(4 * (size_t)kMaxPartials);
+    w.scal.alloc(S_COUNT);
+    w.ticket.alloc(4);
+    w.status.alloc(4);
+    MFEM_CUDA(cudaMemsetAsync(w.ticket, 0, w.ticket.bytes(), c->stream));
+    MFEM_CUDA(cudaMemsetAsync(w.status, 0, w.status.bytes(), c->stream));
+    MFEM_CUDA(cudaMemsetAsync(w.scal, 0, w.scal.bytes(), c->stream));
+    if (c->fixedMask.n != n) {
+        c->fixedMask.alloc(n);
+        c->fixedVals.alloc(n);
+        MFEM_CUDA(cudaMemsetAsync(c->fixedMask, 0, c->fixedMask.bytes(), c->stream));
+        MFEM_CUDA(cudaMemsetAsync(c->fixedVals, 0, c->fixedVals.bytes(), c->stream));
+    }
+    c->workValid = true;
+}
+
+template <int N>
+static void launch_spmv(mfem_b200_ctx *c, const double *x, double *y, bool masked, bool dot) {
+    PcgWork &w = c->work;
+    const int grid = spmv_grid(c);
+    if (masked && dot)
+        k_bsr_spmv<N, true, true><<<grid, kSpmvThreads, 0, c->stream>>>(c->nDofs, c->rowptr, c->colidx, c->vals, x, y,
+                                                                         c->fixedMask, w.partials, w.ticket, w.scal,
+                                                                         w.status);
+    else if (masked)
+        k_bsr_spmv<N, true, false><<<grid, kSpmvThreads, 0, c->stream>>>(c->nDofs, c->rowptr, c->colidx, c->vals, x, y,
+                                                                          c->fixedMask, nullptr, nullptr, nullptr,
+                                                                          nullptr);
+    else
+        k_bsr_spmv<N, false, false><<<grid, kSpmvThreads, 0, c->stream>>>(c->nDofs, c->rowptr, c->colidx, c->vals, x,
+                                                                           y, nullptr, nullptr, nullptr, nullptr,
+                                                                           nullptr);
+    c->launches++;
+}
+
+void spmv_plain(mfem_b200_ctx *c, const double *x_int, double *y_int) {
+    MFEM_REQUIRE(c->valuesValid, MFEM_B200_ERR_INVALID, "spmv: matrix not assembled");
+    if (c->N == 3) launch_spmv<3>(c, x_int, y_int, false, false);
+    else launch_spmv<2>(c, x_int, y_int, false, false);
+    MFEM_CUDA(cudaGetLastError());
+}
+
+void build_preconditioner(mfem_b200_ctx *c) {
+    if (c->precondValid) return;
+    MFEM_REQUIRE(c->valuesValid, MFEM_B200_ERR_INVALID, "preconditioner: matrix not assembled");
+    ensure_work(c);
+    ScopedTimer timer(c, "Fix Variables");
+    const size_t n = (size_t)c->nDofs * c->N * c->N;
+    if (c->Minv.n != n) c->Minv.alloc(n);
+    DevBuf<int> bad(1);
+    MFEM_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), c->stream));
+    if (c->N == 3)
+        k_jacobi_setup<3><<<grid_for(c->nDofs, 256), 256, 0, c->stream>>>(c->nDofs, c->rowptr, c->colidx, c->vals,
+                                                                          c->fixedMask, c->Minv, bad);
+    else
+        k_jacobi_setup<2><<<grid_for(c->nDofs, 256), 256, 0, c->stream>>>(c->nDofs, c->rowptr, c->colidx, c->vals,
+                                                                          c->fixedMask, c->Minv, bad);
+    c->launches++;
+    int nbad = 0;
+    MFEM_CUDA(cudaMemcpyAsync(&nbad, bad, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    MFEM_CUDA(cudaStreamSynchronize(c->stream));
+    MFEM_CUDA(cudaGetLastError());
+    MFEM_REQUIRE(nbad == 0, MFEM_B200_ERR_NOT_SPD,
+                 "block-Jacobi: " + std::to_string(nbad) + " diagonal blocks are not positive definite");
+    c->precondValid = true;
+}
+
+template <int N>
+static void enqueue_iteration(mfem_b200_ctx *c) {
+    PcgWork &w = c->work;
+    const int64_t nb = c->nDofs, n = c->nvar();
+    const int vgrid = vec_grid(c, nb);
+    launch_spmv<N>(c, w.p, w.Ap, true, true);
+    k_pcg_update<N><<<vgrid, kVecThreads, 0, c->stream>>>(nb, c->Minv, w.p, w.Ap, w.x, w.r, w.z, w.partials,
+                                                           w.ticket + 1, w.scal, w.status);
+    k_pcg_direction<N><<<vec_grid(c, n), kVecThreads, 0, c->stream>>>(n, w.z, w.p, w.scal, w.status, w.ticket + 2);
+    c->launches += 2;
+}
+
+template <int N>
+static void pcg_impl(mfem_b200_ctx *c, const double *f_int, double *u_int, double rtol, int maxIters,
+                     mfem_b200_solve_info *info) {
+    PcgWork &w = c->work;
+    cudaStream_t s = c->stream;
+    const int64_t nb = c->nDofs, n = c->nvar();
+    // b = f - K ufix  (masked rows are zeroed by the init kernel)
+    launch_spmv<N>(c, c->fixedVals, w.Ap, false, false);
+    k_axpby<<<vec_grid(c, n), kVecThreads, 0, s>>>(n, 1.0, f_int, -1.0, w.Ap, w.b);
+    k_pcg_init<N><<<vec_grid(c, nb), kVecThreads, 0, s>>>(nb, w.b, c->fixedMask, c->Minv, w.x, w.r, w.z, w.p, w.partials,
+                                                          w.ticket + 1, w.scal, w.status, rtol * rtol);
+    c->launches += 2;
+    MFEM_CUDA(cudaGetLastError());
+
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, s);
+
+    // The iteration is captured once into a CUDA graph of kBatch iterations; kernels turn
+    // into no-ops as soon as the device-side state leaves "running", so the host only polls
+    // the 2-int status between graph launches.
+    const int kBatch = 25;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    if (c->opt_graph) {
+        const int64_t launchesBefore = c->launches;
+        MFEM_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        for (int k = 0; k < kBatch; ++k) enqueue_iteration<N>(c);
+        MFEM_CUDA(cudaStreamEndCapture(s, &graph));
+        MFEM_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+        c->launches = launchesBefore;      // capture does not launch
+    }
+    int hst[2] = {0, 0};
+    int done = 0;
+    while (done < maxIters) {
+        if (exec) {
+            MFEM_CUDA(cudaGraphLaunch(exec, s));
+            c->launches += 3 * kBatch;
+        } else {
+            for (int k = 0; k < kBatch; ++k) enqueue_iteration<N>(c);
+        }
+        MFEM_CUDA(cudaMemcpyAsync(hst, w.status, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+        MFEM_CUDA(cudaStreamSynchronize(s));
+        done = hst[ST_ITERS];
+        if (hst[ST_STATE] != 0) break;
+    }
+    cudaEventRecord(e1, s);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (exec) cudaGraphExecDestroy(exec);
+    if (graph) cudaGraphDestroy(graph);
+    MFEM_CUDA(cudaGetLastError());
+    c->timers["Elasticity Solve"] += ms * 1e-3;
+
+    double hs[S_COUNT];
+    MFEM_CUDA(cudaMemcpyAsync(hs, w.scal, sizeof(hs), cudaMemcpyDeviceToHost, s));
+    // u = x + ufix
+    k_axpby<<<vec_grid(c, n), kVecThreads, 0, s>>>(n, 1.0, w.x, 1.0, c->fixedVals, u_int);
+    c->launches++;
+    MFEM_CUDA(cudaStreamSynchronize(s));
+    if (info) {
+        info->iterations = hst[ST_ITERS];
+        info->converged = hst[ST_STATE] == 1;
+        info->rel_residual = hs[S_BB] > 0 ? std::sqrt(hs[S_RR] / hs[S_BB]) : 0.0;
+        info->seconds = ms * 1e-3;
+        info->spmv_seconds = 0.0;
+    }
+    if (hst[ST_STATE] == 2)
+        throw CudaError(MFEM_B200_ERR_NOT_SPD, "PCG breakdown: p'Ap <= 0 (matrix is not positive definite)");
+    if (hst[ST_STATE] == 3) throw CudaError(MFEM_B200_ERR_NAN, "PCG: NaN encountered");
+    if (hst[ST_STATE] == 0)
+        throw CudaError(MFEM_B200_ERR_NO_CONVERGE, "PCG: no convergence in " + std::to_string(hst[ST_ITERS]) +
+                                                       " iterations (rel. residual " +
+                                                       std::to_string(info ? info->rel_residual : -1.0) + ")");
+}
+
+void pcg_solve(mfem_b200_ctx *c, const double *f_int, double *u_int, double rtol, int maxIters,
+               mfem_b200_solve_info *info) {
+    MFEM_REQUIRE(c->valuesValid, MFEM_B200_ERR_INVALID, "solve: matrix not assembled");
+    ensure_work(c);
+    build_preconditioner(c);
+    if (c->N == 3) pcg_impl<3>(c, f_int, u_int, rtol, maxIters, info);
+    else pcg_impl<2>(c, f_int, u_int, rtol, maxIters, info);
+}
+
+double time_spmv(mfem_b200_ctx *c, int iters) {
+    MFEM_REQUIRE(c->valuesValid, MFEM_B200_ERR_INVALID, "time_spmv: matrix not assembled");
+    ensure_work(c);
+    PcgWork &w = c->work;
+    cudaStream_t s = c->stream;
+    // a non-trivial, reproducible input vector
+    k_axpby<<<vec_grid(c, c->nvar()), kVecThreads, 0, s>>>(c->nvar(), 0.0, w.b, 0.0, w.b, w.p);
+    MFEM_CUDA(cudaMemsetAsync(w.p, 0x3f, w.p.bytes(), s));   // 0x3f3f.. ~ 4.8e-4, finite
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    auto run = [&]() {
+        if (c->N == 3) launch_spmv<3>(c, w.p, w.Ap, false, false);
+        else launch_spmv<2>(c, w.p, w.Ap, false, false);
+    };
+    for (int k = 0; k < 3; ++k) run();
+    cudaEventRecord(e0, s);
+    for (int k = 0; k < iters; ++k) run();
+    cudaEventRecord(e1, s);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    MFEM_CUDA(cudaGetLastError());
+    const double sec = ms * 1e-3 / iters;
+    c->timers["SpMV"] += ms * 1e-3;
+    return sec;
+}
+
+}  // namespace mfem
