@@ -53,8 +53,9 @@ def test_assembled_matrix_matches_oracle(mfem, N, deg, sizes, mat, reorder, mode
     assert K.shape == Kref.shape
     diff = (K - Kref)
     assert sp.linalg.norm(diff) <= 1e-13 * sp.linalg.norm(Kref)
-    # same sparsity pattern (block pattern of the oracle is a subset: exact zeros may be stored)
-    assert (abs(Kref) > 0).multiply(abs(K) == 0).nnz == 0
+    # every significant oracle entry is structurally present in the block pattern
+    big = abs(Kref) > 1e-9 * abs(Kref).max()
+    assert (big.astype(np.int8) - big.multiply(K != 0).astype(np.int8)).nnz == 0
 
 
 @pytest.mark.parametrize("N,deg,sizes", CASES)
