@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 linear-elasticity assemble-and-solve path.
+
+Metric (BASELINE.json): assembly + solve throughput in elements/s on the synthetic `grid -t`
+cantilever of the named size (default: config 5, 220x44x44 hexes -> 10,222,080 quadratic
+tets, 43.96M DoF, isotropic E=200 nu=0.35, examples/cantilever/cantilever.bc), with the PCG
+iteration rate and the SpMV roofline beside it.
+
+One "step" = one numeric assembly of K into the cached block-CSR pattern + one block-Jacobi
+PCG solve to rtol on ||r||/||b||.  `value` times steps with all inputs resident in HBM (CUDA
+events on the library's stream); `e2e` times the same work through the C ABI from HOST
+buffers on a fresh handle (mesh upload, symbolic phase, assembly, constraints, solve, result
+download all inside the timed region).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config cfg5|cfg3|cfg2|GRID:DEG:MAT]
+  python bench.py --impl reference ...     # the reference algorithm on the host cores (oracle port)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+import numpy as np  # noqa: E402
+
+METRIC = "assembly+solve throughput (elements/s), quadratic-tet elasticity cantilever"
+UNIT = "elements/s"
+RTOL = 1e-8
+CPU_SAMPLE_GRID = (40, 8, 8)
+
+
+def parse_config(s):
+    import workloads as wl
+    if s in wl.CONFIGS:
+        grid, deg, mat = wl.CONFIGS[s]
+        return s, tuple(grid), deg, mat
+    g, d, m = s.split(":")
+    return s, tuple(int(x) for x in g.split("x")), int(d), m
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device=0):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 8:
+                continue
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); power.append(float(r[3]))
+            except ValueError:
+                continue
+            for k, nme in enumerate(names):
+                if r[4 + k].lower().startswith("active"):
+                    reasons.add(nme)
+        # "under load": samples whose power draw is above the midpoint of the observed range
+        if sm:
+            thr = 0.5 * (min(power) + max(power))
+            loaded = [s for s, p in zip(sm, power) if p >= thr] or sm
+            return {"sm_mhz": statistics.median(loaded), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                    "samples": len(sm), "power_w_max": max(power)}
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": sorted(reasons)}
+
+
+def pinned_copy(a):
+    """Copy of `a` in page-locked host memory (torch is plumbing for the allocation only)."""
+    try:
+        import torch
+        t = torch.empty(a.shape, dtype=getattr(torch, str(a.dtype)), pin_memory=True)
+        out = t.numpy()
+        out[...] = a
+        out_ref = (out, t)            # keep the tensor alive
+        return out_ref
+    except Exception:
+        return (np.ascontiguousarray(a), None)
+
+
+# ---------------------------------------------------------------------------------------------
+def cpu_port_sample(deg, mat, rtol, threads=None):
+    """The reference algorithm on the host cores, on a bounded sample of the workload:
+    perElementStiffness loop nest + serial triplet scatter + sumRepeated (oracle/ref_cpu.cc,
+    following LinearElasticity.hh:165-232, 1408-1466 and SparseMatrices.hh:280-374), then a
+    block-Jacobi PCG on the same cores standing in for CHOLMOD (not buildable here)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_cpu
+    import workloads as wl
+    m = wl.grid_femmesh(CPU_SAMPLE_GRID, deg)
+    D = wl.material(mat)
+    fixed, vals, f = wl.cantilever_inputs(m)
+    threads = threads or os.cpu_count() or 1
+    t0 = time.perf_counter()
+    A, t_asm = ref_cpu.assemble_upper_csc(3, deg, m.nodes, m.elem_nodes, D, threads=threads)
+    t1 = time.perf_counter()
+    u, info = ref_cpu.solve_fixed_pcg(3, A, f, fixed, vals, rtol=rtol, threads=threads)
+    t_assemble = t_asm["ke"] + t_asm["scatter"] + t_asm["compress"]
+    total = t_assemble + info["seconds"]
+    return {
+        "value": m.num_elements / total, "unit": UNIT, "cores": threads, "kind": "port",
+        "sample": (f"grid {'x'.join(map(str, CPU_SAMPLE_GRID))} -t, degree {deg}, {m.num_elements} elements, same material/BCs; "
+                   f"assembly {t_assemble:.2f}s (Ke {t_asm['ke']:.2f} + serial scatter {t_asm['scatter']:.2f} + compress "
+                   f"{t_asm['compress']:.2f}), block-Jacobi PCG {info['iters']} it in {info['seconds']:.2f}s "
+                   f"(CHOLMOD stand-in; smaller mesh => fewer iterations than the full workload, i.e. favourable to the CPU)"),
+        "seconds": total, "elements": m.num_elements, "pcg_iterations": info["iters"],
+    }
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    name, grid, deg, mat = parse_config(args.config)
+    samples = []
+    for _ in range(args.warmup):
+        cpu_port_sample(deg, mat, RTOL)
+    for _ in range(args.steps):
+        samples.append(cpu_port_sample(deg, mat, RTOL))
+    secs = sum(s["seconds"] for s in samples)
+    elems = sum(s["elements"] for s in samples)
+    value = elems / secs
+    base = dict(samples[-1]); base["value"] = value
+    for k in ("seconds", "elements", "pcg_iterations"):
+        base.pop(k, None)
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(args.steps, 1), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(name, grid, deg, mat), "rtol": RTOL,
+                   "note": "reference algorithm (oracle port) on host cores, bounded sample per step"},
+        "cpu_baseline": base,
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out), flush=True)
+
+
+def workload_name(name, grid, deg, mat):
+    return (f"{name}: grid {'x'.join(map(str, grid))} -t ({24 * grid[0] * grid[1] * grid[2]} "
+            f"{'quadratic' if deg == 2 else 'linear'} tets), {mat} material, cantilever.bc")
+
+
+# ---------------------------------------------------------------------------------------------
+def run_ours(args):
+    import meshfem_b200
+    from meshfem_b200 import build as mb
+    import workloads as wl
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_mod
+        torch.cuda.set_device(local_rank)
+        dist_mod.init_process_group("nccl")
+        dist = dist_mod
+    mb.build_all()
+    name, grid, deg, mat = parse_config(args.config)
+    hbm_peak, peak_src = peaks()
+
+    if world > 1:
+        from multi_gpu import run_multi_gpu   # tools/multi_gpu.py
+        return run_multi_gpu(args, dist, world, rank, local_rank, name, grid, deg, mat, hbm_peak, peak_src)
+
+    t_gen = time.perf_counter()
+    m = wl.grid_femmesh(grid, deg)
+    D = wl.material(mat)
+    fixed, vals, f = wl.cantilever_inputs(m)
+    t_gen = time.perf_counter() - t_gen
+    nodes_p, _k1 = pinned_copy(m.nodes)
+    elems_p, _k2 = pinned_copy(m.elem_nodes)
+    f_p, _k3 = pinned_copy(f)
+    n_elems = m.num_elements
+
+    sampler = ClockSampler(local_rank)
+    # ------------------------------------------------------------------ device-resident steps
+    h = meshfem_b200.Handle(local_rank)
+    h.set_mesh(3, deg, nodes_p, elems_p)
+    h.set_material(D)
+    h.assemble()                      # symbolic phase (pattern + incidence lists) is cached from here on
+    h.fix_variables(fixed, vals)
+    nb, nnzb = h.bsr_sizes()
+    pattern_s = h.timer("Pattern")
+
+    def step():
+        h.reset_timers()
+        h.assemble()
+        _, info = h.solve(f_p, rtol=RTOL, return_info=True)
+        return h.timer("Assemble System"), info[0]["seconds"], info[0]["iterations"], info[0]["rel_residual"], \
+            h.launch_count()
+
+    for _ in range(args.warmup):
+        step()
+    sampler.start()
+    wall0 = time.perf_counter()
+    asm_s, solve_s, iters, launches = 0.0, 0.0, 0, 0
+    relres = None
+    for _ in range(args.steps):
+        a, s, it, relres, nl = step()
+        asm_s += a; solve_s += s; iters += it; launches += nl
+    wall = time.perf_counter() - wall0
+    # dominant kernel: the PCG SpMV, timed live on the library's stream (inputs: 31 GB matrix >> L2)
+    spmv_s = h.time_spmv(20)
+    clocks = sampler.stop()
+    dev_s = asm_s + solve_s
+    value = args.steps * n_elems / dev_s
+    spmv_bytes = nnzb * 76 + nb * 52
+    roofline = {"bound": "hbm", "kernel": "k_bsr_spmv (PCG SpMV)", "achieved": spmv_bytes / spmv_s / 1e9,
+                "peak": hbm_peak, "unit": "GB/s", "frac": spmv_bytes / spmv_s / 1e9 / hbm_peak, "traffic": None,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": spmv_bytes,
+                "seconds_per_launch": spmv_s}
+    asm_bytes = nnzb * 72 + n_elems * (4 * m.elem_nodes.shape[1] + 96)
+    roofline["assembly"] = {"achieved": asm_bytes / (asm_s / args.steps) / 1e9, "unit": "GB/s",
+                            "frac": asm_bytes / (asm_s / args.steps) / 1e9 / hbm_peak,
+                            "algorithmic_bytes_per_launch": asm_bytes}
+    h.close()
+
+    # ------------------------------------------------------------------ end-to-end steps (host buffers)
+    def e2e_step():
+        t0 = time.perf_counter()
+        with meshfem_b200.Handle(local_rank) as hh:
+            hh.set_mesh(3, deg, nodes_p, elems_p)
+            hh.set_material(D)
+            hh.assemble()
+            hh.fix_variables(fixed, vals)
+            u = hh.solve(f_p, rtol=RTOL)
+            tip = float(u.reshape(-1, 3)[:, 1].min())
+        return time.perf_counter() - t0, tip
+
+    n_e2e = max(1, min(args.steps, 2))
+    e2e_step() if args.warmup > 0 else None
+    e2e_s, tip = 0.0, None
+    for _ in range(n_e2e):
+        s, tip = e2e_step()
+        e2e_s += s
+    h2d = nodes_p.nbytes + elems_p.nbytes + f_p.nbytes + fixed.nbytes + vals.nbytes
+    d2h = f_p.nbytes
+    e2e = {"value": n_e2e * n_elems / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+           "seconds_per_step": e2e_s / n_e2e, "steps": n_e2e, "min_uy": tip,
+           "includes": "handle creation, mesh upload, DoF reordering, symbolic pattern, assembly, constraints, PCG, result download"}
+
+    cpu = cpu_port_sample(deg, mat, RTOL) if not args.no_cpu_baseline else None
+    if cpu:
+        for k in ("seconds", "elements", "pcg_iterations"):
+            cpu.pop(k, None)
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(name, grid, deg, mat), "elements": n_elems, "nodes": m.num_nodes,
+                   "dofs": 3 * m.num_nodes, "nnz_blocks": nnzb, "rtol": RTOL, "preconditioner": "block-Jacobi 3x3",
+                   "l2_policy": "inputs larger than L2 (matrix %.1f GB)" % (nnzb * 76 / 1e9)},
+        "assembly_elements_per_s": args.steps * n_elems / asm_s,
+        "pcg_iters_per_s": iters / solve_s, "pcg_iterations_per_solve": iters / args.steps,
+        "pcg_rel_residual": relres, "assembly_ms": 1e3 * asm_s / args.steps, "solve_ms": 1e3 * solve_s / args.steps,
+        "symbolic_pattern_ms": 1e3 * pattern_s, "wall_ms_per_step": 1e3 * wall / args.steps,
+        "mesh_generation_s": t_gen,
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+    }
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="cfg5")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

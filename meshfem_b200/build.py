@@ -77,5 +77,41 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+HOST_LIB = os.path.join(LIBDIR, "libmeshfem_host.so")
+REPO = os.path.dirname(ROOT)
+HOST_SOURCES = [os.path.join(REPO, "src", "host", f) for f in ("MeshIO.cc", "host_capi.cc")]
+
+
+def _host_stamp():
+    h = hashlib.sha256()
+    files = list(HOST_SOURCES)
+    for d, _, fs in os.walk(os.path.join(REPO, "include", "MeshFEM")):
+        files += [os.path.join(d, f) for f in fs]
+    for f in sorted(files):
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
+def build_host(force: bool = False) -> str:
+    """Host C++ mirror of the reference's mesh layer (g++; no CUDA)."""
+    os.makedirs(LIBDIR, exist_ok=True)
+    stamp_file = HOST_LIB + ".stamp"
+    stamp = _host_stamp()
+    if not force and os.path.exists(HOST_LIB) and os.path.exists(stamp_file):
+        if open(stamp_file).read().strip() == stamp:
+            return HOST_LIB
+    cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-I" + os.path.join(REPO, "include")] + HOST_SOURCES + \
+          ["-o", HOST_LIB]
+    subprocess.check_call(cmd)
+    with open(stamp_file, "w") as f:
+        f.write(stamp)
+    return HOST_LIB
+
+
+def build_all(force: bool = False, verbose: bool = False):
+    return build(force, verbose), build_host(force)
+
+
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_all(force="--force" in sys.argv, verbose="-v" in sys.argv))

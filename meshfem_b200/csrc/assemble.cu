@@ -111,7 +111,7 @@ k_assemble_gather(int64_t nJobs, int64_t nb, const int64_t *__restrict__ incPtr,
 
             ke_row_slice<N, DEG>(g, D, li, [&](int j, const double blk[N][N]) {
                 // slot of column DoF dofs[j] inside this incidence's row (sorted colidx)
-                int slot = 0;
+                int slot = 0, jslot = 0;
                 if (valid) {
                     int lo = 0, hi = rowLen;
                     const int32_t want = dofs[j];
@@ -120,6 +120,7 @@ k_assemble_gather(int64_t nJobs, int64_t nb, const int64_t *__restrict__ incPtr,
                         const int mid = (lo + hi) >> 1;
                         if (rc[mid] < want) lo = mid + 1; else hi = mid;
                     }
+                    jslot = lo;
                     slot = rowBase + lo;
                 }
                 // fixed-order accumulation: lanes hitting the same block add one after the
@@ -130,11 +131,12 @@ k_assemble_gather(int64_t nJobs, int64_t nb, const int64_t *__restrict__ incPtr,
                 const int maxRank = __reduce_max_sync(0xffffffffu, valid ? rank : 0);
                 for (int rr = 0; rr <= maxRank; ++rr) {
                     if (valid && rank == rr) {
-                        double *dst = A + (int64_t)slot * NN;
+                        // row-plane layout (core.cuh val_index), relative to the run's first block
+                        double *dst = A + (int64_t)rowBase * NN + N * jslot;
 #pragma unroll
                         for (int cc = 0; cc < N; ++cc)
 #pragma unroll
-                            for (int dd = 0; dd < N; ++dd) dst[cc * N + dd] += blk[cc][dd];
+                            for (int dd = 0; dd < N; ++dd) dst[cc * (N * rowLen) + dd] += blk[cc][dd];
                     }
                     __syncwarp();
                 }
@@ -187,11 +189,12 @@ k_assemble_colored(int64_t nInColor, const int32_t *__restrict__ elems, const in
                 const int64_t mid = (lo + hi) >> 1;
                 if (colidx[mid] < want) lo = mid + 1; else hi = mid;
             }
-            double *dst = vals + lo * NN;
+            double *dst = vals + rb * NN + N * (lo - rb);
+            const int64_t plane = N * (re - rb);
 #pragma unroll
             for (int cc = 0; cc < N; ++cc)
 #pragma unroll
-                for (int dd = 0; dd < N; ++dd) dst[cc * N + dd] += blk[cc][dd];
+                for (int dd = 0; dd < N; ++dd) dst[cc * plane + dd] += blk[cc][dd];
         });
     }
 }

@@ -295,9 +295,14 @@ void export_bsr(mfem_b200_ctx *c, int64_t *rowptrOut, int32_t *colidxOut, double
         for (int64_t k = b; k < e; ++k) tmp.emplace_back(i2e[(size_t)ci[(size_t)k]], k);
         std::sort(tmp.begin(), tmp.end());
         int64_t o = rowptrOut[re];
+        const int N = c->N;
         for (auto &pr : tmp) {
             if (colidxOut) colidxOut[o] = pr.first;
-            if (valsOut) std::copy(v.begin() + pr.second * NN, v.begin() + (pr.second + 1) * NN, valsOut + o * NN);
+            if (valsOut)      // device "row-plane" layout -> plain row-major blocks
+                for (int r = 0; r < N; ++r)
+                    for (int cc = 0; cc < N; ++cc)
+                        valsOut[o * NN + r * N + cc] =
+                            v[(size_t)(NN * b + (int64_t)r * (N * (e - b)) + (int64_t)N * (pr.second - b) + cc)];
             ++o;
         }
     }

@@ -87,6 +87,7 @@ struct mfem_b200_ctx {
     int opt_reorder = 1;
     int opt_assembly = 0;
     int opt_graph = 1;
+    int opt_spmv_lanes = 0;                // lanes per block row in the SpMV (0 = choose from the mean row length)
 
     // mesh
     int N = 0, deg = 0, npe = 0;
@@ -110,7 +111,7 @@ struct mfem_b200_ctx {
     int64_t nnzb = 0;
     mfem::DevBuf<int64_t> rowptr;          // [nDofs+1]
     mfem::DevBuf<int32_t> colidx;          // [nnzb]
-    mfem::DevBuf<double> vals;             // [nnzb*N*N]
+    mfem::DevBuf<double> vals;             // [nnzb*N*N]  "row-plane" layout, see val_index()
     // DoF -> incident (element, local node) lists
     int64_t totalInc = 0;
     mfem::DevBuf<int64_t> incPtr;          // [nDofs+1]
@@ -166,6 +167,16 @@ struct ScopedTimer {           // CUDA-event section timer accumulating into ctx
     }
     ~ScopedTimer() { stop(); }
 };
+
+// Value layout of the block-CSR matrix ("row-plane"): the N*N*n values of a block row with n
+// blocks starting at block b0 are stored as N planes, plane r holding scalar row r of the block
+// row as [block j][component c]:   index = N*N*b0 + r*(N*n) + N*j + c.
+// A warp streaming one scalar row reads contiguous doubles (coalesced at any block size), and
+// the block column index j = f / N is shared by the N lanes that need the same x block.
+template <int N>
+__host__ __device__ __forceinline__ int64_t val_index(int64_t b0, int64_t n, int64_t j, int r, int c) {
+    return (int64_t)N * N * b0 + (int64_t)r * (N * n) + (int64_t)N * j + c;
+}
 
 inline int grid_for(int64_t n, int block) { return static_cast<int>((n + block - 1) / block); }
 

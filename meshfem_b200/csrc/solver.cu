@@ -85,52 +85,88 @@ __device__ __forceinline__ double final_sum(const double *partials, int n) {
 
 // ---------------------------------------------------------------------------
 // K3  bsr_spmv: y = mask(K x) [, dot = x.y]
-// One warp per block row.  The row's values are a contiguous run of NN*nblk doubles; lanes
-// stride over that run ELEMENT-wise (not block-wise), so every value load is a fully
-// coalesced 256 B warp access at any block size, and x is gathered through L1/L2.
+// LPR lanes (8/16/32) cooperate on one block row.  With the row-plane value layout
+// (core.cuh val_index) lane f of a row reads element f of each of the N scalar rows: N fully
+// coalesced streaming loads per step, ONE gathered x load shared by the N lanes of a block
+// column, N FMAs -- no per-element index arithmetic beyond f / N.  The N partial sums are
+// folded across the lanes so that the reduction costs 2 + log2(LPR/2) shuffles instead of
+// N * log2(LPR).
 // ---------------------------------------------------------------------------
-template <int N, bool MASKED, bool DOT>
+template <int N, int LPR>
+__device__ __forceinline__ double fold_reduce(double (&a)[N], int sl) {
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int half = LPR / 2;
+    const bool upper = (sl & half) != 0;
+    double v;
+    if (N == 3) {
+        constexpr int q = LPR / 4;
+        // step A: lower half keeps (a0, a1), upper half keeps a2
+        const double r1 = __shfl_xor_sync(FULL, upper ? a[0] : a[2], half);
+        const double r2 = __shfl_xor_sync(FULL, a[1], half);
+        if (upper) a[2] += r1; else { a[0] += r1; a[1] += r2; }
+        // step B: lower half splits a0 / a1 between its quarters; upper half keeps folding a2
+        const bool bq = (sl & q) != 0;
+        const double send = upper ? a[2] : (bq ? a[0] : a[1]);
+        const double r3 = __shfl_xor_sync(FULL, send, q);
+        v = upper ? a[2] + r3 : (bq ? a[1] + r3 : a[0] + r3);
+#pragma unroll
+        for (int o = q / 2; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    } else {
+        const double r1 = __shfl_xor_sync(FULL, upper ? a[0] : a[1], half);
+        v = upper ? a[1] + r1 : a[0] + r1;
+#pragma unroll
+        for (int o = half / 2; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    }
+    return v;   // component k of the row lives in lane sl == owner_lane<N,LPR>(k)
+}
+template <int N, int LPR>
+__device__ __forceinline__ int owner_component(int sl) {   // -1 if this lane owns no result
+    if (N == 3) return sl == 0 ? 0 : (sl == LPR / 4 ? 1 : (sl == LPR / 2 ? 2 : -1));
+    return sl == 0 ? 0 : (sl == LPR / 2 ? 1 : -1);
+}
+
+template <int N, int LPR, bool MASKED, bool DOT>
 __global__ void __launch_bounds__(kSpmvThreads)
 k_bsr_spmv(int64_t nb, const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
            const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y,
            const uint8_t *__restrict__ fixedMask, double *partials, unsigned *ticket, double *scal,
            const int *status) {
     constexpr int NN = N * N;
+    constexpr int RPW = 32 / LPR;                     // rows per warp
     if (status && status[ST_STATE] != 0) return;
     const int lane = threadIdx.x & 31;
+    const int sub = lane / LPR, sl = lane % LPR;
     const int64_t warpGlobal = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nWarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int comp = owner_component<N, LPR>(sl);
     double dot = 0.0;
-    for (int64_t row = warpGlobal; row < nb; row += nWarps) {
-        const int64_t b0 = rowptr[row], b1 = rowptr[row + 1];
+    for (int64_t rowBase = warpGlobal * RPW; rowBase < nb; rowBase += nWarps * RPW) {
+        const int64_t row = rowBase + sub;
+        int64_t b0 = 0;
+        int L = 0;
+        if (row < nb) {
+            b0 = rowptr[row];
+            L = (int)(rowptr[row + 1] - b0) * N;
+        }
         const double *v = vals + b0 * NN;
         const int32_t *ci = colidx + b0;
-        const int nE = (int)(b1 - b0) * NN;
         double acc[N];
 #pragma unroll
         for (int r = 0; r < N; ++r) acc[r] = 0.0;
-#pragma unroll 4
-        for (int f = lane; f < nE; f += 32) {
-            const int blk = f / NN;
-            const int rc = f - blk * NN;
-            const int r = rc / N, cc = rc - r * N;
-            const double a = __ldcs(v + f);                         // streamed once
-            const double xv = __ldg(x + (int64_t)__ldg(ci + blk) * N + cc);
-            const double p = a * xv;
+#pragma unroll 2
+        for (int f = sl; f < L; f += LPR) {
+            const int j = f / N;
+            const int cc = f - j * N;
+            const double xv = __ldg(x + (int64_t)__ldg(ci + j) * N + cc);
 #pragma unroll
-            for (int k = 0; k < N; ++k) acc[k] += (r == k) ? p : 0.0;
+            for (int r = 0; r < N; ++r) acc[r] = fma(__ldcs(v + r * L + f), xv, acc[r]);
         }
-#pragma unroll
-        for (int k = 0; k < N; ++k)
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
-        if (lane < N) {
-            double out = acc[0];
-#pragma unroll
-            for (int k = 1; k < N; ++k) out = (lane == k) ? acc[k] : out;
-            if (MASKED && fixedMask[row * N + lane]) out = 0.0;
-            y[row * N + lane] = out;
-            if (DOT) dot += out * x[row * N + lane];
+        const double out0 = fold_reduce<N, LPR>(acc, sl);
+        if (comp >= 0 && row < nb) {
+            double out = out0;
+            if (MASKED && fixedMask[row * N + comp]) out = 0.0;
+            y[row * N + comp] = out;
+            if (DOT) dot += out * x[row * N + comp];
         }
     }
     if (DOT) {
@@ -164,7 +200,9 @@ __global__ void k_jacobi_setup(int64_t nb, const int64_t *__restrict__ rowptr, c
 #pragma unroll
     for (int r = 0; r < N; ++r)
 #pragma unroll
-        for (int c = 0; c < N; ++c) a[r][c] = have ? vals[lo * NN + r * N + c] : ((r == c) ? 1.0 : 0.0);
+        for (int c = 0; c < N; ++c)
+            a[r][c] = have ? vals[val_index<N>(rowptr[row], end - rowptr[row], lo - rowptr[row], r, c)]
+                           : ((r == c) ? 1.0 : 0.0);
     bool fx[N];
 #pragma unroll
     for (int r = 0; r < N; ++r) fx[r] = fixedMask[row * N + r] != 0;
@@ -321,11 +359,17 @@ static int sm_count(mfem_b200_ctx *c) {
     return n > 0 ? n : 148;
 }
 
-static int spmv_grid(mfem_b200_ctx *c) {
-    // persistent-style launch: 8 CTAs of 256 threads per SM (full occupancy), rows grid-strided by warp
-    const int64_t warpsNeeded = c->nDofs;
+static int spmv_lanes(mfem_b200_ctx *c) {
+    if (c->opt_spmv_lanes == 8 || c->opt_spmv_lanes == 16 || c->opt_spmv_lanes == 32) return c->opt_spmv_lanes;
+    const double meanL = c->nDofs ? double(c->nnzb) * c->N / double(c->nDofs) : 0.0;   // scalars per scalar row
+    return meanL > 40.0 ? 32 : (meanL > 18.0 ? 16 : 8);
+}
+
+static int spmv_grid(mfem_b200_ctx *c, int lpr) {
+    // persistent-style launch: up to 8 CTAs of 256 threads per SM, row groups grid-strided by warp
+    const int64_t warpsNeeded = (c->nDofs + (32 / lpr) - 1) / (32 / lpr);
     const int64_t ctas = (warpsNeeded + (kSpmvThreads / 32) - 1) / (kSpmvThreads / 32);
-    return (int)std::min<int64_t>(ctas, (int64_t)sm_count(c) * 8);
+    return (int)std::max<int64_t>(1, std::min<int64_t>(ctas, (int64_t)sm_count(c) * 8));
 }
 
 static int vec_grid(mfem_b200_ctx *c, int64_t n) {
@@ -354,23 +398,29 @@ void ensure_work(mfem_b200_ctx *c) {
     c->workValid = true;
 }
 
+template <int N, int LPR>
+static void launch_spmv_l(mfem_b200_ctx *c, const double *x, double *y, bool masked, bool dot) {
+    PcgWork &w = c->work;
+    const int grid = spmv_grid(c, LPR);
+    if (masked && dot)
+        k_bsr_spmv<N, LPR, true, true><<<grid, kSpmvThreads, 0, c->stream>>>(
+            c->nDofs, c->rowptr, c->colidx, c->vals, x, y, c->fixedMask, w.partials, w.ticket, w.scal, w.status);
+    else if (masked)
+        k_bsr_spmv<N, LPR, true, false><<<grid, kSpmvThreads, 0, c->stream>>>(
+            c->nDofs, c->rowptr, c->colidx, c->vals, x, y, c->fixedMask, nullptr, nullptr, nullptr, nullptr);
+    else
+        k_bsr_spmv<N, LPR, false, false><<<grid, kSpmvThreads, 0, c->stream>>>(
+            c->nDofs, c->rowptr, c->colidx, c->vals, x, y, nullptr, nullptr, nullptr, nullptr, nullptr);
+    c->launches++;
+}
+
 template <int N>
 static void launch_spmv(mfem_b200_ctx *c, const double *x, double *y, bool masked, bool dot) {
-    PcgWork &w = c->work;
-    const int grid = spmv_grid(c);
-    if (masked && dot)
-        k_bsr_spmv<N, true, true><<<grid, kSpmvThreads, 0, c->stream>>>(c->nDofs, c->rowptr, c->colidx, c->vals, x, y,
-                                                                         c->fixedMask, w.partials, w.ticket, w.scal,
-                                                                         w.status);
-    else if (masked)
-        k_bsr_spmv<N, true, false><<<grid, kSpmvThreads, 0, c->stream>>>(c->nDofs, c->rowptr, c->colidx, c->vals, x, y,
-                                                                          c->fixedMask, nullptr, nullptr, nullptr,
-                                                                          nullptr);
-    else
-        k_bsr_spmv<N, false, false><<<grid, kSpmvThreads, 0, c->stream>>>(c->nDofs, c->rowptr, c->colidx, c->vals, x,
-                                                                           y, nullptr, nullptr, nullptr, nullptr,
-                                                                           nullptr);
-    c->launches++;
+    switch (spmv_lanes(c)) {
+        case 8: launch_spmv_l<N, 8>(c, x, y, masked, dot); break;
+        case 16: launch_spmv_l<N, 16>(c, x, y, masked, dot); break;
+        default: launch_spmv_l<N, 32>(c, x, y, masked, dot); break;
+    }
 }
 
 void spmv_plain(mfem_b200_ctx *c, const double *x_int, double *y_int) {

@@ -1,0 +1,144 @@
+// C exports of host-side helpers for the Python tests and bench.py: synthetic `grid -t`
+// meshes (src/bin/tools/grid.cc:115-137 of the reference) and FEMMesh construction.  These are
+// input generators / host logic, not part of the GPU ABI (include/mfem_b200.h).
+#include <MeshFEM/FEMMesh.hh>
+#include <MeshFEM/MeshIO.hh>
+#include <MeshFEM/filters/gen_grid.hh>
+#include <MeshFEM/filters/hex_tet_subdiv.hh>
+#include <MeshFEM/filters/quad_tri_subdiv.hh>
+
+#include <cstring>
+#include <string>
+
+namespace {
+
+struct HostMesh {
+    int dim = 0, deg = 0;
+    std::vector<MeshIO::IOVertex> vertices;
+    std::vector<MeshIO::IOElement> elements;
+    // FEMMesh flat data
+    std::vector<double> nodes;
+    std::vector<int32_t> elemNodes, bdryElemNodes, bdryElemVerts, bdryNodes;
+    std::vector<double> bdryVol, bdryNormal;
+    double bbmin[3] = {0, 0, 0}, bbmax[3] = {0, 0, 0};
+    size_t nV = 0, nbe = 0;
+    std::string err;
+};
+
+thread_local std::string g_err;
+
+template <size_t K, size_t Deg>
+void fill(HostMesh &hm) {
+    FEMMesh<K, Deg> m(hm.elements, hm.vertices);
+    hm.nodes = m.nodePositions();
+    hm.elemNodes = m.elementNodes();
+    hm.bdryElemNodes = m.boundaryElementNodes();
+    hm.bdryElemVerts = m.boundaryElementVertices();
+    hm.nV = m.numVertices();
+    hm.nbe = m.numBoundaryElements();
+    hm.bdryNodes.resize(m.numBoundaryNodes());
+    for (size_t i = 0; i < hm.bdryNodes.size(); ++i) hm.bdryNodes[i] = m.volumeNodeForBoundaryNode(i);
+    hm.bdryVol.resize(hm.nbe);
+    hm.bdryNormal.resize(hm.nbe * K);
+    for (size_t be = 0; be < hm.nbe; ++be) {
+        hm.bdryVol[be] = m.boundaryElementVolume(be);
+        for (size_t c = 0; c < K; ++c) hm.bdryNormal[be * K + c] = m.boundaryElementNormal(be)[c];
+    }
+    for (size_t c = 0; c < K; ++c) { hm.bbmin[c] = m.boundingBox().minCorner[c]; hm.bbmax[c] = m.boundingBox().maxCorner[c]; }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *mfemhost_last_error() { return g_err.c_str(); }
+
+// `grid sx x sy [x sz] -t [-m min -M max]`: returns an opaque mesh holding vertices+simplices.
+void *mfemhost_grid(int ndim, const int64_t *sizes, const double *minCorner, const double *maxCorner) {
+    try {
+        auto *hm = new HostMesh();
+        std::vector<size_t> sz(sizes, sizes + ndim);
+        std::vector<MeshIO::IOVertex> gv;
+        std::vector<MeshIO::IOElement> ge;
+        gen_grid(sz, gv, ge);
+        if (minCorner && maxCorner) {
+            Point3D scale, mn;
+            for (int i = 0; i < 3; ++i) { mn[i] = i < ndim ? minCorner[i] : 0.0; scale[i] = i < ndim ? (maxCorner[i] - minCorner[i]) / sizes[i] : 0.0; }
+            for (auto &v : gv) for (int i = 0; i < 3; ++i) v.point[i] = scale[i] * v.point[i] + mn[i];
+        }
+        std::vector<size_t> cellIdx;
+        if (ndim == 2) quad_tri_subdiv(gv, ge, hm->vertices, hm->elements, cellIdx);
+        else hex_tet_subdiv(gv, ge, hm->vertices, hm->elements, cellIdx);
+        hm->dim = ndim;
+        return hm;
+    } catch (const std::exception &e) { g_err = e.what(); return nullptr; }
+}
+
+void *mfemhost_load_mesh(const char *path, int *dimOut) {
+    try {
+        auto *hm = new HostMesh();
+        auto type = MeshIO::load(path, hm->vertices, hm->elements);
+        if (type == MeshIO::MESH_TET) hm->dim = 3;
+        else if (type == MeshIO::MESH_TRI) hm->dim = 2;
+        else { delete hm; throw std::runtime_error("Mesh must be pure triangle or tet."); }
+        if (dimOut) *dimOut = hm->dim;
+        return hm;
+    } catch (const std::exception &e) { g_err = e.what(); return nullptr; }
+}
+
+void *mfemhost_from_arrays(int dim, int64_t nV, const double *V3, int64_t nE, const int64_t *E) {
+    auto *hm = new HostMesh();
+    hm->dim = dim;
+    hm->vertices.resize(nV);
+    for (int64_t i = 0; i < nV; ++i) hm->vertices[i].set(V3[3 * i], V3[3 * i + 1], V3[3 * i + 2]);
+    hm->elements.assign(nE, MeshIO::IOElement(dim + 1));
+    for (int64_t e = 0; e < nE; ++e) for (int c = 0; c <= dim; ++c) hm->elements[e][c] = (size_t)E[e * (dim + 1) + c];
+    return hm;
+}
+
+void mfemhost_free(void *m) { delete static_cast<HostMesh *>(m); }
+
+int mfemhost_raw_sizes(void *m, int64_t *nV, int64_t *nE) {
+    auto *hm = static_cast<HostMesh *>(m);
+    *nV = (int64_t)hm->vertices.size(); *nE = (int64_t)hm->elements.size();
+    return 0;
+}
+int mfemhost_raw_copy(void *m, double *V3, int64_t *E) {
+    auto *hm = static_cast<HostMesh *>(m);
+    for (size_t i = 0; i < hm->vertices.size(); ++i) for (int c = 0; c < 3; ++c) V3[3 * i + c] = hm->vertices[i][c];
+    const size_t n = hm->dim + 1;
+    for (size_t e = 0; e < hm->elements.size(); ++e) for (size_t c = 0; c < n; ++c) E[e * n + c] = (int64_t)hm->elements[e][c];
+    return 0;
+}
+
+// Build FEMMesh<dim,deg>; sizes: [numNodes, numElements, numBoundaryElements, numBoundaryNodes, numVertices]
+int mfemhost_build_femmesh(void *m, int deg, int64_t *sizes5) {
+    auto *hm = static_cast<HostMesh *>(m);
+    try {
+        hm->deg = deg;
+        if (hm->dim == 3 && deg == 1) fill<3, 1>(*hm);
+        else if (hm->dim == 3 && deg == 2) fill<3, 2>(*hm);
+        else if (hm->dim == 2 && deg == 1) fill<2, 1>(*hm);
+        else if (hm->dim == 2 && deg == 2) fill<2, 2>(*hm);
+        else throw std::runtime_error("bad dim/deg");
+        sizes5[0] = (int64_t)(hm->nodes.size() / hm->dim);
+        sizes5[1] = (int64_t)hm->elements.size();
+        sizes5[2] = (int64_t)hm->nbe;
+        sizes5[3] = (int64_t)hm->bdryNodes.size();
+        sizes5[4] = (int64_t)hm->nV;
+        return 0;
+    } catch (const std::exception &e) { g_err = e.what(); return -1; }
+}
+
+int mfemhost_femmesh_copy(void *m, double *nodes, int32_t *elemNodes, int32_t *bdryElemNodes, int32_t *bdryElemVerts,
+                          int32_t *bdryNodes, double *bdryVol, double *bdryNormal, double *bbox6) {
+    auto *hm = static_cast<HostMesh *>(m);
+    auto cp = [](auto &v, auto *dst) { if (dst && !v.empty()) std::memcpy(dst, v.data(), v.size() * sizeof(v[0])); };
+    cp(hm->nodes, nodes); cp(hm->elemNodes, elemNodes); cp(hm->bdryElemNodes, bdryElemNodes);
+    cp(hm->bdryElemVerts, bdryElemVerts); cp(hm->bdryNodes, bdryNodes); cp(hm->bdryVol, bdryVol);
+    cp(hm->bdryNormal, bdryNormal);
+    if (bbox6) for (int c = 0; c < 3; ++c) { bbox6[c] = hm->bbmin[c]; bbox6[3 + c] = hm->bbmax[c]; }
+    return 0;
+}
+
+}  // extern "C"

@@ -15,4 +15,4 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def lib_built():
     from meshfem_b200 import build
-    return build.build()
+    return build.build_all()

@@ -71,13 +71,14 @@ def test_assembly_is_bit_reproducible(mfem, N, deg, sizes):
 
 
 @pytest.mark.parametrize("N,deg,sizes", CASES)
-def test_spmv_and_apply_K(mfem, N, deg, sizes):
+@pytest.mark.parametrize("lanes", [0, 8, 16, 32])
+def test_spmv_and_apply_K(mfem, N, deg, sizes, lanes):
     mesh = grid_mesh(N, deg, sizes)
     D = _material(N, "ortho")
     rng = np.random.default_rng(5)
     x = rng.normal(size=(mesh.num_nodes, N))
     Kref = orc.stiffness_matrix(mesh, D)
-    with _handle(mfem, mesh, D) as h:
+    with _handle(mfem, mesh, D, spmv_lanes=lanes) as h:
         h.assemble()
         y = h.spmv(x)
         z = h.apply_K(x)
