@@ -125,6 +125,34 @@ __device__ __forceinline__ int owner_component(int sl) {   // -1 if this lane ow
     return sl == 0 ? 0 : (sl == LPR / 2 ? 1 : -1);
 }
 
+// L2 residency hints: the matrix (values + column indices) is streamed exactly once per SpMV
+// and must not displace the vectors, which are re-read ~27 times through the gather.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ double ld_stream_f64(const double *p, uint64_t pol) {
+    double v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ int ld_stream_s32(const int32_t *p, uint64_t pol) {
+    int v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ double ld_keep_f64(const double *p, uint64_t pol) {
+    double v;
+    asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+    return v;
+}
+
 template <int N, int LPR, bool MASKED, bool DOT>
 __global__ void __launch_bounds__(kSpmvThreads)
 k_bsr_spmv(int64_t nb, const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
@@ -133,40 +161,58 @@ k_bsr_spmv(int64_t nb, const int64_t *__restrict__ rowptr, const int32_t *__rest
            const int *status) {
     constexpr int NN = N * N;
     constexpr int RPW = 32 / LPR;                     // rows per warp
+    constexpr int U = 3;                              // row chunks whose loads are issued together
     if (status && status[ST_STATE] != 0) return;
     const int lane = threadIdx.x & 31;
     const int sub = lane / LPR, sl = lane % LPR;
     const int64_t warpGlobal = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nWarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int comp = owner_component<N, LPR>(sl);
+    const uint64_t polStream = l2_policy_evict_first(), polKeep = l2_policy_evict_last();
     double dot = 0.0;
+    // software pipeline over rows: the next row's extent is fetched while this one is computed
+    int64_t row = warpGlobal * RPW + sub;
+    int64_t nb0 = 0, nb1 = 0;
+    if (row < nb) { nb0 = rowptr[row]; nb1 = rowptr[row + 1]; }
     for (int64_t rowBase = warpGlobal * RPW; rowBase < nb; rowBase += nWarps * RPW) {
-        const int64_t row = rowBase + sub;
-        int64_t b0 = 0;
-        int L = 0;
-        if (row < nb) {
-            b0 = rowptr[row];
-            L = (int)(rowptr[row + 1] - b0) * N;
-        }
+        const int64_t b0 = nb0;
+        const int L = (int)(nb1 - nb0) * N;
+        const int64_t thisRow = row;
+        row += nWarps * RPW;
+        nb0 = nb1 = 0;
+        if (row < nb) { nb0 = rowptr[row]; nb1 = rowptr[row + 1]; }
         const double *v = vals + b0 * NN;
         const int32_t *ci = colidx + b0;
         double acc[N];
 #pragma unroll
         for (int r = 0; r < N; ++r) acc[r] = 0.0;
-#pragma unroll 2
-        for (int f = sl; f < L; f += LPR) {
-            const int j = f / N;
-            const int cc = f - j * N;
-            const double xv = __ldg(x + (int64_t)__ldg(ci + j) * N + cc);
+        for (int f0 = sl; f0 < L; f0 += U * LPR) {
+            // issue every load of U chunks before the first use (memory-level parallelism)
+            int col[U], cc[U];
+            double a[U][N], xv[U];
 #pragma unroll
-            for (int r = 0; r < N; ++r) acc[r] = fma(__ldcs(v + r * L + f), xv, acc[r]);
+            for (int u = 0; u < U; ++u) {
+                const int f = f0 + u * LPR;
+                const bool ok = f < L;
+                const int j = f / N;
+                cc[u] = f - j * N;
+                col[u] = ok ? ld_stream_s32(ci + j, polStream) : 0;
+#pragma unroll
+                for (int r = 0; r < N; ++r) a[u][r] = ok ? ld_stream_f64(v + r * L + f, polStream) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) xv[u] = ld_keep_f64(x + (int64_t)col[u] * N + cc[u], polKeep);
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int r = 0; r < N; ++r) acc[r] = fma(a[u][r], xv[u], acc[r]);
         }
         const double out0 = fold_reduce<N, LPR>(acc, sl);
-        if (comp >= 0 && row < nb) {
+        if (comp >= 0 && thisRow < nb) {
             double out = out0;
-            if (MASKED && fixedMask[row * N + comp]) out = 0.0;
-            y[row * N + comp] = out;
-            if (DOT) dot += out * x[row * N + comp];
+            if (MASKED && fixedMask[thisRow * N + comp]) out = 0.0;
+            y[thisRow * N + comp] = out;
+            if (DOT) dot += out * x[thisRow * N + comp];
         }
     }
     if (DOT) {
@@ -365,11 +411,16 @@ static int spmv_lanes(mfem_b200_ctx *c) {
     return meanL > 40.0 ? 32 : (meanL > 18.0 ? 16 : 8);
 }
 
-static int spmv_grid(mfem_b200_ctx *c, int lpr) {
-    // persistent-style launch: up to 8 CTAs of 256 threads per SM, row groups grid-strided by warp
+// persistent-style launch: exactly the CTAs that are co-resident (occupancy API), row groups
+// grid-strided by warp so that all SMs sweep one moving window of the matrix together
+template <class Kern>
+static int spmv_grid(mfem_b200_ctx *c, int lpr, Kern kern) {
+    int perSM = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, kSpmvThreads, 0);
+    if (perSM < 1) perSM = 1;
     const int64_t warpsNeeded = (c->nDofs + (32 / lpr) - 1) / (32 / lpr);
     const int64_t ctas = (warpsNeeded + (kSpmvThreads / 32) - 1) / (kSpmvThreads / 32);
-    return (int)std::max<int64_t>(1, std::min<int64_t>(ctas, (int64_t)sm_count(c) * 8));
+    return (int)std::max<int64_t>(1, std::min<int64_t>(ctas, (int64_t)sm_count(c) * perSM));
 }
 
 static int vec_grid(mfem_b200_ctx *c, int64_t n) {
@@ -401,15 +452,14 @@ void ensure_work(mfem_b200_ctx *c) {
 template <int N, int LPR>
 static void launch_spmv_l(mfem_b200_ctx *c, const double *x, double *y, bool masked, bool dot) {
     PcgWork &w = c->work;
-    const int grid = spmv_grid(c, LPR);
     if (masked && dot)
-        k_bsr_spmv<N, LPR, true, true><<<grid, kSpmvThreads, 0, c->stream>>>(
+        k_bsr_spmv<N, LPR, true, true><<<spmv_grid(c, LPR, k_bsr_spmv<N, LPR, true, true>), kSpmvThreads, 0, c->stream>>>(
             c->nDofs, c->rowptr, c->colidx, c->vals, x, y, c->fixedMask, w.partials, w.ticket, w.scal, w.status);
     else if (masked)
-        k_bsr_spmv<N, LPR, true, false><<<grid, kSpmvThreads, 0, c->stream>>>(
+        k_bsr_spmv<N, LPR, true, false><<<spmv_grid(c, LPR, k_bsr_spmv<N, LPR, true, false>), kSpmvThreads, 0, c->stream>>>(
             c->nDofs, c->rowptr, c->colidx, c->vals, x, y, c->fixedMask, nullptr, nullptr, nullptr, nullptr);
     else
-        k_bsr_spmv<N, LPR, false, false><<<grid, kSpmvThreads, 0, c->stream>>>(
+        k_bsr_spmv<N, LPR, false, false><<<spmv_grid(c, LPR, k_bsr_spmv<N, LPR, false, false>), kSpmvThreads, 0, c->stream>>>(
             c->nDofs, c->rowptr, c->colidx, c->vals, x, y, nullptr, nullptr, nullptr, nullptr, nullptr);
     c->launches++;
 }
