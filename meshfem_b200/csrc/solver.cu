@@ -129,79 +129,176 @@ __device__ __forceinline__ int owner_component(int sl) {   // -1 if this lane ow
 // and must not displace the vectors, which are re-read ~27 times through the gather.
 __device__ __forceinline__ uint64_t l2_policy_evict_last() {
     uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
 __device__ __forceinline__ uint64_t l2_policy_evict_first() {
     uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
 __device__ __forceinline__ double ld_stream_f64(const double *p, uint64_t pol) {
     double v;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
     return v;
 }
 __device__ __forceinline__ int ld_stream_s32(const int32_t *p, uint64_t pol) {
     int v;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
     return v;
 }
 __device__ __forceinline__ double ld_keep_f64(const double *p, uint64_t pol) {
     double v;
-    asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+    asm("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
     return v;
 }
 
+// All streaming loads of one chunk (U = 3 sub-chunks: 3 column indices + 3*N matrix scalars per
+// lane) are issued from ONE asm block: the hardware issues in order, so nothing that consumes a
+// load result may sit between them.  Lanes past the end of the row are predicated off and get 0.
+template <int N, int LPR>
+struct ChunkLoader;
+
+#define MFEM_LD_S32 "ld.global.nc.L1::no_allocate.L2::cache_hint.s32"
+#define MFEM_LD_F64 "ld.global.nc.L1::no_allocate.L2::cache_hint.f64"
+
+template <int LPR>
+struct ChunkLoader<3, LPR> {
+    static __device__ __forceinline__ void run(const int32_t *c0, const int32_t *c1, const int32_t *c2,
+                                               const double *p0, const double *p1, const double *p2, int rem,
+                                               uint64_t pol, int (&col)[3], double (&a)[3][3]) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred q0, q1, q2;\n\t"
+            "setp.gt.s32 q0, %18, 0;\n\t"
+            "setp.gt.s32 q1, %18, %20;\n\t"
+            "setp.gt.s32 q2, %18, %21;\n\t"
+            "mov.b32 %0, 0; mov.b32 %1, 0; mov.b32 %2, 0;\n\t"
+            "mov.f64 %3, 0d0000000000000000; mov.f64 %4, 0d0000000000000000; mov.f64 %5, 0d0000000000000000;\n\t"
+            "mov.f64 %6, 0d0000000000000000; mov.f64 %7, 0d0000000000000000; mov.f64 %8, 0d0000000000000000;\n\t"
+            "mov.f64 %9, 0d0000000000000000; mov.f64 %10, 0d0000000000000000; mov.f64 %11, 0d0000000000000000;\n\t"
+            "@q0 " MFEM_LD_S32 " %0, [%12], %19;\n\t"
+            "@q1 " MFEM_LD_S32 " %1, [%13], %19;\n\t"
+            "@q2 " MFEM_LD_S32 " %2, [%14], %19;\n\t"
+            "@q0 " MFEM_LD_F64 " %3, [%15], %19;\n\t"
+            "@q0 " MFEM_LD_F64 " %4, [%16], %19;\n\t"
+            "@q0 " MFEM_LD_F64 " %5, [%17], %19;\n\t"
+            "@q1 " MFEM_LD_F64 " %6, [%15+%22], %19;\n\t"
+            "@q1 " MFEM_LD_F64 " %7, [%16+%22], %19;\n\t"
+            "@q1 " MFEM_LD_F64 " %8, [%17+%22], %19;\n\t"
+            "@q2 " MFEM_LD_F64 " %9, [%15+%23], %19;\n\t"
+            "@q2 " MFEM_LD_F64 " %10, [%16+%23], %19;\n\t"
+            "@q2 " MFEM_LD_F64 " %11, [%17+%23], %19;\n\t"
+            "}"
+            : "=r"(col[0]), "=r"(col[1]), "=r"(col[2]), "=d"(a[0][0]), "=d"(a[0][1]), "=d"(a[0][2]), "=d"(a[1][0]),
+              "=d"(a[1][1]), "=d"(a[1][2]), "=d"(a[2][0]), "=d"(a[2][1]), "=d"(a[2][2])
+            : "l"(c0), "l"(c1), "l"(c2), "l"(p0), "l"(p1), "l"(p2), "r"(rem), "l"(pol), "n"(LPR), "n"(2 * LPR),
+              "n"(8 * LPR), "n"(16 * LPR)
+            : "memory");
+    }
+};
+
+template <int LPR>
+struct ChunkLoader<2, LPR> {
+    static __device__ __forceinline__ void run(const int32_t *c0, const int32_t *c1, const int32_t *c2,
+                                               const double *p0, const double *p1, const double * /*unused*/, int rem,
+                                               uint64_t pol, int (&col)[3], double (&a)[3][2]) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred q0, q1, q2;\n\t"
+            "setp.gt.s32 q0, %14, 0;\n\t"
+            "setp.gt.s32 q1, %14, %16;\n\t"
+            "setp.gt.s32 q2, %14, %17;\n\t"
+            "mov.b32 %0, 0; mov.b32 %1, 0; mov.b32 %2, 0;\n\t"
+            "mov.f64 %3, 0d0000000000000000; mov.f64 %4, 0d0000000000000000; mov.f64 %5, 0d0000000000000000;\n\t"
+            "mov.f64 %6, 0d0000000000000000; mov.f64 %7, 0d0000000000000000; mov.f64 %8, 0d0000000000000000;\n\t"
+            "@q0 " MFEM_LD_S32 " %0, [%9], %15;\n\t"
+            "@q1 " MFEM_LD_S32 " %1, [%10], %15;\n\t"
+            "@q2 " MFEM_LD_S32 " %2, [%11], %15;\n\t"
+            "@q0 " MFEM_LD_F64 " %3, [%12], %15;\n\t"
+            "@q0 " MFEM_LD_F64 " %4, [%13], %15;\n\t"
+            "@q1 " MFEM_LD_F64 " %5, [%12+%18], %15;\n\t"
+            "@q1 " MFEM_LD_F64 " %6, [%13+%18], %15;\n\t"
+            "@q2 " MFEM_LD_F64 " %7, [%12+%19], %15;\n\t"
+            "@q2 " MFEM_LD_F64 " %8, [%13+%19], %15;\n\t"
+            "}"
+            : "=r"(col[0]), "=r"(col[1]), "=r"(col[2]), "=d"(a[0][0]), "=d"(a[0][1]), "=d"(a[1][0]), "=d"(a[1][1]),
+              "=d"(a[2][0]), "=d"(a[2][1])
+            : "l"(c0), "l"(c1), "l"(c2), "l"(p0), "l"(p1), "r"(rem), "l"(pol), "n"(LPR), "n"(2 * LPR), "n"(8 * LPR),
+              "n"(16 * LPR)
+            : "memory");
+    }
+};
+
+// the three gathered x loads of a chunk, again back to back
+__device__ __forceinline__ void gather3(const double *x0, const double *x1, const double *x2, uint64_t pol,
+                                        double (&xv)[3]) {
+    asm volatile(
+        "ld.global.nc.L2::cache_hint.f64 %0, [%3], %6;\n\t"
+        "ld.global.nc.L2::cache_hint.f64 %1, [%4], %6;\n\t"
+        "ld.global.nc.L2::cache_hint.f64 %2, [%5], %6;"
+        : "=d"(xv[0]), "=d"(xv[1]), "=d"(xv[2])
+        : "l"(x0), "l"(x1), "l"(x2), "l"(pol)
+        : "memory");
+}
+
 template <int N, int LPR, bool MASKED, bool DOT>
-__global__ void __launch_bounds__(kSpmvThreads)
+__global__ void __launch_bounds__(kSpmvThreads, 4)   // <= 64 registers: 32 resident warps per SM
 k_bsr_spmv(int64_t nb, const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
            const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y,
            const uint8_t *__restrict__ fixedMask, double *partials, unsigned *ticket, double *scal,
            const int *status) {
     constexpr int NN = N * N;
     constexpr int RPW = 32 / LPR;                     // rows per warp
-    constexpr int U = 3;                              // row chunks whose loads are issued together
+    constexpr int U = 3;                              // sub-chunks whose loads are issued together
+    constexpr int CH = U * LPR;                       // scalars of one scalar row per chunk
+    static_assert(CH % N == 0, "a chunk must cover whole blocks");
     if (status && status[ST_STATE] != 0) return;
     const int lane = threadIdx.x & 31;
     const int sub = lane / LPR, sl = lane % LPR;
     const int64_t warpGlobal = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nWarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int comp = owner_component<N, LPR>(sl);
+    const unsigned groupMask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (sub * LPR));
     const uint64_t polStream = l2_policy_evict_first(), polKeep = l2_policy_evict_last();
+    // lane-constant decomposition of its U scalars of a chunk into (block, component): no
+    // division inside the row loop
+    int jj[U], cc[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int f = sl + u * LPR;
+        jj[u] = f / N;
+        cc[u] = f - jj[u] * N;
+    }
     double dot = 0.0;
     // software pipeline over rows: the next row's extent is fetched while this one is computed
     int64_t row = warpGlobal * RPW + sub;
+    const int64_t rowStride = nWarps * RPW;
     int64_t nb0 = 0, nb1 = 0;
     if (row < nb) { nb0 = rowptr[row]; nb1 = rowptr[row + 1]; }
-    for (int64_t rowBase = warpGlobal * RPW; rowBase < nb; rowBase += nWarps * RPW) {
+    for (int64_t rowBase = warpGlobal * RPW; rowBase < nb; rowBase += rowStride) {
         const int64_t b0 = nb0;
         const int L = (int)(nb1 - nb0) * N;
         const int64_t thisRow = row;
-        row += nWarps * RPW;
+        row += rowStride;
         nb0 = nb1 = 0;
         if (row < nb) { nb0 = rowptr[row]; nb1 = rowptr[row + 1]; }
-        const double *v = vals + b0 * NN;
+        const double *v = vals + b0 * NN + sl;        // plane 0, this lane's first scalar
         const int32_t *ci = colidx + b0;
         double acc[N];
 #pragma unroll
         for (int r = 0; r < N; ++r) acc[r] = 0.0;
-        for (int f0 = sl; f0 < L; f0 += U * LPR) {
-            // issue every load of U chunks before the first use (memory-level parallelism)
-            int col[U], cc[U];
+        for (int base = 0; base < L; base += CH, v += CH, ci += CH / N) {
+            const int rem = L - base - sl;            // scalar f = base + sl + u*LPR is valid iff u*LPR < rem
+            int col[U];
             double a[U][N], xv[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int f = f0 + u * LPR;
-                const bool ok = f < L;
-                const int j = f / N;
-                cc[u] = f - j * N;
-                col[u] = ok ? ld_stream_s32(ci + j, polStream) : 0;
-#pragma unroll
-                for (int r = 0; r < N; ++r) a[u][r] = ok ? ld_stream_f64(v + r * L + f, polStream) : 0.0;
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) xv[u] = ld_keep_f64(x + (int64_t)col[u] * N + cc[u], polKeep);
+            ChunkLoader<N, LPR>::run(ci + jj[0], ci + jj[1], ci + jj[2], v, v + L, v + 2 * L, rem, polStream, col, a);
+            // ptxas would otherwise hoist the dependent gather (and the FMAs behind it) in between the
+            // streaming loads; with in-order issue that stalls the warp before most loads are out.
+            // A warp-level barrier is a scheduling fence for memory instructions.
+            __syncwarp(groupMask);
+            gather3(x + (col[0] * N + cc[0]), x + (col[1] * N + cc[1]), x + (col[2] * N + cc[2]), polKeep, xv);
+            __syncwarp(groupMask);
 #pragma unroll
             for (int u = 0; u < U; ++u)
 #pragma unroll

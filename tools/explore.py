@@ -30,6 +30,7 @@ def run(grid, deg, mat, rtols, direct=False, reorder=1):
         V, T = orc.grid_simplices(list(grid))
         sim = orc.Simulator(3, deg, V, T); sim.set_material(D)
         t = time.time(); K = sim.stiffness(); uref = orc.solve_fixed(K, f.reshape(-1), fixed, vals); out["direct_s"] = round(time.time() - t, 2)
+    h.set_option("spmv_lanes", int(os.environ.get("SPMV_LANES", "0")))
     for rtol in rtols:
         u, info = h.solve(f, rtol=rtol, return_info=True)
         rec = dict(rtol=rtol, iters=info[0]["iterations"], solve_s=round(info[0]["seconds"], 4), relres=info[0]["rel_residual"])
