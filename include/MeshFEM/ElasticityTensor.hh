@@ -1,0 +1,130 @@
+// Rank-4 elasticity tensor stored as the symmetric flattened "D" matrix (mirrors the used part
+// of ElasticityTensor.hh: setIsotropic :100-134, setOrthotropic3D/2D :136-164, operator() :274-277,
+// inverse :315-323, doubleContract :435-447).  Small dense inverse by Gauss-Jordan (Eigen is not
+// available offline).
+#ifndef MESHFEM_B200_ELASTICITYTENSOR_HH
+#define MESHFEM_B200_ELASTICITYTENSOR_HH
+#include <MeshFEM/SymmetricMatrix.hh>
+
+#include <cmath>
+#include <iomanip>
+#include <ostream>
+
+namespace tensor_detail {
+template <size_t F>
+inline void invertInPlace(Real (&A)[F][F]) {
+    Real I[F][F];
+    for (size_t i = 0; i < F; ++i) for (size_t j = 0; j < F; ++j) I[i][j] = (i == j);
+    for (size_t c = 0; c < F; ++c) {
+        size_t piv = c;
+        for (size_t r = c + 1; r < F; ++r) if (std::abs(A[r][c]) > std::abs(A[piv][c])) piv = r;
+        if (A[piv][c] == 0.0) throw std::runtime_error("Singular tensor matrix");
+        if (piv != c) for (size_t j = 0; j < F; ++j) { std::swap(A[piv][j], A[c][j]); std::swap(I[piv][j], I[c][j]); }
+        const Real d = A[c][c];
+        for (size_t j = 0; j < F; ++j) { A[c][j] /= d; I[c][j] /= d; }
+        for (size_t r = 0; r < F; ++r) {
+            if (r == c) continue;
+            const Real f = A[r][c];
+            if (f == 0.0) continue;
+            for (size_t j = 0; j < F; ++j) { A[r][j] -= f * A[c][j]; I[r][j] -= f * I[c][j]; }
+        }
+    }
+    for (size_t i = 0; i < F; ++i) for (size_t j = 0; j < F; ++j) A[i][j] = I[i][j];
+}
+}  // namespace tensor_detail
+
+template <typename _Real, size_t _Dim>
+class ElasticityTensor {
+public:
+    static constexpr size_t Dim = _Dim;
+    static constexpr size_t F = flatLen(_Dim);
+    typedef SymmetricMatrixValue<_Real, _Dim> SMatrix;
+
+    ElasticityTensor() { clear(); }
+    ElasticityTensor(_Real E, _Real nu) { setIsotropic(E, nu); }
+    void clear() { for (auto &r : m_d) for (auto &x : r) x = 0; }
+    void setIdentity() { setIsotropicLame(0, 0.5); }
+
+    void setIsotropic(_Real E, _Real nu) {
+        _Real lambda = (nu * E) / ((1.0 + nu) * (1.0 - 2.0 * nu));
+        const _Real mu = E / (2.0 + 2.0 * nu);
+        if (_Dim == 2) lambda = (nu * E) / (1.0 - nu * nu);   // plane stress (:111-112)
+        setIsotropicLame(lambda, mu);
+    }
+    void setIsotropicLame(_Real lambda, _Real mu) {
+        clear();
+        for (size_t i = 0; i < _Dim; ++i) for (size_t j = 0; j < _Dim; ++j) m_d[i][j] = lambda + (i == j ? 2 * mu : 0.0);
+        for (size_t i = _Dim; i < F; ++i) m_d[i][i] = mu;
+    }
+    void setOrthotropic3D(_Real Ex, _Real Ey, _Real Ez, _Real nuYX, _Real nuZX, _Real nuZY, _Real muYZ, _Real muZX,
+                          _Real muXY) {
+        if (_Dim != 3) throw std::runtime_error("setOrthotropic3D call on non-3D tensor");
+        clear();
+        m_d[0][0] = 1.0 / Ex; m_d[0][1] = -nuYX / Ey; m_d[0][2] = -nuZX / Ez;
+        m_d[1][1] = 1.0 / Ey; m_d[1][2] = -nuZY / Ez;
+        m_d[2][2] = 1.0 / Ez;
+        m_d[3][3] = 1.0 / muYZ; m_d[4][4] = 1.0 / muZX; m_d[5][5] = 1.0 / muXY;
+        m_symmetrizeFromUpper();
+        tensor_detail::invertInPlace<F>(m_d);
+    }
+    void setOrthotropic2D(_Real Ex, _Real Ey, _Real nuYX, _Real muXY) {
+        if (_Dim != 2) throw std::runtime_error("setOrthotropic2D call on non-2D tensor");
+        clear();
+        m_d[0][0] = 1.0 / Ex; m_d[0][1] = -nuYX / Ey;
+        m_d[1][1] = 1.0 / Ey;
+        m_d[2][2] = 1.0 / muXY;
+        m_symmetrizeFromUpper();
+        tensor_detail::invertInPlace<F>(m_d);
+    }
+
+    _Real operator()(size_t i, size_t j, size_t k, size_t l) const { return D(flattenIndices<_Dim>(i, j), flattenIndices<_Dim>(k, l)); }
+    _Real D(size_t i, size_t j) const { return (i <= j) ? m_d[i][j] : m_d[j][i]; }
+    _Real &D(size_t i, size_t j) { return (i <= j) ? m_d[i][j] : m_d[j][i]; }
+    // full symmetric flattened matrix, row-major (what mfem_b200_set_material_* takes)
+    void getFlat(_Real *out) const { for (size_t i = 0; i < F; ++i) for (size_t j = 0; j < F; ++j) out[i * F + j] = D(i, j); }
+    void setFlat(const _Real *in) { for (size_t i = 0; i < F; ++i) for (size_t j = 0; j < F; ++j) m_d[i][j] = in[i * F + j]; m_symmetrizeFromUpper(); }
+
+    // D * shearDoubled(strain)  (:435-447)
+    SMatrix doubleContract(const SMatrix &in) const {
+        SMatrix out;
+        for (size_t i = 0; i < F; ++i) {
+            _Real s = 0;
+            for (size_t j = 0; j < F; ++j) s += D(i, j) * (j >= _Dim ? 2.0 : 1.0) * in[j];
+            out[i] = s;
+        }
+        return out;
+    }
+    // E^-1 with E : E^-1 = identity: invert D, then halve shear rows and columns (:315-323)
+    ElasticityTensor inverse() const {
+        ElasticityTensor r;
+        for (size_t i = 0; i < F; ++i) for (size_t j = 0; j < F; ++j) r.m_d[i][j] = D(i, j);
+        tensor_detail::invertInPlace<F>(r.m_d);
+        for (size_t i = 0; i < F; ++i) for (size_t j = 0; j < F; ++j) {
+            if (i >= _Dim) r.m_d[i][j] *= 0.5;
+            if (j >= _Dim) r.m_d[i][j] *= 0.5;
+        }
+        return r;
+    }
+    ElasticityTensor &operator+=(const ElasticityTensor &b) { for (size_t i = 0; i < F; ++i) for (size_t j = 0; j < F; ++j) m_d[i][j] += b.m_d[i][j]; return *this; }
+    ElasticityTensor &operator*=(_Real s) { for (auto &r : m_d) for (auto &x : r) x *= s; return *this; }
+    ElasticityTensor &operator/=(_Real s) { return (*this) *= (1.0 / s); }
+    friend ElasticityTensor operator*(ElasticityTensor a, _Real s) { return a *= s; }
+    // row i of D viewed as a flattened symmetric matrix (DRowAsSymMatrix)
+    void addToRow(size_t i, const SMatrix &m) { for (size_t j = 0; j < F; ++j) m_d[i][j] += m[j]; }
+    void symmetrizeFromFull() { for (size_t i = 0; i < F; ++i) for (size_t j = i + 1; j < F; ++j) m_d[j][i] = m_d[i][j]; }
+    _Real frobeniusNormSq() const { _Real s = 0; for (size_t i = 0; i < F; ++i) for (size_t j = 0; j < F; ++j) s += D(i, j) * D(i, j); return s; }
+
+    // Isotropic-equivalent moduli read off a compliance-like inverse (PeriodicHomogenization_cli.cc:126-171)
+    friend std::ostream &operator<<(std::ostream &os, const ElasticityTensor &E) {
+        for (size_t i = 0; i < F; ++i) {
+            for (size_t j = 0; j < F; ++j) os << (j ? "\t" : "") << E.D(i, j);
+            os << std::endl;
+        }
+        return os;
+    }
+
+private:
+    _Real m_d[F][F];
+    void m_symmetrizeFromUpper() { for (size_t i = 0; i < F; ++i) for (size_t j = i + 1; j < F; ++j) m_d[j][i] = m_d[i][j]; }
+};
+#endif

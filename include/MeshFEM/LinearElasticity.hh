@@ -1,0 +1,512 @@
+// LinearElasticity::Simulator -- the reference's operator facade (LinearElasticity.hh:434-1659)
+// kept name-for-name for the assemble-and-solve path, with the hot path re-routed through the
+// C ABI of libmfem_b200 (include/mfem_b200.h):
+//   constructor negative-volume check, m_assembleStiffnessMatrix, SPSDSystem fixVariables/solve,
+//   constantStrainLoad, averageStrainField/averageStressField, applyStiffnessMatrix
+// run on the GPU; boundary-condition bookkeeping (O(boundary) work) stays on the host exactly
+// as in the reference: applyBoundaryConditions :881-1027, applyTranslationPins :1095-1111,
+// analyzeDirichletPosedness :1169-1190, assembleConstrainedSystem :1201-1249,
+// m_getDirichletVarsAndValues :1469-1518, m_pinNode :1595-1618, neumannLoad :703-717.
+//
+// Systems that need Lagrange-multiplier rows (no_rigid_motion without periodicity, or an
+// unconstrained translation without the pin option) are indefinite KKT systems; the reference
+// needs UMFPACK for them (off by default, LUFactorizerStub throws).  They throw here too.
+#ifndef MESHFEM_B200_LINEARELASTICITY_HH
+#define MESHFEM_B200_LINEARELASTICITY_HH
+#include <MeshFEM/BoundaryConditions.hh>
+#include <MeshFEM/FEMMesh.hh>
+#include <MeshFEM/Fields.hh>
+#include <MeshFEM/GlobalBenchmark.hh>
+#include <MeshFEM/Materials.hh>
+#include <MeshFEM/SparseMatrices.hh>
+
+#include <iostream>
+#include <memory>
+
+namespace LinearElasticity {
+
+template <size_t _N>
+struct ETensorStoreGetter {
+    typedef ElasticityTensor<Real, _N> ETensor;
+    ETensorStoreGetter(const ETensor &E) : m_E(E) {}
+    ETensorStoreGetter() : m_E(1, 0) {}
+    const ETensor &operator()() const { return m_E; }
+    ETensor &operator()() { return m_E; }
+private:
+    ETensor m_E;
+};
+
+template <size_t _K, size_t _Deg> using Mesh = FEMMesh<_K, _Deg, VectorND<_K>>;
+
+template <class _Mesh>
+class Simulator {
+public:
+    typedef _Mesh Mesh;
+    static constexpr size_t N = _Mesh::K;
+    static constexpr size_t K = _Mesh::K;
+    static constexpr size_t Degree = _Mesh::Deg;
+    typedef VectorND<N> Point;
+    typedef ScalarField<Real> SField;
+    typedef VectorField<Real, N> VField;
+    typedef ElasticityTensor<Real, N> ETensor;
+    typedef SymmetricMatrixValue<Real, N> SMatrix;
+    typedef SymmetricMatrixField<Real, N> SMField;
+    typedef TripletMatrix<Triplet<Real>> TMatrix;
+
+    struct BoundaryNodeData {
+        ComponentMask dirichletComponents;
+        Point dirichletDisplacement;
+        size_t dirichletRegionIdx = 0;
+        bool hasDirichlet() const { return dirichletComponents.hasAny(N); }
+        void setDirichlet(ComponentMask mask, const Point &val) {       // :392-406
+            for (size_t c = 0; c < N; ++c) {
+                if (!mask.has(c)) continue;
+                if (!dirichletComponents.has(c)) { dirichletComponents.set(c); dirichletDisplacement[c] = val[c]; }
+                else if (std::abs(dirichletDisplacement[c] - val[c]) > 1e-10)
+                    throw std::runtime_error("Conflicting dirichlet displacements.");
+            }
+        }
+        void setDirichletRegion(size_t idx) {
+            if (dirichletRegionIdx != 0 && dirichletRegionIdx != idx)
+                std::cerr << "WARNING: region traction currently unsupported for vertices belonging to multiple regions" << std::endl;
+            dirichletRegionIdx = idx;
+        }
+    };
+    struct BoundaryElementData {
+        Point neumannTraction;
+        bool isInternal = false;
+    };
+
+    // device >= 0: CUDA device of the handle.  device < 0: host-only mode (no handle is created;
+    // boundary-condition bookkeeping, loads and fixed-variable lists work, everything that needs
+    // the GPU throws) -- used by the CPU unit tests of the host logic.
+    template <class Elements, class Vertices>
+    Simulator(const Elements &elems, const Vertices &vertices, int device = 0)
+        : m_useRigidMotionConstraint(false), m_useNRTPinConstraint(false), m_hostOnly(device < 0), m_mesh(elems, vertices) {
+        m_system.setDevice(device);
+        m_bnData.resize(m_mesh.numBoundaryNodes());
+        m_beData.resize(m_mesh.numBoundaryElements());
+        m_uploadMesh();          // throws "Mesh has negatively oriented elements." (:465-472)
+        setMaterial(Materials::Constant<N>().getTensor());
+    }
+
+    const _Mesh &mesh() const { return m_mesh; }
+    _Mesh &mesh() { return m_mesh; }
+
+    // ---- material (element(i)->configure(store) in Simulate_cli.cc:104-175)
+    void setMaterial(const ETensor &E) {
+        m_E = E;
+        m_perElementE.clear();
+        if (m_hostOnly) return;
+        Real D[ETensor::F * ETensor::F];
+        E.getFlat(D);
+        mfemCheck(h(), mfem_b200_set_material_constant(h(), D));
+        m_system.clear();
+    }
+    void setPerElementMaterial(const std::vector<ETensor> &Es) {
+        if (Es.size() != m_mesh.numElements()) throw std::runtime_error("Material parameter fields of incorrect size.");
+        m_perElementE = Es;
+        if (m_hostOnly) return;
+        std::vector<Real> D(Es.size() * ETensor::F * ETensor::F);
+        for (size_t e = 0; e < Es.size(); ++e) Es[e].getFlat(&D[e * ETensor::F * ETensor::F]);
+        mfemCheck(h(), mfem_b200_set_material_per_element(h(), D.data()));
+        m_system.clear();
+    }
+    const ETensor &elementTensor(size_t e) const { return m_perElementE.empty() ? m_E : m_perElementE[e]; }
+
+    // ---- solve (:479-487, 657)
+    VField solve(const VField &f) const {
+        if (!m_system.isSet()) m_buildConstrainedSystem();
+        BENCHMARK_START_TIMER_SECTION("Elasticity Solve");
+        std::vector<Real> x;
+        m_system.solve(f.data(), x);
+        BENCHMARK_STOP_TIMER_SECTION("Elasticity Solve");
+        return dofToNodeField(x);
+    }
+    VField solve() const { return solve(neumannLoad()); }
+    void setSolverTolerance(double rtol, int maxIters = 200000) { m_system.setTolerance(rtol, maxIters); }
+    const mfem_b200_solve_info &lastSolveInfo() const { return m_system.lastSolveInfo(); }
+
+    // ---- fields
+    SMField averageStrainField(const VField &u) const {      // :528-537
+        SMField s(m_mesh.numElements());
+        mfemCheck(h(), mfem_b200_avg_strain_stress(h(), u.data().data(), s.data().data(), nullptr));
+        return s;
+    }
+    SMField averageStressField(const VField &u) const {      // :540-549
+        SMField s(m_mesh.numElements());
+        mfemCheck(h(), mfem_b200_avg_strain_stress(h(), u.data().data(), nullptr, s.data().data()));
+        return s;
+    }
+    template <class _SymMat>
+    VField constantStrainLoad(const _SymMat &strain) const {  // :551-562
+        VField load(numDoFs());
+        mfemCheck(h(), mfem_b200_const_strain_load(h(), strain.flattened().data(), load.data().data()));
+        return load;
+    }
+    VField applyStiffnessMatrix(const VField &u) const {      // :801-823
+        VField load(m_mesh.numNodes());
+        mfemCheck(h(), mfem_b200_apply_K(h(), u.data().data(), load.data().data()));
+        return load;
+    }
+    template <class _Vec>
+    VField dofToNodeField(const _Vec &x) const {              // :665-677
+        VField f(m_mesh.numNodes());
+        for (size_t i = 0; i < m_mesh.numNodes(); ++i) {
+            const size_t d = DoF(i);
+            for (size_t c = 0; c < N; ++c) f[N * i + c] = x[N * d + c];
+        }
+        return f;
+    }
+    VField nodeToVertexField(const VField &x) const {
+        VField f(m_mesh.numVertices());
+        for (size_t i = 0; i < m_mesh.numVertices(); ++i) for (size_t c = 0; c < N; ++c) f[N * i + c] = x[N * i + c];
+        return f;
+    }
+
+    // Neumann load on the DoFs (:703-717) with BoundaryElement::nodalNeumannLoad (:341-347):
+    // int phi_n over a boundary element = A/K per vertex (deg 1); deg 2: faces 0 at vertices and
+    // A/3 at edge nodes, edges L/6, L/6, 4L/6 (Functions.hh:247-274).
+    VField neumannLoad() const {
+        VField load(numDoFs());
+        constexpr size_t npbe = _Mesh::nodesPerBoundaryElement;
+        Real w[npbe];
+        if (Degree == 1) for (size_t n = 0; n < npbe; ++n) w[n] = 1.0 / K;
+        else if (K == 3) { for (size_t n = 0; n < 3; ++n) { w[n] = 0.0; w[3 + n] = 1.0 / 3.0; } }
+        else { w[0] = w[1] = 1.0 / 6.0; w[2] = 4.0 / 6.0; }
+        for (size_t be = 0; be < m_mesh.numBoundaryElements(); ++be)
+            for (size_t n = 0; n < npbe; ++n)
+                load.add(DoF(m_mesh.boundaryElementVolumeNode(be, n)), (w[n] * m_mesh.boundaryElementVolume(be)) * m_beData[be].neumannTraction);
+        for (const auto &ndf : m_nodalDeltaFunctionForces) load.add(DoF(ndf.first), ndf.second);
+        return load;
+    }
+
+    bool usingReducedDoFs() const { return m_dofForNode.size() == m_mesh.numNodes(); }
+    size_t numDoFs() const { return usingReducedDoFs() ? m_numDoFs : m_mesh.numNodes(); }
+    size_t DoF(size_t node) const { return usingReducedDoFs() ? m_dofForNode[node] : node; }
+
+    // ---- periodic conditions (:845-854, 874-879)
+    void applyPeriodicConditions(Real epsilon = 1e-7, bool ignoreMismatch = false, std::unique_ptr<PeriodicCondition<N>> pc = nullptr) {
+        m_system.clear();
+        if (!pc) pc.reset(new PeriodicCondition<N>(m_mesh, epsilon, ignoreMismatch));
+        m_dofForNode = pc->periodicDoFsForNodes();
+        m_numDoFs = pc->numPeriodicDoFs();
+        for (size_t i = 0; i < m_mesh.numBoundaryElements(); ++i) m_beData[i].isInternal = pc->isPeriodicBE(i);
+        m_uploadMesh();
+    }
+    void removePeriodicConditions() {
+        m_system.clear();
+        m_dofForNode.clear();
+        for (auto &be : m_beData) be.isInternal = false;
+        m_uploadMesh();
+    }
+    bool isInternalBoundaryElement(size_t be) const { return m_beData[be].isInternal; }
+
+    // ---- boundary conditions (:881-1027)
+    void applyBoundaryConditions(const std::vector<CondPtr<N>> &conds) {
+        ExpressionEnvironment env;
+        const auto &mbb = m_mesh.boundingBox();
+        env.setVectorValue("mesh_size_", mbb.dimensions());
+        env.setVectorValue("mesh_min_", mbb.minCorner);
+        env.setVectorValue("mesh_max_", mbb.maxCorner);
+        size_t dirichletRegionIdx = 0;
+        if (conds.size() > 0) m_system.clear();
+        for (const auto &cond : conds) {
+            env.setVectorValue("region_size_", cond->region->dimensions());
+            env.setVectorValue("region_min_", cond->region->minCorner);
+            env.setVectorValue("region_max_", cond->region->maxCorner);
+            if (auto nc = dynamic_cast<const NeumannCondition<N> *>(cond.get())) {
+                Real regionArea = 0.0;
+                std::vector<size_t> region;
+                for (size_t be = 0; be < m_mesh.numBoundaryElements(); ++be) {
+                    Point center;
+                    for (size_t c = 0; c < K; ++c) center += m_mesh.nodePosition(m_mesh.boundaryElementVolumeVertex(be, c));
+                    center /= Real(K);
+                    if (nc->containsPoint(center)) {
+                        env.setXYZ(center);
+                        regionArea += m_mesh.boundaryElementVolume(be);
+                        region.push_back(be);
+                        if (nc->type == NeumannType::Pressure) m_beData[be].neumannTraction = -nc->pressure(env) * m_mesh.boundaryElementNormal(be);
+                        else m_beData[be].neumannTraction = nc->traction(env);
+                    }
+                }
+                if (region.size() == 0) throw std::runtime_error("Neumann region unmatched");
+                if (nc->type == NeumannType::Force)
+                    for (size_t bei : region) m_beData[bei].neumannTraction /= regionArea;
+            } else if (dynamic_cast<const TargetCondition<N> *>(cond.get()) || dynamic_cast<const TargetNodesCondition<N> *>(cond.get())) {
+                std::cerr << "WARNING: ignoring target boundary conditions." << std::endl;
+            } else if (auto dc = dynamic_cast<const DirichletCondition<N> *>(cond.get())) {
+                ++dirichletRegionIdx;
+                for (size_t bn = 0; bn < m_mesh.numBoundaryNodes(); ++bn) {
+                    const Point p = m_mesh.nodePosition(m_mesh.volumeNodeForBoundaryNode(bn));
+                    if (dc->containsPoint(p)) {
+                        env.setXYZ(p);
+                        m_bnData[bn].setDirichlet(dc->componentMask, dc->displacement(env));
+                        m_bnData[bn].setDirichletRegion(dirichletRegionIdx);
+                    }
+                }
+            } else if (auto dec = dynamic_cast<const DirichletElementsCondition<N> *>(cond.get())) {
+                ++dirichletRegionIdx;
+                for (size_t be = 0; be < m_mesh.numBoundaryElements(); ++be) {
+                    IVectorND<N> idx;
+                    for (size_t c = 0; c < K; ++c) idx[c] = m_mesh.boundaryElementVolumeVertex(be, c);
+                    if (dec->containsElement(idx)) {
+                        for (size_t n = 0; n < _Mesh::nodesPerBoundaryElement; ++n) {
+                            const int vn = m_mesh.boundaryElementVolumeNode(be, n);
+                            env.setXYZ(m_mesh.nodePosition(vn));
+                            auto &bnd = m_bnData[m_mesh.boundaryNodeForVolumeNode(vn)];
+                            bnd.setDirichlet(dec->componentMask, dec->displacement(env));
+                            bnd.setDirichletRegion(dirichletRegionIdx);
+                        }
+                    }
+                }
+            } else if (auto nec = dynamic_cast<const NeumannElementsCondition<N> *>(cond.get())) {
+                size_t numSet = 0;
+                Real regionArea = 0.0;
+                std::vector<size_t> forceRegion;
+                for (size_t be = 0; be < m_mesh.numBoundaryElements(); ++be) {
+                    UnorderedTriplet elem(m_mesh.boundaryElementVolumeVertex(be, 0), m_mesh.boundaryElementVolumeVertex(be, 1),
+                                          (N == 3) ? m_mesh.boundaryElementVolumeVertex(be, 2) : 0);
+                    if (nec->hasValueForElement(elem)) {
+                        const auto &val = nec->getValue(elem);
+                        if (val.type == NeumannType::Pressure) m_beData[be].neumannTraction = -val.pressure() * m_mesh.boundaryElementNormal(be);
+                        else if (val.type == NeumannType::Traction) m_beData[be].neumannTraction = val.traction();
+                        else { m_beData[be].neumannTraction = val.force(); regionArea += m_mesh.boundaryElementVolume(be); forceRegion.push_back(be); }
+                        ++numSet;
+                    }
+                }
+                if (numSet != nec->numElements()) throw std::runtime_error("Some element boundary conditions weren't matched.");
+                for (size_t bei : forceRegion) m_beData[bei].neumannTraction /= regionArea;
+            } else if (auto dnc = dynamic_cast<const DirichletNodesCondition<N> *>(cond.get())) {
+                std::cerr << "WARNING: dirichlet region index currently not set for DirichletNodesCondition; region force printout will be inaccurate." << std::endl;
+                for (size_t i = 0; i < dnc->indices.size(); ++i) {
+                    const size_t ni = dnc->indices[i];
+                    const int bn = ni < m_mesh.numNodes() ? m_mesh.boundaryNodeForVolumeNode(ni) : -1;
+                    if (bn < 0) throw std::runtime_error("Condition applied to non-boundary node " + std::to_string(ni));
+                    m_bnData[bn].setDirichlet(dnc->componentMask, dnc->displacements[i]);
+                }
+            } else if (auto fc = dynamic_cast<const DeltaForceCondition<N> *>(cond.get())) {
+                for (size_t n = 0; n < m_mesh.numNodes(); ++n) {
+                    const Point p = m_mesh.nodePosition(n);
+                    if (fc->containsPoint(p)) { env.setXYZ(p); m_nodalDeltaFunctionForces.emplace_back(n, fc->force(env)); }
+                }
+            } else if (auto fnc = dynamic_cast<const DeltaForceNodesCondition<N> *>(cond.get())) {
+                for (size_t i = 0; i < fnc->indices.size(); ++i) {
+                    const size_t ni = fnc->indices[i];
+                    if (ni >= m_mesh.numNodes()) throw std::runtime_error("DeltaForceNodesCondition node index out of bounds: " + std::to_string(ni));
+                    m_nodalDeltaFunctionForces.emplace_back(ni, fnc->forces[i]);
+                }
+            } else throw std::runtime_error("Illegal BC type");
+        }
+    }
+
+    void removeDirichletConditions() {
+        int removeCount = 0;
+        for (auto &bn : m_bnData) if (bn.hasDirichlet()) { bn.dirichletComponents.clear(); ++removeCount; }
+        if (removeCount > 0) m_system.clear();
+    }
+    void removeNeumanConditions() { for (auto &be : m_beData) be.neumannTraction = Point::Zero(); }
+    void removeAllBoundaryConditions() { removeNeumanConditions(); removeDirichletConditions(); }
+
+    void applyNoRigidMotionConstraint() {                     // :1052-1059
+        if (!m_useRigidMotionConstraint) { m_system.clear(); m_useRigidMotionConstraint = true; }
+    }
+    void setUsePinNoRigidTranslationConstraint(bool use) { m_useNRTPinConstraint = use; }
+    void removeNoRigidMotionConstraint() { if (m_useRigidMotionConstraint) { m_system.clear(); m_useRigidMotionConstraint = false; } }
+
+    void applyPeriodicPairDirichletConditions(std::vector<PeriodicPairDirichletCondition<N>> &pps) {   // :1087-1093
+        for (auto &pp : pps) {
+            std::pair<size_t, size_t> p = pp.pair(m_mesh);
+            m_bnData[p.first].setDirichlet(pp.component(), Point::Zero());
+            m_bnData[p.second].setDirichlet(pp.component(), Point::Zero());
+        }
+        if (!pps.empty()) m_system.clear();
+    }
+
+    void applyTranslationPins(const ComponentMask &c) {      // :1095-1111
+        for (size_t d = 0; d < N; ++d) {
+            if (!c.has(d)) continue;
+            size_t bnMin = 0;
+            for (size_t bn = 0; bn < m_mesh.numBoundaryNodes(); ++bn)
+                if (m_mesh.nodePosition(m_mesh.volumeNodeForBoundaryNode(bn))[d] < m_mesh.nodePosition(m_mesh.volumeNodeForBoundaryNode(bnMin))[d]) bnMin = bn;
+            ComponentMask dmask;
+            dmask.set(d);
+            m_bnData[bnMin].setDirichlet(dmask, Point::Zero());
+            m_system.clear();
+        }
+    }
+
+    void analyzeDirichletPosedness(ComponentMask &needsTranslations, ComponentMask &needsRotations) const {   // :1169-1190
+        needsTranslations.set();
+        size_t totalConstrained = 0;
+        for (const auto &bn : m_bnData)
+            for (size_t c = 0; c < N; ++c)
+                if (bn.dirichletComponents.has(c)) { ++totalConstrained; needsTranslations.clear(c); }
+        needsRotations.clear();
+        if (totalConstrained == 0) needsRotations.set();
+        else if (needsTranslations.hasAny(N) || (totalConstrained < ((N == 2) ? 3 : 6))) {
+            std::cerr << "WARNING: analysis of partial Dirichlet rotational posedness not yet implemented!" << std::endl;
+            std::cerr << "Unconstrained translation components: " << needsTranslations.componentString() << std::endl;
+        }
+    }
+
+    // The constraint half of assembleConstrainedSystem (:1201-1249): which scalar variables
+    // are fixed and to what.  Configurations that would need Lagrange rows throw.
+    void getFixedVariables(std::vector<size_t> &fixedVars, std::vector<Real> &fixedVarValues, bool allowIllPosed = false) const {
+        fixedVars.clear(), fixedVarValues.clear();
+        if (m_useRigidMotionConstraint) {
+            // rotation rows are skipped entirely under periodicity (:1539-1542)
+            const bool rotationsSkipped = ((N == 2) && (numDoFs() < m_mesh.numNodes())) || (numDoFs() + 1 < m_mesh.numNodes());
+            if (!rotationsSkipped || !m_useNRTPinConstraint)
+                throw std::runtime_error("no_rigid_motion without periodic conditions needs Lagrange-multiplier rows (indefinite KKT system; "
+                                         "the reference requires UMFPACK for it) -- not on the SPD assemble-and-solve path");
+            m_pinNode(fixedVars, fixedVarValues);
+        } else if (!allowIllPosed) {
+            ComponentMask needsTranslations, needsRotations;
+            analyzeDirichletPosedness(needsTranslations, needsRotations);
+            if (needsTranslations.hasAny(N)) {
+                if (m_useNRTPinConstraint) m_pinNode(fixedVars, fixedVarValues, needsTranslations);
+                else throw std::runtime_error("unconstrained translation components need a Lagrange-multiplier row (indefinite KKT system); "
+                                              "call setUsePinNoRigidTranslationConstraint(true) or add Dirichlet conditions");
+            }
+            if (needsRotations.hasAny(N)) throw std::runtime_error("Unimplemented");
+        }
+        m_getDirichletVarsAndValues(fixedVars, fixedVarValues);
+    }
+
+    void reportRegionSurfaceForces(const VField &u) const {  // :1251-1270
+        VField f = applyStiffnessMatrix(u);
+        std::vector<Point> forces;
+        for (size_t bni = 0; bni < m_mesh.numBoundaryNodes(); ++bni) {
+            const size_t ri = m_bnData[bni].dirichletRegionIdx;
+            if (ri + 1 > forces.size()) forces.resize(ri + 1, Point::Zero());
+            forces[ri] += f(m_mesh.volumeNodeForBoundaryNode(bni));
+        }
+        for (size_t i = 0; i < forces.size(); ++i) {
+            std::cout << "region " << i << " force:";
+            for (size_t j = 0; j < N; ++j) std::cout << "\t" << forces[i][j];
+            std::cout << std::endl;
+        }
+    }
+
+    void dumpSystem(const std::string &path) const {         // :1272-1277
+        if (!m_system.isSet()) m_buildConstrainedSystem();
+        m_system.sumAndDumpUpper(path);
+    }
+
+    // Build *upper triangle* of the stiffness matrix as triplets (:1406-1466) -- assembled on the
+    // device, exported through the ABI (parity checks and --dumpMatrix).
+    void m_assembleStiffnessMatrix(TMatrix &Ktrip) const {
+        mfemCheck(h(), mfem_b200_assemble(h()));
+        int64_t nb = 0, nnzb = 0;
+        mfemCheck(h(), mfem_b200_get_bsr_sizes(h(), &nb, &nnzb));
+        std::vector<int64_t> rp((size_t)nb + 1);
+        std::vector<int32_t> ci((size_t)nnzb);
+        std::vector<Real> v((size_t)nnzb * N * N);
+        mfemCheck(h(), mfem_b200_get_bsr(h(), rp.data(), ci.data(), v.data()));
+        Ktrip.init(N * numDoFs(), N * numDoFs());
+        for (int64_t bi = 0; bi < nb; ++bi)
+            for (int64_t k = rp[bi]; k < rp[bi + 1]; ++k)
+                for (size_t r = 0; r < N; ++r)
+                    for (size_t c = 0; c < N; ++c) {
+                        const size_t row = N * bi + r, col = N * ci[k] + c;
+                        if (row <= col) Ktrip.addNZ(row, col, v[(size_t)k * N * N + r * N + c]);
+                    }
+    }
+
+    mfem_b200_handle deviceHandle() const { return h(); }
+
+private:
+    mfem_b200_handle h() const {
+        if (m_hostOnly) throw std::runtime_error("Simulator was constructed in host-only mode (device < 0): no GPU operations available");
+        return m_system.handle();
+    }
+
+    void m_uploadMesh() {
+        if (m_hostOnly) return;
+        std::vector<int64_t> dof;
+        if (usingReducedDoFs()) dof.assign(m_dofForNode.begin(), m_dofForNode.end());
+        const int st = mfem_b200_set_mesh(h(), (int)N, (int)Degree, (int64_t)m_mesh.numNodes(), m_mesh.nodePositions().data(),
+                                          (int64_t)m_mesh.numElements(), m_mesh.elementNodes().data(),
+                                          dof.empty() ? nullptr : dof.data(), (int64_t)numDoFs());
+        if (st == MFEM_B200_ERR_NEG_VOLUME) {
+            std::cerr << mfem_b200_last_error(h()) << std::endl;
+            throw std::runtime_error("Mesh has negatively oriented elements.\nCorrect with: mesh_convert --reorientNegativeElements.");
+        }
+        mfemCheck(h(), st);
+        if (m_haveMaterialOnDevice) {
+            if (m_perElementE.empty()) setMaterial(m_E); else setPerElementMaterial(std::vector<ETensor>(m_perElementE));
+        }
+        m_haveMaterialOnDevice = true;
+    }
+
+    void m_buildConstrainedSystem() const {                  // :1377-1404
+        std::vector<size_t> fixedVars;
+        std::vector<Real> fixedVarValues;
+        BENCHMARK_START_TIMER("Assemble System");
+        getFixedVariables(fixedVars, fixedVarValues);
+        BENCHMARK_STOP_TIMER("Assemble System");
+        mfemCheck(h(), mfem_b200_clear_fixed_variables(h()));
+        m_system.setAssembled(N * numDoFs());
+        BENCHMARK_START_TIMER_SECTION("Fix Variables");
+        m_system.fixVariables(fixedVars, fixedVarValues);
+        BENCHMARK_STOP_TIMER_SECTION("Fix Variables");
+        m_system.setEconomyMode(true);
+    }
+
+    void m_getDirichletVarsAndValues(std::vector<size_t> &dirichletVars, std::vector<Real> &dirichletValues) const {   // :1469-1518
+        std::vector<Point> constraintDisplacements;
+        std::vector<size_t> constraintDoFs;
+        std::vector<ComponentMask> constraintComponents;
+        std::vector<int> constraintIndex(numDoFs(), -1);
+        for (size_t i = 0; i < m_mesh.numBoundaryNodes(); ++i) {
+            const auto &bn = m_bnData[i];
+            if (!bn.hasDirichlet()) continue;
+            const size_t dof = DoF(m_mesh.volumeNodeForBoundaryNode(i));
+            if (constraintIndex[dof] < 0) {
+                constraintIndex[dof] = (int)constraintDoFs.size();
+                constraintDoFs.push_back(dof);
+                constraintDisplacements.push_back(bn.dirichletDisplacement);
+                constraintComponents.push_back(bn.dirichletComponents);
+            } else {
+                std::cerr << "WARNING: Dirichlet condition on periodic boundary applies to all identified nodes." << std::endl;
+                const auto diff = bn.dirichletDisplacement - constraintDisplacements[constraintIndex[dof]];
+                const bool cdiffer = (bn.dirichletComponents != constraintComponents[constraintIndex[dof]]);
+                if ((diff.norm() > 1e-10) || cdiffer) throw std::runtime_error("Mismatched Dirichlet constraint on periodic DoF");
+            }
+        }
+        for (size_t i = 0; i < constraintDoFs.size(); ++i)
+            for (size_t c = 0; c < N; ++c) {
+                if (!constraintComponents[i].has(c)) continue;
+                dirichletVars.push_back(N * constraintDoFs[i] + c);
+                dirichletValues.push_back(constraintDisplacements[i][c]);
+            }
+    }
+
+    void m_pinNode(std::vector<size_t> &fixedVars, std::vector<Real> &fixedVarValues,
+                   const ComponentMask &components = ComponentMask("xyz")) const {   // :1595-1618
+        size_t nodeToPin = m_mesh.numNodes();
+        for (size_t i = 0; i < m_mesh.numNodes(); ++i)
+            if (m_mesh.boundaryNodeForVolumeNode(i) < 0) { nodeToPin = i; break; }
+        if (nodeToPin == m_mesh.numNodes()) nodeToPin = 0;
+        for (size_t d = 0; d < N; ++d)
+            if (components.has(d)) { fixedVars.push_back(N * DoF(nodeToPin) + d); fixedVarValues.push_back(0.0); }
+    }
+
+    size_t m_numDoFs = 0;
+    std::vector<size_t> m_dofForNode;
+    bool m_useRigidMotionConstraint, m_useNRTPinConstraint, m_hostOnly;
+    std::vector<std::pair<size_t, Point>> m_nodalDeltaFunctionForces;
+    std::vector<BoundaryNodeData> m_bnData;
+    std::vector<BoundaryElementData> m_beData;
+    ETensor m_E;
+    std::vector<ETensor> m_perElementE;
+    bool m_haveMaterialOnDevice = false;
+
+protected:
+    mutable SPSDSystem<Real> m_system;
+    _Mesh m_mesh;
+};
+
+}  // namespace LinearElasticity
+#endif

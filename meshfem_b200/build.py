@@ -85,7 +85,9 @@ HOST_SOURCES = [os.path.join(REPO, "src", "host", f) for f in ("MeshIO.cc", "hos
 def _host_stamp():
     h = hashlib.sha256()
     files = list(HOST_SOURCES)
-    for d, _, fs in os.walk(os.path.join(REPO, "include", "MeshFEM")):
+    for d, _, fs in os.walk(os.path.join(REPO, "include")):
+        files += [os.path.join(d, f) for f in fs]
+    for d, _, fs in os.walk(os.path.join(REPO, "src", "bin")):
         files += [os.path.join(d, f) for f in fs]
     for f in sorted(files):
         with open(f, "rb") as fh:
@@ -101,9 +103,20 @@ def build_host(force: bool = False) -> str:
     if not force and os.path.exists(HOST_LIB) and os.path.exists(stamp_file):
         if open(stamp_file).read().strip() == stamp:
             return HOST_LIB
+    # the host library mirrors the reference's classes; Simulator/SPSDSystem call the C ABI, so it
+    # links libmfem_b200.so (build() must run first)
     cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-I" + os.path.join(REPO, "include")] + HOST_SOURCES + \
-          ["-o", HOST_LIB]
+          ["-L" + LIBDIR, "-lmfem_b200", "-Wl,-rpath,$ORIGIN", "-o", HOST_LIB]
     subprocess.check_call(cmd)
+    bindir = os.path.join(REPO, "bin")
+    os.makedirs(bindir, exist_ok=True)
+    for name, src in (("Simulate_cli", "src/bin/Simulate_cli.cc"),
+                      ("PeriodicHomogenization_cli", "src/bin/PeriodicHomogenization_cli.cc"),
+                      ("grid", "src/bin/tools/grid.cc")):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-I" + os.path.join(REPO, "include"),
+                               os.path.join(REPO, src), os.path.join(REPO, "src", "host", "MeshIO.cc"),
+                               "-L" + LIBDIR, "-lmfem_b200", "-Wl,-rpath,$ORIGIN/../meshfem_b200/lib",
+                               "-o", os.path.join(bindir, name)])
     with open(stamp_file, "w") as f:
         f.write(stamp)
     return HOST_LIB

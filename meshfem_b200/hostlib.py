@@ -35,6 +35,12 @@ def load_library():
         lib.mfemhost_femmesh_copy.argtypes = [c_void_p, POINTER(c_double), POINTER(c_int32), POINTER(c_int32),
                                               POINTER(c_int32), POINTER(c_int32), POINTER(c_double),
                                               POINTER(c_double), POINTER(c_double)]
+        lib.mfemhost_apply_bc.argtypes = [c_void_p, c_int, c_char_p, c_int, POINTER(c_int64)]
+        lib.mfemhost_bc_copy.argtypes = [POINTER(c_int64), POINTER(c_double), POINTER(c_double), POINTER(c_int64),
+                                         ctypes.POINTER(ctypes.c_uint8)]
+        lib.mfemhost_material.argtypes = [c_int, c_char_p, POINTER(c_double), ctypes.c_char_p, c_int]
+        lib.mfemhost_eval_expr.argtypes = [c_char_p, c_double, c_double, c_double, POINTER(c_double)]
+        lib.mfemhost_save_mesh.argtypes = [c_void_p, c_char_p]
         _lib = lib
     return _lib
 
@@ -62,6 +68,27 @@ class RawMesh:
         self.lib.mfemhost_raw_copy(self._p, V.ctypes.data_as(POINTER(c_double)), E.ctypes.data_as(POINTER(c_int64)))
         return V, E
 
+    def save(self, path):
+        if self.lib.mfemhost_save_mesh(self._p, os.fsencode(path)) != 0:
+            raise _err(self.lib)
+
+    def apply_bc(self, deg, bc_json_text, periodic=False):
+        """Host-side Simulator bookkeeping (host-only mode): returns dict(fixed_vars, fixed_vals,
+        load[numDoFs, dim], dof_for_node, num_dofs, internal_be)."""
+        sz = (c_int64 * 3)()
+        if self.lib.mfemhost_apply_bc(self._p, deg, (bc_json_text or "").encode(), 1 if periodic else 0, sz) != 0:
+            raise _err(self.lib)
+        nfix, ndof, nbe = (int(x) for x in sz)
+        V, E = self.arrays()
+        fm = self.femmesh(deg)
+        fixed = np.zeros(nfix, dtype=np.int64); vals = np.zeros(nfix); load = np.zeros((ndof, self.dim))
+        dof = np.zeros(fm.num_nodes, dtype=np.int64); ibe = np.zeros(nbe, dtype=np.uint8)
+        self.lib.mfemhost_bc_copy(fixed.ctypes.data_as(POINTER(c_int64)), vals.ctypes.data_as(POINTER(c_double)),
+                                  load.ctypes.data_as(POINTER(c_double)), dof.ctypes.data_as(POINTER(c_int64)),
+                                  ibe.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)))
+        return dict(fixed_vars=fixed, fixed_vals=vals, load=load, dof_for_node=dof, num_dofs=ndof,
+                    internal_be=ibe.astype(bool), mesh=fm)
+
     def femmesh(self, deg):
         """FEMMesh<dim,deg> flat data with the reference's numbering."""
         sz = (c_int64 * 5)()
@@ -83,6 +110,25 @@ class RawMesh:
                                        m.bdry_normal.ctypes.data_as(dp), bbox.ctypes.data_as(dp))
         m.bbox_min, m.bbox_max = bbox[:K].copy(), bbox[3:3 + K].copy()
         return m
+
+
+def material_tensor(dim, json_text):
+    """Materials::Constant<dim>::setFromJson -> flattened tensor, plus its anisotropic round-trip JSON."""
+    lib = load_library()
+    F = dim * (dim + 1) // 2
+    D = np.zeros((F, F))
+    buf = ctypes.create_string_buffer(8192)
+    if lib.mfemhost_material(dim, json_text.encode(), D.ctypes.data_as(POINTER(c_double)), buf, 8192) != 0:
+        raise _err(lib)
+    return D, buf.value.decode()
+
+
+def eval_expression(expr, x=0.0, y=0.0, z=0.0):
+    lib = load_library()
+    out = c_double()
+    if lib.mfemhost_eval_expr(expr.encode(), x, y, z, ctypes.byref(out)) != 0:
+        raise _err(lib)
+    return out.value
 
 
 def grid(sizes, min_corner=None, max_corner=None) -> RawMesh:

@@ -111,7 +111,13 @@ def orthotropic_D3(Ex, Ey, Ez, nuYX, nuZX, nuZY, muYZ, muZX, muXY):
     M[2, 2] = 1.0 / Ez
     M[3, 3] = 1.0 / muYZ; M[4, 4] = 1.0 / muZX; M[5, 5] = 1.0 / muXY
     M = np.triu(M) + np.triu(M, 1).T
-    return np.linalg.inv(M)
+    return _upper(np.linalg.inv(M))
+
+
+def _upper(D):
+    """A major-symmetric ElasticityTensor IS its upper triangle: D(i,j) reads m_d(min,max)
+    (ElasticityTensor.hh:279-283)."""
+    return np.triu(D) + np.triu(D, 1).T
 
 
 def orthotropic_D2(Ex, Ey, nuYX, muXY):
@@ -121,7 +127,7 @@ def orthotropic_D2(Ex, Ey, nuYX, muXY):
     M[1, 1] = 1.0 / Ey
     M[2, 2] = 1.0 / muXY
     M = np.triu(M) + np.triu(M, 1).T
-    return np.linalg.inv(M)
+    return _upper(np.linalg.inv(M))
 
 
 def material_from_json(dim, cfg):
@@ -1222,3 +1228,180 @@ def simulate(N, deg, vertices, simplices, D, bc_params):
     strain, stress = sim.average_strain_stress(u)
     load = sim.dof_to_node_field(sim.neumann_load())
     return dict(sim=sim, u=u, strain=strain, stress=stress, load=load, Ku=sim.apply_stiffness_matrix(u))
+
+
+# ----------------------------------------------------------------------------
+# Periodic conditions (PeriodicBoundaryMatcher.hh:38-258, BoundaryConditions.hh:457-561)
+# and periodic homogenization (PeriodicHomogenization.hh:34-186)
+# ----------------------------------------------------------------------------
+def periodic_condition(mesh, eps=1e-7):
+    """Returns (dof_for_node, num_dofs, is_periodic_be)."""
+    N = mesh.N
+    bn = mesh.bdry_nodes
+    P = mesh.nodes[bn]
+    lo, hi = mesh.bbox_min, mesh.bbox_max
+    on_min = np.abs(P - lo) <= eps              # FaceMembership (:44-50)
+    on_max = np.abs(P - hi) <= eps
+    minimal = ~on_max.any(axis=1)
+    # hashed lookup of the non-minimal points (CollisionGrid, cell size max(eps, 1e-7))
+    def find(q):
+        d = np.linalg.norm(P - q, axis=1)
+        d[minimal] = np.inf
+        j = int(np.argmin(d))
+        return j if d[j] <= eps else -1
+    node_set_for = np.full(bn.size, -1, dtype=np.int64)
+    node_sets = []
+    for i in range(bn.size):
+        if not minimal[i]:
+            continue
+        node_set_for[i] = len(node_sets)
+        faces = [d for d in range(N) if on_min[i, d]]
+        ns = [i]
+        for n in range(1, 1 << len(faces)):
+            q = P[i].copy()
+            for idx, d in enumerate(faces):
+                if n & (1 << idx):
+                    q[d] = hi[d]
+            j = find(q)
+            if j < 0:
+                raise RuntimeError("Couldn't find %dth periodic-identified node for minimal boundary node %d" % (n, i))
+            if node_set_for[j] != -1:
+                raise RuntimeError("Non bijective node set assignment.")
+            node_set_for[j] = node_set_for[i]
+            ns.append(j)
+        node_sets.append(ns)
+    if (node_set_for < 0).any():
+        raise RuntimeError("Unmatched non-minimal boundary node")
+    # boundary elements with all nodes on one common cell face (:126-146)
+    memb = np.concatenate([on_min, on_max], axis=1)
+    bnode = mesh.bdry_node_of_node[mesh.bdry_elem_nodes]
+    common = memb[bnode].all(axis=1)
+    if (common.sum(axis=1) > 1).any():
+        raise RuntimeError("Boundary element on more than one cell face.")
+    is_periodic_be = common.any(axis=1)
+    # DoF ids in node order (BoundaryConditions.hh:533-554)
+    dof = np.full(mesh.num_nodes, -1, dtype=np.int64)
+    nd = 0
+    for n in range(mesh.num_nodes):
+        if dof[n] >= 0:
+            continue
+        b = mesh.bdry_node_of_node[n]
+        if b >= 0:
+            for j in node_sets[node_set_for[b]]:
+                dof[bn[j]] = nd
+        else:
+            dof[n] = nd
+        nd += 1
+    return dof, nd, is_periodic_be
+
+
+def canonical_basis(N, i):
+    """SymmetricMatrix::CanonicalBasis (SymmetricMatrix.hh:407-413), flattened."""
+    e = np.zeros(flat_len(N))
+    e[i] = 1.0 if i < N else 0.5
+    return e
+
+
+def solve_cell_problems(sim):
+    """PeriodicHomogenization::solveCellProblems (:34-54): mutates sim."""
+    dof, nd, is_pbe = periodic_condition(sim.mesh)
+    sim.set_periodic(dof, nd, is_pbe)
+    sim.apply_no_rigid_motion_constraint()
+    sim.set_use_pin_no_rigid_translation_constraint(True)
+    w = []
+    for i in range(flat_len(sim.N)):
+        rhs = sim.constant_strain_load(-canonical_basis(sim.N, i))
+        w.append(sim.solve(rhs))
+    return w
+
+
+def homogenized_tensor_displacement_form(sim, w_ij, base_cell_volume=0.0):
+    """homogenizedElasticityTensorDisplacementForm (:146-186)."""
+    m = sim.mesh; N = sim.N
+    if base_cell_volume == 0.0:
+        base_cell_volume = float(np.prod(m.bbox_max - m.bbox_min))
+    F = flat_len(N)
+    Eh = np.zeros((F, F))
+    wts = integrated_phis(N - 1, m.deg)
+    for i, w in enumerate(w_ij):
+        w_int = np.einsum("n,b,bnc->bc", wts, m.bdry_vol, w[m.bdry_elem_nodes])      # int_be w dA
+        nw = 0.5 * (w_int[:, :, None] * m.bdry_normal[:, None, :] + w_int[:, None, :] * m.bdry_normal[:, :, None])
+        nw_flat = np.stack([nw[:, a, b] for a, b in (unflatten_index(N, k) for k in range(F))], axis=1)
+        Eh[i] += double_contract(N, sim.D, nw_flat).sum(axis=0)
+    Eh += sim.D * m.vol.sum()
+    return Eh / base_cell_volume
+
+
+def homogenized_tensor(sim, w_ij, base_cell_volume=0.0):
+    """homogenizedElasticityTensor, stress-like volume form (:72-100)."""
+    m = sim.mesh; N = sim.N
+    if base_cell_volume == 0.0:
+        base_cell_volume = float(np.prod(m.bbox_max - m.bbox_min))
+    F = flat_len(N)
+    Eh = np.zeros((F, F))
+    for i, w in enumerate(w_ij):
+        strain, stress = average_strain_stress(m, sim.D, w)
+        Eh[i] += (stress * m.vol[:, None]).sum(axis=0)
+    Eh += sim.D * m.vol.sum()
+    return Eh / base_cell_volume
+
+
+# ----------------------------------------------------------------------------
+# Gmsh 2.2 reader (MeshIO.cc:625-760) -- fixtures only
+# ----------------------------------------------------------------------------
+def read_msh(path):
+    """Returns (vertices (n,3), elements (m,k), gmsh element type).  ASCII or binary, 8-byte reals."""
+    npe = {2: 3, 4: 4, 3: 4, 5: 8, 9: 6, 11: 10, 1: 2, 8: 3}
+    with open(path, "rb") as f:
+        data = f.read()
+    pos = 0
+
+    def line():
+        nonlocal pos
+        while True:
+            e = data.index(b"\n", pos)
+            s = data[pos:e].decode("latin1").strip()
+            pos = e + 1
+            if s and not s.startswith("#"):
+                return s
+    assert line() == "$MeshFormat"
+    ver, ftype, dsize = line().split()
+    binary = int(ftype) == 1
+    assert int(dsize) == 8
+    if binary:
+        one = struct.unpack_from("<i", data, pos)[0]; pos += 4
+        assert one == 1
+    assert line() == "$EndMeshFormat"
+    assert line() == "$Nodes"
+    nn = int(line())
+    V = np.zeros((nn, 3))
+    if binary:
+        rec = np.frombuffer(data, dtype=np.dtype([("id", "<i4"), ("p", "<f8", 3)]), count=nn, offset=pos)
+        assert np.array_equal(rec["id"], np.arange(1, nn + 1))
+        V[:] = rec["p"]; pos += nn * 28
+    else:
+        for i in range(nn):
+            t = line().split(); assert int(t[0]) == i + 1
+            V[i] = [float(x) for x in t[1:4]]
+    assert line() == "$EndNodes"
+    assert line() == "$Elements"
+    ne = int(line())
+    E = None; etype = None
+    if binary:
+        read = 0
+        rows = []
+        while read < ne:
+            et, cnt, ntags = struct.unpack_from("<3i", data, pos); pos += 12
+            k = npe[et]; etype = et
+            w = 1 + ntags + k
+            blk = np.frombuffer(data, dtype="<i4", count=cnt * w, offset=pos).reshape(cnt, w); pos += cnt * w * 4
+            rows.append(blk[:, 1 + ntags:] - 1); read += cnt
+        E = np.vstack(rows)
+    else:
+        rows = []
+        for i in range(ne):
+            t = [int(x) for x in line().split()]
+            etype = t[1]; ntags = t[2]
+            rows.append([x - 1 for x in t[3 + ntags:3 + ntags + npe[etype]]])
+        E = np.array(rows)
+    return V, E.astype(np.int64), etype

@@ -2,12 +2,15 @@
 // meshes (src/bin/tools/grid.cc:115-137 of the reference) and FEMMesh construction.  These are
 // input generators / host logic, not part of the GPU ABI (include/mfem_b200.h).
 #include <MeshFEM/FEMMesh.hh>
+#include <MeshFEM/LinearElasticity.hh>
+#include <MeshFEM/Materials.hh>
 #include <MeshFEM/MeshIO.hh>
 #include <MeshFEM/filters/gen_grid.hh>
 #include <MeshFEM/filters/hex_tet_subdiv.hh>
 #include <MeshFEM/filters/quad_tri_subdiv.hh>
 
 #include <cstring>
+#include <sstream>
 #include <string>
 
 namespace {
@@ -139,6 +142,99 @@ int mfemhost_femmesh_copy(void *m, double *nodes, int32_t *elemNodes, int32_t *b
     cp(hm->bdryNormal, bdryNormal);
     if (bbox6) for (int c = 0; c < 3; ++c) { bbox6[c] = hm->bbmin[c]; bbox6[3 + c] = hm->bbmax[c]; }
     return 0;
+}
+
+}  // extern "C"
+
+// Host-side boundary-condition bookkeeping of LinearElasticity::Simulator (host-only mode, no GPU):
+// parse a .bc JSON text, apply it, and return the fixed variables + values and the Neumann load.
+// periodic != 0 additionally applies PeriodicCondition first (cell problems) with the pin constraint.
+namespace {
+struct BCResult { std::vector<int64_t> fixedVars, dofForNode; std::vector<double> fixedVals, load; std::vector<uint8_t> internalBE; int64_t numDoFs = 0; };
+thread_local BCResult g_bc;
+
+template <size_t K, size_t Deg>
+void runBC(HostMesh &hm, const char *bcJson, int periodic) {
+    typedef LinearElasticity::Simulator<LinearElasticity::Mesh<K, Deg>> Sim;
+    Sim sim(hm.elements, hm.vertices, -1);
+    if (periodic) {
+        sim.applyPeriodicConditions(1e-7);
+        sim.applyNoRigidMotionConstraint();
+        sim.setUsePinNoRigidTranslationConstraint(true);
+    }
+    if (bcJson && bcJson[0]) {
+        std::istringstream is(bcJson);
+        bool noRigidMotion;
+        std::vector<PeriodicPairDirichletCondition<K>> pps;
+        ComponentMask pin;
+        auto conds = readBoundaryConditions<K>(is, sim.mesh().boundingBox(), noRigidMotion, pps, pin);
+        sim.applyTranslationPins(pin);
+        sim.applyBoundaryConditions(conds);
+        sim.applyPeriodicPairDirichletConditions(pps);
+        if (noRigidMotion) sim.applyNoRigidMotionConstraint();
+    }
+    std::vector<size_t> fv;
+    std::vector<Real> fx;
+    sim.getFixedVariables(fv, fx);
+    g_bc.fixedVars.assign(fv.begin(), fv.end());
+    g_bc.fixedVals = fx;
+    g_bc.load = sim.neumannLoad().data();
+    g_bc.numDoFs = (int64_t)sim.numDoFs();
+    g_bc.dofForNode.resize(sim.mesh().numNodes());
+    for (size_t n = 0; n < sim.mesh().numNodes(); ++n) g_bc.dofForNode[n] = (int64_t)sim.DoF(n);
+    g_bc.internalBE.resize(sim.mesh().numBoundaryElements());
+    for (size_t be = 0; be < g_bc.internalBE.size(); ++be) g_bc.internalBE[be] = sim.isInternalBoundaryElement(be);
+}
+}  // namespace
+
+extern "C" {
+
+// sizes3: [numFixed, numDoFs, numBoundaryElements]
+int mfemhost_apply_bc(void *m, int deg, const char *bcJson, int periodic, int64_t *sizes3) {
+    auto *hm = static_cast<HostMesh *>(m);
+    try {
+        if (hm->dim == 3 && deg == 1) runBC<3, 1>(*hm, bcJson, periodic);
+        else if (hm->dim == 3 && deg == 2) runBC<3, 2>(*hm, bcJson, periodic);
+        else if (hm->dim == 2 && deg == 1) runBC<2, 1>(*hm, bcJson, periodic);
+        else if (hm->dim == 2 && deg == 2) runBC<2, 2>(*hm, bcJson, periodic);
+        else throw std::runtime_error("bad dim/deg");
+        sizes3[0] = (int64_t)g_bc.fixedVars.size(); sizes3[1] = g_bc.numDoFs; sizes3[2] = (int64_t)g_bc.internalBE.size();
+        return 0;
+    } catch (const std::exception &e) { g_err = e.what(); return -1; }
+}
+int mfemhost_bc_copy(int64_t *fixedVars, double *fixedVals, double *load, int64_t *dofForNode, uint8_t *internalBE) {
+    auto cp = [](auto &v, auto *dst) { if (dst && !v.empty()) std::memcpy(dst, v.data(), v.size() * sizeof(v[0])); };
+    cp(g_bc.fixedVars, fixedVars); cp(g_bc.fixedVals, fixedVals); cp(g_bc.load, load); cp(g_bc.dofForNode, dofForNode);
+    cp(g_bc.internalBE, internalBE);
+    return 0;
+}
+
+// .material text -> flattened tensor (flat x flat row-major); returns 0 or -1
+int mfemhost_material(int dim, const char *jsonText, double *Dout, char *roundTripJson, int roundTripCap) {
+    try {
+        auto j = mjson::json::parse(std::string(jsonText));
+        std::string rt;
+        if (dim == 3) { Materials::Constant<3> mat; mat.setFromJson(j); mat.getTensor().getFlat(Dout); rt = mat.getJson().dump(); }
+        else { Materials::Constant<2> mat; mat.setFromJson(j); mat.getTensor().getFlat(Dout); rt = mat.getJson().dump(); }
+        if (roundTripJson && roundTripCap > 0) { std::strncpy(roundTripJson, rt.c_str(), roundTripCap - 1); roundTripJson[roundTripCap - 1] = 0; }
+        return 0;
+    } catch (const std::exception &e) { g_err = e.what(); return -1; }
+}
+
+// tinyexpr-style expression evaluation with variables x, y, z
+int mfemhost_eval_expr(const char *expr, double x, double y, double z, double *out) {
+    try {
+        ExpressionEnvironment env;
+        env.setValue("x", x); env.setValue("y", y); env.setValue("z", z);
+        *out = Expression(expr).eval(env);
+        return 0;
+    } catch (const std::exception &e) { g_err = e.what(); return -1; }
+}
+
+int mfemhost_save_mesh(void *m, const char *path) {
+    auto *hm = static_cast<HostMesh *>(m);
+    try { MeshIO::save(path, hm->vertices, hm->elements); return 0; }
+    catch (const std::exception &e) { g_err = e.what(); return -1; }
 }
 
 }  // extern "C"

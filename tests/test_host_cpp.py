@@ -1,0 +1,203 @@
+"""CPU tests of the host C++ mirror of the reference's mesh / material / boundary-condition layer
+(include/MeshFEM, src/host) against the numpy oracle, plus the ABI-surface checks that need no GPU."""
+import ctypes
+import json
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import meshfem_oracle as orc
+from util import CANTILEVER_2D_BC, CANTILEVER_BC, ORTHO, ROOT
+
+REF = "/root/reference"
+
+
+@pytest.fixture(scope="module")
+def hostlib(lib_built):
+    from meshfem_b200 import hostlib as hl
+    return hl
+
+
+MESH_FIELDS = ("nodes", "elem_nodes", "bdry_elem_nodes", "bdry_elem_vertices", "bdry_nodes", "bdry_vol", "bdry_normal",
+               "bbox_min", "bbox_max")
+
+
+@pytest.mark.parametrize("sizes", [(5, 3), (4, 3, 2)])
+@pytest.mark.parametrize("deg", [1, 2])
+def test_grid_and_femmesh_numbering_match_oracle(hostlib, sizes, deg):
+    rm = hostlib.grid(list(sizes))
+    V, E = rm.arrays()
+    Vo, Eo = orc.grid_simplices(list(sizes))
+    assert np.array_equal(V, Vo) and np.array_equal(E, Eo)
+    m, mo = rm.femmesh(deg), orc.build_mesh(len(sizes), deg, Vo, Eo)
+    for k in MESH_FIELDS:
+        assert np.array_equal(getattr(m, k), getattr(mo, k)), k
+
+
+def test_grid_with_corners(hostlib):
+    rm = hostlib.grid([3, 2, 2], [0, -1, 2], [6, 1, 3])
+    V, E = rm.arrays()
+    Vo, Eo = orc.grid_simplices([3, 2, 2], [0, -1, 2], [6, 1, 3])
+    assert np.allclose(V, Vo, rtol=0, atol=1e-15) and np.array_equal(E, Eo)
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="reference tree not mounted")
+@pytest.mark.parametrize("name,dim", [("ball.msh", 3), ("cube_cross.msh", 3), ("2D_microstructure.msh", 2)])
+def test_reference_example_meshes(hostlib, name, dim, tmp_path):
+    path = os.path.join(REF, "examples/meshes", name)
+    rm = hostlib.load_mesh(path)
+    V, E = rm.arrays()
+    Vo, Eo, _ = orc.read_msh(path)                      # independent reader (binary Gmsh 2.2)
+    assert np.array_equal(V, Vo) and np.array_equal(E, Eo) and rm.dim == dim
+    m, mo = rm.femmesh(2), orc.build_mesh(dim, 2, Vo, Eo)
+    for k in MESH_FIELDS:
+        assert np.array_equal(getattr(m, k), getattr(mo, k)), k
+    # MSH writer round trip (binary), byte-identical re-read
+    out = str(tmp_path / "rt.msh")
+    rm.save(out)
+    V2, E2, _ = orc.read_msh(out)
+    assert np.array_equal(V2, Vo) and np.array_equal(E2, Eo)
+
+
+def test_square_hole_off_edge_count(hostlib):
+    if not os.path.exists(REF):
+        pytest.skip("reference tree not mounted")
+    rm = hostlib.load_mesh(os.path.join(REF, "examples/meshes/square_hole.off"))
+    m = rm.femmesh(2)
+    assert m.num_nodes - m.num_vertices == 760          # tests/test_femmesh_traversal.cc:99
+
+
+@pytest.mark.parametrize("N,deg,sizes,bc", [(3, 1, (5, 2, 2), CANTILEVER_BC), (3, 2, (4, 2, 2), CANTILEVER_BC),
+                                            (2, 1, (6, 3), CANTILEVER_2D_BC), (2, 2, (6, 3), CANTILEVER_2D_BC)])
+def test_boundary_conditions_match_oracle(hostlib, N, deg, sizes, bc):
+    V, T = orc.grid_simplices(list(sizes))
+    sim = orc.Simulator(N, deg, V, T)
+    conds, nr, pps, pin = orc.read_boundary_conditions(N, bc, sim.mesh.bbox_min, sim.mesh.bbox_max)
+    sim.apply_translation_pins(pin)
+    sim.apply_boundary_conditions(conds)
+    fx, vv = sim.fixed_vars_and_values()
+    r = hostlib.grid(list(sizes)).apply_bc(deg, json.dumps(bc))
+    assert np.array_equal(r["fixed_vars"], fx) and np.array_equal(r["fixed_vals"], vv)
+    assert np.array_equal(r["load"], sim.neumann_load())
+    assert np.allclose(r["load"].sum(axis=0)[:2], [0, -10])
+
+
+def test_expression_traction_pressure_pins_and_masks(hostlib):
+    """Every .bc feature on the path: component masks, expressions with mesh_/region_ variables,
+    pressure (-p n), traction, delta force, pin_translation, absolute `box`."""
+    bc = {"pin_translation": "z",
+          "regions": [
+              {"type": "dirichletxy", "value": ["0.01*sin(pi*y)", "x*mesh_size_1", 0],
+               "box%": {"minCorner": [-1e-4, -1e-4, -1e-4], "maxCorner": [1e-4, 1.0001, 1.0001]}},
+              {"type": "pressure", "value": [2.5, 0, 0], "box": {"minCorner": [3.9999, -1, -1], "maxCorner": [4.0001, 3, 3]}},
+              {"type": "traction", "value": ["y", "region_max_0 - x", "1"],
+               "box%": {"minCorner": [-1e-4, 0.9999, -1e-4], "maxCorner": [1.0001, 1.0001, 1.0001]}},
+              {"type": "delta force", "value": [0, 0, 1], "box": {"minCorner": [1.9, 0.9, 0.9], "maxCorner": [2.1, 1.1, 1.1]}},
+              {"type": "target", "value": [0, 0, 0], "box%": {"minCorner": [0, 0, 0], "maxCorner": [1, 1, 1]}}]}
+    V, T = orc.grid_simplices([4, 2, 2])
+    sim = orc.Simulator(3, 2, V, T)
+    conds, nr, pps, pin = orc.read_boundary_conditions(3, bc, sim.mesh.bbox_min, sim.mesh.bbox_max)
+    sim.apply_translation_pins(pin)
+    sim.apply_boundary_conditions(conds)
+    fx, vv = sim.fixed_vars_and_values()
+    r = hostlib.grid([4, 2, 2]).apply_bc(2, json.dumps(bc))
+    assert np.array_equal(r["fixed_vars"], fx)
+    assert np.allclose(r["fixed_vals"], vv, rtol=1e-15, atol=1e-18)
+    assert np.allclose(r["load"], sim.neumann_load(), rtol=1e-14, atol=1e-16)
+    assert np.abs(r["load"]).max() > 0 and (vv != 0).any()
+
+
+def test_bc_error_behaviour(hostlib):
+    rm = hostlib.grid([2, 2, 2])
+    with pytest.raises(RuntimeError, match="Neumann region unmatched"):
+        rm.apply_bc(1, json.dumps({"regions": [{"type": "force", "value": [0, 1, 0],
+                                                "box": {"minCorner": [9, 9, 9], "maxCorner": [10, 10, 10]}}]}))
+    with pytest.raises(RuntimeError, match="Conflicting dirichlet displacements"):
+        rm.apply_bc(1, json.dumps({"regions": [
+            {"type": "dirichlet", "value": [0, 0, 0], "box%": {"minCorner": [-.1, -.1, -.1], "maxCorner": [.1, 1.1, 1.1]}},
+            {"type": "dirichlet", "value": [1, 0, 0], "box%": {"minCorner": [-.1, -.1, -.1], "maxCorner": [.1, 1.1, 1.1]}}]}))
+    with pytest.raises(RuntimeError, match="Invalid type"):
+        rm.apply_bc(1, json.dumps({"regions": [{"type": "spring", "value": [0, 0, 0], "box": {"minCorner": [0, 0, 0], "maxCorner": [1, 1, 1]}}]}))
+    with pytest.raises(RuntimeError, match="Lagrange"):      # no Dirichlet on y,z and no pin: needs a KKT row
+        rm.apply_bc(1, json.dumps({"regions": [{"type": "dirichletx", "value": [0, 0, 0],
+                                                "box%": {"minCorner": [-.1, -.1, -.1], "maxCorner": [.1, 1.1, 1.1]}}]}))
+
+
+@pytest.mark.parametrize("sizes,deg", [((3, 3, 3), 1), ((3, 3, 3), 2), ((4, 4), 2)])
+def test_periodic_condition_matches_oracle(hostlib, sizes, deg):
+    V, T = orc.grid_simplices(list(sizes))
+    sim = orc.Simulator(len(sizes), deg, V, T)
+    dof, nd, pbe = orc.periodic_condition(sim.mesh)
+    sim.set_periodic(dof, nd, pbe)
+    sim.apply_no_rigid_motion_constraint(); sim.set_use_pin_no_rigid_translation_constraint(True)
+    fx, vv = sim.fixed_vars_and_values()
+    r = hostlib.grid(list(sizes)).apply_bc(deg, "", periodic=True)
+    assert r["num_dofs"] == nd and np.array_equal(r["dof_for_node"], dof) and np.array_equal(r["internal_be"], pbe)
+    assert np.array_equal(r["fixed_vars"], fx) and np.array_equal(r["fixed_vals"], vv)
+    # "monotonically increasing with lowest identified node index" (BoundaryConditions.hh:618)
+    first = {}
+    for n, d in enumerate(dof):
+        first.setdefault(d, n)
+    assert list(first.values()) == sorted(first.values())
+
+
+def test_materials_and_expressions(hostlib):
+    from test_oracle_kats import MATERIAL_FIXTURES
+    for name, cfgs in MATERIAL_FIXTURES.items():
+        for dim in (2, 3):
+            D, rt = hostlib.material_tensor(dim, json.dumps(cfgs[dim - 2]))
+            assert np.allclose(D, orc.material_from_json(dim, cfgs[dim - 2]), rtol=1e-13, atol=1e-15), (name, dim)
+            D2, _ = hostlib.material_tensor(dim, rt)       # JSON -> tensor -> JSON -> tensor (test_materials.cc)
+            assert np.array_equal(D, D2)
+    D, _ = hostlib.material_tensor(3, json.dumps(ORTHO))
+    assert np.allclose(D, orc.material_from_json(3, ORTHO), rtol=1e-13)
+    with pytest.raises(RuntimeError, match="violate symmetry"):
+        bad = dict(ORTHO); bad["poisson"] = [0.3, 0.2, 0.12, 0.3, 0.3, 0.5]
+        hostlib.material_tensor(3, json.dumps(bad))
+    with pytest.raises(RuntimeError, match="Invalid type"):
+        hostlib.material_tensor(3, '{"type": "foo"}')
+    env = dict(x=0.3, y=-1.2, z=2.0)
+    for expr in ["sin(pi*x)", "cos(x)*y + z^2", "2^3^2", "-x^2", "atan2(y, x)", "sqrt(z) + abs(y) - exp(x)", "x % 0.2",
+                 "1e-2*(x+y)/(z-1)", "pow(z,3) + ln(e) + log10(100) + fac(4) + ncr(5,2)", "floor(y) + ceil(x)"]:
+        want = orc.eval_expression(expr.replace("2^3^2", "(2^3)^2").replace("-x^2", "(-x)^2"), env)   # tinyexpr: left-assoc ^, tight unary minus
+        assert abs(hostlib.eval_expression(expr, **env) - want) <= 1e-14 * max(1, abs(want)), expr
+    with pytest.raises(RuntimeError):
+        hostlib.eval_expression("sin(")
+
+
+def test_c_abi_exports_every_declared_symbol(lib_built):
+    """libmfem_b200.so loads without a GPU and exports exactly what include/mfem_b200.h declares."""
+    hdr = open(os.path.join(ROOT, "include", "mfem_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(mfem_b200_[A-Za-z_0-9]+)\s*\(", hdr)))
+    lib = ctypes.CDLL(lib_built[0])
+    for name in declared:
+        assert hasattr(lib, name), name
+    from meshfem_b200 import capi
+    assert sorted(capi.SYMBOLS) == declared
+    out = subprocess.run(["nm", "-D", "--defined-only", lib_built[0]], capture_output=True, text=True).stdout
+    exported = sorted(set(re.findall(r" T (mfem_b200_[A-Za-z_0-9]+)", out)))
+    assert exported == declared
+
+
+def test_no_cpu_fallback_without_gpu(lib_built):
+    import meshfem_b200
+    lib = meshfem_b200.load_library()
+    if lib.mfem_b200_device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(meshfem_b200.MfemB200Error, match="no CPU fallback"):
+        meshfem_b200.Handle(0)
+
+
+def test_product_path_does_not_reference_the_oracle():
+    bad = []
+    for base in ("meshfem_b200", "include", "src"):
+        for d, _, fs in os.walk(os.path.join(ROOT, base)):
+            for f in fs:
+                if f.endswith((".py", ".cu", ".cuh", ".cc", ".hh", ".h")):
+                    txt = open(os.path.join(d, f), errors="ignore").read()
+                    if re.search(r"meshfem_oracle|ref_cpu|oracle/", txt):
+                        bad.append(os.path.join(d, f))
+    assert not bad, bad

@@ -53,3 +53,48 @@ def cantilever_problem(N, deg, sizes, D=None):
     fixed, vals = sim.fixed_vars_and_values()
     f = sim.neumann_load()
     return sim, fixed, vals, f
+
+
+B9CREATOR = {"type": "isotropic_material", "dim": 3, "density": 1.0, "young": 200.0, "poisson": 0.35}
+
+
+def read_msh_fields(path):
+    """Fields written by MSHFieldWriter ($NodeData / $ElementData, binary or ascii) -> {name: array}."""
+    import struct
+    data = open(path, "rb").read()
+    binary = data.split(b"\n", 2)[1].split()[1] == b"1"
+    out = {}
+    pos = 0
+    while True:
+        i1 = data.find(b"$NodeData\n", pos)
+        i2 = data.find(b"$ElementData\n", pos)
+        cands = [i for i in (i1, i2) if i >= 0]
+        if not cands:
+            break
+        i = min(cands)
+        p = data.index(b"\n", i) + 1
+        def line():
+            nonlocal p
+            e = data.index(b"\n", p); s = data[p:e].decode(); p = e + 1
+            return s
+        assert line() == "1"
+        name = line().strip('"')
+        assert line() == "0" and line() == "3" and line() == "0"
+        dim = int(line()); n = int(line())
+        if binary:
+            rec = np.frombuffer(data, dtype=np.dtype([("id", "<i4"), ("v", "<f8", dim)]), count=n, offset=p)
+            assert np.array_equal(rec["id"], np.arange(1, n + 1))
+            out[name] = rec["v"].reshape(n, dim).copy(); p += n * (4 + 8 * dim)
+        else:
+            vals = np.zeros((n, dim))
+            for k in range(n):
+                t = line().split(); vals[k] = [float(x) for x in t[1:]]
+            out[name] = vals
+        pos = p
+    return out
+
+
+def sym9_to_flat(N, a9):
+    """9 row-major doubles (padded 3x3) -> flattened Voigt (n, flat)."""
+    idx = [(0, 0), (1, 1), (0, 1)] if N == 2 else [(0, 0), (1, 1), (2, 2), (1, 2), (0, 2), (0, 1)]
+    return np.stack([a9[:, 3 * i + j] for i, j in idx], axis=1)
