@@ -61,7 +61,7 @@ int mfem_b200_device_count(void);
 /* Multi-GPU: element-partitioned execution, one process per GPU.  nccl_unique_id is the
  * 128-byte ncclUniqueId obtained on rank 0 (mfem_b200_comm_unique_id) and broadcast by the
  * caller (torch.distributed / MPI / files).  Must be called before set_mesh; after it,
- * set_mesh receives this rank's LOCAL sub-mesh plus the global ids of its nodes.       */
+ * set_mesh receives this rank's LOCAL sub-mesh and set_interface its shared DoFs.       */
 int mfem_b200_comm_unique_id(void *out128);
 int mfem_b200_comm_init(mfem_b200_handle h, int n_ranks, int rank, const void *nccl_unique_id128);
 
@@ -84,8 +84,16 @@ int mfem_b200_set_option(mfem_b200_handle h, const char *name, int64_t value);
 int mfem_b200_set_mesh(mfem_b200_handle h, int dim, int degree, int64_t n_nodes, const double *nodes,
                        int64_t n_elems, const int32_t *elem_nodes, const int64_t *dof_for_node,
                        int64_t n_dofs);
-/* Multi-GPU only: global DoF id of every local DoF (defines shared interface DoFs).    */
-int mfem_b200_set_global_dof_ids(mfem_b200_handle h, const int64_t *global_id_of_local_dof);
+/* Multi-GPU only, after set_mesh: the interface of this rank's element partition
+ * (include/MeshFEM/Partition.hh).  For neighbour q (n_neighbors of them, ranks ascending) the
+ * LOCAL DoFs shared with it are shared_local_dofs[neighbor_offsets[q] .. neighbor_offsets[q+1]),
+ * listed in the same order (ascending global id) on both sides; owned[d] = 1 iff this rank is
+ * the lowest rank sharing local DoF d (dot products count owned DoFs only).  Right-hand sides
+ * given to solve() must be CONSISTENT (the full global value on every sharer); the returned u is
+ * consistent too.                                                                        */
+int mfem_b200_set_interface(mfem_b200_handle h, int n_neighbors, const int32_t *neighbor_ranks,
+                            const int64_t *neighbor_offsets, const int32_t *shared_local_dofs,
+                            const uint8_t *owned);
 
 /* ---- material -------------------------------------------------------------------- */
 /* D: flattened elasticity tensor, row-major flat x flat (flat = 3 in 2D, 6 in 3D),

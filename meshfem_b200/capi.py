@@ -19,7 +19,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libmfem_b200.so")
 SYMBOLS = [
     "mfem_b200_create", "mfem_b200_destroy", "mfem_b200_last_error", "mfem_b200_device_count",
     "mfem_b200_comm_unique_id", "mfem_b200_comm_init", "mfem_b200_set_option", "mfem_b200_set_mesh",
-    "mfem_b200_set_global_dof_ids", "mfem_b200_set_material_constant", "mfem_b200_set_material_per_element",
+    "mfem_b200_set_interface", "mfem_b200_set_material_constant", "mfem_b200_set_material_per_element",
     "mfem_b200_assemble", "mfem_b200_get_bsr_sizes", "mfem_b200_get_bsr", "mfem_b200_dump_upper_triplets",
     "mfem_b200_set_node_positions", "mfem_b200_fix_variables", "mfem_b200_clear_fixed_variables",
     "mfem_b200_solve", "mfem_b200_apply_K", "mfem_b200_spmv", "mfem_b200_const_strain_load",
@@ -68,7 +68,7 @@ def load_library():
     lib.mfem_b200_comm_init.argtypes = [c_void_p, c_int, c_int, c_void_p]
     lib.mfem_b200_set_option.argtypes = [c_void_p, c_char_p, c_int64]
     lib.mfem_b200_set_mesh.argtypes = [c_void_p, c_int, c_int, c_int64, dp, c_int64, ip, lp, c_int64]
-    lib.mfem_b200_set_global_dof_ids.argtypes = [c_void_p, lp]
+    lib.mfem_b200_set_interface.argtypes = [c_void_p, c_int, ip, lp, ip, POINTER(ctypes.c_uint8)]
     lib.mfem_b200_set_material_constant.argtypes = [c_void_p, dp]
     lib.mfem_b200_set_material_per_element.argtypes = [c_void_p, dp]
     lib.mfem_b200_assemble.argtypes = [c_void_p]
@@ -187,9 +187,16 @@ class Handle:
         self.dim, self.deg = dim, deg
         self.n_nodes, self.n_elems, self.n_dofs = nodes.shape[0], en.shape[0], nd
 
-    def set_global_dof_ids(self, ids):
-        ids = np.ascontiguousarray(ids, dtype=np.int64)
-        self._check(self.lib.mfem_b200_set_global_dof_ids(self._h, ids.ctypes.data_as(POINTER(c_int64))))
+    def set_interface(self, neighbor_ranks, neighbor_offsets, shared_local_dofs, owned):
+        nr = np.ascontiguousarray(neighbor_ranks, dtype=np.int32)
+        no = np.ascontiguousarray(neighbor_offsets, dtype=np.int64)
+        sh = np.ascontiguousarray(shared_local_dofs, dtype=np.int32)
+        ow = np.ascontiguousarray(owned, dtype=np.uint8)
+        assert ow.size == self.n_dofs
+        self._check(self.lib.mfem_b200_set_interface(self._h, nr.size, nr.ctypes.data_as(POINTER(c_int32)),
+                                                     no.ctypes.data_as(POINTER(c_int64)),
+                                                     sh.ctypes.data_as(POINTER(c_int32)),
+                                                     ow.ctypes.data_as(POINTER(ctypes.c_uint8))))
 
     def set_node_positions(self, nodes):
         nodes = _f64(nodes, (self.n_nodes, self.dim))

@@ -1,20 +1,115 @@
-// Multi-GPU plumbing: NCCL communicator owned by the handle (one process per GPU).
-// Element-partitioned execution with interface sum-exchange is described in DESIGN.md;
-// this file currently provides the communicator lifecycle used by the halo exchange.
+// Multi-GPU plumbing (one process per GPU): NCCL communicator owned by the handle, the
+// interface ("halo") sum-exchange that completes partial sums on DoFs shared between element
+// partitions, and the scalar all-reduce behind the PCG dot products.
+//
+// New design -- the reference is single-process.  Non-overlapping element
+// partition with SHARED interface DoFs: a rank's local K holds partial sums on interface rows, so
+// after every local SpMV each pair of neighbouring ranks swaps the values of the DoFs they share
+// and adds what it receives (ncclSend/ncclRecv grouped per neighbour, on the solver's stream).
+// Dot products count every DoF once through the `owned` mask (owner = lowest sharing rank).
 #include <nccl.h>
+
+#include <cstring>
 
 #include "core.cuh"
 
-using namespace mfem;
-
 namespace mfem {
+
+struct Halo {
+    std::vector<int> ranks;              // neighbour ranks
+    std::vector<int64_t> offsets;        // [nNeighbors+1] into idx
+    DevBuf<int32_t> idx;                 // internal DoF ids shared with each neighbour, per-neighbour segments
+    DevBuf<uint8_t> owned;               // [nDofs] internal numbering
+    DevBuf<double> sendBuf, recvBuf;     // total * maxWidth doubles
+    int64_t total = 0;
+    int maxWidth = 9;
+};
+
+#define MFEM_NCCL(call)                                                                              \
+    do {                                                                                             \
+        ncclResult_t r_ = (call);                                                                    \
+        if (r_ != ncclSuccess)                                                                       \
+            throw mfem::CudaError(MFEM_B200_ERR_COMM, std::string(#call) + ": " + ncclGetErrorString(r_)); \
+    } while (0)
+
+__global__ void k_halo_pack(int64_t n, int width, const int32_t *__restrict__ idx, const double *__restrict__ vec,
+                            double *__restrict__ buf) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n * width) return;
+    const int64_t k = t / width;
+    const int c = (int)(t - k * width);
+    buf[t] = vec[(int64_t)idx[k] * width + c];
+}
+// one launch per neighbour: inside a neighbour's segment every DoF appears once -> no write conflicts
+__global__ void k_halo_unpack_add(int64_t n, int width, const int32_t *__restrict__ idx, const double *__restrict__ buf,
+                                  double *__restrict__ vec) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n * width) return;
+    const int64_t k = t / width;
+    const int c = (int)(t - k * width);
+    vec[(int64_t)idx[k] * width + c] += buf[t];
+}
+__global__ void k_map_shared(int64_t n, const int32_t *__restrict__ localIdx, const int32_t *__restrict__ ext2int,
+                             int32_t *__restrict__ out) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t < n) out[t] = ext2int[localIdx[t]];
+}
+__global__ void k_map_owned(int64_t n, const uint8_t *__restrict__ ownedExt, const int32_t *__restrict__ int2ext,
+                            uint8_t *__restrict__ out) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t < n) out[t] = ownedExt[int2ext[t]];
+}
+
 void comm_destroy(mfem_b200_ctx *c) {
+    delete c->halo;
+    c->halo = nullptr;
     if (c->ncclComm) {
         ncclCommDestroy(static_cast<ncclComm_t>(c->ncclComm));
         c->ncclComm = nullptr;
     }
 }
+
+const uint8_t *halo_owned(mfem_b200_ctx *c) {
+    MFEM_REQUIRE(c->halo && c->halo->owned.n == (size_t)c->nDofs, MFEM_B200_ERR_INVALID,
+                 "multi-GPU handle without interface description: call mfem_b200_set_interface after set_mesh");
+    return c->halo->owned;
+}
+
+void halo_exchange_add(mfem_b200_ctx *c, double *vec, int width) {
+    if (c->nRanks <= 1) return;
+    MFEM_REQUIRE(c->halo, MFEM_B200_ERR_INVALID, "multi-GPU handle without interface description");
+    Halo &h = *c->halo;
+    if (h.total == 0) return;
+    MFEM_REQUIRE(width <= h.maxWidth, MFEM_B200_ERR_INVALID, "halo width too large");
+    cudaStream_t s = c->stream;
+    ncclComm_t comm = static_cast<ncclComm_t>(c->ncclComm);
+    k_halo_pack<<<grid_for(h.total * width, 256), 256, 0, s>>>(h.total, width, h.idx, vec, h.sendBuf);
+    c->launches++;
+    MFEM_NCCL(ncclGroupStart());
+    for (size_t q = 0; q < h.ranks.size(); ++q) {
+        const int64_t off = h.offsets[q] * width, cnt = (h.offsets[q + 1] - h.offsets[q]) * width;
+        MFEM_NCCL(ncclSend(h.sendBuf.p + off, (size_t)cnt, ncclDouble, h.ranks[q], comm, s));
+        MFEM_NCCL(ncclRecv(h.recvBuf.p + off, (size_t)cnt, ncclDouble, h.ranks[q], comm, s));
+    }
+    MFEM_NCCL(ncclGroupEnd());
+    for (size_t q = 0; q < h.ranks.size(); ++q) {
+        const int64_t off = h.offsets[q], cnt = h.offsets[q + 1] - h.offsets[q];
+        k_halo_unpack_add<<<grid_for(cnt * width, 256), 256, 0, s>>>(cnt, width, h.idx.p + off, h.recvBuf.p + off * width, vec);
+        c->launches++;
+    }
+}
+
+void allreduce_sum(mfem_b200_ctx *c, const double *in, double *out, int n) {
+    if (c->nRanks <= 1) {
+        if (in != out) MFEM_CUDA(cudaMemcpyAsync(out, in, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
+        return;
+    }
+    MFEM_NCCL(ncclAllReduce(in, out, (size_t)n, ncclDouble, ncclSum, static_cast<ncclComm_t>(c->ncclComm), c->stream));
+}
+
 }  // namespace mfem
+
+using namespace mfem;
 
 extern "C" {
 
@@ -49,11 +144,49 @@ int mfem_b200_comm_init(mfem_b200_handle h, int n_ranks, int rank, const void *n
     return MFEM_B200_OK;
 }
 
-int mfem_b200_set_global_dof_ids(mfem_b200_handle h, const int64_t *ids) {
+int mfem_b200_set_interface(mfem_b200_handle h, int n_neighbors, const int32_t *neighbor_ranks,
+                            const int64_t *neighbor_offsets, const int32_t *shared_local_dofs, const uint8_t *owned) {
     if (!h) return MFEM_B200_ERR_INVALID;
-    (void)ids;
-    h->err = "set_global_dof_ids: multi-GPU interface exchange not built yet";
-    return MFEM_B200_ERR_INVALID;
+    try {
+        MFEM_CUDA(cudaSetDevice(h->device));
+        MFEM_REQUIRE(h->nElems > 0, MFEM_B200_ERR_INVALID, "set_interface: set the mesh first");
+        MFEM_REQUIRE(h->nRanks > 1 && h->ncclComm, MFEM_B200_ERR_INVALID, "set_interface: comm_init was not called");
+        MFEM_REQUIRE(n_neighbors >= 0 && owned && (n_neighbors == 0 || (neighbor_ranks && neighbor_offsets && shared_local_dofs)),
+                     MFEM_B200_ERR_INVALID, "set_interface: bad arguments");
+        delete h->halo;
+        h->halo = new Halo();
+        Halo &H = *h->halo;
+        H.maxWidth = h->N * h->N;
+        H.ranks.assign(neighbor_ranks, neighbor_ranks + n_neighbors);
+        H.offsets.assign(1, 0);
+        if (n_neighbors) H.offsets.assign(neighbor_offsets, neighbor_offsets + n_neighbors + 1);
+        H.total = H.offsets.back();
+        for (int64_t k = 0; k < H.total; ++k)
+            MFEM_REQUIRE(shared_local_dofs[k] >= 0 && shared_local_dofs[k] < h->nDofs, MFEM_B200_ERR_INVALID,
+                         "set_interface: shared DoF out of range");
+        cudaStream_t s = h->stream;
+        if (H.total) {
+            DevBuf<int32_t> tmp((size_t)H.total);
+            MFEM_CUDA(cudaMemcpyAsync(tmp, shared_local_dofs, tmp.bytes(), cudaMemcpyHostToDevice, s));
+            H.idx.alloc((size_t)H.total);
+            k_map_shared<<<grid_for(H.total, 256), 256, 0, s>>>(H.total, tmp, h->ext2int, H.idx);
+            H.sendBuf.alloc((size_t)H.total * H.maxWidth);
+            H.recvBuf.alloc((size_t)H.total * H.maxWidth);
+            MFEM_CUDA(cudaStreamSynchronize(s));
+        }
+        DevBuf<uint8_t> oext((size_t)h->nDofs);
+        MFEM_CUDA(cudaMemcpyAsync(oext, owned, oext.bytes(), cudaMemcpyHostToDevice, s));
+        H.owned.alloc((size_t)h->nDofs);
+        k_map_owned<<<grid_for(h->nDofs, 256), 256, 0, s>>>(h->nDofs, oext, h->int2ext, H.owned);
+        h->launches += 2;
+        MFEM_CUDA(cudaStreamSynchronize(s));
+        MFEM_CUDA(cudaGetLastError());
+        h->precondValid = false;
+        return MFEM_B200_OK;
+    } catch (const CudaError &e) {
+        h->err = e.what();
+        return e.status;
+    }
 }
 
 }  // extern "C"

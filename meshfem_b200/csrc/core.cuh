@@ -70,6 +70,7 @@ struct PcgWork {
     DevBuf<double> x, r, z, p, Ap, b, ufix;
     DevBuf<double> partials;     // per-CTA partial sums, 4 slots
     DevBuf<double> scal;         // device scalars (see solver.cu)
+    DevBuf<double> dotLoc;       // multi-GPU: this rank's partial sums before the all-reduce
     DevBuf<unsigned> ticket;     // last-block tickets
     DevBuf<int> status;          // [0]=iterations done, [1]=state (0 running, 1 converged, 2 breakdown, 3 nan)
 };
@@ -195,6 +196,10 @@ void pcg_solve(mfem_b200_ctx *c, const double *f_ext_dev, double *u_ext_dev, dou
                mfem_b200_solve_info *info);
 void ensure_work(mfem_b200_ctx *c);
 double time_spmv(mfem_b200_ctx *c, int iters);
+// comm.cu
+void halo_exchange_add(mfem_b200_ctx *c, double *vec_int, int width);   // no-op on one rank
+void allreduce_sum(mfem_b200_ctx *c, const double *in, double *out, int n);
+const uint8_t *halo_owned(mfem_b200_ctx *c);
 // aux.cu
 void permute_to_internal(mfem_b200_ctx *c, const double *ext, double *in);   // per-DoF vectors
 void permute_to_external(mfem_b200_ctx *c, const double *in, double *ext);

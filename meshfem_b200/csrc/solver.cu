@@ -21,13 +21,16 @@ constexpr int kMaxPartials = 4096;      // upper bound on CTAs of any reducing k
 // device scalar slots (PcgWork::scal)
 enum {
     S_RZ = 0,      // r.z of the current iterate
-    S_RZ_NEW = 1,  // r.z after the update
-    S_PAP = 2,     // p.Ap
-    S_RR = 3,      // r.r
+    S_PAP = 1,     // p.Ap
+    S_RZ_NEW = 2,  // r.z after the update     } adjacent: one 2-element all-reduce
+    S_RR = 3,      // r.r                      }
     S_BB = 4,      // b.b
     S_TOL2 = 5,    // rtol^2
     S_COUNT = 8
 };
+// Multi-GPU: kernels write their OWNED-DoF partial sums to PcgWork::dotLoc and an ncclAllReduce
+// delivers the global value into the scal slot; single-GPU: kernels write the scal slot directly.
+enum { DL_PAP = 0, DL_RZ_NEW = 1, DL_RR = 2, DL_COUNT = 4 };
 // status slots (PcgWork::status)
 enum { ST_ITERS = 0, ST_STATE = 1 };   // state: 0 running, 1 converged, 2 breakdown (p'Ap<=0), 3 nan
 
@@ -246,7 +249,7 @@ template <int N, int LPR, bool MASKED, bool DOT>
 __global__ void __launch_bounds__(kSpmvThreads, 4)   // <= 64 registers: 32 resident warps per SM
 k_bsr_spmv(int64_t nb, const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
            const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y,
-           const uint8_t *__restrict__ fixedMask, double *partials, unsigned *ticket, double *scal,
+           const uint8_t *__restrict__ fixedMask, double *partials, unsigned *ticket, double *dotOut,
            const int *status) {
     constexpr int NN = N * N;
     constexpr int RPW = 32 / LPR;                     // rows per warp
@@ -317,7 +320,7 @@ k_bsr_spmv(int64_t nb, const int64_t *__restrict__ rowptr, const int32_t *__rest
         block_reduce_store<1>(v1, partials);
         if (last_block(ticket)) {
             const double s = final_sum(partials, gridDim.x);
-            if (threadIdx.x == 0) scal[S_PAP] = s;
+            if (threadIdx.x == 0) dotOut[0] = s;
         }
     }
 }
@@ -325,10 +328,28 @@ k_bsr_spmv(int64_t nb, const int64_t *__restrict__ rowptr, const int32_t *__rest
 // ---------------------------------------------------------------------------
 // K5  block-Jacobi: invert the masked diagonal blocks.
 // ---------------------------------------------------------------------------
+// diagonal block of every row, plain row-major (multi-GPU: summed across sharers before inversion)
+template <int N>
+__global__ void k_diag_extract(int64_t nb, const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
+                               const double *__restrict__ vals, double *__restrict__ out) {
+    constexpr int NN = N * N;
+    const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (row >= nb) return;
+    int64_t lo = rowptr[row], hi = rowptr[row + 1];
+    const int64_t b0 = lo, end = hi;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (colidx[mid] < row) lo = mid + 1; else hi = mid;
+    }
+    const bool have = (lo < end) && (colidx[lo] == row);
+    for (int r = 0; r < N; ++r)
+        for (int c = 0; c < N; ++c) out[row * NN + r * N + c] = have ? vals[val_index<N>(b0, end - b0, lo - b0, r, c)] : 0.0;
+}
+
 template <int N>
 __global__ void k_jacobi_setup(int64_t nb, const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
                                const double *__restrict__ vals, const uint8_t *__restrict__ fixedMask,
-                               double *__restrict__ Minv, int *bad) {
+                               double *Minv, int *bad, bool preExtracted) {
     constexpr int NN = N * N;
     const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (row >= nb) return;
@@ -344,8 +365,19 @@ __global__ void k_jacobi_setup(int64_t nb, const int64_t *__restrict__ rowptr, c
     for (int r = 0; r < N; ++r)
 #pragma unroll
         for (int c = 0; c < N; ++c)
-            a[r][c] = have ? vals[val_index<N>(rowptr[row], end - rowptr[row], lo - rowptr[row], r, c)]
-                           : ((r == c) ? 1.0 : 0.0);
+            a[r][c] = preExtracted ? Minv[row * NN + r * N + c]
+                                   : (have ? vals[val_index<N>(rowptr[row], end - rowptr[row], lo - rowptr[row], r, c)]
+                                           : ((r == c) ? 1.0 : 0.0));
+    if (preExtracted) {      // DoF without any element on any rank: keep the identity
+        bool allZero = true;
+#pragma unroll
+        for (int r = 0; r < N; ++r)
+#pragma unroll
+            for (int c = 0; c < N; ++c) allZero = allZero && (a[r][c] == 0.0);
+        if (allZero)
+#pragma unroll
+            for (int r = 0; r < N; ++r) a[r][r] = 1.0;
+    }
     bool fx[N];
 #pragma unroll
     for (int r = 0; r < N; ++r) fx[r] = fixedMask[row * N + r] != 0;
@@ -387,12 +419,13 @@ __global__ void k_jacobi_setup(int64_t nb, const int64_t *__restrict__ rowptr, c
 // ---------------------------------------------------------------------------
 // K4  fused vector kernels (one thread per DoF block, grid-stride)
 // ---------------------------------------------------------------------------
-// init: r = mask(b); z = Minv r; p = z; x = 0; rz = r.z, rr = r.r (= b.b of the reduced system)
+// init: r = mask(b); z = Minv r; p = z; x = 0; partial sums of r.z and r.r over owned DoFs
 template <int N>
 __global__ void __launch_bounds__(kVecThreads)
 k_pcg_init(int64_t nb, const double *__restrict__ b, const uint8_t *__restrict__ fixedMask,
-           const double *__restrict__ Minv, double *__restrict__ x, double *__restrict__ r, double *__restrict__ z,
-           double *__restrict__ p, double *partials, unsigned *ticket, double *scal, int *status, double tol2) {
+           const uint8_t *__restrict__ owned, const double *__restrict__ Minv, double *__restrict__ x,
+           double *__restrict__ r, double *__restrict__ z, double *__restrict__ p, double *partials, unsigned *ticket,
+           double *dotOut /* [2]: rz, rr */) {
     constexpr int NN = N * N;
     double acc[2] = {0.0, 0.0};
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nb; i += (int64_t)gridDim.x * blockDim.x) {
@@ -406,35 +439,60 @@ k_pcg_init(int64_t nb, const double *__restrict__ b, const uint8_t *__restrict__
             for (int m = 0; m < N; ++m) s += Minv[i * NN + k * N + m] * rv[m];
             zv[k] = s;
         }
+        const double wgt = (owned && !owned[i]) ? 0.0 : 1.0;
 #pragma unroll
         for (int k = 0; k < N; ++k) {
             x[i * N + k] = 0.0; r[i * N + k] = rv[k]; z[i * N + k] = zv[k]; p[i * N + k] = zv[k];
-            acc[0] += rv[k] * zv[k];
-            acc[1] += rv[k] * rv[k];
+            acc[0] += wgt * rv[k] * zv[k];
+            acc[1] += wgt * rv[k] * rv[k];
         }
     }
     block_reduce_store<2>(acc, partials);
     if (last_block(ticket)) {
         const double rz = final_sum(partials, gridDim.x);
         const double rr = final_sum(partials + gridDim.x, gridDim.x);
-        if (threadIdx.x == 0) {
-            scal[S_RZ] = rz; scal[S_RR] = rr; scal[S_BB] = rr; scal[S_TOL2] = tol2;
-            status[ST_ITERS] = 0;
-            status[ST_STATE] = (rr == 0.0) ? 1 : ((rr != rr) ? 3 : 0);
-        }
+        if (threadIdx.x == 0) { dotOut[0] = rz; dotOut[1] = rr; }
     }
 }
 
-// update: alpha = rz/pAp; x += alpha p; r -= alpha Ap; z = Minv r; rz_new = r.z; rr = r.r
+// after the (all-reduced) initial sums are in scal[S_RZ_NEW], scal[S_RR]
+__global__ void k_pcg_init_finalize(double *scal, int *status, double tol2) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const double rr = scal[S_RR];
+    scal[S_RZ] = scal[S_RZ_NEW];
+    scal[S_BB] = rr;
+    scal[S_TOL2] = tol2;
+    status[ST_ITERS] = 0;
+    status[ST_STATE] = (rr == 0.0) ? 1 : ((rr != rr) ? 3 : 0);
+}
+
+// p.Ap over owned DoFs (multi-GPU only: Ap is complete only after the interface exchange)
+__global__ void __launch_bounds__(kVecThreads)
+k_dot_owned(int64_t nb, int N, const double *__restrict__ a, const double *__restrict__ b2,
+            const uint8_t *__restrict__ owned, double *partials, unsigned *ticket, double *dotOut, const int *status) {
+    if (status[ST_STATE] != 0) return;
+    double acc[1] = {0.0};
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nb; i += (int64_t)gridDim.x * blockDim.x) {
+        if (!owned[i]) continue;
+        for (int k = 0; k < N; ++k) acc[0] += a[i * N + k] * b2[i * N + k];
+    }
+    block_reduce_store<1>(acc, partials);
+    if (last_block(ticket)) {
+        const double s = final_sum(partials, gridDim.x);
+        if (threadIdx.x == 0) dotOut[0] = s;
+    }
+}
+
+// update: alpha = rz/pAp; x += alpha p; r -= alpha Ap; z = Minv r; partial sums of r.z and r.r
 template <int N>
 __global__ void __launch_bounds__(kVecThreads)
-k_pcg_update(int64_t nb, const double *__restrict__ Minv, const double *__restrict__ p, const double *__restrict__ Ap,
-             double *__restrict__ x, double *__restrict__ r, double *__restrict__ z, double *partials,
-             unsigned *ticket, double *scal, int *status) {
+k_pcg_update(int64_t nb, const double *__restrict__ Minv, const uint8_t *__restrict__ owned,
+             const double *__restrict__ p, const double *__restrict__ Ap, double *__restrict__ x,
+             double *__restrict__ r, double *__restrict__ z, double *partials, unsigned *ticket,
+             const double *__restrict__ scal, double *dotOut /* [2]: rz_new, rr */, const int *status) {
     constexpr int NN = N * N;
     if (status[ST_STATE] != 0) return;
-    const double pAp = scal[S_PAP];
-    const double alpha = scal[S_RZ] / pAp;
+    const double alpha = scal[S_RZ] / scal[S_PAP];
     double acc[2] = {0.0, 0.0};
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nb; i += (int64_t)gridDim.x * blockDim.x) {
         double rv[N], zv[N];
@@ -450,19 +508,36 @@ k_pcg_update(int64_t nb, const double *__restrict__ Minv, const double *__restri
             for (int m = 0; m < N; ++m) s += Minv[i * NN + k * N + m] * rv[m];
             zv[k] = s;
         }
+        const double wgt = (owned && !owned[i]) ? 0.0 : 1.0;
 #pragma unroll
         for (int k = 0; k < N; ++k) {
             r[i * N + k] = rv[k]; z[i * N + k] = zv[k];
-            acc[0] += rv[k] * zv[k];
-            acc[1] += rv[k] * rv[k];
+            acc[0] += wgt * rv[k] * zv[k];
+            acc[1] += wgt * rv[k] * rv[k];
         }
     }
     block_reduce_store<2>(acc, partials);
     if (last_block(ticket)) {
         const double rz = final_sum(partials, gridDim.x);
         const double rr = final_sum(partials + gridDim.x, gridDim.x);
+        if (threadIdx.x == 0) { dotOut[0] = rz; dotOut[1] = rr; }
+    }
+}
+
+// direction: beta = rz_new/rz; p = z + beta p.  The last CTA then closes the iteration on the
+// (global) scalars: rotates rz, counts the iteration, decides convergence / breakdown.
+template <int N>
+__global__ void __launch_bounds__(kVecThreads)
+k_pcg_direction(int64_t n, const double *__restrict__ z, double *__restrict__ p, double *scal, int *status,
+                unsigned *ticket) {
+    if (status[ST_STATE] != 0) return;
+    const double beta = scal[S_RZ_NEW] / scal[S_RZ];
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        p[i] = z[i] + beta * p[i];
+    if (last_block(ticket)) {
         if (threadIdx.x == 0) {
-            scal[S_RZ_NEW] = rz; scal[S_RR] = rr;
+            const double pAp = scal[S_PAP], rz = scal[S_RZ_NEW], rr = scal[S_RR];
+            scal[S_RZ] = rz;
             status[ST_ITERS] += 1;
             int st = 0;
             if (!(pAp > 0.0)) st = 2;
@@ -470,21 +545,6 @@ k_pcg_update(int64_t nb, const double *__restrict__ Minv, const double *__restri
             if (st == 0 && rr <= scal[S_TOL2] * scal[S_BB]) st = 1;
             status[ST_STATE] = st;     // written last; kernels of later iterations read it first
         }
-    }
-}
-
-// direction: beta = rz_new/rz; p = z + beta p; rz <- rz_new
-template <int N>
-__global__ void __launch_bounds__(kVecThreads)
-k_pcg_direction(int64_t n, const double *__restrict__ z, double *__restrict__ p, double *scal, const int *status,
-                unsigned *ticket) {
-    if (status[ST_STATE] != 0) return;
-    const double beta = scal[S_RZ_NEW] / scal[S_RZ];
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        p[i] = z[i] + beta * p[i];
-    // the last CTA rotates the scalar once every CTA has read it
-    if (last_block(ticket)) {
-        if (threadIdx.x == 0) scal[S_RZ] = scal[S_RZ_NEW];
     }
 }
 
@@ -532,11 +592,13 @@ void ensure_work(mfem_b200_ctx *c) {
     w.x.alloc(n); w.r.alloc(n); w.z.alloc(n); w.p.alloc(n); w.Ap.alloc(n); w.b.alloc(n); w.ufix.alloc(n);
     w.partials.alloc(4 * (size_t)kMaxPartials);
     w.scal.alloc(S_COUNT);
+    w.dotLoc.alloc(DL_COUNT);
     w.ticket.alloc(4);
     w.status.alloc(4);
     MFEM_CUDA(cudaMemsetAsync(w.ticket, 0, w.ticket.bytes(), c->stream));
     MFEM_CUDA(cudaMemsetAsync(w.status, 0, w.status.bytes(), c->stream));
     MFEM_CUDA(cudaMemsetAsync(w.scal, 0, w.scal.bytes(), c->stream));
+    MFEM_CUDA(cudaMemsetAsync(w.dotLoc, 0, w.dotLoc.bytes(), c->stream));
     if (c->fixedMask.n != n) {
         c->fixedMask.alloc(n);
         c->fixedVals.alloc(n);
@@ -551,7 +613,7 @@ static void launch_spmv_l(mfem_b200_ctx *c, const double *x, double *y, bool mas
     PcgWork &w = c->work;
     if (masked && dot)
         k_bsr_spmv<N, LPR, true, true><<<spmv_grid(c, LPR, k_bsr_spmv<N, LPR, true, true>), kSpmvThreads, 0, c->stream>>>(
-            c->nDofs, c->rowptr, c->colidx, c->vals, x, y, c->fixedMask, w.partials, w.ticket, w.scal, w.status);
+            c->nDofs, c->rowptr, c->colidx, c->vals, x, y, c->fixedMask, w.partials, w.ticket, w.scal.p + S_PAP, w.status);
     else if (masked)
         k_bsr_spmv<N, LPR, true, false><<<spmv_grid(c, LPR, k_bsr_spmv<N, LPR, true, false>), kSpmvThreads, 0, c->stream>>>(
             c->nDofs, c->rowptr, c->colidx, c->vals, x, y, c->fixedMask, nullptr, nullptr, nullptr, nullptr);
@@ -586,12 +648,20 @@ void build_preconditioner(mfem_b200_ctx *c) {
     if (c->Minv.n != n) c->Minv.alloc(n);
     DevBuf<int> bad(1);
     MFEM_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), c->stream));
+    const bool multi = c->nRanks > 1;
+    if (multi) {
+        // interface DoFs: the diagonal block is the sum of every sharer's partial block
+        if (c->N == 3) k_diag_extract<3><<<grid_for(c->nDofs, 256), 256, 0, c->stream>>>(c->nDofs, c->rowptr, c->colidx, c->vals, c->Minv);
+        else k_diag_extract<2><<<grid_for(c->nDofs, 256), 256, 0, c->stream>>>(c->nDofs, c->rowptr, c->colidx, c->vals, c->Minv);
+        c->launches++;
+        halo_exchange_add(c, c->Minv, c->N * c->N);
+    }
     if (c->N == 3)
         k_jacobi_setup<3><<<grid_for(c->nDofs, 256), 256, 0, c->stream>>>(c->nDofs, c->rowptr, c->colidx, c->vals,
-                                                                          c->fixedMask, c->Minv, bad);
+                                                                          c->fixedMask, c->Minv, bad, multi);
     else
         k_jacobi_setup<2><<<grid_for(c->nDofs, 256), 256, 0, c->stream>>>(c->nDofs, c->rowptr, c->colidx, c->vals,
-                                                                          c->fixedMask, c->Minv, bad);
+                                                                          c->fixedMask, c->Minv, bad, multi);
     c->launches++;
     int nbad = 0;
     MFEM_CUDA(cudaMemcpyAsync(&nbad, bad, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -602,14 +672,34 @@ void build_preconditioner(mfem_b200_ctx *c) {
     c->precondValid = true;
 }
 
+// y = mask(K x) completed across ranks: local SpMV, then the interface sum-exchange
+template <int N>
+static void spmv_exchanged(mfem_b200_ctx *c, const double *x, double *y, bool masked) {
+    launch_spmv<N>(c, x, y, masked, false);
+    halo_exchange_add(c, y, N);
+}
+
 template <int N>
 static void enqueue_iteration(mfem_b200_ctx *c) {
     PcgWork &w = c->work;
     const int64_t nb = c->nDofs, n = c->nvar();
     const int vgrid = vec_grid(c, nb);
-    launch_spmv<N>(c, w.p, w.Ap, true, true);
-    k_pcg_update<N><<<vgrid, kVecThreads, 0, c->stream>>>(nb, c->Minv, w.p, w.Ap, w.x, w.r, w.z, w.partials,
-                                                           w.ticket + 1, w.scal, w.status);
+    const bool multi = c->nRanks > 1;
+    const uint8_t *owned = multi ? halo_owned(c) : nullptr;
+    if (!multi) {
+        launch_spmv<N>(c, w.p, w.Ap, true, true);             // p.Ap fused into the SpMV epilogue
+    } else {
+        // masked rows stay zero through the exchange: every sharer masks the same DoFs
+        spmv_exchanged<N>(c, w.p, w.Ap, true);
+        k_dot_owned<<<vgrid, kVecThreads, 0, c->stream>>>(nb, N, w.p, w.Ap, owned, w.partials, w.ticket, w.dotLoc.p + DL_PAP,
+                                                         w.status);
+        c->launches++;
+        allreduce_sum(c, w.dotLoc.p + DL_PAP, w.scal.p + S_PAP, 1);
+    }
+    k_pcg_update<N><<<vgrid, kVecThreads, 0, c->stream>>>(nb, c->Minv, owned, w.p, w.Ap, w.x, w.r, w.z, w.partials,
+                                                           w.ticket + 1, w.scal,
+                                                           multi ? w.dotLoc.p + DL_RZ_NEW : w.scal.p + S_RZ_NEW, w.status);
+    if (multi) allreduce_sum(c, w.dotLoc.p + DL_RZ_NEW, w.scal.p + S_RZ_NEW, 2);
     k_pcg_direction<N><<<vec_grid(c, n), kVecThreads, 0, c->stream>>>(n, w.z, w.p, w.scal, w.status, w.ticket + 2);
     c->launches += 2;
 }
@@ -620,12 +710,18 @@ static void pcg_impl(mfem_b200_ctx *c, const double *f_int, double *u_int, doubl
     PcgWork &w = c->work;
     cudaStream_t s = c->stream;
     const int64_t nb = c->nDofs, n = c->nvar();
+    const bool multi = c->nRanks > 1;
+    const uint8_t *owned = multi ? halo_owned(c) : nullptr;
     // b = f - K ufix  (masked rows are zeroed by the init kernel)
-    launch_spmv<N>(c, c->fixedVals, w.Ap, false, false);
+    if (multi) spmv_exchanged<N>(c, c->fixedVals, w.Ap, false);
+    else launch_spmv<N>(c, c->fixedVals, w.Ap, false, false);
     k_axpby<<<vec_grid(c, n), kVecThreads, 0, s>>>(n, 1.0, f_int, -1.0, w.Ap, w.b);
-    k_pcg_init<N><<<vec_grid(c, nb), kVecThreads, 0, s>>>(nb, w.b, c->fixedMask, c->Minv, w.x, w.r, w.z, w.p, w.partials,
-                                                          w.ticket + 1, w.scal, w.status, rtol * rtol);
-    c->launches += 2;
+    k_pcg_init<N><<<vec_grid(c, nb), kVecThreads, 0, s>>>(nb, w.b, c->fixedMask, owned, c->Minv, w.x, w.r, w.z, w.p,
+                                                          w.partials, w.ticket + 1,
+                                                          multi ? w.dotLoc.p + DL_RZ_NEW : w.scal.p + S_RZ_NEW);
+    if (multi) allreduce_sum(c, w.dotLoc.p + DL_RZ_NEW, w.scal.p + S_RZ_NEW, 2);
+    k_pcg_init_finalize<<<1, 32, 0, s>>>(w.scal, w.status, rtol * rtol);
+    c->launches += 3;
     MFEM_CUDA(cudaGetLastError());
 
     cudaEvent_t e0, e1;
@@ -634,11 +730,12 @@ static void pcg_impl(mfem_b200_ctx *c, const double *f_int, double *u_int, doubl
 
     // The iteration is captured once into a CUDA graph of kBatch iterations; kernels turn
     // into no-ops as soon as the device-side state leaves "running", so the host only polls
-    // the 2-int status between graph launches.
+    // the 2-int status between graph launches.  (Multi-GPU: direct launches; the NCCL calls sit
+    // on the same stream between the kernels.)
     const int kBatch = 25;
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
-    if (c->opt_graph) {
+    if (c->opt_graph && !multi) {
         const int64_t launchesBefore = c->launches;
         MFEM_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
         for (int k = 0; k < kBatch; ++k) enqueue_iteration<N>(c);

@@ -41,6 +41,11 @@ def load_library():
         lib.mfemhost_material.argtypes = [c_int, c_char_p, POINTER(c_double), ctypes.c_char_p, c_int]
         lib.mfemhost_eval_expr.argtypes = [c_char_p, c_double, c_double, c_double, POINTER(c_double)]
         lib.mfemhost_save_mesh.argtypes = [c_void_p, c_char_p]
+        lib.mfemhost_partition.argtypes = [c_int, c_int64, POINTER(c_double), c_int64, c_int, POINTER(c_int32), c_int, c_int,
+                                           POINTER(c_int64)]
+        lib.mfemhost_partition_copy.argtypes = [POINTER(c_int64), POINTER(c_int64), POINTER(c_int32),
+                                                ctypes.POINTER(ctypes.c_uint8), POINTER(c_int32), POINTER(c_int64),
+                                                POINTER(c_int32)]
         _lib = lib
     return _lib
 
@@ -161,3 +166,31 @@ def from_arrays(dim, V, E) -> RawMesh:
     p = lib.mfemhost_from_arrays(dim, V3.shape[0], V3.ctypes.data_as(POINTER(c_double)), E.shape[0],
                                  E.ctypes.data_as(POINTER(c_int64)))
     return RawMesh(p, dim)
+
+
+def partition(m, n_parts, rank):
+    """Slab element partition of FEMMesh data `m` (from RawMesh.femmesh): this rank's local sub-mesh
+    and interface description (include/MeshFEM/Partition.hh).  Returns a SimpleNamespace with
+    elems, nodes (global ids), elem_nodes (local ids), local node coordinates, owned mask,
+    neighbor_ranks and shared[q] = local node ids shared with rank q (ascending global id)."""
+    lib = load_library()
+    nodes = np.ascontiguousarray(m.nodes, dtype=np.float64)
+    en = np.ascontiguousarray(m.elem_nodes, dtype=np.int32)
+    sz = (c_int64 * 5)()
+    if lib.mfemhost_partition(m.N, nodes.shape[0], nodes.ctypes.data_as(POINTER(c_double)), en.shape[0], en.shape[1],
+                              en.ctypes.data_as(POINTER(c_int32)), n_parts, rank, sz) != 0:
+        raise _err(lib)
+    ne, nn, nnb, nsh, nowned = (int(x) for x in sz)
+    p = SimpleNamespace(N=m.N, deg=m.deg, rank=rank, n_parts=n_parts, num_owned=nowned)
+    p.elems = np.zeros(ne, dtype=np.int64); p.nodes_global = np.zeros(nn, dtype=np.int64)
+    p.elem_nodes = np.zeros((ne, en.shape[1]), dtype=np.int32); p.owned = np.zeros(nn, dtype=np.uint8)
+    p.neighbor_ranks = np.zeros(nnb, dtype=np.int32); p.neighbor_offsets = np.zeros(nnb + 1, dtype=np.int64)
+    p.shared_local = np.zeros(nsh, dtype=np.int32)
+    ip, lp = POINTER(c_int32), POINTER(c_int64)
+    lib.mfemhost_partition_copy(p.elems.ctypes.data_as(lp), p.nodes_global.ctypes.data_as(lp), p.elem_nodes.ctypes.data_as(ip),
+                                p.owned.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), p.neighbor_ranks.ctypes.data_as(ip),
+                                p.neighbor_offsets.ctypes.data_as(lp), p.shared_local.ctypes.data_as(ip))
+    p.nodes = nodes[p.nodes_global]
+    p.num_nodes, p.num_elements = nn, ne
+    p.shared = {int(q): p.shared_local[p.neighbor_offsets[i]:p.neighbor_offsets[i + 1]] for i, q in enumerate(p.neighbor_ranks)}
+    return p

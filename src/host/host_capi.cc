@@ -4,6 +4,7 @@
 #include <MeshFEM/FEMMesh.hh>
 #include <MeshFEM/LinearElasticity.hh>
 #include <MeshFEM/Materials.hh>
+#include <MeshFEM/Partition.hh>
 #include <MeshFEM/MeshIO.hh>
 #include <MeshFEM/filters/gen_grid.hh>
 #include <MeshFEM/filters/hex_tet_subdiv.hh>
@@ -237,4 +238,29 @@ int mfemhost_save_mesh(void *m, const char *path) {
     catch (const std::exception &e) { g_err = e.what(); return -1; }
 }
 
+}  // extern "C"
+
+// ---- element partitioning (include/MeshFEM/Partition.hh) for the multi-GPU bench and tests
+namespace { thread_local Partition::LocalPart g_part; }
+extern "C" {
+// sizes5: [nLocalElems, nLocalNodes, nNeighbors, nSharedTotal, nOwned]
+int mfemhost_partition(int dim, int64_t nNodes, const double *nodes, int64_t nElems, int npe, const int32_t *elemNodes,
+                       int nParts, int rank, int64_t *sizes5) {
+    try {
+        auto part = Partition::slabPartition(dim, nNodes, nodes, nElems, npe, elemNodes, nParts);
+        g_part = Partition::extractPart(rank, nParts, nNodes, nElems, npe, elemNodes, part);
+        sizes5[0] = (int64_t)g_part.elems.size(); sizes5[1] = (int64_t)g_part.nodes.size();
+        sizes5[2] = (int64_t)g_part.neighborRanks.size(); sizes5[3] = (int64_t)g_part.sharedLocal.size();
+        int64_t owned = 0; for (auto o : g_part.owned) owned += o;
+        sizes5[4] = owned;
+        return 0;
+    } catch (const std::exception &e) { g_err = e.what(); return -1; }
+}
+int mfemhost_partition_copy(int64_t *elems, int64_t *nodes, int32_t *elemNodesLocal, uint8_t *owned, int32_t *neighborRanks,
+                            int64_t *neighborOffsets, int32_t *sharedLocal) {
+    auto cp = [](auto &v, auto *dst) { if (dst && !v.empty()) std::memcpy(dst, v.data(), v.size() * sizeof(v[0])); };
+    cp(g_part.elems, elems); cp(g_part.nodes, nodes); cp(g_part.elemNodes, elemNodesLocal); cp(g_part.owned, owned);
+    cp(g_part.neighborRanks, neighborRanks); cp(g_part.neighborOffsets, neighborOffsets); cp(g_part.sharedLocal, sharedLocal);
+    return 0;
+}
 }  // extern "C"
