@@ -1,0 +1,49 @@
+"""N>1 host-side logic on CPU: element partition + interface lists (C++ Partition.hh) and a gloo
+world-size-2/3 emulation of the distributed PCG (tests/mrank_cpu_worker.py)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from util import ROOT
+
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+
+@pytest.mark.parametrize("nparts", [2, 3, 4, 8])
+def test_partition_invariants(lib_built, nparts):
+    import workloads as wl
+    from meshfem_b200 import hostlib
+    m = wl.grid_femmesh((16, 2, 2), 2)
+    parts = [hostlib.partition(m, nparts, r) for r in range(nparts)]
+    # elements: a partition; nodes: owned exactly once
+    allel = np.concatenate([p.elems for p in parts])
+    assert np.array_equal(np.sort(allel), np.arange(m.num_elements))
+    sizes = [p.num_elements for p in parts]
+    assert max(sizes) - min(sizes) <= 1
+    owned_ids = np.concatenate([p.nodes_global[p.owned.astype(bool)] for p in parts])
+    assert np.array_equal(np.sort(owned_ids), np.arange(m.num_nodes))
+    for r, p in enumerate(parts):
+        # local connectivity refers to the same global nodes
+        assert np.array_equal(p.nodes_global[p.elem_nodes], m.elem_nodes[p.elems])
+        assert np.array_equal(p.nodes, m.nodes[p.nodes_global])
+        for q, idx in p.shared.items():
+            other = parts[q]
+            assert np.array_equal(p.nodes_global[idx], other.nodes_global[other.shared[r]])   # same order on both sides
+            assert np.all(np.diff(p.nodes_global[idx]) > 0)
+        # owner = lowest sharing rank
+        for q, idx in p.shared.items():
+            if q < r:
+                assert not p.owned[idx].any()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_distributed_pcg_gloo(lib_built, world):
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(29600 + world), os.path.join(ROOT, "tests", "mrank_cpu_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert "MRANK_CPU" in r.stdout
