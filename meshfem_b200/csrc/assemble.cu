@@ -22,7 +22,6 @@ namespace mfem {
 
 constexpr int kAsmWarps = 4;        // warps per CTA
 constexpr int kAsmSlots = 224;      // block accumulators per warp in shared memory
-constexpr int kChunk = 32;          // incidences per warp job
 
 template <int N>
 struct AsmSmem {
@@ -38,16 +37,106 @@ __device__ __forceinline__ int64_t lower_bound_i64(const int64_t *a, int64_t lo,
     return lo;
 }
 
-template <int N, int DEG, bool PER_ELEM_D>
-__global__ void __launch_bounds__(kAsmWarps * 32)
-k_assemble_gather(int64_t nJobs, int64_t nb, const int64_t *__restrict__ incPtr, const int32_t *__restrict__ incList,
-                  const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
-                  const int32_t *__restrict__ elemDof, const double *__restrict__ geom, const MatD Dc,
-                  const double *__restrict__ Delem, double *__restrict__ vals) {
+// One run of consecutive rows [r0, r1) whose blocks [s0, s1) are accumulated either in the warp's
+// shared-memory buffer (BIG = false) or, for a single row larger than the buffer, directly in HBM.
+template <int N, int DEG, bool PER_ELEM_D, bool BIG>
+__device__ __forceinline__ void asm_process_run(int lane, int64_t r0, int64_t r1, int64_t s0, int ns, double *acc,
+                                                int32_t *cols, const int64_t *__restrict__ incPtr,
+                                                const int32_t *__restrict__ incList, const int64_t *__restrict__ rowptr,
+                                                const int32_t *__restrict__ colidx, const int32_t *__restrict__ elemDof,
+                                                const double *__restrict__ geom, const MatD &Dc,
+                                                const double *__restrict__ Delem, double *__restrict__ vals) {
     constexpr int NPE = nodes_per_elem(N, DEG);
     constexpr int NN = N * N;
     constexpr int GS = 1 + N * (N + 1);
     constexpr int F = flat_len(N);
+    double *A = BIG ? vals + s0 * NN : acc;
+    for (int64_t k = lane; k < (int64_t)ns * NN; k += 32) A[k] = 0.0;
+    if (!BIG)
+        for (int k = lane; k < ns; k += 32) cols[k] = colidx[s0 + k];
+    __syncwarp();
+
+    const int64_t i0 = incPtr[r0], i1 = incPtr[r1];
+    for (int64_t tb = i0; tb < i1; tb += 32) {
+        const int64_t t = tb + lane;
+        const bool valid = t < i1;
+        int64_t e = 0;
+        int li = 0, rowBase = 0, rowLen = 0;
+        if (valid) {
+            const int32_t id = incList[t];
+            e = id / NPE;
+            li = id - (int)e * NPE;
+            int64_t r = r0;                     // row of this incidence: last r with incPtr[r] <= t
+            while (r + 1 < r1 && incPtr[r + 1] <= t) ++r;
+            rowBase = (int)(rowptr[r] - s0);
+            rowLen = (int)(rowptr[r + 1] - rowptr[r]);
+        }
+        ElemGeom<N> g;
+        {
+            const double *gp = geom + e * GS;
+            g.vol = gp[0];
+#pragma unroll
+            for (int r = 0; r < N; ++r)
+#pragma unroll
+                for (int a = 0; a <= N; ++a) g.G[r][a] = gp[1 + r * (N + 1) + a];
+        }
+        int32_t dofs[NPE];
+#pragma unroll
+        for (int j = 0; j < NPE; ++j) dofs[j] = elemDof[e * NPE + j];
+        const double *D = PER_ELEM_D ? Delem + e * (F * F) : Dc.d;
+        double *rowAcc = A + (int64_t)rowBase * NN;
+        const int planeStride = N * rowLen;
+
+        // lanes of one row start at different barycentric indices -> they meet a shared column
+        // block at different steps (fewer serialised same-block additions)
+        ke_row_slice_rot<N, DEG>(g, D, li, lane % (N + 1), [&](int j, const double blk[N][N]) {
+            // slot of column DoF dofs[j] inside this incidence's row (sorted colidx)
+            int jslot = 0;
+            if (valid) {
+                int lo = 0, hi = rowLen;
+                const int32_t want = dofs[j];
+                if (BIG) {
+                    const int32_t *rc = colidx + s0 + rowBase;
+                    while (lo < hi) { const int mid = (lo + hi) >> 1; if (rc[mid] < want) lo = mid + 1; else hi = mid; }
+                } else {
+                    const int32_t *rc = cols + rowBase;
+                    while (lo < hi) { const int mid = (lo + hi) >> 1; if (rc[mid] < want) lo = mid + 1; else hi = mid; }
+                }
+                jslot = lo;
+            }
+            // fixed-order accumulation: lanes hitting the same block add one after the other in
+            // lane (= element) order -> no atomics, reproducible sums
+            const unsigned key = valid ? (unsigned)(rowBase + jslot) : (0x40000000u | (unsigned)lane);
+            const unsigned peers = __match_any_sync(0xffffffffu, key);
+            const int rank = __popc(peers & ((1u << lane) - 1u));
+            const int maxRank = __reduce_max_sync(0xffffffffu, valid ? rank : 0);
+            double *dst = rowAcc + N * jslot;           // row-plane layout (core.cuh val_index)
+            for (int rr = 0; rr <= maxRank; ++rr) {
+                if (valid && rank == rr) {
+#pragma unroll
+                    for (int cc = 0; cc < N; ++cc)
+#pragma unroll
+                        for (int dd = 0; dd < N; ++dd) dst[cc * planeStride + dd] += blk[cc][dd];
+                }
+                __syncwarp();
+            }
+        });
+    }
+    __syncwarp();
+    if (!BIG) {
+        double *out = vals + s0 * NN;
+        for (int k = lane; k < ns * NN; k += 32) out[k] = acc[k];
+    }
+    __syncwarp();
+}
+
+template <int N, int DEG, bool PER_ELEM_D>
+__global__ void __launch_bounds__(kAsmWarps * 32)
+k_assemble_gather(int64_t nJobs, int64_t nb, const int64_t *__restrict__ jobRow, const int64_t *__restrict__ incPtr,
+                  const int32_t *__restrict__ incList, const int64_t *__restrict__ rowptr,
+                  const int32_t *__restrict__ colidx, const int32_t *__restrict__ elemDof,
+                  const double *__restrict__ geom, const MatD Dc, const double *__restrict__ Delem,
+                  double *__restrict__ vals) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     AsmSmem<N> &sm = *reinterpret_cast<AsmSmem<N> *>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -55,12 +144,10 @@ k_assemble_gather(int64_t nJobs, int64_t nb, const int64_t *__restrict__ incPtr,
     if (job >= nJobs) return;     // warp-uniform; no block-level barrier is used below
 
     // rows whose first incidence falls into this job's chunk of the incidence list
-    const int64_t t0 = job * kChunk, t1 = t0 + kChunk;
-    const int64_t rBegin = lower_bound_i64(incPtr, 0, nb + 1, t0);
-    const int64_t rEnd = lower_bound_i64(incPtr, rBegin, nb + 1, t1);
+    // (jobRow[k] = first row r with incPtr[r] >= k * kChunk, precomputed with the pattern)
+    const int64_t rBegin = jobRow[job], rEnd = jobRow[job + 1];
     if (rBegin >= rEnd || rBegin >= nb) return;
     const int64_t rStop = rEnd < nb ? rEnd : nb;
-
     double *acc = sm.acc[warp];
     int32_t *cols = sm.cols[warp];
 
@@ -70,84 +157,13 @@ k_assemble_gather(int64_t nJobs, int64_t nb, const int64_t *__restrict__ incPtr,
         const int64_t s0 = rowptr[r0];
         int64_t r1 = r0 + 1;
         while (r1 < rStop && rowptr[r1 + 1] - s0 <= kAsmSlots) ++r1;
-        const int64_t s1 = rowptr[r1];
-        const int ns = (int)(s1 - s0);
-        const bool big = ns > kAsmSlots;        // a single row larger than the buffer: accumulate in HBM
-        double *A = big ? vals + s0 * NN : acc;
-        const int32_t *C = big ? colidx + s0 : cols;
-        for (int64_t k = lane; k < (int64_t)ns * NN; k += 32) A[k] = 0.0;
-        if (!big)
-            for (int k = lane; k < ns; k += 32) cols[k] = colidx[s0 + k];
-        __syncwarp();
-
-        const int64_t i0 = incPtr[r0], i1 = incPtr[r1];
-        for (int64_t tb = i0; tb < i1; tb += 32) {
-            const int64_t t = tb + lane;
-            const bool valid = t < i1;
-            int64_t e = 0;
-            int li = 0, rowBase = 0, rowLen = 0;
-            if (valid) {
-                const int32_t id = incList[t];
-                e = id / NPE;
-                li = id - (int)e * NPE;
-                int64_t r = r0;                     // row of this incidence: last r with incPtr[r] <= t
-                while (r + 1 < r1 && incPtr[r + 1] <= t) ++r;
-                rowBase = (int)(rowptr[r] - s0);
-                rowLen = (int)(rowptr[r + 1] - rowptr[r]);
-            }
-            ElemGeom<N> g;
-            {
-                const double *gp = geom + e * GS;
-                g.vol = gp[0];
-#pragma unroll
-                for (int r = 0; r < N; ++r)
-#pragma unroll
-                    for (int a = 0; a <= N; ++a) g.G[r][a] = gp[1 + r * (N + 1) + a];
-            }
-            int32_t dofs[NPE];
-#pragma unroll
-            for (int j = 0; j < NPE; ++j) dofs[j] = elemDof[e * NPE + j];
-            const double *D = PER_ELEM_D ? Delem + e * (F * F) : Dc.d;
-
-            ke_row_slice<N, DEG>(g, D, li, [&](int j, const double blk[N][N]) {
-                // slot of column DoF dofs[j] inside this incidence's row (sorted colidx)
-                int slot = 0, jslot = 0;
-                if (valid) {
-                    int lo = 0, hi = rowLen;
-                    const int32_t want = dofs[j];
-                    const int32_t *rc = C + rowBase;
-                    while (lo < hi) {
-                        const int mid = (lo + hi) >> 1;
-                        if (rc[mid] < want) lo = mid + 1; else hi = mid;
-                    }
-                    jslot = lo;
-                    slot = rowBase + lo;
-                }
-                // fixed-order accumulation: lanes hitting the same block add one after the
-                // other in lane (= element) order -> no atomics, reproducible sums
-                const unsigned key = valid ? (unsigned)slot : (0x40000000u | (unsigned)lane);
-                const unsigned peers = __match_any_sync(0xffffffffu, key);
-                const int rank = __popc(peers & ((1u << lane) - 1u));
-                const int maxRank = __reduce_max_sync(0xffffffffu, valid ? rank : 0);
-                for (int rr = 0; rr <= maxRank; ++rr) {
-                    if (valid && rank == rr) {
-                        // row-plane layout (core.cuh val_index), relative to the run's first block
-                        double *dst = A + (int64_t)rowBase * NN + N * jslot;
-#pragma unroll
-                        for (int cc = 0; cc < N; ++cc)
-#pragma unroll
-                            for (int dd = 0; dd < N; ++dd) dst[cc * (N * rowLen) + dd] += blk[cc][dd];
-                    }
-                    __syncwarp();
-                }
-            });
-        }
-        __syncwarp();
-        if (!big) {
-            double *out = vals + s0 * NN;
-            for (int k = lane; k < ns * NN; k += 32) out[k] = acc[k];
-        }
-        __syncwarp();
+        const int ns = (int)(rowptr[r1] - s0);
+        if (ns > kAsmSlots)      // a single row larger than the buffer: accumulate in HBM
+            asm_process_run<N, DEG, PER_ELEM_D, true>(lane, r0, r1, s0, ns, acc, cols, incPtr, incList, rowptr, colidx,
+                                                      elemDof, geom, Dc, Delem, vals);
+        else
+            asm_process_run<N, DEG, PER_ELEM_D, false>(lane, r0, r1, s0, ns, acc, cols, incPtr, incList, rowptr, colidx,
+                                                       elemDof, geom, Dc, Delem, vals);
         r0 = r1;
     }
 }
@@ -203,18 +219,18 @@ template <int N, int DEG>
 static void launch_assemble(mfem_b200_ctx *c) {
     cudaStream_t s = c->stream;
     if (c->opt_assembly == 0) {
-        const int64_t nJobs = (c->totalInc + kChunk - 1) / kChunk;
+        const int64_t nJobs = (c->totalInc + kAsmChunk - 1) / kAsmChunk;
         const int grid = (int)((nJobs + kAsmWarps - 1) / kAsmWarps);
         const size_t smem = sizeof(AsmSmem<N>);
         if (c->perElemD) {
             auto kern = k_assemble_gather<N, DEG, true>;
             MFEM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            kern<<<grid, kAsmWarps * 32, smem, s>>>(nJobs, c->nDofs, c->incPtr, c->incList, c->rowptr, c->colidx,
+            kern<<<grid, kAsmWarps * 32, smem, s>>>(nJobs, c->nDofs, c->jobRow, c->incPtr, c->incList, c->rowptr, c->colidx,
                                                     c->elemDof, c->geom, c->Dconst, c->Delem, c->vals);
         } else {
             auto kern = k_assemble_gather<N, DEG, false>;
             MFEM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            kern<<<grid, kAsmWarps * 32, smem, s>>>(nJobs, c->nDofs, c->incPtr, c->incList, c->rowptr, c->colidx,
+            kern<<<grid, kAsmWarps * 32, smem, s>>>(nJobs, c->nDofs, c->jobRow, c->incPtr, c->incList, c->rowptr, c->colidx,
                                                     c->elemDof, c->geom, c->Dconst, nullptr, c->vals);
         }
         c->launches++;

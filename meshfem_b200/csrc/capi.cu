@@ -92,6 +92,9 @@ int mfem_b200_set_option(mfem_b200_handle h, const char *name, int64_t value) {
         h->opt_assembly = (int)value;
     } else if (n == "graph") {
         h->opt_graph = value != 0;
+    } else if (n == "spmv_kernel") {
+        MFEM_REQUIRE(value >= 0 && value <= 2, MFEM_B200_ERR_INVALID, "spmv_kernel must be 0 (auto), 1 (direct loads) or 2 (TMA ring)");
+        h->opt_spmv_kernel = (int)value;
     } else if (n == "spmv_lanes") {
         MFEM_REQUIRE(value == 0 || value == 8 || value == 16 || value == 32, MFEM_B200_ERR_INVALID,
                      "spmv_lanes must be 0 (auto), 8, 16 or 32");

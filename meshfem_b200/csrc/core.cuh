@@ -88,6 +88,7 @@ struct mfem_b200_ctx {
     int opt_reorder = 1;
     int opt_assembly = 0;
     int opt_graph = 1;
+    int opt_spmv_kernel = 0;               // 0 auto, 1 direct-load kernel, 2 TMA-ring kernel
     int opt_spmv_lanes = 0;                // lanes per block row in the SpMV (0 = choose from the mean row length)
 
     // mesh
@@ -112,11 +113,14 @@ struct mfem_b200_ctx {
     int64_t nnzb = 0;
     mfem::DevBuf<int64_t> rowptr;          // [nDofs+1]
     mfem::DevBuf<int32_t> colidx;          // [nnzb]
-    mfem::DevBuf<double> vals;             // [nnzb*N*N]  "row-plane" layout, see val_index()
+    mfem::DevBuf<double> vals;             // [nnzb*N*N (+2 pad)]  "row-plane" layout, see val_index()
+    mfem::DevBuf<int64_t> tileRow;         // [nTiles+1] first row of each kSpmvTileWindow-block window (TMA SpMV)
+    int64_t maxRowLen = 0;                 // longest block row
     // DoF -> incident (element, local node) lists
     int64_t totalInc = 0;
     mfem::DevBuf<int64_t> incPtr;          // [nDofs+1]
     mfem::DevBuf<int32_t> incList;         // [totalInc]  e*npe + i
+    mfem::DevBuf<int64_t> jobRow;          // [ceil(totalInc/kAsmChunk)+1] first row of each assembly job
     // element colouring (assembly mode 1)
     int nColors = 0;
     std::vector<int64_t> colorPtr;         // host: [nColors+1]
@@ -178,6 +182,9 @@ template <int N>
 __host__ __device__ __forceinline__ int64_t val_index(int64_t b0, int64_t n, int64_t j, int r, int c) {
     return (int64_t)N * N * b0 + (int64_t)r * (N * n) + (int64_t)N * j + c;
 }
+
+constexpr int kSpmvTileWindow = 512;  // blocks per tile window of the TMA-ring SpMV (solver.cu kTmaWindow)
+constexpr int kAsmChunk = 32;       // element incidences per warp job of the owner-gather assembly
 
 inline int grid_for(int64_t n, int block) { return static_cast<int>((n + block - 1) / block); }
 

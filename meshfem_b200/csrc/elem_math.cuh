@@ -204,6 +204,71 @@ MFEM_HD void ke_row_slice(const ElemGeom<N> &g, const double *D, int i, Emit &&e
     }
 }
 
+// Edges incident to each vertex (tet: 3 per vertex, triangle: 2), as local edge indices k with
+// edge_start(k) == v or edge_end(k) == v.
+template <int N>
+MFEM_HD int vertex_edge(int v, int t) {
+    // tet edges: 0:(0,1) 1:(1,2) 2:(2,0) 3:(0,3) 4:(2,3) 5:(1,3); triangle: first three
+    if (N == 3) {
+        const int tab[4][3] = {{0, 2, 3}, {0, 1, 5}, {1, 2, 4}, {3, 4, 5}};
+        return tab[v][t];
+    }
+    const int tab[3][2] = {{0, 2}, {0, 1}, {1, 2}};
+    return tab[v][t];
+}
+
+// Same row slice as ke_row_slice, but with a control flow that is UNIFORM across the lanes of a
+// warp whatever b each lane works on: (N+1) outer steps x (1 vertex column + N edge columns)
+// emits, and the barycentric index visited at outer step s is (s + rot) mod (N+1).  Lanes of a
+// warp that process incidences of the same DoF row use different `rot`, so they reach a shared
+// column block at different steps (fewer same-address accumulations per step).
+template <int N, int DEG, class Emit>
+MFEM_HD void ke_row_slice_rot(const ElemGeom<N> &g, const double *D, int i, int rot, Emit &&emit) {
+    const NodeTerms<N, DEG> ti = node_terms<N, DEG>(i);
+    double Q[flat_len(N)][N];
+    double S0[N][N], S1[N][N];
+    double blk[N][N];
+#pragma unroll
+    for (int c = 0; c < N; ++c)
+#pragma unroll
+        for (int d = 0; d < N; ++d) S1[c][d] = 0.0;
+#pragma unroll 1
+    for (int s = 0; s <= N; ++s) {
+        int b = s + rot;
+        if (b > N) b -= (N + 1);
+        contract_Q<N>(D, g, b, Q);
+        contract_S<N>(g, ti.a[0], Q, S0);
+        if (ti.n == 2) contract_S<N>(g, ti.a[1], Q, S1);
+        if (DEG == 1) {
+#pragma unroll
+            for (int c = 0; c < N; ++c)
+#pragma unroll
+                for (int d = 0; d < N; ++d) blk[c][d] = g.vol * S0[c][d];
+            emit(b, blk);
+        } else {
+#pragma unroll 1
+            for (int t = 0; t <= N; ++t) {
+                // t == 0: vertex column b; t >= 1: the t-th edge column touching vertex b
+                int col, pB;
+                bool colEdge;
+                if (t == 0) { col = b; pB = b; colEdge = false; }
+                else {
+                    const int k = vertex_edge<N>(b, t - 1);
+                    const int es = edge_start(k), ee = edge_end(k);
+                    col = N + 1 + k; pB = (es == b) ? ee : es; colEdge = true;
+                }
+                const double w0 = g.vol * w_coeff<N>(ti.edge, ti.p[0], colEdge, pB);
+                const double w1 = (ti.n == 2) ? g.vol * w_coeff<N>(ti.edge, ti.p[1], colEdge, pB) : 0.0;
+#pragma unroll
+                for (int c = 0; c < N; ++c)
+#pragma unroll
+                    for (int d = 0; d < N; ++d) blk[c][d] = w0 * S0[c][d] + w1 * S1[c][d];
+                emit(col, blk);
+            }
+        }
+    }
+}
+
 // Integrated shape-function gradient  int grad phi_i dV = vol * sum_a t[a] G[:,a]
 // (EmbeddedElement.hh:288-313 interpolant, integrated: Functions.hh:247-253).
 // Degree 2: vertex i -> (3 - N)/(N+1) * ... evaluates to mean of nodal values:

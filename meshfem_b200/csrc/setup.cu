@@ -158,6 +158,37 @@ __global__ void k_rowptr_from_keys32(int64_t nRows, int64_t nKeys, const uint32_
     rowptr[r] = lo;
 }
 
+// jobRow[k] = first row r with incPtr[r] >= k * chunk  (k = 0..nJobs; jobRow[nJobs] = nb + 1 sentinel side)
+__global__ void k_job_rows(int64_t nJobs, int64_t nb, int chunk, const int64_t *incPtr, int64_t *jobRow) {
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k > nJobs) return;
+    const int64_t target = k * chunk;
+    int64_t lo = 0, hi = nb + 1;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (incPtr[mid] < target) lo = mid + 1; else hi = mid;
+    }
+    jobRow[k] = lo;
+}
+
+// tileRow[t] = first row r with rowptr[r] >= t * window (t < nTiles); tileRow[nTiles] = nb
+__global__ void k_tile_rows(int64_t nTiles, int64_t nb, int window, const int64_t *rowptr, int64_t *tileRow) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t > nTiles) return;
+    if (t == nTiles) { tileRow[t] = nb; return; }
+    const int64_t target = t * window;
+    int64_t lo = 0, hi = nb;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (rowptr[mid] < target) lo = mid + 1; else hi = mid;
+    }
+    tileRow[t] = lo;
+}
+__global__ void k_max_row_len(int64_t nb, const int64_t *rowptr, unsigned long long *out) {
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r < nb) atomicMax(out, (unsigned long long)(rowptr[r + 1] - rowptr[r]));
+}
+
 static int bits_for(int64_t n) {
     int b = 1;
     while ((int64_t(1) << b) < n) ++b;
@@ -321,8 +352,8 @@ void build_pattern(mfem_b200_ctx *c) {
             c->nnzb = n;
         }
         keysSorted.free();
-        c->colidx.alloc((size_t)c->nnzb);
-        c->rowptr.alloc((size_t)nb + 1);
+        c->colidx.alloc((size_t)c->nnzb + 4);     // +16 B: bulk copies round the last tile up to 16 B
+        c->rowptr.alloc((size_t)nb + 1 + 2);      // +16 B pad for the same reason
         k_low32<<<grid_for(c->nnzb, 256), 256, 0, s>>>(c->nnzb, keys, c->colidx);
         k_rowptr_from_keys64<<<grid_for(nb + 1, 256), 256, 0, s>>>(nb, c->nnzb, keys, c->rowptr);
         c->launches += 2;
@@ -346,10 +377,27 @@ void build_pattern(mfem_b200_ctx *c) {
         k_rowptr_from_keys32<<<grid_for(nb + 1, 256), 256, 0, s>>>(nb, nInc, keysOut, c->incPtr);
         c->launches++;
         c->totalInc = nInc;
+        const int64_t nJobs = (nInc + kAsmChunk - 1) / kAsmChunk;
+        c->jobRow.alloc((size_t)nJobs + 1);
+        k_job_rows<<<grid_for(nJobs + 1, 256), 256, 0, s>>>(nJobs, nb, kAsmChunk, c->incPtr, c->jobRow);
+        c->launches++;
         MFEM_CUDA(cudaStreamSynchronize(s));
     }
+    {   // tiles of the TMA-ring SpMV + longest row
+        const int64_t nTiles = (c->nnzb + kSpmvTileWindow - 1) / kSpmvTileWindow;
+        c->tileRow.alloc((size_t)nTiles + 1);
+        k_tile_rows<<<grid_for(nTiles + 1, 256), 256, 0, s>>>(nTiles, nb, kSpmvTileWindow, c->rowptr, c->tileRow);
+        DevBuf<unsigned long long> mx(1);
+        MFEM_CUDA(cudaMemsetAsync(mx, 0, 8, s));
+        k_max_row_len<<<grid_for(nb, 256), 256, 0, s>>>(nb, c->rowptr, mx);
+        c->launches += 2;
+        unsigned long long hmx = 0;
+        MFEM_CUDA(cudaMemcpyAsync(&hmx, mx, 8, cudaMemcpyDeviceToHost, s));
+        MFEM_CUDA(cudaStreamSynchronize(s));
+        c->maxRowLen = (int64_t)hmx;
+    }
     MFEM_CUDA(cudaGetLastError());
-    c->vals.alloc((size_t)c->nnzb * c->N * c->N);
+    c->vals.alloc((size_t)c->nnzb * c->N * c->N + 2);
     c->patternValid = true;
     c->valuesValid = false;
     c->precondValid = false;

@@ -73,7 +73,7 @@ __device__ __forceinline__ bool last_block(unsigned *ticket) {
 
 // sum partials[k][0..n) in fixed order with one warp-shaped tree (whole block participates)
 __device__ __forceinline__ double final_sum(const double *partials, int n) {
-    __shared__ double red2[kVecThreads / 32];
+    __shared__ double red2[32];
     double s = 0.0;
     for (int i = threadIdx.x; i < n; i += blockDim.x) s += partials[i];
 #pragma unroll
@@ -321,6 +321,213 @@ k_bsr_spmv(int64_t nb, const int64_t *__restrict__ rowptr, const int32_t *__rest
         if (last_block(ticket)) {
             const double s = final_sum(partials, gridDim.x);
             if (threadIdx.x == 0) dotOut[0] = s;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K3b  bsr_spmv_tma: the same SpMV with the matrix stream decoupled from the compute warps.
+// One persistent CTA per SM.  A producer warp walks the CTA's tiles (a tile = the consecutive
+// block rows whose first block falls into a window of kTmaWindow blocks) and moves each tile's
+// values and column indices -- two contiguous byte ranges -- into a ring of shared-memory stages
+// with 1-D bulk TMA copies (cp.async.bulk, completion on an mbarrier, L2 evict-first policy).
+// Consumer warps wait on the stage's "full" barrier, pull rows of the tile off a shared counter
+// (dynamic balance), read values/indices with conflict-free LDS, gather x from L2, and signal the
+// stage's "empty" barrier when they leave the tile.  HBM requests in flight are then bounded by
+// the ring (kTmaStages x ~29 KB per SM), not by the registers of stalled warps.
+// ---------------------------------------------------------------------------
+constexpr int kTmaWindow = kSpmvTileWindow;     // blocks per tile window (tile table built in setup.cu)
+constexpr int kTmaMaxRow = 128;                 // longest block row the ring is sized for
+constexpr int kTmaStageBlocks = kTmaWindow + kTmaMaxRow;
+constexpr int kTmaStages = 4;
+constexpr int kTmaConsumers = 31;               // consumer warps
+constexpr int kTmaThreads = 32 * (kTmaConsumers + 1);
+
+template <int N>
+struct TmaStage {
+    double vals[kTmaStageBlocks * N * N + 2];   // +16 B: the copy starts at the 16 B boundary below the tile
+    long long rows[kTmaWindow + 4];             // rowptr[r0 .. r1] of the tile (when it has <= kTmaWindow rows)
+    long long hdr[4];                           // r0, r1, first block of the tile (written by the producer)
+    int32_t cols[kTmaStageBlocks + 8];
+};
+template <int N>
+struct TmaSmem {
+    TmaStage<N> stage[kTmaStages];
+    unsigned long long full[kTmaStages], empty[kTmaStages];
+    int next[kTmaStages];
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, unsigned long long *bar,
+                                             uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+        ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+
+template <int N, bool MASKED, bool DOT>
+__global__ void __launch_bounds__(kTmaThreads, 1)
+k_bsr_spmv_tma(int64_t nb, int64_t nTiles, const int64_t *__restrict__ tileRow, const int64_t *__restrict__ rowptr,
+               const int32_t *__restrict__ colidx, const double *__restrict__ vals, const double *__restrict__ x,
+               double *__restrict__ y, const uint8_t *__restrict__ fixedMask, double *partials, unsigned *ticket,
+               double *dotOut, const int *status) {
+    constexpr int NN = N * N;
+    constexpr int U = 3, LPR = 32, CH = U * LPR;
+    extern __shared__ __align__(128) unsigned char tma_smem_raw[];
+    TmaSmem<N> &sm = *reinterpret_cast<TmaSmem<N> *>(tma_smem_raw);
+    if (status && status[ST_STATE] != 0) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kTmaStages; ++s) {
+            mbar_init(&sm.full[s], 1);
+            mbar_init(&sm.empty[s], kTmaConsumers);
+            sm.next[s] = 0;
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    // tiles of this CTA: t = blockIdx.x + k * gridDim.x
+    const int64_t myTiles = (nTiles > blockIdx.x) ? (nTiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    double dot = 0.0;
+
+    if (warp == kTmaConsumers) {
+        // ===== producer warp: lanes fetch tile metadata in batches of 32, lane 0 issues the copies =====
+        const uint64_t pol = l2_policy_evict_first();
+        for (int64_t kb = 0; kb < myTiles; kb += 32) {
+            const int64_t k = kb + lane;
+            int64_t b0 = 0, b1 = 0, q0 = 0, q1 = 0;
+            if (k < myTiles) {
+                const int64_t t = blockIdx.x + k * gridDim.x;
+                q0 = tileRow[t];
+                q1 = tileRow[t + 1];
+                b0 = rowptr[q0];
+                b1 = rowptr[q1];
+            }
+            const int cnt = (int)((myTiles - kb < 32) ? (myTiles - kb) : 32);
+            for (int i = 0; i < cnt; ++i) {
+                const int64_t tb0 = __shfl_sync(0xffffffffu, b0, i), tb1 = __shfl_sync(0xffffffffu, b1, i);
+                const int64_t tr0 = __shfl_sync(0xffffffffu, q0, i), tr1 = __shfl_sync(0xffffffffu, q1, i);
+                if (lane == 0) {
+                    const int64_t kk = kb + i;
+                    const int s = (int)(kk % kTmaStages);
+                    if (kk >= kTmaStages) mbar_wait(&sm.empty[s], (uint32_t)(((kk / kTmaStages) - 1) & 1));
+                    sm.next[s] = 0;
+                    sm.stage[s].hdr[0] = tr0; sm.stage[s].hdr[1] = tr1; sm.stage[s].hdr[2] = tb0;
+                    // 16-byte aligned source ranges enclosing the tile's values / column indices
+                    const uintptr_t v0 = (uintptr_t)(vals + tb0 * NN), v1 = (uintptr_t)(vals + tb1 * NN);
+                    const uintptr_t c0 = (uintptr_t)(colidx + tb0), c1 = (uintptr_t)(colidx + tb1);
+                    const uintptr_t v0a = v0 & ~(uintptr_t)15, v1a = (v1 + 15) & ~(uintptr_t)15;
+                    const uintptr_t c0a = c0 & ~(uintptr_t)15, c1a = (c1 + 15) & ~(uintptr_t)15;
+                    const uint32_t vb = (uint32_t)(v1a - v0a), cb = (uint32_t)(c1a - c0a);
+                    // the tile's slice of rowptr travels too (unless it has too many -- empty -- rows)
+                    const uintptr_t p0 = (uintptr_t)(rowptr + tr0), p1 = (uintptr_t)(rowptr + tr1 + 1);
+                    const uintptr_t p0a = p0 & ~(uintptr_t)15, p1a = (p1 + 15) & ~(uintptr_t)15;
+                    const uint32_t pb = (tr1 - tr0 <= kTmaWindow) ? (uint32_t)(p1a - p0a) : 0u;
+                    mbar_arrive_expect_tx(&sm.full[s], vb + cb + pb);
+                    if (vb) tma_bulk_g2s(sm.stage[s].vals, (const void *)v0a, vb, &sm.full[s], pol);
+                    if (cb) tma_bulk_g2s(sm.stage[s].cols, (const void *)c0a, cb, &sm.full[s], pol);
+                    if (pb) tma_bulk_g2s(sm.stage[s].rows, (const void *)p0a, pb, &sm.full[s], pol);
+                }
+            }
+        }
+    } else {
+        // ===== consumer warps =====
+        const int comp = owner_component<N, LPR>(lane);
+        const uint64_t polKeep = l2_policy_evict_last();
+        int jj[U], cc[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int f = lane + u * LPR;
+            jj[u] = f / N;
+            cc[u] = f - jj[u] * N;
+        }
+        for (int64_t k = 0; k < myTiles; ++k) {
+            const int s = (int)(k % kTmaStages);
+            mbar_wait(&sm.full[s], (uint32_t)((k / kTmaStages) & 1));
+            const int64_t r0 = sm.stage[s].hdr[0], r1 = sm.stage[s].hdr[1], tb0 = sm.stage[s].hdr[2];
+            const double *sv = sm.stage[s].vals + (((uintptr_t)(vals + tb0 * NN) & 15) >> 3);
+            const int32_t *sc = sm.stage[s].cols + (((uintptr_t)(colidx + tb0) & 15) >> 2);
+            const bool rowsStaged = (r1 - r0) <= kTmaWindow;
+            const long long *sr = sm.stage[s].rows + (((uintptr_t)(rowptr + r0) & 15) >> 3);
+            while (true) {
+                int idx = 0;
+                if (lane == 0) idx = atomicAdd(&sm.next[s], 1);
+                idx = __shfl_sync(0xffffffffu, idx, 0);
+                const int64_t row = r0 + idx;
+                if (row >= r1) break;
+                const int64_t b0 = rowsStaged ? sr[idx] : rowptr[row];
+                const int L = (int)((rowsStaged ? sr[idx + 1] : rowptr[row + 1]) - b0) * N;
+                const double *v = sv + (b0 - tb0) * NN + lane;
+                const int32_t *ci = sc + (b0 - tb0);
+                double acc[N];
+#pragma unroll
+                for (int r = 0; r < N; ++r) acc[r] = 0.0;
+                for (int base = 0; base < L; base += CH, v += CH, ci += CH / N) {
+                    const int rem = L - base - lane;
+                    int col[U];
+                    double a[U][N], xv[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const bool ok = u * LPR < rem;
+                        col[u] = ok ? ci[jj[u]] : 0;
+#pragma unroll
+                        for (int r = 0; r < N; ++r) a[u][r] = ok ? v[r * L + u * LPR] : 0.0;
+                    }
+                    gather3(x + (col[0] * N + cc[0]), x + (col[1] * N + cc[1]), x + (col[2] * N + cc[2]), polKeep, xv);
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+#pragma unroll
+                        for (int r = 0; r < N; ++r) acc[r] = fma(a[u][r], xv[u], acc[r]);
+                }
+                const double out0 = fold_reduce<N, LPR>(acc, lane);
+                if (comp >= 0) {
+                    double out = out0;
+                    if (MASKED && fixedMask[row * N + comp]) out = 0.0;
+                    y[row * N + comp] = out;
+                    if (DOT) dot += out * x[row * N + comp];
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.empty[s]);
+        }
+    }
+    if (DOT) {
+        __shared__ double redT[kTmaThreads / 32];
+        double xsum = dot;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) xsum += __shfl_xor_sync(0xffffffffu, xsum, o);
+        if (lane == 0) redT[warp] = xsum;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double sum = 0.0;
+            for (int w = 0; w < kTmaThreads / 32; ++w) sum += redT[w];
+            partials[blockIdx.x] = sum;
+        }
+        if (last_block(ticket)) {
+            const double tot = final_sum(partials, gridDim.x);
+            if (threadIdx.x == 0) dotOut[0] = tot;
         }
     }
 }
@@ -623,8 +830,41 @@ static void launch_spmv_l(mfem_b200_ctx *c, const double *x, double *y, bool mas
     c->launches++;
 }
 
+static bool spmv_use_tma(mfem_b200_ctx *c) {
+    if (c->opt_spmv_kernel == 1) return false;
+    const bool fits = c->maxRowLen <= kTmaMaxRow && c->tileRow.n > 1;
+    if (c->opt_spmv_kernel == 2) {
+        MFEM_REQUIRE(fits, MFEM_B200_ERR_INVALID, "spmv_kernel=2 (TMA ring) needs block rows of at most 128 blocks");
+        return true;
+    }
+    // auto: the direct-load kernel is faster today (cfg3: 1.30 ms vs 1.63 ms); see DESIGN.md section 4
+    return false;
+}
+
+template <int N>
+static void launch_spmv_tma(mfem_b200_ctx *c, const double *x, double *y, bool masked, bool dot) {
+    PcgWork &w = c->work;
+    const int64_t nTiles = (int64_t)c->tileRow.n - 1;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(nTiles, sm_count(c)));
+    const size_t smem = sizeof(TmaSmem<N>);
+#define MFEM_TMA_LAUNCH(M_, D_, MASK_, PART_, TICK_, DOUT_, ST_)                                                        \
+    do {                                                                                                               \
+        auto kern = k_bsr_spmv_tma<N, M_, D_>;                                                                         \
+        static bool attr = false;                                                                                      \
+        if (!attr) { MFEM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; } \
+        kern<<<grid, kTmaThreads, smem, c->stream>>>(c->nDofs, nTiles, c->tileRow, c->rowptr, c->colidx, c->vals, x, y, MASK_, \
+                                                     PART_, TICK_, DOUT_, ST_);                                        \
+    } while (0)
+    if (masked && dot) MFEM_TMA_LAUNCH(true, true, c->fixedMask, w.partials, w.ticket, w.scal.p + S_PAP, w.status);
+    else if (masked) MFEM_TMA_LAUNCH(true, false, c->fixedMask, nullptr, nullptr, nullptr, nullptr);
+    else MFEM_TMA_LAUNCH(false, false, nullptr, nullptr, nullptr, nullptr, nullptr);
+#undef MFEM_TMA_LAUNCH
+    c->launches++;
+}
+
 template <int N>
 static void launch_spmv(mfem_b200_ctx *c, const double *x, double *y, bool masked, bool dot) {
+    if (spmv_use_tma(c)) { launch_spmv_tma<N>(c, x, y, masked, dot); return; }
     switch (spmv_lanes(c)) {
         case 8: launch_spmv_l<N, 8>(c, x, y, masked, dot); break;
         case 16: launch_spmv_l<N, 16>(c, x, y, masked, dot); break;

@@ -32,6 +32,30 @@ static void int_grads(const double *pts, double *out) {
     for (int i = 0; i < NPE; ++i) int_grad_phi<N, DEG>(g, i, out + i * N);
 }
 
+template <int N, int DEG>
+static void ke_full_rot(const double *pts, const double *D, double *Ke, int rot0) {
+    constexpr int NPE = nodes_per_elem(N, DEG);
+    double p[N + 1][N];
+    for (int v = 0; v <= N; ++v) for (int r = 0; r < N; ++r) p[v][r] = pts[v * N + r];
+    ElemGeom<N> g;
+    embed(p, g);
+    const int n = N * NPE;
+    std::memset(Ke, 0, sizeof(double) * n * n);
+    for (int i = 0; i < NPE; ++i) {
+        ke_row_slice_rot<N, DEG>(g, D, i, (rot0 + i) % (N + 1), [&](int j, const double blk[N][N]) {
+            for (int c = 0; c < N; ++c) for (int d = 0; d < N; ++d) Ke[(N * i + c) * n + N * j + d] += blk[c][d];
+        });
+    }
+}
+extern "C" int harness_ke_rot(int N, int deg, const double *pts, const double *D, double *Ke, int rot0) {
+    if (N == 2 && deg == 1) ke_full_rot<2, 1>(pts, D, Ke, rot0);
+    else if (N == 2 && deg == 2) ke_full_rot<2, 2>(pts, D, Ke, rot0);
+    else if (N == 3 && deg == 1) ke_full_rot<3, 1>(pts, D, Ke, rot0);
+    else if (N == 3 && deg == 2) ke_full_rot<3, 2>(pts, D, Ke, rot0);
+    else return 1;
+    return 0;
+}
+
 extern "C" int harness_ke(int N, int deg, const double *pts, const double *D, double *Ke, double *geom) {
     if (N == 2 && deg == 1) ke_full<2, 1>(pts, D, Ke, geom);
     else if (N == 2 && deg == 2) ke_full<2, 2>(pts, D, Ke, geom);

@@ -70,15 +70,16 @@ def test_assembly_is_bit_reproducible(mfem, N, deg, sizes):
     assert np.array_equal(vals[0], vals[1])
 
 
-@pytest.mark.parametrize("N,deg,sizes", CASES)
-@pytest.mark.parametrize("lanes", [0, 8, 16, 32])
-def test_spmv_and_apply_K(mfem, N, deg, sizes, lanes):
+@pytest.mark.parametrize("N,deg,sizes", CASES + [(3, 2, (9, 4, 3))])
+@pytest.mark.parametrize("lanes,kernel", [(0, 1), (8, 1), (16, 1), (32, 1), (0, 2)])
+def test_spmv_and_apply_K(mfem, N, deg, sizes, lanes, kernel):
+    """kernel 1 = direct-load SpMV (8/16/32 lanes per row), kernel 2 = TMA-ring SpMV."""
     mesh = grid_mesh(N, deg, sizes)
     D = _material(N, "ortho")
     rng = np.random.default_rng(5)
     x = rng.normal(size=(mesh.num_nodes, N))
     Kref = orc.stiffness_matrix(mesh, D)
-    with _handle(mfem, mesh, D, spmv_lanes=lanes) as h:
+    with _handle(mfem, mesh, D, spmv_lanes=lanes, spmv_kernel=kernel) as h:
         h.assemble()
         y = h.spmv(x)
         z = h.apply_K(x)
@@ -133,11 +134,11 @@ def test_loads_and_strain_stress(mfem, N, deg, sizes, mat):
 
 
 @pytest.mark.parametrize("N,deg,sizes", [(2, 1, (20, 4)), (2, 2, (10, 2)), (3, 1, (10, 2, 2)), (3, 2, (10, 2, 2))])
-@pytest.mark.parametrize("reorder", [0, 1])
-def test_cantilever_displacements_match_direct_solve(mfem, N, deg, sizes, reorder):
+@pytest.mark.parametrize("reorder,kernel", [(0, 1), (1, 1), (1, 2)])
+def test_cantilever_displacements_match_direct_solve(mfem, N, deg, sizes, reorder, kernel):
     sim, fixed, vals, f = cantilever_problem(N, deg, sizes)
     u_ref = sim.solve(f)
-    with _handle(mfem, sim.mesh, sim.D, reorder=reorder) as h:
+    with _handle(mfem, sim.mesh, sim.D, reorder=reorder, spmv_kernel=kernel) as h:
         h.assemble()
         h.fix_variables(fixed, vals)
         u, info = h.solve(f, rtol=1e-12, return_info=True)

@@ -19,11 +19,12 @@ def run(grid, deg, mat, rtols, direct=False, reorder=1):
     h.reset_timers(); h.assemble(); out["assemble2_s"] = h.timer("Assemble System")
     nb, nnzb = h.bsr_sizes(); out["nnzb"] = nnzb
     h.fix_variables(fixed, vals)
-    for lanes in (32, 16, 8, 0):
-        h.set_option("spmv_lanes", lanes)
+    for kern, lanes in ((1, 32), (1, 16), (2, 0)):
+        h.set_option("spmv_kernel", kern); h.set_option("spmv_lanes", lanes)
         spmv = h.time_spmv(20)
-        out[f"spmv_ms_l{lanes}"] = round(spmv * 1e3, 4)
-        out[f"spmv_GBs_l{lanes}"] = round((nnzb * 76 + nb * 52) / spmv / 1e9, 1)
+        out[f"spmv_ms_k{kern}l{lanes}"] = round(spmv * 1e3, 4)
+        out[f"spmv_GBs_k{kern}l{lanes}"] = round((nnzb * 76 + nb * 52) / spmv / 1e9, 1)
+    h.set_option("spmv_kernel", int(os.environ.get("SPMV_KERNEL", "0")))
     uref = None
     if direct:
         import meshfem_oracle as orc
