@@ -6,6 +6,7 @@
 #define MESHFEM_B200_ELASTICITYTENSOR_HH
 #include <MeshFEM/SymmetricMatrix.hh>
 
+#include <array>
 #include <cmath>
 #include <iomanip>
 #include <ostream>
@@ -112,6 +113,75 @@ public:
     // row i of D viewed as a flattened symmetric matrix (DRowAsSymMatrix)
     void addToRow(size_t i, const SMatrix &m) { for (size_t j = 0; j < F; ++j) m_d[i][j] += m[j]; }
     void symmetrizeFromFull() { for (size_t i = 0; i < F; ++i) for (size_t j = i + 1; j < F; ++j) m_d[j][i] = m_d[i][j]; }
+    // Orthotropic parameters of the tensor, read off its inverse (ElasticityTensor.hh:193-225 of the reference;
+    // shear entries of the flattened compliance are 1/(4 mu)).
+    void getOrthotropic3D(_Real &Ex, _Real &Ey, _Real &Ez, _Real &nuYX, _Real &nuZX, _Real &nuZY, _Real &muYZ, _Real &muZX,
+                          _Real &muXY) const {
+        if (_Dim != 3) throw std::runtime_error("getOrthotropic3D call on non-3D tensor");
+        const ElasticityTensor S = inverse();
+        Ex = 1.0 / S.D(0, 0), Ey = 1.0 / S.D(1, 1), Ez = 1.0 / S.D(2, 2);
+        nuYX = -S.D(0, 1) * Ey, nuZX = -S.D(0, 2) * Ez, nuZY = -S.D(1, 2) * Ez;
+        muYZ = 0.25 / S.D(3, 3), muZX = 0.25 / S.D(4, 4), muXY = 0.25 / S.D(5, 5);
+    }
+    void getOrthotropic2D(_Real &Ex, _Real &Ey, _Real &nuYX, _Real &muXY) const {
+        if (_Dim != 2) throw std::runtime_error("getOrthotropic2D call on non-2D tensor");
+        const ElasticityTensor S = inverse();
+        Ex = 1.0 / S.D(0, 0), Ey = 1.0 / S.D(1, 1);
+        nuYX = -S.D(0, 1) * Ey;
+        muXY = 0.25 / S.D(2, 2);
+    }
+    // mu_avg / mu_iso(E_avg, nu_avg)  (:251-268)
+    _Real anisotropy() const {
+        _Real muAvg, EAvg, nuAvg;
+        if (_Dim == 2) {
+            _Real Ex, Ey, nuYX, muXY;
+            getOrthotropic2D(Ex, Ey, nuYX, muXY);
+            EAvg = (Ex + Ey) / 2.0, nuAvg = nuYX, muAvg = muXY;
+        } else {
+            _Real Ex, Ey, Ez, nuYX, nuZX, nuZY, muYZ, muZX, muXY;
+            getOrthotropic3D(Ex, Ey, Ez, nuYX, nuZX, nuZY, muYZ, muZX, muXY);
+            EAvg = (Ex + Ey + Ez) / 3.0, nuAvg = (nuYX + nuZX + nuZY) / 3.0, muAvg = (muYZ + muZX + muXY) / 3.0;
+        }
+        return muAvg / (EAvg / (2 * (1 + nuAvg)));
+    }
+    // Eigenstrains E : s = lambda s (:555-579): ordinary symmetric eigenproblem of
+    // D^(1/2) F(E) D^(1/2) (D = shear doubler), eigenvalues ascending, strains[k] = D^(-1/2) q_k.
+    // Cyclic Jacobi on the F x F matrix (Eigen's SelfAdjointEigenSolver in the reference).
+    struct EigenDecomposition {
+        std::array<_Real, F> lambdas;
+        std::array<std::array<_Real, F>, F> strains;   // strains[k][component]
+    };
+    EigenDecomposition computeEigenstrains() const {
+        _Real A[F][F], Q[F][F];
+        const _Real rt2 = std::sqrt(2.0);
+        for (size_t i = 0; i < F; ++i) for (size_t j = 0; j < F; ++j) {
+            A[i][j] = D(i, j) * (i >= _Dim ? rt2 : 1.0) * (j >= _Dim ? rt2 : 1.0);
+            Q[i][j] = (i == j);
+        }
+        for (int sweep = 0; sweep < 64; ++sweep) {
+            _Real off = 0, diag = 0;
+            for (size_t i = 0; i < F; ++i) for (size_t j = 0; j < F; ++j) (i == j ? diag : off) += A[i][j] * A[i][j];
+            if (off <= 1e-32 * diag) break;
+            for (size_t p = 0; p < F; ++p) for (size_t q = p + 1; q < F; ++q) {
+                if (A[p][q] == 0.0) continue;
+                const _Real theta = (A[q][q] - A[p][p]) / (2.0 * A[p][q]);
+                const _Real t = (theta >= 0 ? 1.0 : -1.0) / (std::abs(theta) + std::sqrt(theta * theta + 1.0));
+                const _Real c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
+                for (size_t k = 0; k < F; ++k) { const _Real akp = A[k][p], akq = A[k][q]; A[k][p] = c * akp - s * akq; A[k][q] = s * akp + c * akq; }
+                for (size_t k = 0; k < F; ++k) { const _Real apk = A[p][k], aqk = A[q][k]; A[p][k] = c * apk - s * aqk; A[q][k] = s * apk + c * aqk; }
+                for (size_t k = 0; k < F; ++k) { const _Real qkp = Q[k][p], qkq = Q[k][q]; Q[k][p] = c * qkp - s * qkq; Q[k][q] = s * qkp + c * qkq; }
+            }
+        }
+        std::array<size_t, F> order;
+        for (size_t i = 0; i < F; ++i) order[i] = i;
+        for (size_t i = 0; i < F; ++i) for (size_t j = i + 1; j < F; ++j) if (A[order[j]][order[j]] < A[order[i]][order[i]]) std::swap(order[i], order[j]);
+        EigenDecomposition r;
+        for (size_t k = 0; k < F; ++k) {
+            r.lambdas[k] = A[order[k]][order[k]];
+            for (size_t i = 0; i < F; ++i) r.strains[k][i] = Q[i][order[k]] / (i >= _Dim ? rt2 : 1.0);
+        }
+        return r;
+    }
     _Real frobeniusNormSq() const { _Real s = 0; for (size_t i = 0; i < F; ++i) for (size_t j = 0; j < F; ++j) s += D(i, j) * D(i, j); return s; }
 
     // Isotropic-equivalent moduli read off a compliance-like inverse (PeriodicHomogenization_cli.cc:126-171)

@@ -5,7 +5,7 @@
 #include <MeshFEM/SymmetricMatrix.hh>
 #include <MeshFEM/Types.hh>
 
-enum class DomainType { PER_ELEMENT, PER_NODE, GUESS };
+enum class DomainType { PER_ELEMENT, PER_NODE, GUESS, ANY };
 enum FieldType { FIELD_SCALAR, FIELD_VECTOR, FIELD_MATRIX };
 
 template <typename _Real>
