@@ -68,8 +68,10 @@ int mfem_b200_comm_init(mfem_b200_handle h, int n_ranks, int rank, const void *n
 /* ---- options (before set_mesh) --------------------------------------------------- */
 /* "reorder": 1 (default) renumbers DoFs along a space-filling curve inside the handle;
  *            every ABI function still speaks the caller's numbering.
- * "assembly": 0 = owner-gather (default: every BSR block written exactly once),
- *             1 = graph-coloured element scatter (read-modify-write, no atomics).       */
+ * "assembly": 0 = block-owner (default: every BSR block summed by one thread from its sorted
+ *                 contribution list and written exactly once, coalesced),
+ *             1 = graph-coloured element scatter (read-modify-write, no atomics),
+ *             2 = owner-gather by DoF row (first-generation kernel, kept for A/B).      */
 int mfem_b200_set_option(mfem_b200_handle h, const char *name, int64_t value);
 
 /* ---- mesh ------------------------------------------------------------------------ */

@@ -4,7 +4,20 @@
 // Ke then a SERIAL triplet scatter) and the numeric half of TripletMatrix::sumRepeated
 // (SparseMatrices.hh:280-374).
 //
-// Mode 0 "owner-gather" (default).  The write pattern is turned inside out: instead of
+// Mode 0 "block-owner" (default).  Every BSR block is owned by one thread.  The symbolic phase
+// (setup.cu) sorted all (element, i, j) pairs by their block, so a block's contributions are a
+// contiguous list; the thread sums them in list (= element) order and the block is written to
+// HBM exactly once -- no atomics, no colouring, bit-reproducible.  The sum is done in "geometry
+// space": with a constant material
+//     K[r,c] = sum_e Ke[i,j] = C : ( sum_e vol_e sum_{a,b} W[i,a][j,b] G_a (x) G_b ) = C : M[r,c]
+// so a contribution costs one 3x3 accumulation of outer products (~36 FMA) and the 81-FMA
+// contraction with the elasticity tensor happens once per block (per contribution only with
+// per-element materials).  A CTA owns a chunk of 256 consecutive blocks; their lists are cut into
+// segments of <= 4 contributions handed to the threads in order of decreasing length (balanced
+// warps, coalesced interleaved id lists), the per-segment partial sums are combined per block in
+// shared memory in list order, and the chunk is written to HBM coalesced in the row-plane layout.
+//
+// Mode 2 "owner-gather" (first-generation kernel, kept for A/B).  Instead of
 // elements scattering 100 blocks each into shared rows (which needs atomics or colouring and
 // moves every block ~2.5 times through HBM as read-modify-write), the DoF rows own the work.
 // A warp takes a run of consecutive block rows whose element incidences fill ~one warp
@@ -169,6 +182,307 @@ k_assemble_gather(int64_t nJobs, int64_t nb, const int64_t *__restrict__ jobRow,
 }
 
 // ---------------------------------------------------------------------------
+// Mode 0: block-owner assembly.
+// Pair table (one entry per (i,j) of the element, built on the host from node_terms / w_coeff):
+//   idx  = barycentric-gradient indices a of the (up to two) terms of row node i (bytes 0,1) and
+//          column node j (bytes 2,3); the kernel reads G_a from the packed geometry records
+//   w[q] = W[i,a_ta][j,b_tb] for q = 2*ta + tb (0 where a term does not exist)
+struct PairTable {
+    std::vector<double> w;        // [4][npe*npe]
+    std::vector<uint32_t> idx;    // [npe*npe]
+};
+
+template <int N, int DEG>
+static PairTable make_pair_table() {
+    constexpr int NPE = nodes_per_elem(N, DEG), PP = NPE * NPE;
+    PairTable t;
+    t.w.assign(4 * PP, 0.0);
+    t.idx.assign(PP, 0);
+    for (int i = 0; i < NPE; ++i)
+        for (int j = 0; j < NPE; ++j) {
+            const NodeTerms<N, DEG> ti = node_terms<N, DEG>(i), tj = node_terms<N, DEG>(j);
+            const int ij = i * NPE + j;
+            const int a0 = ti.a[0], a1 = ti.n == 2 ? ti.a[1] : ti.a[0];
+            const int b0 = tj.a[0], b1 = tj.n == 2 ? tj.a[1] : tj.a[0];
+            t.idx[ij] = (uint32_t)a0 | ((uint32_t)a1 << 8) | ((uint32_t)b0 << 16) | ((uint32_t)b1 << 24);
+            for (int ta = 0; ta < ti.n; ++ta)
+                for (int tb = 0; tb < tj.n; ++tb)
+                    t.w[(2 * ta + tb) * PP + ij] = (DEG == 1) ? 1.0 : w_coeff<N>(ti.edge, ti.p[ta], tj.edge, tj.p[tb]);
+        }
+    return t;
+}
+
+// B[c][d] (+)= sum_{r,t} D[flat(r,c)][flat(d,t)] M[r][t]
+template <int N, bool ACC>
+__device__ __forceinline__ void contract_CM(const double *D, const double (&M)[N][N], double (&B)[N][N]) {
+    constexpr int F = flat_len(N);
+#pragma unroll
+    for (int c = 0; c < N; ++c)
+#pragma unroll
+        for (int d = 0; d < N; ++d) {
+            double s = ACC ? B[c][d] : 0.0;
+#pragma unroll
+            for (int r = 0; r < N; ++r)
+#pragma unroll
+                for (int t = 0; t < N; ++t) s = fma(D[flat_idx<N>(r, c) * F + flat_idx<N>(d, t)], M[r][t], s);
+            B[c][d] = s;
+        }
+}
+
+// Packed element geometry for the block-owner kernel: 4 slots of 32 bytes per element, slot a =
+// (G[0][a], G[1][a], G[2][a] (0 in 2D), vol) -- one 256-bit load fetches a gradient and the volume.
+template <int N>
+__global__ void k_pack_geom(int64_t nElems, const double *__restrict__ geom, double *__restrict__ geomP) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= nElems * 4) return;
+    const int64_t e = t >> 2;
+    const int a = (int)(t & 3);
+    constexpr int GS = 1 + N * (N + 1);
+    const double *g = geom + e * GS;
+    double o[4] = {0.0, 0.0, 0.0, g[0]};
+    if (a <= N)
+        for (int r = 0; r < N; ++r) o[r] = g[1 + r * (N + 1) + a];
+    for (int q = 0; q < 4; ++q) geomP[t * 4 + q] = o[q];
+}
+
+struct GeomSlot { double g[3], vol; };
+__device__ __forceinline__ GeomSlot ld_geom_slot(const double *p) {
+    GeomSlot s;
+    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(s.g[0]), "=d"(s.g[1]), "=d"(s.g[2]), "=d"(s.vol) : "l"(p));
+    return s;
+}
+
+__device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
+// Accumulate the contributions of one segment (pair ids read interleaved from `lp`, nIt trips of
+// the warp) into acc: M in geometry space, or -- with per-element materials -- the block itself.
+template <int N, int DEG, bool PER_ELEM_D, int PP>
+__device__ __forceinline__ void accumulate_segment(const uint32_t *lp, int nIt, const double *__restrict__ geomP,
+                                                   const double *__restrict__ Delem, const double (*sW)[PP],
+                                                   const uint32_t *sIdx, double (&acc)[N][N]) {
+    constexpr int F = flat_len(N);
+    uint32_t vnext = nIt > 0 ? ld_stream_u32(lp) : kPlanSentinel;
+    for (int it = 0; it < nIt; ++it) {
+        const uint32_t v = vnext;
+        if (it + 1 < nIt) vnext = ld_stream_u32(lp + 32 * (it + 1));
+        if (v == kPlanSentinel) continue;       // slots are sorted by length: only trailing lanes idle
+        const uint32_t e = v / (uint32_t)PP;
+        const int ij = (int)(v - e * (uint32_t)PP);
+        const uint32_t idx = sIdx[ij];
+        const double *g = geomP + (int64_t)e * 16;
+        const GeomSlot A0 = ld_geom_slot(g + 4 * (idx & 0xffu));
+        const GeomSlot B0 = ld_geom_slot(g + 4 * ((idx >> 16) & 0xffu));
+        const double vol = A0.vol;
+        double u0[N];
+        double Mc[N][N];
+        if (DEG == 1) {
+#pragma unroll
+            for (int r = 0; r < N; ++r) u0[r] = vol * A0.g[r];
+#pragma unroll
+            for (int r = 0; r < N; ++r)
+#pragma unroll
+                for (int q = 0; q < N; ++q) {
+                    if (PER_ELEM_D) Mc[r][q] = u0[r] * B0.g[q]; else acc[r][q] = fma(u0[r], B0.g[q], acc[r][q]);
+                }
+        } else {
+            const GeomSlot A1 = ld_geom_slot(g + 4 * ((idx >> 8) & 0xffu));
+            const GeomSlot B1 = ld_geom_slot(g + 4 * (idx >> 24));
+            double u1[N];
+            const double w00 = vol * sW[0][ij], w01 = vol * sW[1][ij], w10 = vol * sW[2][ij], w11 = vol * sW[3][ij];
+#pragma unroll
+            for (int r = 0; r < N; ++r) {
+                u0[r] = fma(w10, A1.g[r], w00 * A0.g[r]);     // pairs with column term 0
+                u1[r] = fma(w11, A1.g[r], w01 * A0.g[r]);     // pairs with column term 1
+            }
+#pragma unroll
+            for (int r = 0; r < N; ++r)
+#pragma unroll
+                for (int q = 0; q < N; ++q) {
+                    if (PER_ELEM_D) Mc[r][q] = fma(u1[r], B1.g[q], u0[r] * B0.g[q]);
+                    else acc[r][q] = fma(u1[r], B1.g[q], fma(u0[r], B0.g[q], acc[r][q]));
+                }
+        }
+        if (PER_ELEM_D) {
+            double De[F * F];
+            const double *dp = Delem + (int64_t)e * (F * F);
+#pragma unroll
+            for (int q = 0; q < F * F; ++q) De[q] = __ldg(dp + q);
+            contract_CM<N, true>(De, Mc, acc);
+        }
+    }
+}
+
+template <int N, int DEG, bool PER_ELEM_D>
+__global__ void __launch_bounds__(kBlkChunk, PER_ELEM_D ? 2 : 4)
+k_assemble_blocks(int64_t nnzb, const int32_t *__restrict__ chunkRow, const int64_t *__restrict__ rowptr,
+                  const uint16_t *__restrict__ planSegOff, const uint8_t *__restrict__ planNseg,
+                  const uint16_t *__restrict__ segOrder, const int64_t *__restrict__ warpBase,
+                  const uint32_t *__restrict__ list, const double *__restrict__ geomP, const MatD Dc,
+                  const double *__restrict__ Delem, const double *__restrict__ pairW,
+                  const uint32_t *__restrict__ pairIdx, double *__restrict__ vals) {
+    constexpr int NPE = nodes_per_elem(N, DEG);
+    constexpr int PP = NPE * NPE;
+    constexpr int NN = N * N;
+    __shared__ long long sRowPtr[kBlkChunk + 2];
+    __shared__ double sW[4][PP];
+    __shared__ uint32_t sIdx[PP];
+    __shared__ double sPart[kSegSlots * NN];      // per-segment partial sums; later the chunk's output staging
+    __shared__ long long sBase[kBlkChunk];
+    __shared__ int sStride[kBlkChunk];
+    const int t = threadIdx.x, lane = t & 31;
+    const int64_t chunk = blockIdx.x;
+    const int64_t k = chunk * kBlkChunk + t;
+    for (int q = t; q < PP; q += kBlkChunk) {
+        sIdx[q] = pairIdx[q];
+#pragma unroll
+        for (int w = 0; w < 4; ++w) sW[w][q] = pairW[w * PP + q];
+    }
+    // natural-order bookkeeping: segments of block (chunk, t), and where the block lives in HBM.
+    // The chunk's slice of rowptr is staged in shared memory so the row search costs one global
+    // round trip instead of one per bisection step.
+    int mySegs = 0, mySegOff = 0;
+    if (k < nnzb) { mySegs = planNseg[k]; mySegOff = planSegOff[k]; }
+    const int64_t rLo = chunkRow[chunk], rHi = chunkRow[chunk + 1];
+    const int nRowPtr = (int)min((int64_t)kBlkChunk, rHi - rLo + 1) + 1;      // rowptr[rLo .. rLo+nRowPtr-1]
+    if (t < nRowPtr) sRowPtr[t] = rowptr[rLo + t];
+    __syncthreads();
+    if (k < nnzb) {
+        int64_t lo = rLo, hi = rHi;
+        if (rHi - rLo + 1 <= kBlkChunk) {
+            int l = 0, h = (int)(rHi - rLo);
+            while (l < h) {                      // last row with rowptr[row] <= k
+                const int mid = (l + h + 1) >> 1;
+                if (sRowPtr[mid] <= k) l = mid; else h = mid - 1;
+            }
+            lo = rLo + l;
+            const int64_t b0 = sRowPtr[l], n = sRowPtr[l + 1] - b0;
+            sBase[t] = (long long)(NN * b0 + N * (k - b0));
+            sStride[t] = (int)(N * n);
+        } else {                                 // more than 256 (empty) rows inside one chunk: search in HBM
+            while (lo < hi) {
+                const int64_t mid = (lo + hi + 1) >> 1;
+                if (rowptr[mid] <= k) lo = mid; else hi = mid - 1;
+            }
+            const int64_t b0 = rowptr[lo], n = rowptr[lo + 1] - b0;
+            sBase[t] = (long long)(NN * b0 + N * (k - b0));
+            sStride[t] = (int)(N * n);
+        }
+    }
+    __syncthreads();
+
+    // phase 1: one segment per thread slot, two rounds
+#pragma unroll 1
+    for (int round = 0; round < kSegSlots / kBlkChunk; ++round) {
+        // warp-rounds are sorted by decreasing trip count: warp w takes the w-th longest in round 0 and
+        // the w-th shortest in round 1, so the warps of the CTA reach the barrier together
+        const int wrLocal = round == 0 ? (t >> 5) : (kSegSlots / 32 - 1 - (t >> 5));
+        const int slot = wrLocal * 32 + lane;
+        const int64_t wr = chunk * (kSegSlots / 32) + wrLocal;
+        const int64_t base = warpBase[wr];
+        const int nIt = (int)((warpBase[wr + 1] - base) >> 5);
+        if (nIt == 0) continue;                  // warp-uniform
+        const int sg = segOrder[chunk * kSegSlots + slot];
+        double acc[N][N];
+#pragma unroll
+        for (int r = 0; r < N; ++r)
+#pragma unroll
+            for (int q = 0; q < N; ++q) acc[r][q] = 0.0;
+        accumulate_segment<N, DEG, PER_ELEM_D, PP>(list + base + lane, nIt, geomP, Delem, sW, sIdx, acc);
+        if (sg != 0xffff) {
+#pragma unroll
+            for (int r = 0; r < N; ++r)
+#pragma unroll
+                for (int q = 0; q < N; ++q) sPart[(r * N + q) * kSegSlots + sg] = acc[r][q];
+        }
+    }
+    __syncthreads();
+
+    // phase 2: block (chunk, t) sums its segments in list order, then the material contraction
+    double out[N][N];
+    {
+        double M[N][N];
+#pragma unroll
+        for (int r = 0; r < N; ++r)
+#pragma unroll
+            for (int q = 0; q < N; ++q) M[r][q] = 0.0;
+        for (int p = 0; p < mySegs; ++p)
+#pragma unroll
+            for (int r = 0; r < N; ++r)
+#pragma unroll
+                for (int q = 0; q < N; ++q) M[r][q] += sPart[(r * N + q) * kSegSlots + mySegOff + p];
+        if (PER_ELEM_D) {
+#pragma unroll
+            for (int r = 0; r < N; ++r)
+#pragma unroll
+                for (int q = 0; q < N; ++q) out[r][q] = M[r][q];
+        } else {
+            contract_CM<N, false>(Dc.d, M, out);
+        }
+    }
+    __syncthreads();                             // all partials consumed: reuse sPart as output staging
+    double *sOut = sPart;
+#pragma unroll
+    for (int r = 0; r < N; ++r)
+#pragma unroll
+        for (int q = 0; q < N; ++q) sOut[(r * kBlkChunk + t) * N + q] = out[r][q];
+    __syncthreads();
+    // phase 3: coalesced write-out.  Plane r of the chunk is N*kBlkChunk scalars = N passes of the CTA;
+    // in pass m thread t owns scalar rem = t + m*kBlkChunk of every plane: consecutive threads ->
+    // consecutive addresses inside a block row.
+#pragma unroll
+    for (int m = 0; m < N; ++m) {
+        const int rem = t + m * kBlkChunk;
+        const int kb = rem / N, q = rem - kb * N;
+        if (chunk * kBlkChunk + kb < nnzb) {
+            double *dst = vals + sBase[kb] + q;
+            const int stride = sStride[kb];
+#pragma unroll
+            for (int r = 0; r < N; ++r) dst[(long long)r * stride] = sOut[r * (N * kBlkChunk) + rem];
+        }
+    }
+}
+
+template <int N, int DEG>
+static void launch_assemble_blocks(mfem_b200_ctx *c) {
+    cudaStream_t s = c->stream;
+    constexpr int PP = nodes_per_elem(N, DEG) * nodes_per_elem(N, DEG);
+    if (c->pairTabKey != N * 10 + DEG) {
+        const PairTable tab = make_pair_table<N, DEG>();
+        c->pairW.alloc(tab.w.size());
+        c->pairIdx.alloc(tab.idx.size());
+        MFEM_CUDA(cudaMemcpyAsync(c->pairW, tab.w.data(), tab.w.size() * 8, cudaMemcpyHostToDevice, s));
+        MFEM_CUDA(cudaMemcpyAsync(c->pairIdx, tab.idx.data(), tab.idx.size() * 4, cudaMemcpyHostToDevice, s));
+        MFEM_CUDA(cudaStreamSynchronize(s));     // `tab` is pageable host memory going out of scope
+        c->pairTabKey = N * 10 + DEG;
+    }
+    static_assert(PP <= 100, "pair table sized for at most 10 nodes per element");
+    if (!c->geomPValid) {
+        if (c->geomP.n != (size_t)c->nElems * 16) c->geomP.alloc((size_t)c->nElems * 16);
+        k_pack_geom<N><<<grid_for(c->nElems * 4, 256), 256, 0, s>>>(c->nElems, c->geom, c->geomP);
+        c->launches++;
+        c->geomPValid = true;
+    }
+    const int64_t nChunks = (c->nnzb + kBlkChunk - 1) / kBlkChunk;
+    // static shared memory ~45 KB per CTA: ask for the largest carve-out so 4-5 CTAs fit an SM
+    MFEM_CUDA(cudaFuncSetAttribute(k_assemble_blocks<N, DEG, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    MFEM_CUDA(cudaFuncSetAttribute(k_assemble_blocks<N, DEG, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    if (c->perElemD)
+        k_assemble_blocks<N, DEG, true><<<(unsigned)nChunks, kBlkChunk, 0, s>>>(
+            c->nnzb, c->planChunkRow, c->rowptr, c->planSegOff, c->planNseg, c->planSegOrder, c->planWarpBase, c->planList,
+            c->geomP, c->Dconst, c->Delem, c->pairW, c->pairIdx, c->vals);
+    else
+        k_assemble_blocks<N, DEG, false><<<(unsigned)nChunks, kBlkChunk, 0, s>>>(
+            c->nnzb, c->planChunkRow, c->rowptr, c->planSegOff, c->planNseg, c->planSegOrder, c->planWarpBase, c->planList,
+            c->geomP, c->Dconst, nullptr, c->pairW, c->pairIdx, c->vals);
+    c->launches++;
+    MFEM_CUDA(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------
 // Mode 1: coloured element scatter.  One thread per element of the colour; the element's
 // full Ke is produced row slice by row slice and added with plain loads/stores.
 template <int N, int DEG, bool PER_ELEM_D>
@@ -219,6 +533,8 @@ template <int N, int DEG>
 static void launch_assemble(mfem_b200_ctx *c) {
     cudaStream_t s = c->stream;
     if (c->opt_assembly == 0) {
+        launch_assemble_blocks<N, DEG>(c);
+    } else if (c->opt_assembly == 2) {
         const int64_t nJobs = (c->totalInc + kAsmChunk - 1) / kAsmChunk;
         const int grid = (int)((nJobs + kAsmWarps - 1) / kAsmWarps);
         const size_t smem = sizeof(AsmSmem<N>);

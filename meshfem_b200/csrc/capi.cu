@@ -88,12 +88,12 @@ int mfem_b200_set_option(mfem_b200_handle h, const char *name, int64_t value) {
         MFEM_REQUIRE(h->nElems == 0, MFEM_B200_ERR_INVALID, "option 'reorder' must be set before set_mesh");
         h->opt_reorder = value != 0;
     } else if (n == "assembly") {
-        MFEM_REQUIRE(value == 0 || value == 1, MFEM_B200_ERR_INVALID, "assembly must be 0 or 1");
+        MFEM_REQUIRE(value >= 0 && value <= 2, MFEM_B200_ERR_INVALID, "assembly must be 0 (block-owner), 1 (coloured) or 2 (owner-gather)");
         h->opt_assembly = (int)value;
     } else if (n == "graph") {
         h->opt_graph = value != 0;
     } else if (n == "spmv_kernel") {
-        MFEM_REQUIRE(value >= 0 && value <= 2, MFEM_B200_ERR_INVALID, "spmv_kernel must be 0 (auto), 1 (direct loads) or 2 (TMA ring)");
+        MFEM_REQUIRE(value >= 0 && value <= 3, MFEM_B200_ERR_INVALID, "spmv_kernel must be 0 (auto), 1 (direct loads), 2 (TMA ring) or 3 (index-pipelined)");
         h->opt_spmv_kernel = (int)value;
     } else if (n == "spmv_lanes") {
         MFEM_REQUIRE(value == 0 || value == 8 || value == 16 || value == 32, MFEM_B200_ERR_INVALID,

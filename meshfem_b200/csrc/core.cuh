@@ -102,6 +102,8 @@ struct mfem_b200_ctx {
     mfem::DevBuf<int32_t> ext2int, int2ext;  // [nDofs]
     mfem::DevBuf<double> geom;             // [nElems*(1+N*(N+1))]  vol, G
     bool geomValid = false;
+    mfem::DevBuf<double> geomP;            // [nElems*16] packed (G_a, vol) slots for the block-owner assembly
+    bool geomPValid = false;
 
     // material
     bool haveMaterial = false, perElemD = false;
@@ -121,6 +123,19 @@ struct mfem_b200_ctx {
     mfem::DevBuf<int64_t> incPtr;          // [nDofs+1]
     mfem::DevBuf<int32_t> incList;         // [totalInc]  e*npe + i
     mfem::DevBuf<int64_t> jobRow;          // [ceil(totalInc/kAsmChunk)+1] first row of each assembly job
+    // block-owner assembly plan (setup.cu k_plan_*): per chunk of kBlkChunk blocks
+    mfem::DevBuf<uint16_t> planCnt;        // [nnzb] element contributions per block (plan build only)
+    mfem::DevBuf<uint16_t> planSegOff;     // [nnzb] first segment of the block inside its chunk
+    mfem::DevBuf<uint8_t> planNseg;        // [nnzb] segments of the block
+    mfem::DevBuf<uint8_t> planChunkL;      // [nChunks] segment length of the chunk
+    mfem::DevBuf<uint16_t> planSegOrder;   // [nChunks*kSegSlots] segment (chunk-local id) of each thread slot, 0xffff = none
+    mfem::DevBuf<int64_t> planWarpBase;    // [nChunks*kSegSlots/32+1] first list entry of each warp-round
+    mfem::DevBuf<uint32_t> planList;       // [planEntries] interleaved pair ids e*npe^2 + i*npe + j, kPlanSentinel = none
+    mfem::DevBuf<int32_t> planChunkRow;    // [nChunks+1] block row containing the chunk's first block
+    int64_t planEntries = 0;
+    mfem::DevBuf<double> pairW;            // [4][npe*npe] W weights of the (i,j) pair table (assemble.cu)
+    mfem::DevBuf<uint32_t> pairIdx;        // [npe*npe]    packed gradient offsets
+    int pairTabKey = 0;                    // 10*N + deg the table was built for
     // element colouring (assembly mode 1)
     int nColors = 0;
     std::vector<int64_t> colorPtr;         // host: [nColors+1]
@@ -185,6 +200,9 @@ __host__ __device__ __forceinline__ int64_t val_index(int64_t b0, int64_t n, int
 
 constexpr int kSpmvTileWindow = 512;  // blocks per tile window of the TMA-ring SpMV (solver.cu kTmaWindow)
 constexpr int kAsmChunk = 32;       // element incidences per warp job of the owner-gather assembly
+constexpr int kBlkChunk = 256;      // BSR blocks per CTA of the block-owner assembly (one thread per block)
+constexpr int kSegSlots = 512;      // thread slots (segments) per chunk: two rounds of kBlkChunk threads
+constexpr uint32_t kPlanSentinel = 0xffffffffu;
 
 inline int grid_for(int64_t n, int block) { return static_cast<int>((n + block - 1) / block); }
 

@@ -189,6 +189,119 @@ __global__ void k_max_row_len(int64_t nb, const int64_t *rowptr, unsigned long l
     if (r < nb) atomicMax(out, (unsigned long long)(rowptr[r + 1] - rowptr[r]));
 }
 
+// ---- block-owner assembly plan (assemble.cu k_assemble_blocks) -----------------------------
+// Blocks are processed in chunks of kBlkChunk consecutive BSR blocks, one CTA per chunk.  The
+// contribution list of every block is cut into SEGMENTS of at most L pair ids (L = 4 unless a
+// chunk would then need more than kSegSlots segments), so that a vertex-row diagonal block with
+// 48 contributions costs twelve threads four loop trips each instead of one thread 48 trips.
+// The segments of a chunk are handed to the thread slots in order of decreasing length (the 32
+// lanes of a warp loop the same number of times); the pair ids of a warp-round are stored
+// interleaved (entry `it` of lane l at warpBase + 32*it + l, padded with kPlanSentinel) so that
+// every loop trip is one coalesced 128-byte load.
+__device__ __forceinline__ int plan_segments_of(int cnt, int L) { return (cnt + L - 1) / L; }
+
+__global__ void __launch_bounds__(kBlkChunk)
+k_plan_segments(int64_t nnzb, const int32_t *__restrict__ counts, uint16_t *__restrict__ planCnt,
+                uint16_t *__restrict__ planSegOff, uint8_t *__restrict__ planNseg,
+                uint8_t *__restrict__ chunkL, uint16_t *__restrict__ segOrder, int64_t *__restrict__ warpEntries,
+                int *__restrict__ overflow) {
+    typedef cub::BlockScan<int, kBlkChunk> Scan;
+    typedef cub::BlockReduce<int, kBlkChunk> Reduce;
+    typedef cub::BlockRadixSort<uint32_t, kBlkChunk, 2, uint32_t> Sort;
+    __shared__ union { typename Scan::TempStorage scan; typename Reduce::TempStorage red; typename Sort::TempStorage sort; } temp;
+    __shared__ int sTotal;
+    __shared__ uint16_t sLen[kSegSlots], sLenSorted[kSegSlots], sIdxSorted[kSegSlots];
+    const int t = threadIdx.x;
+    const int64_t chunk = blockIdx.x, k = chunk * kBlkChunk + t;
+    int cnt = k < nnzb ? counts[k] : 0;
+    if (cnt > 65535) { atomicExch(overflow, 1); cnt = 65535; }
+    int L = 4;
+    while (true) {
+        // (a block with more than 255 segments counts as "too many" so that nseg fits a byte)
+        const int mine = plan_segments_of(cnt, L);
+        const int tot = Reduce(temp.red).Sum(mine > 255 ? kSegSlots + 1 : mine);
+        if (t == 0) sTotal = tot;
+        __syncthreads();
+        const bool ok = sTotal <= kSegSlots;
+        __syncthreads();
+        if (ok) break;
+        L *= 2;
+    }
+    const int nseg = plan_segments_of(cnt, L);
+    int off;
+    Scan(temp.scan).ExclusiveSum(nseg, off);
+    for (int j = t; j < kSegSlots; j += kBlkChunk) sLen[j] = 0;
+    __syncthreads();
+    for (int p = 0; p < nseg; ++p) sLen[off + p] = (uint16_t)min(L, cnt - p * L);
+    __syncthreads();
+    uint32_t key[2] = {sLen[2 * t], sLen[2 * t + 1]};
+    uint32_t val[2] = {(uint32_t)(2 * t), (uint32_t)(2 * t + 1)};
+    Sort(temp.sort).SortDescending(key, val);        // stable; blocked: thread t holds ranks 2t, 2t+1
+    for (int i = 0; i < 2; ++i) { sLenSorted[2 * t + i] = (uint16_t)key[i]; sIdxSorted[2 * t + i] = (uint16_t)val[i]; }
+    __syncthreads();
+    for (int j = t; j < kSegSlots; j += kBlkChunk)
+        segOrder[chunk * kSegSlots + j] = sLenSorted[j] ? sIdxSorted[j] : (uint16_t)0xffff;
+    if (t < kSegSlots / 32) warpEntries[chunk * (kSegSlots / 32) + t] = 32 * (int64_t)sLenSorted[32 * t];
+    if (k < nnzb) { planCnt[k] = (uint16_t)cnt; planSegOff[k] = (uint16_t)off; planNseg[k] = (uint8_t)nseg; }
+    if (t == 0) chunkL[chunk] = (uint8_t)L;
+}
+
+__global__ void __launch_bounds__(kBlkChunk)
+k_plan_fill(int64_t nnzb, const uint16_t *__restrict__ planCnt, const uint8_t *__restrict__ chunkL,
+            const int32_t *__restrict__ blockStart, const uint32_t *__restrict__ sortedPairs,
+            const uint16_t *__restrict__ segOrder, const int64_t *__restrict__ warpBase, uint32_t *__restrict__ list) {
+    typedef cub::BlockScan<int, kBlkChunk> Scan;
+    __shared__ typename Scan::TempStorage temp;
+    __shared__ int sOff[kBlkChunk + 1], sCnt[kBlkChunk];
+    const int t = threadIdx.x;
+    const int64_t chunk = blockIdx.x, k = chunk * kBlkChunk + t;
+    const int cnt = k < nnzb ? planCnt[k] : 0;
+    const int L = chunkL[chunk];
+    int off, total;
+    Scan(temp).ExclusiveSum(plan_segments_of(cnt, L), off, total);
+    sOff[t] = off; sCnt[t] = cnt;
+    if (t == 0) sOff[kBlkChunk] = total;
+    __syncthreads();
+    for (int j = t; j < kSegSlots; j += kBlkChunk) {
+        const int64_t wr = chunk * (kSegSlots / 32) + (j >> 5);
+        const int64_t base = warpBase[wr];
+        const int nIt = (int)((warpBase[wr + 1] - base) >> 5);
+        const int sg = segOrder[chunk * kSegSlots + j];
+        int len = 0;
+        int64_t start = 0;
+        if (sg != 0xffff) {
+            int lo = 0, hi = kBlkChunk - 1;           // last block kb with sOff[kb] <= sg and a segment of its own
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (sOff[mid] <= sg) lo = mid; else hi = mid - 1;
+            }
+            const int part = sg - sOff[lo];
+            len = min(L, sCnt[lo] - part * L);
+            start = (int64_t)blockStart[chunk * kBlkChunk + lo] + (int64_t)part * L;
+        }
+        for (int it = 0; it < nIt; ++it) list[base + 32 * (int64_t)it + (j & 31)] = it < len ? sortedPairs[start + it] : kPlanSentinel;
+    }
+}
+
+// chunkRow[c] = block row containing block min(c * kBlkChunk, nnzb - 1), c = 0..nChunks
+__global__ void k_chunk_rows(int64_t nChunks, int64_t nb, int64_t nnzb, const int64_t *rowptr, int32_t *chunkRow) {
+    const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c > nChunks) return;
+    int64_t k = c * kBlkChunk;
+    if (k > nnzb - 1) k = nnzb - 1;
+    int64_t lo = 0, hi = nb - 1;                     // last r with rowptr[r] <= k
+    while (lo < hi) {
+        const int64_t mid = (lo + hi + 1) >> 1;
+        if (rowptr[mid] <= k) lo = mid; else hi = mid - 1;
+    }
+    chunkRow[c] = (int32_t)lo;
+}
+
+__global__ void k_iota_u32(int64_t n, uint32_t *a) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) a[i] = (uint32_t)i;
+}
+
 static int bits_for(int64_t n) {
     int b = 1;
     while ((int64_t(1) << b) < n) ++b;
@@ -307,6 +420,7 @@ void compute_geometry(mfem_b200_ctx *c) {
     MFEM_CUDA(cudaStreamSynchronize(s));
     MFEM_CUDA(cudaGetLastError());
     c->geomValid = true;
+    c->geomPValid = false;
     c->valuesValid = false;
     if (nneg > 0)
         throw CudaError(MFEM_B200_ERR_NEG_VOLUME,
@@ -328,24 +442,33 @@ void build_pattern(mfem_b200_ctx *c) {
                  "pattern build: more than 2^31 element block pairs on one device; partition the mesh");
     const int dofBits = bits_for(nb + 1);
 
-    {   // ---- block pattern
+    {   // ---- block pattern + the per-block element contribution lists
+        // key = (row DoF, col DoF), value = pair id e*npe*npe + i*npe + j; the stable sort keeps the
+        // contributions of a block in element order (fixed summation order => reproducible values)
         DevBuf<uint64_t> keys((size_t)nPairs), keysSorted((size_t)nPairs);
+        DevBuf<uint32_t> pairs((size_t)nPairs), pairsSorted((size_t)nPairs);
         k_pair_keys<<<grid_for(nPairs, 256), 256, 0, s>>>(c->nElems, npe, c->elemDof, keys);
-        c->launches++;
+        k_iota_u32<<<grid_for(nPairs, 256), 256, 0, s>>>(nPairs, pairs);
+        c->launches += 2;
         size_t tmpBytes = 0;
-        MFEM_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmpBytes, keys.p, keysSorted.p, nPairs, 0, 32 + dofBits, s));
+        MFEM_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmpBytes, keys.p, keysSorted.p, pairs.p, pairsSorted.p, nPairs,
+                                                  0, 32 + dofBits, s));
         {
             DevBuf<uint8_t> tmp(tmpBytes);
-            MFEM_CUDA(cub::DeviceRadixSort::SortKeys(tmp.p, tmpBytes, keys.p, keysSorted.p, nPairs, 0, 32 + dofBits, s));
+            MFEM_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmpBytes, keys.p, keysSorted.p, pairs.p, pairsSorted.p,
+                                                      nPairs, 0, 32 + dofBits, s));
             MFEM_CUDA(cudaStreamSynchronize(s));
         }
-        // unique into `keys` (reused as output)
+        pairs.free();
+        // run-length encode: unique keys (into `keys`, reused as output) + contributions per block
+        DevBuf<int32_t> counts((size_t)nPairs);   // at most one run per pair
         DevBuf<int> nSel(1);
         tmpBytes = 0;
-        MFEM_CUDA(cub::DeviceSelect::Unique(nullptr, tmpBytes, keysSorted.p, keys.p, nSel.p, (int)nPairs, s));
+        MFEM_CUDA(cub::DeviceRunLengthEncode::Encode(nullptr, tmpBytes, keysSorted.p, keys.p, counts.p, nSel.p, (int)nPairs, s));
         {
             DevBuf<uint8_t> tmp(tmpBytes);
-            MFEM_CUDA(cub::DeviceSelect::Unique(tmp.p, tmpBytes, keysSorted.p, keys.p, nSel.p, (int)nPairs, s));
+            MFEM_CUDA(cub::DeviceRunLengthEncode::Encode(tmp.p, tmpBytes, keysSorted.p, keys.p, counts.p, nSel.p,
+                                                         (int)nPairs, s));
             int n = 0;
             MFEM_CUDA(cudaMemcpyAsync(&n, nSel, sizeof(int), cudaMemcpyDeviceToHost, s));
             MFEM_CUDA(cudaStreamSynchronize(s));
@@ -358,6 +481,53 @@ void build_pattern(mfem_b200_ctx *c) {
         k_rowptr_from_keys64<<<grid_for(nb + 1, 256), 256, 0, s>>>(nb, c->nnzb, keys, c->rowptr);
         c->launches += 2;
         MFEM_CUDA(cudaStreamSynchronize(s));
+        keys.free();
+
+        // ---- plan of the block-owner assembly
+        const int64_t nChunks = (c->nnzb + kBlkChunk - 1) / kBlkChunk;
+        DevBuf<int32_t> blockStart((size_t)c->nnzb);
+        tmpBytes = 0;
+        MFEM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, counts.p, blockStart.p, (int)c->nnzb, s));
+        {
+            DevBuf<uint8_t> tmp(tmpBytes);
+            MFEM_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmpBytes, counts.p, blockStart.p, (int)c->nnzb, s));
+        }
+        const int64_t nWarpRounds = nChunks * (kSegSlots / 32);
+        c->planCnt.alloc((size_t)c->nnzb);
+        c->planSegOff.alloc((size_t)c->nnzb);
+        c->planNseg.alloc((size_t)c->nnzb);
+        c->planChunkL.alloc((size_t)nChunks);
+        c->planSegOrder.alloc((size_t)nChunks * kSegSlots);
+        c->planWarpBase.alloc((size_t)nWarpRounds + 1);
+        MFEM_CUDA(cudaMemsetAsync(c->planWarpBase, 0, c->planWarpBase.bytes(), s));
+        DevBuf<int> overflow(1);
+        MFEM_CUDA(cudaMemsetAsync(overflow, 0, sizeof(int), s));
+        k_plan_segments<<<(unsigned)nChunks, kBlkChunk, 0, s>>>(c->nnzb, counts, c->planCnt, c->planSegOff, c->planNseg, c->planChunkL, c->planSegOrder,
+                                                               c->planWarpBase, overflow);
+        c->launches++;
+        tmpBytes = 0;
+        MFEM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, c->planWarpBase.p, c->planWarpBase.p, (int)(nWarpRounds + 1), s));
+        int64_t planEntries = 0;
+        {
+            DevBuf<uint8_t> tmp(tmpBytes);
+            MFEM_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmpBytes, c->planWarpBase.p, c->planWarpBase.p,
+                                                    (int)(nWarpRounds + 1), s));
+            int ovf = 0;
+            MFEM_CUDA(cudaMemcpyAsync(&planEntries, c->planWarpBase.p + nWarpRounds, 8, cudaMemcpyDeviceToHost, s));
+            MFEM_CUDA(cudaMemcpyAsync(&ovf, overflow, sizeof(int), cudaMemcpyDeviceToHost, s));
+            MFEM_CUDA(cudaStreamSynchronize(s));
+            MFEM_REQUIRE(ovf == 0, MFEM_B200_ERR_INVALID, "pattern build: a block receives more than 65535 element contributions");
+        }
+        c->planEntries = planEntries;
+        c->timers["Plan Padding Ratio"] = (double)planEntries / (double)nPairs;   // diagnostic, not a time
+        c->planList.alloc((size_t)planEntries + 32);
+        k_plan_fill<<<(unsigned)nChunks, kBlkChunk, 0, s>>>(c->nnzb, c->planCnt, c->planChunkL, blockStart, pairsSorted,
+                                                           c->planSegOrder, c->planWarpBase, c->planList);
+        c->planChunkRow.alloc((size_t)nChunks + 1);
+        k_chunk_rows<<<grid_for(nChunks + 1, 256), 256, 0, s>>>(nChunks, nb, c->nnzb, c->rowptr, c->planChunkRow);
+        c->launches += 2;
+        MFEM_CUDA(cudaStreamSynchronize(s));
+        MFEM_CUDA(cudaGetLastError());
     }
     {   // ---- incidence lists (stable sort keeps (element, local node) order inside a row)
         const int64_t nInc = c->nElems * npe;

@@ -326,6 +326,199 @@ k_bsr_spmv(int64_t nb, const int64_t *__restrict__ rowptr, const int32_t *__rest
 }
 
 // ---------------------------------------------------------------------------
+// K3p  bsr_spmv_pipe: the same warp-per-row SpMV with the COLUMN INDICES software-pipelined one
+// work item (row chunk) ahead.  In k_bsr_spmv an item costs two dependent memory round trips
+// (matrix values + indices, then the gathered x).  Here the indices of item k+1 are fetched
+// together with the values of item k, so the x gather of item k (whose indices arrived with
+// item k-1) is issued in the same batch as its values: ONE round trip per item, twice the bytes
+// in flight per resident warp at the same register budget.  Row extents are prefetched two rows
+// ahead for the same reason.  LPR = 32 only (one block row per warp at a time).
+// ---------------------------------------------------------------------------
+template <int N>
+struct PipeLoader;
+
+template <>
+struct PipeLoader<3> {
+    // values of the current item (predicated by rem) + column indices of the NEXT item (remx)
+    static __device__ __forceinline__ void run(const int32_t *c0, const int32_t *c1, const int32_t *c2,
+                                               const double *p0, const double *p1, const double *p2, int rem, int remx,
+                                               uint64_t pol, int (&col)[3], double (&a)[3][3]) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred q0, q1, q2, n0, n1, n2;\n\t"
+            "setp.gt.s32 q0, %18, 0;\n\t"
+            "setp.gt.s32 q1, %18, %20;\n\t"
+            "setp.gt.s32 q2, %18, %21;\n\t"
+            "setp.gt.s32 n0, %24, 0;\n\t"
+            "setp.gt.s32 n1, %24, %20;\n\t"
+            "setp.gt.s32 n2, %24, %21;\n\t"
+            "mov.b32 %0, 0; mov.b32 %1, 0; mov.b32 %2, 0;\n\t"
+            "mov.f64 %3, 0d0000000000000000; mov.f64 %4, 0d0000000000000000; mov.f64 %5, 0d0000000000000000;\n\t"
+            "mov.f64 %6, 0d0000000000000000; mov.f64 %7, 0d0000000000000000; mov.f64 %8, 0d0000000000000000;\n\t"
+            "mov.f64 %9, 0d0000000000000000; mov.f64 %10, 0d0000000000000000; mov.f64 %11, 0d0000000000000000;\n\t"
+            "@q0 " MFEM_LD_F64 " %3, [%15], %19;\n\t"
+            "@q0 " MFEM_LD_F64 " %4, [%16], %19;\n\t"
+            "@q0 " MFEM_LD_F64 " %5, [%17], %19;\n\t"
+            "@q1 " MFEM_LD_F64 " %6, [%15+%22], %19;\n\t"
+            "@q1 " MFEM_LD_F64 " %7, [%16+%22], %19;\n\t"
+            "@q1 " MFEM_LD_F64 " %8, [%17+%22], %19;\n\t"
+            "@q2 " MFEM_LD_F64 " %9, [%15+%23], %19;\n\t"
+            "@q2 " MFEM_LD_F64 " %10, [%16+%23], %19;\n\t"
+            "@q2 " MFEM_LD_F64 " %11, [%17+%23], %19;\n\t"
+            "@n0 " MFEM_LD_S32 " %0, [%12], %19;\n\t"
+            "@n1 " MFEM_LD_S32 " %1, [%13], %19;\n\t"
+            "@n2 " MFEM_LD_S32 " %2, [%14], %19;\n\t"
+            "}"
+            : "=r"(col[0]), "=r"(col[1]), "=r"(col[2]), "=d"(a[0][0]), "=d"(a[0][1]), "=d"(a[0][2]), "=d"(a[1][0]),
+              "=d"(a[1][1]), "=d"(a[1][2]), "=d"(a[2][0]), "=d"(a[2][1]), "=d"(a[2][2])
+            : "l"(c0), "l"(c1), "l"(c2), "l"(p0), "l"(p1), "l"(p2), "r"(rem), "l"(pol), "n"(32), "n"(64), "n"(256),
+              "n"(512), "r"(remx)
+            : "memory");
+    }
+};
+
+template <>
+struct PipeLoader<2> {
+    static __device__ __forceinline__ void run(const int32_t *c0, const int32_t *c1, const int32_t *c2,
+                                               const double *p0, const double *p1, const double * /*unused*/, int rem,
+                                               int remx, uint64_t pol, int (&col)[3], double (&a)[3][2]) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred q0, q1, q2, n0, n1, n2;\n\t"
+            "setp.gt.s32 q0, %14, 0;\n\t"
+            "setp.gt.s32 q1, %14, %16;\n\t"
+            "setp.gt.s32 q2, %14, %17;\n\t"
+            "setp.gt.s32 n0, %20, 0;\n\t"
+            "setp.gt.s32 n1, %20, %16;\n\t"
+            "setp.gt.s32 n2, %20, %17;\n\t"
+            "mov.b32 %0, 0; mov.b32 %1, 0; mov.b32 %2, 0;\n\t"
+            "mov.f64 %3, 0d0000000000000000; mov.f64 %4, 0d0000000000000000; mov.f64 %5, 0d0000000000000000;\n\t"
+            "mov.f64 %6, 0d0000000000000000; mov.f64 %7, 0d0000000000000000; mov.f64 %8, 0d0000000000000000;\n\t"
+            "@q0 " MFEM_LD_F64 " %3, [%12], %15;\n\t"
+            "@q0 " MFEM_LD_F64 " %4, [%13], %15;\n\t"
+            "@q1 " MFEM_LD_F64 " %5, [%12+%18], %15;\n\t"
+            "@q1 " MFEM_LD_F64 " %6, [%13+%18], %15;\n\t"
+            "@q2 " MFEM_LD_F64 " %7, [%12+%19], %15;\n\t"
+            "@q2 " MFEM_LD_F64 " %8, [%13+%19], %15;\n\t"
+            "@n0 " MFEM_LD_S32 " %0, [%9], %15;\n\t"
+            "@n1 " MFEM_LD_S32 " %1, [%10], %15;\n\t"
+            "@n2 " MFEM_LD_S32 " %2, [%11], %15;\n\t"
+            "}"
+            : "=r"(col[0]), "=r"(col[1]), "=r"(col[2]), "=d"(a[0][0]), "=d"(a[0][1]), "=d"(a[1][0]), "=d"(a[1][1]),
+              "=d"(a[2][0]), "=d"(a[2][1])
+            : "l"(c0), "l"(c1), "l"(c2), "l"(p0), "l"(p1), "r"(rem), "l"(pol), "n"(32), "n"(64), "n"(256), "n"(512),
+              "r"(remx)
+            : "memory");
+    }
+};
+
+template <int N, bool MASKED, bool DOT>
+__global__ void __launch_bounds__(kSpmvThreads, 4)
+k_bsr_spmv_pipe(int64_t nb, const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
+                const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y,
+                const uint8_t *__restrict__ fixedMask, double *partials, unsigned *ticket, double *dotOut,
+                const int *status) {
+    constexpr int NN = N * N;
+    constexpr int LPR = 32, U = 3, CH = U * LPR;
+    static_assert(CH % N == 0, "a chunk must cover whole blocks");
+    __shared__ double sZero;
+    if (status && status[ST_STATE] != 0) return;
+    if (threadIdx.x == 0) sZero = 0.0;
+    __syncthreads();
+    const int sl = threadIdx.x & 31;
+    const int64_t warpGlobal = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t rowStride = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int comp = owner_component<N, LPR>(sl);
+    const uint64_t polStream = l2_policy_evict_first(), polKeep = l2_policy_evict_last();
+    int jj[U], cc[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int f = sl + u * LPR;
+        jj[u] = f / N;
+        cc[u] = f - jj[u] * N;
+    }
+    double dot = 0.0;
+    int64_t row = warpGlobal;
+    // extents of the current row and of the next one
+    int64_t b0c = 0, b0n = 0;
+    int Lc = 0, Ln = 0;
+    if (row < nb) { const int64_t a0 = rowptr[row], a1 = rowptr[row + 1]; b0c = a0; Lc = (int)(a1 - a0) * N; }
+    if (row + rowStride < nb) {
+        const int64_t a0 = rowptr[row + rowStride], a1 = rowptr[row + rowStride + 1];
+        b0n = a0; Ln = (int)(a1 - a0) * N;
+    }
+    // column indices of the first item
+    int colc[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) colc[u] = (u * LPR < Lc - sl) ? colidx[b0c + jj[u]] : 0;
+    int base = 0;
+    double acc[N];
+#pragma unroll
+    for (int r = 0; r < N; ++r) acc[r] = 0.0;
+    while (row < nb) {
+        const bool lastOfRow = base + CH >= Lc;
+        // the item after this one: next chunk of this row, or the first chunk of the next row
+        const int64_t b0x = lastOfRow ? b0n : b0c;
+        const int Lx = lastOfRow ? Ln : Lc;
+        const int basex = lastOfRow ? 0 : base + CH;
+        // leaving the row: fetch the extent of the row after next (consumed one item later)
+        int64_t b0f = 0;
+        int Lf = 0;
+        if (lastOfRow) {
+            const int64_t r2 = row + 2 * rowStride;
+            if (r2 < nb) { const int64_t a0 = rowptr[r2], a1 = rowptr[r2 + 1]; b0f = a0; Lf = (int)(a1 - a0) * N; }
+        }
+        const double *v = vals + b0c * NN + base + sl;
+        const int32_t *cn = colidx + b0x + basex / N;
+        int coln[U];
+        double a[U][N], xv[U];
+        PipeLoader<N>::run(cn + jj[0], cn + jj[1], cn + jj[2], v, v + Lc, v + 2 * Lc, Lc - base - sl, Lx - basex - sl,
+                           polStream, coln, a);
+        gather3(x + (colc[0] * N + cc[0]), x + (colc[1] * N + cc[1]), x + (colc[2] * N + cc[2]), polKeep, xv);
+        // Scheduling fence.  ptxas would otherwise start the FMA chain as soon as the first two loads
+        // are back, in between the remaining loads of the batch, and with in-order issue the warp
+        // then stalls with most of its loads not yet sent.  Memory instructions do not cross a warp
+        // barrier, arithmetic does -- so the FMAs are made to depend on a (zero-valued) shared-memory
+        // load placed after the barrier.
+        __syncwarp();
+        const double z = *reinterpret_cast<volatile double *>(&sZero);
+#pragma unroll
+        for (int u = 0; u < U; ++u) xv[u] += z;
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int r = 0; r < N; ++r) acc[r] = fma(a[u][r], xv[u], acc[r]);
+#pragma unroll
+        for (int u = 0; u < U; ++u) colc[u] = coln[u];
+        if (lastOfRow) {
+            const double out0 = fold_reduce<N, LPR>(acc, sl);
+            if (comp >= 0) {
+                double out = out0;
+                if (MASKED && fixedMask[row * N + comp]) out = 0.0;
+                y[row * N + comp] = out;
+                if (DOT) dot += out * x[row * N + comp];
+            }
+#pragma unroll
+            for (int r = 0; r < N; ++r) acc[r] = 0.0;
+            row += rowStride;
+            b0c = b0n; Lc = Ln;
+            b0n = b0f; Ln = Lf;
+            base = 0;
+        } else {
+            base += CH;
+        }
+    }
+    if (DOT) {
+        double v1[1] = {dot};
+        block_reduce_store<1>(v1, partials);
+        if (last_block(ticket)) {
+            const double s = final_sum(partials, gridDim.x);
+            if (threadIdx.x == 0) dotOut[0] = s;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // K3b  bsr_spmv_tma: the same SpMV with the matrix stream decoupled from the compute warps.
 // One persistent CTA per SM.  A producer warp walks the CTA's tiles (a tile = the consecutive
 // block rows whose first block falls into a window of kTmaWindow blocks) and moves each tile's
@@ -830,8 +1023,23 @@ static void launch_spmv_l(mfem_b200_ctx *c, const double *x, double *y, bool mas
     c->launches++;
 }
 
+template <int N>
+static void launch_spmv_pipe(mfem_b200_ctx *c, const double *x, double *y, bool masked, bool dot) {
+    PcgWork &w = c->work;
+    if (masked && dot)
+        k_bsr_spmv_pipe<N, true, true><<<spmv_grid(c, 32, k_bsr_spmv_pipe<N, true, true>), kSpmvThreads, 0, c->stream>>>(
+            c->nDofs, c->rowptr, c->colidx, c->vals, x, y, c->fixedMask, w.partials, w.ticket, w.scal.p + S_PAP, w.status);
+    else if (masked)
+        k_bsr_spmv_pipe<N, true, false><<<spmv_grid(c, 32, k_bsr_spmv_pipe<N, true, false>), kSpmvThreads, 0, c->stream>>>(
+            c->nDofs, c->rowptr, c->colidx, c->vals, x, y, c->fixedMask, nullptr, nullptr, nullptr, nullptr);
+    else
+        k_bsr_spmv_pipe<N, false, false><<<spmv_grid(c, 32, k_bsr_spmv_pipe<N, false, false>), kSpmvThreads, 0, c->stream>>>(
+            c->nDofs, c->rowptr, c->colidx, c->vals, x, y, nullptr, nullptr, nullptr, nullptr, nullptr);
+    c->launches++;
+}
+
 static bool spmv_use_tma(mfem_b200_ctx *c) {
-    if (c->opt_spmv_kernel == 1) return false;
+    if (c->opt_spmv_kernel == 1 || c->opt_spmv_kernel == 3) return false;
     const bool fits = c->maxRowLen <= kTmaMaxRow && c->tileRow.n > 1;
     if (c->opt_spmv_kernel == 2) {
         MFEM_REQUIRE(fits, MFEM_B200_ERR_INVALID, "spmv_kernel=2 (TMA ring) needs block rows of at most 128 blocks");
@@ -865,6 +1073,10 @@ static void launch_spmv_tma(mfem_b200_ctx *c, const double *x, double *y, bool m
 template <int N>
 static void launch_spmv(mfem_b200_ctx *c, const double *x, double *y, bool masked, bool dot) {
     if (spmv_use_tma(c)) { launch_spmv_tma<N>(c, x, y, masked, dot); return; }
+    // index-pipelined kernel (option 3): one block row per warp, i.e. the 32-lane configuration.  Not the
+    // default: measured equal on cfg3 (1.33 vs 1.32 ms) and slower on cfg5 (6.75 vs 6.33 ms) -- the direct
+    // kernel is not bound by the per-row round trips.
+    if (spmv_lanes(c) == 32 && c->opt_spmv_kernel == 3) { launch_spmv_pipe<N>(c, x, y, masked, dot); return; }
     switch (spmv_lanes(c)) {
         case 8: launch_spmv_l<N, 8>(c, x, y, masked, dot); break;
         case 16: launch_spmv_l<N, 16>(c, x, y, masked, dot); break;

@@ -40,7 +40,7 @@ def _handle(mfem, mesh, D, **opt):
 @pytest.mark.parametrize("N,deg,sizes", CASES)
 @pytest.mark.parametrize("mat", ["iso", "ortho", "perelem"])
 @pytest.mark.parametrize("reorder", [0, 1])
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 2])
 def test_assembled_matrix_matches_oracle(mfem, N, deg, sizes, mat, reorder, mode):
     mesh = grid_mesh(N, deg, sizes)
     D = _material(N, mat, mesh.num_elements)
@@ -71,9 +71,10 @@ def test_assembly_is_bit_reproducible(mfem, N, deg, sizes):
 
 
 @pytest.mark.parametrize("N,deg,sizes", CASES + [(3, 2, (9, 4, 3))])
-@pytest.mark.parametrize("lanes,kernel", [(0, 1), (8, 1), (16, 1), (32, 1), (0, 2)])
+@pytest.mark.parametrize("lanes,kernel", [(0, 0), (0, 1), (8, 1), (16, 1), (32, 1), (0, 2), (32, 3)])
 def test_spmv_and_apply_K(mfem, N, deg, sizes, lanes, kernel):
-    """kernel 1 = direct-load SpMV (8/16/32 lanes per row), kernel 2 = TMA-ring SpMV."""
+    """kernel 0 = auto, 1 = direct-load SpMV (8/16/32 lanes per row), 2 = TMA-ring SpMV,
+    3 = index-pipelined SpMV (32 lanes)."""
     mesh = grid_mesh(N, deg, sizes)
     D = _material(N, "ortho")
     rng = np.random.default_rng(5)
@@ -134,11 +135,11 @@ def test_loads_and_strain_stress(mfem, N, deg, sizes, mat):
 
 
 @pytest.mark.parametrize("N,deg,sizes", [(2, 1, (20, 4)), (2, 2, (10, 2)), (3, 1, (10, 2, 2)), (3, 2, (10, 2, 2))])
-@pytest.mark.parametrize("reorder,kernel", [(0, 1), (1, 1), (1, 2)])
+@pytest.mark.parametrize("reorder,kernel", [(0, 1), (1, 1), (1, 2), (1, 3), (1, 0)])
 def test_cantilever_displacements_match_direct_solve(mfem, N, deg, sizes, reorder, kernel):
     sim, fixed, vals, f = cantilever_problem(N, deg, sizes)
     u_ref = sim.solve(f)
-    with _handle(mfem, sim.mesh, sim.D, reorder=reorder, spmv_kernel=kernel) as h:
+    with _handle(mfem, sim.mesh, sim.D, reorder=reorder, spmv_kernel=kernel, spmv_lanes=32 if kernel == 3 else 0) as h:
         h.assemble()
         h.fix_variables(fixed, vals)
         u, info = h.solve(f, rtol=1e-12, return_info=True)
