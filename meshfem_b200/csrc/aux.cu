@@ -186,6 +186,9 @@ void const_strain_load(mfem_b200_ctx *c, const double *epsFlatHost, double *f_ex
     else LAUNCH(2, 2);
 #undef LAUNCH
     c->launches++;
+    // element-partitioned run: every rank integrated its own elements only, the shared DoFs hold
+    // partial sums -> one interface sum-exchange makes the load consistent on all sharers
+    if (c->nRanks > 1) halo_exchange_add(c, f_int, c->N);
     permute_to_external(c, f_int, f_ext_dev);
     MFEM_CUDA(cudaGetLastError());
 }

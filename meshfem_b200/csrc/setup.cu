@@ -186,7 +186,10 @@ __global__ void k_tile_rows(int64_t nTiles, int64_t nb, int window, const int64_
 }
 __global__ void k_max_row_len(int64_t nb, const int64_t *rowptr, unsigned long long *out) {
     const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (r < nb) atomicMax(out, (unsigned long long)(rowptr[r + 1] - rowptr[r]));
+    unsigned long long len = r < nb ? (unsigned long long)(rowptr[r + 1] - rowptr[r]) : 0ULL;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, len);      // one atomic per warp instead of per row
 }
 
 // ---- block-owner assembly plan (assemble.cu k_assemble_blocks) -----------------------------

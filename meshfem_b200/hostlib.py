@@ -41,11 +41,14 @@ def load_library():
         lib.mfemhost_material.argtypes = [c_int, c_char_p, POINTER(c_double), ctypes.c_char_p, c_int]
         lib.mfemhost_eval_expr.argtypes = [c_char_p, c_double, c_double, c_double, POINTER(c_double)]
         lib.mfemhost_save_mesh.argtypes = [c_void_p, c_char_p]
+        lib.mfemhost_msh_field.argtypes = [c_int, c_char_p, c_char_p, c_int, c_int, POINTER(c_double), c_int64,
+                                           POINTER(c_int64), POINTER(c_int)]
+        lib.mfemhost_tensor_analysis.argtypes = [c_int, POINTER(c_double)] + [POINTER(c_double)] * 5
         lib.mfemhost_partition.argtypes = [c_int, c_int64, POINTER(c_double), c_int64, c_int, POINTER(c_int32), c_int, c_int,
-                                           POINTER(c_int64)]
+                                           POINTER(c_int64), c_int64, POINTER(c_int64)]
         lib.mfemhost_partition_copy.argtypes = [POINTER(c_int64), POINTER(c_int64), POINTER(c_int32),
                                                 ctypes.POINTER(ctypes.c_uint8), POINTER(c_int32), POINTER(c_int64),
-                                                POINTER(c_int32)]
+                                                POINTER(c_int32), POINTER(c_int64), POINTER(c_int64)]
         _lib = lib
     return _lib
 
@@ -128,6 +131,37 @@ def material_tensor(dim, json_text):
     return D, buf.value.decode()
 
 
+def msh_field(dim, path, name, kind="scalar", domain="any"):
+    """MSHFieldParser<dim>(path).{scalar,vector,symmetricMatrix}Field(name, domain) -> (values, actual domain)."""
+    lib = load_library()
+    k = {"scalar": 0, "vector": 1, "matrix": 2}[kind]
+    d = {"element": 0, "node": 1, "any": 2}[domain]
+    n, got = c_int64(), c_int()
+    if lib.mfemhost_msh_field(dim, path.encode(), name.encode(), k, d, None, 0, ctypes.byref(n), ctypes.byref(got)) != 0:
+        raise _err(lib)
+    width = {0: 1, 1: dim, 2: dim * (dim + 1) // 2}[k]
+    out = np.zeros((n.value, width))
+    if lib.mfemhost_msh_field(dim, path.encode(), name.encode(), k, d, out.ctypes.data_as(POINTER(c_double)), out.size,
+                              ctypes.byref(n), ctypes.byref(got)) != 0:
+        raise _err(lib)
+    return (out[:, 0] if k == 0 else out), ("element" if got.value == 0 else "node")
+
+
+def tensor_analysis(D):
+    """Eigenstrains, compliance, orthotropic parameters and anisotropy of a flattened elasticity tensor
+    (ElasticityTensor::computeEigenstrains / inverse / getOrthotropic* / anisotropy)."""
+    lib = load_library()
+    D = np.ascontiguousarray(D, dtype=np.float64)
+    F = D.shape[0]
+    dim = 3 if F == 6 else 2
+    lam, strains, S = np.zeros(F), np.zeros((F, F)), np.zeros((F, F))
+    ortho, aniso = np.zeros(9 if dim == 3 else 4), c_double()
+    dp = lambda a: a.ctypes.data_as(POINTER(c_double))
+    if lib.mfemhost_tensor_analysis(dim, dp(D), dp(lam), dp(strains), dp(S), dp(ortho), ctypes.byref(aniso)) != 0:
+        raise _err(lib)
+    return SimpleNamespace(lambdas=lam, strains=strains, compliance=S, orthotropic=ortho, anisotropy=aniso.value)
+
+
 def eval_expression(expr, x=0.0, y=0.0, z=0.0):
     lib = load_library()
     out = c_double()
@@ -168,29 +202,38 @@ def from_arrays(dim, V, E) -> RawMesh:
     return RawMesh(p, dim)
 
 
-def partition(m, n_parts, rank):
+def partition(m, n_parts, rank, dof_for_node=None):
     """Slab element partition of FEMMesh data `m` (from RawMesh.femmesh): this rank's local sub-mesh
     and interface description (include/MeshFEM/Partition.hh).  Returns a SimpleNamespace with
-    elems, nodes (global ids), elem_nodes (local ids), local node coordinates, owned mask,
-    neighbor_ranks and shared[q] = local node ids shared with rank q (ascending global id)."""
+    elems, nodes_global, elem_nodes (local node ids), local node coordinates, and -- in terms of
+    DoFs, which are the nodes unless `dof_for_node` (periodic identification) is given --
+    dofs_global, dof_for_node (local, or None), owned mask, neighbor_ranks and shared[q] = local DoF
+    ids shared with rank q (ascending global id)."""
     lib = load_library()
     nodes = np.ascontiguousarray(m.nodes, dtype=np.float64)
     en = np.ascontiguousarray(m.elem_nodes, dtype=np.int32)
-    sz = (c_int64 * 5)()
+    sz = (c_int64 * 6)()
+    dfn = None if dof_for_node is None else np.ascontiguousarray(dof_for_node, dtype=np.int64)
+    n_dofs = 0 if dfn is None else int(dfn.max()) + 1
     if lib.mfemhost_partition(m.N, nodes.shape[0], nodes.ctypes.data_as(POINTER(c_double)), en.shape[0], en.shape[1],
-                              en.ctypes.data_as(POINTER(c_int32)), n_parts, rank, sz) != 0:
+                              en.ctypes.data_as(POINTER(c_int32)), n_parts, rank,
+                              None if dfn is None else dfn.ctypes.data_as(POINTER(c_int64)), n_dofs, sz) != 0:
         raise _err(lib)
-    ne, nn, nnb, nsh, nowned = (int(x) for x in sz)
+    ne, nn, nnb, nsh, nowned, nd = (int(x) for x in sz)
     p = SimpleNamespace(N=m.N, deg=m.deg, rank=rank, n_parts=n_parts, num_owned=nowned)
     p.elems = np.zeros(ne, dtype=np.int64); p.nodes_global = np.zeros(nn, dtype=np.int64)
-    p.elem_nodes = np.zeros((ne, en.shape[1]), dtype=np.int32); p.owned = np.zeros(nn, dtype=np.uint8)
+    p.elem_nodes = np.zeros((ne, en.shape[1]), dtype=np.int32); p.owned = np.zeros(nd, dtype=np.uint8)
     p.neighbor_ranks = np.zeros(nnb, dtype=np.int32); p.neighbor_offsets = np.zeros(nnb + 1, dtype=np.int64)
     p.shared_local = np.zeros(nsh, dtype=np.int32)
+    p.dofs_global = np.zeros(nd, dtype=np.int64)
+    p.dof_for_node = None if dfn is None else np.zeros(nn, dtype=np.int64)
     ip, lp = POINTER(c_int32), POINTER(c_int64)
     lib.mfemhost_partition_copy(p.elems.ctypes.data_as(lp), p.nodes_global.ctypes.data_as(lp), p.elem_nodes.ctypes.data_as(ip),
                                 p.owned.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), p.neighbor_ranks.ctypes.data_as(ip),
-                                p.neighbor_offsets.ctypes.data_as(lp), p.shared_local.ctypes.data_as(ip))
+                                p.neighbor_offsets.ctypes.data_as(lp), p.shared_local.ctypes.data_as(ip),
+                                p.dofs_global.ctypes.data_as(lp),
+                                None if dfn is None else p.dof_for_node.ctypes.data_as(lp))
     p.nodes = nodes[p.nodes_global]
-    p.num_nodes, p.num_elements = nn, ne
+    p.num_nodes, p.num_elements, p.num_dofs = nn, ne, nd
     p.shared = {int(q): p.shared_local[p.neighbor_offsets[i]:p.neighbor_offsets[i + 1]] for i, q in enumerate(p.neighbor_ranks)}
     return p

@@ -3,6 +3,7 @@
 // input generators / host logic, not part of the GPU ABI (include/mfem_b200.h).
 #include <MeshFEM/FEMMesh.hh>
 #include <MeshFEM/LinearElasticity.hh>
+#include <MeshFEM/MSHFieldParser.hh>
 #include <MeshFEM/Materials.hh>
 #include <MeshFEM/Partition.hh>
 #include <MeshFEM/MeshIO.hh>
@@ -232,6 +233,51 @@ int mfemhost_eval_expr(const char *expr, double x, double y, double z, double *o
     } catch (const std::exception &e) { g_err = e.what(); return -1; }
 }
 
+// MSHFieldParser: number of entries of the named field (kind 0 scalar, 1 vector, 2 symmetric matrix;
+// domain 0 per-element, 1 per-node, 2 any) and, when `out` is non-null, its values (flattened).
+int mfemhost_msh_field(int dim, const char *path, const char *name, int kind, int domain, double *out, int64_t cap,
+                       int64_t *nEntries, int *actualDomain) {
+    try {
+        const DomainType want = domain == 0 ? DomainType::PER_ELEMENT : (domain == 1 ? DomainType::PER_NODE : DomainType::ANY);
+        DomainType got = want;
+        auto run = [&](auto &parser) {
+            const std::vector<Real> *data = nullptr;
+            size_t n = 0;
+            if (kind == 0) { const auto &f = parser.scalarField(name, want, got); data = &f.data(); n = f.domainSize(); }
+            else if (kind == 1) { const auto &f = parser.vectorField(name, want, got); data = &f.data(); n = f.domainSize(); }
+            else { const auto &f = parser.symmetricMatrixField(name, want); data = &f.data(); n = f.domainSize(); }
+            *nEntries = (int64_t)n;
+            if (out) {
+                if ((int64_t)data->size() > cap) throw std::runtime_error("output buffer too small");
+                std::memcpy(out, data->data(), data->size() * sizeof(Real));
+            }
+        };
+        if (dim == 3) { MSHFieldParser<3> p(path); run(p); } else { MSHFieldParser<2> p(path); run(p); }
+        if (actualDomain) *actualDomain = got == DomainType::PER_ELEMENT ? 0 : 1;
+        return 0;
+    } catch (const std::exception &e) { g_err = e.what(); return -1; }
+}
+
+// ElasticityTensor analysis used by PeriodicHomogenization_cli: eigenstrains (ascending eigenvalues,
+// strains[k][component]), compliance D(inverse()), orthotropic parameters, anisotropy.
+int mfemhost_tensor_analysis(int dim, const double *Dflat, double *lambdas, double *strains, double *compliance,
+                             double *ortho, double *anisotropy) {
+    try {
+        auto run = [&](auto E) {
+            constexpr size_t F = decltype(E)::F;
+            E.setFlat(Dflat);
+            const auto eig = E.computeEigenstrains();
+            for (size_t k = 0; k < F; ++k) { lambdas[k] = eig.lambdas[k]; for (size_t i = 0; i < F; ++i) strains[k * F + i] = eig.strains[k][i]; }
+            E.inverse().getFlat(compliance);
+            *anisotropy = E.anisotropy();
+            if (decltype(E)::Dim == 3) E.getOrthotropic3D(ortho[0], ortho[1], ortho[2], ortho[3], ortho[4], ortho[5], ortho[6], ortho[7], ortho[8]);
+            else E.getOrthotropic2D(ortho[0], ortho[1], ortho[2], ortho[3]);
+        };
+        if (dim == 3) run(ElasticityTensor<Real, 3>()); else run(ElasticityTensor<Real, 2>());
+        return 0;
+    } catch (const std::exception &e) { g_err = e.what(); return -1; }
+}
+
 int mfemhost_save_mesh(void *m, const char *path) {
     auto *hm = static_cast<HostMesh *>(m);
     try { MeshIO::save(path, hm->vertices, hm->elements); return 0; }
@@ -245,22 +291,24 @@ namespace { thread_local Partition::LocalPart g_part; }
 extern "C" {
 // sizes5: [nLocalElems, nLocalNodes, nNeighbors, nSharedTotal, nOwned]
 int mfemhost_partition(int dim, int64_t nNodes, const double *nodes, int64_t nElems, int npe, const int32_t *elemNodes,
-                       int nParts, int rank, int64_t *sizes5) {
+                       int nParts, int rank, const int64_t *dofForNode, int64_t nDofs, int64_t *sizes6) {
     try {
         auto part = Partition::slabPartition(dim, nNodes, nodes, nElems, npe, elemNodes, nParts);
-        g_part = Partition::extractPart(rank, nParts, nNodes, nElems, npe, elemNodes, part);
-        sizes5[0] = (int64_t)g_part.elems.size(); sizes5[1] = (int64_t)g_part.nodes.size();
-        sizes5[2] = (int64_t)g_part.neighborRanks.size(); sizes5[3] = (int64_t)g_part.sharedLocal.size();
+        g_part = Partition::extractPart(rank, nParts, nNodes, nElems, npe, elemNodes, part, dofForNode, nDofs);
+        sizes6[0] = (int64_t)g_part.elems.size(); sizes6[1] = (int64_t)g_part.nodes.size();
+        sizes6[2] = (int64_t)g_part.neighborRanks.size(); sizes6[3] = (int64_t)g_part.sharedLocal.size();
         int64_t owned = 0; for (auto o : g_part.owned) owned += o;
-        sizes5[4] = owned;
+        sizes6[4] = owned;
+        sizes6[5] = (int64_t)g_part.dofs.size();
         return 0;
     } catch (const std::exception &e) { g_err = e.what(); return -1; }
 }
 int mfemhost_partition_copy(int64_t *elems, int64_t *nodes, int32_t *elemNodesLocal, uint8_t *owned, int32_t *neighborRanks,
-                            int64_t *neighborOffsets, int32_t *sharedLocal) {
+                            int64_t *neighborOffsets, int32_t *sharedLocal, int64_t *dofs, int64_t *dofForNodeLocal) {
     auto cp = [](auto &v, auto *dst) { if (dst && !v.empty()) std::memcpy(dst, v.data(), v.size() * sizeof(v[0])); };
     cp(g_part.elems, elems); cp(g_part.nodes, nodes); cp(g_part.elemNodes, elemNodesLocal); cp(g_part.owned, owned);
     cp(g_part.neighborRanks, neighborRanks); cp(g_part.neighborOffsets, neighborOffsets); cp(g_part.sharedLocal, sharedLocal);
+    cp(g_part.dofs, dofs); cp(g_part.dofForNode, dofForNodeLocal);
     return 0;
 }
 }  // extern "C"

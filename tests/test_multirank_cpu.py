@@ -39,6 +39,33 @@ def test_partition_invariants(lib_built, nparts):
                 assert not p.owned[idx].any()
 
 
+@pytest.mark.parametrize("nparts", [2, 3, 4])
+@pytest.mark.parametrize("deg", [1, 2])
+def test_periodic_partition_works_on_dofs(lib_built, nparts, deg):
+    """Periodic cell: identified nodes are one DoF BEFORE partitioning -- the x-slab wrap
+    makes the first and the last rank neighbours and cell edges/corners are shared by several ranks."""
+    from meshfem_b200 import hostlib
+    raw = hostlib.grid([4, 4, 4], (0, 0, 0), (1, 1, 1))
+    info = raw.apply_bc(deg, "", periodic=True)
+    m, dfn, nd = info["mesh"], info["dof_for_node"], info["num_dofs"]
+    assert nd < m.num_nodes
+    parts = [hostlib.partition(m, nparts, r, dof_for_node=dfn) for r in range(nparts)]
+    owned_ids = np.concatenate([p.dofs_global[p.owned.astype(bool)] for p in parts])
+    assert np.array_equal(np.sort(owned_ids), np.arange(nd))                 # every DoF owned exactly once
+    assert np.array_equal(np.sort(np.concatenate([p.elems for p in parts])), np.arange(m.num_elements))
+    for r, p in enumerate(parts):
+        assert p.num_dofs == p.dofs_global.size and np.all(np.diff(p.dofs_global) > 0)
+        assert np.array_equal(p.dofs_global[p.dof_for_node], dfn[p.nodes_global])   # local map == global map
+        assert np.array_equal(p.nodes_global[p.elem_nodes], m.elem_nodes[p.elems])
+        for q, idx in p.shared.items():
+            other = parts[q]
+            assert np.array_equal(p.dofs_global[idx], other.dofs_global[other.shared[r]])
+            if q < r:
+                assert not p.owned[idx].any()
+    if nparts > 2:     # the wrap: rank 0 and the last rank share the identified x-faces
+        assert (nparts - 1) in parts[0].shared and 0 in parts[-1].shared
+
+
 @pytest.mark.parametrize("world", [2, 3])
 def test_distributed_pcg_gloo(lib_built, world):
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1")

@@ -15,43 +15,13 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 
 
-def broadcast_bytes(dist, payload: bytes | None, n: int, device=None) -> bytes:
-    import torch
-    t = torch.zeros(n, dtype=torch.uint8, device=device)
-    if dist.get_rank() == 0:
-        t.copy_(torch.frombuffer(bytearray(payload), dtype=torch.uint8))
-    dist.broadcast(t, src=0)
-    return bytes(t.cpu().numpy().tobytes())
-
-
-def local_problem(m, fixed, vals, f, world, rank):
-    """Slice the global problem (FEMMesh data m, fixed vars/values, consistent load f) for `rank`."""
-    from meshfem_b200 import hostlib
-    p = hostlib.partition(m, world, rank)
-    N = m.N
-    glob2loc = -np.ones(m.num_nodes, dtype=np.int64)
-    glob2loc[p.nodes_global] = np.arange(p.num_nodes)
-    fnode, fcomp = fixed // N, fixed % N
-    loc = glob2loc[fnode]
-    keep = loc >= 0
-    lfixed = (N * loc[keep] + fcomp[keep]).astype(np.int64)
-    lvals = np.asarray(vals)[keep]
-    lf = np.ascontiguousarray(f[p.nodes_global])
-    return p, lfixed, lvals, lf
+from meshfem_b200.distributed import broadcast_bytes, local_problem  # noqa: E402,F401
+from meshfem_b200 import distributed as _dist_mod  # noqa: E402
 
 
 def make_handle(mfem, dist, world, rank, local_rank, p, D, **options):
-    """Handle with communicator, local mesh, interface and material."""
-    import torch
-    uid = mfem.Handle.comm_unique_id() if rank == 0 else None
-    dev = torch.device("cuda", local_rank) if dist.get_backend() == "nccl" else None
-    uid = broadcast_bytes(dist, uid, 128, dev)
-    h = mfem.Handle(local_rank, **options)
-    h.comm_init(world, rank, uid)
-    h.set_mesh(p.N, p.deg, p.nodes, p.elem_nodes)
-    h.set_interface(p.neighbor_ranks, p.neighbor_offsets, p.shared_local, p.owned)
-    h.set_material(D)
-    return h
+    """Handle with communicator, local mesh, interface and material (meshfem_b200.distributed)."""
+    return _dist_mod.make_handle(dist, world, rank, local_rank, p, D, **options)
 
 
 def max_over_ranks(dist, value, device):
