@@ -35,7 +35,7 @@ import numpy as np  # noqa: E402
 METRIC = "assembly+solve throughput (elements/s), quadratic-tet elasticity cantilever"
 UNIT = "elements/s"
 RTOL = 1e-8
-CPU_SAMPLE_GRID = (40, 8, 8)
+CPU_SAMPLE_GRID = (60, 12, 12)     # 207,360 quadratic tets: ~10-25 s of CPU work per sample
 
 
 def parse_config(s):
