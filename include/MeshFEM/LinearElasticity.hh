@@ -124,6 +124,18 @@ public:
         return dofToNodeField(x);
     }
     VField solve() const { return solve(neumannLoad()); }
+    // all right-hand sides against one assembled system (batched on the device when there are flatLen(N))
+    std::vector<VField> solve(const std::vector<VField> &fs) const {
+        if (!m_system.isSet()) m_buildConstrainedSystem();
+        BENCHMARK_START_TIMER_SECTION("Elasticity Solve");
+        std::vector<std::vector<Real>> rhs, xs;
+        for (const auto &f : fs) rhs.push_back(f.data());
+        m_system.solveMultiple(rhs, xs);
+        BENCHMARK_STOP_TIMER_SECTION("Elasticity Solve");
+        std::vector<VField> result;
+        for (const auto &x : xs) result.push_back(dofToNodeField(x));
+        return result;
+    }
     void setSolverTolerance(double rtol, int maxIters = 200000) { m_system.setTolerance(rtol, maxIters); }
     const mfem_b200_solve_info &lastSolveInfo() const { return m_system.lastSolveInfo(); }
 

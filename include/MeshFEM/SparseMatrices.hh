@@ -120,6 +120,29 @@ public:
         m_lastInfo = info;
         BENCHMARK_ADD_DEVICE_SECONDS("PCG (device)", info.seconds);
     }
+    // Several right-hand sides against the same system -- the reference factorises once and back-solves
+    // per right-hand side; here flatLen(N) right-hand sides (the cell problems) run as ONE batched PCG
+    // whose SpMM streams the matrix once for all of them (csrc/solver_multi.inl).
+    template <class _Vec, class _SolnVec>
+    void solveMultiple(const std::vector<_Vec> &fs, std::vector<_SolnVec> &us) {
+        if (!isSet()) throw std::runtime_error("No system to solve");
+        const size_t nrhs = fs.size();
+        std::vector<_Real> f(nrhs * m_numVars), u(nrhs * m_numVars);
+        for (size_t k = 0; k < nrhs; ++k) {
+            if (fs[k].size() != m_numVars) throw std::runtime_error("Bad RHS");
+            std::copy(fs[k].begin(), fs[k].end(), f.begin() + k * m_numVars);
+        }
+        std::vector<mfem_b200_solve_info> info(nrhs);
+        mfemCheck(handle(), mfem_b200_solve(handle(), (int)nrhs, f.data(), u.data(), m_rtol, m_maxIters, info.data()));
+        us.resize(nrhs);
+        double seconds = 0;
+        for (size_t k = 0; k < nrhs; ++k) {
+            us[k].assign(u.begin() + k * m_numVars, u.begin() + (k + 1) * m_numVars);
+            seconds += info[k].seconds;
+        }
+        m_lastInfo = info.back();
+        BENCHMARK_ADD_DEVICE_SECONDS("PCG (device)", seconds);
+    }
     void setTolerance(double rtol, int maxIters) { m_rtol = rtol; m_maxIters = maxIters; }
     const mfem_b200_solve_info &lastSolveInfo() const { return m_lastInfo; }
     void setEconomyMode(bool) {}

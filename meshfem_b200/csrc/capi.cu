@@ -70,6 +70,7 @@ int mfem_b200_destroy(mfem_b200_handle h) {
     if (!h) return MFEM_B200_ERR_INVALID;
     cudaSetDevice(h->device);
     comm_destroy(h);
+    free_work_multi(h);
     if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
     delete h;
     return MFEM_B200_OK;
@@ -90,6 +91,10 @@ int mfem_b200_set_option(mfem_b200_handle h, const char *name, int64_t value) {
     } else if (n == "assembly") {
         MFEM_REQUIRE(value >= 0 && value <= 2, MFEM_B200_ERR_INVALID, "assembly must be 0 (block-owner), 1 (coloured) or 2 (owner-gather)");
         h->opt_assembly = (int)value;
+    } else if (n == "spmm_kernel") {
+        h->opt_spmm_kernel = (int)value;
+    } else if (n == "batch_rhs") {
+        h->opt_batch_rhs = value != 0;
     } else if (n == "graph") {
         h->opt_graph = value != 0;
     } else if (n == "spmv_kernel") {
@@ -276,9 +281,30 @@ int mfem_b200_solve(mfem_b200_handle h, int nrhs, const double *f, double *u, do
     MFEM_REQUIRE(h->valuesValid, MFEM_B200_ERR_INVALID, "No system to solve");
     MFEM_REQUIRE(rtol > 0 && max_iters > 0, MFEM_B200_ERR_INVALID, "solve: bad tolerance / iteration limit");
     const size_t n = (size_t)h->nvar();
-    DevBuf<double> fext(n), fin(n), uin(n), uext(n);
     int firstErr = MFEM_B200_OK;
     std::string firstMsg;
+    if (h->opt_batch_rhs && nrhs == flat_len(h->N)) {
+        // the cell-problem case: all right-hand sides in one batched PCG (one matrix stream for all of them)
+        DevBuf<double> fext(n), fin(n * nrhs), uin(n * nrhs), uext(n);
+        for (int k = 0; k < nrhs; ++k) {
+            MFEM_CUDA(cudaMemcpyAsync(fext, f + (size_t)k * n, n * 8, cudaMemcpyHostToDevice, h->stream));
+            permute_to_internal(h, fext, fin.p + (size_t)k * n);
+        }
+        try {
+            pcg_solve_multi(h, nrhs, fin, uin, rtol, max_iters, info);
+        } catch (const CudaError &e) {
+            if (e.status != MFEM_B200_ERR_NO_CONVERGE) throw;
+            firstErr = e.status; firstMsg = e.what();
+        }
+        for (int k = 0; k < nrhs; ++k) {
+            permute_to_external(h, uin.p + (size_t)k * n, uext);
+            MFEM_CUDA(cudaMemcpyAsync(u + (size_t)k * n, uext, n * 8, cudaMemcpyDeviceToHost, h->stream));
+        }
+        MFEM_CUDA(cudaStreamSynchronize(h->stream));
+        if (firstErr != MFEM_B200_OK) throw CudaError(firstErr, firstMsg);
+        return MFEM_B200_OK;
+    }
+    DevBuf<double> fext(n), fin(n), uin(n), uext(n);
     for (int k = 0; k < nrhs; ++k) {
         MFEM_CUDA(cudaMemcpyAsync(fext, f + (size_t)k * n, n * 8, cudaMemcpyHostToDevice, h->stream));
         permute_to_internal(h, fext, fin);

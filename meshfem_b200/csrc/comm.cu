@@ -11,6 +11,8 @@
 
 #include <cstring>
 
+#include <algorithm>
+
 #include "core.cuh"
 
 namespace mfem {
@@ -156,7 +158,7 @@ int mfem_b200_set_interface(mfem_b200_handle h, int n_neighbors, const int32_t *
         delete h->halo;
         h->halo = new Halo();
         Halo &H = *h->halo;
-        H.maxWidth = h->N * h->N;
+        H.maxWidth = h->N * std::max(h->N, flat_len(h->N));    // diagonal blocks (N*N) or a batch of flatLen(N) vectors
         H.ranks.assign(neighbor_ranks, neighbor_ranks + n_neighbors);
         H.offsets.assign(1, 0);
         if (n_neighbors) H.offsets.assign(neighbor_offsets, neighbor_offsets + n_neighbors + 1);

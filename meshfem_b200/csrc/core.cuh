@@ -76,6 +76,7 @@ struct PcgWork {
 };
 
 struct Halo;   // multi-GPU interface exchange (comm.cu)
+struct PcgWorkMulti;   // workspace of the batched (multi right-hand-side) PCG (solver_multi.inl)
 
 }  // namespace mfem
 
@@ -89,6 +90,8 @@ struct mfem_b200_ctx {
     int opt_assembly = 0;
     int opt_graph = 1;
     int opt_spmv_kernel = 0;               // 0 auto, 1 direct-load kernel, 2 TMA-ring kernel
+    int opt_spmm_kernel = 0;               // batched PCG: 0/1 full-warp SpMM, 2 half-warp split SpMM (even batch sizes)
+    int opt_batch_rhs = 1;                 // solve flatLen(N) right-hand sides as one batched PCG (SpMM)
     int opt_spmv_lanes = 0;                // lanes per block row in the SpMV (0 = choose from the mean row length)
 
     // mesh
@@ -151,6 +154,7 @@ struct mfem_b200_ctx {
 
     mfem::PcgWork work;
     bool workValid = false;
+    mfem::PcgWorkMulti *workMulti = nullptr;
 
     // multi-GPU
     int nRanks = 1, rank = 0;
@@ -220,6 +224,9 @@ void build_preconditioner(mfem_b200_ctx *c);
 void pcg_solve(mfem_b200_ctx *c, const double *f_ext_dev, double *u_ext_dev, double rtol, int maxIters,
                mfem_b200_solve_info *info);
 void ensure_work(mfem_b200_ctx *c);
+bool pcg_solve_multi(mfem_b200_ctx *c, int nrhs, const double *f_int, double *u_int, double rtol, int maxIters,
+                     mfem_b200_solve_info *info);
+void free_work_multi(mfem_b200_ctx *c);
 double time_spmv(mfem_b200_ctx *c, int iters);
 // comm.cu
 void halo_exchange_add(mfem_b200_ctx *c, double *vec_int, int width);   // no-op on one rank

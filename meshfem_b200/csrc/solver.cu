@@ -1250,6 +1250,8 @@ void pcg_solve(mfem_b200_ctx *c, const double *f_int, double *u_int, double rtol
     else pcg_impl<2>(c, f_int, u_int, rtol, maxIters, info);
 }
 
+#include "solver_multi.inl"
+
 double time_spmv(mfem_b200_ctx *c, int iters) {
     MFEM_REQUIRE(c->valuesValid, MFEM_B200_ERR_INVALID, "time_spmv: matrix not assembled");
     ensure_work(c);

@@ -96,12 +96,14 @@ def homogenize(raw_mesh, deg, D, dist=None, local_rank=0, rtol=1e-10, max_iters=
         h.assemble()
         h.fix_variables(lfixed, lvals)
         w_nodes, strains = [], []
+        loads = []
         for i in range(F):
             eps = np.zeros(F); eps[i] = -(1.0 if i < N else 0.5)          # -SMatrix::CanonicalBasis(i)
-            rhs = h.const_strain_load(eps)                                  # consistent on shared DoFs
-            u, inf = h.solve(rhs, rtol=rtol, max_iters=max_iters, return_info=True)
-            stats.append(inf[0])
-            w = u.reshape(-1, N)[node_dof]                                  # dofToNodeField
+            loads.append(h.const_strain_load(eps))                          # consistent on shared DoFs
+        # flatLen(N) right-hand sides in one call: the library runs them as one batched PCG (SpMM)
+        U, stats = h.solve(np.stack(loads), rtol=rtol, max_iters=max_iters, return_info=True)
+        for i in range(F):
+            w = U[i].reshape(-1, N)[node_dof]                               # dofToNodeField
             w_nodes.append(w)
             strains.append(h.avg_strain_stress(w)[0])
         Eh = _volume_form(N, D, h.volumes(), strains, cell_volume)

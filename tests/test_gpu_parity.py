@@ -148,6 +148,40 @@ def test_cantilever_displacements_match_direct_solve(mfem, N, deg, sizes, reorde
     assert err < 1e-8, f"rel L2 {err}, iterations {info[0]['iterations']}"
 
 
+@pytest.mark.parametrize("N,deg,sizes", [(3, 2, (6, 2, 2)), (3, 1, (8, 3, 2)), (2, 2, (8, 3)), (2, 1, (12, 4))])
+def test_batched_pcg_matches_sequential_and_direct(mfem, N, deg, sizes):
+    """flatLen(N) right-hand sides in one call run as ONE batched PCG (SpMM, csrc/solver_multi.inl): every
+    system must reproduce the one-at-a-time solve and the oracle's direct solve, whatever its scale --
+    including a zero load vector and systems that finish at different iterations (frozen while the
+    others continue)."""
+    sim, fixed, vals, f = cantilever_problem(N, deg, sizes)
+    F = orc.flat_len(N)
+    rng = np.random.default_rng(3)
+    vals = 1e-3 * rng.normal(size=vals.shape)
+    rhs = np.stack([f * 1.0] + [rng.normal(size=f.shape) * 10.0 ** (-2 * k) for k in range(1, F)])
+    rhs[F - 1] = 0.0
+    rhs[1, :, :] *= np.linspace(0, 1, f.shape[0])[:, None] ** 8        # smooth, fast-converging load
+    K = sim.stiffness()
+    ref = [orc.solve_fixed(K, r.reshape(-1), fixed, vals).reshape(-1, N) for r in rhs]
+    out = {}
+    for batch, kern in ((1, 0), (1, 2), (0, 0)):           # full-warp SpMM, half-warp split SpMM, one at a time
+        with _handle(mfem, sim.mesh, sim.D, batch_rhs=batch, spmm_kernel=kern) as h:
+            h.assemble()
+            h.fix_variables(fixed, vals)
+            out[batch, kern] = h.solve(rhs, rtol=1e-12, return_info=True)
+    us, iseq = out[0, 0]
+    assert all(i["converged"] for i in iseq)
+    for kern in (0, 2):
+        ub, ib = out[1, kern]
+        assert all(i["converged"] for i in ib)
+        for k in range(F):
+            scale = max(np.linalg.norm(ref[k]), 1e-300)
+            assert np.linalg.norm(ub[k] - ref[k]) / scale < 1e-8, k
+            assert np.linalg.norm(ub[k] - us[k]) / scale < 1e-9, k
+            assert abs(ib[k]["iterations"] - iseq[k]["iterations"]) <= 2, (k, ib[k], iseq[k])
+        assert len({i["iterations"] for i in ib}) > 1      # the systems did finish at different iterations
+
+
 def test_nonzero_dirichlet_values_and_multiple_rhs(mfem):
     """fixVariables with non-zero values moves K_fc u_c to the RHS (SparseMatrices.hh:2457-2470)."""
     sim, fixed, vals, f = cantilever_problem(3, 2, (4, 2, 2), D=orc.material_from_json(3, ORTHO))

@@ -22,6 +22,13 @@ if what == "spmv":
     print("spmv s/launch", h.time_spmv(5))
 elif what == "assemble":
     h.assemble()
+elif what == "solve6":
+    import numpy as np
+    rhs = np.stack([f * (k + 1.0) for k in range(6)])
+    try:
+        h.solve(rhs, rtol=1e-30, max_iters=50)
+    except meshfem_b200.MfemB200Error as e:
+        print("expected:", e)
 elif what == "solve":
     try:
         h.solve(f, rtol=1e-30, max_iters=50)
