@@ -74,6 +74,27 @@ template <typename _Real>
 class SPSDSystem {
 public:
     SPSDSystem() {}
+    // The reference's constructor (SparseMatrices.hh:2325-2348, set(K)): a symmetric positive
+    // (semi-)definite matrix assembled by the caller, upper triangle in triplet form, variables ordered
+    // blockDim*DoF + component.  The triplets are summed and laid out on the device; fixVariables / solve
+    // then work as for a mesh-assembled system.
+    template <class _TMatrix>
+    explicit SPSDSystem(const _TMatrix &K, int blockDim = 3, int device = 0) : m_device(device) { set(K, blockDim); }
+    template <class _TMatrix>
+    void set(const _TMatrix &K, int blockDim = 3) {
+        if (K.m != K.n) throw std::runtime_error("SPSDSystem: K must be square");
+        std::vector<int64_t> I(K.nnz()), J(K.nnz());
+        std::vector<_Real> V(K.nnz());
+        bool upper = true;
+        for (size_t k = 0; k < K.nnz(); ++k) {
+            I[k] = (int64_t)K.nz[k].i; J[k] = (int64_t)K.nz[k].j; V[k] = K.nz[k].v;
+            upper = upper && K.nz[k].i <= K.nz[k].j;
+        }
+        mfemCheck(handle(), mfem_b200_set_matrix_triplets(handle(), blockDim, (int64_t)K.m, (int64_t)K.nnz(), I.data(), J.data(),
+                                                          V.data(), upper ? 1 : 0));
+        m_numVars = K.m;
+        m_isSet = true;
+    }
     SPSDSystem(const SPSDSystem &) = delete;
     SPSDSystem &operator=(const SPSDSystem &) = delete;
     ~SPSDSystem() { if (m_handle) mfem_b200_destroy(m_handle); }

@@ -122,6 +122,16 @@ int mfem_b200_dump_upper_triplets(mfem_b200_handle h, const char *path);
 /* Update node positions (Simulator::updateMeshNodePositions); pattern is kept.         */
 int mfem_b200_set_node_positions(mfem_b200_handle h, const double *nodes);
 
+/* ---- a matrix assembled elsewhere -------------------------------------------------- */
+/* SPSDSystem(K) / setConstrained(K, C = empty) (SparseMatrices.hh:2321-2348) for a symmetric positive
+ * (semi-)definite matrix the caller assembled itself: COO triplets over n_vars scalar variables
+ * ordered block_dim*DoF + component (block_dim in {2,3}); repeated entries are summed
+ * (TripletMatrix::sumRepeated); upper_triangle_only != 0: only i <= j given (the reference's storage),
+ * mirrored here.  Replaces any mesh of the handle; fix_variables / solve / spmv / get_bsr work on it,
+ * mesh-based calls (assemble, apply_K, loads, strains) fail.                            */
+int mfem_b200_set_matrix_triplets(mfem_b200_handle h, int block_dim, int64_t n_vars, int64_t nnz, const int64_t *rows,
+                                  const int64_t *cols, const double *vals, int upper_triangle_only);
+
 /* ---- constraints + solve (SPSDSystem) -------------------------------------------- */
 /* SPSDSystem::fixVariables (SparseMatrices.hh:2389-2500): scalar variable indices
  * dim*DoF+c and the values they are fixed to (values may be NULL = 0).  Cumulative;

@@ -122,8 +122,48 @@ def build_host(force: bool = False) -> str:
     return HOST_LIB
 
 
+PY_DIR = os.path.join(REPO, "python")
+PY_MODULES = (("TENSORS", "tensors"), ("SPARSE_MATRICES", "sparse_matrices"), ("HOMOGENIZATION", "periodic_homogenization"))
+
+
+def build_python(force: bool = False):
+    """pybind11 modules python/{tensors,sparse_matrices,periodic_homogenization} (src/python_bindings/bindings.cc)
+    over the host classes; they link libmfem_b200.so like the CLIs do."""
+    import sysconfig
+    import pybind11
+    os.makedirs(PY_DIR, exist_ok=True)
+    suffix = sysconfig.get_config_var("EXT_SUFFIX")
+    src = os.path.join(REPO, "src", "python_bindings", "bindings.cc")
+    h = hashlib.sha256()
+    h.update(_host_stamp().encode())
+    with open(src, "rb") as fh:
+        h.update(fh.read())
+    stamp = h.hexdigest()
+    stamp_file = os.path.join(PY_DIR, "build.stamp")
+    outs = [os.path.join(PY_DIR, name + suffix) for _, name in PY_MODULES]
+    if not force and all(os.path.exists(o) for o in outs) and os.path.exists(stamp_file):
+        if open(stamp_file).read().strip() == stamp:
+            return outs
+    inc = ["-I" + sysconfig.get_paths()["include"], "-I" + pybind11.get_include(), "-I" + os.path.join(REPO, "include")]
+    procs = []
+    for (define, name), out in zip(PY_MODULES, outs):
+        cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-fvisibility=hidden", "-DBIND_" + define] + inc + \
+              [src, os.path.join(REPO, "src", "host", "MeshIO.cc"), "-L" + LIBDIR, "-lmfem_b200",
+               "-Wl,-rpath,$ORIGIN/../meshfem_b200/lib", "-o", out]
+        procs.append((name, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for name, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            raise RuntimeError(f"pybind11 module {name} failed to build:\n{out}")
+    with open(stamp_file, "w") as f:
+        f.write(stamp)
+    return outs
+
+
 def build_all(force: bool = False, verbose: bool = False):
-    return build(force, verbose), build_host(force)
+    lib, host = build(force, verbose), build_host(force)
+    build_python(force)
+    return lib, host
 
 
 if __name__ == "__main__":

@@ -24,7 +24,7 @@ SYMBOLS = [
     "mfem_b200_set_node_positions", "mfem_b200_fix_variables", "mfem_b200_clear_fixed_variables",
     "mfem_b200_solve", "mfem_b200_apply_K", "mfem_b200_spmv", "mfem_b200_const_strain_load",
     "mfem_b200_avg_strain_stress", "mfem_b200_get_volumes", "mfem_b200_get_timer", "mfem_b200_reset_timers",
-    "mfem_b200_launch_count", "mfem_b200_time_spmv",
+    "mfem_b200_launch_count", "mfem_b200_time_spmv", "mfem_b200_set_matrix_triplets",
 ]
 
 STATUS_NAMES = {
@@ -90,6 +90,7 @@ def load_library():
     lib.mfem_b200_launch_count.argtypes = [c_void_p]
     lib.mfem_b200_launch_count.restype = c_int64
     lib.mfem_b200_time_spmv.argtypes = [c_void_p, c_int, dp]
+    lib.mfem_b200_set_matrix_triplets.argtypes = [c_void_p, c_int, c_int64, c_int64, lp, lp, dp, c_int]
     for name in SYMBOLS:
         fn = getattr(lib, name)
         if fn.restype is c_int and name not in ("mfem_b200_device_count",):
@@ -215,6 +216,24 @@ class Handle:
     # ---- assembly ------------------------------------------------------------
     def assemble(self):
         self._check(self.lib.mfem_b200_assemble(self._h))
+
+    def set_matrix(self, K, block_dim=3, upper_triangle_only=False):
+        """SPSDSystem(K) for a matrix assembled elsewhere: K = scipy sparse matrix (any format; summed COO
+        semantics) or a tuple (n_vars, rows, cols, vals)."""
+        if isinstance(K, tuple):
+            n, rows, cols, vals = K
+        else:
+            coo = K.tocoo()
+            n, rows, cols, vals = coo.shape[0], coo.row, coo.col, coo.data
+        rows = np.ascontiguousarray(rows, dtype=np.int64); cols = np.ascontiguousarray(cols, dtype=np.int64)
+        vals = _f64(vals)
+        self._check(self.lib.mfem_b200_set_matrix_triplets(self._h, block_dim, int(n), rows.size,
+                                                           rows.ctypes.data_as(POINTER(c_int64)),
+                                                           cols.ctypes.data_as(POINTER(c_int64)), _dptr(vals),
+                                                           1 if upper_triangle_only else 0))
+        self.dim, self.deg = block_dim, 0
+        self.n_nodes = self.n_dofs = int(n) // block_dim
+        self.n_elems = 0
 
     def bsr_sizes(self):
         nb, nnzb = c_int64(), c_int64()

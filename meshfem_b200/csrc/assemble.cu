@@ -569,6 +569,7 @@ static void launch_assemble(mfem_b200_ctx *c) {
 }
 
 void assemble_values(mfem_b200_ctx *c) {
+    MFEM_REQUIRE(!c->externalMatrix, MFEM_B200_ERR_INVALID, "assemble: the matrix of this handle was set with set_matrix_triplets");
     MFEM_REQUIRE(c->geomValid, MFEM_B200_ERR_INVALID, "assemble: no mesh set");
     MFEM_REQUIRE(c->haveMaterial, MFEM_B200_ERR_INVALID, "assemble: no material set");
     build_pattern(c);

@@ -3,6 +3,8 @@
 #include <cstring>
 #include <fstream>
 
+#include <algorithm>
+
 #include "core.cuh"
 
 using namespace mfem;
@@ -233,9 +235,52 @@ __global__ void k_set_fixed(int64_t n, int N, const int64_t *vars, const double 
     fixedVals[vi] = vals ? vals[i] : 0.0;
 }
 
+// SPSDSystem(K) for a matrix assembled elsewhere (SparseMatrices.hh:2332-2348 setConstrained with an
+// empty C): COO triplets -> summed block-CSR on the host (the reference's TripletMatrix is a host object
+// and its sumRepeated is host work too), then the usual device layout.
+int mfem_b200_set_matrix_triplets(mfem_b200_handle h, int block_dim, int64_t n_vars, int64_t nnz, const int64_t *rows,
+                                  const int64_t *cols, const double *vals, int upper_triangle_only) {
+    API_BEGIN(h)
+    MFEM_REQUIRE(block_dim == 2 || block_dim == 3, MFEM_B200_ERR_INVALID, "set_matrix: block_dim must be 2 or 3");
+    MFEM_REQUIRE(n_vars > 0 && n_vars % block_dim == 0, MFEM_B200_ERR_INVALID, "set_matrix: n_vars must be a positive multiple of block_dim");
+    MFEM_REQUIRE(n_vars / block_dim < INT32_MAX, MFEM_B200_ERR_INVALID, "set_matrix: too many block rows");
+    MFEM_REQUIRE(nnz > 0 && rows && cols && vals, MFEM_B200_ERR_INVALID, "set_matrix: empty matrix");
+    MFEM_REQUIRE(h->nRanks <= 1, MFEM_B200_ERR_INVALID, "set_matrix: single-GPU handles only");
+    const int d = block_dim;
+    const int64_t nb = n_vars / d;
+    struct Entry { uint64_t key; int rc; double v; };
+    std::vector<Entry> e;
+    e.reserve((size_t)nnz * (upper_triangle_only ? 2 : 1));
+    for (int64_t k = 0; k < nnz; ++k) {
+        const int64_t i = rows[k], j = cols[k];
+        MFEM_REQUIRE(i >= 0 && i < n_vars && j >= 0 && j < n_vars, MFEM_B200_ERR_INVALID, "set_matrix: index out of range");
+        if (upper_triangle_only) MFEM_REQUIRE(i <= j, MFEM_B200_ERR_INVALID, "set_matrix: entry below the diagonal in an upper-triangle matrix");
+        e.push_back({((uint64_t)(i / d) << 32) | (uint64_t)(j / d), (int)((i % d) * d + (j % d)), vals[k]});
+        if (upper_triangle_only && i != j)
+            e.push_back({((uint64_t)(j / d) << 32) | (uint64_t)(i / d), (int)((j % d) * d + (i % d)), vals[k]});
+    }
+    std::stable_sort(e.begin(), e.end(), [](const Entry &a, const Entry &b) { return a.key < b.key; });
+    std::vector<int64_t> rowptr((size_t)nb + 1, 0);
+    std::vector<int32_t> colidx;
+    std::vector<double> blocks;
+    uint64_t prev = ~0ULL;
+    for (const Entry &t : e) {
+        if (t.key != prev) {
+            prev = t.key;
+            colidx.push_back((int32_t)(t.key & 0xffffffffULL));
+            blocks.insert(blocks.end(), (size_t)d * d, 0.0);
+            rowptr[(size_t)(t.key >> 32) + 1]++;
+        }
+        blocks[blocks.size() - (size_t)d * d + t.rc] += t.v;       // repeated entries are summed (sumRepeated)
+    }
+    for (int64_t r = 0; r < nb; ++r) rowptr[(size_t)r + 1] += rowptr[(size_t)r];
+    upload_external_bsr(h, d, nb, rowptr, colidx, blocks);
+    API_END(h)
+}
+
 int mfem_b200_fix_variables(mfem_b200_handle h, int64_t n, const int64_t *vars, const double *values) {
     API_BEGIN(h)
-    MFEM_REQUIRE(h->nElems > 0, MFEM_B200_ERR_INVALID, "fix_variables: no mesh set");
+    MFEM_REQUIRE(h->nDofs > 0, MFEM_B200_ERR_INVALID, "fix_variables: no mesh or matrix set");
     if (n == 0) return MFEM_B200_OK;
     MFEM_REQUIRE(n > 0 && vars, MFEM_B200_ERR_INVALID, "fix_variables: bad arguments");
     const int64_t nvar = h->nvar();

@@ -98,6 +98,7 @@ struct mfem_b200_ctx {
     int N = 0, deg = 0, npe = 0;
     int64_t nNodes = 0, nElems = 0, nDofs = 0;
     bool periodic = false;                 // dof_for_node given
+    bool externalMatrix = false;           // K came from mfem_b200_set_matrix_triplets (no mesh, no assembly)
     mfem::DevBuf<double> nodes;            // [nNodes*N]   caller's node order
     mfem::DevBuf<int32_t> elemNodes;       // [nElems*npe] caller's node ids
     mfem::DevBuf<int32_t> elemDof;         // [nElems*npe] INTERNAL dof ids
@@ -215,6 +216,9 @@ void setup_mesh(mfem_b200_ctx *c, int dim, int degree, int64_t nNodes, const dou
                 const int32_t *elemNodes, const int64_t *dofForNode, int64_t nDofs);
 void compute_geometry(mfem_b200_ctx *c);
 void build_pattern(mfem_b200_ctx *c);
+void finish_pattern(mfem_b200_ctx *c);
+void upload_external_bsr(mfem_b200_ctx *c, int dim, int64_t nb, const std::vector<int64_t> &rowptr,
+                         const std::vector<int32_t> &colidx, const std::vector<double> &blocks);
 void build_coloring(mfem_b200_ctx *c);
 // assemble.cu
 void assemble_values(mfem_b200_ctx *c);

@@ -311,6 +311,70 @@ static int bits_for(int64_t n) {
     return b;
 }
 
+// Pattern by-products every SpMV variant needs: tile table of the TMA-ring kernel and the longest row.
+void finish_pattern(mfem_b200_ctx *c) {
+    cudaStream_t s = c->stream;
+    const int64_t nb = c->nDofs;
+    const int64_t nTiles = (c->nnzb + kSpmvTileWindow - 1) / kSpmvTileWindow;
+    c->tileRow.alloc((size_t)nTiles + 1);
+    k_tile_rows<<<grid_for(nTiles + 1, 256), 256, 0, s>>>(nTiles, nb, kSpmvTileWindow, c->rowptr, c->tileRow);
+    DevBuf<unsigned long long> mx(1);
+    MFEM_CUDA(cudaMemsetAsync(mx, 0, 8, s));
+    k_max_row_len<<<grid_for(nb, 256), 256, 0, s>>>(nb, c->rowptr, mx);
+    c->launches += 2;
+    unsigned long long hmx = 0;
+    MFEM_CUDA(cudaMemcpyAsync(&hmx, mx, 8, cudaMemcpyDeviceToHost, s));
+    MFEM_CUDA(cudaStreamSynchronize(s));
+    c->maxRowLen = (int64_t)hmx;
+}
+
+// External matrix (mfem_b200_set_matrix_triplets): block-major values [k][r][c] -> row-plane layout
+template <int N>
+__global__ void k_blocks_to_planes(int64_t nb, const int64_t *__restrict__ rowptr, const double *__restrict__ blk,
+                                   double *__restrict__ vals) {
+    const int64_t row = blockIdx.x;
+    if (row >= nb) return;
+    const int64_t b0 = rowptr[row], n = rowptr[row + 1] - b0;
+    for (int64_t t = threadIdx.x; t < n * N * N; t += blockDim.x) {
+        const int64_t j = t / (N * N);
+        const int rc = (int)(t - j * N * N);
+        vals[val_index<N>(b0, n, j, rc / N, rc % N)] = blk[(b0 + j) * N * N + rc];
+    }
+}
+
+void upload_external_bsr(mfem_b200_ctx *c, int dim, int64_t nb, const std::vector<int64_t> &rowptr,
+                         const std::vector<int32_t> &colidx, const std::vector<double> &blocks) {
+    cudaStream_t s = c->stream;
+    c->N = dim; c->deg = 0; c->npe = 0;
+    c->nNodes = nb; c->nElems = 0; c->nDofs = nb;
+    c->periodic = false;
+    c->externalMatrix = true;
+    c->geomValid = c->haveMaterial = false;
+    c->precondValid = c->workValid = false;
+    c->fixedHost.assign((size_t)nb * dim, 0);
+    c->nFixed = 0;
+    c->nnzb = (int64_t)colidx.size();
+    c->rowptr.alloc((size_t)nb + 1 + 2);
+    c->colidx.alloc((size_t)c->nnzb + 4);
+    c->vals.alloc((size_t)c->nnzb * dim * dim + 2);
+    DevBuf<double> blk(blocks.size());
+    MFEM_CUDA(cudaMemcpyAsync(c->rowptr, rowptr.data(), (nb + 1) * 8, cudaMemcpyHostToDevice, s));
+    MFEM_CUDA(cudaMemcpyAsync(c->colidx, colidx.data(), colidx.size() * 4, cudaMemcpyHostToDevice, s));
+    MFEM_CUDA(cudaMemcpyAsync(blk, blocks.data(), blocks.size() * 8, cudaMemcpyHostToDevice, s));
+    if (dim == 3) k_blocks_to_planes<3><<<(unsigned)nb, 128, 0, s>>>(nb, c->rowptr, blk, c->vals);
+    else k_blocks_to_planes<2><<<(unsigned)nb, 128, 0, s>>>(nb, c->rowptr, blk, c->vals);
+    // identity numbering: the caller's variable order is kept (no coordinates to order along)
+    c->int2ext.alloc((size_t)nb);
+    c->ext2int.alloc((size_t)nb);
+    k_iota<<<grid_for(nb, 256), 256, 0, s>>>(nb, c->int2ext);
+    k_iota<<<grid_for(nb, 256), 256, 0, s>>>(nb, c->ext2int);
+    c->launches += 3;
+    MFEM_CUDA(cudaStreamSynchronize(s));
+    MFEM_CUDA(cudaGetLastError());
+    finish_pattern(c);
+    c->patternValid = c->valuesValid = true;
+}
+
 // ---------------------------------------------------------------------------
 void setup_mesh(mfem_b200_ctx *c, int dim, int degree, int64_t nNodes, const double *nodes, int64_t nElems,
                 const int32_t *elemNodes, const int64_t *dofForNode, int64_t nDofs) {
@@ -326,6 +390,7 @@ void setup_mesh(mfem_b200_ctx *c, int dim, int degree, int64_t nNodes, const dou
     c->nDofs = c->periodic ? nDofs : nNodes;
     MFEM_REQUIRE(c->nDofs > 0 && c->nDofs <= nNodes, MFEM_B200_ERR_INVALID, "bad n_dofs");
     c->patternValid = c->valuesValid = c->geomValid = c->precondValid = c->workValid = false;
+    c->externalMatrix = false;
     c->fixedHost.assign((size_t)c->nDofs * dim, 0);
     c->nFixed = 0;
 
@@ -556,19 +621,7 @@ void build_pattern(mfem_b200_ctx *c) {
         c->launches++;
         MFEM_CUDA(cudaStreamSynchronize(s));
     }
-    {   // tiles of the TMA-ring SpMV + longest row
-        const int64_t nTiles = (c->nnzb + kSpmvTileWindow - 1) / kSpmvTileWindow;
-        c->tileRow.alloc((size_t)nTiles + 1);
-        k_tile_rows<<<grid_for(nTiles + 1, 256), 256, 0, s>>>(nTiles, nb, kSpmvTileWindow, c->rowptr, c->tileRow);
-        DevBuf<unsigned long long> mx(1);
-        MFEM_CUDA(cudaMemsetAsync(mx, 0, 8, s));
-        k_max_row_len<<<grid_for(nb, 256), 256, 0, s>>>(nb, c->rowptr, mx);
-        c->launches += 2;
-        unsigned long long hmx = 0;
-        MFEM_CUDA(cudaMemcpyAsync(&hmx, mx, 8, cudaMemcpyDeviceToHost, s));
-        MFEM_CUDA(cudaStreamSynchronize(s));
-        c->maxRowLen = (int64_t)hmx;
-    }
+    finish_pattern(c);
     MFEM_CUDA(cudaGetLastError());
     c->vals.alloc((size_t)c->nnzb * c->N * c->N + 2);
     c->patternValid = true;

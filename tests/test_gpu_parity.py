@@ -182,6 +182,41 @@ def test_batched_pcg_matches_sequential_and_direct(mfem, N, deg, sizes):
         assert len({i["iterations"] for i in ib}) > 1      # the systems did finish at different iterations
 
 
+@pytest.mark.parametrize("N,deg,sizes", [(3, 2, (5, 2, 2)), (2, 1, (9, 4))])
+@pytest.mark.parametrize("upper", [True, False])
+def test_external_matrix_spsd_system(mfem, N, deg, sizes, upper):
+    """Seam S2 (SPSDSystem(K), SparseMatrices.hh:2321-2348): a matrix assembled elsewhere -- here the
+    oracle's K as triplets, upper triangle with REPEATED entries as the reference produces them
+    (LinearElasticity.hh:1408-1466) or full -- is summed, laid out on the device and solved with fixed
+    variables; SpMV, export and the solution must match scipy."""
+    sim, fixed, vals, f = cantilever_problem(N, deg, sizes)
+    vals = 1e-3 * np.cos(np.arange(vals.size))
+    K = sim.stiffness().tocsr()
+    if upper:
+        I, J, W = orc.assemble_upper_triplets(sim.mesh, sim.D)      # unsummed, i <= j
+        Kin = (K.shape[0], I, J, W)
+    else:
+        Kin = K
+    rng = np.random.default_rng(9)
+    x = rng.normal(size=K.shape[0])
+    with mfem.Handle(0) as h:
+        h.set_matrix(Kin, block_dim=N, upper_triangle_only=upper)
+        y = h.spmv(x.reshape(-1, N)).reshape(-1)
+        assert rel_l2(y, K @ x) < 1e-13
+        assert abs(h.get_matrix() - K).max() <= 1e-13 * abs(K).max()
+        h.fix_variables(fixed, vals)
+        u, info = h.solve(f, rtol=1e-12, return_info=True)
+        assert info[0]["converged"]
+        assert rel_l2(u, orc.solve_fixed(K, f.reshape(-1), fixed, vals)) < 1e-8
+        with pytest.raises(mfem.MfemB200Error, match="set_matrix_triplets"):
+            h.assemble()
+    with mfem.Handle(0) as h:
+        with pytest.raises(mfem.MfemB200Error, match="below the diagonal"):
+            h.set_matrix((4, [1], [0], [1.0]), block_dim=2, upper_triangle_only=True)
+        with pytest.raises(mfem.MfemB200Error, match="multiple of block_dim"):
+            h.set_matrix((5, [0], [0], [1.0]), block_dim=2)
+
+
 def test_nonzero_dirichlet_values_and_multiple_rhs(mfem):
     """fixVariables with non-zero values moves K_fc u_c to the RHS (SparseMatrices.hh:2457-2470)."""
     sim, fixed, vals, f = cantilever_problem(3, 2, (4, 2, 2), D=orc.material_from_json(3, ORTHO))
