@@ -365,6 +365,7 @@ struct FaceMembership {
     static FaceMembership AllFaces() { FaceMembership r; r.membership.set(); return r; }
     bool onMinFace(size_t d) const { return membership[d]; }
     bool onMaxFace(size_t d) const { return membership[N + d]; }
+    bool onMinOrMaxFace(size_t d) const { return onMinFace(d) || onMaxFace(d); }
     size_t count() const { return membership.count(); }
     bool onAnyMaxFace() const { return (membership >> N).any(); }
     bool isMinimalNode() const { return !onAnyMaxFace(); }

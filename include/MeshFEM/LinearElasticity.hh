@@ -124,6 +124,25 @@ public:
         return dofToNodeField(x);
     }
     VField solve() const { return solve(neumannLoad()); }
+    // Solve against the assembled K with an explicit set of fixed variables instead of the ones the
+    // boundary conditions imply (OrthotropicHomogenization.hh:64-119 builds one SPSDSystem per set; here
+    // the matrix stays on the device and only the mask + preconditioner change).  The cached
+    // constrained system is invalidated afterwards.
+    std::vector<VField> solveWithFixedVariables(const std::vector<size_t> &fixedVars, const std::vector<Real> &fixedVarValues,
+                                                const std::vector<VField> &fs) const {
+        mfemCheck(h(), mfem_b200_clear_fixed_variables(h()));
+        m_system.setAssembled(N * numDoFs());
+        m_system.fixVariables(fixedVars, fixedVarValues);
+        BENCHMARK_START_TIMER_SECTION("Elasticity Solve");
+        std::vector<std::vector<Real>> rhs, xs;
+        for (const auto &f : fs) rhs.push_back(f.data());
+        m_system.solveMultiple(rhs, xs);
+        BENCHMARK_STOP_TIMER_SECTION("Elasticity Solve");
+        std::vector<VField> result;
+        for (const auto &x : xs) result.push_back(dofToNodeField(x));
+        m_system.clear();
+        return result;
+    }
     // all right-hand sides against one assembled system (batched on the device when there are flatLen(N))
     std::vector<VField> solve(const std::vector<VField> &fs) const {
         if (!m_system.isSet()) m_buildConstrainedSystem();

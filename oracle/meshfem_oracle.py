@@ -1405,3 +1405,70 @@ def read_msh(path):
             rows.append([x - 1 for x in t[3 + ntags:3 + ntags + npe[etype]]])
         E = np.array(rows)
     return V, E.astype(np.int64), etype
+
+
+# ---------------------------------------------------------------------------------------------
+# Orthotropic-cell homogenization (OrthotropicHomogenization.hh:42-240): the positive octant
+# (quadrant) of a base cell with reflective symmetries; no periodic DoFs, one K, 1 + (flat - N)
+# different sets of fixed variables.
+def orthotropic_fixed_variable_sets(mesh, eps=1e-7):
+    """[stretch set, shear set 0, ...] of scalar variable indices (:77-119)."""
+    N = mesh.N
+    bn = mesh.bdry_nodes
+    P = mesh.nodes[bn]
+    on = (np.abs(P - mesh.bbox_min[None, :]) <= eps) | (np.abs(P - mesh.bbox_max[None, :]) <= eps)   # (nbn, N): onMinOrMaxFace(c)
+    stretch = sorted(int(N * n + c) for k, n in enumerate(bn) for c in range(N) if on[k, c])
+    sets = [stretch]
+    for s in range(flat_len(N) - N):
+        fix = set()
+        for k, n in enumerate(bn):
+            for c in range(N):
+                if on[k, c]:
+                    if N == 3:
+                        fix.add(int(N * n + s))
+                        if c != s:
+                            fix.add(int(N * n + (N - (c + s))))
+                    else:
+                        fix.add(int(N * n + (1 if c == 0 else 0)))
+        sets.append(sorted(fix))
+    return sets
+
+
+def solve_orthotropic_cell_problems(sim, eps=1e-7):
+    """Orthotropic::solveCellProblems (:42-145): w_ij on the orthotropic base cell."""
+    N = sim.N
+    F = flat_len(N)
+    K = stiffness_matrix(sim.mesh, sim.D)
+    sets = orthotropic_fixed_variable_sets(sim.mesh, eps)
+    w = []
+    for ij in range(F):
+        rhs = constant_strain_load(sim.mesh, sim.D, -canonical_basis(N, ij)).reshape(-1)
+        fixed = sets[0] if ij < N else sets[ij - N + 1]
+        w.append(solve_fixed(K, rhs, np.array(fixed, dtype=np.int64), np.zeros(len(fixed))).reshape(-1, N))
+    return w
+
+
+def fluctuation_displacement_sign(N, ij, r):
+    """:149-163"""
+    if ij < N:
+        return 1.0
+    bits = [(r >> b) & 1 for b in range(N)]
+    if N == 3:
+        bits[ij - N] = 0
+    return -1.0 if sum(bits) == 1 else 1.0
+
+
+def homogenized_tensor_from_ortho_cell_quantity(N, EhO):
+    """:165-185 -- only the upper triangle of EhO is read; the result is symmetric."""
+    F = flat_len(N)
+    Eh = np.zeros((F, F))
+    for r in range(1 << N):
+        for kl in range(F):
+            for ij in range(kl + 1):
+                Eh[ij, kl] += fluctuation_displacement_sign(N, ij, r) * fluctuation_displacement_sign(N, kl, r) * EhO[ij, kl]
+    Eh /= (1 << N)
+    return np.triu(Eh) + np.triu(Eh, 1).T
+
+
+def orthotropic_homogenized_tensor_displacement_form(sim, w_ij):
+    return homogenized_tensor_from_ortho_cell_quantity(sim.N, homogenized_tensor_displacement_form(sim, w_ij))

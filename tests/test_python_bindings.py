@@ -116,5 +116,14 @@ def test_homogenize_and_probe(pymods, deg):
     trans = np.array([w[bn][np.abs(m.nodes[bn][:, d] - m.bbox_min[d]) < 1e-9, d].mean() for d in range(3)])
     assert rel_l2(u, w - trans[None, :] + m.nodes @ Em.T) < 1e-12
     assert rel_l2(strain, sum(dbl[i] * e[i] * hr.strain_w_ij[i] for i in range(6)) + e[None, :]) < 1e-12
-    with pytest.raises(RuntimeError, match="orthotropicCell"):
-        ph.homogenize(V, T, C.D, degree=deg, orthotropicCell=True)
+    # orthotropic base cell (positive octant): same tensor as the full periodic cell, w_ij as the oracle's
+    from test_gpu_cli import _perforated_octant
+    Vo, To = _perforated_octant()
+    ho = ph.homogenize(Vo, To, C.D, degree=deg, orthotropicCell=True, centerFluctuationDisplacements=False, rtol=1e-12)
+    assert np.abs(ho.Ch - gold[f"Eh_deg{deg}"]).max() < 1e-7 * np.abs(ho.Ch).max()
+    sim = orc.Simulator(3, deg, Vo, To); sim.set_material(C.D)
+    wo = orc.solve_orthotropic_cell_problems(sim)
+    for i in range(6):
+        assert rel_l2(ho.w_ij[i], wo[i]) < 1e-6
+    with pytest.raises(RuntimeError, match="manualPeriodicVerticesFile"):
+        ph.homogenize(V, T, C.D, degree=deg, manualPeriodicVerticesFile="x.txt")
