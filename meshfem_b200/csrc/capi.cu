@@ -100,7 +100,7 @@ int mfem_b200_set_option(mfem_b200_handle h, const char *name, int64_t value) {
     } else if (n == "graph") {
         h->opt_graph = value != 0;
     } else if (n == "spmv_kernel") {
-        MFEM_REQUIRE(value >= 0 && value <= 3, MFEM_B200_ERR_INVALID, "spmv_kernel must be 0 (auto), 1 (direct loads), 2 (TMA ring) or 3 (index-pipelined)");
+        MFEM_REQUIRE(value >= 0 && value <= 4, MFEM_B200_ERR_INVALID, "spmv_kernel must be 0 (auto), 1 (direct loads), 2 (TMA ring), 3 (index-pipelined) or 4 (symmetric)");
         h->opt_spmv_kernel = (int)value;
     } else if (n == "spmv_lanes") {
         MFEM_REQUIRE(value == 0 || value == 8 || value == 16 || value == 32, MFEM_B200_ERR_INVALID,

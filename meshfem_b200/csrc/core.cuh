@@ -89,7 +89,7 @@ struct mfem_b200_ctx {
     int opt_reorder = 1;
     int opt_assembly = 0;
     int opt_graph = 1;
-    int opt_spmv_kernel = 0;               // 0 auto, 1 direct-load kernel, 2 TMA-ring kernel
+    int opt_spmv_kernel = 0;               // 0 auto, 1 direct-load kernel, 2 TMA-ring kernel, 3 index-pipelined, 4 symmetric (upper tails + atomics)
     int opt_spmm_kernel = 0;               // batched PCG: 0/1 full-warp SpMM, 2 half-warp split SpMM (even batch sizes)
     int opt_batch_rhs = 1;                 // solve flatLen(N) right-hand sides as one batched PCG (SpMM)
     int opt_spmv_lanes = 0;                // lanes per block row in the SpMV (0 = choose from the mean row length)
@@ -122,6 +122,7 @@ struct mfem_b200_ctx {
     mfem::DevBuf<double> vals;             // [nnzb*N*N (+2 pad)]  "row-plane" layout, see val_index()
     mfem::DevBuf<int64_t> tileRow;         // [nTiles+1] first row of each kSpmvTileWindow-block window (TMA SpMV)
     int64_t maxRowLen = 0;                 // longest block row
+    mfem::DevBuf<int32_t> upperStart;      // [nDofs] first slot with column >= row (symmetric SpMV reads only that tail)
     // DoF -> incident (element, local node) lists
     int64_t totalInc = 0;
     mfem::DevBuf<int64_t> incPtr;          // [nDofs+1]

@@ -311,10 +311,28 @@ static int bits_for(int64_t n) {
     return b;
 }
 
-// Pattern by-products every SpMV variant needs: tile table of the TMA-ring kernel and the longest row.
+// upperStart[r] = first slot of block row r whose column is >= r (the diagonal when it is present)
+__global__ void k_upper_start(int64_t nb, const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
+                              int32_t *__restrict__ upperStart) {
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= nb) return;
+    const int64_t b0 = rowptr[r];
+    int lo = 0, hi = (int)(rowptr[r + 1] - b0);
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (colidx[b0 + mid] < r) lo = mid + 1; else hi = mid;
+    }
+    upperStart[r] = lo;
+}
+
+// Pattern by-products every SpMV variant needs: tile table of the TMA-ring kernel, the longest row, and
+// the start of every row's upper-triangular tail (symmetric SpMV).
 void finish_pattern(mfem_b200_ctx *c) {
     cudaStream_t s = c->stream;
     const int64_t nb = c->nDofs;
+    c->upperStart.alloc((size_t)nb + 2);
+    k_upper_start<<<grid_for(nb, 256), 256, 0, s>>>(nb, c->rowptr, c->colidx, c->upperStart);
+    c->launches++;
     const int64_t nTiles = (c->nnzb + kSpmvTileWindow - 1) / kSpmvTileWindow;
     c->tileRow.alloc((size_t)nTiles + 1);
     k_tile_rows<<<grid_for(nTiles + 1, 256), 256, 0, s>>>(nTiles, nb, kSpmvTileWindow, c->rowptr, c->tileRow);

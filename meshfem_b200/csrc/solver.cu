@@ -519,6 +519,120 @@ k_bsr_spmv_pipe(int64_t nb, const int64_t *__restrict__ rowptr, const int32_t *_
 }
 
 // ---------------------------------------------------------------------------
+// K3s  bsr_spmv_sym: y += K x reading only the UPPER-triangular tail of every block row.
+// K is symmetric (K_ji = K_ij^T), and the row-plane layout stores a row's blocks in column order, so the
+// blocks with column >= row are a contiguous tail of each plane: the kernel streams that tail only --
+// half the matrix bytes -- and applies every off-diagonal block twice:
+//     y_i += K_ij x_j          (row part, reduced across the lanes as in k_bsr_spmv)
+//     y_j += K_ij^T x_i        (transposed part: one fire-and-forget red.global.add.f64 per (block, component))
+// y must be zero on entry; every update of y is an atomic add (rows receive transposed contributions from
+// other warps).  Summation order therefore varies from run to run: results agree to rounding, not
+// bit for bit (the assembly stays bit-reproducible).  Masking of fixed rows and the p.Ap dot product
+// move to k_mask_dot.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void red_add_f64(double *p, double v) {
+    asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+
+template <int N, int LPR>
+__global__ void __launch_bounds__(kSpmvThreads, 4)
+k_bsr_spmv_sym(int64_t nb, const int64_t *__restrict__ rowptr, const int32_t *__restrict__ upperStart,
+               const int32_t *__restrict__ colidx, const double *__restrict__ vals, const double *__restrict__ x,
+               double *__restrict__ y, const int *status) {
+    constexpr int NN = N * N;
+    constexpr int RPW = 32 / LPR;
+    constexpr int U = 3;
+    constexpr int CH = U * LPR;
+    static_assert(CH % N == 0, "a chunk must cover whole blocks");
+    if (status && status[ST_STATE] != 0) return;
+    const int lane = threadIdx.x & 31;
+    const int sub = lane / LPR, sl = lane % LPR;
+    const int64_t warpGlobal = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nWarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int comp = owner_component<N, LPR>(sl);
+    const unsigned groupMask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (sub * LPR));
+    const uint64_t polStream = l2_policy_evict_first(), polKeep = l2_policy_evict_last();
+    int jj[U], cc[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int f = sl + u * LPR;
+        jj[u] = f / N;
+        cc[u] = f - jj[u] * N;
+    }
+    int64_t row = warpGlobal * RPW + sub;
+    const int64_t rowStride = nWarps * RPW;
+    int64_t nb0 = 0, nb1 = 0;
+    int us1 = 0;
+    if (row < nb) { nb0 = rowptr[row]; nb1 = rowptr[row + 1]; us1 = upperStart[row]; }
+    for (int64_t rowBase = warpGlobal * RPW; rowBase < nb; rowBase += rowStride) {
+        const int64_t b0 = nb0;
+        const int n = (int)(nb1 - nb0), us = us1;
+        const int L = n * N;                      // plane stride of the full row
+        const int Lu = (n - us) * N;              // scalars of the upper tail per plane
+        const int64_t thisRow = row;
+        row += rowStride;
+        nb0 = nb1 = 0; us1 = 0;
+        if (row < nb) { nb0 = rowptr[row]; nb1 = rowptr[row + 1]; us1 = upperStart[row]; }
+        const double *v = vals + b0 * NN + N * us + sl;
+        const int32_t *ci = colidx + b0 + us;
+        double xi[N];
+#pragma unroll
+        for (int r = 0; r < N; ++r) xi[r] = (thisRow < nb) ? x[thisRow * N + r] : 0.0;
+        double acc[N];
+#pragma unroll
+        for (int r = 0; r < N; ++r) acc[r] = 0.0;
+        for (int base = 0; base < Lu; base += CH, v += CH, ci += CH / N) {
+            const int rem = Lu - base - sl;
+            int col[U];
+            double a[U][N], xv[U];
+            ChunkLoader<N, LPR>::run(ci + jj[0], ci + jj[1], ci + jj[2], v, v + L, v + 2 * L, rem, polStream, col, a);
+            __syncwarp(groupMask);
+            gather3(x + (col[0] * N + cc[0]), x + (col[1] * N + cc[1]), x + (col[2] * N + cc[2]), polKeep, xv);
+            __syncwarp(groupMask);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                double t = 0.0;
+#pragma unroll
+                for (int r = 0; r < N; ++r) {
+                    acc[r] = fma(a[u][r], xv[u], acc[r]);
+                    t = fma(a[u][r], xi[r], t);
+                }
+                // transposed part: this lane holds column (col, cc) of the block for all N rows
+                if (u * LPR < rem && col[u] != (int)thisRow) red_add_f64(y + ((int64_t)col[u] * N + cc[u]), t);
+            }
+        }
+        const double out0 = fold_reduce<N, LPR>(acc, sl);
+        if (comp >= 0 && thisRow < nb) red_add_f64(y + (thisRow * N + comp), out0);
+    }
+}
+
+// after the symmetric SpMV (and, on several GPUs, the interface exchange): zero Ap on fixed variables and
+// reduce p.Ap over the owned DoFs
+template <int N>
+__global__ void __launch_bounds__(kVecThreads)
+k_mask_dot(int64_t nb, const uint8_t *__restrict__ fixedMask, const uint8_t *__restrict__ owned,
+           const double *__restrict__ p, double *__restrict__ Ap, double *partials, unsigned *ticket, double *dotOut,
+           const int *status) {
+    if (status && status[ST_STATE] != 0) return;
+    double acc[1] = {0.0};
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nb; i += (int64_t)gridDim.x * blockDim.x) {
+        const double wgt = (owned && !owned[i]) ? 0.0 : 1.0;
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            if (fixedMask && fixedMask[i * N + k]) Ap[i * N + k] = 0.0;
+            else acc[0] += wgt * p[i * N + k] * Ap[i * N + k];
+        }
+    }
+    if (dotOut) {
+        block_reduce_store<1>(acc, partials);
+        if (last_block(ticket)) {
+            const double s = final_sum(partials, gridDim.x);
+            if (threadIdx.x == 0) dotOut[0] = s;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // K3b  bsr_spmv_tma: the same SpMV with the matrix stream decoupled from the compute warps.
 // One persistent CTA per SM.  A producer warp walks the CTA's tiles (a tile = the consecutive
 // block rows whose first block falls into a window of kTmaWindow blocks) and moves each tile's
@@ -1038,8 +1152,27 @@ static void launch_spmv_pipe(mfem_b200_ctx *c, const double *x, double *y, bool 
     c->launches++;
 }
 
+static bool spmv_use_sym(mfem_b200_ctx *c) { return c->opt_spmv_kernel == 4; }
+
+// y = K x through the upper tails (y zeroed here); no masking, no dot
+template <int N>
+static void launch_spmv_sym(mfem_b200_ctx *c, const double *x, double *y, const int *status) {
+    MFEM_CUDA(cudaMemsetAsync(y, 0, sizeof(double) * c->nvar(), c->stream));
+    const double meanLu = c->nDofs ? double(c->nnzb + c->nDofs) * 0.5 * c->N / double(c->nDofs) : 0.0;
+    const int lanes = (c->opt_spmv_lanes == 8 || c->opt_spmv_lanes == 16 || c->opt_spmv_lanes == 32)
+                          ? c->opt_spmv_lanes : (meanLu > 40.0 ? 32 : (meanLu > 18.0 ? 16 : 8));
+#define MFEM_SYM_LAUNCH(L_)                                                                                         \
+    k_bsr_spmv_sym<N, L_><<<spmv_grid(c, L_, k_bsr_spmv_sym<N, L_>), kSpmvThreads, 0, c->stream>>>(                  \
+        c->nDofs, c->rowptr, c->upperStart, c->colidx, c->vals, x, y, status)
+    if (lanes == 8) MFEM_SYM_LAUNCH(8);
+    else if (lanes == 16) MFEM_SYM_LAUNCH(16);
+    else MFEM_SYM_LAUNCH(32);
+#undef MFEM_SYM_LAUNCH
+    c->launches++;
+}
+
 static bool spmv_use_tma(mfem_b200_ctx *c) {
-    if (c->opt_spmv_kernel == 1 || c->opt_spmv_kernel == 3) return false;
+    if (c->opt_spmv_kernel == 1 || c->opt_spmv_kernel == 3 || c->opt_spmv_kernel == 4) return false;
     const bool fits = c->maxRowLen <= kTmaMaxRow && c->tileRow.n > 1;
     if (c->opt_spmv_kernel == 2) {
         MFEM_REQUIRE(fits, MFEM_B200_ERR_INVALID, "spmv_kernel=2 (TMA ring) needs block rows of at most 128 blocks");
@@ -1072,6 +1205,17 @@ static void launch_spmv_tma(mfem_b200_ctx *c, const double *x, double *y, bool m
 
 template <int N>
 static void launch_spmv(mfem_b200_ctx *c, const double *x, double *y, bool masked, bool dot) {
+    if (spmv_use_sym(c)) {
+        PcgWork &w = c->work;
+        launch_spmv_sym<N>(c, x, y, (masked && dot) ? w.status.p : nullptr);
+        if (masked || dot) {
+            k_mask_dot<N><<<vec_grid(c, c->nDofs), kVecThreads, 0, c->stream>>>(
+                c->nDofs, masked ? c->fixedMask.p : nullptr, nullptr, x, y, w.partials, w.ticket, dot ? w.scal.p + S_PAP : nullptr,
+                (masked && dot) ? w.status.p : nullptr);
+            c->launches++;
+        }
+        return;
+    }
     if (spmv_use_tma(c)) { launch_spmv_tma<N>(c, x, y, masked, dot); return; }
     // index-pipelined kernel (option 3): one block row per warp, i.e. the 32-lane configuration.  Not the
     // default: measured equal on cfg3 (1.33 vs 1.32 ms) and slower on cfg5 (6.75 vs 6.33 ms) -- the direct

@@ -71,10 +71,10 @@ def test_assembly_is_bit_reproducible(mfem, N, deg, sizes):
 
 
 @pytest.mark.parametrize("N,deg,sizes", CASES + [(3, 2, (9, 4, 3))])
-@pytest.mark.parametrize("lanes,kernel", [(0, 0), (0, 1), (8, 1), (16, 1), (32, 1), (0, 2), (32, 3)])
+@pytest.mark.parametrize("lanes,kernel", [(0, 0), (0, 1), (8, 1), (16, 1), (32, 1), (0, 2), (32, 3), (0, 4), (8, 4), (16, 4), (32, 4)])
 def test_spmv_and_apply_K(mfem, N, deg, sizes, lanes, kernel):
     """kernel 0 = auto, 1 = direct-load SpMV (8/16/32 lanes per row), 2 = TMA-ring SpMV,
-    3 = index-pipelined SpMV (32 lanes)."""
+    3 = index-pipelined SpMV (32 lanes), 4 = symmetric SpMV (upper tails + atomic adds)."""
     mesh = grid_mesh(N, deg, sizes)
     D = _material(N, "ortho")
     rng = np.random.default_rng(5)
@@ -135,7 +135,7 @@ def test_loads_and_strain_stress(mfem, N, deg, sizes, mat):
 
 
 @pytest.mark.parametrize("N,deg,sizes", [(2, 1, (20, 4)), (2, 2, (10, 2)), (3, 1, (10, 2, 2)), (3, 2, (10, 2, 2))])
-@pytest.mark.parametrize("reorder,kernel", [(0, 1), (1, 1), (1, 2), (1, 3), (1, 0)])
+@pytest.mark.parametrize("reorder,kernel", [(0, 1), (1, 1), (1, 2), (1, 3), (1, 0), (1, 4), (0, 4)])
 def test_cantilever_displacements_match_direct_solve(mfem, N, deg, sizes, reorder, kernel):
     sim, fixed, vals, f = cantilever_problem(N, deg, sizes)
     u_ref = sim.solve(f)
