@@ -112,6 +112,7 @@ def build_host(force: bool = False) -> str:
     os.makedirs(bindir, exist_ok=True)
     for name, src in (("Simulate_cli", "src/bin/Simulate_cli.cc"),
                       ("PeriodicHomogenization_cli", "src/bin/PeriodicHomogenization_cli.cc"),
+                      ("ConstStrainDisplacement_cli", "src/bin/ConstStrainDisplacement_cli.cc"),
                       ("grid", "src/bin/tools/grid.cc")):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-I" + os.path.join(REPO, "include"),
                                os.path.join(REPO, src), os.path.join(REPO, "src", "host", "MeshIO.cc"),
