@@ -64,6 +64,9 @@ int mfem_b200_device_count(void);
  * set_mesh receives this rank's LOCAL sub-mesh and set_interface its shared DoFs.       */
 int mfem_b200_comm_unique_id(void *out128);
 int mfem_b200_comm_init(mfem_b200_handle h, int n_ranks, int rank, const void *nccl_unique_id128);
+/* Put h on the communicator of `parent` (same process, same device) instead of creating another one:
+ * a long-lived parent handle plays the role of the process group; parent must outlive h.      */
+int mfem_b200_comm_share(mfem_b200_handle h, mfem_b200_handle parent);
 
 /* ---- options (before set_mesh) --------------------------------------------------- */
 /* "reorder": 1 (default) renumbers DoFs along a space-filling curve inside the handle;

@@ -24,7 +24,7 @@ SYMBOLS = [
     "mfem_b200_set_node_positions", "mfem_b200_fix_variables", "mfem_b200_clear_fixed_variables",
     "mfem_b200_solve", "mfem_b200_apply_K", "mfem_b200_spmv", "mfem_b200_const_strain_load",
     "mfem_b200_avg_strain_stress", "mfem_b200_get_volumes", "mfem_b200_get_timer", "mfem_b200_reset_timers",
-    "mfem_b200_launch_count", "mfem_b200_time_spmv", "mfem_b200_set_matrix_triplets",
+    "mfem_b200_launch_count", "mfem_b200_time_spmv", "mfem_b200_set_matrix_triplets", "mfem_b200_comm_share",
 ]
 
 STATUS_NAMES = {
@@ -66,6 +66,7 @@ def load_library():
     lib.mfem_b200_device_count.argtypes = []
     lib.mfem_b200_comm_unique_id.argtypes = [c_void_p]
     lib.mfem_b200_comm_init.argtypes = [c_void_p, c_int, c_int, c_void_p]
+    lib.mfem_b200_comm_share.argtypes = [c_void_p, c_void_p]
     lib.mfem_b200_set_option.argtypes = [c_void_p, c_char_p, c_int64]
     lib.mfem_b200_set_mesh.argtypes = [c_void_p, c_int, c_int, c_int64, dp, c_int64, ip, lp, c_int64]
     lib.mfem_b200_set_interface.argtypes = [c_void_p, c_int, ip, lp, ip, POINTER(ctypes.c_uint8)]
@@ -162,6 +163,11 @@ class Handle:
     def comm_init(self, n_ranks, rank, unique_id: bytes):
         buf = ctypes.create_string_buffer(unique_id, 128)
         self._check(self.lib.mfem_b200_comm_init(self._h, n_ranks, rank, buf))
+
+    def comm_share(self, parent):
+        """Use the communicator of `parent` (a long-lived handle of this process) instead of creating one."""
+        self._check(self.lib.mfem_b200_comm_share(self._h, parent._h))
+        self._comm_parent = parent          # keep it alive
 
     @staticmethod
     def comm_unique_id() -> bytes:

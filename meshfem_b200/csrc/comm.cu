@@ -65,10 +65,8 @@ __global__ void k_map_owned(int64_t n, const uint8_t *__restrict__ ownedExt, con
 void comm_destroy(mfem_b200_ctx *c) {
     delete c->halo;
     c->halo = nullptr;
-    if (c->ncclComm) {
-        ncclCommDestroy(static_cast<ncclComm_t>(c->ncclComm));
-        c->ncclComm = nullptr;
-    }
+    if (c->ncclComm && c->ownsComm) ncclCommDestroy(static_cast<ncclComm_t>(c->ncclComm));
+    c->ncclComm = nullptr;
 }
 
 const uint8_t *halo_owned(mfem_b200_ctx *c) {
@@ -141,8 +139,24 @@ int mfem_b200_comm_init(mfem_b200_handle h, int n_ranks, int rank, const void *n
         return MFEM_B200_ERR_COMM;
     }
     h->ncclComm = comm;
+    h->ownsComm = true;
     h->nRanks = n_ranks;
     h->rank = rank;
+    return MFEM_B200_OK;
+}
+
+// A further handle of the same process on the communicator of `parent` (a long-lived "process group"
+// handle): no second ncclCommInitRank.  `parent` must outlive h; the two must not run collectives
+// concurrently (one stream at a time per communicator).
+int mfem_b200_comm_share(mfem_b200_handle h, mfem_b200_handle parent) {
+    if (!h || !parent) return MFEM_B200_ERR_INVALID;
+    if (!parent->ncclComm || parent->nRanks < 2) { h->err = "comm_share: parent has no communicator"; return MFEM_B200_ERR_INVALID; }
+    if (h->nElems != 0) { h->err = "comm_share must precede set_mesh"; return MFEM_B200_ERR_INVALID; }
+    if (h->device != parent->device) { h->err = "comm_share: handles live on different devices"; return MFEM_B200_ERR_INVALID; }
+    h->ncclComm = parent->ncclComm;
+    h->ownsComm = false;
+    h->nRanks = parent->nRanks;
+    h->rank = parent->rank;
     return MFEM_B200_OK;
 }
 

@@ -161,6 +161,7 @@ struct mfem_b200_ctx {
     // multi-GPU
     int nRanks = 1, rank = 0;
     void *ncclComm = nullptr;
+    bool ownsComm = false;                 // false: borrowed from another handle (mfem_b200_comm_share)
     mfem::Halo *halo = nullptr;
 
     // bookkeeping

@@ -207,13 +207,15 @@ __global__ void __launch_bounds__(kBlkChunk)
 k_plan_segments(int64_t nnzb, const int32_t *__restrict__ counts, uint16_t *__restrict__ planCnt,
                 uint16_t *__restrict__ planSegOff, uint8_t *__restrict__ planNseg,
                 uint8_t *__restrict__ chunkL, uint16_t *__restrict__ segOrder, int64_t *__restrict__ warpEntries,
-                int *__restrict__ overflow) {
+                int *__restrict__ overflow, const int32_t *__restrict__ blockStart, const uint32_t *__restrict__ sortedPairs,
+                int pairsPerElem) {
     typedef cub::BlockScan<int, kBlkChunk> Scan;
     typedef cub::BlockReduce<int, kBlkChunk> Reduce;
     typedef cub::BlockRadixSort<uint32_t, kBlkChunk, 2, uint32_t> Sort;
     __shared__ union { typename Scan::TempStorage scan; typename Reduce::TempStorage red; typename Sort::TempStorage sort; } temp;
     __shared__ int sTotal;
     __shared__ uint16_t sLen[kSegSlots], sLenSorted[kSegSlots], sIdxSorted[kSegSlots];
+    __shared__ uint32_t sElem[kSegSlots];     // element of the first contribution of every segment
     const int t = threadIdx.x;
     const int64_t chunk = blockIdx.x, k = chunk * kBlkChunk + t;
     int cnt = k < nnzb ? counts[k] : 0;
@@ -235,16 +237,30 @@ k_plan_segments(int64_t nnzb, const int32_t *__restrict__ counts, uint16_t *__re
     Scan(temp.scan).ExclusiveSum(nseg, off);
     for (int j = t; j < kSegSlots; j += kBlkChunk) sLen[j] = 0;
     __syncthreads();
-    for (int p = 0; p < nseg; ++p) sLen[off + p] = (uint16_t)min(L, cnt - p * L);
+    for (int p = 0; p < nseg; ++p) {
+        sLen[off + p] = (uint16_t)min(L, cnt - p * L);
+        sElem[off + p] = sortedPairs[(int64_t)blockStart[k] + (int64_t)p * L] / (uint32_t)pairsPerElem;
+    }
     __syncthreads();
-    uint32_t key[2] = {sLen[2 * t], sLen[2 * t + 1]};
+    // Sort key: length first (the lanes of a warp loop equally often), then the element of the first
+    // contribution: segments that read the same element records end up in the same warp, so a geometry
+    // gather touches few distinct cache lines.
+    uint32_t key[2];
+    for (int i = 0; i < 2; ++i) {
+        const int sgi = 2 * t + i;
+        key[i] = sLen[sgi] ? (((uint32_t)min((int)sLen[sgi], 255) << 24) | (sElem[sgi] & 0xffffffu)) : 0u;
+    }
     uint32_t val[2] = {(uint32_t)(2 * t), (uint32_t)(2 * t + 1)};
     Sort(temp.sort).SortDescending(key, val);        // stable; blocked: thread t holds ranks 2t, 2t+1
-    for (int i = 0; i < 2; ++i) { sLenSorted[2 * t + i] = (uint16_t)key[i]; sIdxSorted[2 * t + i] = (uint16_t)val[i]; }
+    for (int i = 0; i < 2; ++i) { sLenSorted[2 * t + i] = sLen[val[i]]; sIdxSorted[2 * t + i] = (uint16_t)val[i]; }
     __syncthreads();
     for (int j = t; j < kSegSlots; j += kBlkChunk)
         segOrder[chunk * kSegSlots + j] = sLenSorted[j] ? sIdxSorted[j] : (uint16_t)0xffff;
-    if (t < kSegSlots / 32) warpEntries[chunk * (kSegSlots / 32) + t] = 32 * (int64_t)sLenSorted[32 * t];
+    if (t < kSegSlots / 32) {          // trips of a warp-round = its longest segment
+        int mx = 0;
+        for (int j = 0; j < 32; ++j) mx = max(mx, (int)sLenSorted[32 * t + j]);
+        warpEntries[chunk * (kSegSlots / 32) + t] = 32 * (int64_t)mx;
+    }
     if (k < nnzb) { planCnt[k] = (uint16_t)cnt; planSegOff[k] = (uint16_t)off; planNseg[k] = (uint8_t)nseg; }
     if (t == 0) chunkL[chunk] = (uint8_t)L;
 }
@@ -589,7 +605,7 @@ void build_pattern(mfem_b200_ctx *c) {
         DevBuf<int> overflow(1);
         MFEM_CUDA(cudaMemsetAsync(overflow, 0, sizeof(int), s));
         k_plan_segments<<<(unsigned)nChunks, kBlkChunk, 0, s>>>(c->nnzb, counts, c->planCnt, c->planSegOff, c->planNseg, c->planChunkL, c->planSegOrder,
-                                                               c->planWarpBase, overflow);
+                                                               c->planWarpBase, overflow, blockStart, pairsSorted, npe * npe);
         c->launches++;
         tmpBytes = 0;
         MFEM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, c->planWarpBase.p, c->planWarpBase.p, (int)(nWarpRounds + 1), s));

@@ -42,14 +42,18 @@ def local_problem(m, fixed, vals, f, world, rank, dof_for_node=None):
     return p, lfixed, lvals, lf
 
 
-def make_handle(dist, world, rank, local_rank, p, D, **options):
-    """Handle with communicator, local mesh, interface and material."""
+def make_handle(dist, world, rank, local_rank, p, D, comm_parent=None, **options):
+    """Handle with communicator, local mesh, interface and material.  comm_parent: a live handle of this
+    process whose NCCL communicator is reused (no second ncclCommInitRank)."""
     import torch
-    uid = Handle.comm_unique_id() if rank == 0 else None
-    dev = torch.device("cuda", local_rank) if dist.get_backend() == "nccl" else None
-    uid = broadcast_bytes(dist, uid, 128, dev)
     h = Handle(local_rank, **options)
-    h.comm_init(world, rank, uid)
+    if comm_parent is not None:
+        h.comm_share(comm_parent)
+    else:
+        uid = Handle.comm_unique_id() if rank == 0 else None
+        dev = torch.device("cuda", local_rank) if dist.get_backend() == "nccl" else None
+        uid = broadcast_bytes(dist, uid, 128, dev)
+        h.comm_init(world, rank, uid)
     h.set_mesh(p.N, p.deg, p.nodes, p.elem_nodes, dof_for_node=p.dof_for_node,
                n_dofs=p.num_dofs if p.dof_for_node is not None else None)
     h.set_interface(p.neighbor_ranks, p.neighbor_offsets, p.shared_local, p.owned)

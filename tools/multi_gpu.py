@@ -19,9 +19,9 @@ from meshfem_b200.distributed import broadcast_bytes, local_problem  # noqa: E40
 from meshfem_b200 import distributed as _dist_mod  # noqa: E402
 
 
-def make_handle(mfem, dist, world, rank, local_rank, p, D, **options):
+def make_handle(mfem, dist, world, rank, local_rank, p, D, comm_parent=None, **options):
     """Handle with communicator, local mesh, interface and material (meshfem_b200.distributed)."""
-    return _dist_mod.make_handle(dist, world, rank, local_rank, p, D, **options)
+    return _dist_mod.make_handle(dist, world, rank, local_rank, p, D, comm_parent=comm_parent, **options)
 
 
 def max_over_ranks(dist, value, device):
@@ -91,13 +91,13 @@ def run_multi_gpu(args, dist, world, rank, local_rank, name, grid, deg, mat, hbm
     nnzb_tot = sum_over_ranks(dist, nnzb, device)
     nb_tot = sum_over_ranks(dist, nb, device)
     launches_tot = sum_over_ranks(dist, launches, device)
-    h.close()
 
-    # end-to-end: fresh handle from host buffers on every rank
+    # end-to-end: fresh handle from host buffers on every rank.  The NCCL communicator is process-level
+    # state (like a torch process group): the e2e handles borrow the one created above.
     def e2e_step():
         dist.barrier()
         t = time.perf_counter()
-        hh = make_handle(meshfem_b200, dist, world, rank, local_rank, p, D)
+        hh = make_handle(meshfem_b200, dist, world, rank, local_rank, p, D, comm_parent=h)
         hh.assemble()
         hh.fix_variables(lfixed, lvals)
         u = hh.solve(f_p, rtol=RTOL)
@@ -110,6 +110,7 @@ def run_multi_gpu(args, dist, world, rank, local_rank, name, grid, deg, mat, hbm
     e2e_s, tip = e2e_step()
     e2e_max = max_over_ranks(dist, e2e_s, device)
     tip_min = -max_over_ranks(dist, -tip, device)
+    h.close()
     h2d = sum_over_ranks(dist, nodes_p.nbytes + elems_p.nbytes + f_p.nbytes + lfixed.nbytes + lvals.nbytes, device)
     d2h = sum_over_ranks(dist, f_p.nbytes, device)
 
