@@ -41,6 +41,8 @@ def load_library():
         lib.mfemhost_material.argtypes = [c_int, c_char_p, POINTER(c_double), ctypes.c_char_p, c_int]
         lib.mfemhost_eval_expr.argtypes = [c_char_p, c_double, c_double, c_double, POINTER(c_double)]
         lib.mfemhost_save_mesh.argtypes = [c_void_p, c_char_p]
+        lib.mfemhost_perforated_cell.argtypes = [c_int, c_int64, c_int64]
+        lib.mfemhost_perforated_cell.restype = c_void_p
         lib.mfemhost_msh_field.argtypes = [c_int, c_char_p, c_char_p, c_int, c_int, POINTER(c_double), c_int64,
                                            POINTER(c_int64), POINTER(c_int)]
         lib.mfemhost_tensor_analysis.argtypes = [c_int, POINTER(c_double)] + [POINTER(c_double)] * 5
@@ -182,6 +184,15 @@ def grid(sizes, min_corner=None, max_corner=None) -> RawMesh:
     if not p:
         raise _err(lib)
     return RawMesh(p, len(sizes))
+
+
+def perforated_cell(ndim, n, hole) -> RawMesh:
+    """BASELINE config-4 family: n^ndim voxels on the unit cell minus the centred hole^ndim block, tesselated."""
+    lib = load_library()
+    p = lib.mfemhost_perforated_cell(ndim, n, hole)
+    if not p:
+        raise _err(lib)
+    return RawMesh(p, ndim)
 
 
 def load_mesh(path) -> RawMesh:

@@ -79,6 +79,43 @@ void *mfemhost_grid(int ndim, const int64_t *sizes, const double *minCorner, con
     } catch (const std::exception &e) { g_err = e.what(); return nullptr; }
 }
 
+// Perforated periodic cell of BASELINE config 4: n^ndim voxels on [0,1]^ndim with the centred hole^ndim block
+// removed BEFORE the symmetric simplex subdivision; unused vertices are dropped.
+void *mfemhost_perforated_cell(int ndim, int64_t n, int64_t hole) {
+    try {
+        if (ndim != 2 && ndim != 3) throw std::runtime_error("perforated_cell: ndim must be 2 or 3");
+        if (n < 1 || hole < 0 || hole >= n || ((n - hole) % 2) != 0) throw std::runtime_error("perforated_cell: need 0 <= hole < n and n - hole even");
+        auto *hm = new HostMesh();
+        std::vector<size_t> sz((size_t)ndim, (size_t)n);
+        std::vector<MeshIO::IOVertex> gv;
+        std::vector<MeshIO::IOElement> ge, kept;
+        gen_grid(sz, gv, ge);
+        for (auto &v : gv) for (int i = 0; i < ndim; ++i) v.point[i] /= (Real)n;
+        const int64_t lo = (n - hole) / 2, hi = lo + hole;       // removed index range [lo, hi) per axis
+        // gen_grid element order: slices (z) outermost, then rows (y), then columns (x)
+        size_t e = 0;
+        for (int64_t s = 0; s < (ndim == 3 ? n : 1); ++s)
+            for (int64_t r = 0; r < n; ++r)
+                for (int64_t c = 0; c < n; ++c, ++e) {
+                    const bool inHole = c >= lo && c < hi && r >= lo && r < hi && (ndim == 2 || (s >= lo && s < hi));
+                    if (!inHole) kept.push_back(ge[e]);
+                }
+        std::vector<MeshIO::IOVertex> sv;
+        std::vector<MeshIO::IOElement> se;
+        std::vector<size_t> cellIdx;
+        if (ndim == 2) quad_tri_subdiv(gv, kept, sv, se, cellIdx);
+        else hex_tet_subdiv(gv, kept, sv, se, cellIdx);
+        std::vector<int64_t> remap(sv.size(), -1);
+        for (const auto &el : se) for (size_t c = 0; c < el.size(); ++c) remap[el[c]] = 0;
+        int64_t next = 0;
+        for (size_t v = 0; v < sv.size(); ++v) if (remap[v] == 0) { remap[v] = next++; hm->vertices.push_back(sv[v]); }
+        hm->elements = se;
+        for (auto &el : hm->elements) for (size_t c = 0; c < el.size(); ++c) el[c] = (size_t)remap[el[c]];
+        hm->dim = ndim;
+        return hm;
+    } catch (const std::exception &e) { g_err = e.what(); return nullptr; }
+}
+
 void *mfemhost_load_mesh(const char *path, int *dimOut) {
     try {
         auto *hm = new HostMesh();
