@@ -12,10 +12,14 @@
 //     K[r,c] = sum_e Ke[i,j] = C : ( sum_e vol_e sum_{a,b} W[i,a][j,b] G_a (x) G_b ) = C : M[r,c]
 // so a contribution costs one 3x3 accumulation of outer products (~36 FMA) and the 81-FMA
 // contraction with the elasticity tensor happens once per block (per contribution only with
-// per-element materials).  A CTA owns a chunk of 256 consecutive blocks; their lists are cut into
-// segments of <= 4 contributions handed to the threads in order of decreasing length (balanced
-// warps, coalesced interleaved id lists), the per-segment partial sums are combined per block in
-// shared memory in list order, and the chunk is written to HBM coalesced in the row-plane layout.
+// per-element materials).  A CTA owns a chunk of 256 consecutive blocks.  The 128-byte geometry records
+// of the chunk's distinct elements (a few dozen) are staged in shared memory by TMA bulk copies
+// (cp.async.bulk completing on an mbarrier) while the threads do their bookkeeping; the blocks'
+// contribution lists are cut into segments of <= 4 contributions handed to the threads in order of
+// decreasing length (balanced warps, coalesced interleaved id lists of chunk-local element ids), the
+// per-segment partial sums are combined per block in shared memory in list order, and every thread
+// writes its block to HBM once (the lanes of a warp hold consecutive blocks of a row, so the stores of a
+// plane fill its sectors together).
 //
 // Mode 2 "owner-gather" (first-generation kernel, kept for A/B).  Instead of
 // elements scattering 100 blocks each into shared rows (which needs atomics or colouring and
@@ -213,7 +217,9 @@ static PairTable make_pair_table() {
 }
 
 // B[c][d] (+)= sum_{r,t} D[flat(r,c)][flat(d,t)] M[r][t]
-template <int N, bool ACC>
+// ORTHO: D has the orthotropic sparsity pattern (normal-normal block + diagonal shear entries; covers
+// isotropic materials) -- the other 2/3 of the 81 products are structurally zero and are skipped.
+template <int N, bool ACC, bool ORTHO = false>
 __device__ __forceinline__ void contract_CM(const double *D, const double (&M)[N][N], double (&B)[N][N]) {
     constexpr int F = flat_len(N);
 #pragma unroll
@@ -224,13 +230,17 @@ __device__ __forceinline__ void contract_CM(const double *D, const double (&M)[N
 #pragma unroll
             for (int r = 0; r < N; ++r)
 #pragma unroll
-                for (int t = 0; t < N; ++t) s = fma(D[flat_idx<N>(r, c) * F + flat_idx<N>(d, t)], M[r][t], s);
+                for (int t = 0; t < N; ++t) {
+                    const int a = flat_idx<N>(r, c), b = flat_idx<N>(d, t);
+                    if (ORTHO && !((a < N && b < N) || a == b)) continue;
+                    s = fma(D[a * F + b], M[r][t], s);
+                }
             B[c][d] = s;
         }
 }
 
 // Packed element geometry for the block-owner kernel: 4 slots of 32 bytes per element, slot a =
-// (G[0][a], G[1][a], G[2][a] (0 in 2D), vol) -- one 256-bit load fetches a gradient and the volume.
+// (G[0][a], G[1][a], G[2][a] (0 in 2D), vol) -- one 128-byte record per element, the unit of the TMA staging.
 template <int N>
 __global__ void k_pack_geom(int64_t nElems, const double *__restrict__ geom, double *__restrict__ geomP) {
     const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -245,13 +255,6 @@ __global__ void k_pack_geom(int64_t nElems, const double *__restrict__ geom, dou
     for (int q = 0; q < 4; ++q) geomP[t * 4 + q] = o[q];
 }
 
-struct GeomSlot { double g[3], vol; };
-__device__ __forceinline__ GeomSlot ld_geom_slot(const double *p) {
-    GeomSlot s;
-    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(s.g[0]), "=d"(s.g[1]), "=d"(s.g[2]), "=d"(s.vol) : "l"(p));
-    return s;
-}
-
 __device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t *p) {
     uint32_t v;
     asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
@@ -260,8 +263,24 @@ __device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t *p) {
 
 // Accumulate the contributions of one segment (pair ids read interleaved from `lp`, nIt trips of
 // the warp) into acc: M in geometry space, or -- with per-element materials -- the block itself.
-template <int N, int DEG, bool PER_ELEM_D, int PP>
+struct GeomSlot { double g[3], vol; };
+__device__ __forceinline__ GeomSlot ld_geom_slot(const double *p) {
+    GeomSlot s;
+    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(s.g[0]), "=d"(s.g[1]), "=d"(s.g[2]), "=d"(s.vol) : "l"(p));
+    return s;
+}
+__device__ __forceinline__ GeomSlot lds_geom_slot(const double *p) {      // 32-byte aligned shared-memory slot
+    GeomSlot s;
+    const double2 a = *reinterpret_cast<const double2 *>(p), b = *reinterpret_cast<const double2 *>(p + 2);
+    s.g[0] = a.x; s.g[1] = a.y; s.g[2] = b.x; s.vol = b.y;
+    return s;
+}
+
+// STAGED: the entries carry chunk-local element ids and the records are read from the shared-memory copy
+// the TMA made (sGeom); otherwise global element ids and 256-bit gathers from HBM/L2.
+template <int N, int DEG, bool PER_ELEM_D, int PP, bool STAGED>
 __device__ __forceinline__ void accumulate_segment(const uint32_t *lp, int nIt, const double *__restrict__ geomP,
+                                                   const double *sGeom, const uint32_t *sElems,
                                                    const double *__restrict__ Delem, const double (*sW)[PP],
                                                    const uint32_t *sIdx, double (&acc)[N][N]) {
     constexpr int F = flat_len(N);
@@ -273,9 +292,9 @@ __device__ __forceinline__ void accumulate_segment(const uint32_t *lp, int nIt, 
         const uint32_t e = v / (uint32_t)PP;
         const int ij = (int)(v - e * (uint32_t)PP);
         const uint32_t idx = sIdx[ij];
-        const double *g = geomP + (int64_t)e * 16;
-        const GeomSlot A0 = ld_geom_slot(g + 4 * (idx & 0xffu));
-        const GeomSlot B0 = ld_geom_slot(g + 4 * ((idx >> 16) & 0xffu));
+        const double *g = STAGED ? sGeom + e * 16 : geomP + (int64_t)e * 16;
+        const GeomSlot A0 = STAGED ? lds_geom_slot(g + 4 * (idx & 0xffu)) : ld_geom_slot(g + 4 * (idx & 0xffu));
+        const GeomSlot B0 = STAGED ? lds_geom_slot(g + 4 * ((idx >> 16) & 0xffu)) : ld_geom_slot(g + 4 * ((idx >> 16) & 0xffu));
         const double vol = A0.vol;
         double u0[N];
         double Mc[N][N];
@@ -289,8 +308,8 @@ __device__ __forceinline__ void accumulate_segment(const uint32_t *lp, int nIt, 
                     if (PER_ELEM_D) Mc[r][q] = u0[r] * B0.g[q]; else acc[r][q] = fma(u0[r], B0.g[q], acc[r][q]);
                 }
         } else {
-            const GeomSlot A1 = ld_geom_slot(g + 4 * ((idx >> 8) & 0xffu));
-            const GeomSlot B1 = ld_geom_slot(g + 4 * (idx >> 24));
+            const GeomSlot A1 = STAGED ? lds_geom_slot(g + 4 * ((idx >> 8) & 0xffu)) : ld_geom_slot(g + 4 * ((idx >> 8) & 0xffu));
+            const GeomSlot B1 = STAGED ? lds_geom_slot(g + 4 * (idx >> 24)) : ld_geom_slot(g + 4 * (idx >> 24));
             double u1[N];
             const double w00 = vol * sW[0][ij], w01 = vol * sW[1][ij], w10 = vol * sW[2][ij], w11 = vol * sW[3][ij];
 #pragma unroll
@@ -308,7 +327,7 @@ __device__ __forceinline__ void accumulate_segment(const uint32_t *lp, int nIt, 
         }
         if (PER_ELEM_D) {
             double De[F * F];
-            const double *dp = Delem + (int64_t)e * (F * F);
+            const double *dp = Delem + (int64_t)(STAGED ? sElems[e] : e) * (F * F);     // per-element D by GLOBAL element id
 #pragma unroll
             for (int q = 0; q < F * F; ++q) De[q] = __ldg(dp + q);
             contract_CM<N, true>(De, Mc, acc);
@@ -316,72 +335,119 @@ __device__ __forceinline__ void accumulate_segment(const uint32_t *lp, int nIt, 
     }
 }
 
-template <int N, int DEG, bool PER_ELEM_D>
+// ---- TMA staging helpers (1-D bulk copies completing on an mbarrier) ----
+__device__ __forceinline__ uint32_t asm_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void asm_mbar_init(unsigned long long *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(asm_smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void asm_mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(asm_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void asm_mbar_wait(unsigned long long *bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(asm_smem_u32(bar)), "r"(parity)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void asm_tma_g2s(void *dst, const void *src, uint32_t bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(asm_smem_u32(dst)), "l"(src), "r"(bytes), "r"(asm_smem_u32(bar))
+                 : "memory");
+}
+
+template <int N, int DEG, bool PER_ELEM_D, bool ORTHO>
 __global__ void __launch_bounds__(kBlkChunk, PER_ELEM_D ? 2 : 4)
 k_assemble_blocks(int64_t nnzb, const int32_t *__restrict__ chunkRow, const int64_t *__restrict__ rowptr,
                   const uint16_t *__restrict__ planSegOff, const uint8_t *__restrict__ planNseg,
                   const uint16_t *__restrict__ segOrder, const int64_t *__restrict__ warpBase,
                   const uint32_t *__restrict__ list, const double *__restrict__ geomP, const MatD Dc,
                   const double *__restrict__ Delem, const double *__restrict__ pairW,
-                  const uint32_t *__restrict__ pairIdx, double *__restrict__ vals) {
+                  const uint32_t *__restrict__ pairIdx, const int64_t *__restrict__ elemPtr,
+                  const uint32_t *__restrict__ elems, double *__restrict__ vals) {
     constexpr int NPE = nodes_per_elem(N, DEG);
     constexpr int PP = NPE * NPE;
     constexpr int NN = N * N;
-    __shared__ long long sRowPtr[kBlkChunk + 2];
+    __shared__ __align__(128) double sGeom[kGeomCap * 16];   // TMA destination: the chunk's element records (G_a, vol) x 4
+    __shared__ uint32_t sElems[kGeomCap];         // their global element ids
+    __shared__ unsigned long long sBar;           // mbarrier the bulk copies complete on
     __shared__ double sW[4][PP];
     __shared__ uint32_t sIdx[PP];
-    __shared__ double sPart[kSegSlots * NN];      // per-segment partial sums; later the chunk's output staging
-    __shared__ long long sBase[kBlkChunk];
-    __shared__ int sStride[kBlkChunk];
+    __shared__ double sPart[kSegSlots * NN];      // per-segment partial sums
+    __shared__ long long sRowPtr[kBlkChunk + 2];  // the chunk's slice of rowptr
     const int t = threadIdx.x, lane = t & 31;
     const int64_t chunk = blockIdx.x;
     const int64_t k = chunk * kBlkChunk + t;
+    // ---- set-up, one barrier: pair table, mbarrier, rowptr slice (one global round trip for all of it)
     for (int q = t; q < PP; q += kBlkChunk) {
         sIdx[q] = pairIdx[q];
 #pragma unroll
         for (int w = 0; w < 4; ++w) sW[w][q] = pairW[w * PP + q];
     }
-    // natural-order bookkeeping: segments of block (chunk, t), and where the block lives in HBM.
-    // The chunk's slice of rowptr is staged in shared memory so the row search costs one global
-    // round trip instead of one per bisection step.
+    const int64_t ePtr = elemPtr[chunk];
+    const int nLocal = (int)(elemPtr[chunk + 1] - ePtr);          // 0: unstaged chunk (global-load path)
+    if (t == 0) asm_mbar_init(&sBar, 1);
     int mySegs = 0, mySegOff = 0;
     if (k < nnzb) { mySegs = planNseg[k]; mySegOff = planSegOff[k]; }
     const int64_t rLo = chunkRow[chunk], rHi = chunkRow[chunk + 1];
+    const bool rowsStaged = rHi - rLo + 1 <= kBlkChunk;
     const int nRowPtr = (int)min((int64_t)kBlkChunk, rHi - rLo + 1) + 1;      // rowptr[rLo .. rLo+nRowPtr-1]
     if (t < nRowPtr) sRowPtr[t] = rowptr[rLo + t];
+    uint32_t myElem = 0;
+    if (t < nLocal) myElem = elems[ePtr + t];
     __syncthreads();
+    // TMA staging of the element geometry: one 128-byte bulk copy per distinct element of the chunk, issued
+    // by the first nLocal threads, all completing on one mbarrier (waited on right before phase 1)
+    if (nLocal > 0) {
+        if (t == 0) asm_mbar_expect_tx(&sBar, (uint32_t)nLocal * 128u);
+        if (t < nLocal) {
+            sElems[t] = myElem;
+            asm_tma_g2s(sGeom + t * 16, geomP + (int64_t)myElem * 16, 128u, &sBar);
+        }
+    }
+    // where block (chunk, t) lives in the row-plane layout (kept in registers for the write-out)
+    double *myDst = nullptr;
+    int64_t myStride = 0;
     if (k < nnzb) {
-        int64_t lo = rLo, hi = rHi;
-        if (rHi - rLo + 1 <= kBlkChunk) {
+        int64_t b0, n;
+        if (rowsStaged) {
             int l = 0, h = (int)(rHi - rLo);
             while (l < h) {                      // last row with rowptr[row] <= k
                 const int mid = (l + h + 1) >> 1;
                 if (sRowPtr[mid] <= k) l = mid; else h = mid - 1;
             }
-            lo = rLo + l;
-            const int64_t b0 = sRowPtr[l], n = sRowPtr[l + 1] - b0;
-            sBase[t] = (long long)(NN * b0 + N * (k - b0));
-            sStride[t] = (int)(N * n);
+            b0 = sRowPtr[l]; n = sRowPtr[l + 1] - b0;
         } else {                                 // more than 256 (empty) rows inside one chunk: search in HBM
+            int64_t lo = rLo, hi = rHi;
             while (lo < hi) {
                 const int64_t mid = (lo + hi + 1) >> 1;
                 if (rowptr[mid] <= k) lo = mid; else hi = mid - 1;
             }
-            const int64_t b0 = rowptr[lo], n = rowptr[lo + 1] - b0;
-            sBase[t] = (long long)(NN * b0 + N * (k - b0));
-            sStride[t] = (int)(N * n);
+            b0 = rowptr[lo]; n = rowptr[lo + 1] - b0;
         }
+        myDst = vals + NN * b0 + N * (k - b0);
+        myStride = N * n;
     }
-    __syncthreads();
 
-    // phase 1: one segment per thread slot, two rounds
+    // phase 1: one segment per thread slot.  kSegSlots/32 warp-rounds sorted by decreasing trip count:
+    // round 0 gives warp w the w-th longest; the remaining (shorter) ones go, longest first, to the warps
+    // that had the least to do in round 0, so the warps of the CTA reach the barrier together.
+    constexpr int nW = kBlkChunk / 32, nWR = kSegSlots / 32;
+    static_assert(nWR >= nW && nWR <= 2 * nW, "one full and at most one more round");
+    if (nLocal > 0) asm_mbar_wait(&sBar, 0);      // geometry records have landed
 #pragma unroll 1
-    for (int round = 0; round < kSegSlots / kBlkChunk; ++round) {
-        // warp-rounds are sorted by decreasing trip count: warp w takes the w-th longest in round 0 and
-        // the w-th shortest in round 1, so the warps of the CTA reach the barrier together
-        const int wrLocal = round == 0 ? (t >> 5) : (kSegSlots / 32 - 1 - (t >> 5));
+    for (int round = 0; round < 2; ++round) {
+        const int w = t >> 5;
+        if (round == 1 && w < 2 * nW - nWR) break;              // warp-uniform: no second item for this warp
+        const int wrLocal = round == 0 ? w : nW + (nW - 1 - w);
         const int slot = wrLocal * 32 + lane;
-        const int64_t wr = chunk * (kSegSlots / 32) + wrLocal;
+        const int64_t wr = chunk * nWR + wrLocal;
         const int64_t base = warpBase[wr];
         const int nIt = (int)((warpBase[wr + 1] - base) >> 5);
         if (nIt == 0) continue;                  // warp-uniform
@@ -391,7 +457,10 @@ k_assemble_blocks(int64_t nnzb, const int32_t *__restrict__ chunkRow, const int6
         for (int r = 0; r < N; ++r)
 #pragma unroll
             for (int q = 0; q < N; ++q) acc[r][q] = 0.0;
-        accumulate_segment<N, DEG, PER_ELEM_D, PP>(list + base + lane, nIt, geomP, Delem, sW, sIdx, acc);
+        if (nLocal > 0)
+            accumulate_segment<N, DEG, PER_ELEM_D, PP, true>(list + base + lane, nIt, geomP, sGeom, sElems, Delem, sW, sIdx, acc);
+        else
+            accumulate_segment<N, DEG, PER_ELEM_D, PP, false>(list + base + lane, nIt, geomP, sGeom, sElems, Delem, sW, sIdx, acc);
         if (sg != 0xffff) {
 #pragma unroll
             for (int r = 0; r < N; ++r)
@@ -420,29 +489,17 @@ k_assemble_blocks(int64_t nnzb, const int32_t *__restrict__ chunkRow, const int6
 #pragma unroll
                 for (int q = 0; q < N; ++q) out[r][q] = M[r][q];
         } else {
-            contract_CM<N, false>(Dc.d, M, out);
+            contract_CM<N, false, ORTHO>(Dc.d, M, out);
         }
     }
-    __syncthreads();                             // all partials consumed: reuse sPart as output staging
-    double *sOut = sPart;
+    // write-out straight from registers: a block is N runs of N doubles (one per plane); the lanes of a warp
+    // hold consecutive blocks of a row, so the N stores of a plane fill its sectors together and every
+    // block of K is written exactly once
+    if (myDst) {
 #pragma unroll
-    for (int r = 0; r < N; ++r)
+        for (int r = 0; r < N; ++r)
 #pragma unroll
-        for (int q = 0; q < N; ++q) sOut[(r * kBlkChunk + t) * N + q] = out[r][q];
-    __syncthreads();
-    // phase 3: coalesced write-out.  Plane r of the chunk is N*kBlkChunk scalars = N passes of the CTA;
-    // in pass m thread t owns scalar rem = t + m*kBlkChunk of every plane: consecutive threads ->
-    // consecutive addresses inside a block row.
-#pragma unroll
-    for (int m = 0; m < N; ++m) {
-        const int rem = t + m * kBlkChunk;
-        const int kb = rem / N, q = rem - kb * N;
-        if (chunk * kBlkChunk + kb < nnzb) {
-            double *dst = vals + sBase[kb] + q;
-            const int stride = sStride[kb];
-#pragma unroll
-            for (int r = 0; r < N; ++r) dst[(long long)r * stride] = sOut[r * (N * kBlkChunk) + rem];
-        }
+            for (int q = 0; q < N; ++q) myDst[r * myStride + q] = out[r][q];
     }
 }
 
@@ -467,17 +524,25 @@ static void launch_assemble_blocks(mfem_b200_ctx *c) {
         c->geomPValid = true;
     }
     const int64_t nChunks = (c->nnzb + kBlkChunk - 1) / kBlkChunk;
-    // static shared memory ~45 KB per CTA: ask for the largest carve-out so 4-5 CTAs fit an SM
-    MFEM_CUDA(cudaFuncSetAttribute(k_assemble_blocks<N, DEG, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    MFEM_CUDA(cudaFuncSetAttribute(k_assemble_blocks<N, DEG, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    if (c->perElemD)
-        k_assemble_blocks<N, DEG, true><<<(unsigned)nChunks, kBlkChunk, 0, s>>>(
-            c->nnzb, c->planChunkRow, c->rowptr, c->planSegOff, c->planNseg, c->planSegOrder, c->planWarpBase, c->planList,
-            c->geomP, c->Dconst, c->Delem, c->pairW, c->pairIdx, c->vals);
-    else
-        k_assemble_blocks<N, DEG, false><<<(unsigned)nChunks, kBlkChunk, 0, s>>>(
-            c->nnzb, c->planChunkRow, c->rowptr, c->planSegOff, c->planNseg, c->planSegOrder, c->planWarpBase, c->planList,
-            c->geomP, c->Dconst, nullptr, c->pairW, c->pairIdx, c->vals);
+    // orthotropic sparsity pattern of the constant tensor (isotropic included)?
+    constexpr int F = flat_len(N);
+    bool ortho = !c->perElemD;
+    for (int a = 0; a < F && ortho; ++a)
+        for (int b = 0; b < F; ++b)
+            if (!((a < N && b < N) || a == b) && c->Dconst.d[a * F + b] != 0.0) { ortho = false; break; }
+#define MFEM_BLK_LAUNCH(PE_, OR_, DELEM_)                                                                              \
+    do {                                                                                                              \
+        auto kern = k_assemble_blocks<N, DEG, PE_, OR_>;                                                              \
+        /* static shared memory ~45 KB per CTA: ask for the largest carve-out so 4 CTAs fit an SM */                  \
+        MFEM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));                   \
+        kern<<<(unsigned)nChunks, kBlkChunk, 0, s>>>(c->nnzb, c->planChunkRow, c->rowptr, c->planSegOff, c->planNseg,  \
+                                                     c->planSegOrder, c->planWarpBase, c->planList, c->geomP, c->Dconst, \
+                                                     DELEM_, c->pairW, c->pairIdx, c->planElemPtr, c->planElems, c->vals); \
+    } while (0)
+    if (c->perElemD) MFEM_BLK_LAUNCH(true, false, c->Delem.p);
+    else if (ortho) MFEM_BLK_LAUNCH(false, true, nullptr);
+    else MFEM_BLK_LAUNCH(false, false, nullptr);
+#undef MFEM_BLK_LAUNCH
     c->launches++;
     MFEM_CUDA(cudaGetLastError());
 }

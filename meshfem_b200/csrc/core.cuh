@@ -137,6 +137,8 @@ struct mfem_b200_ctx {
     mfem::DevBuf<int64_t> planWarpBase;    // [nChunks*kSegSlots/32+1] first list entry of each warp-round
     mfem::DevBuf<uint32_t> planList;       // [planEntries] interleaved pair ids e*npe^2 + i*npe + j, kPlanSentinel = none
     mfem::DevBuf<int32_t> planChunkRow;    // [nChunks+1] block row containing the chunk's first block
+    mfem::DevBuf<int64_t> planElemPtr;     // [nChunks+1] elements staged per chunk (prefix); empty range = unstaged chunk
+    mfem::DevBuf<uint32_t> planElems;      // distinct elements of every staged chunk, in chunk-local order
     int64_t planEntries = 0;
     mfem::DevBuf<double> pairW;            // [4][npe*npe] W weights of the (i,j) pair table (assemble.cu)
     mfem::DevBuf<uint32_t> pairIdx;        // [npe*npe]    packed gradient offsets
@@ -208,7 +210,8 @@ __host__ __device__ __forceinline__ int64_t val_index(int64_t b0, int64_t n, int
 constexpr int kSpmvTileWindow = 512;  // blocks per tile window of the TMA-ring SpMV (solver.cu kTmaWindow)
 constexpr int kAsmChunk = 32;       // element incidences per warp job of the owner-gather assembly
 constexpr int kBlkChunk = 256;      // BSR blocks per CTA of the block-owner assembly (one thread per block)
-constexpr int kSegSlots = 512;      // thread slots (segments) per chunk: two rounds of kBlkChunk threads
+constexpr int kSegSlots = 384;      // thread slots (segments) per chunk: one full round of kBlkChunk threads + a partial one
+constexpr int kGeomCap = 96;        // element geometry records staged in shared memory per chunk (TMA)
 constexpr uint32_t kPlanSentinel = 0xffffffffu;
 
 inline int grid_for(int64_t n, int block) { return static_cast<int>((n + block - 1) / block); }

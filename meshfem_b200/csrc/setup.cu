@@ -246,13 +246,18 @@ k_plan_segments(int64_t nnzb, const int32_t *__restrict__ counts, uint16_t *__re
     // contribution: segments that read the same element records end up in the same warp, so a geometry
     // gather touches few distinct cache lines.
     uint32_t key[2];
+    static_assert(kSegSlots <= 2 * kBlkChunk, "two sort items per thread");
     for (int i = 0; i < 2; ++i) {
         const int sgi = 2 * t + i;
-        key[i] = sLen[sgi] ? (((uint32_t)min((int)sLen[sgi], 255) << 24) | (sElem[sgi] & 0xffffffu)) : 0u;
+        key[i] = (sgi < kSegSlots && sLen[sgi]) ? (((uint32_t)min((int)sLen[sgi], 255) << 24) | (sElem[sgi] & 0xffffffu)) : 0u;
     }
     uint32_t val[2] = {(uint32_t)(2 * t), (uint32_t)(2 * t + 1)};
     Sort(temp.sort).SortDescending(key, val);        // stable; blocked: thread t holds ranks 2t, 2t+1
-    for (int i = 0; i < 2; ++i) { sLenSorted[2 * t + i] = sLen[val[i]]; sIdxSorted[2 * t + i] = (uint16_t)val[i]; }
+    for (int i = 0; i < 2; ++i)
+        if (2 * t + i < kSegSlots) {          // ranks beyond kSegSlots hold only empty items
+            sLenSorted[2 * t + i] = key[i] ? sLen[val[i]] : (uint16_t)0;
+            sIdxSorted[2 * t + i] = (uint16_t)val[i];
+        }
     __syncthreads();
     for (int j = t; j < kSegSlots; j += kBlkChunk)
         segOrder[chunk * kSegSlots + j] = sLenSorted[j] ? sIdxSorted[j] : (uint16_t)0xffff;
@@ -265,15 +270,91 @@ k_plan_segments(int64_t nnzb, const int32_t *__restrict__ counts, uint16_t *__re
     if (t == 0) chunkL[chunk] = (uint8_t)L;
 }
 
+// ---- distinct elements of a chunk (TMA staging of the geometry records, assemble.cu) ----------
+// The contributions of a chunk are one contiguous range of the sorted pair list.  Their elements
+// (a few dozen: the tets around ~9 DoF rows) go into a shared-memory hash set; slot order gives the
+// chunk-local element numbering.  Chunks with more than kGeomCap distinct elements are left unstaged.
+constexpr int kElemHash = 1024;                  // hash slots (power of two), load factor <= 1/2 enforced
+constexpr uint32_t kHashEmpty = 0xffffffffu;
+
+__device__ __forceinline__ int elem_hash_slot(uint32_t e) { return (int)((e * 2654435761u) >> 22); }
+
+// inserts the elements of pairs [a, b) -- returns false (for every thread) if the table overflowed
+__device__ __forceinline__ bool chunk_hash_build(uint32_t *sKeys, int *sFlag, int64_t a, int64_t b,
+                                                 const uint32_t *__restrict__ sortedPairs, uint32_t pairsPerElem) {
+    for (int j = threadIdx.x; j < kElemHash; j += blockDim.x) sKeys[j] = kHashEmpty;
+    if (threadIdx.x == 0) *sFlag = 0;
+    __syncthreads();
+    for (int64_t i = a + threadIdx.x; i < b; i += blockDim.x) {
+        const uint32_t e = sortedPairs[i] / pairsPerElem;
+        int slot = elem_hash_slot(e);
+        for (int probe = 0; probe < kElemHash; ++probe) {
+            const uint32_t old = atomicCAS(&sKeys[slot], kHashEmpty, e);
+            if (old == kHashEmpty || old == e) break;
+            slot = (slot + 1) & (kElemHash - 1);
+            if (probe > kElemHash / 2) { *sFlag = 1; break; }
+        }
+    }
+    __syncthreads();
+    return *sFlag == 0;
+}
+
+__device__ __forceinline__ int chunk_hash_find(const uint32_t *sKeys, uint32_t e) {
+    int slot = elem_hash_slot(e);
+    while (sKeys[slot] != e) slot = (slot + 1) & (kElemHash - 1);
+    return slot;
+}
+
+// number of elements to stage per chunk (0 = chunk stays on the global-load path)
+__global__ void __launch_bounds__(kBlkChunk)
+k_plan_count_elems(int64_t nnzb, int64_t nPairs, const int32_t *__restrict__ blockStart,
+                   const uint32_t *__restrict__ sortedPairs, int pairsPerElem, int64_t *__restrict__ chunkNElems) {
+    typedef cub::BlockReduce<int, kBlkChunk> Reduce;
+    __shared__ typename Reduce::TempStorage temp;
+    __shared__ uint32_t sKeys[kElemHash];
+    __shared__ int sFlag;
+    const int64_t k0 = (int64_t)blockIdx.x * kBlkChunk;
+    const int64_t a = blockStart[k0], b = (k0 + kBlkChunk < nnzb) ? blockStart[k0 + kBlkChunk] : nPairs;
+    const bool ok = chunk_hash_build(sKeys, &sFlag, a, b, sortedPairs, (uint32_t)pairsPerElem);
+    int mine = 0;
+    for (int j = threadIdx.x; j < kElemHash; j += blockDim.x) mine += sKeys[j] != kHashEmpty;
+    const int total = Reduce(temp).Sum(mine);
+    if (threadIdx.x == 0) chunkNElems[blockIdx.x] = (ok && total <= kGeomCap) ? total : 0;
+}
+
 __global__ void __launch_bounds__(kBlkChunk)
 k_plan_fill(int64_t nnzb, const uint16_t *__restrict__ planCnt, const uint8_t *__restrict__ chunkL,
             const int32_t *__restrict__ blockStart, const uint32_t *__restrict__ sortedPairs,
-            const uint16_t *__restrict__ segOrder, const int64_t *__restrict__ warpBase, uint32_t *__restrict__ list) {
+            const uint16_t *__restrict__ segOrder, const int64_t *__restrict__ warpBase, uint32_t *__restrict__ list,
+            int64_t nPairs, int pairsPerElem, const int64_t *__restrict__ chunkElemPtr, uint32_t *__restrict__ chunkElems) {
     typedef cub::BlockScan<int, kBlkChunk> Scan;
     __shared__ typename Scan::TempStorage temp;
     __shared__ int sOff[kBlkChunk + 1], sCnt[kBlkChunk];
+    __shared__ uint32_t sKeys[kElemHash];
+    __shared__ uint16_t sLocal[kElemHash];
+    __shared__ int sFlag;
     const int t = threadIdx.x;
     const int64_t chunk = blockIdx.x, k = chunk * kBlkChunk + t;
+    // staged chunk: chunk-local element numbering = order of the occupied hash slots
+    const int64_t ePtr = chunkElemPtr[chunk];
+    const bool staged = chunkElemPtr[chunk + 1] > ePtr;
+    if (staged) {
+        const int64_t k0 = chunk * kBlkChunk;
+        const int64_t a = blockStart[k0], b = (k0 + kBlkChunk < nnzb) ? blockStart[k0 + kBlkChunk] : nPairs;
+        chunk_hash_build(sKeys, &sFlag, a, b, sortedPairs, (uint32_t)pairsPerElem);
+        constexpr int PER = kElemHash / kBlkChunk;
+        int occ = 0;
+        for (int q = 0; q < PER; ++q) occ += sKeys[PER * t + q] != kHashEmpty;
+        int first;
+        Scan(temp).ExclusiveSum(occ, first);
+        for (int q = 0; q < PER; ++q)
+            if (sKeys[PER * t + q] != kHashEmpty) {
+                sLocal[PER * t + q] = (uint16_t)first;
+                chunkElems[ePtr + first] = sKeys[PER * t + q];
+                ++first;
+            }
+        __syncthreads();
+    }
     const int cnt = k < nnzb ? planCnt[k] : 0;
     const int L = chunkL[chunk];
     int off, total;
@@ -298,7 +379,17 @@ k_plan_fill(int64_t nnzb, const uint16_t *__restrict__ planCnt, const uint8_t *_
             len = min(L, sCnt[lo] - part * L);
             start = (int64_t)blockStart[chunk * kBlkChunk + lo] + (int64_t)part * L;
         }
-        for (int it = 0; it < nIt; ++it) list[base + 32 * (int64_t)it + (j & 31)] = it < len ? sortedPairs[start + it] : kPlanSentinel;
+        for (int it = 0; it < nIt; ++it) {
+            uint32_t v = kPlanSentinel;
+            if (it < len) {
+                v = sortedPairs[start + it];
+                if (staged) {       // (element, i, j) -> (chunk-local element, i, j)
+                    const uint32_t e = v / (uint32_t)pairsPerElem;
+                    v = (uint32_t)sLocal[chunk_hash_find(sKeys, e)] * (uint32_t)pairsPerElem + (v - e * (uint32_t)pairsPerElem);
+                }
+            }
+            list[base + 32 * (int64_t)it + (j & 31)] = v;
+        }
     }
 }
 
@@ -623,8 +714,25 @@ void build_pattern(mfem_b200_ctx *c) {
         c->planEntries = planEntries;
         c->timers["Plan Padding Ratio"] = (double)planEntries / (double)nPairs;   // diagnostic, not a time
         c->planList.alloc((size_t)planEntries + 32);
+        // elements to stage per chunk (TMA) and their list
+        c->planElemPtr.alloc((size_t)nChunks + 1);
+        MFEM_CUDA(cudaMemsetAsync(c->planElemPtr, 0, c->planElemPtr.bytes(), s));
+        k_plan_count_elems<<<(unsigned)nChunks, kBlkChunk, 0, s>>>(c->nnzb, nPairs, blockStart, pairsSorted, npe * npe, c->planElemPtr);
+        tmpBytes = 0;
+        MFEM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, c->planElemPtr.p, c->planElemPtr.p, (int)(nChunks + 1), s));
+        int64_t nStaged = 0;
+        {
+            DevBuf<uint8_t> tmp(tmpBytes);
+            MFEM_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmpBytes, c->planElemPtr.p, c->planElemPtr.p, (int)(nChunks + 1), s));
+            MFEM_CUDA(cudaMemcpyAsync(&nStaged, c->planElemPtr.p + nChunks, 8, cudaMemcpyDeviceToHost, s));
+            MFEM_CUDA(cudaStreamSynchronize(s));
+        }
+        c->planElems.alloc((size_t)nStaged + 4);
+        c->timers["Plan Staged Elements Per Chunk"] = (double)nStaged / (double)nChunks;   // diagnostic, not a time
         k_plan_fill<<<(unsigned)nChunks, kBlkChunk, 0, s>>>(c->nnzb, c->planCnt, c->planChunkL, blockStart, pairsSorted,
-                                                           c->planSegOrder, c->planWarpBase, c->planList);
+                                                           c->planSegOrder, c->planWarpBase, c->planList, nPairs, npe * npe,
+                                                           c->planElemPtr, c->planElems);
+        c->launches++;
         c->planChunkRow.alloc((size_t)nChunks + 1);
         k_chunk_rows<<<grid_for(nChunks + 1, 256), 256, 0, s>>>(nChunks, nb, c->nnzb, c->rowptr, c->planChunkRow);
         c->launches += 2;
