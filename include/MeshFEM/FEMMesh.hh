@@ -142,6 +142,25 @@ public:
         const Real e1x = p[0][0] - p[2][0], e1y = p[0][1] - p[2][1], e2x = p[1][0] - p[0][0], e2y = p[1][1] - p[0][1];
         return (e1x * e2y - e1y * e2x) / 2.0;
     }
+    // gradients of the barycentric coordinates of element e: g[a][r] = d lambda_a / d x_r
+    // (LinearlyEmbeddedSimplex::embed, EmbeddedElement.hh:170-190, 211-231)
+    void elementGradLambda(size_t e, Real g[_K + 1][_K]) const {
+        Point p[_K + 1];
+        for (size_t c = 0; c <= _K; ++c) p[c] = nodePosition(elementVertex(e, c));
+        if (_K == 3) {
+            auto v3 = [&](size_t i) { return Vector3D{p[i][0], p[i][1], p[i][2]}; };
+            const Vector3D n0 = cross(v3(3) - v3(1), v3(2) - v3(1)), n1 = cross(v3(2) - v3(0), v3(3) - v3(0)),
+                           n2 = cross(v3(3) - v3(0), v3(1) - v3(0)), n3 = cross(v3(1) - v3(0), v3(2) - v3(0));
+            const Real V6 = (v3(0) - v3(1)).dot(n0);
+            const Vector3D *n[4] = {&n0, &n1, &n2, &n3};
+            for (size_t a = 0; a < 4; ++a) for (size_t r = 0; r < 3; ++r) g[a][r] = (*n[a])[r] / V6;
+        } else {
+            const Real ex[3] = {p[2][0] - p[1][0], p[0][0] - p[2][0], p[1][0] - p[0][0]};
+            const Real ey[3] = {p[2][1] - p[1][1], p[0][1] - p[2][1], p[1][1] - p[0][1]};
+            const Real dblA = ex[1] * ey[2] - ey[1] * ex[2];
+            for (size_t a = 0; a < 3; ++a) { g[a][0] = -ey[a] / dblA; g[a][1] = ex[a] / dblA; }
+        }
+    }
     Real volume() const {
         Real v = 0;
         for (size_t e = 0; e < m_ne; ++e) v += elementVolume(e);

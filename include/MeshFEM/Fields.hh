@@ -83,4 +83,23 @@ public:
 private:
     std::vector<_Real> m_v;
 };
+// Per-element field of symmetric-matrix interpolants: nodesPerElem nodal values per element, the form in
+// which the reference writes full-degree strain/stress ($ElementNodeData, MSHFieldWriter.hh:262-306).
+template <typename _Real, size_t _N>
+class SymmetricMatrixInterpolantField {
+public:
+    static constexpr size_t F = flatLen(_N);
+    SymmetricMatrixInterpolantField() {}
+    SymmetricMatrixInterpolantField(size_t numElements, size_t nodesPerElem) : m_npe(nodesPerElem), m_v(numElements * nodesPerElem * F, 0) {}
+    size_t domainSize() const { return m_npe ? m_v.size() / (m_npe * F) : 0; }
+    size_t nodesPerElement() const { return m_npe; }
+    size_t N() const { return _N; }
+    _Real &operator()(size_t e, size_t n, size_t k) { return m_v[(e * m_npe + n) * F + k]; }
+    _Real operator()(size_t e, size_t n, size_t k) const { return m_v[(e * m_npe + n) * F + k]; }
+    const std::vector<_Real> &data() const { return m_v; }
+
+private:
+    size_t m_npe = 0;
+    std::vector<_Real> m_v;
+};
 #endif

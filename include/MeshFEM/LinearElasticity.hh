@@ -169,6 +169,15 @@ public:
         mfemCheck(h(), mfem_b200_avg_strain_stress(h(), u.data().data(), nullptr, s.data().data()));
         return s;
     }
+    // Full-degree strain / stress (Element::strain :99-116, Simulator::strainField / stressField): the strain
+    // of a degree-Deg displacement is a degree-(Deg-1) interpolant -- one value per element for Deg 1, a
+    // linear interpolant given by its values at the K+1 vertices for Deg 2.  Returned UPSAMPLED to the
+    // element's full node set (vertex values, edge nodes = mean of the end points) as Simulate_cli writes it
+    // (Simulate_cli.cc:208-224).  Host loop over the elements (post-processing, O(elements)).
+    typedef SymmetricMatrixInterpolantField<Real, N> SMInterpField;
+    SMInterpField strainField(const VField &u) const { return m_strainOrStressField(u, false); }
+    SMInterpField stressField(const VField &u) const { return m_strainOrStressField(u, true); }
+
     template <class _SymMat>
     VField constantStrainLoad(const _SymMat &strain) const {  // :551-562
         VField load(numDoFs());
@@ -512,6 +521,46 @@ private:
                 dirichletVars.push_back(N * constraintDoFs[i] + c);
                 dirichletValues.push_back(constraintDisplacements[i][c]);
             }
+    }
+
+    SMInterpField m_strainOrStressField(const VField &u, bool stress) const {
+        constexpr size_t npe = _Mesh::nodesPerElement, F = flatLen(N);
+        if (u.domainSize() != m_mesh.numNodes()) throw std::runtime_error("strainField: per-node displacement expected");
+        SMInterpField out(m_mesh.numElements(), npe);
+        for (size_t e = 0; e < m_mesh.numElements(); ++e) {
+            Real g[K + 1][K];
+            m_mesh.elementGradLambda(e, g);
+            SMatrix atVertex[K + 1];
+            const size_t nv = (Degree == 1) ? 1 : K + 1;            // evaluation points of the interpolant
+            for (size_t v = 0; v < nv; ++v) {
+                Real grad[N][N] = {};                               // grad[c][r] = d u_c / d x_r at vertex v
+                for (size_t i = 0; i < npe; ++i) {
+                    Real gphi[K] = {};
+                    if (Degree == 1) { for (size_t r = 0; r < K; ++r) gphi[r] = g[i][r]; }
+                    else if (i <= K) { const Real w = (i == v) ? 3.0 : -1.0; for (size_t r = 0; r < K; ++r) gphi[r] = w * g[i][r]; }
+                    else {                                          // edge node (s, e): 4 (x_e grad l_s + x_s grad l_e)
+                        const size_t k = i - (K + 1);
+                        const size_t es = Simplex::edgeStartNode(k), ee = Simplex::edgeEndNode(k);
+                        if (v == es) for (size_t r = 0; r < K; ++r) gphi[r] = 4.0 * g[ee][r];
+                        else if (v == ee) for (size_t r = 0; r < K; ++r) gphi[r] = 4.0 * g[es][r];
+                    }
+                    const auto ui = u(m_mesh.elementNode(e, i));
+                    for (size_t c = 0; c < N; ++c) for (size_t r = 0; r < K; ++r) grad[c][r] += ui[c] * gphi[r];
+                }
+                SMatrix eps;
+                for (size_t c = 0; c < N; ++c) for (size_t r = c; r < N; ++r) eps(c, r) = 0.5 * (grad[c][r] + grad[r][c]);
+                atVertex[v] = stress ? elementTensor(e).doubleContract(eps) : eps;
+            }
+            for (size_t n = 0; n < npe; ++n)
+                for (size_t kf = 0; kf < F; ++kf) {
+                    Real val;
+                    if (Degree == 1) val = atVertex[0][kf];
+                    else if (n <= K) val = atVertex[n][kf];
+                    else { const size_t k = n - (K + 1); val = 0.5 * (atVertex[Simplex::edgeStartNode(k)][kf] + atVertex[Simplex::edgeEndNode(k)][kf]); }
+                    out(e, n, kf) = val;
+                }
+        }
+        return out;
     }
 
     void m_pinNode(std::vector<size_t> &fixedVars, std::vector<Real> &fixedVarValues,

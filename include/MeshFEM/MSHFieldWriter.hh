@@ -30,6 +30,7 @@ public:
         std::vector<MeshIO::IOElement> outElements;
         const size_t nOut = linearSubsample ? mesh.numVertices() : mesh.numNodes();
         const size_t perElem = linearSubsample ? Mesh::verticesPerElement : Mesh::nodesPerElement;
+        m_outNodesPerElement = perElem;
         outNodes.reserve(nOut);
         for (size_t n = 0; n < nOut; ++n) outNodes.emplace_back(padTo3D(mesh.nodePosition(n)));
         outElements.reserve(m_numElements);
@@ -76,6 +77,32 @@ public:
         m_outStream << "$End" << sectionHeader << std::endl;
     }
 
+    // Vector-of-interpolants field -> $ElementNodeData (MSHFieldWriter.hh:262-306): per element its index, the
+    // number of output nodes per element, then 9 (padded 3x3) values per node.  With linear subsampling only
+    // the vertex values of a higher-degree interpolant are written.
+    template <typename _Real, size_t _N>
+    void addField(const std::string &name, const SymmetricMatrixInterpolantField<_Real, _N> &f, DomainType type = DomainType::PER_ELEMENT) {
+        if (type != DomainType::PER_ELEMENT || f.domainSize() != m_numElements)
+            throw std::runtime_error("Vector-of-interpolants must be per-element.");
+        const size_t nOut = m_outNodesPerElement;
+        if (nOut == 0) throw std::runtime_error("ElementNodeData needs a writer constructed from a mesh");
+        if (f.nodesPerElement() < nOut) throw std::runtime_error("Interpolant has too few nodes");
+        m_outStream << "$ElementNodeData" << std::endl << '1' << std::endl << '"' << name << '"' << std::endl << '0' << std::endl
+                    << '3' << std::endl << '0' << std::endl << 9 << std::endl << m_numElements << std::endl;
+        for (size_t i = 1; i <= m_numElements; ++i) {
+            if (m_binary) { int out[2] = {int(i), int(nOut)}; m_outStream.write((char *)out, 2 * sizeof(int)); }
+            else m_outStream << i << ' ' << nOut;
+            for (size_t n = 0; n < nOut; ++n)
+                for (size_t k = 0; k < 3; ++k)
+                    for (size_t l = 0; l < 3; ++l) {
+                        const double value = ((k < _N) && (l < _N)) ? f(i - 1, n, flattenIndices(_N, k, l)) : 0.0;
+                        if (m_binary) m_outStream.write((const char *)&value, sizeof(double)); else m_outStream << ' ' << value;
+                    }
+            if (!m_binary) m_outStream << std::endl;
+        }
+        m_outStream << "$EndElementNodeData" << std::endl;
+    }
+
 private:
     void m_determineDomainTypeAndNumEntries(size_t domainSize, DomainType &type, size_t &numEntries) const {
         std::runtime_error invalidSize("Invalid field domain size.");
@@ -91,6 +118,7 @@ private:
         }
     }
     bool m_linearSubsample;
+    size_t m_outNodesPerElement = 0;     // nodes per element of the written mesh (ElementNodeData)
     std::ofstream m_outStream;
     size_t m_numVertices, m_numNodes, m_numElements;
     bool m_binary;

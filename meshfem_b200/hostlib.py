@@ -42,6 +42,8 @@ def load_library():
         lib.mfemhost_eval_expr.argtypes = [c_char_p, c_double, c_double, c_double, POINTER(c_double)]
         lib.mfemhost_save_mesh.argtypes = [c_void_p, c_char_p]
         lib.mfemhost_perforated_cell.argtypes = [c_int, c_int64, c_int64]
+        lib.mfemhost_strain_field.argtypes = [c_void_p, c_int, POINTER(c_double), c_int, POINTER(c_double), POINTER(c_double),
+                                              c_char_p, c_int]
         lib.mfemhost_perforated_cell.restype = c_void_p
         lib.mfemhost_msh_field.argtypes = [c_int, c_char_p, c_char_p, c_int, c_int, POINTER(c_double), c_int64,
                                            POINTER(c_int64), POINTER(c_int)]
@@ -98,6 +100,22 @@ class RawMesh:
                                   ibe.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)))
         return dict(fixed_vars=fixed, fixed_vals=vals, load=load, dof_for_node=dof, num_dofs=ndof,
                     internal_be=ibe.astype(bool), mesh=fm)
+
+    def strain_field(self, deg, u_nodes, D=None, stress=False, path=None, binary=True):
+        """Simulator::strainField / stressField (host): (numElements, nodesPerElem, flat) nodal values of the
+        upsampled interpolant; path: also write u + the field as a full-degree .msh ($ElementNodeData)."""
+        K = self.dim
+        F = K * (K + 1) // 2
+        npe = K + 1 if deg == 1 else (6 if K == 2 else 10)
+        _, E = self.arrays()
+        u = np.ascontiguousarray(u_nodes, dtype=np.float64)
+        Dm = np.ascontiguousarray(np.eye(F) if D is None else D, dtype=np.float64)
+        out = np.zeros((E.shape[0], npe, F))
+        dp = POINTER(c_double)
+        if self.lib.mfemhost_strain_field(self._p, deg, u.ctypes.data_as(dp), 1 if stress else 0, Dm.ctypes.data_as(dp),
+                                          out.ctypes.data_as(dp), None if path is None else os.fsencode(path), 1 if binary else 0) != 0:
+            raise _err(self.lib)
+        return out
 
     def femmesh(self, deg):
         """FEMMesh<dim,deg> flat data with the reference's numbering."""

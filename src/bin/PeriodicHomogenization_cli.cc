@@ -6,8 +6,7 @@
 // The assembly and the solves run on the GPU through libmfem_b200 (no CPU fallback).
 //
 // Differences from the reference, all outside the hot path: --m2mstress, --manualPeriodicVertices and
-// --distanceToIsotropy belong to SURVEY 8(f) "next" rows and are rejected with a message; with -D on degree-2 meshes the per-element average strain is written
-// instead of ElementNodeData; extra options --device / --rtol / --maxIters control the PCG.
+// --distanceToIsotropy belong to SURVEY 8(f) "next" rows and are rejected with a message; extra options --device / --rtol / --maxIters control the PCG.
 #include <MeshFEM/CmdLine.hh>
 #include <MeshFEM/GlobalBenchmark.hh>
 #include <MeshFEM/LinearElasticity.hh>
@@ -149,7 +148,10 @@ void execute(const CmdLine &args, const vector<MeshIO::IOVertex> &inVertices, co
         for (size_t i = 0; i < w_ij.size(); ++i) {
             writer.addField("load_ij " + to_string(i), sim.dofToNodeField(sim.constantStrainLoad(-Simulator::SMatrix::CanonicalBasis(i))), DomainType::PER_NODE);
             writer.addField("w_ij " + to_string(i), w_ij[i], DomainType::PER_NODE);
-            writer.addField("strain w_ij " + to_string(i), sim.averageStrainField(w_ij[i]), DomainType::PER_ELEMENT);
+            if ((_FEMDegree == 1) || linearSubsampleFields)
+                writer.addField("strain w_ij " + to_string(i), sim.averageStrainField(w_ij[i]), DomainType::PER_ELEMENT);
+            else        // full-degree per-element strain as ElementNodeData (:214-226)
+                writer.addField("strain w_ij " + to_string(i), sim.strainField(w_ij[i]), DomainType::PER_ELEMENT);
         }
     }
 

@@ -8,8 +8,6 @@
 // Differences from the reference, all outside the hot path:
 //  * heterogeneous material from a .msh (-m x.msh -f name) is read by MSHFieldParser (E/nu or the
 //    orthotropic parameter fields) and uploaded as a per-element D array;
-//  * with -D on degree-2 meshes the reference writes ElementNodeData (full-degree strain); we write
-//    the per-element average strain/stress in both modes;
 //  * extra options: --device, --rtol, --maxIters (PCG controls; the reference's direct solver has none).
 #include <MeshFEM/CmdLine.hh>
 #include <MeshFEM/GlobalBenchmark.hh>
@@ -161,8 +159,15 @@ void execute(const CmdLine &args, const vector<MeshIO::IOVertex> &inVertices, co
     MSHFieldWriter writer(outMSH, sim.mesh(), linearSubsampleFields);
     writer.addField("u", u, DomainType::PER_NODE);
     writer.addField("load", f, DomainType::PER_NODE);
-    writer.addField("strain", e, DomainType::PER_ELEMENT);
-    writer.addField("stress", s, DomainType::PER_ELEMENT);
+    if ((_Deg == 1) || linearSubsampleFields) {
+        // constant (average) strain/stress for piecewise linear u (:203-207)
+        writer.addField("strain", e, DomainType::PER_ELEMENT);
+        writer.addField("stress", s, DomainType::PER_ELEMENT);
+    } else {
+        // full-degree per-element strain/stress as ElementNodeData (:208-224)
+        writer.addField("strain", sim.strainField(u), DomainType::PER_ELEMENT);
+        writer.addField("stress", sim.stressField(u), DomainType::PER_ELEMENT);
+    }
 
     sim.reportRegionSurfaceForces(u);
     writer.addField("Ku", sim.applyStiffnessMatrix(u), DomainType::PER_NODE);

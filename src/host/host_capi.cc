@@ -4,6 +4,7 @@
 #include <MeshFEM/FEMMesh.hh>
 #include <MeshFEM/LinearElasticity.hh>
 #include <MeshFEM/MSHFieldParser.hh>
+#include <MeshFEM/MSHFieldWriter.hh>
 #include <MeshFEM/Materials.hh>
 #include <MeshFEM/Partition.hh>
 #include <MeshFEM/MeshIO.hh>
@@ -53,6 +54,8 @@ void fill(HostMesh &hm) {
 }
 
 }  // namespace
+
+template <class T> struct TypeTag { typedef T type; };
 
 extern "C" {
 
@@ -311,6 +314,38 @@ int mfemhost_tensor_analysis(int dim, const double *Dflat, double *lambdas, doub
             else E.getOrthotropic2D(ortho[0], ortho[1], ortho[2], ortho[3]);
         };
         if (dim == 3) run(ElasticityTensor<Real, 3>()); else run(ElasticityTensor<Real, 2>());
+        return 0;
+    } catch (const std::exception &e) { g_err = e.what(); return -1; }
+}
+
+// Simulator::strainField / stressField (full-degree, upsampled to the element's nodes) in host-only mode:
+// out[numElements][nodesPerElem][flat]; with path != NULL also written as $ElementNodeData "strain"/"stress"
+// next to the $NodeData "u" (MSHFieldWriter, full-degree output as Simulate_cli -D).
+int mfemhost_strain_field(void *m, int deg, const double *uNodes, int stress, const double *Dflat, double *out,
+                          const char *path, int binary) {
+    auto *hm = static_cast<HostMesh *>(m);
+    try {
+        auto run = [&](auto simTag) {
+            typedef typename decltype(simTag)::type Sim;
+            Sim sim(hm->elements, hm->vertices, -1);
+            typename Sim::ETensor E;
+            E.setFlat(Dflat);
+            sim.setMaterial(E);
+            typename Sim::VField u(sim.mesh().numNodes());
+            std::copy(uNodes, uNodes + u.size(), u.data().begin());
+            const auto f = stress ? sim.stressField(u) : sim.strainField(u);
+            std::copy(f.data().begin(), f.data().end(), out);
+            if (path) {
+                MSHFieldWriter writer(path, sim.mesh(), false, MeshIO::MESH_GUESS, binary != 0);
+                writer.addField("u", u, DomainType::PER_NODE);
+                writer.addField(stress ? "stress" : "strain", f, DomainType::PER_ELEMENT);
+            }
+        };
+        if (hm->dim == 3 && deg == 1) run(TypeTag<LinearElasticity::Simulator<LinearElasticity::Mesh<3, 1>>>());
+        else if (hm->dim == 3 && deg == 2) run(TypeTag<LinearElasticity::Simulator<LinearElasticity::Mesh<3, 2>>>());
+        else if (hm->dim == 2 && deg == 1) run(TypeTag<LinearElasticity::Simulator<LinearElasticity::Mesh<2, 1>>>());
+        else if (hm->dim == 2 && deg == 2) run(TypeTag<LinearElasticity::Simulator<LinearElasticity::Mesh<2, 2>>>());
+        else throw std::runtime_error("bad dim/deg");
         return 0;
     } catch (const std::exception &e) { g_err = e.what(); return -1; }
 }

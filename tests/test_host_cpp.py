@@ -200,6 +200,42 @@ def test_msh_field_parser_reads_what_the_writer_wrote(hostlib, tmp_path):
     assert np.array_equal(sm, np.stack([np.arange(len(T)), 2.0 * np.arange(len(T)), np.full(len(T), 7.0)], axis=1))
 
 
+@pytest.mark.parametrize("sizes,deg", [((3, 2), 1), ((3, 2), 2), ((2, 2, 2), 1), ((3, 2, 2), 2)])
+@pytest.mark.parametrize("binary", [True, False])
+def test_full_degree_strain_stress_fields(hostlib, tmp_path, sizes, deg, binary):
+    """Simulator::strainField / stressField (Element::strain, LinearElasticity.hh:99-123) upsampled to the
+    element's nodes, and their $ElementNodeData output (MSHFieldWriter.hh:262-306) -- what Simulate_cli -D
+    writes for degree-2 meshes -- against the oracle's vertex strains."""
+    from util import read_msh_fields, sym9_to_flat
+    N = len(sizes)
+    raw = hostlib.grid(list(sizes))
+    V, T = raw.arrays()
+    m = orc.build_mesh(N, deg, V[:, :N], T)
+    rng = np.random.default_rng(4)
+    u = rng.normal(size=(m.num_nodes, N))
+    D = orc.material_from_json(3, ORTHO) if N == 3 else orc.orthotropic_D2(200.0, 120.0, 0.18, 60.0)
+    ev = orc.element_strain_vertices(m, u)                       # (ne, 1 | N+1, N, N)
+    F = orc.flat_len(N)
+    flat = np.stack([ev[:, :, a, b] for a, b in (orc.unflatten_index(N, i) for i in range(F))], axis=2)   # (ne, nv, F)
+    npe = m.elem_nodes.shape[1]
+    if deg == 1:
+        want = np.repeat(flat, npe, axis=1)
+    else:
+        edges = [(orc.EDGE_START[k], orc.EDGE_END[k]) for k in range(orc.num_edges(N))]
+        want = np.concatenate([flat] + [0.5 * (flat[:, [s]] + flat[:, [e]]) for s, e in edges], axis=1)
+    path = str(tmp_path / "f.msh")
+    got = raw.strain_field(deg, u, path=path, binary=binary)
+    assert got.shape == want.shape and np.abs(got - want).max() <= 1e-13 * np.abs(want).max()
+    dbl = np.ones(F); dbl[N:] = 2.0
+    sig = raw.strain_field(deg, u, D=D, stress=True)
+    assert np.abs(sig - (want * dbl) @ D.T).max() <= 1e-12 * np.abs(sig).max()
+    f = read_msh_fields(path)
+    assert f["strain"].shape == (m.num_elements, npe, 9)
+    written = np.stack([sym9_to_flat(N, f["strain"][:, n, :]) for n in range(npe)], axis=1)
+    assert np.abs(written - want).max() <= (1e-13 if binary else 1e-5) * np.abs(want).max()
+    assert np.abs(f["u"][:, :N] - u).max() <= (0 if binary else 1e-5)
+
+
 def test_tensor_analysis_matches_numpy(hostlib):
     """computeEigenstrains (ElasticityTensor.hh:555-579), inverse, getOrthotropic3D, anisotropy (:251-268)."""
     D = orc.material_from_json(3, ORTHO)

@@ -288,3 +288,33 @@ def test_orthotropic_cell_reproduces_full_periodic_cell():
     # reflected across exactly one of its two in-plane axes
     assert [orc.fluctuation_displacement_sign(3, 5, r) for r in range(8)] == [1, -1, -1, 1, 1, -1, -1, 1]
     assert [orc.fluctuation_displacement_sign(2, 2, r) for r in range(4)] == [1, -1, -1, 1]
+
+
+# ---- tests/test_interpolant.cc:28-66, 200-260: nodal interpolation reproduces every monomial of degree
+# <= Deg pointwise (1e-13) and the interpolant's integral (integrated shape functions) equals the quadrature
+# of the function (1e-16 in the reference; 1e-15 here for the float summation order)
+@pytest.mark.parametrize("K", [1, 2, 3])
+@pytest.mark.parametrize("deg", [1, 2])
+def test_interpolant_exactness_and_integrals(K, deg):
+    rng = np.random.default_rng(1)
+    # node barycentric coordinates: vertices, then edge midpoints in the reference edge order
+    nodes = [np.eye(K + 1)[v] for v in range(K + 1)]
+    if deg == 2:
+        if K == 1:
+            nodes.append(np.array([0.5, 0.5]))
+        else:
+            for k in range(orc.num_edges(K)):
+                e = np.zeros(K + 1); e[orc.EDGE_START[k]] = e[orc.EDGE_END[k]] = 0.5
+                nodes.append(e)
+    nodes = np.array(nodes)
+    assert len(nodes) == orc.num_nodes(K, deg)
+    monos = [m for m in itertools.product(range(deg + 1), repeat=K) if sum(m) <= deg]       # u^a v^b w^c
+    X = rng.random((200, K + 1)); X /= X.sum(axis=1, keepdims=True)
+    P, w = orc.quadrature_points(K, deg)
+    iphi = orc.integrated_phis(K, deg)
+    for m in monos:
+        f = lambda lam: np.prod([lam[..., i] ** m[i] for i in range(K)], axis=0)
+        nodal = f(nodes)
+        vals = np.array([orc.shape_functions(K, deg, x) @ nodal for x in X])
+        assert np.abs(vals - f(X)).max() <= 1e-13, m
+        assert abs(iphi @ nodal - sum(wq * f(p) for p, wq in zip(P, w))) <= 1e-15, m

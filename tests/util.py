@@ -68,10 +68,12 @@ def read_msh_fields(path):
     while True:
         i1 = data.find(b"$NodeData\n", pos)
         i2 = data.find(b"$ElementData\n", pos)
-        cands = [i for i in (i1, i2) if i >= 0]
+        i3 = data.find(b"$ElementNodeData\n", pos)
+        cands = [i for i in (i1, i2, i3) if i >= 0]
         if not cands:
             break
         i = min(cands)
+        elem_node = i == i3
         p = data.index(b"\n", i) + 1
         def line():
             nonlocal p
@@ -81,6 +83,18 @@ def read_msh_fields(path):
         name = line().strip('"')
         assert line() == "0" and line() == "3" and line() == "0"
         dim = int(line()); n = int(line())
+        if elem_node:        # per element: id, nodes per element, then nodesPerElem x dim values -> (n, npe, dim)
+            if binary:
+                npe = int(np.frombuffer(data, dtype="<i4", count=2, offset=p)[1])
+                rec = np.frombuffer(data, dtype=np.dtype([("id", "<i4"), ("npe", "<i4"), ("v", "<f8", npe * dim)]), count=n, offset=p)
+                assert np.array_equal(rec["id"], np.arange(1, n + 1)) and (rec["npe"] == npe).all()
+                out[name] = rec["v"].reshape(n, npe, dim).copy(); p += n * (8 + 8 * npe * dim)
+            else:
+                rows = [line().split() for _ in range(n)]
+                npe = int(rows[0][1])
+                out[name] = np.array([[float(x) for x in r[2:]] for r in rows]).reshape(n, npe, dim)
+            pos = p
+            continue
         if binary:
             rec = np.frombuffer(data, dtype=np.dtype([("id", "<i4"), ("v", "<f8", dim)]), count=n, offset=p)
             assert np.array_equal(rec["id"], np.arange(1, n + 1))
