@@ -48,6 +48,7 @@ def load_library():
         lib.mfemhost_msh_field.argtypes = [c_int, c_char_p, c_char_p, c_int, c_int, POINTER(c_double), c_int64,
                                            POINTER(c_int64), POINTER(c_int)]
         lib.mfemhost_tensor_analysis.argtypes = [c_int, POINTER(c_double)] + [POINTER(c_double)] * 5
+        lib.mfemhost_closest_isotropic.argtypes = [c_int, POINTER(c_double), POINTER(c_double)]
         lib.mfemhost_partition.argtypes = [c_int, c_int64, POINTER(c_double), c_int64, c_int, POINTER(c_int32), c_int, c_int,
                                            POINTER(c_int64), c_int64, POINTER(c_int64)]
         lib.mfemhost_partition_copy.argtypes = [POINTER(c_int64), POINTER(c_int64), POINTER(c_int32),
@@ -180,6 +181,17 @@ def tensor_analysis(D):
     if lib.mfemhost_tensor_analysis(dim, dp(D), dp(lam), dp(strains), dp(S), dp(ortho), ctypes.byref(aniso)) != 0:
         raise _err(lib)
     return SimpleNamespace(lambdas=lam, strains=strains, compliance=S, orthotropic=ortho, anisotropy=aniso.value)
+
+
+def closest_isotropic_tensor(D):
+    """closestIsotropicTensor (TensorProjection.hh): Frobenius projection onto the isotropic tensors."""
+    lib = load_library()
+    D = np.ascontiguousarray(D, dtype=np.float64)
+    out = np.zeros_like(D)
+    if lib.mfemhost_closest_isotropic(3 if D.shape[0] == 6 else 2, D.ctypes.data_as(POINTER(c_double)),
+                                      out.ctypes.data_as(POINTER(c_double))) != 0:
+        raise _err(lib)
+    return out
 
 
 def eval_expression(expr, x=0.0, y=0.0, z=0.0):

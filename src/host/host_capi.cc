@@ -4,6 +4,7 @@
 #include <MeshFEM/FEMMesh.hh>
 #include <MeshFEM/LinearElasticity.hh>
 #include <MeshFEM/MSHFieldParser.hh>
+#include <MeshFEM/TensorProjection.hh>
 #include <MeshFEM/MSHFieldWriter.hh>
 #include <MeshFEM/Materials.hh>
 #include <MeshFEM/Partition.hh>
@@ -300,6 +301,14 @@ int mfemhost_msh_field(int dim, const char *path, const char *name, int kind, in
 
 // ElasticityTensor analysis used by PeriodicHomogenization_cli: eigenstrains (ascending eigenvalues,
 // strains[k][component]), compliance D(inverse()), orthotropic parameters, anisotropy.
+int mfemhost_closest_isotropic(int dim, const double *Dflat, double *out) {
+    try {
+        if (dim == 3) { ElasticityTensor<Real, 3> E; E.setFlat(Dflat); closestIsotropicTensor(E).getFlat(out); }
+        else { ElasticityTensor<Real, 2> E; E.setFlat(Dflat); closestIsotropicTensor(E).getFlat(out); }
+        return 0;
+    } catch (const std::exception &e) { g_err = e.what(); return -1; }
+}
+
 int mfemhost_tensor_analysis(int dim, const double *Dflat, double *lambdas, double *strains, double *compliance,
                              double *ortho, double *anisotropy) {
     try {

@@ -255,6 +255,28 @@ def test_tensor_analysis_matches_numpy(hostlib):
     assert abs(iso2.anisotropy - 1.0) < 1e-12 and np.allclose(iso2.lambdas, np.linalg.eigvalsh(np.diag([1, 1, np.sqrt(2)]) @ orc.isotropic_D(2, 200.0, 0.35) @ np.diag([1, 1, np.sqrt(2)])))
 
 
+@pytest.mark.parametrize("N", [2, 3])
+def test_closest_isotropic_tensor(hostlib, N):
+    """closestIsotropicTensor (TensorProjection.hh:20-53): identity on isotropic tensors, and the Frobenius
+    minimiser over (lambda, mu) of ||C - Iso(lambda, mu)||^2 in the FULL rank-4 norm (shear entries of the
+    flattened matrix count 2x / 4x)."""
+    iso = orc.isotropic_D(N, 200.0, 0.35)
+    assert np.allclose(hostlib.closest_isotropic_tensor(iso), iso, rtol=1e-13)
+    D = orc.material_from_json(3, ORTHO) if N == 3 else orc.orthotropic_D2(200.0, 120.0, 0.18, 60.0)
+    fit = hostlib.closest_isotropic_tensor(D)
+    F = orc.flat_len(N)
+    wgt = np.ones(F); wgt[N:] = 2.0
+    W = np.outer(wgt, wgt)                       # multiplicity of a flattened entry in the rank-4 tensor
+    def iso_lame(lam, mu):
+        A = np.zeros((F, F)); A[:N, :N] = lam; A[np.arange(N), np.arange(N)] += 2 * mu; A[np.arange(N, F), np.arange(N, F)] = mu
+        return A
+    lam, mu = fit[0, 1], fit[F - 1, F - 1]
+    assert np.allclose(fit, iso_lame(lam, mu), rtol=1e-13, atol=1e-13)
+    base = (W * (D - fit) ** 2).sum()
+    for dl, dm in [(1e-3, 0), (-1e-3, 0), (0, 1e-3), (0, -1e-3)]:
+        assert (W * (D - iso_lame(lam + dl, mu + dm)) ** 2).sum() > base
+
+
 def test_cli_usage_errors_need_no_gpu():
     """Command-line validation of the CLIs mirrors the reference (Simulate_cli.cc:58-80,
     PeriodicHomogenization_cli.cc:65-80): error text, usage, exit status 1."""
