@@ -34,9 +34,10 @@ struct HostMesh {
 
 thread_local std::string g_err;
 
-template <size_t K, size_t Deg>
-void fill(HostMesh &hm) {
-    FEMMesh<K, Deg> m(hm.elements, hm.vertices);
+template <class Mesh>
+void fillFrom(HostMesh &hm, const Mesh &m, int deg) {
+    constexpr size_t K = Mesh::K;
+    hm.deg = deg;
     hm.nodes = m.nodePositions();
     hm.elemNodes = m.elementNodes();
     hm.bdryElemNodes = m.boundaryElementNodes();
@@ -52,6 +53,13 @@ void fill(HostMesh &hm) {
         for (size_t c = 0; c < K; ++c) hm.bdryNormal[be * K + c] = m.boundaryElementNormal(be)[c];
     }
     for (size_t c = 0; c < K; ++c) { hm.bbmin[c] = m.boundingBox().minCorner[c]; hm.bbmax[c] = m.boundingBox().maxCorner[c]; }
+}
+
+template <size_t K, size_t Deg>
+void fill(HostMesh &hm) {
+    if (hm.deg == (int)Deg && !hm.nodes.empty()) return;      // flat FEMMesh data of this degree already cached
+    FEMMesh<K, Deg> m(hm.elements, hm.vertices);
+    fillFrom(hm, m, (int)Deg);
 }
 
 }  // namespace
@@ -161,7 +169,6 @@ int mfemhost_raw_copy(void *m, double *V3, int64_t *E) {
 int mfemhost_build_femmesh(void *m, int deg, int64_t *sizes5) {
     auto *hm = static_cast<HostMesh *>(m);
     try {
-        hm->deg = deg;
         if (hm->dim == 3 && deg == 1) fill<3, 1>(*hm);
         else if (hm->dim == 3 && deg == 2) fill<3, 2>(*hm);
         else if (hm->dim == 2 && deg == 1) fill<2, 1>(*hm);
@@ -200,6 +207,7 @@ template <size_t K, size_t Deg>
 void runBC(HostMesh &hm, const char *bcJson, int periodic) {
     typedef LinearElasticity::Simulator<LinearElasticity::Mesh<K, Deg>> Sim;
     Sim sim(hm.elements, hm.vertices, -1);
+    fillFrom(hm, sim.mesh(), (int)Deg);        // the FEMMesh is built once; femmesh() reuses it
     if (periodic) {
         sim.applyPeriodicConditions(1e-7);
         sim.applyNoRigidMotionConstraint();
