@@ -74,3 +74,15 @@ def test_distributed_pcg_gloo(lib_built, world):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     assert "MRANK_CPU" in r.stdout
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_distributed_periodic_homogenization_gloo(lib_built, world):
+    """tests/mrank_cpu_homog_worker.py: DoF-based partition of a periodic cell, pinned variable, exchanged
+    constant-strain loads, distributed PCG and the all-reduced volume form against the golden tensor."""
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(29620 + world), os.path.join(ROOT, "tests", "mrank_cpu_homog_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert "MRANK_CPU_HOMOG" in r.stdout
