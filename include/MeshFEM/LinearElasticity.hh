@@ -8,9 +8,10 @@
 // analyzeDirichletPosedness :1169-1190, assembleConstrainedSystem :1201-1249,
 // m_getDirichletVarsAndValues :1469-1518, m_pinNode :1595-1618, neumannLoad :703-717.
 //
-// Systems that need Lagrange-multiplier rows (no_rigid_motion without periodicity, or an
-// unconstrained translation without the pin option) are indefinite KKT systems; the reference
-// needs UMFPACK for them (off by default, LUFactorizerStub throws).  They throw here too.
+// Systems with Lagrange-multiplier rows (no_rigid_motion without periodicity, or an unconstrained
+// translation without the pin option) are saddle-point systems the reference hands to UMFPACK; here the
+// rows are resolved on the host around the device PCG (RigidMotionConstraints.hh: multipliers from the
+// free rigid modes, a consistent semi-definite solve, then the rigid part fixed so that C u = d).
 #ifndef MESHFEM_B200_LINEARELASTICITY_HH
 #define MESHFEM_B200_LINEARELASTICITY_HH
 #include <MeshFEM/BoundaryConditions.hh>
@@ -18,6 +19,7 @@
 #include <MeshFEM/Fields.hh>
 #include <MeshFEM/GlobalBenchmark.hh>
 #include <MeshFEM/Materials.hh>
+#include <MeshFEM/RigidMotionConstraints.hh>
 #include <MeshFEM/SparseMatrices.hh>
 
 #include <iostream>
@@ -117,6 +119,7 @@ public:
     // ---- solve (:479-487, 657)
     VField solve(const VField &f) const {
         if (!m_system.isSet()) m_buildConstrainedSystem();
+        if (m_constraintRows.m() > 0) return m_solveWithConstraintRows(std::vector<VField>(1, f))[0];
         BENCHMARK_START_TIMER_SECTION("Elasticity Solve");
         std::vector<Real> x;
         m_system.solve(f.data(), x);
@@ -146,6 +149,7 @@ public:
     // all right-hand sides against one assembled system (batched on the device when there are flatLen(N))
     std::vector<VField> solve(const std::vector<VField> &fs) const {
         if (!m_system.isSet()) m_buildConstrainedSystem();
+        if (m_constraintRows.m() > 0) return m_solveWithConstraintRows(fs);
         BENCHMARK_START_TIMER_SECTION("Elasticity Solve");
         std::vector<std::vector<Real>> rhs, xs;
         for (const auto &f : fs) rhs.push_back(f.data());
@@ -157,6 +161,8 @@ public:
     }
     void setSolverTolerance(double rtol, int maxIters = 200000) { m_system.setTolerance(rtol, maxIters); }
     const mfem_b200_solve_info &lastSolveInfo() const { return m_system.lastSolveInfo(); }
+    // multipliers of the last solve with Lagrange rows, one vector per right-hand side
+    const std::vector<std::vector<Real>> &lastLagrangeMultipliers() const { return m_lastMultipliers; }
 
     // ---- fields
     SMField averageStrainField(const VField &u) const {      // :528-537
@@ -349,9 +355,51 @@ public:
     void removeAllBoundaryConditions() { removeNeumanConditions(); removeDirichletConditions(); }
 
     void applyNoRigidMotionConstraint() {                     // :1052-1059
-        if (!m_useRigidMotionConstraint) { m_system.clear(); m_useRigidMotionConstraint = true; }
+        if (!m_useRigidMotionConstraint || m_rigidMotionConstraintRHS.size() != 0) {
+            m_rigidMotionConstraintRHS.clear();
+            m_system.clear();
+            m_useRigidMotionConstraint = true;
+        }
     }
-    void setUsePinNoRigidTranslationConstraint(bool use) { m_useNRTPinConstraint = use; }
+    void setUsePinNoRigidTranslationConstraint(bool use) { if (use != m_useNRTPinConstraint) m_system.clear(); m_useNRTPinConstraint = use; }
+    // match the rigid motion of the per-DoF field u: the no-rigid-motion rows with right-hand side R u (:1069-1076)
+    void applyRigidMotionConstraint(const VField &u) {
+        applyNoRigidMotionConstraint();
+        m_system.clear();
+        getRigidInnerProduct(u, m_rigidMotionConstraintRHS);
+    }
+    // R u for the rigid-mode matrix R = [rotation rows; translation rows] (:1114-1126, m_assembleRigidModeMatrix :1522-1528)
+    void getRigidInnerProduct(const VField &u, std::vector<Real> &innerProduct) const {
+        if (u.domainSize() != numDoFs()) throw std::runtime_error("getRigidInnerProduct: per-DoF field expected");
+        ConstraintRows R;
+        m_appendInfinitesimalRotationRows(R);
+        m_appendTranslationRows(R);
+        innerProduct.assign(R.m(), 0.0);
+        for (size_t i = 0; i < R.m(); ++i) innerProduct[i] = RigidMotionConstraints::dot(R.rows[i], u.data());
+    }
+    // v -= sum_i (R_i . v) R_i / |R_i|^2 for the rigid-mode rows (:1128-1164; rows orthogonal, not normalised)
+    void projectOutRigidComponent(VField &v, const std::vector<bool> &dofMask = std::vector<bool>()) const {
+        if (v.domainSize() != numDoFs()) throw std::runtime_error("projectOutRigidComponent: per-DoF field expected");
+        const bool hasDofMask = dofMask.size() == numDoFs();
+        ConstraintRows R;
+        m_appendInfinitesimalRotationRows(R);
+        m_appendTranslationRows(R);
+        std::vector<Real> rowSqNorms(R.m(), 0.0), innerProduct(R.m(), 0.0);
+        auto &vd = v.data();
+        for (size_t i = 0; i < R.m(); ++i)
+            for (size_t j = 0; j < vd.size(); ++j) {
+                if (hasDofMask && dofMask[j / N]) continue;
+                rowSqNorms[i] += R.rows[i][j] * R.rows[i][j];
+                innerProduct[i] += R.rows[i][j] * vd[j];
+            }
+        for (size_t i = 0; i < R.m(); ++i) {
+            if (rowSqNorms[i] == 0.0) continue;
+            for (size_t j = 0; j < vd.size(); ++j) {
+                if (hasDofMask && dofMask[j / N]) continue;
+                vd[j] -= innerProduct[i] * R.rows[i][j] / rowSqNorms[i];
+            }
+        }
+    }
     void removeNoRigidMotionConstraint() { if (m_useRigidMotionConstraint) { m_system.clear(); m_useRigidMotionConstraint = false; } }
 
     void applyPeriodicPairDirichletConditions(std::vector<PeriodicPairDirichletCondition<N>> &pps) {   // :1087-1093
@@ -390,28 +438,35 @@ public:
         }
     }
 
-    // The constraint half of assembleConstrainedSystem (:1201-1249): which scalar variables
-    // are fixed and to what.  Configurations that would need Lagrange rows throw.
-    void getFixedVariables(std::vector<size_t> &fixedVars, std::vector<Real> &fixedVarValues, bool allowIllPosed = false) const {
+    // The constraint half of assembleConstrainedSystem (:1201-1249): which scalar variables are fixed and to
+    // what, and the Lagrange-multiplier rows C with their right-hand side.
+    typedef RigidMotionConstraints::Rows ConstraintRows;
+    void assembleConstraints(std::vector<size_t> &fixedVars, std::vector<Real> &fixedVarValues, ConstraintRows &C,
+                             bool allowIllPosed = false) const {
         fixedVars.clear(), fixedVarValues.clear();
+        C.clear();
         if (m_useRigidMotionConstraint) {
-            // rotation rows are skipped entirely under periodicity (:1539-1542)
-            const bool rotationsSkipped = ((N == 2) && (numDoFs() < m_mesh.numNodes())) || (numDoFs() + 1 < m_mesh.numNodes());
-            if (!rotationsSkipped || !m_useNRTPinConstraint)
-                throw std::runtime_error("no_rigid_motion without periodic conditions needs Lagrange-multiplier rows (indefinite KKT system; "
-                                         "the reference requires UMFPACK for it) -- not on the SPD assemble-and-solve path");
-            m_pinNode(fixedVars, fixedVarValues);
+            m_appendInfinitesimalRotationRows(C);              // NO RIGID ROTATIONS
+            if (m_useNRTPinConstraint) m_pinNode(fixedVars, fixedVarValues);
+            else m_appendTranslationRows(C);
+            // rigid-motion = 0 unless a right-hand side was supplied (applyRigidMotionConstraint)
+            C.rhs = m_rigidMotionConstraintRHS;
+            if (C.rhs.size() == 0) C.rhs.assign(C.m(), 0.0);
+            if (C.rhs.size() != C.m()) throw std::runtime_error("Invalid rigid motion RHS");
         } else if (!allowIllPosed) {
             ComponentMask needsTranslations, needsRotations;
             analyzeDirichletPosedness(needsTranslations, needsRotations);
             if (needsTranslations.hasAny(N)) {
                 if (m_useNRTPinConstraint) m_pinNode(fixedVars, fixedVarValues, needsTranslations);
-                else throw std::runtime_error("unconstrained translation components need a Lagrange-multiplier row (indefinite KKT system); "
-                                              "call setUsePinNoRigidTranslationConstraint(true) or add Dirichlet conditions");
+                else { m_appendTranslationRows(C, needsTranslations); C.rhs.assign(needsTranslations.count(N), 0.0); }
             }
             if (needsRotations.hasAny(N)) throw std::runtime_error("Unimplemented");
         }
         m_getDirichletVarsAndValues(fixedVars, fixedVarValues);
+    }
+    void getFixedVariables(std::vector<size_t> &fixedVars, std::vector<Real> &fixedVarValues, bool allowIllPosed = false) const {
+        ConstraintRows C;
+        assembleConstraints(fixedVars, fixedVarValues, C, allowIllPosed);
     }
 
     void reportRegionSurfaceForces(const VField &u) const {  // :1251-1270
@@ -484,7 +539,8 @@ private:
         std::vector<size_t> fixedVars;
         std::vector<Real> fixedVarValues;
         BENCHMARK_START_TIMER("Assemble System");
-        getFixedVariables(fixedVars, fixedVarValues);
+        assembleConstraints(fixedVars, fixedVarValues, m_constraintRows);
+        m_systemFixedVars = fixedVars;
         BENCHMARK_STOP_TIMER("Assemble System");
         mfemCheck(h(), mfem_b200_clear_fixed_variables(h()));
         m_system.setAssembled(N * numDoFs());
@@ -492,6 +548,62 @@ private:
         m_system.fixVariables(fixedVars, fixedVarValues);
         BENCHMARK_STOP_TIMER_SECTION("Fix Variables");
         m_system.setEconomyMode(true);
+    }
+
+    // ---- Lagrange rows, dense over the N * numDoFs() variables
+    static constexpr size_t numRotModes = (N == 3) ? 3 : 1;
+    // no-rigid-rotation rows (:1530-1568).  Periodic conditions pin the rotations, so the rows are skipped then.
+    void m_appendInfinitesimalRotationRows(ConstraintRows &R) const {
+        if ((N == 2) && (numDoFs() < m_mesh.numNodes())) return;
+        if (numDoFs() + 1 < m_mesh.numNodes()) return;
+        if (numDoFs() < m_mesh.numNodes()) throw std::runtime_error("Single pair periodic BC unsupported in 3D.");
+        const size_t old = R.rows.size(), nn = m_mesh.numNodes();
+        R.rows.resize(old + numRotModes, std::vector<Real>(N * numDoFs(), 0.0));
+        for (size_t k = 0; k < nn; ++k) {
+            const Point x = m_mesh.nodePosition(k);
+            if (N == 3) {
+                R.rows[old    ][N * k + 1] = -x[2]; R.rows[old    ][N * k + 2] =  x[1];    // x axis: (0, -z, y)
+                R.rows[old + 1][N * k    ] =  x[2]; R.rows[old + 1][N * k + 2] = -x[0];    // y axis: (z, 0, -x)
+                R.rows[old + 2][N * k    ] = -x[1]; R.rows[old + 2][N * k + 1] =  x[0];    // z axis: (-y, x, 0)
+            } else {
+                R.rows[old][N * k] = -x[1]; R.rows[old][N * k + 1] = x[0];                  // "z axis": (-y, x)
+            }
+        }
+    }
+    // no-rigid-translation rows on the (possibly periodic) DoFs (:1571-1593)
+    void m_appendTranslationRows(ConstraintRows &T, const ComponentMask &components = ComponentMask("xyz")) const {
+        for (size_t c = 0; c < N; ++c) {
+            if (!components.has(c)) continue;
+            std::vector<Real> row(N * numDoFs(), 0.0);
+            for (size_t i = 0; i < numDoFs(); ++i) row[N * i + c] = 1.0;
+            T.rows.push_back(std::move(row));
+        }
+    }
+public:
+    // candidates for the null space of K on the DoFs: translations always, infinitesimal rotations when
+    // nodes and DoFs coincide (periodic identification is not rotation invariant)
+    std::vector<std::vector<Real>> candidateRigidModes() const {
+        ConstraintRows B;
+        m_appendTranslationRows(B);
+        if (numDoFs() == m_mesh.numNodes()) m_appendInfinitesimalRotationRows(B);
+        return B.rows;
+    }
+private:
+    std::vector<VField> m_solveWithConstraintRows(const std::vector<VField> &fs) const {
+        BENCHMARK_START_TIMER_SECTION("Elasticity Solve");
+        std::vector<std::vector<Real>> rhs;
+        for (const auto &f : fs) rhs.push_back(f.data());
+        auto us = RigidMotionConstraints::solve(N * numDoFs(), m_constraintRows, m_systemFixedVars, candidateRigidModes(), rhs,
+            [&](const std::vector<std::vector<Real>> &bs) {
+                std::vector<std::vector<Real>> xs;
+                if (bs.size() == 1) { xs.resize(1); m_system.solve(bs[0], xs[0]); }
+                else m_system.solveMultiple(bs, xs);
+                return xs;
+            }, &m_lastMultipliers);
+        BENCHMARK_STOP_TIMER_SECTION("Elasticity Solve");
+        std::vector<VField> result;
+        for (const auto &x : us) result.push_back(dofToNodeField(x));
+        return result;
     }
 
     void m_getDirichletVarsAndValues(std::vector<size_t> &dirichletVars, std::vector<Real> &dirichletValues) const {   // :1469-1518
@@ -585,6 +697,10 @@ private:
 
 protected:
     mutable SPSDSystem<Real> m_system;
+    mutable ConstraintRows m_constraintRows;                 // Lagrange rows of the cached system
+    mutable std::vector<size_t> m_systemFixedVars;
+    mutable std::vector<std::vector<Real>> m_lastMultipliers;
+    std::vector<Real> m_rigidMotionConstraintRHS;
     _Mesh m_mesh;
 };
 

@@ -36,6 +36,7 @@ def load_library():
                                               POINTER(c_int32), POINTER(c_int32), POINTER(c_double),
                                               POINTER(c_double), POINTER(c_double)]
         lib.mfemhost_apply_bc.argtypes = [c_void_p, c_int, c_char_p, c_int, POINTER(c_int64)]
+        lib.mfemhost_bc_rows.argtypes = [POINTER(c_int64), POINTER(c_double), POINTER(c_double), POINTER(c_double)]
         lib.mfemhost_bc_copy.argtypes = [POINTER(c_int64), POINTER(c_double), POINTER(c_double), POINTER(c_int64),
                                          ctypes.POINTER(ctypes.c_uint8)]
         lib.mfemhost_material.argtypes = [c_int, c_char_p, POINTER(c_double), ctypes.c_char_p, c_int]
@@ -85,11 +86,14 @@ class RawMesh:
         if self.lib.mfemhost_save_mesh(self._p, os.fsencode(path)) != 0:
             raise _err(self.lib)
 
-    def apply_bc(self, deg, bc_json_text, periodic=False):
+    def apply_bc(self, deg, bc_json_text, periodic=False, pin=None):
         """Host-side Simulator bookkeeping (host-only mode): returns dict(fixed_vars, fixed_vals,
-        load[numDoFs, dim], dof_for_node, num_dofs, internal_be)."""
+        load[numDoFs, dim], dof_for_node, num_dofs, internal_be) and, for configurations with Lagrange-multiplier
+        rows (no_rigid_motion, unconstrained translations; periodic with pin=False; pin = the
+        setUsePinNoRigidTranslationConstraint option, default on under periodicity and off otherwise), constraint_rows [m, N*numDoFs],
+        constraint_rhs [m] and the candidate rigid_modes of the null space."""
         sz = (c_int64 * 3)()
-        if self.lib.mfemhost_apply_bc(self._p, deg, (bc_json_text or "").encode(), 1 if periodic else 0, sz) != 0:
+        if self.lib.mfemhost_apply_bc(self._p, deg, (bc_json_text or "").encode(), ((2 if pin is False else 1) if periodic else (4 if pin else 0)), sz) != 0:
             raise _err(self.lib)
         nfix, ndof, nbe = (int(x) for x in sz)
         V, E = self.arrays()
@@ -99,8 +103,15 @@ class RawMesh:
         self.lib.mfemhost_bc_copy(fixed.ctypes.data_as(POINTER(c_int64)), vals.ctypes.data_as(POINTER(c_double)),
                                   load.ctypes.data_as(POINTER(c_double)), dof.ctypes.data_as(POINTER(c_int64)),
                                   ibe.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)))
+        cnt = (c_int64 * 3)()
+        self.lib.mfemhost_bc_rows(cnt, None, None, None)
+        nrows, nmodes, nvar = (int(x) for x in cnt)
+        rows = np.zeros((nrows, nvar)); rhs = np.zeros(nrows); modes = np.zeros((nmodes, nvar))
+        if nrows:
+            dp = POINTER(c_double)
+            self.lib.mfemhost_bc_rows(cnt, rows.ctypes.data_as(dp), rhs.ctypes.data_as(dp), modes.ctypes.data_as(dp))
         return dict(fixed_vars=fixed, fixed_vals=vals, load=load, dof_for_node=dof, num_dofs=ndof,
-                    internal_be=ibe.astype(bool), mesh=fm)
+                    internal_be=ibe.astype(bool), mesh=fm, constraint_rows=rows, constraint_rhs=rhs, rigid_modes=modes)
 
     def strain_field(self, deg, u_nodes, D=None, stress=False, path=None, binary=True):
         """Simulator::strainField / stressField (host): (numElements, nodesPerElem, flat) nodal values of the
@@ -278,3 +289,44 @@ def partition(m, n_parts, rank, dof_for_node=None):
     p.num_nodes, p.num_elements, p.num_dofs = nn, ne, nd
     p.shared = {int(q): p.shared_local[p.neighbor_offsets[i]:p.neighbor_offsets[i + 1]] for i, q in enumerate(p.neighbor_ranks)}
     return p
+
+
+def constrained_solve(rows, rows_rhs, fixed_vars, rigid_modes, fs, spsd_solve):
+    """RigidMotionConstraints::solve (include/MeshFEM/RigidMotionConstraints.hh) -- the host algebra that resolves
+    Lagrange-multiplier rows around an SPSD solver.  spsd_solve(B[nrhs, n]) -> U[nrhs, n] must solve
+    K_ff u_f = b_f - K_fc u_c with the fixed values in place (the Simulator passes the device PCG; this entry
+    exists so that the algebra can be exercised with any solver).  Returns (U[nrhs, n], multipliers[nrhs, m])."""
+    lib = load_library()
+    rows = np.ascontiguousarray(np.atleast_2d(rows), dtype=np.float64)
+    m, n = rows.shape
+    rows_rhs = np.ascontiguousarray(rows_rhs, dtype=np.float64)
+    fixed_vars = np.ascontiguousarray(fixed_vars, dtype=np.int64)
+    rigid_modes = np.ascontiguousarray(np.atleast_2d(rigid_modes), dtype=np.float64)
+    fs = np.ascontiguousarray(np.atleast_2d(fs), dtype=np.float64)
+    nrhs = fs.shape[0]
+    us = np.zeros((nrhs, n)); lam = np.zeros((nrhs, m))
+    CB = ctypes.CFUNCTYPE(c_int, c_int, POINTER(c_double), POINTER(c_double))
+    failure = []
+
+    def _cb(k, rhs_p, u_p):
+        try:
+            B = np.ctypeslib.as_array(rhs_p, shape=(k, n)).copy()
+            U = np.asarray(spsd_solve(B), dtype=np.float64).reshape(k, n)
+            np.ctypeslib.as_array(u_p, shape=(k, n))[:] = U
+            return 0
+        except Exception as e:                            # reported through the C++ exception path
+            failure.append(e)
+            return 1
+    cb = CB(_cb)
+    dp = POINTER(c_double)
+    lib.mfemhost_constrained_solve.argtypes = [c_int64, c_int, dp, dp, c_int64, POINTER(c_int64), c_int, dp, c_int, dp, dp, dp, CB]
+    lib.mfemhost_constrained_solve.restype = c_int
+    rc = lib.mfemhost_constrained_solve(n, m, rows.ctypes.data_as(dp), rows_rhs.ctypes.data_as(dp), fixed_vars.size,
+                                        fixed_vars.ctypes.data_as(POINTER(c_int64)), rigid_modes.shape[0] if rigid_modes.size else 0,
+                                        rigid_modes.ctypes.data_as(dp), nrhs, fs.ctypes.data_as(dp), us.ctypes.data_as(dp),
+                                        lam.ctypes.data_as(dp), cb)
+    if rc != 0:
+        if failure:
+            raise failure[0]
+        raise _err(lib)
+    return us, lam

@@ -720,6 +720,35 @@ def solve_fixed(K, f, fixed_vars, fixed_vals):
     return u
 
 
+def solve_constrained(K, C, C_rhs, f, fixed_vars, fixed_vals):
+    """SPSDSystem::setConstrained + fixVariables + solve with Lagrange rows (SparseMatrices.hh:2332-2348,
+    2389-2500, 2516-2606): the saddle-point matrix [[K, C^T], [C, 0]] with the fixed variables' rows and
+    columns removed (their columns moved to the right-hand side, also for the constraint rows), solved
+    directly (sparse LU stands in for UMFPACK).  Returns (u, multipliers)."""
+    n = K.shape[0]
+    C = sp.csr_matrix(np.atleast_2d(np.asarray(C, dtype=float)))
+    m = C.shape[0]
+    if C.shape[1] != n or len(C_rhs) != m:
+        raise RuntimeError("Bad constraint rows")
+    if np.asarray(f).reshape(-1).shape[0] != n:
+        raise RuntimeError("Bad RHS")
+    fixed_vars = np.asarray(fixed_vars, dtype=np.int64)
+    if len(set(fixed_vars.tolist())) != fixed_vars.size:
+        raise RuntimeError("Variable already fixed.")
+    free = np.ones(n, dtype=bool)
+    free[fixed_vars] = False
+    u = np.zeros(n)
+    u[fixed_vars] = fixed_vals
+    Kcsr = K.tocsr()
+    b = np.concatenate([np.asarray(f, float).reshape(-1)[free] - Kcsr[free][:, ~free] @ u[~free],
+                        np.asarray(C_rhs, float) - C[:, ~free] @ u[~free]])
+    Cf = C[:, free]
+    A = sp.bmat([[Kcsr[free][:, free], Cf.T], [Cf, None]], format="csc")
+    x = spla.splu(A).solve(b)
+    u[free] = x[:free.sum()]
+    return u, x[free.sum():]
+
+
 # ----------------------------------------------------------------------------
 # Loads and post-processing
 # ----------------------------------------------------------------------------
@@ -1153,31 +1182,83 @@ class Simulator:
                     vars_.append(N * dof + c); vals.append(disp[c])
         return vars_, vals
 
-    def fixed_vars_and_values(self):
-        """assembleConstrainedSystem's constraint half (:1201-1249) for the SPD
-        configurations (no Lagrange rows); raises for the ones needing a KKT solve."""
+    # -- Lagrange rows (m_appendInfinitesimalRotationMatrix :1530-1568, m_appendTranslationMatrix :1571-1593)
+    def _rotation_rows(self):
+        N, m = self.N, self.mesh
+        nd, nn = self.num_dofs(), m.num_nodes
+        if N == 2 and nd < nn:                            # periodic conditions pin the rotations (:1539)
+            return np.zeros((0, N * nd))
+        if nd < nn - 1:
+            return np.zeros((0, N * nd))
+        if nd < nn:
+            raise RuntimeError("Single pair periodic BC unsupported in 3D.")
+        X = m.nodes
+        if N == 3:
+            R = np.zeros((3, nn, 3))
+            R[0, :, 1], R[0, :, 2] = -X[:, 2], X[:, 1]    # (0, -z, y)
+            R[1, :, 0], R[1, :, 2] = X[:, 2], -X[:, 0]    # (z, 0, -x)
+            R[2, :, 0], R[2, :, 1] = -X[:, 1], X[:, 0]    # (-y, x, 0)
+            return R.reshape(3, -1)
+        R = np.zeros((1, nn, 2))
+        R[0, :, 0], R[0, :, 1] = -X[:, 1], X[:, 0]
+        return R.reshape(1, -1)
+
+    def _translation_rows(self, comps=(True, True, True)):
+        N, nd = self.N, self.num_dofs()
+        rows = []
+        for c in range(N):
+            if comps[c]:
+                T = np.zeros((nd, N)); T[:, c] = 1.0
+                rows.append(T.reshape(-1))
+        return np.array(rows).reshape(len(rows), N * nd)
+
+    def rigid_mode_matrix(self):                          # m_assembleRigidModeMatrix :1522-1528 (rotations first)
+        return np.vstack([self._rotation_rows(), self._translation_rows()])
+
+    def rigid_inner_product(self, u_dofs):                # getRigidInnerProduct :1114-1126
+        return self.rigid_mode_matrix() @ np.asarray(u_dofs, float).reshape(-1)
+
+    def apply_rigid_motion_constraint(self, u_dofs):      # :1069-1076
+        self.apply_no_rigid_motion_constraint()
+        self.rigid_motion_rhs = self.rigid_inner_product(u_dofs)
+
+    def constraints(self, allow_ill_posed=False):
+        """assembleConstrainedSystem's constraint half (:1201-1249): fixed variables and values plus the
+        Lagrange-multiplier rows C and their right-hand side."""
         N = self.N
         fixed, vals = [], []
-        periodic = self.dof_for_node is not None and self.num_dofs_ < self.mesh.num_nodes
+        C = np.zeros((0, N * self.num_dofs()))
+        rhs = np.zeros(0)
         if self.use_rigid_motion_constraint:
-            rotations_skipped = (N == 2 and periodic) or (self.num_dofs() < self.mesh.num_nodes - 1)   # :1539-1540
-            if not rotations_skipped or not self.use_nrt_pin:
-                raise NotImplementedError("no_rigid_motion needs Lagrange-multiplier rows (KKT system; the "
-                                          "reference needs UMFPACK for it)")
-            v, x = self._pin_node()
-            fixed += v; vals += x
-        else:
+            C = self._rotation_rows()
+            if self.use_nrt_pin:
+                v, x = self._pin_node()
+                fixed += v; vals += x
+            else:
+                C = np.vstack([C, self._translation_rows()])
+            rhs = np.asarray(getattr(self, "rigid_motion_rhs", np.zeros(0)), float)
+            if rhs.size == 0:
+                rhs = np.zeros(C.shape[0])
+            if rhs.size != C.shape[0]:
+                raise RuntimeError("Invalid rigid motion RHS")
+        elif not allow_ill_posed:
             needs_t = [not self.dirichlet_comp[:, c].any() for c in range(N)]      # :1169-1190
+            if any(needs_t):
+                if self.use_nrt_pin:
+                    v, x = self._pin_node(tuple(needs_t) + (False,) * (3 - N))
+                    fixed += v; vals += x
+                else:
+                    C = self._translation_rows(tuple(needs_t) + (False,) * (3 - N))
+                    rhs = np.zeros(C.shape[0])
             if self.dirichlet_comp.sum() == 0:
                 raise RuntimeError("Unimplemented")                                  # :1240
-            if any(needs_t):
-                if not self.use_nrt_pin:
-                    raise NotImplementedError("unconstrained translation components need a Lagrange row")
-                v, x = self._pin_node(tuple(needs_t) + (False,) * (3 - N))
-                fixed += v; vals += x
         v, x = self._dirichlet_vars_and_values()
         fixed += v; vals += x
-        return np.array(fixed, dtype=np.int64), np.array(vals, dtype=float)
+        return np.array(fixed, dtype=np.int64), np.array(vals, dtype=float), C, rhs
+
+    def fixed_vars_and_values(self, allow_ill_posed=False):
+        fixed, vals, _, _ = self.constraints(allow_ill_posed)
+        return fixed, vals
 
     # -- loads / solve
     def neumann_load(self):                               # :703-717
@@ -1201,8 +1282,11 @@ class Simulator:
             f = self.neumann_load()
         if not hasattr(self, "_K"):
             self._K = self.stiffness()
-        fixed, vals = self.fixed_vars_and_values()
-        x = solve_fixed(self._K, np.asarray(f, float).reshape(-1), fixed, vals)
+        fixed, vals, C, rhs = self.constraints()
+        if C.shape[0]:
+            x, self.multipliers = solve_constrained(self._K, C, rhs, np.asarray(f, float).reshape(-1), fixed, vals)
+        else:
+            x = solve_fixed(self._K, np.asarray(f, float).reshape(-1), fixed, vals)
         return self.dof_to_node_field(x)
 
     def average_strain_stress(self, u):

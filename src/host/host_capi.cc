@@ -200,7 +200,14 @@ int mfemhost_femmesh_copy(void *m, double *nodes, int32_t *elemNodes, int32_t *b
 // parse a .bc JSON text, apply it, and return the fixed variables + values and the Neumann load.
 // periodic != 0 additionally applies PeriodicCondition first (cell problems) with the pin constraint.
 namespace {
-struct BCResult { std::vector<int64_t> fixedVars, dofForNode; std::vector<double> fixedVals, load; std::vector<uint8_t> internalBE; int64_t numDoFs = 0; };
+struct BCResult {
+    std::vector<int64_t> fixedVars, dofForNode;
+    std::vector<double> fixedVals, load;
+    std::vector<uint8_t> internalBE;
+    int64_t numDoFs = 0;
+    RigidMotionConstraints::Rows rows;                     // Lagrange rows of the configuration (usually none)
+    std::vector<std::vector<double>> rigidModes;           // candidate null-space modes on the DoFs
+};
 thread_local BCResult g_bc;
 
 template <size_t K, size_t Deg>
@@ -208,11 +215,11 @@ void runBC(HostMesh &hm, const char *bcJson, int periodic) {
     typedef LinearElasticity::Simulator<LinearElasticity::Mesh<K, Deg>> Sim;
     Sim sim(hm.elements, hm.vertices, -1);
     fillFrom(hm, sim.mesh(), (int)Deg);        // the FEMMesh is built once; femmesh() reuses it
-    if (periodic) {
+    if (periodic == 1 || periodic == 2) {
         sim.applyPeriodicConditions(1e-7);
         sim.applyNoRigidMotionConstraint();
-        sim.setUsePinNoRigidTranslationConstraint(true);
-    }
+        sim.setUsePinNoRigidTranslationConstraint(periodic != 2);   // 2: translation rows instead of the pinned node
+    } else if (periodic == 4) sim.setUsePinNoRigidTranslationConstraint(true);   // 4: pin option without periodicity
     if (bcJson && bcJson[0]) {
         std::istringstream is(bcJson);
         bool noRigidMotion;
@@ -226,7 +233,9 @@ void runBC(HostMesh &hm, const char *bcJson, int periodic) {
     }
     std::vector<size_t> fv;
     std::vector<Real> fx;
-    sim.getFixedVariables(fv, fx);
+    sim.assembleConstraints(fv, fx, g_bc.rows);
+    g_bc.rigidModes.clear();
+    if (g_bc.rows.m() > 0) g_bc.rigidModes = sim.candidateRigidModes();
     g_bc.fixedVars.assign(fv.begin(), fv.end());
     g_bc.fixedVals = fx;
     g_bc.load = sim.neumannLoad().data();
@@ -258,6 +267,50 @@ int mfemhost_bc_copy(int64_t *fixedVars, double *fixedVals, double *load, int64_
     cp(g_bc.fixedVars, fixedVars); cp(g_bc.fixedVals, fixedVals); cp(g_bc.load, load); cp(g_bc.dofForNode, dofForNode);
     cp(g_bc.internalBE, internalBE);
     return 0;
+}
+
+// Lagrange-multiplier rows of the last mfemhost_apply_bc: counts[0] = rows, counts[1] = candidate rigid modes,
+// counts[2] = variables per row; rows / rhs / modes are copied when non-null.
+int mfemhost_bc_rows(int64_t *counts3, double *rows, double *rhs, double *modes) {
+    const size_t n = g_bc.load.size();                     // N * numDoFs
+    counts3[0] = (int64_t)g_bc.rows.m(); counts3[1] = (int64_t)g_bc.rigidModes.size(); counts3[2] = (int64_t)n;
+    for (size_t i = 0; rows && i < g_bc.rows.m(); ++i) std::memcpy(rows + i * n, g_bc.rows.rows[i].data(), n * sizeof(double));
+    if (rhs && g_bc.rows.m()) std::memcpy(rhs, g_bc.rows.rhs.data(), g_bc.rows.m() * sizeof(double));
+    for (size_t i = 0; modes && i < g_bc.rigidModes.size(); ++i) std::memcpy(modes + i * n, g_bc.rigidModes[i].data(), n * sizeof(double));
+    return 0;
+}
+
+// RigidMotionConstraints::solve with the SPSD solve supplied by the caller (the Simulator passes the device
+// PCG; the CPU tests of the host algebra pass their own): cb(nrhs, rhs[nrhs*n], u[nrhs*n]) returns 0 on success
+// and must solve K_ff u_f = rhs_f - K_fc u_c with the fixed values in place.
+typedef int (*mfemhost_spsd_solve_cb)(int nrhs, const double *rhs, double *u);
+int mfemhost_constrained_solve(int64_t n, int m, const double *rows, const double *rowsRhs, int64_t nFixed, const int64_t *fixedVars,
+                               int nModes, const double *modes, int nrhs, const double *fs, double *us, double *multipliers,
+                               mfemhost_spsd_solve_cb cb) {
+    try {
+        namespace RMC = RigidMotionConstraints;
+        RMC::Rows C;
+        for (int i = 0; i < m; ++i) C.rows.emplace_back(rows + (size_t)i * n, rows + (size_t)(i + 1) * n);
+        C.rhs.assign(rowsRhs, rowsRhs + m);
+        std::vector<size_t> fv(fixedVars, fixedVars + nFixed);
+        std::vector<RMC::Vec> B, F;
+        for (int i = 0; i < nModes; ++i) B.emplace_back(modes + (size_t)i * n, modes + (size_t)(i + 1) * n);
+        for (int k = 0; k < nrhs; ++k) F.emplace_back(fs + (size_t)k * n, fs + (size_t)(k + 1) * n);
+        std::vector<RMC::Vec> lambdas;
+        auto U = RMC::solve((size_t)n, C, fv, B, F, [&](const std::vector<RMC::Vec> &bs) {
+            std::vector<double> flat(bs.size() * (size_t)n), out(bs.size() * (size_t)n);
+            for (size_t k = 0; k < bs.size(); ++k) std::copy(bs[k].begin(), bs[k].end(), flat.begin() + k * n);
+            if (cb((int)bs.size(), flat.data(), out.data()) != 0) throw std::runtime_error("constrained solve: the SPSD solve callback failed");
+            std::vector<RMC::Vec> xs;
+            for (size_t k = 0; k < bs.size(); ++k) xs.emplace_back(out.begin() + k * n, out.begin() + (k + 1) * n);
+            return xs;
+        }, &lambdas);
+        for (int k = 0; k < nrhs; ++k) {
+            std::copy(U[k].begin(), U[k].end(), us + (size_t)k * n);
+            if (multipliers) std::copy(lambdas[k].begin(), lambdas[k].end(), multipliers + (size_t)k * m);
+        }
+        return 0;
+    } catch (const std::exception &e) { g_err = e.what(); return -1; }
 }
 
 // .material text -> flattened tensor (flat x flat row-major); returns 0 or -1

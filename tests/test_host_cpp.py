@@ -121,9 +121,13 @@ def test_bc_error_behaviour(hostlib):
             {"type": "dirichlet", "value": [1, 0, 0], "box%": {"minCorner": [-.1, -.1, -.1], "maxCorner": [.1, 1.1, 1.1]}}]}))
     with pytest.raises(RuntimeError, match="Invalid type"):
         rm.apply_bc(1, json.dumps({"regions": [{"type": "spring", "value": [0, 0, 0], "box": {"minCorner": [0, 0, 0], "maxCorner": [1, 1, 1]}}]}))
-    with pytest.raises(RuntimeError, match="Lagrange"):      # no Dirichlet on y,z and no pin: needs a KKT row
-        rm.apply_bc(1, json.dumps({"regions": [{"type": "dirichletx", "value": [0, 0, 0],
+    # no Dirichlet on y,z and no pin: two translation rows (LinearElasticity.hh:1236-1238)
+    r = rm.apply_bc(1, json.dumps({"regions": [{"type": "dirichletx", "value": [0, 0, 0],
                                                 "box%": {"minCorner": [-.1, -.1, -.1], "maxCorner": [.1, 1.1, 1.1]}}]}))
+    assert r["constraint_rows"].shape[0] == 2
+    with pytest.raises(RuntimeError, match="Unimplemented"):          # no Dirichlet condition at all (:1240)
+        rm.apply_bc(1, json.dumps({"regions": [{"type": "force", "value": [0, 1, 0],
+                                                "box%": {"minCorner": [.9, -.1, -.1], "maxCorner": [1.1, 1.1, 1.1]}}]}))
 
 
 @pytest.mark.parametrize("sizes,deg", [((3, 3, 3), 1), ((3, 3, 3), 2), ((4, 4), 2)])
