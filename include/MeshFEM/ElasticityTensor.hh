@@ -10,6 +10,7 @@
 #include <cmath>
 #include <iomanip>
 #include <ostream>
+#include <vector>
 
 namespace tensor_detail {
 template <size_t F>
@@ -182,7 +183,48 @@ public:
         }
         return r;
     }
-    _Real frobeniusNormSq() const { _Real s = 0; for (size_t i = 0; i < F; ++i) for (size_t j = 0; j < F; ++j) s += D(i, j) * D(i, j); return s; }
+    // sum_ijkl a_ijkl b_ijkl (:498-506): every flattened shear index stands for two index pairs
+    _Real quadrupleContract(const ElasticityTensor &b) const {
+        _Real s = 0;
+        for (size_t i = 0; i < F; ++i) for (size_t j = 0; j < F; ++j) s += (i >= _Dim ? 2.0 : 1.0) * (j >= _Dim ? 2.0 : 1.0) * D(i, j) * b.D(i, j);
+        return s;
+    }
+    _Real frobeniusNormSq() const { return quadrupleContract(*this); }        // :508
+    // Change of coordinates E'_ijkl = E_pqrs R_ip R_jq R_kr R_ls (:515-541); R row-major _Dim x _Dim, any invertible
+    // matrix (DeformedCells_cli uses the deformation jacobian and its inverse).
+    ElasticityTensor transform(const _Real (&R)[_Dim][_Dim]) const {
+        ElasticityTensor result;
+        for (size_t i = 0; i < _Dim; ++i) for (size_t j = i; j < _Dim; ++j)
+            for (size_t k = 0; k < _Dim; ++k) for (size_t l = k; l < _Dim; ++l) {
+                const size_t ij = flattenIndices<_Dim>(i, j), kl = flattenIndices<_Dim>(k, l);
+                if (ij > kl) continue;
+                _Real comp = 0;
+                for (size_t p = 0; p < _Dim; ++p) for (size_t q = 0; q < _Dim; ++q)
+                    for (size_t r = 0; r < _Dim; ++r) for (size_t t = 0; t < _Dim; ++t)
+                        comp += (*this)(p, q, r, t) * R[i][p] * R[j][q] * R[k][r] * R[l][t];
+                result.m_d[ij][kl] = comp;
+            }
+        result.m_symmetrizeFromUpper();
+        return result;
+    }
+    // row-major F x F coefficients (:636-654) and the orthotropic parameter list
+    // (2D: Ex Ey nuYX muXY -- the reference's own comment says "nuXY" for the 4th, the value is muXY; 3D: Ex Ey Ez nuYX nuZX nuZY muYZ muZX muXY; :168-184)
+    std::vector<_Real> getCoefficients() const {
+        std::vector<_Real> c;
+        for (size_t i = 0; i < F; ++i) for (size_t j = 0; j < F; ++j) c.push_back(D(i, j));
+        return c;
+    }
+    std::vector<_Real> getOrthotropicParameters() const {
+        std::vector<_Real> m(_Dim == 2 ? 4 : 9);
+        if (_Dim == 2) getOrthotropic2D(m[0], m[1], m[2], m[3]);
+        else getOrthotropic3D(m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], m[8]);
+        return m;
+    }
+    void printOrthotropic(std::ostream &os) const {                           // :236-249
+        const auto m = getOrthotropicParameters();
+        for (size_t i = 0; i < m.size(); ++i) os << (i ? "\t" : "") << m[i];
+        os << std::endl;
+    }
 
     // Isotropic-equivalent moduli read off a compliance-like inverse (PeriodicHomogenization_cli.cc:126-171)
     friend std::ostream &operator<<(std::ostream &os, const ElasticityTensor &E) {

@@ -240,6 +240,14 @@ public:
         for (size_t i = 0; i < m_mesh.numBoundaryElements(); ++i) m_beData[i].isInternal = pc->isPeriodicBE(i);
         m_uploadMesh();
     }
+    // (re-)embed the mesh elements (:1279-1284): vertex positions change, connectivity, periodic DoF
+    // identification and boundary conditions stay; the device copy of the mesh is refreshed.
+    template <typename Vertices>
+    void updateMeshNodePositions(const Vertices &vertices) {
+        m_mesh.setNodePositions(vertices);
+        m_system.clear();
+        m_uploadMesh();
+    }
     void removePeriodicConditions() {
         m_system.clear();
         m_dofForNode.clear();

@@ -113,6 +113,7 @@ def build_host(force: bool = False) -> str:
     for name, src in (("Simulate_cli", "src/bin/Simulate_cli.cc"),
                       ("PeriodicHomogenization_cli", "src/bin/PeriodicHomogenization_cli.cc"),
                       ("ConstStrainDisplacement_cli", "src/bin/ConstStrainDisplacement_cli.cc"),
+                      ("DeformedCells_cli", "src/bin/DeformedCells_cli.cc"),
                       ("grid", "src/bin/tools/grid.cc")):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-I" + os.path.join(REPO, "include"),
                                os.path.join(REPO, src), os.path.join(REPO, "src", "host", "MeshIO.cc"),

@@ -129,6 +129,24 @@ class RawMesh:
             raise _err(self.lib)
         return out
 
+    def deformed_displacement_form(self, deg, D, J, w_ij):
+        """Host half of DeformedCells_cli --homogenize: (Eh, deformed node positions) for fluctuation displacements
+        w_ij[flat, numNodes, dim] on the cell deformed by x -> J (x - centre); J None = undeformed."""
+        K = self.dim
+        F = K * (K + 1) // 2
+        dp = POINTER(c_double)
+        fm = self.femmesh(deg)
+        w = np.ascontiguousarray(w_ij, dtype=np.float64)
+        assert w.shape == (F, fm.num_nodes, K)
+        Dm = np.ascontiguousarray(D, dtype=np.float64)
+        Jm = None if J is None else np.ascontiguousarray(J, dtype=np.float64)
+        Eh = np.zeros((F, F)); nodes = np.zeros((fm.num_nodes, K))
+        self.lib.mfemhost_deformed_displacement_form.argtypes = [c_void_p, c_int, dp, dp, dp, dp, dp]
+        if self.lib.mfemhost_deformed_displacement_form(self._p, deg, Dm.ctypes.data_as(dp), None if Jm is None else Jm.ctypes.data_as(dp),
+                                                        w.ctypes.data_as(dp), Eh.ctypes.data_as(dp), nodes.ctypes.data_as(dp)) != 0:
+            raise _err(self.lib)
+        return Eh, nodes
+
     def femmesh(self, deg):
         """FEMMesh<dim,deg> flat data with the reference's numbering."""
         sz = (c_int64 * 5)()

@@ -1433,6 +1433,82 @@ def homogenized_tensor(sim, w_ij, base_cell_volume=0.0):
 # ----------------------------------------------------------------------------
 # Gmsh 2.2 reader (MeshIO.cc:625-760) -- fixtures only
 # ----------------------------------------------------------------------------
+def set_node_positions(mesh, vertices):
+    """FEMMesh::setNodePositions (FEMMesh.hh:221-237): re-embed with new vertex positions, edge nodes at the
+    edge midpoints; connectivity and numbering untouched."""
+    N = mesh.N
+    V = np.asarray(vertices, dtype=float)[:, :N].copy()
+    nV = mesh.simplices.max() + 1 if mesh.deg == 1 else mesh.vertices.shape[0]
+    assert V.shape[0] == mesh.vertices.shape[0]
+    S = mesh.simplices
+    if mesh.deg == 2:
+        # edge node k sits between the two vertices of the first (element, local edge) that references it
+        nedge = num_edges(N)
+        mid = np.zeros((mesh.nodes.shape[0] - V.shape[0], N))
+        for ei in range(nedge):
+            ids = mesh.elem_nodes[:, N + 1 + ei] - V.shape[0]
+            mid[ids] = 0.5 * (V[S[:, EDGE_START[ei]]] + V[S[:, EDGE_END[ei]]])
+        mesh.nodes = np.vstack([V, mid])
+    else:
+        mesh.nodes = V.copy()
+    mesh.vertices = V
+    mesh.vol, mesh.G = embed_simplices(V[S])
+    if mesh.bdry_elem_vertices.shape[0]:
+        mesh.bdry_vol, mesh.bdry_normal = embed_boundary(V[mesh.bdry_elem_vertices])
+    mesh.bbox_min = mesh.nodes.min(axis=0)
+    mesh.bbox_max = mesh.nodes.max(axis=0)
+    del nV
+    return mesh
+
+
+def transform_tensor(N, D, R):
+    """ElasticityTensor::transform (ElasticityTensor.hh:515-541): E'_ijkl = E_pqrs R_ip R_jq R_kr R_ls."""
+    C = tensor_C(N, D)
+    R = np.asarray(R, dtype=float)
+    Ct = np.einsum("pqrs,ip,jq,kr,ls->ijkl", C, R, R, R, R)
+    F = flat_len(N)
+    out = np.zeros((F, F))
+    for a in range(F):
+        i, j = unflatten_index(N, a)
+        for b in range(F):
+            k, l = unflatten_index(N, b)
+            out[a, b] = Ct[i, j, k, l]
+    return out
+
+
+def frobenius_norm_sq(N, D):
+    """ElasticityTensor::frobeniusNormSq = quadrupleContract(self) (:498-508): sum over all ijkl."""
+    C = tensor_C(N, D)
+    return float((C * C).sum())
+
+
+def deformed_cell_homogenization(N, deg, vertices, simplices, D, jacobian, transform_version=False):
+    """DeformedCells_cli --homogenize (src/bin/DeformedCells_cli.cc:222-262).  Direct version: periodic conditions
+    matched on the undeformed cell, nodes moved by x -> J (x - centre), Eh over |bbox| det J.  Transform version:
+    undeformed cell with the pulled-back material E.transform(J^-1), result pushed forward with J."""
+    J = np.asarray(jacobian, dtype=float)
+    sim = Simulator(N, deg, vertices, simplices)
+    if transform_version:
+        sim.set_material(transform_tensor(N, D, np.linalg.inv(J)))
+        w = solve_cell_problems(sim)
+        return transform_tensor(N, homogenized_tensor_displacement_form(sim, w), J), w, sim
+    sim.set_material(D)
+    m = sim.mesh
+    bbox_volume = float(np.prod(m.bbox_max - m.bbox_min))
+    center = 0.5 * (m.bbox_min + m.bbox_max)
+    dof, nd, is_pbe = periodic_condition(m)
+    sim.set_periodic(dof, nd, is_pbe)
+    sim.apply_no_rigid_motion_constraint()
+    sim.set_use_pin_no_rigid_translation_constraint(True)
+    set_node_positions(m, (m.vertices - center) @ J.T)
+    if hasattr(sim, "_K"):
+        del sim._K
+    w = []
+    for i in range(flat_len(N)):
+        w.append(sim.solve(sim.constant_strain_load(-canonical_basis(N, i))))
+    return homogenized_tensor_displacement_form(sim, w, bbox_volume * float(np.linalg.det(J))), w, sim
+
+
 def read_msh(path):
     """Returns (vertices (n,3), elements (m,k), gmsh element type).  ASCII or binary, 8-byte reals."""
     npe = {2: 3, 4: 4, 3: 4, 5: 8, 9: 6, 11: 10, 1: 2, 8: 3}

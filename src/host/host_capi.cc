@@ -3,6 +3,7 @@
 // input generators / host logic, not part of the GPU ABI (include/mfem_b200.h).
 #include <MeshFEM/FEMMesh.hh>
 #include <MeshFEM/LinearElasticity.hh>
+#include <MeshFEM/PeriodicHomogenization.hh>
 #include <MeshFEM/MSHFieldParser.hh>
 #include <MeshFEM/TensorProjection.hh>
 #include <MeshFEM/MSHFieldWriter.hh>
@@ -410,6 +411,62 @@ int mfemhost_strain_field(void *m, int deg, const double *uNodes, int stress, co
                 writer.addField("u", u, DomainType::PER_NODE);
                 writer.addField(stress ? "stress" : "strain", f, DomainType::PER_ELEMENT);
             }
+        };
+        if (hm->dim == 3 && deg == 1) run(TypeTag<LinearElasticity::Simulator<LinearElasticity::Mesh<3, 1>>>());
+        else if (hm->dim == 3 && deg == 2) run(TypeTag<LinearElasticity::Simulator<LinearElasticity::Mesh<3, 2>>>());
+        else if (hm->dim == 2 && deg == 1) run(TypeTag<LinearElasticity::Simulator<LinearElasticity::Mesh<2, 1>>>());
+        else if (hm->dim == 2 && deg == 2) run(TypeTag<LinearElasticity::Simulator<LinearElasticity::Mesh<2, 2>>>());
+        else throw std::runtime_error("bad dim/deg");
+        return 0;
+    } catch (const std::exception &e) { g_err = e.what(); return -1; }
+}
+
+// Host half of DeformedCells_cli --homogenize: periodic conditions on the undeformed cell, nodes moved by
+// x -> J (x - centre) (J row-major dim x dim, NULL = identity), then homogenizedElasticityTensorDisplacementForm of
+// the given fluctuation displacements w[flat][numNodes][dim] over |bbox| det J.  Also returns the neumann-free
+// constant-strain bookkeeping the CLI relies on: dofForNode is unchanged by the deformation (checked).
+int mfemhost_deformed_displacement_form(void *m, int deg, const double *Dflat, const double *J, const double *w, double *EhOut,
+                                        double *deformedNodes) {
+    auto *hm = static_cast<HostMesh *>(m);
+    try {
+        auto run = [&](auto simTag) {
+            typedef typename decltype(simTag)::type Sim;
+            constexpr size_t N = Sim::N, F = flatLen(N);
+            Sim sim(hm->elements, hm->vertices, -1);
+            typename Sim::ETensor E;
+            E.setFlat(Dflat);
+            sim.setMaterial(E);
+            const auto bbox = sim.mesh().boundingBox();
+            const auto center = bbox.center();
+            sim.applyPeriodicConditions();
+            sim.applyNoRigidMotionConstraint();
+            sim.setUsePinNoRigidTranslationConstraint(true);
+            std::vector<size_t> dofBefore(sim.mesh().numNodes());
+            for (size_t n = 0; n < dofBefore.size(); ++n) dofBefore[n] = sim.DoF(n);
+            Real det = 1.0;
+            if (J) {
+                std::vector<MeshIO::IOVertex> deformed;
+                for (size_t v = 0; v < sim.mesh().numVertices(); ++v) {
+                    MeshIO::IOVertex d;
+                    const auto p = sim.mesh().nodePosition(v);
+                    for (size_t i = 0; i < N; ++i) { Real acc = 0.0; for (size_t j = 0; j < N; ++j) acc += J[i * N + j] * (p[j] - center[j]); d[i] = acc; }
+                    deformed.push_back(d);
+                }
+                sim.updateMeshNodePositions(deformed);
+                det = (N == 2) ? J[0] * J[3] - J[1] * J[2]
+                               : J[0] * (J[4] * J[8 % (N * N)] - J[5] * J[7 % (N * N)]) - J[1] * (J[3] * J[8 % (N * N)] - J[5] * J[6 % (N * N)]) +
+                                 J[2] * (J[3] * J[7 % (N * N)] - J[4] * J[6 % (N * N)]);
+            }
+            for (size_t n = 0; n < dofBefore.size(); ++n) if (sim.DoF(n) != dofBefore[n]) throw std::runtime_error("periodic DoFs changed under deformation");
+            std::vector<typename Sim::VField> w_ij;
+            const size_t nn = sim.mesh().numNodes();
+            for (size_t i = 0; i < F; ++i) {
+                typename Sim::VField wi(nn);
+                std::copy(w + i * nn * N, w + (i + 1) * nn * N, wi.data().begin());
+                w_ij.push_back(wi);
+            }
+            PeriodicHomogenization::homogenizedElasticityTensorDisplacementForm(w_ij, sim, bbox.volume() * det).getFlat(EhOut);
+            if (deformedNodes) std::copy(sim.mesh().nodePositions().begin(), sim.mesh().nodePositions().end(), deformedNodes);
         };
         if (hm->dim == 3 && deg == 1) run(TypeTag<LinearElasticity::Simulator<LinearElasticity::Mesh<3, 1>>>());
         else if (hm->dim == 3 && deg == 2) run(TypeTag<LinearElasticity::Simulator<LinearElasticity::Mesh<3, 2>>>());

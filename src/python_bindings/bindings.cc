@@ -104,6 +104,13 @@ static void bindTensors(py::module &m) {
         .def("inverse", &ETensor::inverse)
         .def("pseudoinverse", &ETensor::inverse)
         .def("frobeniusNormSq", &ETensor::frobeniusNormSq)
+        .def("quadrupleContract", [](const ETensor &E, const ETensor &other) { return E.quadrupleContract(other); }, py::arg("E"))
+        .def("transform", [](const ETensor &E, const NpArr &R) {
+            if (R.ndim() != 2 || (size_t)R.shape(0) != N || (size_t)R.shape(1) != N) throw std::runtime_error("transform: R must be N x N");
+            Real M[N][N];
+            auto r = R.template unchecked<2>();
+            for (size_t i = 0; i < N; ++i) for (size_t j = 0; j < N; ++j) M[i][j] = r(i, j);
+            return E.transform(M); }, py::arg("R"), "Apply a *orthogonal* change of coordinates to this tensor")
         .def("__sub__", [](const ETensor &a, const ETensor &b) { ETensor r = b; r *= -1.0; r += a; return r; })
         .def("__repr__", [](const ETensor &E) {
             std::stringstream ss;

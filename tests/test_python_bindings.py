@@ -43,6 +43,16 @@ def test_tensors_module(pymods, tmp_path):
     assert np.allclose(E.doubleContract(ed.eigenstrains[:, k]), ed.eigenvalues[k] * ed.eigenstrains[:, k], rtol=1e-9, atol=1e-9)
     assert np.allclose(E.inverse().D, np.linalg.inv(D) / np.outer(dbl, dbl), rtol=1e-12)
     assert (E - E).frobeniusNormSq() == 0
+    # frobeniusNormSq = full rank-4 contraction (ElasticityTensor.hh:498-508); transform (:515-541)
+    assert np.isclose(E.frobeniusNormSq(), orc.frobenius_norm_sq(3, D), rtol=1e-14)
+    assert np.isclose(E.quadrupleContract(E.inverse()), (orc.tensor_C(3, D) * orc.tensor_C(3, E.inverse().D)).sum(), rtol=1e-12)
+    R = np.array([[1.1, 0.2, 0.0], [0.05, 0.9, 0.1], [0.0, 0.15, 1.05]])
+    assert np.allclose(E.transform(R).D, orc.transform_tensor(3, D, R), rtol=1e-13, atol=1e-12)
+    th = 0.3
+    Q = np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1.0]])
+    Eiso = tensors.ElasticityTensor3D(200.0, 0.35)
+    assert np.allclose(Eiso.transform(Q).D, Eiso.D, atol=1e-12)          # isotropic tensors are rotation invariant
+    assert np.isclose(E.transform(Q).frobeniusNormSq(), E.frobeniusNormSq(), rtol=1e-13)
     mat = tmp_path / "m.material"
     mat.write_text('{"type": "isotropic_material", "dim": 2, "young": 10.0, "poisson": 0.25}')
     E2 = tensors.ElasticityTensor2D(str(mat))
