@@ -17,8 +17,11 @@
 #include <MeshFEM/JSON.hh>
 #include <MeshFEM/Types.hh>
 
+#include <algorithm>
+#include <array>
 #include <bitset>
 #include <fstream>
+#include <iostream>
 #include <limits>
 #include <map>
 #include <memory>
@@ -456,16 +459,74 @@ void match(const std::vector<VectorND<N>> &bdryPoints, const BBox<VectorND<N>> &
         if (nodeSetForNode[i] == NONE) throw std::runtime_error("Unmatched non-minimal boundary node " + std::to_string(i));
 }
 
+// PeriodicBoundaryMatcher::matchPermittingMismatch (:268-372): for regular voxel grids whose opposite faces do not
+// carry the same nodes.  Per axis, every max-face node is paired with the min-face node at its projected position
+// if there is one; the identified node sets are the connected components of that pairing graph, created in
+// boundary-node order.  Unpaired face memberships are counted and reported, not errors.
+template <size_t N>
+void matchPermittingMismatch(const std::vector<VectorND<N>> &bdryPoints, const BBox<VectorND<N>> &cell,
+                             const std::vector<FaceMembership<N>> &faceMembership, std::vector<std::vector<size_t>> &nodeSets,
+                             std::vector<size_t> &nodeSetForNode, Real epsilon = 1e-7) {
+    const size_t numBdryPts = bdryPoints.size();
+    std::vector<std::array<size_t, N>> pair(numBdryPts);
+    for (auto &p : pair) p.fill(NONE);
+    for (size_t d = 0; d < N; ++d) {
+        CollisionGrid<N> cgrid(std::max(epsilon, 1.0e-7));
+        for (size_t i = 0; i < numBdryPts; ++i)
+            if (faceMembership[i].onMinFace(d)) cgrid.addPoint(bdryPoints[i], i);
+        for (size_t i = 0; i < numBdryPts; ++i) {
+            if (!faceMembership[i].onMaxFace(d)) continue;
+            auto query = bdryPoints[i];
+            query[d] = cell.minCorner[d];
+            const auto result = cgrid.getClosestPoint(query, epsilon);
+            if (result.first < 0) continue;                     // mismatch
+            const size_t pi = (size_t)result.first;
+            if (pair[i][d] != NONE || pair[pi][d] != NONE) throw std::runtime_error("Non-bijective boundary matching");
+            pair[i][d] = pi;
+            pair[pi][d] = i;
+        }
+    }
+    nodeSetForNode.assign(numBdryPts, NONE);
+    nodeSets.clear();
+    size_t numMismatches = 0;
+    std::vector<size_t> queue;
+    for (size_t i = 0; i < numBdryPts; ++i) {
+        if (nodeSetForNode[i] != NONE) continue;
+        const size_t nsi = nodeSets.size();
+        nodeSetForNode[i] = nsi;
+        nodeSets.emplace_back(1, i);
+        queue.assign(1, i);
+        for (size_t head = 0; head < queue.size(); ++head) {
+            const size_t u = queue[head];
+            for (size_t d = 0; d < N; ++d) {
+                if (!faceMembership[u].onMinOrMaxFace(d)) continue;
+                const size_t v = pair[u][d];
+                if (v == NONE) { ++numMismatches; continue; }
+                if (nodeSetForNode[v] != NONE) {
+                    if (nodeSetForNode[v] != nsi) throw std::runtime_error("node set conflict in periodic matching");
+                    continue;
+                }
+                nodeSetForNode[v] = nsi;
+                nodeSets[nsi].push_back(v);
+                queue.push_back(v);
+            }
+        }
+    }
+    if (numMismatches > 0)
+        std::cerr << "WARNING: detected " << numMismatches << " mismatches in periodic node identification" << std::endl;
+}
+
 }  // namespace PeriodicBoundaryMatcher
 
 template <size_t _N>
 class PeriodicCondition {
 public:
     static constexpr size_t NO_DOF = std::numeric_limits<size_t>::max();
+    // ignoreDims: axes along which the cell is NOT periodic (BoundaryConditions.hh:457-505 of the reference)
     template <typename Mesh>
-    PeriodicCondition(const Mesh &mesh, Real epsilon = 1e-7, bool ignoreMismatch = false) {
+    PeriodicCondition(const Mesh &mesh, Real epsilon = 1e-7, bool ignoreMismatch = false,
+                      const std::vector<size_t> &ignoreDims = std::vector<size_t>()) : m_ignoreDims(ignoreDims) {
         using namespace PeriodicBoundaryMatcher;
-        if (ignoreMismatch) throw std::runtime_error("ignoreMismatch periodic matching is not supported by this build");
         const BBox<VectorND<_N>> cell = mesh.boundingBox();
         std::vector<VectorND<_N>> bdryPts;
         bdryPts.reserve(mesh.numBoundaryNodes());
@@ -473,9 +534,24 @@ public:
         std::vector<FaceMembership<_N>> fm;
         fm.reserve(bdryPts.size());
         for (const auto &p : bdryPts) fm.emplace_back(p, cell, epsilon);
+        if (!ignoreDims.empty()) {
+            // nodes on a periodic face lose their membership of the ignored faces; all others lose every membership
+            std::vector<size_t> periodicDims;
+            for (size_t d = 0; d < _N; ++d)
+                if (std::find(ignoreDims.begin(), ignoreDims.end(), d) == ignoreDims.end()) periodicDims.push_back(d);
+            for (auto &m : fm) {
+                bool onSignificantDim = false;
+                for (size_t d : periodicDims) onSignificantDim = onSignificantDim || m.onMinOrMaxFace(d);
+                for (size_t d = 0; d < _N; ++d) {
+                    const bool ignored = std::find(ignoreDims.begin(), ignoreDims.end(), d) != ignoreDims.end();
+                    if (!onSignificantDim || ignored) { m.membership[d] = false; m.membership[d + _N] = false; }
+                }
+            }
+        }
         std::vector<std::vector<size_t>> bdryNodeSets;
         std::vector<size_t> bdryNodeSetForBdryNode;
-        match<_N>(bdryPts, cell, fm, bdryNodeSets, bdryNodeSetForBdryNode, epsilon);
+        if (ignoreMismatch) matchPermittingMismatch<_N>(bdryPts, cell, fm, bdryNodeSets, bdryNodeSetForBdryNode, epsilon);
+        else match<_N>(bdryPts, cell, fm, bdryNodeSets, bdryNodeSetForBdryNode, epsilon);
 
         // boundary elements whose nodes all share one cell face (determineCellFaceBoundaryElements :126-146)
         m_isPeriodicBoundaryElement.assign(mesh.numBoundaryElements(), false);
@@ -505,6 +581,43 @@ public:
             }
         }
     }
+    // Identified node pairs read from a file, one "a b" pair of volume node indices per line (:563-610; the
+    // reference calls this format a temporary hack): DoFs are the connected components of the pair graph, in order
+    // of their lowest node.  No boundary element is marked periodic.
+    template <typename Mesh>
+    PeriodicCondition(const Mesh &mesh, const std::string &pcFile) {
+        std::cerr << "WARNING: periodic boundary condition files are a temporary hack." << std::endl;
+        std::ifstream file(pcFile);
+        if (!file.is_open()) throw std::runtime_error("Couldn't open " + pcFile);
+        std::vector<std::vector<size_t>> adj(mesh.numNodes());
+        std::string line;
+        while (std::getline(file, line)) {
+            std::istringstream ls(line);
+            size_t a, b;
+            if (!(ls >> a >> b)) continue;
+            if (a >= mesh.numNodes() || b >= mesh.numNodes()) throw std::runtime_error("Periodic pair node index out of bounds in " + pcFile);
+            adj[a].push_back(b);
+            adj[b].push_back(a);
+        }
+        m_dofForNode.assign(mesh.numNodes(), NO_DOF);
+        m_nodesForDoF.clear();
+        std::vector<size_t> queue;
+        for (size_t n = 0; n < mesh.numNodes(); ++n) {
+            if (m_dofForNode[n] != NO_DOF) continue;
+            const size_t dof = m_nodesForDoF.size();
+            m_dofForNode[n] = dof;
+            queue.assign(1, n);
+            for (size_t head = 0; head < queue.size(); ++head)
+                for (size_t v : adj[queue[head]]) {
+                    if (m_dofForNode[v] != NO_DOF) continue;
+                    m_dofForNode[v] = dof;
+                    queue.push_back(v);
+                }
+            m_nodesForDoF.push_back(queue);
+        }
+        m_isPeriodicBoundaryElement.assign(mesh.numBoundaryElements(), false);
+    }
+    const std::vector<size_t> &getIgnoreDims() const { return m_ignoreDims; }
     const std::vector<size_t> &periodicDoFsForNodes() const { return m_dofForNode; }
     size_t numPeriodicDoFs() const { return m_nodesForDoF.size(); }
     bool isPeriodicBE(size_t be) const { return m_isPeriodicBoundaryElement.at(be); }
@@ -515,5 +628,6 @@ private:
     std::vector<size_t> m_dofForNode;
     std::vector<std::vector<size_t>> m_nodesForDoF;
     std::vector<bool> m_isPeriodicBoundaryElement;
+    std::vector<size_t> m_ignoreDims;
 };
 #endif

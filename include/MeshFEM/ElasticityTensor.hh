@@ -35,6 +35,47 @@ inline void invertInPlace(Real (&A)[F][F]) {
 }
 }  // namespace tensor_detail
 
+// Rank-4 tensor with the minor symmetries only, stored as the full flattened F x F matrix
+// (ElasticityTensor<Real, Dim, false> of the reference): results of tensor : tensor contractions.
+template <typename _Real, size_t _Dim>
+struct MinorSymmetricTensor {
+    static constexpr size_t F = flatLen(_Dim);
+    _Real d[F][F];
+    MinorSymmetricTensor() { for (auto &r : d) for (auto &x : r) x = 0; }
+    _Real operator()(size_t i, size_t j, size_t k, size_t l) const { return d[flattenIndices<_Dim>(i, j)][flattenIndices<_Dim>(k, l)]; }
+    _Real D(size_t i, size_t j) const { return d[i][j]; }
+    _Real &D(size_t i, size_t j) { return d[i][j]; }
+    // F(A : B) = F(A) S F(B), S = shear doubler (ElasticityTensor.hh:483-495)
+    template <class Other>
+    MinorSymmetricTensor doubleContract(const Other &B) const {
+        MinorSymmetricTensor r;
+        for (size_t i = 0; i < F; ++i) for (size_t j = 0; j < F; ++j) {
+            _Real s = 0;
+            for (size_t k = 0; k < F; ++k) s += d[i][k] * (k >= _Dim ? 2.0 : 1.0) * B.D(k, j);
+            r.d[i][j] = s;
+        }
+        return r;
+    }
+    // Mathematica array syntax (:613-633)
+    void writeUnflattened(std::ostream &os) const {
+        os << "{";
+        for (size_t i = 0; i < _Dim; ++i) {
+            os << "{";
+            for (size_t j = 0; j < _Dim; ++j) {
+                os << "{";
+                for (size_t k = 0; k < _Dim; ++k) {
+                    os << "{";
+                    for (size_t l = 0; l < _Dim; ++l) { os << (*this)(i, j, k, l); if (l < _Dim - 1) os << ", "; }
+                    os << ((k < _Dim - 1) ? "}, " : "}");
+                }
+                os << ((j < _Dim - 1) ? "}, " : "}");
+            }
+            os << ((i < _Dim - 1) ? "}, " : "}");
+        }
+        os << "}";
+    }
+};
+
 template <typename _Real, size_t _Dim>
 class ElasticityTensor {
 public:
@@ -95,6 +136,17 @@ public:
             out[i] = s;
         }
         return out;
+    }
+    // A : B for two rank-4 tensors; the result has no major symmetry in general (:483-495)
+    template <class Other>
+    MinorSymmetricTensor<_Real, _Dim> doubleContractTensor(const Other &B) const {
+        MinorSymmetricTensor<_Real, _Dim> r;
+        for (size_t i = 0; i < F; ++i) for (size_t j = 0; j < F; ++j) {
+            _Real s = 0;
+            for (size_t k = 0; k < F; ++k) s += D(i, k) * (k >= _Dim ? 2.0 : 1.0) * B.D(k, j);
+            r.d[i][j] = s;
+        }
+        return r;
     }
     // E^-1 with E : E^-1 = identity: invert D, then halve shear rows and columns (:315-323)
     ElasticityTensor inverse() const {

@@ -92,5 +92,23 @@ typename _Sim::ETensor homogenizedElasticityTensorDisplacementForm(const std::ve
     return Eh;
 }
 
+// Macroscopic-strain-to-microscopic-strain tensors (:188-210): G_ijkl = [avg_e strain(w^kl) + e^kl]_ij, one
+// (minor-symmetric only) tensor per element; column kl of the flattened matrix is that average strain.
+template <class _Sim>
+std::vector<MinorSymmetricTensor<Real, _Sim::N>> macroStrainToMicroStrainTensors(const std::vector<typename _Sim::VField> &w, const _Sim &sim) {
+    constexpr size_t N = _Sim::N, F = flatLen(N);
+    const size_t numElems = sim.mesh().numElements();
+    std::vector<MinorSymmetricTensor<Real, N>> G(numElems);
+    for (size_t ij = 0; ij < w.size(); ++ij) {
+        const auto strain = sim.averageStrainField(w[ij]);
+        const auto eij = _Sim::SMatrix::CanonicalBasis(ij);
+        for (size_t e = 0; e < numElems; ++e) {
+            const auto se = strain(e);
+            for (size_t r = 0; r < F; ++r) G[e].d[r][ij] = se[r] + eij[r];
+        }
+    }
+    return G;
+}
+
 }  // namespace PeriodicHomogenization
 #endif

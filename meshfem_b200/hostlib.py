@@ -147,6 +147,22 @@ class RawMesh:
             raise _err(self.lib)
         return Eh, nodes
 
+    def periodic_condition(self, deg, eps=1e-7, ignore_mismatch=False, ignore_dims=(), pairs_file=None):
+        """PeriodicCondition of the reference: (dof_for_node, num_dofs, is_periodic_be)."""
+        fm = self.femmesh(deg)
+        dof = np.zeros(fm.num_nodes, dtype=np.int64)
+        ibe = np.zeros(fm.bdry_elem_nodes.shape[0], dtype=np.uint8)
+        nd = c_int64()
+        ig = np.ascontiguousarray(ignore_dims, dtype=np.int64)
+        self.lib.mfemhost_periodic_condition.argtypes = [c_void_p, c_int, c_double, c_int, c_int, POINTER(c_int64), c_char_p,
+                                                         POINTER(c_int64), POINTER(ctypes.c_uint8), POINTER(c_int64)]
+        if self.lib.mfemhost_periodic_condition(self._p, deg, eps, 1 if ignore_mismatch else 0, ig.size, ig.ctypes.data_as(POINTER(c_int64)),
+                                                None if pairs_file is None else os.fsencode(pairs_file),
+                                                dof.ctypes.data_as(POINTER(c_int64)), ibe.ctypes.data_as(POINTER(ctypes.c_uint8)),
+                                                ctypes.byref(nd)) != 0:
+            raise _err(self.lib)
+        return dof, int(nd.value), ibe.astype(bool)
+
     def femmesh(self, deg):
         """FEMMesh<dim,deg> flat data with the reference's numbering."""
         sz = (c_int64 * 5)()
@@ -348,3 +364,19 @@ def constrained_solve(rows, rows_rhs, fixed_vars, rigid_modes, fs, spsd_solve):
             raise failure[0]
         raise _err(lib)
     return us, lam
+
+
+def m2m_tensor(dim, E, G, S):
+    """E : G : S for flattened rank-4 tensors (G without major symmetry) as PeriodicHomogenization_cli --m2mstress
+    computes and prints it: (flattened result, Mathematica-array text)."""
+    lib = load_library()
+    F = dim * (dim + 1) // 2
+    dp = POINTER(c_double)
+    a = [np.ascontiguousarray(x, dtype=np.float64).reshape(F, F) for x in (E, G, S)]
+    out = np.zeros((F, F))
+    text = ctypes.create_string_buffer(1 << 14)
+    lib.mfemhost_m2m_tensor.argtypes = [c_int, dp, dp, dp, dp, ctypes.c_char_p, c_int]
+    if lib.mfemhost_m2m_tensor(dim, a[0].ctypes.data_as(dp), a[1].ctypes.data_as(dp), a[2].ctypes.data_as(dp), out.ctypes.data_as(dp),
+                               text, len(text)) != 0:
+        raise _err(lib)
+    return out, text.value.decode()

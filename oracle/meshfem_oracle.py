@@ -1318,24 +1318,19 @@ def simulate(N, deg, vertices, simplices, D, bc_params):
 # Periodic conditions (PeriodicBoundaryMatcher.hh:38-258, BoundaryConditions.hh:457-561)
 # and periodic homogenization (PeriodicHomogenization.hh:34-186)
 # ----------------------------------------------------------------------------
-def periodic_condition(mesh, eps=1e-7):
-    """Returns (dof_for_node, num_dofs, is_periodic_be)."""
-    N = mesh.N
-    bn = mesh.bdry_nodes
-    P = mesh.nodes[bn]
-    lo, hi = mesh.bbox_min, mesh.bbox_max
-    on_min = np.abs(P - lo) <= eps              # FaceMembership (:44-50)
-    on_max = np.abs(P - hi) <= eps
+def _match_periodic(P, lo, hi, on_min, on_max, eps):
+    """PeriodicBoundaryMatcher::match (:149-258): one node set per minimal node, 2^(#faces) identified copies."""
+    N = P.shape[1]
     minimal = ~on_max.any(axis=1)
-    # hashed lookup of the non-minimal points (CollisionGrid, cell size max(eps, 1e-7))
+
     def find(q):
         d = np.linalg.norm(P - q, axis=1)
         d[minimal] = np.inf
         j = int(np.argmin(d))
         return j if d[j] <= eps else -1
-    node_set_for = np.full(bn.size, -1, dtype=np.int64)
+    node_set_for = np.full(P.shape[0], -1, dtype=np.int64)
     node_sets = []
-    for i in range(bn.size):
+    for i in range(P.shape[0]):
         if not minimal[i]:
             continue
         node_set_for[i] = len(node_sets)
@@ -1356,6 +1351,76 @@ def periodic_condition(mesh, eps=1e-7):
         node_sets.append(ns)
     if (node_set_for < 0).any():
         raise RuntimeError("Unmatched non-minimal boundary node")
+    return node_sets, node_set_for
+
+
+def _match_periodic_permitting_mismatch(P, lo, hi, on_min, on_max, eps):
+    """PeriodicBoundaryMatcher::matchPermittingMismatch (:268-372): per-axis pairing of max-face nodes with the
+    min-face node at the projected position (if any); node sets = connected components in boundary-node order.
+    Returns (node_sets, node_set_for, num_mismatches)."""
+    nb, N = P.shape
+    pair = np.full((nb, N), -1, dtype=np.int64)
+    for d in range(N):
+        cand = np.nonzero(on_min[:, d])[0]
+        for i in np.nonzero(on_max[:, d])[0]:
+            if cand.size == 0:
+                continue
+            q = P[i].copy(); q[d] = lo[d]
+            dist = np.linalg.norm(P[cand] - q, axis=1)
+            j = int(np.argmin(dist))
+            if dist[j] > eps:
+                continue
+            pi = int(cand[j])
+            if pair[i, d] != -1 or pair[pi, d] != -1:
+                raise RuntimeError("Non-bijective boundary matching")
+            pair[i, d] = pi; pair[pi, d] = i
+    node_set_for = np.full(nb, -1, dtype=np.int64)
+    node_sets = []
+    mismatches = 0
+    for i in range(nb):
+        if node_set_for[i] != -1:
+            continue
+        nsi = len(node_sets)
+        node_set_for[i] = nsi
+        ns = [i]
+        head = 0
+        while head < len(ns):
+            u = ns[head]; head += 1
+            for d in range(N):
+                if not (on_min[u, d] or on_max[u, d]):
+                    continue
+                v = pair[u, d]
+                if v == -1:
+                    mismatches += 1
+                    continue
+                if node_set_for[v] != -1:
+                    assert node_set_for[v] == nsi
+                    continue
+                node_set_for[v] = nsi
+                ns.append(int(v))
+        node_sets.append(ns)
+    return node_sets, node_set_for, mismatches
+
+
+def periodic_condition(mesh, eps=1e-7, ignore_mismatch=False, ignore_dims=()):
+    """PeriodicCondition (BoundaryConditions.hh:457-561).  Returns (dof_for_node, num_dofs, is_periodic_be)."""
+    N = mesh.N
+    bn = mesh.bdry_nodes
+    P = mesh.nodes[bn]
+    lo, hi = mesh.bbox_min, mesh.bbox_max
+    on_min = np.abs(P - lo) <= eps              # FaceMembership (:44-50)
+    on_max = np.abs(P - hi) <= eps
+    if len(ignore_dims):
+        # nodes on a periodic face lose the ignored faces; every other node loses all memberships (:472-500)
+        periodic_dims = [d for d in range(N) if d not in ignore_dims]
+        significant = (on_min[:, periodic_dims] | on_max[:, periodic_dims]).any(axis=1)
+        for d in range(N):
+            drop = ~significant if d not in ignore_dims else np.ones(bn.size, bool)
+            on_min[drop, d] = False; on_max[drop, d] = False
+    if ignore_mismatch:
+        node_sets, node_set_for, _ = _match_periodic_permitting_mismatch(P, lo, hi, on_min, on_max, eps)
+    else:
+        node_sets, node_set_for = _match_periodic(P, lo, hi, on_min, on_max, eps)
     # boundary elements with all nodes on one common cell face (:126-146)
     memb = np.concatenate([on_min, on_max], axis=1)
     bnode = mesh.bdry_node_of_node[mesh.bdry_elem_nodes]
@@ -1377,6 +1442,30 @@ def periodic_condition(mesh, eps=1e-7):
             dof[n] = nd
         nd += 1
     return dof, nd, is_periodic_be
+
+
+def periodic_condition_from_pairs(mesh, pairs):
+    """PeriodicCondition(mesh, pcFile) (:563-610): DoFs = connected components of the identified-pair graph, numbered
+    by their lowest node; no boundary element is marked periodic."""
+    adj = [[] for _ in range(mesh.num_nodes)]
+    for a, b in pairs:
+        adj[a].append(b); adj[b].append(a)
+    dof = np.full(mesh.num_nodes, -1, dtype=np.int64)
+    nd = 0
+    for n in range(mesh.num_nodes):
+        if dof[n] >= 0:
+            continue
+        dof[n] = nd
+        queue = [n]
+        head = 0
+        while head < len(queue):
+            for v in adj[queue[head]]:
+                if dof[v] < 0:
+                    dof[v] = nd
+                    queue.append(v)
+            head += 1
+        nd += 1
+    return dof, nd, np.zeros(mesh.bdry_elem_nodes.shape[0], dtype=bool)
 
 
 def canonical_basis(N, i):
@@ -1507,6 +1596,39 @@ def deformed_cell_homogenization(N, deg, vertices, simplices, D, jacobian, trans
     for i in range(flat_len(N)):
         w.append(sim.solve(sim.constant_strain_load(-canonical_basis(N, i))))
     return homogenized_tensor_displacement_form(sim, w, bbox_volume * float(np.linalg.det(J))), w, sim
+
+
+def macro_to_micro_strain_tensors(sim, w_ij):
+    """macroStrainToMicroStrainTensors (PeriodicHomogenization.hh:188-210): per element the flattened (F x F, no major
+    symmetry) tensor whose column kl is avg strain(w_kl) + e_kl."""
+    N = sim.N; F = flat_len(N)
+    G = np.zeros((sim.mesh.num_elements, F, F))
+    for kl, w in enumerate(w_ij):
+        strain, _ = average_strain_stress(sim.mesh, sim.D, w)
+        G[:, :, kl] = strain + canonical_basis(N, kl)[None, :]
+    return G
+
+
+def macro_to_micro_stress_tensors(sim, w_ij, Eh):
+    """PeriodicHomogenization_cli --m2mstress (:173-186): E : G_e : Eh^-1 with F(A : B) = F(A) S F(B), S the shear
+    doubler (ElasticityTensor.hh:483-495).  Returns the flattened (numElements, F, F) tensors."""
+    N = sim.N
+    dbl = np.ones(flat_len(N)); dbl[N:] = 2.0
+    Sh = np.linalg.inv(Eh) / np.outer(dbl, dbl)           # ElasticityTensor::inverse (:315-323)
+    G = macro_to_micro_strain_tensors(sim, w_ij)
+    GS = np.einsum("eik,k,kj->eij", G, dbl, Sh)
+    return np.einsum("ik,k,ekj->eij", sim.D, dbl, GS)
+
+
+def unflatten_rank4(N, Mflat):
+    """(i,j,k,l) array of a flattened rank-4 tensor with the minor symmetries."""
+    out = np.zeros((N,) * 4)
+    for i in range(N):
+        for j in range(N):
+            for k in range(N):
+                for l in range(N):
+                    out[i, j, k, l] = Mflat[flatten_indices(N, i, j), flatten_indices(N, k, l)]
+    return out
 
 
 def read_msh(path):

@@ -5,7 +5,6 @@
 // A macroscopic STRESS probe (-S) is converted with the homogenized compliance.  Fields written:
 // "w_ij k" (with -f), "u_cstrain", "f_cstrain" = K u (with -l), "stress" (element averages).
 // The cell problems, K u and the stress field run on the GPU through libmfem_b200.
-// Not supported: --manualPeriodicVertices.
 #include <MeshFEM/CmdLine.hh>
 #include <MeshFEM/LinearElasticity.hh>
 #include <MeshFEM/MSHFieldWriter.hh>
@@ -75,9 +74,10 @@ void execute(const CmdLine &args, const vector<MeshIO::IOVertex> &inVertices, co
     if (args.count("material")) mat.setFromFile(args.str("material"));
     typedef LinearElasticity::Simulator<LinearElasticity::Mesh<_N, _FEMDegree>> Simulator;
     typedef typename Simulator::VField VField;
-    if (args.count("manualPeriodicVertices")) throw std::runtime_error("--manualPeriodicVertices is not supported by this build");
     Simulator sim(inElements, inVertices, args.integer("device"));
     sim.setMaterial(mat.getTensor());
+    std::unique_ptr<PeriodicCondition<_N>> pc;
+    if (args.count("manualPeriodicVertices")) pc.reset(new PeriodicCondition<_N>(sim.mesh(), args.str("manualPeriodicVertices")));
     sim.setSolverTolerance(std::stod(args.str("rtol")));
     const auto &mesh = sim.mesh();
     MSHFieldWriter writer(args.str("outMesh"), mesh);
@@ -96,7 +96,7 @@ void execute(const CmdLine &args, const vector<MeshIO::IOVertex> &inVertices, co
     std::vector<VField> w_ij;
     const bool ortho = args.count("orthotropicCell") != 0;
     auto doCellProblemSolve = [&]() {
-        if (!ortho) solveCellProblems(w_ij, sim, 1e-7);
+        if (!ortho) solveCellProblems(w_ij, sim, 1e-7, false, std::move(pc));
         else PeriodicHomogenization::Orthotropic::solveCellProblems(w_ij, sim, 1e-7);
     };
     auto getHomogenizedTensor = [&]() {

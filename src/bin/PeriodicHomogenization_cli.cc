@@ -5,8 +5,7 @@
 //   compliance, approximate moduli / Poisson ratios, anisotropy -> optional field output.
 // The assembly and the solves run on the GPU through libmfem_b200 (no CPU fallback).
 //
-// Differences from the reference, all outside the hot path: --m2mstress and --manualPeriodicVertices
-// belong to SURVEY 8(f) "next" rows and are rejected with a message; extra options --device / --rtol / --maxIters control the PCG.
+// Differences from the reference, all outside the hot path: extra options --device / --rtol / --maxIters control the PCG.
 #include <MeshFEM/CmdLine.hh>
 #include <MeshFEM/GlobalBenchmark.hh>
 #include <MeshFEM/LinearElasticity.hh>
@@ -18,6 +17,7 @@
 #include <MeshFEM/TensorProjection.hh>
 
 #include <cstdlib>
+#include <fstream>
 #include <iomanip>
 #include <iostream>
 #include <vector>
@@ -84,13 +84,13 @@ void execute(const CmdLine &args, const vector<MeshIO::IOVertex> &inVertices, co
     typedef typename Simulator::ETensor ETensor;
     typedef typename Simulator::VField VField;
 
-    for (const char *unsupported : {"m2mstress", "manualPeriodicVertices"})
-        if (args.count(unsupported)) throw std::runtime_error(std::string("--") + unsupported + " is not supported by this build (SURVEY 8(f) next row)");
+    std::unique_ptr<PeriodicCondition<_N>> pc;
+    if (args.count("manualPeriodicVertices")) pc.reset(new PeriodicCondition<_N>(sim.mesh(), args.str("manualPeriodicVertices")));
 
     BENCHMARK_START_TIMER_SECTION("Cell Problems");
     std::vector<VField> w_ij;
     const bool orthotropicCell = args.count("orthotropicCell") != 0;
-    if (!orthotropicCell) solveCellProblems(w_ij, sim, 1e-7, args.count("ignorePeriodicMismatch") != 0);
+    if (!orthotropicCell) solveCellProblems(w_ij, sim, 1e-7, args.count("ignorePeriodicMismatch") != 0, std::move(pc));
     else PeriodicHomogenization::Orthotropic::solveCellProblems(w_ij, sim, 1e-7);
     BENCHMARK_STOP_TIMER_SECTION("Cell Problems");
 
@@ -134,6 +134,23 @@ void execute(const CmdLine &args, const vector<MeshIO::IOVertex> &inVertices, co
         cout << "v_xy, v_xz, v_yz:\t" << poisson[3] << "\t" << poisson[4] << "\t" << poisson[5] << endl;
     }
     cout << "Anisotropy:\t" << Eh.anisotropy() << endl;
+
+    if (args.count("m2mstress")) {
+        // macroscopic-to-microscopic stress tensors E : G_e : Eh^-1 per element, and the G_e in gtensors.txt (:173-186)
+        const string mpath = args.str("m2mstress");
+        ofstream mfile(mpath);
+        ofstream gfile("gtensors.txt");
+        mfile << setprecision(16);
+        gfile << setprecision(16);
+        if (!mfile.is_open()) throw runtime_error("Failed to open output file " + mpath);
+        const auto G = macroStrainToMicroStrainTensors(w_ij, sim);
+        for (size_t ei = 0; ei < sim.mesh().numElements(); ++ei) {
+            G[ei].writeUnflattened(gfile);
+            gfile << endl;
+            sim.elementTensor(ei).doubleContractTensor(G[ei].doubleContract(S)).writeUnflattened(mfile);
+            mfile << endl;
+        }
+    }
 
     if (args.count("fieldOutput")) {
         const bool linearSubsampleFields = args.count("fullDegreeFieldOutput") == 0;

@@ -477,6 +477,55 @@ int mfemhost_deformed_displacement_form(void *m, int deg, const double *Dflat, c
     } catch (const std::exception &e) { g_err = e.what(); return -1; }
 }
 
+// PeriodicCondition variants (BoundaryConditions.hh:457-610 of the reference): geometric matching with optional
+// mismatch tolerance and non-periodic axes, or identified pairs read from a file (pcFile != NULL).
+// out: dofForNode[numNodes], isPeriodicBE[numBoundaryElements]; returns numDoFs through numDofs.
+int mfemhost_periodic_condition(void *m, int deg, double eps, int ignoreMismatch, int nIgnoreDims, const int64_t *ignoreDims,
+                                const char *pcFile, int64_t *dofForNode, uint8_t *isPeriodicBE, int64_t *numDofs) {
+    auto *hm = static_cast<HostMesh *>(m);
+    try {
+        auto run = [&](auto meshTag) {
+            typedef typename decltype(meshTag)::type Mesh;
+            Mesh mesh(hm->elements, hm->vertices);
+            std::unique_ptr<PeriodicCondition<Mesh::K>> pc;
+            if (pcFile) pc.reset(new PeriodicCondition<Mesh::K>(mesh, std::string(pcFile)));
+            else pc.reset(new PeriodicCondition<Mesh::K>(mesh, eps, ignoreMismatch != 0, std::vector<size_t>(ignoreDims, ignoreDims + nIgnoreDims)));
+            const auto &d = pc->periodicDoFsForNodes();
+            for (size_t n = 0; n < d.size(); ++n) dofForNode[n] = (int64_t)d[n];
+            for (size_t be = 0; be < mesh.numBoundaryElements(); ++be) isPeriodicBE[be] = pc->isPeriodicBE(be);
+            *numDofs = (int64_t)pc->numPeriodicDoFs();
+        };
+        if (hm->dim == 3 && deg == 1) run(TypeTag<LinearElasticity::Mesh<3, 1>>());
+        else if (hm->dim == 3 && deg == 2) run(TypeTag<LinearElasticity::Mesh<3, 2>>());
+        else if (hm->dim == 2 && deg == 1) run(TypeTag<LinearElasticity::Mesh<2, 1>>());
+        else if (hm->dim == 2 && deg == 2) run(TypeTag<LinearElasticity::Mesh<2, 2>>());
+        else throw std::runtime_error("bad dim/deg");
+        return 0;
+    } catch (const std::exception &e) { g_err = e.what(); return -1; }
+}
+
+// E : G : S for flattened tensors (what PeriodicHomogenization_cli --m2mstress writes per element), through the
+// same MinorSymmetricTensor / doubleContractTensor code; text = writeUnflattened of the result.
+int mfemhost_m2m_tensor(int dim, const double *Eflat, const double *Gflat, const double *Sflat, double *out, char *text, int textCap) {
+    try {
+        auto run = [&](auto E) {
+            constexpr size_t N = decltype(E)::Dim, F = flatLen(N);
+            decltype(E) S;
+            E.setFlat(Eflat); S.setFlat(Sflat);
+            MinorSymmetricTensor<Real, N> G;
+            for (size_t i = 0; i < F; ++i) for (size_t j = 0; j < F; ++j) G.d[i][j] = Gflat[i * F + j];
+            const auto M = E.doubleContractTensor(G.doubleContract(S));
+            for (size_t i = 0; i < F; ++i) for (size_t j = 0; j < F; ++j) out[i * F + j] = M.d[i][j];
+            std::ostringstream os;
+            os << std::setprecision(16);
+            M.writeUnflattened(os);
+            if (text && textCap > 0) { std::strncpy(text, os.str().c_str(), textCap - 1); text[textCap - 1] = 0; }
+        };
+        if (dim == 3) run(ElasticityTensor<Real, 3>()); else run(ElasticityTensor<Real, 2>());
+        return 0;
+    } catch (const std::exception &e) { g_err = e.what(); return -1; }
+}
+
 int mfemhost_save_mesh(void *m, const char *path) {
     auto *hm = static_cast<HostMesh *>(m);
     try { MeshIO::save(path, hm->vertices, hm->elements); return 0; }

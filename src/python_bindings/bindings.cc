@@ -10,7 +10,6 @@
 //    (vertices [nv x 3|2], elements [ne x (N+1)], degree) instead;
 //  * SPSDSystem takes the block size of K (variables ordered blockDim*DoF + component) and exposes the
 //    PCG controls (setTolerance); C / C_rhs constraint rows are not supported (SPD path only);
-//  * manualPeriodicVerticesFile: SURVEY 8(f) next row, rejected with a message.
 #include <pybind11/numpy.h>
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
@@ -220,8 +219,8 @@ static void toIO(const NpArr &V, const NpIdx &F, std::vector<MeshIO::IOVertex> &
 
 template <size_t N, size_t Deg>
 static HomogenizationResult runHomogenization(const std::vector<MeshIO::IOVertex> &verts, const std::vector<MeshIO::IOElement> &elems,
-                                              const NpArr &Cbase, bool orthotropicCell, bool center, bool ignoreMismatch, int device,
-                                              double rtol) {
+                                              const NpArr &Cbase, bool orthotropicCell, const std::string &manualPeriodicVerticesFile, bool center,
+                                              bool ignoreMismatch, int device, double rtol) {
     typedef LinearElasticity::Simulator<LinearElasticity::Mesh<N, Deg>> Sim;
     constexpr size_t F = flatLen(N);
     Sim sim(elems, verts, device);
@@ -234,7 +233,9 @@ static HomogenizationResult runHomogenization(const std::vector<MeshIO::IOVertex
         PeriodicHomogenization::Orthotropic::solveCellProblems(w_ij, sim);
         r.Ch = tensorD<N>(PeriodicHomogenization::Orthotropic::homogenizedElasticityTensorDisplacementForm(w_ij, sim));
     } else {
-        PeriodicHomogenization::solveCellProblems(w_ij, sim, 1e-7, ignoreMismatch);
+        std::unique_ptr<PeriodicCondition<N>> pc;
+        if (!manualPeriodicVerticesFile.empty()) pc.reset(new PeriodicCondition<N>(sim.mesh(), manualPeriodicVerticesFile));
+        PeriodicHomogenization::solveCellProblems(w_ij, sim, 1e-7, ignoreMismatch, std::move(pc));
         r.Ch = tensorD<N>(PeriodicHomogenization::homogenizedElasticityTensorDisplacementForm(w_ij, sim));
     }
     if (center)
@@ -259,16 +260,15 @@ static HomogenizationResult runHomogenization(const std::vector<MeshIO::IOVertex
 static HomogenizationResult homogenize(const NpArr &V, const NpIdx &F, const NpArr &Cbase, int degree, bool orthotropicCell,
                                        const std::string &manualPeriodicVerticesFile, bool center, bool ignoreMismatch,
                                        int device, double rtol) {
-    if (!manualPeriodicVerticesFile.empty()) throw std::runtime_error("manualPeriodicVerticesFile is not supported by this build");
     std::vector<MeshIO::IOVertex> verts;
     std::vector<MeshIO::IOElement> elems;
     toIO(V, F, verts, elems);
     const bool tet = F.shape(1) == 4;
     if (degree != 1 && degree != 2) throw std::runtime_error("degree must be 1 or 2");
-    if (tet) return degree == 2 ? runHomogenization<3, 2>(verts, elems, Cbase, orthotropicCell, center, ignoreMismatch, device, rtol)
-                                : runHomogenization<3, 1>(verts, elems, Cbase, orthotropicCell, center, ignoreMismatch, device, rtol);
-    return degree == 2 ? runHomogenization<2, 2>(verts, elems, Cbase, orthotropicCell, center, ignoreMismatch, device, rtol)
-                       : runHomogenization<2, 1>(verts, elems, Cbase, orthotropicCell, center, ignoreMismatch, device, rtol);
+    if (tet) return degree == 2 ? runHomogenization<3, 2>(verts, elems, Cbase, orthotropicCell, manualPeriodicVerticesFile, center, ignoreMismatch, device, rtol)
+                                : runHomogenization<3, 1>(verts, elems, Cbase, orthotropicCell, manualPeriodicVerticesFile, center, ignoreMismatch, device, rtol);
+    return degree == 2 ? runHomogenization<2, 2>(verts, elems, Cbase, orthotropicCell, manualPeriodicVerticesFile, center, ignoreMismatch, device, rtol)
+                       : runHomogenization<2, 1>(verts, elems, Cbase, orthotropicCell, manualPeriodicVerticesFile, center, ignoreMismatch, device, rtol);
 }
 
 // getProbeResult (periodic_homogenization.cc:92-143): displacement and strain of the cell under a macroscopic
