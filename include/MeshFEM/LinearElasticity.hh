@@ -20,6 +20,7 @@
 #include <MeshFEM/GlobalBenchmark.hh>
 #include <MeshFEM/Materials.hh>
 #include <MeshFEM/RigidMotionConstraints.hh>
+#include <MeshFEM/ShapeDerivatives.hh>
 #include <MeshFEM/SparseMatrices.hh>
 
 #include <iostream>
@@ -225,6 +226,107 @@ public:
                 load.add(DoF(m_mesh.boundaryElementVolumeNode(be, n)), (w[n] * m_mesh.boundaryElementVolume(be)) * m_beData[be].neumannTraction);
         for (const auto &ndf : m_nodalDeltaFunctionForces) load.add(DoF(ndf.first), ndf.second);
         return load;
+    }
+
+    // ---- discrete shape derivatives (ShapeDerivatives.hh; reference :1286-1373)
+    // (delta K) u: change in the force of the fixed per-NODE field u under the per-vertex perturbation deltaP,
+    // returned per DoF (:1301-1330)
+    VField applyDeltaStiffnessMatrix(const VField &u, const VField &deltaP) const {
+        namespace SD = ShapeDerivatives;
+        if (u.domainSize() != m_mesh.numNodes()) throw std::runtime_error("applyDeltaStiffnessMatrix: per-node displacement expected");
+        if (deltaP.domainSize() != m_mesh.numVertices()) throw std::runtime_error("applyDeltaStiffnessMatrix: per-vertex perturbation expected");
+        constexpr size_t npe = _Mesh::nodesPerElement;
+        const SD::ElementQuadrature<K, Degree> quad;
+        VField load(numDoFs());
+        for (size_t e = 0; e < m_mesh.numElements(); ++e) {
+            Real g[K + 1][K], G[K][K], gphi[npe][K];
+            m_mesh.elementGradLambda(e, g);
+            SD::velocityGradient(m_mesh, e, g, deltaP, G);
+            Real div = 0.0;
+            for (size_t a = 0; a < K; ++a) div += G[a][a];
+            const Real vol = m_mesh.elementVolume(e);
+            const ETensor &E = elementTensor(e);
+            Point f[npe];
+            for (size_t q = 0; q < quad.numPoints; ++q) {
+                SD::gradPhis<K, Degree>(g, quad.lambda[q], gphi);
+                Real gu[N][N] = {}, dgu[N][N] = {};
+                for (size_t i = 0; i < npe; ++i) {
+                    const auto ui = u(m_mesh.elementNode(e, i));
+                    for (size_t c = 0; c < N; ++c) for (size_t r = 0; r < K; ++r) gu[c][r] += ui[c] * gphi[i][r];
+                }
+                for (size_t c = 0; c < N; ++c) for (size_t r = 0; r < K; ++r) for (size_t m = 0; m < K; ++m) dgu[c][r] -= gu[c][m] * G[m][r];
+                const SMatrix sig = E.doubleContract(SD::symmetrized<N>(gu)), dsig = E.doubleContract(SD::symmetrized<N>(dgu));
+                const Real wq = quad.weight[q] * vol;
+                for (size_t i = 0; i < npe; ++i) {
+                    Real dgphi[K];
+                    for (size_t r = 0; r < K; ++r) { dgphi[r] = 0.0; for (size_t m = 0; m < K; ++m) dgphi[r] -= G[m][r] * gphi[i][m]; }
+                    for (size_t c = 0; c < N; ++c) {
+                        Real acc = 0.0;
+                        for (size_t r = 0; r < K; ++r) acc += (div * sig(c, r) + dsig(c, r)) * gphi[i][r] + sig(c, r) * dgphi[r];
+                        f[i][c] += wq * acc;
+                    }
+                }
+            }
+            for (size_t i = 0; i < npe; ++i) load.add(DoF(m_mesh.elementNode(e, i)), f[i]);
+        }
+        return load;
+    }
+    // change in constantStrainLoad(cstrain) under deltaP (:1333-1348)
+    template <class _SymMat>
+    VField deltaConstantStrainLoad(const _SymMat &cstrain, const VField &deltaP) const {
+        namespace SD = ShapeDerivatives;
+        if (deltaP.domainSize() != m_mesh.numVertices()) throw std::runtime_error("deltaConstantStrainLoad: per-vertex perturbation expected");
+        constexpr size_t npe = _Mesh::nodesPerElement;
+        VField dload(numDoFs());
+        Real centroid[K + 1];
+        for (size_t v = 0; v <= K; ++v) centroid[v] = 1.0 / (K + 1);
+        for (size_t e = 0; e < m_mesh.numElements(); ++e) {
+            Real g[K + 1][K], G[K][K], gavg[npe][K];
+            m_mesh.elementGradLambda(e, g);
+            SD::velocityGradient(m_mesh, e, g, deltaP, G);
+            // grad phi_i is (at most) linear: its element average is its centroid value
+            SD::gradPhis<K, Degree>(g, centroid, gavg);
+            Real div = 0.0;
+            for (size_t a = 0; a < K; ++a) div += G[a][a];
+            const SMatrix s = elementTensor(e).doubleContract(cstrain);
+            const Real vol = m_mesh.elementVolume(e);
+            for (size_t i = 0; i < npe; ++i) {
+                Point l;
+                for (size_t c = 0; c < N; ++c)
+                    for (size_t r = 0; r < K; ++r) {
+                        Real dg = 0.0;
+                        for (size_t m = 0; m < K; ++m) dg -= G[m][r] * gavg[i][m];
+                        l[c] += vol * s(c, r) * (div * gavg[i][r] + dg);
+                    }
+                dload.add(DoF(m_mesh.elementNode(e, i)), l);
+            }
+        }
+        return dload;
+    }
+    // change in the element-averaged strain: avg (delta strain)(u) + avg strain(deltaU) (:1365-1375)
+    SMField deltaAverageStrainField(const VField &u, const VField &deltaU, const VField &deltaP) const {
+        namespace SD = ShapeDerivatives;
+        if (u.domainSize() != m_mesh.numNodes() || deltaU.domainSize() != m_mesh.numNodes()) throw std::runtime_error("deltaAverageStrainField: per-node fields expected");
+        if (deltaP.domainSize() != m_mesh.numVertices()) throw std::runtime_error("deltaAverageStrainField: per-vertex perturbation expected");
+        constexpr size_t npe = _Mesh::nodesPerElement;
+        SMField ds(m_mesh.numElements());
+        Real centroid[K + 1];
+        for (size_t v = 0; v <= K; ++v) centroid[v] = 1.0 / (K + 1);
+        for (size_t e = 0; e < m_mesh.numElements(); ++e) {
+            Real g[K + 1][K], G[K][K], gavg[npe][K];
+            m_mesh.elementGradLambda(e, g);
+            SD::velocityGradient(m_mesh, e, g, deltaP, G);
+            SD::gradPhis<K, Degree>(g, centroid, gavg);
+            Real gu[N][N] = {}, total[N][N] = {};
+            for (size_t i = 0; i < npe; ++i) {
+                const auto ui = u(m_mesh.elementNode(e, i)), dui = deltaU(m_mesh.elementNode(e, i));
+                for (size_t c = 0; c < N; ++c) for (size_t r = 0; r < K; ++r) { gu[c][r] += ui[c] * gavg[i][r]; total[c][r] += dui[c] * gavg[i][r]; }
+            }
+            for (size_t c = 0; c < N; ++c) for (size_t r = 0; r < K; ++r) for (size_t m = 0; m < K; ++m) total[c][r] -= gu[c][m] * G[m][r];
+            const SMatrix eps = SD::symmetrized<N>(total);
+            for (size_t kf = 0; kf < flatLen(N); ++kf) ds.data()[flatLen(N) * e + kf] = eps[kf];
+        }
+        return ds;
     }
 
     bool usingReducedDoFs() const { return m_dofForNode.size() == m_mesh.numNodes(); }

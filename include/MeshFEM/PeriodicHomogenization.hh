@@ -110,5 +110,112 @@ std::vector<MinorSymmetricTensor<Real, _Sim::N>> macroStrainToMicroStrainTensors
     return G;
 }
 
+// Exact discrete differential of the homogenized tensor with respect to the vertex positions (:383-478):
+// dCh(v)[c] is the change of Ch per unit motion of vertex v along axis c, at fixed fluctuation displacements
+// (they are stationary points of the cell energy, so this is the total derivative);
+//   dCh_ijkl = 1/|Y| int [ div dp  eps_ij : C : eps_kl - sigma_kl : (grad w_ij grad dp) - sigma_ij : (grad w_kl grad dp) ],
+// eps_ij = e_ij + strain(w_ij).  |Y| (the bounding box) is not differentiated, as in the reference.
+template <class _Sim>
+ShapeDerivatives::OneForm<typename _Sim::ETensor, _Sim::N>
+homogenizedElasticityTensorDiscreteDifferential(const std::vector<typename _Sim::VField> &w, const _Sim &sim) {
+    namespace SD = ShapeDerivatives;
+    constexpr size_t N = _Sim::N, K = _Sim::K, Deg = _Sim::Degree, F = flatLen(N);
+    typedef typename _Sim::Mesh Mesh;
+    typedef typename _Sim::SMatrix SMatrix;
+    constexpr size_t npe = Mesh::nodesPerElement;
+    const auto &mesh = sim.mesh();
+    if (w.size() != F) throw std::runtime_error("homogenizedElasticityTensorDiscreteDifferential: flatLen(N) fluctuation fields expected");
+    SD::OneForm<typename _Sim::ETensor, N> dCh(mesh.numVertices());
+    const SD::ElementQuadrature<K, Deg> quad;
+    const Real invCell = 1.0 / mesh.boundingBox().volume();
+    for (size_t e = 0; e < mesh.numElements(); ++e) {
+        Real g[K + 1][K], gphi[npe][K];
+        mesh.elementGradLambda(e, g);
+        const Real vol = mesh.elementVolume(e);
+        const auto &E = sim.elementTensor(e);
+        // per (ij <= kl): the scalar energy and the N x N matrix A = grad w_ij^T sigma_kl + grad w_kl^T sigma_ij, integrated
+        Real energy[F][F] = {}, A[F][F][N][N] = {};
+        for (size_t q = 0; q < quad.numPoints; ++q) {
+            SD::gradPhis<K, Deg>(g, quad.lambda[q], gphi);
+            Real gw[F][N][N] = {};
+            SMatrix eps[F], sig[F];
+            for (size_t ij = 0; ij < F; ++ij) {
+                for (size_t i = 0; i < npe; ++i) {
+                    const auto wi = w[ij](mesh.elementNode(e, i));
+                    for (size_t c = 0; c < N; ++c) for (size_t r = 0; r < K; ++r) gw[ij][c][r] += wi[c] * gphi[i][r];
+                }
+                eps[ij] = SD::symmetrized<N>(gw[ij]);
+                eps[ij] += SMatrix::CanonicalBasis(ij);
+                sig[ij] = E.doubleContract(eps[ij]);
+            }
+            const Real wq = quad.weight[q] * vol;
+            for (size_t ij = 0; ij < F; ++ij)
+                for (size_t kl = ij; kl < F; ++kl) {
+                    energy[ij][kl] += wq * eps[ij].doubleContract(sig[kl]);
+                    for (size_t c = 0; c < N; ++c) for (size_t b = 0; b < N; ++b) {
+                        Real acc = 0.0;
+                        for (size_t a = 0; a < N; ++a) acc += gw[ij][a][c] * sig[kl](a, b) + gw[kl][a][c] * sig[ij](a, b);
+                        A[ij][kl][c][b] += wq * acc;
+                    }
+                }
+        }
+        for (size_t v = 0; v <= K; ++v) {
+            auto &out = dCh(mesh.elementVertex(e, v));
+            for (size_t c = 0; c < N; ++c)
+                for (size_t ij = 0; ij < F; ++ij)
+                    for (size_t kl = ij; kl < F; ++kl) {
+                        Real val = energy[ij][kl] * g[v][c];
+                        for (size_t b = 0; b < N; ++b) val -= A[ij][kl][c][b] * g[v][b];
+                        out[c].D(ij, kl) += invCell * val;
+                    }
+        }
+    }
+    return dCh;
+}
+
+// Change in the homogenized tensor under the per-vertex perturbation delta_p.  The reference integrates its
+// continuous boundary shape derivative against the normal velocity (:480-510); here the exact discrete
+// differential above is applied, which is what a finite difference of the discrete Ch converges to.
+template <class _Sim>
+typename _Sim::ETensor deltaHomogenizedElasticityTensor(const _Sim &sim, const std::vector<typename _Sim::VField> &w,
+                                                        const typename _Sim::VField &delta_p) {
+    return homogenizedElasticityTensorDiscreteDifferential(w, sim)[delta_p];
+}
+
+// Change in the fluctuation displacements under delta_p (:520-540): K dw_ij = delta load(-e_ij) - (delta K) w_ij
+// with the constraints of the cell problems; the solves run on the device (one batched PCG).
+template <class _Sim>
+std::vector<typename _Sim::VField> deltaFluctuationDisplacements(const _Sim &sim, const std::vector<typename _Sim::VField> &w,
+                                                                 const typename _Sim::VField &delta_p) {
+    typedef typename _Sim::VField VField;
+    typedef typename _Sim::SMatrix SMatrix;
+    std::vector<VField> rhs;
+    for (size_t ij = 0; ij < w.size(); ++ij) {
+        VField r = sim.deltaConstantStrainLoad(-SMatrix::CanonicalBasis(ij), delta_p);
+        const VField dKw = sim.applyDeltaStiffnessMatrix(w[ij], delta_p);
+        for (size_t k = 0; k < r.data().size(); ++k) r.data()[k] -= dKw.data()[k];
+        rhs.push_back(r);
+    }
+    return sim.solve(rhs);
+}
+
+// Change in the macro-to-micro strain tensors under delta_p (:542-560): column kl = delta avg strain(w_kl)
+template <class _Sim>
+std::vector<MinorSymmetricTensor<Real, _Sim::N>> deltaMacroStrainToMicroStrainTensors(const _Sim &sim, const std::vector<typename _Sim::VField> &w,
+                                                                                      const std::vector<typename _Sim::VField> &delta_w,
+                                                                                      const typename _Sim::VField &delta_p) {
+    constexpr size_t F = flatLen(_Sim::N);
+    const size_t numElems = sim.mesh().numElements();
+    std::vector<MinorSymmetricTensor<Real, _Sim::N>> deltaG(numElems);
+    for (size_t kl = 0; kl < w.size(); ++kl) {
+        const auto dwe = sim.deltaAverageStrainField(w[kl], delta_w[kl], delta_p);
+        for (size_t e = 0; e < numElems; ++e) {
+            const auto s = dwe(e);
+            for (size_t r = 0; r < F; ++r) deltaG[e].d[r][kl] = s[r];
+        }
+    }
+    return deltaG;
+}
+
 }  // namespace PeriodicHomogenization
 #endif

@@ -163,6 +163,30 @@ class RawMesh:
             raise _err(self.lib)
         return dof, int(nd.value), ibe.astype(bool)
 
+    def shape_derivatives(self, deg, D, u, du, strain, delta_p, w_ij=None, periodic=False, num_dofs=None):
+        """Discrete shape derivatives of the host Simulator for the per-vertex perturbation delta_p: dict with
+        dKu (applyDeltaStiffnessMatrix), dload (deltaConstantStrainLoad), dstrain (deltaAverageStrainField) and, when
+        w_ij is given, dCh[numVertices, dim, F, F] (homogenizedElasticityTensorDiscreteDifferential)."""
+        K = self.dim
+        F = K * (K + 1) // 2
+        dp_ = POINTER(c_double)
+        fm = self.femmesh(deg)
+        nd = fm.num_nodes if num_dofs is None else num_dofs
+        arr = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        D, u, du, strain, delta_p = arr(D), arr(u), arr(du), arr(strain), arr(delta_p)
+        assert u.shape == (fm.num_nodes, K) and du.shape == u.shape and delta_p.shape == (fm.num_vertices, K)
+        dKu = np.zeros((nd, K)); dload = np.zeros((nd, K)); dstrain = np.zeros((fm.num_elements, F))
+        w = None if w_ij is None else arr(w_ij)
+        dCh = None if w is None else np.zeros((fm.num_vertices, K, F, F))
+        self.lib.mfemhost_shape_derivatives.argtypes = [c_void_p, c_int, c_int] + [dp_] * 10
+        if self.lib.mfemhost_shape_derivatives(self._p, deg, 1 if periodic else 0, D.ctypes.data_as(dp_), u.ctypes.data_as(dp_),
+                                               du.ctypes.data_as(dp_), strain.ctypes.data_as(dp_), delta_p.ctypes.data_as(dp_),
+                                               None if w is None else w.ctypes.data_as(dp_), dKu.ctypes.data_as(dp_),
+                                               dload.ctypes.data_as(dp_), dstrain.ctypes.data_as(dp_),
+                                               None if dCh is None else dCh.ctypes.data_as(dp_)) != 0:
+            raise _err(self.lib)
+        return dict(dKu=dKu, dload=dload, dstrain=dstrain, dCh=dCh)
+
     def femmesh(self, deg):
         """FEMMesh<dim,deg> flat data with the reference's numbering."""
         sz = (c_int64 * 5)()

@@ -1631,6 +1631,124 @@ def unflatten_rank4(N, Mflat):
     return out
 
 
+# ----------------------------------------------------------------------------
+# Discrete shape derivatives (LinearElasticity.hh:232-331, 1286-1373; EmbeddedElement.hh:269-372;
+# PeriodicHomogenization.hh:383-563).  Vertex perturbations delta_p move the straight-sided elements; nodal values
+# are transported (Lagrangian derivative).  With the piecewise-linear velocity field dp_h = sum_k delta_p_k lambda_k:
+#   delta grad lambda_i = -(grad dp_h)^T grad lambda_i          (EmbeddedElement.hh:269-278)
+#   delta vol / vol     = div dp_h                               (:365-372)
+# and the same rule for every grad phi_i, whose barycentric coefficients do not move (:338-363).
+# ----------------------------------------------------------------------------
+def _shape_derivative_context(mesh, delta_p):
+    N, deg = mesh.N, mesh.deg
+    T = grad_phi_interpolant(N, deg)
+    P, w = quadrature_points(N, 2 * (deg - 1))
+    Tq = T[:, 0, :][None] if deg == 1 else np.einsum("qv,iva->qia", P, T)
+    gp = np.einsum("qia,era->eqir", Tq, mesh.G)                       # grad phi_i at the quadrature points
+    gavg = np.einsum("ia,era->eir", T.mean(axis=1), mesh.G)           # int grad phi_i / vol
+    grad_dp = None
+    if delta_p is not None:
+        dpe = np.asarray(delta_p, dtype=float)[mesh.simplices]        # (ne, N+1, N)
+        grad_dp = np.einsum("eka,erk->ear", dpe, mesh.G)              # d(dp_a)/dx_r, constant per element
+    return gp, gavg, w, grad_dp
+
+
+def _element_C(N, D, ne):
+    D = np.asarray(D)
+    if D.ndim == 2:
+        return np.broadcast_to(tensor_C(N, D), (ne,) + (N,) * 4)
+    return np.stack([tensor_C(N, D[e]) for e in range(ne)])
+
+
+def apply_delta_stiffness_matrix(mesh, D, u_nodes, delta_p, dof_for_node=None, num_dofs=None):
+    """Simulator::applyDeltaStiffnessMatrix (:1301-1330): (delta K) u for the fixed per-NODE field u under the vertex
+    perturbation delta_p, as a per-DoF load."""
+    N = mesh.N
+    gp, _, w, gdp = _shape_derivative_context(mesh, delta_p)
+    C = _element_C(N, D, mesh.num_elements)
+    div = np.einsum("eaa->e", gdp)
+    ue = np.asarray(u_nodes)[mesh.elem_nodes]
+    gu = np.einsum("eic,eqir->eqcr", ue, gp)
+    dgu = -np.einsum("eqcm,emr->eqcr", gu, gdp)
+    sym = lambda g: 0.5 * (g + np.swapaxes(g, -1, -2))
+    sig = np.einsum("eabcd,eqcd->eqab", C, sym(gu))
+    dsig = np.einsum("eabcd,eqcd->eqab", C, sym(dgu))
+    dgp = -np.einsum("emr,eqim->eqir", gdp, gp)
+    f = (np.einsum("e,eqcr,eqir->eqic", div, sig, gp) + np.einsum("eqcr,eqir->eqic", dsig, gp)
+         + np.einsum("eqcr,eqir->eqic", sig, dgp))
+    f = np.einsum("q,e,eqic->eic", w, mesh.vol, f)
+    nd = mesh.num_nodes if dof_for_node is None else num_dofs
+    dof = mesh.elem_nodes if dof_for_node is None else np.asarray(dof_for_node)[mesh.elem_nodes]
+    load = np.zeros((nd, N))
+    np.add.at(load, dof.reshape(-1), f.reshape(-1, N))
+    return load
+
+
+def delta_constant_strain_load(mesh, D, strain_flat, delta_p, dof_for_node=None, num_dofs=None):
+    """Simulator::deltaConstantStrainLoad (:1333-1348) with deltaPerElementConstantStrainLoad (:286-302)."""
+    N = mesh.N
+    _, gavg, _, gdp = _shape_derivative_context(mesh, delta_p)
+    C = _element_C(N, D, mesh.num_elements)
+    s = np.einsum("eabcd,cd->eab", C, flat_to_sym(N, np.asarray(strain_flat, dtype=float)))
+    div = np.einsum("eaa->e", gdp)
+    dgavg = -np.einsum("emr,eim->eir", gdp, gavg)
+    l = np.einsum("e,ecr,eir->eic", mesh.vol * div, s, gavg) + np.einsum("e,ecr,eir->eic", mesh.vol, s, dgavg)
+    nd = mesh.num_nodes if dof_for_node is None else num_dofs
+    dof = mesh.elem_nodes if dof_for_node is None else np.asarray(dof_for_node)[mesh.elem_nodes]
+    load = np.zeros((nd, N))
+    np.add.at(load, dof.reshape(-1), l.reshape(-1, N))
+    return load
+
+
+def delta_average_strain_field(mesh, u_nodes, delta_u_nodes, delta_p):
+    """Simulator::deltaAverageStrainField (:1365-1375): avg (delta strain)(u) + avg strain(delta u), flattened."""
+    N = mesh.N
+    _, gavg, _, gdp = _shape_derivative_context(mesh, delta_p)
+    gu = np.einsum("eic,eir->ecr", np.asarray(u_nodes)[mesh.elem_nodes], gavg)
+    gdu = np.einsum("eic,eir->ecr", np.asarray(delta_u_nodes)[mesh.elem_nodes], gavg)
+    g = -np.einsum("ecm,emr->ecr", gu, gdp) + gdu
+    eps = 0.5 * (g + np.swapaxes(g, 1, 2))
+    return np.stack([eps[:, a, b] for a, b in (unflatten_index(N, i) for i in range(flat_len(N)))], axis=1)
+
+
+def homogenized_tensor_discrete_differential(sim, w_ij):
+    """homogenizedElasticityTensorDiscreteDifferential (PeriodicHomogenization.hh:383-478): dCh[v, c] (flattened
+    F x F) such that delta Ch = sum_v sum_c dCh[v, c] delta_p[v, c]; fluctuations held fixed (they are stationary
+    points of the cell energy, so this is the full derivative)."""
+    m = sim.mesh; N = sim.N; F = flat_len(N)
+    gp, _, wq, _ = _shape_derivative_context(m, None)
+    C = _element_C(N, sim.D, m.num_elements)
+    gw = np.stack([np.einsum("eic,eqir->eqcr", np.asarray(w)[m.elem_nodes], gp) for w in w_ij])      # (F, ne, q, N, N)
+    eps = 0.5 * (gw + np.swapaxes(gw, -1, -2))
+    for ij in range(F):
+        eps[ij] += flat_to_sym(N, canonical_basis(N, ij))
+    sig = np.einsum("eabcd,feqcd->feqab", C, eps)
+    energy = np.einsum("feqab,geqab->eqfg", eps, sig)
+    wv = np.einsum("q,e->eq", wq, m.vol)
+    t1 = np.einsum("eq,eqfg,ecv->evcfg", wv, energy, m.G)
+    A = np.einsum("feqac,geqab->eqfgcb", gw, sig)
+    A = A + np.swapaxes(A, 2, 3)                                       # grad w_ij^T sig_kl + grad w_kl^T sig_ij
+    t2 = np.einsum("eq,eqfgcb,ebv->evcfg", wv, A, m.G)
+    out = np.zeros((m.vertices.shape[0], N, F, F))
+    np.add.at(out, m.simplices.reshape(-1), (t1 - t2).reshape(-1, N, F, F))
+    return out / float(np.prod(m.bbox_max - m.bbox_min))
+
+
+def delta_fluctuation_displacements(sim, w_ij, delta_p):
+    """deltaFluctuationDisplacements (:520-540): K dw_ij = delta load(-e_ij) - (delta K) w_ij with the cell problem's
+    constraints (periodic DoFs, pinned node at value 0)."""
+    out = []
+    N = sim.N
+    K = sim.stiffness()
+    fixed, vals = sim.fixed_vars_and_values()
+    for ij, w in enumerate(w_ij):
+        rhs = delta_constant_strain_load(sim.mesh, sim.D, -canonical_basis(N, ij), delta_p, sim.dof_for_node, sim.num_dofs())
+        rhs = rhs - apply_delta_stiffness_matrix(sim.mesh, sim.D, w, delta_p, sim.dof_for_node, sim.num_dofs())
+        x = solve_fixed(K, rhs.reshape(-1), fixed, np.zeros_like(vals))
+        out.append(sim.dof_to_node_field(x))
+    return out
+
+
 def read_msh(path):
     """Returns (vertices (n,3), elements (m,k), gmsh element type).  ASCII or binary, 8-byte reals."""
     npe = {2: 3, 4: 4, 3: 4, 5: 8, 9: 6, 11: 10, 1: 2, 8: 3}

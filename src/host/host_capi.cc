@@ -526,6 +526,62 @@ int mfemhost_m2m_tensor(int dim, const double *Eflat, const double *Gflat, const
     } catch (const std::exception &e) { g_err = e.what(); return -1; }
 }
 
+// Discrete shape derivatives on the host-only Simulator (ShapeDerivatives.hh): for the per-vertex perturbation deltaP
+//   dKu[numDoFs*N]      = applyDeltaStiffnessMatrix(u, deltaP)
+//   dload[numDoFs*N]    = deltaConstantStrainLoad(strain, deltaP)
+//   dstrain[numElems*F] = deltaAverageStrainField(u, du, deltaP)
+//   dCh[numVertices*N*F*F] = homogenizedElasticityTensorDiscreteDifferential(w)   (when w != NULL)
+// periodic != 0 applies the periodic conditions first (loads are per DoF).
+int mfemhost_shape_derivatives(void *m, int deg, int periodic, const double *Dflat, const double *u, const double *du, const double *strain,
+                               const double *deltaP, const double *w, double *dKu, double *dload, double *dstrain, double *dCh) {
+    auto *hm = static_cast<HostMesh *>(m);
+    try {
+        auto run = [&](auto simTag) {
+            typedef typename decltype(simTag)::type Sim;
+            constexpr size_t N = Sim::N, F = flatLen(N);
+            Sim sim(hm->elements, hm->vertices, -1);
+            typename Sim::ETensor E;
+            E.setFlat(Dflat);
+            sim.setMaterial(E);
+            if (periodic) sim.applyPeriodicConditions();
+            const size_t nn = sim.mesh().numNodes(), nv = sim.mesh().numVertices();
+            typename Sim::VField U(nn), DU(nn), DP(nv);
+            std::copy(u, u + nn * N, U.data().begin());
+            std::copy(du, du + nn * N, DU.data().begin());
+            std::copy(deltaP, deltaP + nv * N, DP.data().begin());
+            typename Sim::SMatrix eps;
+            for (size_t k = 0; k < F; ++k) eps[k] = strain[k];
+            const auto a = sim.applyDeltaStiffnessMatrix(U, DP);
+            std::copy(a.data().begin(), a.data().end(), dKu);
+            const auto b = sim.deltaConstantStrainLoad(eps, DP);
+            std::copy(b.data().begin(), b.data().end(), dload);
+            const auto c = sim.deltaAverageStrainField(U, DU, DP);
+            std::copy(c.data().begin(), c.data().end(), dstrain);
+            if (w && dCh) {
+                std::vector<typename Sim::VField> w_ij;
+                for (size_t i = 0; i < F; ++i) {
+                    typename Sim::VField wi(nn);
+                    std::copy(w + i * nn * N, w + (i + 1) * nn * N, wi.data().begin());
+                    w_ij.push_back(wi);
+                }
+                const auto form = PeriodicHomogenization::homogenizedElasticityTensorDiscreteDifferential(w_ij, sim);
+                for (size_t v = 0; v < nv; ++v) for (size_t cc = 0; cc < N; ++cc) form(v)[cc].getFlat(dCh + (v * N + cc) * F * F);
+                // the one-form applied to deltaP must agree with the contraction of its entries
+                typename Sim::ETensor applied = PeriodicHomogenization::deltaHomogenizedElasticityTensor(sim, w_ij, DP), manual;
+                for (size_t v = 0; v < nv; ++v) for (size_t cc = 0; cc < N; ++cc) { auto t = form(v)[cc]; t *= DP(v)[cc]; manual += t; }
+                for (size_t i = 0; i < F; ++i) for (size_t j = i; j < F; ++j)
+                    if (std::abs(applied.D(i, j) - manual.D(i, j)) > 1e-12 * (1.0 + std::abs(manual.D(i, j)))) throw std::runtime_error("OneForm application mismatch");
+            }
+        };
+        if (hm->dim == 3 && deg == 1) run(TypeTag<LinearElasticity::Simulator<LinearElasticity::Mesh<3, 1>>>());
+        else if (hm->dim == 3 && deg == 2) run(TypeTag<LinearElasticity::Simulator<LinearElasticity::Mesh<3, 2>>>());
+        else if (hm->dim == 2 && deg == 1) run(TypeTag<LinearElasticity::Simulator<LinearElasticity::Mesh<2, 1>>>());
+        else if (hm->dim == 2 && deg == 2) run(TypeTag<LinearElasticity::Simulator<LinearElasticity::Mesh<2, 2>>>());
+        else throw std::runtime_error("bad dim/deg");
+        return 0;
+    } catch (const std::exception &e) { g_err = e.what(); return -1; }
+}
+
 int mfemhost_save_mesh(void *m, const char *path) {
     auto *hm = static_cast<HostMesh *>(m);
     try { MeshIO::save(path, hm->vertices, hm->elements); return 0; }

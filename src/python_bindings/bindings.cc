@@ -318,6 +318,54 @@ static py::tuple probe(const NpArr &V, const NpIdx &F, int degree, const Homogen
     return degree == 2 ? probeImpl<2, 2>(verts, elems, hr, macroStrain) : probeImpl<2, 1>(verts, elems, hr, macroStrain);
 }
 
+// Shape sensitivity of the homogenized tensor (not in the reference's binding; its C++ callers use
+// PeriodicHomogenization.hh:383-563): cell problems on the GPU, then the exact discrete differential dCh[v, c] on the
+// host and -- when a per-vertex perturbation is given -- the change of the fluctuation displacements (one more
+// batched solve on the GPU) and of Ch.
+template <size_t N, size_t Deg>
+static py::dict shapeDerivativeImpl(const std::vector<MeshIO::IOVertex> &verts, const std::vector<MeshIO::IOElement> &elems,
+                                    const NpArr &Cbase, const py::object &deltaP, int device, double rtol) {
+    typedef LinearElasticity::Simulator<LinearElasticity::Mesh<N, Deg>> Sim;
+    constexpr size_t F = flatLen(N);
+    Sim sim(elems, verts, device);
+    sim.setMaterial(tensorFromArray<N>(Cbase));
+    sim.setSolverTolerance(rtol);
+    std::vector<typename Sim::VField> w_ij;
+    PeriodicHomogenization::solveCellProblems(w_ij, sim);
+    py::dict out;
+    out["Ch"] = tensorD<N>(PeriodicHomogenization::homogenizedElasticityTensorDisplacementForm(w_ij, sim));
+    const auto form = PeriodicHomogenization::homogenizedElasticityTensorDiscreteDifferential(w_ij, sim);
+    const size_t nv = sim.mesh().numVertices(), nn = sim.mesh().numNodes();
+    NpArr dCh({nv, N, F, F});
+    for (size_t v = 0; v < nv; ++v) for (size_t c = 0; c < N; ++c) form(v)[c].getFlat(dCh.mutable_data() + (v * N + c) * F * F);
+    out["dCh"] = dCh;
+    NpArr w({F, nn, N});
+    for (size_t i = 0; i < F; ++i) std::copy(w_ij[i].data().begin(), w_ij[i].data().end(), w.mutable_data() + i * nn * N);
+    out["w_ij"] = w;
+    if (!deltaP.is_none()) {
+        const NpArr dp = deltaP.cast<NpArr>();
+        if (dp.ndim() != 2 || (size_t)dp.shape(0) != nv || (size_t)dp.shape(1) != N) throw std::runtime_error("deltaP must be numVertices x N");
+        typename Sim::VField DP(nv);
+        std::copy(dp.data(), dp.data() + nv * N, DP.data().begin());
+        const auto dw = PeriodicHomogenization::deltaFluctuationDisplacements(sim, w_ij, DP);
+        NpArr dwa({F, nn, N});
+        for (size_t i = 0; i < F; ++i) std::copy(dw[i].data().begin(), dw[i].data().end(), dwa.mutable_data() + i * nn * N);
+        out["delta_w_ij"] = dwa;
+        out["delta_Ch"] = tensorD<N>(form[DP]);
+    }
+    return out;
+}
+
+static py::dict shapeDerivative(const NpArr &V, const NpIdx &F, const NpArr &Cbase, int degree, const py::object &deltaP, int device, double rtol) {
+    std::vector<MeshIO::IOVertex> verts;
+    std::vector<MeshIO::IOElement> elems;
+    toIO(V, F, verts, elems);
+    const bool tet = F.shape(1) == 4;
+    if (degree != 1 && degree != 2) throw std::runtime_error("degree must be 1 or 2");
+    if (tet) return degree == 2 ? shapeDerivativeImpl<3, 2>(verts, elems, Cbase, deltaP, device, rtol) : shapeDerivativeImpl<3, 1>(verts, elems, Cbase, deltaP, device, rtol);
+    return degree == 2 ? shapeDerivativeImpl<2, 2>(verts, elems, Cbase, deltaP, device, rtol) : shapeDerivativeImpl<2, 1>(verts, elems, Cbase, deltaP, device, rtol);
+}
+
 PYBIND11_MODULE(periodic_homogenization, m) {
     m.doc() = "Periodic homogenization of a base cell on the GPU";
     py::module detail = m.def_submodule("detail");
@@ -331,5 +379,9 @@ PYBIND11_MODULE(periodic_homogenization, m) {
           py::arg("rtol") = 1e-10);
     m.def("probe", &probe, py::arg("vertices"), py::arg("elements"), py::arg("degree"), py::arg("homogenizationResult"),
           py::arg("macroStrain"));
+    m.def("shapeDerivative", &shapeDerivative, py::arg("vertices"), py::arg("elements"), py::arg("Cbase"), py::arg("degree") = 2,
+          py::arg("deltaP") = py::none(), py::arg("device") = 0, py::arg("rtol") = 1e-10,
+          "Ch, its exact discrete differential dCh[v, c] with respect to the vertex positions, the fluctuation displacements and, for a "
+          "per-vertex perturbation deltaP, delta_w_ij and delta_Ch");
 }
 #endif
