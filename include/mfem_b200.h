@@ -74,7 +74,10 @@ int mfem_b200_comm_share(mfem_b200_handle h, mfem_b200_handle parent);
  * "assembly": 0 = block-owner (default: every BSR block summed by one thread from its sorted
  *                 contribution list and written exactly once, coalesced),
  *             1 = graph-coloured element scatter (read-modify-write, no atomics),
- *             2 = owner-gather by DoF row (first-generation kernel, kept for A/B).      */
+ *             2 = owner-gather by DoF row (first-generation kernel, kept for A/B).
+ * "coarse_aggregates": S > 0 adds an aggregation coarse space (rigid-body modes of S contiguous runs of the
+ *             internal DoF numbering) to the block-Jacobi preconditioner, M^-1 = B^-1 + Z (Z'KZ)^-1 Z'
+ *             (csrc/coarse.inl; single GPU, single right-hand side; default 0 = off; may be changed between solves). */
 int mfem_b200_set_option(mfem_b200_handle h, const char *name, int64_t value);
 
 /* ---- mesh ------------------------------------------------------------------------ */

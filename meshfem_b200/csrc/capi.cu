@@ -73,6 +73,7 @@ int mfem_b200_destroy(mfem_b200_handle h) {
     cudaSetDevice(h->device);
     comm_destroy(h);
     free_work_multi(h);
+    free_coarse_space(h);
     if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
     delete h;
     return MFEM_B200_OK;
@@ -102,6 +103,10 @@ int mfem_b200_set_option(mfem_b200_handle h, const char *name, int64_t value) {
     } else if (n == "spmv_kernel") {
         MFEM_REQUIRE(value >= 0 && value <= 4, MFEM_B200_ERR_INVALID, "spmv_kernel must be 0 (auto), 1 (direct loads), 2 (TMA ring), 3 (index-pipelined) or 4 (symmetric)");
         h->opt_spmv_kernel = (int)value;
+    } else if (n == "coarse_aggregates") {
+        MFEM_REQUIRE(value >= 0 && value <= 5461, MFEM_B200_ERR_INVALID, "coarse_aggregates must be 0 (block-Jacobi only) .. 5461");
+        h->opt_coarse = (int)value;
+        h->precondValid = false;
     } else if (n == "spmv_lanes") {
         MFEM_REQUIRE(value == 0 || value == 8 || value == 16 || value == 32, MFEM_B200_ERR_INVALID,
                      "spmv_lanes must be 0 (auto), 8, 16 or 32");
@@ -328,7 +333,7 @@ int mfem_b200_solve(mfem_b200_handle h, int nrhs, const double *f, double *u, do
     const size_t n = (size_t)h->nvar();
     int firstErr = MFEM_B200_OK;
     std::string firstMsg;
-    if (h->opt_batch_rhs && nrhs == flat_len(h->N)) {
+    if (h->opt_batch_rhs && nrhs == flat_len(h->N) && h->opt_coarse == 0) {
         // the cell-problem case: all right-hand sides in one batched PCG (one matrix stream for all of them)
         DevBuf<double> fext(n), fin(n * nrhs), uin(n * nrhs), uext(n);
         for (int k = 0; k < nrhs; ++k) {

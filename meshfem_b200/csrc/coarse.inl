@@ -1,0 +1,362 @@
+// Two-level preconditioner (option coarse_aggregates = S > 0, default off):  M^-1 = B^-1 + Z E^-1 Z^T,
+// B = the block-Jacobi of solver.cu, Z = rigid-body modes of S aggregates (6 per aggregate in 3D, 3 in 2D: the
+// tentative prolongator of smoothed-aggregation AMG), E = Z^T K_ff Z.  Aggregates are contiguous runs of the internal
+// (Morton-ordered) DoF numbering, agg(i) = floor(i S / nDofs), so restriction and prolongation are segmented
+// reductions / broadcasts over index ranges with no indirection.
+//
+// Why: the cantilever workloads are bending-dominated and block-Jacobi PCG needs thousands of iterations (cfg5: 6074);
+// tools/proto_two_level.py (CPU, numpy) measures 4.8x fewer iterations with 180 nodes per aggregate and 7x with 45,
+// independent of the mesh size at fixed aggregate size.  Cost per iteration: one pass over r and z (120 B per DoF)
+// plus a dense (6S)^2 GEMV, a few percent of the SpMV.
+//
+// STATUS: written after the round-1 GPU budget was spent -- compiled, never run on a GPU; opt-in only.
+//   * single GPU, single right-hand side (the batched PCG ignores it);
+//   * E is dense and inverted explicitly with cuSOLVER (potrf + potri), loaded with dlopen so that the library has no
+//     link-time dependency on it: a setup step of O((6S)^3), not on the per-iteration path;
+//   * restriction uses FP64 atomics: the solve is no longer bit-reproducible run to run with this option on.
+// Included by solver.cu inside namespace mfem (which includes <cusolverDn.h> and <dlfcn.h> for it).
+
+struct CoarseSpace {
+    int S = 0, M = 0;                 // aggregates, modes per aggregate
+    int64_t nc = 0;                   // M * S
+    DevBuf<double> Y;                 // [nDofs*N] DoF position relative to its aggregate's centroid (internal order)
+    DevBuf<double> Einv;              // [nc*nc] row-major, symmetric
+    DevBuf<double> cvec, yvec;        // [nc]
+};
+
+__host__ __device__ __forceinline__ int64_t coarse_agg(int64_t i, int64_t S, int64_t nb) { return (i * S) / nb; }
+
+// q = R_i^T v (M values) for the rigid modes at relative position y: translations, then rotations
+// 3D: (0,-z,y), (z,0,-x), (-y,x,0); 2D: (-y,x)
+template <int N>
+__device__ __forceinline__ void coarse_Rt(const double *y, const double *v, double *q) {
+    if (N == 3) {
+        q[0] = v[0]; q[1] = v[1]; q[2] = v[2];
+        q[3] = y[1] * v[2] - y[2] * v[1];
+        q[4] = y[2] * v[0] - y[0] * v[2];
+        q[5] = y[0] * v[1] - y[1] * v[0];
+    } else {
+        q[0] = v[0]; q[1] = v[1];
+        q[2] = y[0] * v[1] - y[1] * v[0];
+    }
+}
+// v = R_i c
+template <int N>
+__device__ __forceinline__ void coarse_R(const double *y, const double *c, double *v) {
+    if (N == 3) {
+        v[0] = c[0] + y[2] * c[4] - y[1] * c[5];
+        v[1] = c[1] - y[2] * c[3] + y[0] * c[5];
+        v[2] = c[2] + y[1] * c[3] - y[0] * c[4];
+    } else {
+        v[0] = c[0] - y[1] * c[2];
+        v[1] = c[1] + y[0] * c[2];
+    }
+}
+
+// lowest node of every DoF (periodic DoFs have several nodes; any would do, the lowest is deterministic)
+__global__ void k_coarse_first_node(int64_t nNodes, const int32_t *__restrict__ nodeDof, int32_t *firstNode) {
+    const int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (n < nNodes) atomicMin(&firstNode[nodeDof[n]], (int32_t)n);
+}
+template <int N>
+__global__ void k_coarse_positions(int64_t nb, int64_t S, int64_t nNodes, const int32_t *__restrict__ firstNode,
+                                   const double *__restrict__ nodes, double *__restrict__ Y, double *cen /* [S*(N+1)] sums and counts */) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= nb) return;
+    const int64_t a = coarse_agg(i, S, nb);
+    const int64_t node = firstNode[i];
+    if (node < 0 || node >= nNodes) return;              // a DoF without a node: stays at the origin
+    for (int k = 0; k < N; ++k) {
+        const double x = nodes[node * N + k];
+        Y[i * N + k] = x;
+        atomicAdd(&cen[a * (N + 1) + k], x);
+    }
+    atomicAdd(&cen[a * (N + 1) + N], 1.0);
+}
+template <int N>
+__global__ void k_coarse_center(int64_t nb, int64_t S, const double *__restrict__ cen, double *__restrict__ Y) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= nb) return;
+    const int64_t a = coarse_agg(i, S, nb);
+    const double cnt = cen[a * (N + 1) + N];
+    if (cnt > 0.0)
+        for (int k = 0; k < N; ++k) Y[i * N + k] -= cen[a * (N + 1) + k] / cnt;
+}
+
+// E += Z^T K_ff Z: one warp per block row, one lane per block; lanes whose columns fall into the same aggregate
+// (contiguous: columns are sorted and agg is monotone) are combined by a segmented shuffle reduction, the head lane
+// of each segment adds the M x M result to E.
+template <int N>
+__global__ void __launch_bounds__(256)
+k_coarse_matrix(int64_t nb, int64_t S, const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
+                const double *__restrict__ vals, const uint8_t *__restrict__ fixedMask, const double *__restrict__ Y,
+                double *E) {
+    constexpr int M = N == 3 ? 6 : 3;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nWarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t nc = (int64_t)M * S;
+    for (int64_t row = warp; row < nb; row += nWarps) {
+        const int64_t b0 = rowptr[row], n = rowptr[row + 1] - b0;
+        const int64_t ai = coarse_agg(row, S, nb);
+        double yi[N];
+        bool fi[N];
+        for (int k = 0; k < N; ++k) { yi[k] = Y[row * N + k]; fi[k] = fixedMask[row * N + k] != 0; }
+        for (int64_t j0 = 0; j0 < n; j0 += 32) {
+            const int64_t j = j0 + lane;
+            const bool active = j < n;
+            double C[M][M];
+            int64_t aj = -1 - lane;                      // inactive lanes: unique keys, never merged
+            for (int a = 0; a < M; ++a) for (int b = 0; b < M; ++b) C[a][b] = 0.0;
+            if (active) {
+                const int64_t col = colidx[b0 + j];
+                aj = coarse_agg(col, S, nb);
+                double yj[N];
+                for (int k = 0; k < N; ++k) yj[k] = Y[col * N + k];
+                // T[r][b] = sum_c K[r][c] R_j[c][b] with fixed rows / columns masked out
+                double T[N][M];
+                for (int r = 0; r < N; ++r) {
+                    double krow[N];
+                    for (int cc = 0; cc < N; ++cc)
+                        krow[cc] = (fi[r] || fixedMask[col * N + cc]) ? 0.0 : vals[val_index<N>(b0, n, j, r, cc)];
+                    coarse_Rt<N>(yj, krow, T[r]);      // (K_row R_j) = R_j^T K_row^T
+                }
+                for (int b = 0; b < M; ++b) {
+                    double tcol[N], q[M];
+                    for (int r = 0; r < N; ++r) tcol[r] = T[r][b];
+                    coarse_Rt<N>(yi, tcol, q);
+                    for (int a = 0; a < M; ++a) C[a][b] = q[a];
+                }
+            }
+            // segmented reduction over contiguous lanes with equal aj
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int64_t ajo = __shfl_down_sync(0xffffffffu, aj, o);
+                const bool take = (lane + o < 32) && (ajo == aj);
+                for (int a = 0; a < M; ++a)
+                    for (int b = 0; b < M; ++b) {
+                        const double other = __shfl_down_sync(0xffffffffu, C[a][b], o);
+                        if (take) C[a][b] += other;
+                    }
+            }
+            const int64_t ajPrev = __shfl_up_sync(0xffffffffu, aj, 1);
+            const bool head = active && (lane == 0 || ajPrev != aj);
+            if (head)
+                for (int a = 0; a < M; ++a)
+                    for (int b = 0; b < M; ++b)
+                        if (C[a][b] != 0.0) atomicAdd(&E[(ai * M + a) * nc + aj * M + b], C[a][b]);
+        }
+    }
+}
+
+// dead modes (all-zero rows: aggregates without free variables, rotations without coordinates) get a unit diagonal;
+// a relative shift keeps E safely positive definite
+__global__ void k_coarse_regularize(int64_t nc, double *E, double shift) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= nc) return;
+    const double d = E[i * nc + i];
+    E[i * nc + i] = (d == 0.0) ? 1.0 : d * (1.0 + shift);
+}
+// potri leaves the inverse in one triangle (column-major lower = row-major upper): mirror it
+__global__ void k_coarse_symmetrize(int64_t nc, double *E) {
+    const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, r = blockIdx.y;
+    if (c < r && c < nc) E[r * nc + c] = E[c * nc + r];
+}
+
+// c += Z^T r (c zeroed by k_coarse_prolong of the previous application)
+template <int N>
+__global__ void __launch_bounds__(kVecThreads)
+k_coarse_restrict(int64_t nb, int64_t S, const double *__restrict__ r, const uint8_t *__restrict__ fixedMask,
+                  const double *__restrict__ Y, double *cvec, const int *status) {
+    constexpr int M = N == 3 ? 6 : 3;
+    if (status && status[ST_STATE] != 0) return;
+    const int lane = threadIdx.x & 31;
+    // contiguous slabs per warp iteration: the 32 lanes hold consecutive DoFs
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nWarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t base = warp * 32; base < nb; base += nWarps * 32) {
+        const int64_t i = base + lane;
+        double q[M];
+        int64_t a = -1 - lane;
+        for (int m = 0; m < M; ++m) q[m] = 0.0;
+        if (i < nb) {
+            a = coarse_agg(i, S, nb);
+            double v[N], y[N];
+            for (int k = 0; k < N; ++k) { v[k] = fixedMask[i * N + k] ? 0.0 : r[i * N + k]; y[k] = Y[i * N + k]; }
+            coarse_Rt<N>(y, v, q);
+        }
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int64_t ao = __shfl_down_sync(0xffffffffu, a, o);
+            const bool take = (lane + o < 32) && (ao == a);
+            for (int m = 0; m < M; ++m) {
+                const double other = __shfl_down_sync(0xffffffffu, q[m], o);
+                if (take) q[m] += other;
+            }
+        }
+        const int64_t aPrev = __shfl_up_sync(0xffffffffu, a, 1);
+        if (i < nb && (lane == 0 || aPrev != a))
+            for (int m = 0; m < M; ++m) atomicAdd(&cvec[a * M + m], q[m]);
+    }
+}
+
+// y = Einv c (one warp per row) and rz += c.y
+__global__ void __launch_bounds__(256)
+k_coarse_gemv(int64_t nc, const double *__restrict__ Einv, const double *__restrict__ cvec, double *__restrict__ yvec,
+              double *rzOut, const int *status) {
+    if (status && status[ST_STATE] != 0) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nWarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    double dot = 0.0;
+    for (int64_t row = warp; row < nc; row += nWarps) {
+        const double *e = Einv + row * nc;
+        double s = 0.0;
+        for (int64_t k = lane; k < nc; k += 32) s = fma(e[k], cvec[k], s);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) { yvec[row] = s; dot += s * cvec[row]; }
+    }
+    if (lane == 0 && dot != 0.0) atomicAdd(rzOut, dot);
+}
+
+// z += mask(Z y) [and p = z for the initial direction]; clears c for the next application
+template <int N>
+__global__ void __launch_bounds__(kVecThreads)
+k_coarse_prolong(int64_t nb, int64_t S, const double *__restrict__ yvec, const uint8_t *__restrict__ fixedMask,
+                 const double *__restrict__ Y, double *__restrict__ z, double *p /* may be null */, double *cvec, int64_t nc,
+                 const int *status) {
+    constexpr int M = N == 3 ? 6 : 3;
+    if (status && status[ST_STATE] != 0) return;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nb; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t a = coarse_agg(i, S, nb);
+        double c[M], y[N], v[N];
+        for (int m = 0; m < M; ++m) c[m] = yvec[a * M + m];
+        for (int k = 0; k < N; ++k) y[k] = Y[i * N + k];
+        coarse_R<N>(y, c, v);
+        for (int k = 0; k < N; ++k) {
+            const double zk = z[i * N + k] + (fixedMask[i * N + k] ? 0.0 : v[k]);
+            z[i * N + k] = zk;
+            if (p) p[i * N + k] = zk;
+        }
+        if (i < nc) cvec[i] = 0.0;
+    }
+    // nc > nb cannot happen (S <= nb / 8), so the loop above clears all of c
+}
+
+// ---- cuSOLVER through dlopen (setup only)
+struct CusolverApi {
+    void *lib = nullptr;
+    cusolverStatus_t (*create)(cusolverDnHandle_t *) = nullptr;
+    cusolverStatus_t (*destroy)(cusolverDnHandle_t) = nullptr;
+    cusolverStatus_t (*setStream)(cusolverDnHandle_t, cudaStream_t) = nullptr;
+    cusolverStatus_t (*potrfBuf)(cusolverDnHandle_t, cublasFillMode_t, int, double *, int, int *) = nullptr;
+    cusolverStatus_t (*potrf)(cusolverDnHandle_t, cublasFillMode_t, int, double *, int, double *, int, int *) = nullptr;
+    cusolverStatus_t (*potriBuf)(cusolverDnHandle_t, cublasFillMode_t, int, double *, int, int *) = nullptr;
+    cusolverStatus_t (*potri)(cusolverDnHandle_t, cublasFillMode_t, int, double *, int, double *, int, int *) = nullptr;
+};
+static CusolverApi &cusolver_api() {
+    static CusolverApi api;
+    if (api.lib) return api;
+    for (const char *name : {"libcusolver.so.11", "/usr/local/cuda/lib64/libcusolver.so.11", "libcusolver.so"}) {
+        api.lib = dlopen(name, RTLD_NOW | RTLD_LOCAL);
+        if (api.lib) break;
+    }
+    MFEM_REQUIRE(api.lib, MFEM_B200_ERR_INVALID, std::string("coarse_aggregates: cannot load libcusolver (") + dlerror() + ")");
+    auto sym = [&](const char *n) {
+        void *p = dlsym(api.lib, n);
+        MFEM_REQUIRE(p, MFEM_B200_ERR_INVALID, std::string("coarse_aggregates: libcusolver lacks ") + n);
+        return p;
+    };
+    api.create = reinterpret_cast<decltype(api.create)>(sym("cusolverDnCreate"));
+    api.destroy = reinterpret_cast<decltype(api.destroy)>(sym("cusolverDnDestroy"));
+    api.setStream = reinterpret_cast<decltype(api.setStream)>(sym("cusolverDnSetStream"));
+    api.potrfBuf = reinterpret_cast<decltype(api.potrfBuf)>(sym("cusolverDnDpotrf_bufferSize"));
+    api.potrf = reinterpret_cast<decltype(api.potrf)>(sym("cusolverDnDpotrf"));
+    api.potriBuf = reinterpret_cast<decltype(api.potriBuf)>(sym("cusolverDnDpotri_bufferSize"));
+    api.potri = reinterpret_cast<decltype(api.potri)>(sym("cusolverDnDpotri"));
+    return api;
+}
+
+static void free_coarse(mfem_b200_ctx *c) {
+    delete c->coarse;
+    c->coarse = nullptr;
+}
+
+template <int N>
+static void build_coarse_impl(mfem_b200_ctx *c) {
+    constexpr int M = N == 3 ? 6 : 3;
+    cudaStream_t s = c->stream;
+    const int64_t nb = c->nDofs;
+    int64_t S = std::min<int64_t>(c->opt_coarse, std::max<int64_t>(1, nb / 8));
+    S = std::min<int64_t>(S, 32768 / M);
+    free_coarse(c);
+    c->coarse = new CoarseSpace();
+    CoarseSpace &cs = *c->coarse;
+    cs.S = (int)S; cs.M = M; cs.nc = M * S;
+    const int64_t nc = cs.nc;
+    cs.Y.alloc((size_t)nb * N);
+    cs.Einv.alloc((size_t)nc * nc);
+    cs.cvec.alloc((size_t)nc); cs.yvec.alloc((size_t)nc);
+    MFEM_CUDA(cudaMemsetAsync(cs.Y, 0, cs.Y.bytes(), s));
+    MFEM_CUDA(cudaMemsetAsync(cs.Einv, 0, cs.Einv.bytes(), s));
+    MFEM_CUDA(cudaMemsetAsync(cs.cvec, 0, cs.cvec.bytes(), s));
+    if (!c->externalMatrix && c->nNodes > 0) {
+        DevBuf<int32_t> firstNode((size_t)nb);
+        DevBuf<double> cen((size_t)S * (N + 1));
+        MFEM_CUDA(cudaMemsetAsync(firstNode, 0x7f, firstNode.bytes(), s));
+        MFEM_CUDA(cudaMemsetAsync(cen, 0, cen.bytes(), s));
+        k_coarse_first_node<<<grid_for(c->nNodes, 256), 256, 0, s>>>(c->nNodes, c->nodeDof, firstNode);
+        k_coarse_positions<N><<<grid_for(nb, 256), 256, 0, s>>>(nb, S, c->nNodes, firstNode, c->nodes, cs.Y, cen);
+        k_coarse_center<N><<<grid_for(nb, 256), 256, 0, s>>>(nb, S, cen, cs.Y);
+        c->launches += 3;
+        MFEM_CUDA(cudaStreamSynchronize(s));          // firstNode / cen go out of scope
+    }
+    const int grid = (int)std::min<int64_t>((nb + 7) / 8, (int64_t)sm_count(c) * 8);
+    k_coarse_matrix<N><<<grid, 256, 0, s>>>(nb, S, c->rowptr, c->colidx, c->vals, c->fixedMask, cs.Y, cs.Einv);
+    k_coarse_regularize<<<grid_for(nc, 256), 256, 0, s>>>(nc, cs.Einv, 1e-12);
+    c->launches += 2;
+    MFEM_CUDA(cudaGetLastError());
+    // explicit inverse: E = L L^T, E^-1 from the factor
+    CusolverApi &api = cusolver_api();
+    cusolverDnHandle_t h = nullptr;
+    MFEM_REQUIRE(api.create(&h) == CUSOLVER_STATUS_SUCCESS, MFEM_B200_ERR_CUDA, "cusolverDnCreate failed");
+    struct Guard { CusolverApi &a; cusolverDnHandle_t h; ~Guard() { if (h) a.destroy(h); } } guard{api, h};
+    MFEM_REQUIRE(api.setStream(h, s) == CUSOLVER_STATUS_SUCCESS, MFEM_B200_ERR_CUDA, "cusolverDnSetStream failed");
+    int lw1 = 0, lw2 = 0;
+    MFEM_REQUIRE(api.potrfBuf(h, CUBLAS_FILL_MODE_LOWER, (int)nc, cs.Einv, (int)nc, &lw1) == CUSOLVER_STATUS_SUCCESS, MFEM_B200_ERR_CUDA, "potrf_bufferSize failed");
+    MFEM_REQUIRE(api.potriBuf(h, CUBLAS_FILL_MODE_LOWER, (int)nc, cs.Einv, (int)nc, &lw2) == CUSOLVER_STATUS_SUCCESS, MFEM_B200_ERR_CUDA, "potri_bufferSize failed");
+    DevBuf<double> wbuf((size_t)std::max(lw1, lw2) + 1);
+    DevBuf<int> info(1);
+    int hinfo = 0;
+    MFEM_REQUIRE(api.potrf(h, CUBLAS_FILL_MODE_LOWER, (int)nc, cs.Einv, (int)nc, wbuf, lw1, info) == CUSOLVER_STATUS_SUCCESS, MFEM_B200_ERR_CUDA, "potrf failed");
+    MFEM_CUDA(cudaMemcpyAsync(&hinfo, info, sizeof(int), cudaMemcpyDeviceToHost, s));
+    MFEM_CUDA(cudaStreamSynchronize(s));
+    MFEM_REQUIRE(hinfo == 0, MFEM_B200_ERR_NOT_SPD, "coarse matrix is not positive definite (leading minor " + std::to_string(hinfo) +
+                                                         "): fewer aggregates, or a singular system");
+    MFEM_REQUIRE(api.potri(h, CUBLAS_FILL_MODE_LOWER, (int)nc, cs.Einv, (int)nc, wbuf, lw2, info) == CUSOLVER_STATUS_SUCCESS, MFEM_B200_ERR_CUDA, "potri failed");
+    MFEM_CUDA(cudaMemcpyAsync(&hinfo, info, sizeof(int), cudaMemcpyDeviceToHost, s));
+    MFEM_CUDA(cudaStreamSynchronize(s));
+    MFEM_REQUIRE(hinfo == 0, MFEM_B200_ERR_NOT_SPD, "coarse matrix inversion failed (" + std::to_string(hinfo) + ")");
+    k_coarse_symmetrize<<<dim3((unsigned)grid_for(nc, 256), (unsigned)nc), 256, 0, s>>>(nc, cs.Einv);
+    c->launches++;
+    MFEM_CUDA(cudaStreamSynchronize(s));
+    MFEM_CUDA(cudaGetLastError());
+}
+
+static void build_coarse(mfem_b200_ctx *c) {
+    MFEM_REQUIRE(c->nRanks == 1, MFEM_B200_ERR_INVALID, "coarse_aggregates: single-GPU only in this version");
+    ScopedTimer timer(c, "Coarse Space");
+    if (c->N == 3) build_coarse_impl<3>(c); else build_coarse_impl<2>(c);
+}
+
+// z += Z Einv Z^T r, rz += (Z^T r).(Einv Z^T r); p = z when p != null (initial direction)
+template <int N>
+static void apply_coarse(mfem_b200_ctx *c, const double *r, double *z, double *p, double *rzSlot, const int *status) {
+    CoarseSpace &cs = *c->coarse;
+    cudaStream_t s = c->stream;
+    const int vgrid = vec_grid(c, c->nDofs);
+    k_coarse_restrict<N><<<vgrid, kVecThreads, 0, s>>>(c->nDofs, cs.S, r, c->fixedMask, cs.Y, cs.cvec, status);
+    const int ggrid = (int)std::min<int64_t>((cs.nc + 7) / 8, (int64_t)sm_count(c) * 8);
+    k_coarse_gemv<<<ggrid, 256, 0, s>>>(cs.nc, cs.Einv, cs.cvec, cs.yvec, rzSlot, status);
+    k_coarse_prolong<N><<<vgrid, kVecThreads, 0, s>>>(c->nDofs, cs.S, cs.yvec, c->fixedMask, cs.Y, z, p, cs.cvec, cs.nc, status);
+    c->launches += 3;
+}
+

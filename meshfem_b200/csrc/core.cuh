@@ -77,6 +77,7 @@ struct PcgWork {
 
 struct Halo;   // multi-GPU interface exchange (comm.cu)
 struct PcgWorkMulti;   // workspace of the batched (multi right-hand-side) PCG (solver_multi.inl)
+struct CoarseSpace;    // aggregation coarse space of the optional two-level preconditioner (coarse.inl)
 
 }  // namespace mfem
 
@@ -93,6 +94,7 @@ struct mfem_b200_ctx {
     int opt_spmm_kernel = 0;               // batched PCG: 0/1 full-warp SpMM, 2 half-warp split SpMM (even batch sizes)
     int opt_batch_rhs = 1;                 // solve flatLen(N) right-hand sides as one batched PCG (SpMM)
     int opt_spmv_lanes = 0;                // lanes per block row in the SpMV (0 = choose from the mean row length)
+    int opt_coarse = 0;                    // aggregates of the two-level preconditioner (0 = block-Jacobi only)
 
     // mesh
     int N = 0, deg = 0, npe = 0;
@@ -159,6 +161,7 @@ struct mfem_b200_ctx {
     mfem::PcgWork work;
     bool workValid = false;
     mfem::PcgWorkMulti *workMulti = nullptr;
+    mfem::CoarseSpace *coarse = nullptr;   // built with the preconditioner when opt_coarse > 0
 
     // multi-GPU
     int nRanks = 1, rank = 0;
@@ -236,6 +239,7 @@ void ensure_work(mfem_b200_ctx *c);
 bool pcg_solve_multi(mfem_b200_ctx *c, int nrhs, const double *f_int, double *u_int, double rtol, int maxIters,
                      mfem_b200_solve_info *info);
 void free_work_multi(mfem_b200_ctx *c);
+void free_coarse_space(mfem_b200_ctx *c);
 double time_spmv(mfem_b200_ctx *c, int iters);
 // comm.cu
 void halo_exchange_add(mfem_b200_ctx *c, double *vec_int, int width);   // no-op on one rank

@@ -12,6 +12,9 @@
 // finish sums them in index order): results are bit-reproducible run to run.
 #include "core.cuh"
 
+#include <cusolverDn.h>   // types only: the library is loaded with dlopen by coarse.inl (optional two-level preconditioner)
+#include <dlfcn.h>
+
 namespace mfem {
 
 constexpr int kSpmvThreads = 256;
@@ -1235,6 +1238,10 @@ void spmv_plain(mfem_b200_ctx *c, const double *x_int, double *y_int) {
     MFEM_CUDA(cudaGetLastError());
 }
 
+#include "coarse.inl"
+
+void free_coarse_space(mfem_b200_ctx *c) { free_coarse(c); }
+
 void build_preconditioner(mfem_b200_ctx *c) {
     if (c->precondValid) return;
     MFEM_REQUIRE(c->valuesValid, MFEM_B200_ERR_INVALID, "preconditioner: matrix not assembled");
@@ -1265,6 +1272,8 @@ void build_preconditioner(mfem_b200_ctx *c) {
     MFEM_CUDA(cudaGetLastError());
     MFEM_REQUIRE(nbad == 0, MFEM_B200_ERR_NOT_SPD,
                  "block-Jacobi: " + std::to_string(nbad) + " diagonal blocks are not positive definite");
+    timer.stop();
+    if (c->opt_coarse > 0) build_coarse(c); else free_coarse(c);
     c->precondValid = true;
 }
 
@@ -1296,6 +1305,7 @@ static void enqueue_iteration(mfem_b200_ctx *c) {
                                                            w.ticket + 1, w.scal,
                                                            multi ? w.dotLoc.p + DL_RZ_NEW : w.scal.p + S_RZ_NEW, w.status);
     if (multi) allreduce_sum(c, w.dotLoc.p + DL_RZ_NEW, w.scal.p + S_RZ_NEW, 2);
+    if (c->coarse) apply_coarse<N>(c, w.r, w.z, nullptr, w.scal.p + S_RZ_NEW, w.status);      // z += Z E^-1 Z^T r
     k_pcg_direction<N><<<vec_grid(c, n), kVecThreads, 0, c->stream>>>(n, w.z, w.p, w.scal, w.status, w.ticket + 2);
     c->launches += 2;
 }
@@ -1316,6 +1326,10 @@ static void pcg_impl(mfem_b200_ctx *c, const double *f_int, double *u_int, doubl
                                                           w.partials, w.ticket + 1,
                                                           multi ? w.dotLoc.p + DL_RZ_NEW : w.scal.p + S_RZ_NEW);
     if (multi) allreduce_sum(c, w.dotLoc.p + DL_RZ_NEW, w.scal.p + S_RZ_NEW, 2);
+    if (c->coarse) {
+        MFEM_CUDA(cudaMemsetAsync(c->coarse->cvec, 0, c->coarse->cvec.bytes(), s));
+        apply_coarse<N>(c, w.r, w.z, w.p, w.scal.p + S_RZ_NEW, nullptr);                         // z0, p0 = z0, r.z0
+    }
     k_pcg_init_finalize<<<1, 32, 0, s>>>(w.scal, w.status, rtol * rtol);
     c->launches += 3;
     MFEM_CUDA(cudaGetLastError());
@@ -1344,7 +1358,7 @@ static void pcg_impl(mfem_b200_ctx *c, const double *f_int, double *u_int, doubl
     while (done < maxIters) {
         if (exec) {
             MFEM_CUDA(cudaGraphLaunch(exec, s));
-            c->launches += 3 * kBatch;
+            c->launches += (c->coarse ? 6 : 3) * kBatch;
         } else {
             for (int k = 0; k < kBatch; ++k) enqueue_iteration<N>(c);
         }

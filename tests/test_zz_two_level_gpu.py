@@ -1,0 +1,40 @@
+"""GPU: the optional two-level preconditioner (option coarse_aggregates; csrc/coarse.inl): same solution as the
+direct solve, clearly fewer iterations than block-Jacobi alone (CPU prototype tools/proto_two_level.py: 555 -> ~180
+on this problem with ~100 nodes per aggregate), reusable across solves and switchable between them.
+Written after the round-1 GPU budget was spent: first run is in round 2."""
+import numpy as np
+import pytest
+
+import meshfem_oracle as orc
+from util import cantilever_problem, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mfem(lib_built):
+    import meshfem_b200
+    return meshfem_b200
+
+
+@pytest.mark.parametrize("N,deg,sizes,aggregates", [(3, 2, (20, 4, 4), 128), (3, 1, (24, 6, 6), 64), (2, 2, (40, 8), 32)])
+def test_two_level_pcg_matches_direct_solve_with_fewer_iterations(mfem, N, deg, sizes, aggregates):
+    sim, fixed, vals, f = cantilever_problem(N, deg, sizes)
+    u_ref = sim.solve(f)
+    with mfem.Handle(0) as h:
+        h.set_mesh(sim.mesh.N, sim.mesh.deg, sim.mesh.nodes, sim.mesh.elem_nodes)
+        h.set_material(sim.D)
+        h.assemble()
+        h.fix_variables(fixed, vals)
+        u0, info0 = h.solve(f, rtol=1e-10, return_info=True)
+        h.set_option("coarse_aggregates", aggregates)
+        u1, info1 = h.solve(f, rtol=1e-10, return_info=True)
+        u2, info2 = h.solve(2.0 * f, rtol=1e-10, return_info=True)          # coarse space reused
+        h.set_option("coarse_aggregates", 0)
+        u3, info3 = h.solve(f, rtol=1e-10, return_info=True)                # and switched off again
+    assert info0[0]["converged"] and info1[0]["converged"] and info2[0]["converged"]
+    assert rel_l2(u0, u_ref) < 1e-7 and rel_l2(u1, u_ref) < 1e-7
+    assert rel_l2(u2, 2.0 * u_ref) < 1e-7 and rel_l2(u3, u_ref) < 1e-7
+    assert info1[0]["iterations"] < 0.6 * info0[0]["iterations"], (info0[0]["iterations"], info1[0]["iterations"])
+    assert abs(info2[0]["iterations"] - info1[0]["iterations"]) <= 0.2 * info1[0]["iterations"] + 5
+    assert info3[0]["iterations"] == info0[0]["iterations"]
