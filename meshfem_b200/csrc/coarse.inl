@@ -149,7 +149,8 @@ k_coarse_matrix(int64_t nb, int64_t S, const int64_t *__restrict__ rowptr, const
 }
 
 // dead modes (all-zero rows: aggregates without free variables, rotations without coordinates) get a unit diagonal;
-// a relative shift keeps E safely positive definite
+// a relative diagonal shift keeps E positive definite when an aggregate has too few free nodes for six independent
+// modes (1e-8: far above rounding, far below anything that matters for a preconditioner)
 __global__ void k_coarse_regularize(int64_t nc, double *E, double shift) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= nc) return;
@@ -311,7 +312,7 @@ static void build_coarse_impl(mfem_b200_ctx *c) {
     }
     const int grid = (int)std::min<int64_t>((nb + 7) / 8, (int64_t)sm_count(c) * 8);
     k_coarse_matrix<N><<<grid, 256, 0, s>>>(nb, S, c->rowptr, c->colidx, c->vals, c->fixedMask, cs.Y, cs.Einv);
-    k_coarse_regularize<<<grid_for(nc, 256), 256, 0, s>>>(nc, cs.Einv, 1e-12);
+    k_coarse_regularize<<<grid_for(nc, 256), 256, 0, s>>>(nc, cs.Einv, 1e-8);
     c->launches += 2;
     MFEM_CUDA(cudaGetLastError());
     // explicit inverse: E = L L^T, E^-1 from the factor
