@@ -1,6 +1,7 @@
 """GPU: the optional two-level preconditioner (option coarse_aggregates; csrc/coarse.inl): same solution as the
 direct solve, clearly fewer iterations than block-Jacobi alone (CPU prototype tools/proto_two_level.py: 555 -> ~180
-on this problem with ~100 nodes per aggregate), reusable across solves and switchable between them.
+on this problem with ~100 nodes per aggregate; a numpy emulation of exactly the device algorithm on the three
+cases below gives ratios 0.36 / 0.44 / 0.36, so 0.7 leaves margin for ordering differences), reusable across solves and switchable between them.
 Written after the round-1 GPU budget was spent: first run is in round 2."""
 import numpy as np
 import pytest
@@ -17,7 +18,7 @@ def mfem(lib_built):
     return meshfem_b200
 
 
-@pytest.mark.parametrize("N,deg,sizes,aggregates", [(3, 2, (20, 4, 4), 128), (3, 1, (24, 6, 6), 64), (2, 2, (40, 8), 32)])
+@pytest.mark.parametrize("N,deg,sizes,aggregates", [(3, 2, (20, 4, 4), 128), (3, 1, (24, 6, 6), 64), (2, 2, (40, 8), 96)])
 def test_two_level_pcg_matches_direct_solve_with_fewer_iterations(mfem, N, deg, sizes, aggregates):
     sim, fixed, vals, f = cantilever_problem(N, deg, sizes)
     u_ref = sim.solve(f)
@@ -35,6 +36,6 @@ def test_two_level_pcg_matches_direct_solve_with_fewer_iterations(mfem, N, deg, 
     assert info0[0]["converged"] and info1[0]["converged"] and info2[0]["converged"]
     assert rel_l2(u0, u_ref) < 1e-7 and rel_l2(u1, u_ref) < 1e-7
     assert rel_l2(u2, 2.0 * u_ref) < 1e-7 and rel_l2(u3, u_ref) < 1e-7
-    assert info1[0]["iterations"] < 0.6 * info0[0]["iterations"], (info0[0]["iterations"], info1[0]["iterations"])
+    assert info1[0]["iterations"] < 0.7 * info0[0]["iterations"], (info0[0]["iterations"], info1[0]["iterations"])
     assert abs(info2[0]["iterations"] - info1[0]["iterations"]) <= 0.2 * info1[0]["iterations"] + 5
     assert info3[0]["iterations"] == info0[0]["iterations"]
