@@ -161,6 +161,30 @@ def cpu_port_sample(deg, mat, rtol, threads=None):
     }
 
 
+def two_level_trial(cfg, device, expect_min_uy, aggregates=2048, timeout_s=240):
+    """Extra, NOT the headline: the optional two-level preconditioner (coarse_aggregates; csrc/coarse.inl, DESIGN.md
+    section 8 item 0) on the same workload, in a subprocess with a timeout so that nothing it does can touch the
+    numbers above.  Returns the subprocess's JSON (validated there against the block-Jacobi tip deflection and the
+    true residual) or {"error": ...}."""
+    cmd = [sys.executable, os.path.join(ROOT, "tools", "two_level_trial.py"), "--config", cfg, "--aggregates", str(aggregates),
+           "--device", str(device), "--rtol", str(RTOL)]
+    if expect_min_uy is not None:
+        cmd += ["--expect-min-uy", repr(float(expect_min_uy))]
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s, cwd=ROOT)
+        lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+        if not lines:
+            return {"error": f"no output (exit {r.returncode}): {r.stderr[-300:]}"}
+        out = json.loads(lines[-1])
+    except subprocess.TimeoutExpired:
+        return {"error": f"timed out after {timeout_s}s"}
+    except Exception as e:  # noqa: BLE001
+        return {"error": f"{type(e).__name__}: {e}"[:300]}
+    out["note"] = ("experimental option, reported beside the block-Jacobi headline; single GPU only, so the headline stays "
+                   "block-Jacobi to keep the 1/2/4/8-GPU series on one algorithm")
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -296,6 +320,7 @@ def run_ours(args):
            "seconds_per_step": e2e_s / n_e2e, "steps": n_e2e, "min_uy": tip,
            "includes": "handle creation, mesh upload, DoF reordering, symbolic pattern, assembly, constraints, PCG, result download"}
 
+    two_level = two_level_trial(name, local_rank, tip) if not args.no_two_level_trial else None
     cpu = cpu_port_sample(deg, mat, RTOL) if not args.no_cpu_baseline else None
     if cpu:
         for k in ("seconds", "elements", "pcg_iterations"):
@@ -314,6 +339,7 @@ def run_ours(args):
         "symbolic_pattern_ms": 1e3 * pattern_s, "wall_ms_per_step": 1e3 * wall / args.steps,
         "mesh_generation_s": t_gen,
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "two_level_trial": two_level,
     }
     print(json.dumps(out), flush=True)
 
@@ -326,6 +352,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="cfg5")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-two-level-trial", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
