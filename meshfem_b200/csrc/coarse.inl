@@ -10,7 +10,7 @@
 // plus a dense (6S)^2 GEMV, a few percent of the SpMV.
 //
 // STATUS: written after the round-1 GPU budget was spent -- compiled, never run on a GPU; opt-in only.
-//   * single GPU, single right-hand side (the batched PCG ignores it);
+//   * single right-hand side (the batched PCG ignores it); one GPU here, the multi-GPU variant is further down;
 //   * E is dense and inverted explicitly with cuSOLVER (potrf + potri), loaded with dlopen so that the library has no
 //     link-time dependency on it: a setup step of O((6S)^3), not on the per-iteration path;
 //   * restriction uses FP64 atomics: the solve is no longer bit-reproducible run to run with this option on.
@@ -22,6 +22,8 @@ struct CoarseSpace {
     DevBuf<double> Y;                 // [nDofs*N] DoF position relative to its aggregate's centroid (internal order)
     DevBuf<double> Einv;              // [nc*nc] row-major, symmetric
     DevBuf<double> cvec, yvec;        // [nc]
+    bool indexed = false;             // multi-GPU: aggregate ids from the array below (owner-based aggregates)
+    DevBuf<int32_t> agg;              // [nDofs] global aggregate of every local DoF (indexed only)
 };
 
 __host__ __device__ __forceinline__ int64_t coarse_agg(int64_t i, int64_t S, int64_t nb) { return (i * S) / nb; }
@@ -215,7 +217,7 @@ k_coarse_gemv(int64_t nc, const double *__restrict__ Einv, const double *__restr
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         if (lane == 0) { yvec[row] = s; dot += s * cvec[row]; }
     }
-    if (lane == 0 && dot != 0.0) atomicAdd(rzOut, dot);
+    if (rzOut && lane == 0 && dot != 0.0) atomicAdd(rzOut, dot);
 }
 
 // z += mask(Z y) [and p = z for the initial direction]; clears c for the next application
@@ -281,6 +283,40 @@ static void free_coarse(mfem_b200_ctx *c) {
     c->coarse = nullptr;
 }
 
+// E (assembled, both triangles) -> regularised -> explicit inverse in place (potrf + potri + mirror)
+static void invert_coarse_matrix(mfem_b200_ctx *c, CoarseSpace &cs) {
+    cudaStream_t s = c->stream;
+    const int64_t nc = cs.nc;
+    k_coarse_regularize<<<grid_for(nc, 256), 256, 0, s>>>(nc, cs.Einv, 1e-8);
+    c->launches++;
+    MFEM_CUDA(cudaGetLastError());
+    // explicit inverse: E = L L^T, E^-1 from the factor
+    CusolverApi &api = cusolver_api();
+    cusolverDnHandle_t h = nullptr;
+    MFEM_REQUIRE(api.create(&h) == CUSOLVER_STATUS_SUCCESS, MFEM_B200_ERR_CUDA, "cusolverDnCreate failed");
+    struct Guard { CusolverApi &a; cusolverDnHandle_t h; ~Guard() { if (h) a.destroy(h); } } guard{api, h};
+    MFEM_REQUIRE(api.setStream(h, s) == CUSOLVER_STATUS_SUCCESS, MFEM_B200_ERR_CUDA, "cusolverDnSetStream failed");
+    int lw1 = 0, lw2 = 0;
+    MFEM_REQUIRE(api.potrfBuf(h, CUBLAS_FILL_MODE_LOWER, (int)nc, cs.Einv, (int)nc, &lw1) == CUSOLVER_STATUS_SUCCESS, MFEM_B200_ERR_CUDA, "potrf_bufferSize failed");
+    MFEM_REQUIRE(api.potriBuf(h, CUBLAS_FILL_MODE_LOWER, (int)nc, cs.Einv, (int)nc, &lw2) == CUSOLVER_STATUS_SUCCESS, MFEM_B200_ERR_CUDA, "potri_bufferSize failed");
+    DevBuf<double> wbuf((size_t)std::max(lw1, lw2) + 1);
+    DevBuf<int> info(1);
+    int hinfo = 0;
+    MFEM_REQUIRE(api.potrf(h, CUBLAS_FILL_MODE_LOWER, (int)nc, cs.Einv, (int)nc, wbuf, lw1, info) == CUSOLVER_STATUS_SUCCESS, MFEM_B200_ERR_CUDA, "potrf failed");
+    MFEM_CUDA(cudaMemcpyAsync(&hinfo, info, sizeof(int), cudaMemcpyDeviceToHost, s));
+    MFEM_CUDA(cudaStreamSynchronize(s));
+    MFEM_REQUIRE(hinfo == 0, MFEM_B200_ERR_NOT_SPD, "coarse matrix is not positive definite (leading minor " + std::to_string(hinfo) +
+                                                         "): fewer aggregates, or a singular system");
+    MFEM_REQUIRE(api.potri(h, CUBLAS_FILL_MODE_LOWER, (int)nc, cs.Einv, (int)nc, wbuf, lw2, info) == CUSOLVER_STATUS_SUCCESS, MFEM_B200_ERR_CUDA, "potri failed");
+    MFEM_CUDA(cudaMemcpyAsync(&hinfo, info, sizeof(int), cudaMemcpyDeviceToHost, s));
+    MFEM_CUDA(cudaStreamSynchronize(s));
+    MFEM_REQUIRE(hinfo == 0, MFEM_B200_ERR_NOT_SPD, "coarse matrix inversion failed (" + std::to_string(hinfo) + ")");
+    k_coarse_symmetrize<<<dim3((unsigned)grid_for(nc, 256), (unsigned)nc), 256, 0, s>>>(nc, cs.Einv);
+    c->launches++;
+    MFEM_CUDA(cudaStreamSynchronize(s));
+    MFEM_CUDA(cudaGetLastError());
+}
+
 template <int N>
 static void build_coarse_impl(mfem_b200_ctx *c) {
     constexpr int M = N == 3 ? 6 : 3;
@@ -312,39 +348,291 @@ static void build_coarse_impl(mfem_b200_ctx *c) {
     }
     const int grid = (int)std::min<int64_t>((nb + 7) / 8, (int64_t)sm_count(c) * 8);
     k_coarse_matrix<N><<<grid, 256, 0, s>>>(nb, S, c->rowptr, c->colidx, c->vals, c->fixedMask, cs.Y, cs.Einv);
-    k_coarse_regularize<<<grid_for(nc, 256), 256, 0, s>>>(nc, cs.Einv, 1e-8);
-    c->launches += 2;
-    MFEM_CUDA(cudaGetLastError());
-    // explicit inverse: E = L L^T, E^-1 from the factor
-    CusolverApi &api = cusolver_api();
-    cusolverDnHandle_t h = nullptr;
-    MFEM_REQUIRE(api.create(&h) == CUSOLVER_STATUS_SUCCESS, MFEM_B200_ERR_CUDA, "cusolverDnCreate failed");
-    struct Guard { CusolverApi &a; cusolverDnHandle_t h; ~Guard() { if (h) a.destroy(h); } } guard{api, h};
-    MFEM_REQUIRE(api.setStream(h, s) == CUSOLVER_STATUS_SUCCESS, MFEM_B200_ERR_CUDA, "cusolverDnSetStream failed");
-    int lw1 = 0, lw2 = 0;
-    MFEM_REQUIRE(api.potrfBuf(h, CUBLAS_FILL_MODE_LOWER, (int)nc, cs.Einv, (int)nc, &lw1) == CUSOLVER_STATUS_SUCCESS, MFEM_B200_ERR_CUDA, "potrf_bufferSize failed");
-    MFEM_REQUIRE(api.potriBuf(h, CUBLAS_FILL_MODE_LOWER, (int)nc, cs.Einv, (int)nc, &lw2) == CUSOLVER_STATUS_SUCCESS, MFEM_B200_ERR_CUDA, "potri_bufferSize failed");
-    DevBuf<double> wbuf((size_t)std::max(lw1, lw2) + 1);
-    DevBuf<int> info(1);
-    int hinfo = 0;
-    MFEM_REQUIRE(api.potrf(h, CUBLAS_FILL_MODE_LOWER, (int)nc, cs.Einv, (int)nc, wbuf, lw1, info) == CUSOLVER_STATUS_SUCCESS, MFEM_B200_ERR_CUDA, "potrf failed");
-    MFEM_CUDA(cudaMemcpyAsync(&hinfo, info, sizeof(int), cudaMemcpyDeviceToHost, s));
-    MFEM_CUDA(cudaStreamSynchronize(s));
-    MFEM_REQUIRE(hinfo == 0, MFEM_B200_ERR_NOT_SPD, "coarse matrix is not positive definite (leading minor " + std::to_string(hinfo) +
-                                                         "): fewer aggregates, or a singular system");
-    MFEM_REQUIRE(api.potri(h, CUBLAS_FILL_MODE_LOWER, (int)nc, cs.Einv, (int)nc, wbuf, lw2, info) == CUSOLVER_STATUS_SUCCESS, MFEM_B200_ERR_CUDA, "potri failed");
-    MFEM_CUDA(cudaMemcpyAsync(&hinfo, info, sizeof(int), cudaMemcpyDeviceToHost, s));
-    MFEM_CUDA(cudaStreamSynchronize(s));
-    MFEM_REQUIRE(hinfo == 0, MFEM_B200_ERR_NOT_SPD, "coarse matrix inversion failed (" + std::to_string(hinfo) + ")");
-    k_coarse_symmetrize<<<dim3((unsigned)grid_for(nc, 256), (unsigned)nc), 256, 0, s>>>(nc, cs.Einv);
     c->launches++;
-    MFEM_CUDA(cudaStreamSynchronize(s));
     MFEM_CUDA(cudaGetLastError());
+    invert_coarse_matrix(c, cs);
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Multi-GPU variant (nRanks > 1).  Every rank aggregates the DoFs it OWNS (S / nRanks aggregates per rank, contiguous
+// runs of its owned DoFs in internal order; global aggregate id = rank * S_r + local id).  A DoF shared with other
+// ranks carries its OWNER's aggregate id and its owner's centred position on every sharer (one interface
+// sum-exchange at setup in which only the owner contributes), so the rows of Z agree on all sharers and
+//     E = Z^T K Z = sum over ranks of Z_loc^T K_loc Z_loc      (K_loc holds partial sums on interface rows)
+// is one all-reduce of the (M S)^2 partial matrices; every rank then inverts E redundantly.  Per application:
+// restriction over owned DoFs, all-reduce of the M S coarse residuals (98 kB at S = 2048), the dense GEMV replicated
+// on every rank, prolongation on all local DoFs (consistent on shared DoFs, like the block-Jacobi part).  The scalar
+// c.y is added to the already all-reduced r.z by a single-CTA fixed-order reduction so that every rank holds the same
+// bits.  Aggregate ids come from an array here (the single-GPU kernels above use the closed form), and runs of equal
+// ids inside a warp are found with head flags because foreign aggregates may interleave.
+// STATUS: written without GPU access -- compiled, never run; opt-in like the single-GPU variant.
+
+// lanes [lane+1, lane+o] hold no run head  <=>  lane+o belongs to lane's run
+__device__ __forceinline__ bool coarse_same_run(unsigned heads, int lane, int o) {
+    return (lane + o < 32) && (((heads >> (lane + 1)) & ((1u << o) - 1u)) == 0u);
+}
+
+// owned DoFs: T[i] = (aggregate id + 1, position); centroid sums per LOCAL aggregate.  Non-owned rows stay zero.
+template <int N>
+__global__ void k_coarse_positions_idx(int64_t nb, int64_t aggBase, const int32_t *__restrict__ agg, int64_t nNodes,
+                                       const int32_t *__restrict__ firstNode, const double *__restrict__ nodes,
+                                       double *__restrict__ T, double *cen) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= nb) return;
+    const int64_t a = agg[i];
+    if (a < 0) return;
+    T[i * (N + 1)] = (double)(a + 1);
+    const int64_t node = firstNode[i];
+    if (node < 0 || node >= nNodes) return;
+    for (int k = 0; k < N; ++k) {
+        const double x = nodes[node * N + k];
+        T[i * (N + 1) + 1 + k] = x;
+        atomicAdd(&cen[(a - aggBase) * (N + 1) + k], x);
+    }
+    atomicAdd(&cen[(a - aggBase) * (N + 1) + N], 1.0);
+}
+template <int N>
+__global__ void k_coarse_center_idx(int64_t nb, int64_t aggBase, const int32_t *__restrict__ agg, int64_t nNodes,
+                                    const int32_t *__restrict__ firstNode, const double *__restrict__ cen, double *__restrict__ T) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= nb) return;
+    const int64_t a = agg[i];
+    if (a < 0) return;
+    const int64_t node = firstNode[i];
+    if (node < 0 || node >= nNodes) return;
+    const double cnt = cen[(a - aggBase) * (N + 1) + N];
+    if (cnt > 0.0)
+        for (int k = 0; k < N; ++k) T[i * (N + 1) + 1 + k] -= cen[(a - aggBase) * (N + 1) + k] / cnt;
+}
+// after the owner-contributes sum-exchange: split T into agg / Y on every local DoF
+template <int N>
+__global__ void k_coarse_unpack(int64_t nb, int64_t S, const double *__restrict__ T, int32_t *__restrict__ agg,
+                                double *__restrict__ Y, int *bad) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= nb) return;
+    int64_t a = llrint(T[i * (N + 1)]) - 1;
+    if (a < 0 || a >= S) { atomicAdd(bad, 1); a = 0; }
+    agg[i] = (int32_t)a;
+    for (int k = 0; k < N; ++k) Y[i * N + k] = T[i * (N + 1) + 1 + k];
+}
+
+// E_loc += Z_loc^T K_loc Z_loc with aggregate ids from the array
+template <int N>
+__global__ void __launch_bounds__(256)
+k_coarse_matrix_idx(int64_t nb, int64_t S, const int32_t *__restrict__ agg, const int64_t *__restrict__ rowptr,
+                    const int32_t *__restrict__ colidx, const double *__restrict__ vals, const uint8_t *__restrict__ fixedMask,
+                    const double *__restrict__ Y, double *E) {
+    constexpr int M = N == 3 ? 6 : 3;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nWarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t nc = (int64_t)M * S;
+    for (int64_t row = warp; row < nb; row += nWarps) {
+        const int64_t b0 = rowptr[row], n = rowptr[row + 1] - b0;
+        const int64_t ai = agg[row];
+        double yi[N];
+        bool fi[N];
+        for (int k = 0; k < N; ++k) { yi[k] = Y[row * N + k]; fi[k] = fixedMask[row * N + k] != 0; }
+        for (int64_t j0 = 0; j0 < n; j0 += 32) {
+            const int64_t j = j0 + lane;
+            const bool active = j < n;
+            double C[M][M];
+            int64_t aj = -1 - lane;
+            for (int a = 0; a < M; ++a) for (int b = 0; b < M; ++b) C[a][b] = 0.0;
+            if (active) {
+                const int64_t col = colidx[b0 + j];
+                aj = agg[col];
+                double yj[N];
+                for (int k = 0; k < N; ++k) yj[k] = Y[col * N + k];
+                double T[N][M];
+                for (int r = 0; r < N; ++r) {
+                    double krow[N];
+                    for (int cc = 0; cc < N; ++cc)
+                        krow[cc] = (fi[r] || fixedMask[col * N + cc]) ? 0.0 : vals[val_index<N>(b0, n, j, r, cc)];
+                    coarse_Rt<N>(yj, krow, T[r]);
+                }
+                for (int b = 0; b < M; ++b) {
+                    double tcol[N], q[M];
+                    for (int r = 0; r < N; ++r) tcol[r] = T[r][b];
+                    coarse_Rt<N>(yi, tcol, q);
+                    for (int a = 0; a < M; ++a) C[a][b] = q[a];
+                }
+            }
+            const int64_t ajPrev = __shfl_up_sync(0xffffffffu, aj, 1);
+            const bool head = (lane == 0) || (ajPrev != aj);
+            const unsigned heads = __ballot_sync(0xffffffffu, head);
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const bool take = coarse_same_run(heads, lane, o);
+                for (int a = 0; a < M; ++a)
+                    for (int b = 0; b < M; ++b) {
+                        const double other = __shfl_down_sync(0xffffffffu, C[a][b], o);
+                        if (take) C[a][b] += other;
+                    }
+            }
+            if (active && head)
+                for (int a = 0; a < M; ++a)
+                    for (int b = 0; b < M; ++b)
+                        if (C[a][b] != 0.0) atomicAdd(&E[(ai * M + a) * nc + aj * M + b], C[a][b]);
+        }
+    }
+}
+
+// c += Z^T r over the OWNED free variables
+template <int N>
+__global__ void __launch_bounds__(kVecThreads)
+k_coarse_restrict_idx(int64_t nb, const int32_t *__restrict__ agg, const uint8_t *__restrict__ owned,
+                      const double *__restrict__ r, const uint8_t *__restrict__ fixedMask, const double *__restrict__ Y,
+                      double *cvec, const int *status) {
+    constexpr int M = N == 3 ? 6 : 3;
+    if (status && status[ST_STATE] != 0) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nWarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t base = warp * 32; base < nb; base += nWarps * 32) {
+        const int64_t i = base + lane;
+        double q[M];
+        int64_t a = -1 - lane;
+        for (int m = 0; m < M; ++m) q[m] = 0.0;
+        if (i < nb) {
+            a = agg[i];
+            const bool mine = owned[i] != 0;
+            double v[N], y[N];
+            for (int k = 0; k < N; ++k) { v[k] = (!mine || fixedMask[i * N + k]) ? 0.0 : r[i * N + k]; y[k] = Y[i * N + k]; }
+            coarse_Rt<N>(y, v, q);
+        }
+        const int64_t aPrev = __shfl_up_sync(0xffffffffu, a, 1);
+        const bool head = (lane == 0) || (aPrev != a);
+        const unsigned heads = __ballot_sync(0xffffffffu, head);
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const bool take = coarse_same_run(heads, lane, o);
+            for (int m = 0; m < M; ++m) {
+                const double other = __shfl_down_sync(0xffffffffu, q[m], o);
+                if (take) q[m] += other;
+            }
+        }
+        if (i < nb && head)
+            for (int m = 0; m < M; ++m)
+                if (q[m] != 0.0) atomicAdd(&cvec[a * M + m], q[m]);
+    }
+}
+
+// rz += c.y in a fixed order (one CTA): bit-identical on every rank, which holds the same c and y
+__global__ void __launch_bounds__(256) k_coarse_cy(int64_t nc, const double *__restrict__ cvec, const double *__restrict__ yvec,
+                                                   double *rzOut, const int *status) {
+    if (status && status[ST_STATE] != 0) return;
+    __shared__ double sh[256];
+    double s = 0.0;
+    for (int64_t k = threadIdx.x; k < nc; k += 256) s = fma(cvec[k], yvec[k], s);
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *rzOut += sh[0];
+}
+
+// z += mask(Z y) on every local DoF [and p = z]; clears c for the next application
+template <int N>
+__global__ void __launch_bounds__(kVecThreads)
+k_coarse_prolong_idx(int64_t nb, const int32_t *__restrict__ agg, const double *__restrict__ yvec,
+                     const uint8_t *__restrict__ fixedMask, const double *__restrict__ Y, double *__restrict__ z, double *p,
+                     double *cvec, int64_t nc, const int *status) {
+    constexpr int M = N == 3 ? 6 : 3;
+    if (status && status[ST_STATE] != 0) return;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x, t0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    for (int64_t i = t0; i < nb; i += stride) {
+        const int64_t a = agg[i];
+        double c[M], y[N], v[N];
+        for (int m = 0; m < M; ++m) c[m] = yvec[a * M + m];
+        for (int k = 0; k < N; ++k) y[k] = Y[i * N + k];
+        coarse_R<N>(y, c, v);
+        for (int k = 0; k < N; ++k) {
+            const double zk = z[i * N + k] + (fixedMask[i * N + k] ? 0.0 : v[k]);
+            z[i * N + k] = zk;
+            if (p) p[i * N + k] = zk;
+        }
+    }
+    for (int64_t k = t0; k < nc; k += stride) cvec[k] = 0.0;      // nobody reads c in this kernel
+}
+
+template <int N>
+static void build_coarse_multi_impl(mfem_b200_ctx *c) {
+    constexpr int M = N == 3 ? 6 : 3;
+    cudaStream_t s = c->stream;
+    const int64_t nb = c->nDofs;
+    const uint8_t *ownedDev = halo_owned(c);
+    // aggregates per rank: the same on every rank (the option and nRanks are), so global ids need no negotiation
+    const int64_t Sr = std::max<int64_t>(1, std::min<int64_t>(c->opt_coarse, 32768 / M) / c->nRanks);
+    const int64_t S = Sr * c->nRanks, aggBase = Sr * c->rank;
+    free_coarse(c);
+    c->coarse = new CoarseSpace();
+    CoarseSpace &cs = *c->coarse;
+    cs.S = (int)S; cs.M = M; cs.nc = M * S; cs.indexed = true;
+    const int64_t nc = cs.nc;
+    // owned DoFs in internal order -> contiguous runs (host: setup only, one byte per DoF each way)
+    std::vector<uint8_t> ownedHost((size_t)nb);
+    MFEM_CUDA(cudaMemcpyAsync(ownedHost.data(), ownedDev, (size_t)nb, cudaMemcpyDeviceToHost, s));
+    MFEM_CUDA(cudaStreamSynchronize(s));
+    int64_t nOwned = 0;
+    for (int64_t i = 0; i < nb; ++i) nOwned += ownedHost[i] != 0;
+    std::vector<int32_t> aggHost((size_t)nb, -1);
+    int64_t k = 0;
+    for (int64_t i = 0; i < nb; ++i)
+        if (ownedHost[i]) { aggHost[i] = (int32_t)(aggBase + std::min<int64_t>(Sr - 1, (k * Sr) / std::max<int64_t>(nOwned, 1))); ++k; }
+    cs.agg.alloc((size_t)nb);
+    MFEM_CUDA(cudaMemcpyAsync(cs.agg, aggHost.data(), sizeof(int32_t) * (size_t)nb, cudaMemcpyHostToDevice, s));
+    cs.Y.alloc((size_t)nb * N);
+    cs.Einv.alloc((size_t)nc * nc);
+    cs.cvec.alloc((size_t)nc); cs.yvec.alloc((size_t)nc);
+    MFEM_CUDA(cudaMemsetAsync(cs.Einv, 0, cs.Einv.bytes(), s));
+    MFEM_CUDA(cudaMemsetAsync(cs.cvec, 0, cs.cvec.bytes(), s));
+    {
+        DevBuf<double> T((size_t)nb * (N + 1));
+        DevBuf<int32_t> firstNode((size_t)nb);
+        DevBuf<double> cen((size_t)Sr * (N + 1));
+        DevBuf<int> bad(1);
+        MFEM_CUDA(cudaMemsetAsync(T, 0, T.bytes(), s));
+        MFEM_CUDA(cudaMemsetAsync(firstNode, 0x7f, firstNode.bytes(), s));
+        MFEM_CUDA(cudaMemsetAsync(cen, 0, cen.bytes(), s));
+        MFEM_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), s));
+        const bool havePositions = !c->externalMatrix && c->nNodes > 0;
+        if (havePositions) {
+            k_coarse_first_node<<<grid_for(c->nNodes, 256), 256, 0, s>>>(c->nNodes, c->nodeDof, firstNode);
+            c->launches++;
+        }
+        k_coarse_positions_idx<N><<<grid_for(nb, 256), 256, 0, s>>>(nb, aggBase, cs.agg, havePositions ? c->nNodes : 0, firstNode,
+                                                                    c->nodes, T, cen);
+        k_coarse_center_idx<N><<<grid_for(nb, 256), 256, 0, s>>>(nb, aggBase, cs.agg, havePositions ? c->nNodes : 0, firstNode, cen, T);
+        c->launches += 2;
+        halo_exchange_add(c, T, N + 1);                       // only the owner's rows are non-zero
+        k_coarse_unpack<N><<<grid_for(nb, 256), 256, 0, s>>>(nb, S, T, cs.agg, cs.Y, bad);
+        c->launches++;
+        int nbad = 0;
+        MFEM_CUDA(cudaMemcpyAsync(&nbad, bad, sizeof(int), cudaMemcpyDeviceToHost, s));
+        MFEM_CUDA(cudaStreamSynchronize(s));                  // also: T / firstNode / cen / aggHost go out of scope
+        MFEM_CUDA(cudaGetLastError());
+        // no throw before the collectives below: every rank must reach them; a bad rank poisons E instead
+        if (nbad) MFEM_CUDA(cudaMemsetAsync(cs.Einv, 0xff, sizeof(double), s));   // NaN in E[0] -> potrf fails on all ranks
+    }
+    const int grid = (int)std::min<int64_t>((nb + 7) / 8, (int64_t)sm_count(c) * 8);
+    k_coarse_matrix_idx<N><<<grid, 256, 0, s>>>(nb, S, cs.agg, c->rowptr, c->colidx, c->vals, c->fixedMask, cs.Y, cs.Einv);
+    c->launches++;
+    MFEM_CUDA(cudaGetLastError());
+    // one all-reduce of the partial coarse matrices (chunked: NCCL counts are size_t, but keep single calls moderate)
+    const size_t total = (size_t)nc * nc, chunk = (size_t)1 << 27;
+    for (size_t off = 0; off < total; off += chunk)
+        allreduce_sum(c, cs.Einv.p + off, cs.Einv.p + off, (int)std::min(chunk, total - off));
+    invert_coarse_matrix(c, cs);
 }
 
 static void build_coarse(mfem_b200_ctx *c) {
-    MFEM_REQUIRE(c->nRanks == 1, MFEM_B200_ERR_INVALID, "coarse_aggregates: single-GPU only in this version");
     ScopedTimer timer(c, "Coarse Space");
+    if (c->nRanks > 1) {
+        if (c->N == 3) build_coarse_multi_impl<3>(c); else build_coarse_multi_impl<2>(c);
+        return;
+    }
     if (c->N == 3) build_coarse_impl<3>(c); else build_coarse_impl<2>(c);
 }
 
@@ -354,6 +642,16 @@ static void apply_coarse(mfem_b200_ctx *c, const double *r, double *z, double *p
     CoarseSpace &cs = *c->coarse;
     cudaStream_t s = c->stream;
     const int vgrid = vec_grid(c, c->nDofs);
+    if (cs.indexed) {
+        const int ggridM = (int)std::min<int64_t>((cs.nc + 7) / 8, (int64_t)sm_count(c) * 8);
+        k_coarse_restrict_idx<N><<<vgrid, kVecThreads, 0, s>>>(c->nDofs, cs.agg, halo_owned(c), r, c->fixedMask, cs.Y, cs.cvec, status);
+        allreduce_sum(c, cs.cvec, cs.cvec, (int)cs.nc);
+        k_coarse_gemv<<<ggridM, 256, 0, s>>>(cs.nc, cs.Einv, cs.cvec, cs.yvec, nullptr, status);
+        k_coarse_cy<<<1, 256, 0, s>>>(cs.nc, cs.cvec, cs.yvec, rzSlot, status);
+        k_coarse_prolong_idx<N><<<vgrid, kVecThreads, 0, s>>>(c->nDofs, cs.agg, cs.yvec, c->fixedMask, cs.Y, z, p, cs.cvec, cs.nc, status);
+        c->launches += 4;
+        return;
+    }
     k_coarse_restrict<N><<<vgrid, kVecThreads, 0, s>>>(c->nDofs, cs.S, r, c->fixedMask, cs.Y, cs.cvec, status);
     const int ggrid = (int)std::min<int64_t>((cs.nc + 7) / 8, (int64_t)sm_count(c) * 8);
     k_coarse_gemv<<<ggrid, 256, 0, s>>>(cs.nc, cs.Einv, cs.cvec, cs.yvec, rzSlot, status);

@@ -90,14 +90,85 @@ def main():
         pvec = z + (rzn / rz) * pvec
         rz = rzn
     u = (x + ufix).reshape(-1, N)
+
+    # ---- two-level variant, exactly the multi-GPU algorithm of csrc/coarse.inl (build_coarse_multi_impl): aggregates
+    # over the OWNED DoFs of each rank (contiguous runs along a Morton curve, the device's internal order), owner's
+    # aggregate id and centred position sent to the sharers by a sum-exchange in which only the owner contributes,
+    # E = all-reduce of Z_loc' K_loc Z_loc, restriction over owned DoFs + all-reduce, replicated coarse solve,
+    # prolongation on every local DoF, r.z corrected by c.y after its all-reduce.
+    Sr, M = 4, 6
+    S = Sr * world
+    X = p.nodes
+    q = np.floor((X - X.min(0)) / (X.max(0) - X.min(0)).max() * 1023).astype(np.int64)
+    key = np.zeros(p.num_nodes, dtype=np.int64)
+    for bit in range(10):
+        for kk in range(3):
+            key |= ((q[:, kk] >> bit) & 1) << (3 * bit + kk)
+    order = np.argsort(key, kind="stable")                    # internal order
+    own_n = p.owned.astype(bool)
+    rank_in_owned = np.cumsum(own_n[order]) - 1
+    agg = np.full(p.num_nodes, -1, dtype=np.int64)
+    sel = order[own_n[order]]
+    agg[sel] = rank * Sr + np.minimum(Sr - 1, (rank_in_owned[own_n[order]] * Sr) // max(int(own_n.sum()), 1))
+    T = np.zeros((p.num_nodes, 4))
+    cen = np.zeros((Sr, 4))
+    np.add.at(cen, agg[own_n] - rank * Sr, np.hstack([X[own_n], np.ones((int(own_n.sum()), 1))]))
+    T[own_n, 0] = agg[own_n] + 1
+    T[own_n, 1:] = X[own_n] - (cen[:, :3] / np.maximum(cen[:, 3:], 1))[agg[own_n] - rank * Sr]
+    T = exchange_add(T.reshape(-1).copy(), 4).reshape(p.num_nodes, 4)
+    agg = np.rint(T[:, 0]).astype(np.int64) - 1
+    assert agg.min() >= 0 and agg.max() < S
+    Y = T[:, 1:]
+    R = np.zeros((p.num_nodes, N, M))
+    R[:, 0, 0] = R[:, 1, 1] = R[:, 2, 2] = 1.0
+    R[:, 1, 3], R[:, 2, 3] = -Y[:, 2], Y[:, 1]
+    R[:, 0, 4], R[:, 2, 4] = Y[:, 2], -Y[:, 0]
+    R[:, 0, 5], R[:, 1, 5] = -Y[:, 1], Y[:, 0]
+    import scipy.sparse as sp
+    rows = np.repeat(np.arange(n), M)
+    cols = (M * np.repeat(agg, N)[:, None] + np.arange(M)[None, :]).reshape(-1)
+    Z = sp.csr_matrix((R.reshape(-1) * np.repeat(free, M), (rows, cols)), shape=(n, M * S))
+    Et = torch.from_numpy((Z.T @ K @ Z).toarray())
+    dist.all_reduce(Et)
+    E = Et.numpy()
+    d = np.diag(E).copy()
+    E[np.diag_indices_from(E)] = np.where(d == 0.0, 1.0, d * (1 + 1e-8))
+    Einv = np.linalg.inv(E)
+    Zown = sp.diags(owned.astype(float)) @ Z
+
+    def coarse(rv):
+        ct = torch.from_numpy(Zown.T @ rv); dist.all_reduce(ct)
+        cv = ct.numpy(); yv = Einv @ cv
+        return Z @ yv, float(cv @ yv)
+
+    x = np.zeros(n); r = b.copy(); z = apply_M(r)
+    rz = gsum(r[owned] @ z[owned]); zc, cy = coarse(r); z = z + zc; rz += cy
+    pvec = z.copy()
+    its2 = 0
+    while its2 < 5000:
+        Ap = spmv(pvec)
+        alpha = rz / gsum(pvec[owned] @ Ap[owned])
+        x += alpha * pvec; r -= alpha * Ap
+        z = apply_M(r)
+        rzn = gsum(r[owned] @ z[owned]); rr = gsum(r[owned] @ r[owned])
+        zc, cy = coarse(r); z = z + zc; rzn += cy
+        its2 += 1
+        if rr <= 1e-24 * bb:
+            break
+        pvec = z + (rzn / rz) * pvec
+        rz = rzn
+    u2 = (x + ufix).reshape(-1, N)
     V, T = orc.grid_simplices(list(grid))
     sim = orc.Simulator(3, deg, V, T); sim.set_material(D)
     u_ref = orc.solve_fixed(sim.stiffness(), f.reshape(-1), fixed, vals).reshape(-1, N)[p.nodes_global]
     err = float(np.linalg.norm(u - u_ref) / np.linalg.norm(u_ref))
+    err2 = float(np.linalg.norm(u2 - u_ref) / np.linalg.norm(u_ref))
+    t2 = torch.tensor([err2], dtype=torch.float64); dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    assert t2.item() < 1e-8 and its2 < 0.8 * its, (t2.item(), its, its2)
     t = torch.tensor([err], dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX)
     nowned = gsum(float(p.owned.sum()))
     if rank == 0:
-        print(f"MRANK_CPU world={world} iters={its} err={t.item():.3e} owned_total={int(nowned)} nodes={m.num_nodes}", flush=True)
+        print(f"MRANK_CPU world={world} iters={its} err={t.item():.3e} two_level_iters={its2} two_level_err={t2.item():.3e} owned_total={int(nowned)} nodes={m.num_nodes}", flush=True)
     assert t.item() < 1e-8 and int(nowned) == m.num_nodes
     dist.destroy_process_group()
 

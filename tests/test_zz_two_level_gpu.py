@@ -39,3 +39,19 @@ def test_two_level_pcg_matches_direct_solve_with_fewer_iterations(mfem, N, deg, 
     assert info1[0]["iterations"] < 0.7 * info0[0]["iterations"], (info0[0]["iterations"], info1[0]["iterations"])
     assert abs(info2[0]["iterations"] - info1[0]["iterations"]) <= 0.2 * info1[0]["iterations"] + 5
     assert info3[0]["iterations"] == info0[0]["iterations"]
+
+
+def test_two_level_pcg_two_ranks(mfem):
+    """Multi-GPU variant (owner-based aggregates, all-reduced coarse matrix / residuals): tests/mgpu_two_level_check.py
+    under torchrun; skipped with fewer than 2 devices (tests/mrank_cpu_worker.py emulates the algorithm with gloo)."""
+    import os
+    import subprocess
+    import sys
+    from util import ROOT
+    n = mfem.load_library().mfem_b200_device_count()
+    if n < 2:
+        pytest.skip(f"{n} CUDA device(s) visible")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(ROOT, "tests", "mgpu_two_level_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "MGPU_TWO_LEVEL_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
