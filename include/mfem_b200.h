@@ -77,7 +77,9 @@ int mfem_b200_comm_share(mfem_b200_handle h, mfem_b200_handle parent);
  *             2 = owner-gather by DoF row (first-generation kernel, kept for A/B).
  * "coarse_aggregates": S > 0 adds an aggregation coarse space (rigid-body modes of S contiguous runs of the
  *             internal DoF numbering) to the block-Jacobi preconditioner, M^-1 = B^-1 + Z (Z'KZ)^-1 Z'
- *             (csrc/coarse.inl; single GPU, single right-hand side; default 0 = off; may be changed between solves). */
+ *             (csrc/coarse.inl; single right-hand side; on several GPUs every rank aggregates the DoFs it owns and the coarse
+ *             matrix / residuals are all-reduced -- set the same value on every rank; default 0 = off; may be changed
+ *             between solves). */
 int mfem_b200_set_option(mfem_b200_handle h, const char *name, int64_t value);
 
 /* ---- mesh ------------------------------------------------------------------------ */
