@@ -17,6 +17,11 @@
 #include <MeshFEM/Types.hh>
 
 #include <algorithm>
+#include <cstdlib>
+#include <new>
+#if defined(__linux__)
+#include <sys/mman.h>
+#endif
 #include <memory>
 #include <stdexcept>
 #include <vector>
@@ -26,25 +31,73 @@ namespace femmesh_detail {
 // open-addressing hash: 64-bit key (+32-bit tag for 96-bit keys) -> int32 value
 struct Hash96 {
     struct Slot { uint64_t k; uint32_t t; int32_t val; int32_t aux; };
-    std::vector<Slot> slots;
+    // the slot array: 2 MB-aligned and advised into transparent huge pages where the system allows it (the
+    // tables of a 10M-element mesh are GBs of randomly probed memory: with 4 kB pages every probe is also a
+    // TLB miss)
+    struct SlotArray {
+        Slot *p = nullptr;
+        size_t n = 0;
+        ~SlotArray() { std::free(p); }
+        SlotArray() = default;
+        SlotArray(const SlotArray &) = delete;
+        SlotArray &operator=(const SlotArray &) = delete;
+        void assign(size_t count, const Slot &v) {
+            std::free(p);
+            const size_t huge = size_t(2) << 20, bytes = (count * sizeof(Slot) + huge - 1) / huge * huge;
+            p = static_cast<Slot *>(std::aligned_alloc(huge, bytes));
+            if (!p) throw std::bad_alloc();
+#if defined(__linux__) && defined(MADV_HUGEPAGE)
+            madvise(p, bytes, MADV_HUGEPAGE);
+#endif
+            n = count;
+            for (size_t i = 0; i < count; ++i) p[i] = v;
+        }
+        Slot &operator[](size_t i) { return p[i]; }
+        const Slot &operator[](size_t i) const { return p[i]; }
+        const Slot *begin() const { return p; }
+        const Slot *end() const { return p + n; }
+    };
+    SlotArray slots;
     uint64_t mask;
+    size_t count = 0;
+    // `expected` is an estimate, not a bound: the table doubles when it passes 70 % load (values are
+    // kept, so nothing the callers number depends on the growth)
     explicit Hash96(size_t expected) {
         size_t cap = 16;
-        while (cap < 2 * expected + 16) cap <<= 1;
-        slots.assign(cap, Slot{~0ULL, ~0u, -1, 0});
+        while (2 * cap < 3 * expected + 32) cap <<= 1;
+        slots.assign(cap, emptySlot());
         mask = cap - 1;
     }
+    static Slot emptySlot() { return Slot{~0ULL, ~0u, -1, 0}; }
+    static bool isEmpty(const Slot &s) { return s.val == -1 && s.k == ~0ULL && s.t == ~0u; }
     static uint64_t mix(uint64_t k, uint32_t t) {
         uint64_t h = k * 0x9e3779b97f4a7c15ULL + t;
         h ^= h >> 32; h *= 0xd6e8feb86659fd93ULL; h ^= h >> 32;
         return h;
     }
-    // returns slot reference; `inserted` tells whether the key was new
+    // the build loops issue the cache-line fetch of a probe a few elements ahead of its use (same probes,
+    // same order -- numbering is unchanged)
+    void prefetch(uint64_t k, uint32_t t) const { __builtin_prefetch(&slots[mix(k, t) & mask], 1, 1); }
+    void grow() {
+        SlotArray old;
+        std::swap(old.p, slots.p); std::swap(old.n, slots.n);
+        slots.assign(2 * old.n, emptySlot());
+        mask = slots.n - 1;
+        for (const Slot &o : old) {
+            if (isEmpty(o)) continue;
+            uint64_t i = mix(o.k, o.t) & mask;
+            while (!isEmpty(slots[i])) i = (i + 1) & mask;
+            slots[i] = o;
+        }
+    }
+    // returns slot reference (valid until the next insertion); `inserted` tells whether the key was new.
+    // A new slot must be given a value != -1 or a key != ~0 by the caller (all callers set val >= 0).
     Slot &findOrInsert(uint64_t k, uint32_t t, bool &inserted) {
+        if (10 * (count + 1) > 7 * slots.n) grow();
         uint64_t i = mix(k, t) & mask;
         while (true) {
             Slot &s = slots[i];
-            if (s.val == -1 && s.k == ~0ULL && s.t == ~0u) { s.k = k; s.t = t; inserted = true; return s; }
+            if (isEmpty(s)) { s.k = k; s.t = t; inserted = true; ++count; return s; }
             if (s.k == k && s.t == t) { inserted = false; return s; }
             i = (i + 1) & mask;
         }
@@ -53,7 +106,7 @@ struct Hash96 {
         uint64_t i = mix(k, t) & mask;
         while (true) {
             const Slot &s = slots[i];
-            if (s.val == -1 && s.k == ~0ULL && s.t == ~0u) return nullptr;
+            if (isEmpty(s)) return nullptr;
             if (s.k == k && s.t == t) return &s;
             i = (i + 1) & mask;
         }
@@ -217,7 +270,12 @@ private:
         if (_Deg == 2) {
             edgeTable.reset(new Hash96(m_ne * nedge / (_K == 3 ? 4 : 1) + m_nV));
             m_edgeEnds.clear();
-            for (size_t e = 0; e < m_ne; ++e)
+            constexpr size_t kAhead = 12;
+            for (size_t e = 0; e < m_ne; ++e) {
+                if (e + kAhead < m_ne)
+                    for (size_t ei = 0; ei < nedge; ++ei)
+                        edgeTable->prefetch(pairKey(m_elemNodes[(e + kAhead) * npe + Simplex::edgeStartNode(ei)],
+                                                    m_elemNodes[(e + kAhead) * npe + Simplex::edgeEndNode(ei)]), 0);
                 for (size_t ei = 0; ei < nedge; ++ei) {
                     const int a = m_elemNodes[e * npe + Simplex::edgeStartNode(ei)];
                     const int b = m_elemNodes[e * npe + Simplex::edgeEndNode(ei)];
@@ -230,6 +288,7 @@ private:
                     }
                     m_elemNodes[e * npe + nv + ei] = (int32_t)(m_nV + slot.val);
                 }
+            }
         }
         // ---- boundary extraction
         struct BFace { int v[3]; int hf; };
@@ -237,15 +296,31 @@ private:
         if (_K == 3) {
             static const int fc[4][3] = {{1, 3, 2}, {0, 2, 3}, {0, 3, 1}, {0, 1, 2}};   // TetMesh.hh:221-226
             Hash96 faces(2 * m_ne + 16);
-            for (size_t t = 0; t < m_ne; ++t)
+            auto faceKey = [&](size_t t, int f, uint64_t &k, uint32_t &tag) {      // sorted vertex triple of face f of tet t
+                int v[3] = {m_elemNodes[t * npe + fc[f][0]], m_elemNodes[t * npe + fc[f][1]], m_elemNodes[t * npe + fc[f][2]]};
+                if (v[0] > v[1]) std::swap(v[0], v[1]);
+                if (v[1] > v[2]) std::swap(v[1], v[2]);
+                if (v[0] > v[1]) std::swap(v[0], v[1]);
+                k = ((uint64_t)(uint32_t)v[0] << 32) | (uint32_t)v[1];
+                tag = (uint32_t)v[2];
+            };
+            constexpr size_t kAhead = 12;
+            for (size_t t = 0; t < m_ne; ++t) {
+                if (t + kAhead < m_ne)
+                    for (int f = 0; f < 4; ++f) {
+                        uint64_t k; uint32_t tag;
+                        faceKey(t + kAhead, f, k, tag);
+                        faces.prefetch(k, tag);
+                    }
                 for (int f = 0; f < 4; ++f) {
-                    int v[3] = {m_elemNodes[t * npe + fc[f][0]], m_elemNodes[t * npe + fc[f][1]], m_elemNodes[t * npe + fc[f][2]]};
-                    std::sort(v, v + 3);
+                    uint64_t k; uint32_t tag;
+                    faceKey(t, f, k, tag);
                     bool ins;
-                    auto &slot = faces.findOrInsert(((uint64_t)(uint32_t)v[0] << 32) | (uint32_t)v[1], (uint32_t)v[2], ins);
+                    auto &slot = faces.findOrInsert(k, tag, ins);
                     if (ins) { slot.val = (int32_t)(4 * t + f); slot.aux = 1; }
                     else if (++slot.aux > 2) throw std::runtime_error("Non-manifold input detected.");
                 }
+            }
             for (const auto &s : faces.slots)
                 if (s.val >= 0 && s.aux == 1)
                     bfaces.push_back(BFace{{(int)(s.k >> 32), (int)(s.k & 0xffffffffu), (int)s.t}, s.val});

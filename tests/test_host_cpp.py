@@ -37,6 +37,22 @@ def test_grid_and_femmesh_numbering_match_oracle(hostlib, sizes, deg):
         assert np.array_equal(getattr(m, k), getattr(mo, k)), k
 
 
+@pytest.mark.parametrize("N", [2, 3])
+def test_femmesh_hash_tables_grow_on_disconnected_simplices(hostlib, N):
+    """Every simplex on its own vertices: all edges / faces are distinct, far more than the tables' initial
+    estimate (which assumes a connected mesh), so the open-addressing tables of FEMMesh.hh must double on the way;
+    numbering still equals the oracle's."""
+    ne = 1500
+    rng = np.random.default_rng(7)
+    base = np.eye(N + 1, N)[[N] + list(range(N))]                      # origin + unit vectors: positive volume
+    V = (base[None, :, :] + 3.0 * np.arange(ne)[:, None, None] + 0.1 * rng.random((ne, 1, N))).reshape(-1, N)
+    E = np.arange(ne * (N + 1)).reshape(ne, N + 1)
+    m, mo = hostlib.from_arrays(N, V, E).femmesh(2), orc.build_mesh(N, 2, V, E)
+    assert m.num_nodes == ne * (6 if N == 2 else 10)
+    for k in MESH_FIELDS:
+        assert np.allclose(getattr(m, k), getattr(mo, k), rtol=0, atol=1e-12), k
+
+
 def test_grid_with_corners(hostlib):
     rm = hostlib.grid([3, 2, 2], [0, -1, 2], [6, 1, 3])
     V, E = rm.arrays()
