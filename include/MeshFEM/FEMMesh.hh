@@ -23,7 +23,9 @@
 #include <sys/mman.h>
 #endif
 #include <memory>
+#include <exception>
 #include <stdexcept>
+#include <thread>
 #include <vector>
 
 namespace femmesh_detail {
@@ -112,6 +114,32 @@ struct Hash96 {
         }
     }
 };
+
+// threads for the table-building sweeps of large meshes: MESHFEM_NUM_THREADS=n (default 1 = the plain sweep: the
+// sweeps are bound by random memory probes, and whether n threads help depends on the host -- on the 8-vCPU
+// development VM eight threads probing private 24 MB tables run 10x slower EACH than one thread alone, so the
+// parallel build is opt-in); MESHFEM_PARALLEL_MIN_ELEMENTS moves the size threshold (the tests set it to 1)
+inline unsigned buildThreads(size_t numElements) {
+    unsigned n = 1;
+    if (const char *e = std::getenv("MESHFEM_NUM_THREADS")) n = (unsigned)std::max(1, std::atoi(e));
+    size_t minElements = 200000;
+    if (const char *e = std::getenv("MESHFEM_PARALLEL_MIN_ELEMENTS")) minElements = (size_t)std::max(1L, std::atol(e));
+    if (numElements < minElements) return 1;
+    return std::max(1u, std::min(n, 64u));
+}
+// f(chunk, begin, end) over T contiguous chunks of [0, n) (the same chunks on every call with the same n, T);
+// the first exception thrown by a chunk is rethrown here
+template <class F>
+inline void parallelChunks(size_t n, unsigned T, F &&f) {
+    std::vector<std::thread> threads;
+    std::unique_ptr<std::exception_ptr[]> errors(new std::exception_ptr[T]);
+    for (unsigned c = 0; c < T; ++c)
+        threads.emplace_back([&, c]() {
+            try { f(c, n * c / T, n * (c + 1) / T); } catch (...) { errors[c] = std::current_exception(); }
+        });
+    for (auto &t : threads) t.join();
+    for (unsigned c = 0; c < T; ++c) if (errors[c]) std::rethrow_exception(errors[c]);
+}
 
 inline uint64_t pairKey(int a, int b) {
     const uint32_t lo = (uint32_t)std::min(a, b), hi = (uint32_t)std::max(a, b);
@@ -271,6 +299,58 @@ private:
             edgeTable.reset(new Hash96(m_ne * nedge / (_K == 3 ? 4 : 1) + m_nV));
             m_edgeEnds.clear();
             constexpr size_t kAhead = 12;
+            const unsigned T = buildThreads(m_ne);
+            if (T > 1) {
+                // Parallel first-encounter numbering: every chunk of elements numbers ITS edges in its own sweep
+                // order (chunk-local table), then the chunks' distinct edges are merged in chunk order -- an edge
+                // first met in chunk c is numbered in c's turn, after every edge of the earlier chunks and in c's
+                // local order, which is exactly the order of the plain sweep.  The sequential part probes each
+                // chunk's distinct edges once (~1.2 per element) instead of every element edge (6 per tet).
+                std::vector<std::vector<uint64_t>> keys(T);
+                parallelChunks(m_ne, T, [&](unsigned c, size_t e0, size_t e1) {
+                    Hash96 local((e1 - e0) * nedge / (_K == 3 ? 4 : 1) + (e1 - e0) / 2 + 64);
+                    std::vector<uint64_t> lk;                 // thread-private while it grows (no false sharing)
+                    lk.reserve((e1 - e0) * 5 / 4 + 64);
+                    for (size_t e = e0; e < e1; ++e) {
+                        if (e + kAhead < e1)
+                            for (size_t ei = 0; ei < nedge; ++ei)
+                                local.prefetch(pairKey(m_elemNodes[(e + kAhead) * npe + Simplex::edgeStartNode(ei)],
+                                                       m_elemNodes[(e + kAhead) * npe + Simplex::edgeEndNode(ei)]), 0);
+                        for (size_t ei = 0; ei < nedge; ++ei) {
+                            const uint64_t key = pairKey(m_elemNodes[e * npe + Simplex::edgeStartNode(ei)],
+                                                         m_elemNodes[e * npe + Simplex::edgeEndNode(ei)]);
+                            bool ins;
+                            auto &slot = local.findOrInsert(key, 0, ins);
+                            if (ins) { slot.val = (int32_t)lk.size(); lk.push_back(key); }
+                            m_elemNodes[e * npe + nv + ei] = slot.val;        // chunk-local id until the merge
+                        }
+                    }
+                    keys[c] = std::move(lk);
+                });
+                std::vector<std::vector<int32_t>> remap(T);
+                for (unsigned c = 0; c < T; ++c) {
+                    const std::vector<uint64_t> &lk = keys[c];
+                    remap[c].resize(lk.size());
+                    for (size_t i = 0; i < lk.size(); ++i) {
+                        if (i + kAhead < lk.size()) edgeTable->prefetch(lk[i + kAhead], 0);
+                        bool ins;
+                        auto &slot = edgeTable->findOrInsert(lk[i], 0, ins);
+                        if (ins) {
+                            slot.val = (int32_t)m_nEdgeNodes++;
+                            m_edgeEnds.push_back((int32_t)(lk[i] >> 32));            // pairKey: (min, max)
+                            m_edgeEnds.push_back((int32_t)(lk[i] & 0xffffffffu));
+                        }
+                        remap[c][i] = slot.val;
+                    }
+                }
+                parallelChunks(m_ne, T, [&](unsigned c, size_t e0, size_t e1) {
+                    for (size_t e = e0; e < e1; ++e)
+                        for (size_t ei = 0; ei < nedge; ++ei) {
+                            int32_t &en = m_elemNodes[e * npe + nv + ei];
+                            en = (int32_t)(m_nV + remap[c][en]);
+                        }
+                });
+            } else
             for (size_t e = 0; e < m_ne; ++e) {
                 if (e + kAhead < m_ne)
                     for (size_t ei = 0; ei < nedge; ++ei)
@@ -295,7 +375,6 @@ private:
         std::vector<BFace> bfaces;
         if (_K == 3) {
             static const int fc[4][3] = {{1, 3, 2}, {0, 2, 3}, {0, 3, 1}, {0, 1, 2}};   // TetMesh.hh:221-226
-            Hash96 faces(2 * m_ne + 16);
             auto faceKey = [&](size_t t, int f, uint64_t &k, uint32_t &tag) {      // sorted vertex triple of face f of tet t
                 int v[3] = {m_elemNodes[t * npe + fc[f][0]], m_elemNodes[t * npe + fc[f][1]], m_elemNodes[t * npe + fc[f][2]]};
                 if (v[0] > v[1]) std::swap(v[0], v[1]);
@@ -305,21 +384,63 @@ private:
                 tag = (uint32_t)v[2];
             };
             constexpr size_t kAhead = 12;
-            for (size_t t = 0; t < m_ne; ++t) {
-                if (t + kAhead < m_ne)
+            // count the occurrences of every face of tets [t0, t1) in `table` (val = first half-face 4t+f)
+            auto sweepFaces = [&](Hash96 &table, size_t t0, size_t t1) {
+                for (size_t t = t0; t < t1; ++t) {
+                    if (t + kAhead < t1)
+                        for (int f = 0; f < 4; ++f) {
+                            uint64_t k; uint32_t tag;
+                            faceKey(t + kAhead, f, k, tag);
+                            table.prefetch(k, tag);
+                        }
                     for (int f = 0; f < 4; ++f) {
                         uint64_t k; uint32_t tag;
-                        faceKey(t + kAhead, f, k, tag);
-                        faces.prefetch(k, tag);
+                        faceKey(t, f, k, tag);
+                        bool ins;
+                        auto &slot = table.findOrInsert(k, tag, ins);
+                        if (ins) { slot.val = (int32_t)(4 * t + f); slot.aux = 1; }
+                        else if (++slot.aux > 2) throw std::runtime_error("Non-manifold input detected.");
                     }
-                for (int f = 0; f < 4; ++f) {
-                    uint64_t k; uint32_t tag;
-                    faceKey(t, f, k, tag);
-                    bool ins;
-                    auto &slot = faces.findOrInsert(k, tag, ins);
-                    if (ins) { slot.val = (int32_t)(4 * t + f); slot.aux = 1; }
-                    else if (++slot.aux > 2) throw std::runtime_error("Non-manifold input detected.");
                 }
+            };
+            const unsigned T = buildThreads(m_ne);
+            std::vector<std::unique_ptr<Hash96>> chunkFaces(T > 1 ? T : 0);
+            size_t unpaired = 0;
+            if (T > 1) {
+                // every chunk pairs the faces interior to it; only its unpaired faces (true boundary + the faces
+                // it shares with other chunks) go through the sequential table below
+                std::vector<size_t> cnt(T, 0);
+                parallelChunks(m_ne, T, [&](unsigned c, size_t t0, size_t t1) {
+                    chunkFaces[c].reset(new Hash96(2 * (t1 - t0) + 1024));
+                    sweepFaces(*chunkFaces[c], t0, t1);
+                    size_t n = 0;
+                    for (const auto &sl : chunkFaces[c]->slots) n += (sl.val >= 0 && sl.aux == 1);
+                    cnt[c] = n;
+                });
+                for (size_t n : cnt) unpaired += n;
+            }
+            Hash96 faces(T > 1 ? unpaired + 16 : 2 * m_ne + 16);
+            if (T > 1) {
+                for (unsigned c = 0; c < T; ++c)
+                    for (const auto &sl : chunkFaces[c]->slots) {
+                        if (!(sl.val >= 0 && sl.aux == 1)) continue;
+                        bool ins;
+                        auto &slot = faces.findOrInsert(sl.k, sl.t, ins);
+                        if (ins) { slot.val = sl.val; slot.aux = 1; }
+                        else if (++slot.aux > 2) throw std::runtime_error("Non-manifold input detected.");
+                    }
+                // a face still unpaired here must not be hidden as an interior pair of another chunk (three tets on one face)
+                for (const auto &sl : faces.slots) {
+                    if (!(sl.val >= 0 && sl.aux == 1)) continue;
+                    const size_t t = size_t(sl.val) / 4;
+                    for (unsigned c = 0; c < T; ++c) {
+                        if (t >= m_ne * c / T && t < m_ne * (c + 1) / T) continue;       // its own chunk
+                        if (chunkFaces[c]->find(sl.k, sl.t)) throw std::runtime_error("Non-manifold input detected.");
+                    }
+                }
+                chunkFaces.clear();
+            } else {
+                sweepFaces(faces, 0, m_ne);
             }
             for (const auto &s : faces.slots)
                 if (s.val >= 0 && s.aux == 1)

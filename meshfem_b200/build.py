@@ -105,7 +105,7 @@ def build_host(force: bool = False) -> str:
             return HOST_LIB
     # the host library mirrors the reference's classes; Simulator/SPSDSystem call the C ABI, so it
     # links libmfem_b200.so (build() must run first)
-    cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-I" + os.path.join(REPO, "include")] + HOST_SOURCES + \
+    cmd = ["g++", "-O2", "-std=c++17", "-pthread", "-shared", "-fPIC", "-I" + os.path.join(REPO, "include")] + HOST_SOURCES + \
           ["-L" + LIBDIR, "-lmfem_b200", "-Wl,-rpath,$ORIGIN", "-o", HOST_LIB]
     subprocess.check_call(cmd)
     bindir = os.path.join(REPO, "bin")
@@ -115,7 +115,7 @@ def build_host(force: bool = False) -> str:
                       ("ConstStrainDisplacement_cli", "src/bin/ConstStrainDisplacement_cli.cc"),
                       ("DeformedCells_cli", "src/bin/DeformedCells_cli.cc"),
                       ("grid", "src/bin/tools/grid.cc")):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-I" + os.path.join(REPO, "include"),
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-pthread", "-I" + os.path.join(REPO, "include"),
                                os.path.join(REPO, src), os.path.join(REPO, "src", "host", "MeshIO.cc"),
                                "-L" + LIBDIR, "-lmfem_b200", "-Wl,-rpath,$ORIGIN/../meshfem_b200/lib",
                                "-o", os.path.join(bindir, name)])
@@ -149,7 +149,7 @@ def build_python(force: bool = False):
     inc = ["-I" + sysconfig.get_paths()["include"], "-I" + pybind11.get_include(), "-I" + os.path.join(REPO, "include")]
     procs = []
     for (define, name), out in zip(PY_MODULES, outs):
-        cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-fvisibility=hidden", "-DBIND_" + define] + inc + \
+        cmd = ["g++", "-O2", "-std=c++17", "-pthread", "-shared", "-fPIC", "-fvisibility=hidden", "-DBIND_" + define] + inc + \
               [src, os.path.join(REPO, "src", "host", "MeshIO.cc"), "-L" + LIBDIR, "-lmfem_b200",
                "-Wl,-rpath,$ORIGIN/../meshfem_b200/lib", "-o", out]
         procs.append((name, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

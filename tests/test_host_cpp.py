@@ -53,6 +53,29 @@ def test_femmesh_hash_tables_grow_on_disconnected_simplices(hostlib, N):
         assert np.allclose(getattr(m, k), getattr(mo, k), rtol=0, atol=1e-12), k
 
 
+@pytest.mark.parametrize("threads", [2, 3, 7])
+def test_femmesh_parallel_build_numbers_like_the_plain_sweep(hostlib, threads, monkeypatch):
+    """Large meshes build their edge / face tables on several threads (FEMMesh.hh: chunk-local numbering merged in
+    chunk order); forced here on small meshes: every array equals the oracle's (= the single-thread sweep's)."""
+    monkeypatch.setenv("MESHFEM_PARALLEL_MIN_ELEMENTS", "1")
+    monkeypatch.setenv("MESHFEM_NUM_THREADS", str(threads))
+    for sizes, deg in [((5, 4, 3), 2), ((4, 3, 2), 1), ((7, 5), 2)]:
+        Vo, Eo = orc.grid_simplices(list(sizes))
+        m, mo = hostlib.grid(list(sizes)).femmesh(deg), orc.build_mesh(len(sizes), deg, Vo, Eo)
+        for k in MESH_FIELDS:
+            assert np.array_equal(getattr(m, k), getattr(mo, k)), (sizes, deg, k)
+    raw = hostlib.perforated_cell(3, 6, 2)
+    V, E = raw.arrays()
+    m, mo = raw.femmesh(2), orc.build_mesh(3, 2, V, E)
+    for k in MESH_FIELDS:
+        assert np.array_equal(getattr(m, k), getattr(mo, k)), k
+    # non-manifold input (three tets on one face) is still refused, wherever the chunk boundaries fall
+    V = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1], [0, 0, -1], [1, 1, -1.0]])
+    E = np.array([[0, 1, 2, 3], [0, 2, 1, 4], [0, 2, 1, 5]])
+    with pytest.raises(RuntimeError, match="Non-manifold"):
+        hostlib.from_arrays(3, V, E).femmesh(1)
+
+
 def test_grid_with_corners(hostlib):
     rm = hostlib.grid([3, 2, 2], [0, -1, 2], [6, 1, 3])
     V, E = rm.arrays()
