@@ -1,0 +1,95 @@
+"""CPU checks of the logic of the two-level preconditioner kernels (meshfem_b200/csrc/coarse.inl), which cannot run
+here: lane-level emulations of the two warp segmented reductions (equal-key variant of the single-GPU kernels,
+head-flag variant of the multi-GPU kernels) against a direct per-key sum, and the rigid-mode operators
+(coarse_R / coarse_Rt restated line by line) against each other and against the infinitesimal rigid motions."""
+import numpy as np
+
+L = np.arange(32)
+
+
+def _shfl_down(v, o):
+    out = v.copy()
+    out[:32 - o] = v[o:]
+    return out                      # lanes >= 32-o keep their own value (CUDA semantics)
+
+
+def _shfl_up1(v):
+    out = v.copy()
+    out[1:] = v[:-1]
+    return out
+
+
+def _equal_keys(keys, vals, active):               # k_coarse_matrix / k_coarse_restrict
+    aj = np.where(active, keys, -1 - L)
+    C = np.where(active, vals, 0.0)
+    for o in (1, 2, 4, 8, 16):
+        take = (L + o < 32) & (_shfl_down(aj, o) == aj)
+        C = np.where(take, C + _shfl_down(C, o), C)
+    head = active & ((L == 0) | (_shfl_up1(aj) != aj))
+    out = {}
+    for l in L[head]:
+        out[aj[l]] = out.get(aj[l], 0.0) + C[l]
+    return out
+
+
+def _head_flags(keys, vals, active):               # k_coarse_matrix_idx / k_coarse_restrict_idx (coarse_same_run)
+    aj = np.where(active, keys, -1 - L)
+    C = np.where(active, vals, 0.0)
+    head = (L == 0) | (_shfl_up1(aj) != aj)
+    heads = sum(1 << int(l) for l in L[head])
+    for o in (1, 2, 4, 8, 16):
+        take = np.array([(l + o < 32) and (((heads >> (l + 1)) & ((1 << o) - 1)) == 0) for l in L])
+        C = np.where(take, C + _shfl_down(C, o), C)
+    out = {}
+    for l in L[active & head]:
+        out[aj[l]] = out.get(aj[l], 0.0) + C[l]
+    return out
+
+
+def _direct(keys, vals, active):
+    out = {}
+    for k, v, a in zip(keys, vals, active):
+        if a:
+            out[k] = out.get(k, 0.0) + v
+    return out
+
+
+def _same(r, d):
+    return r.keys() == d.keys() and all(abs(r[k] - d[k]) < 1e-12 for k in d)
+
+
+def test_warp_segmented_reductions():
+    rng = np.random.default_rng(0)
+    for _ in range(500):
+        active = L < rng.integers(1, 33)
+        vals = rng.random(32)
+        keys = np.sort(rng.integers(0, rng.integers(1, 12), size=32))          # contiguous runs (sorted columns)
+        d = _direct(keys, vals, active)
+        assert _same(_equal_keys(keys, vals, active), d) and _same(_head_flags(keys, vals, active), d)
+        keys = rng.integers(0, rng.integers(1, 6), size=32)                    # interleaved foreign aggregates
+        assert _same(_head_flags(keys, vals, active), _direct(keys, vals, active))
+
+
+def _R(N, y, c):                                    # coarse_R
+    if N == 3:
+        return np.array([c[0] + y[2] * c[4] - y[1] * c[5], c[1] - y[2] * c[3] + y[0] * c[5], c[2] + y[1] * c[3] - y[0] * c[4]])
+    return np.array([c[0] - y[1] * c[2], c[1] + y[0] * c[2]])
+
+
+def _Rt(N, y, v):                                   # coarse_Rt
+    if N == 3:
+        return np.array([v[0], v[1], v[2], y[1] * v[2] - y[2] * v[1], y[2] * v[0] - y[0] * v[2], y[0] * v[1] - y[1] * v[0]])
+    return np.array([v[0], v[1], y[0] * v[1] - y[1] * v[0]])
+
+
+def test_rigid_mode_operators():
+    rng = np.random.default_rng(1)
+    for N, M in ((3, 6), (2, 3)):
+        for _ in range(20):
+            y, c, v = rng.standard_normal(N), rng.standard_normal(M), rng.standard_normal(N)
+            assert abs(_R(N, y, c) @ v - c @ _Rt(N, y, v)) < 1e-12                 # transposes of each other
+            # translation + infinitesimal rotation omega x y
+            if N == 3:
+                assert np.allclose(_R(N, y, c), c[:3] + np.cross(c[3:], y))
+            else:
+                assert np.allclose(_R(N, y, c), c[:2] + c[2] * np.array([-y[1], y[0]]))
