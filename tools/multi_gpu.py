@@ -42,7 +42,7 @@ def run_multi_gpu(args, dist, world, rank, local_rank, name, grid, deg, mat, hbm
     import torch
     import meshfem_b200
     import workloads as wl
-    from bench import METRIC, UNIT, RTOL, ClockSampler, workload_name, pinned_copy
+    from bench import METRIC, UNIT, RTOL, ClockSampler, workload_name, pinned_copy, precond_name
 
     device = torch.device("cuda", local_rank)
     m = wl.grid_femmesh(grid, deg)
@@ -57,7 +57,8 @@ def run_multi_gpu(args, dist, world, rank, local_rank, name, grid, deg, mat, hbm
     p.nodes, p.elem_nodes = nodes_p, elems_p
 
     sampler = ClockSampler(local_rank)
-    h = make_handle(meshfem_b200, dist, world, rank, local_rank, p, D)
+    opts = {"coarse_aggregates": args.coarse_aggregates} if getattr(args, "coarse_aggregates", 0) else {}
+    h = make_handle(meshfem_b200, dist, world, rank, local_rank, p, D, **opts)
     h.assemble()
     h.fix_variables(lfixed, lvals)
     nb, nnzb = h.bsr_sizes()
@@ -97,7 +98,7 @@ def run_multi_gpu(args, dist, world, rank, local_rank, name, grid, deg, mat, hbm
     def e2e_step():
         dist.barrier()
         t = time.perf_counter()
-        hh = make_handle(meshfem_b200, dist, world, rank, local_rank, p, D, comm_parent=h)
+        hh = make_handle(meshfem_b200, dist, world, rank, local_rank, p, D, comm_parent=h, **opts)
         hh.assemble()
         hh.fix_variables(lfixed, lvals)
         u = hh.solve(f_p, rtol=RTOL)
@@ -123,7 +124,7 @@ def run_multi_gpu(args, dist, world, rank, local_rank, name, grid, deg, mat, hbm
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(name, grid, deg, mat), "elements": n_elems_total, "rtol": RTOL,
                        "partition": f"{world} x-slabs of elements, shared interface DoFs, NCCL send/recv sum-exchange + all-reduced dots",
-                       "preconditioner": "block-Jacobi 3x3", "l2_policy": "inputs larger than L2"},
+                       "preconditioner": precond_name(getattr(args, "coarse_aggregates", 0)), "l2_policy": "inputs larger than L2"},
             "assembly_elements_per_s": args.steps * n_elems_total / asm_max, "pcg_iters_per_s": iters / solve_max,
             "pcg_iterations_per_solve": iters / args.steps, "pcg_rel_residual": relres,
             "assembly_ms": 1e3 * asm_max / args.steps, "solve_ms": 1e3 * solve_max / args.steps,
