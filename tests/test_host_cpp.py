@@ -187,6 +187,27 @@ def test_periodic_condition_matches_oracle(hostlib, sizes, deg):
     assert list(first.values()) == sorted(first.values())
 
 
+@pytest.mark.parametrize("deg", [1, 2])
+def test_periodic_condition_on_the_reference_microstructure(hostlib, deg):
+    """The same on real geometry: examples/meshes/2D_microstructure.msh (tests/golden/microstructures.npz), whose
+    boundary nodes are not on a lattice -- host C++ matcher, pinned node and FEMMesh numbering against the oracle."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "microstructures.npz"))
+    V, T = g["V_2d_full"], g["T_2d_full"]
+    sim = orc.Simulator(2, deg, V, T)
+    dof, nd, pbe = orc.periodic_condition(sim.mesh)
+    sim.set_periodic(dof, nd, pbe)
+    sim.apply_no_rigid_motion_constraint(); sim.set_use_pin_no_rigid_translation_constraint(True)
+    fx, vv = sim.fixed_vars_and_values()
+    raw = hostlib.from_arrays(2, V, T)
+    r = raw.apply_bc(deg, "", periodic=True)
+    assert r["num_dofs"] == nd < sim.mesh.num_nodes
+    assert np.array_equal(r["dof_for_node"], dof) and np.array_equal(r["internal_be"], pbe)
+    assert np.array_equal(r["fixed_vars"], fx) and np.array_equal(r["fixed_vals"], vv)
+    m = raw.femmesh(deg)
+    for k in MESH_FIELDS:
+        assert np.allclose(getattr(m, k), getattr(sim.mesh, k), rtol=0, atol=1e-15), k
+
+
 def test_materials_and_expressions(hostlib):
     from test_oracle_kats import MATERIAL_FIXTURES
     for name, cfgs in MATERIAL_FIXTURES.items():

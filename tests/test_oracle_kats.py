@@ -318,3 +318,30 @@ def test_interpolant_exactness_and_integrals(K, deg):
         vals = np.array([orc.shape_functions(K, deg, x) @ nodal for x in X])
         assert np.abs(vals - f(X)).max() <= 1e-13, m
         assert abs(iphi @ nodal - sum(wq * f(p) for p, wq in zip(P, w))) <= 1e-15, m
+
+
+def test_reference_microstructures_orthotropic_cell_equals_periodic_cell():
+    """The reference's example microstructures (examples/meshes/*microstructure*.msh, committed as arrays in
+    tests/golden/microstructures.npz by make_microstructure_golden.py) with the base material of
+    python/examples/Homogenization.ipynb (E = 200, nu = 0.35).  The notebook's closing self-check -- orthotropic
+    base-cell homogenization of the positive orthant gives the tensor of the full periodic cell -- must hold for the
+    oracle on the reference's own 2D pair, and the committed tensors must be reproduced."""
+    g = np.load(os.path.join(GOLD, "microstructures.npz"))
+    D2 = orc.isotropic_D(2, 200.0, 0.35)
+    for deg in (1, 2):
+        sim = orc.Simulator(2, deg, g["V_2d_full"], g["T_2d_full"]); sim.set_material(D2)
+        full = orc.homogenized_tensor_displacement_form(sim, orc.solve_cell_problems(sim))
+        sim = orc.Simulator(2, deg, g["V_2d_ortho"], g["T_2d_ortho"]); sim.set_material(D2)
+        ortho = orc.orthotropic_homogenized_tensor_displacement_form(sim, orc.solve_orthotropic_cell_problems(sim))
+        scale = np.abs(full).max()
+        assert np.abs(ortho - full).max() < 1e-11 * scale
+        assert np.abs(full - g[f"Eh_2d_full_deg{deg}"]).max() < 1e-12 * scale
+        assert np.abs(ortho - g[f"Eh_2d_ortho_deg{deg}"]).max() < 1e-12 * scale
+        # a perforated structure of an E = 200 material is far softer than the solid, and orthotropic
+        assert 0 < full[0, 0] < 0.1 * D2[0, 0] and abs(full[0, 2]) < 1e-10 * scale and abs(full[1, 2]) < 1e-10 * scale
+    sim = orc.Simulator(3, 1, g["V_3d_ortho"], g["T_3d_ortho"]); sim.set_material(orc.isotropic_D(3, 200.0, 0.35))
+    Eh = orc.orthotropic_homogenized_tensor_displacement_form(sim, orc.solve_orthotropic_cell_problems(sim))
+    assert np.abs(Eh - g["Eh_3d_ortho_deg1"]).max() < 1e-11 * np.abs(Eh).max()
+    assert np.linalg.eigvalsh(Eh).min() > 0
+    # the full 3D cell (68,888 vertices, periodic, ~95 s of oracle time: tensor committed, mesh not) agrees as well
+    assert np.abs(Eh - g["Eh_3d_full_deg1"]).max() < 1e-11 * np.abs(Eh).max()
