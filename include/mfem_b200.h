@@ -75,8 +75,9 @@ int mfem_b200_comm_share(mfem_b200_handle h, mfem_b200_handle parent);
  *                 contribution list and written exactly once, coalesced),
  *             1 = graph-coloured element scatter (read-modify-write, no atomics),
  *             2 = owner-gather by DoF row (first-generation kernel, kept for A/B).
- * "coarse_aggregates": S > 0 adds an aggregation coarse space (rigid-body modes of S contiguous runs of the
- *             internal DoF numbering) to the block-Jacobi preconditioner, M^-1 = B^-1 + Z (Z'KZ)^-1 Z'
+ * "coarse_aggregates": S > 0 adds an aggregation coarse space (rigid-body modes of at most S aggregates: near-cubic
+ *             boxes over the bounding box of the DoFs; "coarse_shape" = 1 selects contiguous runs of the internal
+ *             DoF numbering instead, one GPU only) to the block-Jacobi preconditioner, M^-1 = B^-1 + Z (Z'KZ)^-1 Z'
  *             (csrc/coarse.inl; single right-hand side; on several GPUs every rank aggregates the DoFs it owns and the coarse
  *             matrix / residuals are all-reduced -- set the same value on every rank; default 0 = off; may be changed
  *             between solves). */

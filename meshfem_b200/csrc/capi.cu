@@ -107,6 +107,10 @@ int mfem_b200_set_option(mfem_b200_handle h, const char *name, int64_t value) {
         MFEM_REQUIRE(value >= 0 && value <= 5461, MFEM_B200_ERR_INVALID, "coarse_aggregates must be 0 (block-Jacobi only) .. 5461");
         h->opt_coarse = (int)value;
         h->precondValid = false;
+    } else if (n == "coarse_shape") {
+        MFEM_REQUIRE(value == 0 || value == 1, MFEM_B200_ERR_INVALID, "coarse_shape must be 0 (boxes) or 1 (runs of the internal numbering)");
+        h->opt_coarse_shape = (int)value;
+        h->precondValid = false;
     } else if (n == "spmv_lanes") {
         MFEM_REQUIRE(value == 0 || value == 8 || value == 16 || value == 32, MFEM_B200_ERR_INVALID,
                      "spmv_lanes must be 0 (auto), 8, 16 or 32");

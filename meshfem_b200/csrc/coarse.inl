@@ -495,7 +495,7 @@ k_coarse_restrict_idx(int64_t nb, const int32_t *__restrict__ agg, const uint8_t
         for (int m = 0; m < M; ++m) q[m] = 0.0;
         if (i < nb) {
             a = agg[i];
-            const bool mine = owned[i] != 0;
+            const bool mine = !owned || owned[i] != 0;
             double v[N], y[N];
             for (int k = 0; k < N; ++k) { v[k] = (!mine || fixedMask[i * N + k]) ? 0.0 : r[i * N + k]; y[k] = Y[i * N + k]; }
             coarse_Rt<N>(y, v, q);
@@ -557,80 +557,178 @@ k_coarse_prolong_idx(int64_t nb, const int32_t *__restrict__ agg, const double *
     for (int64_t k = t0; k < nc; k += stride) cvec[k] = 0.0;      // nobody reads c in this kernel
 }
 
+// ---- box aggregates.  tools/proto_two_level.py-style experiments on the CPU show that the SHAPE of the aggregates
+// matters as much as their number: contiguous runs of the Morton order are ragged (a run cuts across the cells of
+// the curve), and compact boxes of the same count need 1.6-1.7x fewer iterations (quadratic cantilever 20x4x4:
+// 32 aggregates 293 -> 169, 64: 234 -> 140, 256: 145 -> 90).  So the indexed path bins the (owned) DoFs into a
+// regular grid of near-cubic boxes over their bounding box; empty boxes are dead modes (unit diagonal in E).
+
+// order-preserving map double -> uint64 for atomicMin / atomicMax
+__device__ __forceinline__ unsigned long long coarse_key(double x) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(x);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+static double coarse_unkey(unsigned long long k) {
+    const unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+    double x;
+    std::memcpy(&x, &b, sizeof(double));
+    return x;
+}
+// keys[0..N) = min, keys[N..2N) = max over the owned DoFs that have a node
 template <int N>
-static void build_coarse_multi_impl(mfem_b200_ctx *c) {
+__global__ void k_coarse_bbox(int64_t nb, const uint8_t *__restrict__ owned, int64_t nNodes, const int32_t *__restrict__ firstNode,
+                              const double *__restrict__ nodes, unsigned long long *keys) {
+    double lo[N], hi[N];
+    for (int k = 0; k < N; ++k) { lo[k] = 1e300; hi[k] = -1e300; }
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nb; i += (int64_t)gridDim.x * blockDim.x) {
+        if (owned && !owned[i]) continue;
+        const int64_t node = firstNode[i];
+        if (node < 0 || node >= nNodes) continue;
+        for (int k = 0; k < N; ++k) { const double x = nodes[node * N + k]; lo[k] = fmin(lo[k], x); hi[k] = fmax(hi[k], x); }
+    }
+    for (int k = 0; k < N; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[k] = fmin(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
+            hi[k] = fmax(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicMin(&keys[k], coarse_key(lo[k]));
+            atomicMax(&keys[N + k], coarse_key(hi[k]));
+        }
+    }
+}
+struct CoarseBoxes { double lo[3], scale[3]; int b[3]; };     // box of x along k: min(b-1, floor((x - lo) * scale))
+// agg[i] = aggBase + box of the DoF's first node (owned DoFs; -1 for the others)
+template <int N>
+__global__ void k_coarse_box_agg(int64_t nb, const uint8_t *__restrict__ owned, int64_t nNodes, const int32_t *__restrict__ firstNode,
+                                 const double *__restrict__ nodes, const CoarseBoxes bx, int64_t aggBase, int32_t *__restrict__ agg) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= nb) return;
+    if (owned && !owned[i]) { agg[i] = -1; return; }
+    const int64_t node = firstNode[i];
+    int64_t id = 0;
+    if (node >= 0 && node < nNodes)
+        for (int k = 0; k < N; ++k) {
+            int q = (int)floor((nodes[node * N + k] - bx.lo[k]) * bx.scale[k]);
+            q = max(0, min(bx.b[k] - 1, q));
+            id = id * bx.b[k] + q;
+        }
+    agg[i] = (int32_t)(aggBase + id);
+}
+
+// near-cubic boxes, at most `budget` of them, over the extents L (flat directions get one layer)
+static void coarse_choose_boxes(int N, const double *L, int64_t budget, int *b) {
+    double vol = 1.0;
+    int nd = 0;
+    for (int k = 0; k < N; ++k) if (L[k] > 0.0) { vol *= L[k]; ++nd; }
+    const double h = nd ? std::pow(vol / (double)std::max<int64_t>(budget, 1), 1.0 / nd) : 1.0;
+    for (int k = 0; k < N; ++k) b[k] = L[k] > 0.0 ? (int)std::max<int64_t>(1, std::llround(L[k] / h)) : 1;
+    auto count = [&]() { int64_t p = 1; for (int k = 0; k < N; ++k) p *= b[k]; return p; };
+    while (count() > budget) {                       // rounding up overshot: shrink the direction with the most layers
+        int kmax = 0;
+        for (int k = 1; k < N; ++k) if (b[k] > b[kmax]) kmax = k;
+        if (b[kmax] == 1) break;
+        --b[kmax];
+    }
+}
+
+// Indexed coarse space (1..N ranks): box aggregates over the DoFs this rank owns, owner's aggregate id / centred
+// position on every sharer, all-reduced partial coarse matrix.  On one rank the exchange and the all-reduces are no-ops.
+template <int N>
+static void build_coarse_indexed_impl(mfem_b200_ctx *c) {
     constexpr int M = N == 3 ? 6 : 3;
     cudaStream_t s = c->stream;
     const int64_t nb = c->nDofs;
-    const uint8_t *ownedDev = halo_owned(c);
-    // aggregates per rank: the same on every rank (the option and nRanks are), so global ids need no negotiation
-    const int64_t Sr = std::max<int64_t>(1, std::min<int64_t>(c->opt_coarse, 32768 / M) / c->nRanks);
-    const int64_t S = Sr * c->nRanks, aggBase = Sr * c->rank;
+    const bool multi = c->nRanks > 1;
+    const uint8_t *ownedDev = multi ? halo_owned(c) : nullptr;
+    // aggregate ids per rank: a fixed stride (the option and nRanks are the same everywhere), so global ids need no
+    // negotiation; a rank that uses fewer boxes than its stride leaves dead modes behind
+    int64_t Sr = std::max<int64_t>(1, std::min<int64_t>(c->opt_coarse, 32768 / M) / c->nRanks);
+    if (!multi) Sr = std::min<int64_t>(Sr, std::max<int64_t>(1, nb / 8));
+    const int64_t aggBase = Sr * c->rank;
+    const bool havePositions = !c->externalMatrix && c->nNodes > 0;
+    const int64_t nNodesEff = havePositions ? c->nNodes : 0;
+    DevBuf<int32_t> firstNode((size_t)nb);
+    MFEM_CUDA(cudaMemsetAsync(firstNode, 0x7f, firstNode.bytes(), s));
+    CoarseBoxes bx;
+    for (int k = 0; k < 3; ++k) { bx.lo[k] = 0.0; bx.scale[k] = 0.0; bx.b[k] = 1; }
+    if (havePositions) {
+        k_coarse_first_node<<<grid_for(c->nNodes, 256), 256, 0, s>>>(c->nNodes, c->nodeDof, firstNode);
+        DevBuf<unsigned long long> keys(2 * N);
+        MFEM_CUDA(cudaMemsetAsync(keys, 0xff, sizeof(unsigned long long) * N, s));           // min slots: +inf keys
+        MFEM_CUDA(cudaMemsetAsync(keys.p + N, 0x00, sizeof(unsigned long long) * N, s));     // max slots: -inf keys
+        k_coarse_bbox<N><<<(int)std::min<int64_t>(grid_for(nb, 256), (int64_t)sm_count(c) * 8), 256, 0, s>>>(nb, ownedDev, c->nNodes, firstNode,
+                                                                                                  c->nodes, keys);
+        c->launches += 2;
+        unsigned long long hk[2 * N];
+        MFEM_CUDA(cudaMemcpyAsync(hk, keys, sizeof(hk), cudaMemcpyDeviceToHost, s));
+        MFEM_CUDA(cudaStreamSynchronize(s));
+        double L[3] = {0.0, 0.0, 0.0};
+        bool any = true;
+        for (int k = 0; k < N; ++k) {
+            const double lo = coarse_unkey(hk[k]), hi = coarse_unkey(hk[N + k]);
+            if (!(hi >= lo)) { any = false; break; }                                          // this rank owns no positioned DoF
+            bx.lo[k] = lo; L[k] = hi - lo;
+        }
+        if (any) {
+            coarse_choose_boxes(N, L, Sr, bx.b);
+            for (int k = 0; k < N; ++k) bx.scale[k] = L[k] > 0.0 ? bx.b[k] / L[k] : 0.0;
+        }
+    }
+    const int64_t S = Sr * c->nRanks;
     free_coarse(c);
     c->coarse = new CoarseSpace();
     CoarseSpace &cs = *c->coarse;
     cs.S = (int)S; cs.M = M; cs.nc = M * S; cs.indexed = true;
     const int64_t nc = cs.nc;
-    // owned DoFs in internal order -> contiguous runs (host: setup only, one byte per DoF each way)
-    std::vector<uint8_t> ownedHost((size_t)nb);
-    MFEM_CUDA(cudaMemcpyAsync(ownedHost.data(), ownedDev, (size_t)nb, cudaMemcpyDeviceToHost, s));
-    MFEM_CUDA(cudaStreamSynchronize(s));
-    int64_t nOwned = 0;
-    for (int64_t i = 0; i < nb; ++i) nOwned += ownedHost[i] != 0;
-    std::vector<int32_t> aggHost((size_t)nb, -1);
-    int64_t k = 0;
-    for (int64_t i = 0; i < nb; ++i)
-        if (ownedHost[i]) { aggHost[i] = (int32_t)(aggBase + std::min<int64_t>(Sr - 1, (k * Sr) / std::max<int64_t>(nOwned, 1))); ++k; }
     cs.agg.alloc((size_t)nb);
-    MFEM_CUDA(cudaMemcpyAsync(cs.agg, aggHost.data(), sizeof(int32_t) * (size_t)nb, cudaMemcpyHostToDevice, s));
     cs.Y.alloc((size_t)nb * N);
     cs.Einv.alloc((size_t)nc * nc);
     cs.cvec.alloc((size_t)nc); cs.yvec.alloc((size_t)nc);
     MFEM_CUDA(cudaMemsetAsync(cs.Einv, 0, cs.Einv.bytes(), s));
     MFEM_CUDA(cudaMemsetAsync(cs.cvec, 0, cs.cvec.bytes(), s));
+    k_coarse_box_agg<N><<<grid_for(nb, 256), 256, 0, s>>>(nb, ownedDev, nNodesEff, firstNode, c->nodes, bx, aggBase, cs.agg);
+    c->launches++;
     {
         DevBuf<double> T((size_t)nb * (N + 1));
-        DevBuf<int32_t> firstNode((size_t)nb);
         DevBuf<double> cen((size_t)Sr * (N + 1));
         DevBuf<int> bad(1);
         MFEM_CUDA(cudaMemsetAsync(T, 0, T.bytes(), s));
-        MFEM_CUDA(cudaMemsetAsync(firstNode, 0x7f, firstNode.bytes(), s));
         MFEM_CUDA(cudaMemsetAsync(cen, 0, cen.bytes(), s));
         MFEM_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), s));
-        const bool havePositions = !c->externalMatrix && c->nNodes > 0;
-        if (havePositions) {
-            k_coarse_first_node<<<grid_for(c->nNodes, 256), 256, 0, s>>>(c->nNodes, c->nodeDof, firstNode);
-            c->launches++;
-        }
-        k_coarse_positions_idx<N><<<grid_for(nb, 256), 256, 0, s>>>(nb, aggBase, cs.agg, havePositions ? c->nNodes : 0, firstNode,
-                                                                    c->nodes, T, cen);
-        k_coarse_center_idx<N><<<grid_for(nb, 256), 256, 0, s>>>(nb, aggBase, cs.agg, havePositions ? c->nNodes : 0, firstNode, cen, T);
+        k_coarse_positions_idx<N><<<grid_for(nb, 256), 256, 0, s>>>(nb, aggBase, cs.agg, nNodesEff, firstNode, c->nodes, T, cen);
+        k_coarse_center_idx<N><<<grid_for(nb, 256), 256, 0, s>>>(nb, aggBase, cs.agg, nNodesEff, firstNode, cen, T);
         c->launches += 2;
-        halo_exchange_add(c, T, N + 1);                       // only the owner's rows are non-zero
+        halo_exchange_add(c, T, N + 1);                       // only the owner's rows are non-zero (no-op on one rank)
         k_coarse_unpack<N><<<grid_for(nb, 256), 256, 0, s>>>(nb, S, T, cs.agg, cs.Y, bad);
         c->launches++;
         int nbad = 0;
         MFEM_CUDA(cudaMemcpyAsync(&nbad, bad, sizeof(int), cudaMemcpyDeviceToHost, s));
-        MFEM_CUDA(cudaStreamSynchronize(s));                  // also: T / firstNode / cen / aggHost go out of scope
+        MFEM_CUDA(cudaStreamSynchronize(s));                  // also: T / cen go out of scope
         MFEM_CUDA(cudaGetLastError());
         // no throw before the collectives below: every rank must reach them; a bad rank poisons E instead
-        if (nbad) MFEM_CUDA(cudaMemsetAsync(cs.Einv, 0xff, sizeof(double), s));   // NaN in E[0] -> potrf fails on all ranks
+        if (nbad) MFEM_CUDA(cudaMemsetAsync(cs.Einv, 0xff, sizeof(double), s));   // NaN in E[0] -> the inversion fails on all ranks
     }
     const int grid = (int)std::min<int64_t>((nb + 7) / 8, (int64_t)sm_count(c) * 8);
     k_coarse_matrix_idx<N><<<grid, 256, 0, s>>>(nb, S, cs.agg, c->rowptr, c->colidx, c->vals, c->fixedMask, cs.Y, cs.Einv);
     c->launches++;
     MFEM_CUDA(cudaGetLastError());
-    // one all-reduce of the partial coarse matrices (chunked: NCCL counts are size_t, but keep single calls moderate)
-    const size_t total = (size_t)nc * nc, chunk = (size_t)1 << 27;
-    for (size_t off = 0; off < total; off += chunk)
-        allreduce_sum(c, cs.Einv.p + off, cs.Einv.p + off, (int)std::min(chunk, total - off));
+    if (multi) {
+        // one all-reduce of the partial coarse matrices (chunked: keep single calls moderate)
+        const size_t total = (size_t)nc * nc, chunk = (size_t)1 << 27;
+        for (size_t off = 0; off < total; off += chunk)
+            allreduce_sum(c, cs.Einv.p + off, cs.Einv.p + off, (int)std::min(chunk, total - off));
+    }
     invert_coarse_matrix(c, cs);
 }
 
 static void build_coarse(mfem_b200_ctx *c) {
     ScopedTimer timer(c, "Coarse Space");
-    if (c->nRanks > 1) {
-        if (c->N == 3) build_coarse_multi_impl<3>(c); else build_coarse_multi_impl<2>(c);
+    // default: box aggregates through the indexed kernels; coarse_shape = 1 keeps the first version (contiguous runs of
+    // the internal numbering, closed-form aggregate ids, one rank only) for A/B runs
+    if (c->nRanks > 1 || c->opt_coarse_shape == 0) {
+        if (c->N == 3) build_coarse_indexed_impl<3>(c); else build_coarse_indexed_impl<2>(c);
         return;
     }
     if (c->N == 3) build_coarse_impl<3>(c); else build_coarse_impl<2>(c);
@@ -644,8 +742,9 @@ static void apply_coarse(mfem_b200_ctx *c, const double *r, double *z, double *p
     const int vgrid = vec_grid(c, c->nDofs);
     if (cs.indexed) {
         const int ggridM = (int)std::min<int64_t>((cs.nc + 7) / 8, (int64_t)sm_count(c) * 8);
-        k_coarse_restrict_idx<N><<<vgrid, kVecThreads, 0, s>>>(c->nDofs, cs.agg, halo_owned(c), r, c->fixedMask, cs.Y, cs.cvec, status);
-        allreduce_sum(c, cs.cvec, cs.cvec, (int)cs.nc);
+        k_coarse_restrict_idx<N><<<vgrid, kVecThreads, 0, s>>>(c->nDofs, cs.agg, c->nRanks > 1 ? halo_owned(c) : nullptr, r, c->fixedMask, cs.Y,
+                                                               cs.cvec, status);
+        if (c->nRanks > 1) allreduce_sum(c, cs.cvec, cs.cvec, (int)cs.nc);
         k_coarse_gemv<<<ggridM, 256, 0, s>>>(cs.nc, cs.Einv, cs.cvec, cs.yvec, nullptr, status);
         k_coarse_cy<<<1, 256, 0, s>>>(cs.nc, cs.cvec, cs.yvec, rzSlot, status);
         k_coarse_prolong_idx<N><<<vgrid, kVecThreads, 0, s>>>(c->nDofs, cs.agg, cs.yvec, c->fixedMask, cs.Y, z, p, cs.cvec, cs.nc, status);

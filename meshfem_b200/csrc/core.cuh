@@ -95,6 +95,7 @@ struct mfem_b200_ctx {
     int opt_batch_rhs = 1;                 // solve flatLen(N) right-hand sides as one batched PCG (SpMM)
     int opt_spmv_lanes = 0;                // lanes per block row in the SpMV (0 = choose from the mean row length)
     int opt_coarse = 0;                    // aggregates of the two-level preconditioner (0 = block-Jacobi only)
+    int opt_coarse_shape = 0;              // 0 = near-cubic boxes (default), 1 = contiguous runs of the internal numbering
 
     // mesh
     int N = 0, deg = 0, npe = 0;

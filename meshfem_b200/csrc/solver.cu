@@ -15,6 +15,9 @@
 #include <cusolverDn.h>   // types only: the library is loaded with dlopen by coarse.inl (optional two-level preconditioner)
 #include <dlfcn.h>
 
+#include <cmath>
+#include <cstring>
+
 namespace mfem {
 
 constexpr int kSpmvThreads = 256;

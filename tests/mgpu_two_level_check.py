@@ -3,7 +3,7 @@
 Every rank solves its slab of a cantilever twice -- block-Jacobi PCG, then with coarse_aggregates on (owner-based
 aggregates, all-reduced coarse matrix and coarse residuals; csrc/coarse.inl, multi-GPU variant) -- and compares both
 with the CPU oracle's direct solve (rel L2 <= 1e-8); the two-level run must need clearly fewer iterations
-(tests/mrank_cpu_worker.py, the gloo emulation of the same algorithm: 581 -> 233 / 221 on 2 / 3 ranks)."""
+(tests/mrank_cpu_worker.py, the gloo emulation of the same algorithm: 581 -> 167 / 143 on 2 / 3 ranks)."""
 import os
 import sys
 

@@ -91,25 +91,29 @@ def main():
         rz = rzn
     u = (x + ufix).reshape(-1, N)
 
-    # ---- two-level variant, exactly the multi-GPU algorithm of csrc/coarse.inl (build_coarse_multi_impl): aggregates
-    # over the OWNED DoFs of each rank (contiguous runs along a Morton curve, the device's internal order), owner's
+    # ---- two-level variant, exactly the multi-GPU algorithm of csrc/coarse.inl (build_coarse_indexed_impl): box aggregates
+    # over the OWNED DoFs of each rank, owner's
     # aggregate id and centred position sent to the sharers by a sum-exchange in which only the owner contributes,
     # E = all-reduce of Z_loc' K_loc Z_loc, restriction over owned DoFs + all-reduce, replicated coarse solve,
     # prolongation on every local DoF, r.z corrected by c.y after its all-reduce.
-    Sr, M = 4, 6
+    Sr, M = 8, 6
     S = Sr * world
     X = p.nodes
-    q = np.floor((X - X.min(0)) / (X.max(0) - X.min(0)).max() * 1023).astype(np.int64)
-    key = np.zeros(p.num_nodes, dtype=np.int64)
-    for bit in range(10):
-        for kk in range(3):
-            key |= ((q[:, kk] >> bit) & 1) << (3 * bit + kk)
-    order = np.argsort(key, kind="stable")                    # internal order
     own_n = p.owned.astype(bool)
-    rank_in_owned = np.cumsum(own_n[order]) - 1
-    agg = np.full(p.num_nodes, -1, dtype=np.int64)
-    sel = order[own_n[order]]
-    agg[sel] = rank * Sr + np.minimum(Sr - 1, (rank_in_owned[own_n[order]] * Sr) // max(int(own_n.sum()), 1))
+    # near-cubic boxes over the bounding box of the OWNED nodes, at most Sr of them (coarse_choose_boxes / k_coarse_box_agg)
+    lo, hi = X[own_n].min(0), X[own_n].max(0)
+    L = hi - lo
+    h = (np.prod(L[L > 0]) / Sr) ** (1.0 / (L > 0).sum())
+    bx = [int(max(1, np.floor(l / h + 0.5))) if l > 0 else 1 for l in L]
+    while np.prod(bx) > Sr:
+        k = int(np.argmax(bx))
+        if bx[k] == 1:
+            break
+        bx[k] -= 1
+    scale = np.where(L > 0, np.array(bx) / np.where(L > 0, L, 1.0), 0.0)
+    q = np.clip(np.floor((X - lo) * scale).astype(np.int64), 0, np.array(bx) - 1)
+    box = (q[:, 0] * bx[1] + q[:, 1]) * bx[2] + q[:, 2]
+    agg = np.where(own_n, rank * Sr + box, -1)
     T = np.zeros((p.num_nodes, 4))
     cen = np.zeros((Sr, 4))
     np.add.at(cen, agg[own_n] - rank * Sr, np.hstack([X[own_n], np.ones((int(own_n.sum()), 1))]))

@@ -93,3 +93,35 @@ def test_rigid_mode_operators():
                 assert np.allclose(_R(N, y, c), c[:3] + np.cross(c[3:], y))
             else:
                 assert np.allclose(_R(N, y, c), c[:2] + c[2] * np.array([-y[1], y[0]]))
+
+
+def _choose_boxes(L, budget):                       # coarse_choose_boxes
+    L = np.asarray(L, float)
+    nz = L > 0
+    h = (np.prod(L[nz]) / max(budget, 1)) ** (1.0 / nz.sum()) if nz.any() else 1.0
+    b = [int(max(1, np.floor(l / h + 0.5))) if l > 0 else 1 for l in L]
+    while np.prod(b) > budget:
+        k = int(np.argmax(b))
+        if b[k] == 1:
+            break
+        b[k] -= 1
+    return b
+
+
+def test_box_grid_choice():
+    """Near-cubic boxes within the budget; flat directions get one layer."""
+    assert _choose_boxes((220, 44, 44), 2048) == [37, 7, 7]
+    assert _choose_boxes((20, 4, 4), 128) == [14, 3, 3]
+    assert _choose_boxes((40, 8), 96) == [22, 4]
+    assert _choose_boxes((1, 1, 0), 16) == [4, 4, 1]
+    rng = np.random.default_rng(2)
+    for _ in range(200):
+        L = rng.random(3) * 10 + 0.1
+        budget = int(rng.integers(1, 5000))
+        b = _choose_boxes(L, budget)
+        assert np.prod(b) <= budget and min(b) >= 1
+        if budget >= 64 and np.prod(b) > 8:            # box edge lengths within a factor ~2 of each other away from the 1-layer limit
+            edges = L / np.array(b)
+            multi = np.array(b) > 1
+            if multi.sum() >= 2:
+                assert edges[multi].max() / edges[multi].min() < 2.5

@@ -10,9 +10,9 @@ timeout 1200 python -m pytest tests/test_zz_two_level_gpu.py tests/test_zz_lagra
     tests/test_zz_periodic_variants_gpu.py tests/test_zz_shape_derivatives_gpu.py tests/test_zzz_microstructures_gpu.py \
     -q -m gpu 2>&1 | tail -80 > gpurun_out/zz_tests.log
 # 2. the two-level preconditioner on the bench workloads (iterations, step time, e2e, validation)
-for cfg_s in "cfg3 1024" "cfg5 2048" "cfg5 4096"; do
+for cfg_s in "cfg3 1024 0" "cfg3 1024 1" "cfg5 2048 0" "cfg5 4096 0" "cfg5 2048 1"; do
     set -- $cfg_s
-    timeout 300 python tools/two_level_trial.py --config $1 --aggregates $2 > gpurun_out/two_level_$1_$2.json 2> gpurun_out/two_level_$1_$2.err
+    timeout 300 python tools/two_level_trial.py --config $1 --aggregates $2 --shape $3 > gpurun_out/two_level_$1_$2_shape$3.json 2> gpurun_out/two_level_$1_$2_shape$3.err
 done
 # 3. where the coarse-space time goes: launch list of one trial (per-launch times are cold-cache and serialised)
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/launches_two_level_cfg3.csv \

@@ -35,6 +35,7 @@ def main():
     ap.add_argument("--rtol", type=float, default=1e-8)
     ap.add_argument("--device", type=int, default=0)
     ap.add_argument("--expect-min-uy", type=float, default=None)
+    ap.add_argument("--shape", type=int, default=0, help="0 = near-cubic boxes (default), 1 = contiguous runs of the internal numbering")
     args = ap.parse_args()
 
     import meshfem_b200
@@ -46,13 +47,15 @@ def main():
     D = wl.material(mat)
     fixed, vals, f = wl.cantilever_inputs(m)
     n_elems = m.num_elements
-    out = {"config": name, "aggregates": args.aggregates, "rtol": args.rtol, "elements": int(n_elems)}
+    out = {"config": name, "aggregates": args.aggregates, "aggregate_shape": "boxes" if args.shape == 0 else "runs", "rtol": args.rtol,
+           "elements": int(n_elems)}
 
     with meshfem_b200.Handle(args.device) as h:
         h.set_mesh(3, deg, m.nodes, m.elem_nodes)
         h.set_material(D)
         h.assemble()
         h.fix_variables(fixed, vals)
+        h.set_option("coarse_shape", args.shape)
         h.set_option("coarse_aggregates", args.aggregates)
         h.reset_timers()
         h.solve(f, rtol=args.rtol, max_iters=8000)                                  # warm-up: builds the coarse space
@@ -79,7 +82,7 @@ def main():
     })
 
     t0 = time.perf_counter()
-    with meshfem_b200.Handle(args.device, coarse_aggregates=args.aggregates) as hh:
+    with meshfem_b200.Handle(args.device, coarse_shape=args.shape, coarse_aggregates=args.aggregates) as hh:
         hh.set_mesh(3, deg, m.nodes, m.elem_nodes)
         hh.set_material(D)
         hh.assemble()
