@@ -1361,7 +1361,7 @@ static void pcg_impl(mfem_b200_ctx *c, const double *f_int, double *u_int, doubl
     while (done < maxIters) {
         if (exec) {
             MFEM_CUDA(cudaGraphLaunch(exec, s));
-            c->launches += (c->coarse ? 6 : 3) * kBatch;
+            c->launches += (c->coarse ? (c->coarse->indexed ? 7 : 6) : 3) * kBatch;
         } else {
             for (int k = 0; k < kBatch; ++k) enqueue_iteration<N>(c);
         }
