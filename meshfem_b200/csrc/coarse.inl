@@ -674,6 +674,7 @@ static void build_coarse_indexed_impl(mfem_b200_ctx *c) {
         if (any) {
             coarse_choose_boxes(N, L, Sr, bx.b);
             for (int k = 0; k < N; ++k) bx.scale[k] = L[k] > 0.0 ? bx.b[k] / L[k] : 0.0;
+            if (!multi) { Sr = 1; for (int k = 0; k < N; ++k) Sr *= bx.b[k]; }     // one rank: no stride to keep, no dead ids
         }
     }
     const int64_t S = Sr * c->nRanks;
