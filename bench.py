@@ -161,7 +161,7 @@ def cpu_port_sample(deg, mat, rtol, threads=None):
     }
 
 
-def two_level_trial(cfg, device, expect_min_uy, aggregates=2048, timeout_s=200):
+def two_level_trial(cfg, device, expect_min_uy, aggregates=2048, timeout_s=150):
     """Extra, NOT the headline: the optional two-level preconditioner (coarse_aggregates; csrc/coarse.inl, DESIGN.md
     section 8 item 0) on the same workload, in a subprocess with a timeout so that nothing it does can touch the
     numbers above.  Returns the subprocess's JSON (validated there against the block-Jacobi tip deflection and the
@@ -185,7 +185,7 @@ def two_level_trial(cfg, device, expect_min_uy, aggregates=2048, timeout_s=200):
 
     out = one(0, timeout_s)
     if "error" in out or not out.get("valid", False):
-        out["fallback_runs"] = one(1, 150)
+        out["fallback_runs"] = one(1, 100)
     out["note"] = ("experimental option, reported beside the block-Jacobi headline (the headline stays block-Jacobi until this "
                    "path has been validated on hardware, on every GPU count)")
     return out
