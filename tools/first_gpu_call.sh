@@ -7,7 +7,7 @@ mkdir -p gpurun_out
 python __graft_entry__.py > gpurun_out/build.log 2>&1
 # 1. the never-run GPU tests, all of them (no -x), slowest-to-diagnose first
 timeout 1200 python -m pytest tests/test_zz_two_level_gpu.py tests/test_zz_lagrange_gpu.py tests/test_zz_deformed_cells_gpu.py \
-    tests/test_zz_periodic_variants_gpu.py tests/test_zz_shape_derivatives_gpu.py tests/test_zzz_microstructures_gpu.py \
+    tests/test_zz_periodic_variants_gpu.py tests/test_zz_shape_derivatives_gpu.py tests/test_zy_microstructures_gpu.py \
     -q -m gpu 2>&1 | tail -80 > gpurun_out/zz_tests.log
 # 2. the two-level preconditioner on the bench workloads (iterations, step time, e2e, validation)
 for cfg_s in "cfg3 1024 0" "cfg3 1024 1" "cfg5 2048 0" "cfg5 4096 0" "cfg5 2048 1"; do
