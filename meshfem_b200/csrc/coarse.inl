@@ -142,7 +142,9 @@ k_coarse_matrix(int64_t nb, int64_t S, const int64_t *__restrict__ rowptr, const
             }
             const int64_t ajPrev = __shfl_up_sync(0xffffffffu, aj, 1);
             const bool head = active && (lane == 0 || ajPrev != aj);
-            if (head)
+            // the factorisation reads only the row-major UPPER triangle of E (= column-major lower): block columns
+            // left of the diagonal block are never looked at, so half of the reductions can be skipped
+            if (head && aj >= ai)
                 for (int a = 0; a < M; ++a)
                     for (int b = 0; b < M; ++b)
                         if (C[a][b] != 0.0) atomicAdd(&E[(ai * M + a) * nc + aj * M + b], C[a][b]);
@@ -283,7 +285,8 @@ static void free_coarse(mfem_b200_ctx *c) {
     c->coarse = nullptr;
 }
 
-// E (assembled, both triangles) -> regularised -> explicit inverse in place (potrf + potri + mirror)
+// E (assembled: the row-major upper block triangle, which is all potrf reads) -> regularised -> explicit inverse in place
+// (potrf + potri + mirror)
 static void invert_coarse_matrix(mfem_b200_ctx *c, CoarseSpace &cs) {
     cudaStream_t s = c->stream;
     const int64_t nc = cs.nc;
@@ -470,7 +473,7 @@ k_coarse_matrix_idx(int64_t nb, int64_t S, const int32_t *__restrict__ agg, cons
                         if (take) C[a][b] += other;
                     }
             }
-            if (active && head)
+            if (active && head && aj >= ai)          // upper block triangle only (see k_coarse_matrix)
                 for (int a = 0; a < M; ++a)
                     for (int b = 0; b < M; ++b)
                         if (C[a][b] != 0.0) atomicAdd(&E[(ai * M + a) * nc + aj * M + b], C[a][b]);
