@@ -9,7 +9,8 @@ and inverted exactly (what csrc/coarse.inl does today with one coarse level).  E
 iteration still costs ONE fine SpMV; the extra work is segmented reductions / broadcasts over index ranges and 6x6
 block solves.  Prints PCG iteration counts next to block-Jacobi and the two-level method of tools/proto_two_level.py.
 
-  python tools/proto_three_level.py 40x8x8 2 30 64      # grid, degree, nodes per small aggregate, large aggregates
+  python tools/proto_three_level.py 40x8x8 2 30 64 [boxes]   # grid, degree, nodes per small aggregate, large aggregates;
+                                                             # "boxes": nested near-cubic box grids instead of Morton runs
 """
 import os
 import sys
@@ -36,7 +37,20 @@ def rigid_modes(Y):
     return R
 
 
-def run(sizes, deg, nodes_per_small, S2, rtol=1e-8):
+def choose_boxes(L, budget):
+    """Near-cubic box grid with at most `budget` boxes (csrc/coarse.inl coarse_choose_boxes)."""
+    L = np.asarray(L, float)
+    h = (np.prod(L) / max(budget, 1)) ** (1.0 / len(L))
+    b = [int(max(1, np.floor(l / h + 0.5))) for l in L]
+    while np.prod(b) > budget:
+        k = int(np.argmax(b))
+        if b[k] == 1:
+            break
+        b[k] -= 1
+    return np.array(b)
+
+
+def run(sizes, deg, nodes_per_small, S2, rtol=1e-8, boxes=False):
     sim, fixed, vals, f = cantilever_problem(3, deg, sizes)
     K = sim.stiffness().tocsr()
     n = K.shape[0]; N = 3; nd = n // N
@@ -59,9 +73,20 @@ def run(sizes, deg, nodes_per_small, S2, rtol=1e-8):
     order = morton_order(X)
     pos = np.empty(nd, dtype=np.int64); pos[order] = np.arange(nd)
 
-    def level(S):
-        agg = (pos * S) // nd
-        cen = np.zeros((S, 3)); np.add.at(cen, agg, X); cen /= np.bincount(agg, minlength=S)[:, None]
+    lo, hi = X.min(0), X.max(0)
+    if boxes:      # nested box grids: large boxes b2, small boxes bg1 = bg2 * r (so every small box lies in one large box)
+        bg2 = choose_boxes(hi - lo, S2)
+        r = max(1, int(round((nd / np.prod(bg2) / nodes_per_small) ** (1.0 / 3.0))))
+        bg1 = bg2 * r
+        S2 = int(np.prod(bg2))
+
+    def box_ids(b):
+        q = np.minimum(np.floor((X - lo) / (hi - lo) * b).astype(np.int64), b - 1)
+        return q, (q[:, 0] * b[1] + q[:, 1]) * b[2] + q[:, 2]
+
+    def level(S, b=None):
+        agg = (pos * S) // nd if b is None else box_ids(b)[1]
+        cen = np.zeros((S, 3)); np.add.at(cen, agg, X); cen /= np.maximum(np.bincount(agg, minlength=S), 1)[:, None]
         R = rigid_modes(X - cen[agg])
         rows = np.repeat(np.arange(n), 6)
         cols = (6 * np.repeat(agg, N)[:, None] + np.arange(6)[None, :]).reshape(-1)
@@ -74,14 +99,14 @@ def run(sizes, deg, nodes_per_small, S2, rtol=1e-8):
         return sla.cho_solve(sla.cho_factor(E), np.eye(E.shape[0]))
 
     # two-level with the large aggregates only (today's csrc/coarse.inl)
-    _, _, Z2 = level(S2)
+    _, _, Z2 = level(S2, bg2 if boxes else None)
     E2inv = dense_inverse((Z2.T @ Km @ Z2).toarray())
     _, it2 = pcg(Kff, b, lambda r: jac(r) + Z2 @ (E2inv @ (Z2.T @ r)), rtol, 20000)
     print(f"   two-level, {S2} aggregates ({nd / S2:.0f} nodes each): {it2} iterations", flush=True)
 
     # three-level: small aggregates (S1 a multiple of S2 so that the large ones are unions of consecutive small ones)
-    S1 = max(S2, int(round(nd / nodes_per_small / S2)) * S2)
-    agg1, cen1, Z1 = level(S1)
+    S1 = int(np.prod(bg1)) if boxes else max(S2, int(round(nd / nodes_per_small / S2)) * S2)
+    agg1, cen1, Z1 = level(S1, bg1 if boxes else None)
     K1 = (Z1.T @ Km @ Z1).tocsr()
     b1 = K1.tobsr((6, 6)); b1.sort_indices()
     B1inv = np.zeros((S1, 6, 6))
@@ -92,9 +117,13 @@ def run(sizes, deg, nodes_per_small, S2, rtol=1e-8):
         blk[np.diag_indices(6)] = np.where(d == 0.0, 1.0, d * (1 + 1e-8))
         B1inv[a] = np.linalg.inv(blk)
     # level 2 in level-1 coordinates: small aggregate a in large aggregate A: t_a = T + W x (x_a - X_A), w_a = W
-    grp = (np.arange(S1) * S2) // S1
+    if boxes:      # small box (i, j, k) of grid b1 lies in large box (i // r, j // r, k // r) of grid b2
+        ii, jj, kk = np.meshgrid(np.arange(bg1[0]), np.arange(bg1[1]), np.arange(bg1[2]), indexing="ij")
+        grp = (((ii // r) * bg2[1] + jj // r) * bg2[2] + kk // r).reshape(-1)
+    else:
+        grp = (np.arange(S1) * S2) // S1
     cen2 = np.zeros((S2, 3)); cnt1 = np.bincount(agg1, minlength=S1).astype(float)
-    np.add.at(cen2, grp, cen1 * cnt1[:, None]); cen2 /= np.bincount(grp, weights=cnt1, minlength=S2)[:, None]
+    np.add.at(cen2, grp, np.nan_to_num(cen1) * cnt1[:, None]); cen2 /= np.maximum(np.bincount(grp, weights=cnt1, minlength=S2), 1)[:, None]
     dvec = cen1 - cen2[grp]
     blocks = np.zeros((S1, 6, 6))
     blocks[:, :3, :3] = np.eye(3); blocks[:, 3:, 3:] = np.eye(3)
@@ -158,4 +187,4 @@ if __name__ == "__main__":
     deg = int(sys.argv[2]) if len(sys.argv) > 2 else 2
     nps = int(sys.argv[3]) if len(sys.argv) > 3 else 30
     S2 = int(sys.argv[4]) if len(sys.argv) > 4 else 32
-    run(sizes, deg, nps, S2)
+    run(sizes, deg, nps, S2, boxes=len(sys.argv) > 5 and sys.argv[5] == "boxes")
