@@ -125,3 +125,14 @@ def test_box_grid_choice():
             multi = np.array(b) > 1
             if multi.sum() >= 2:
                 assert edges[multi].max() / edges[multi].min() < 2.5
+
+
+def test_emulated_two_level_pcg_needs_far_fewer_iterations():
+    """tools/emulate_two_level.py: the device algorithm (box aggregates, masked rigid modes, regularised dense E,
+    additive correction with r.z += c.y) restated in numpy, on a small linear-tet cantilever."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    from emulate_two_level import run
+    it0, it1 = run(3, 1, (16, 4, 4), 32, verbose=False)
+    assert it1 < 0.5 * it0, (it0, it1)
