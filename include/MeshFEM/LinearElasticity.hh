@@ -703,6 +703,9 @@ private:
         BENCHMARK_START_TIMER_SECTION("Elasticity Solve");
         std::vector<std::vector<Real>> rhs;
         for (const auto &f : fs) rhs.push_back(f.data());
+        // the system under the rows is singular (its rigid modes are free): block-Jacobi PCG handles a consistent
+        // semi-definite system, the aggregation coarse space (whose E = Z'KZ would be singular too) stays off
+        m_system.setOption("coarse_aggregates", 0);
         auto us = RigidMotionConstraints::solve(N * numDoFs(), m_constraintRows, m_systemFixedVars, candidateRigidModes(), rhs,
             [&](const std::vector<std::vector<Real>> &bs) {
                 std::vector<std::vector<Real>> xs;

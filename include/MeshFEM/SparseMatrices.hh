@@ -165,6 +165,8 @@ public:
         BENCHMARK_ADD_DEVICE_SECONDS("PCG (device)", seconds);
     }
     void setTolerance(double rtol, int maxIters) { m_rtol = rtol; m_maxIters = maxIters; }
+    // solver options of the C ABI (include/mfem_b200.h: "coarse_aggregates", "coarse_fine_nodes", ...)
+    void setOption(const char *name, long long value) { mfemCheck(handle(), mfem_b200_set_option(handle(), name, (int64_t)value)); }
     const mfem_b200_solve_info &lastSolveInfo() const { return m_lastInfo; }
     void setEconomyMode(bool) {}
     void sumAndDumpUpper(const std::string &path) { mfemCheck(handle(), mfem_b200_dump_upper_triplets(handle(), path.c_str())); }

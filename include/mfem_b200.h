@@ -182,6 +182,15 @@ int64_t mfem_b200_launch_count(mfem_b200_handle h);
  * vectors and return the mean device seconds per launch (CUDA events on the handle's
  * stream).  Used by bench.py for the roofline of the dominant kernel.                  */
 int mfem_b200_time_spmv(mfem_b200_handle h, int iters, double *seconds_per_launch);
+/* Diagnostics: z = M^-1 r and *rz = r.z for the preconditioner the next solve would use (block-Jacobi alone, or with the
+ * aggregation levels of "coarse_aggregates" / "coarse_fine_nodes"), r masked on the fixed variables first; per-DoF
+ * vectors in the caller's numbering.  Runs the PCG's own start-up kernels, so the parity tests can compare the operator
+ * inside the iteration with its numpy restatement (tools/emulate_multilevel.py) term by term.                        */
+int mfem_b200_apply_preconditioner(mfem_b200_handle h, const double *r, double *z, double *rz);
+/* Diagnostics: a named array of the aggregation levels as doubles ("sizes" = S1, S2, R, n1, aggBase, level1; "agg1",
+ * "Y1" in the handle's internal DoF order with "int2ext" the map to the caller's; "shift", "B1inv", "Einv", "y1", "y2").
+ * out may be NULL to query the length *n.                                                                           */
+int mfem_b200_get_coarse_array(mfem_b200_handle h, const char *name, double *out, int64_t capacity, int64_t *n);
 
 #ifdef __cplusplus
 }

@@ -25,6 +25,7 @@ SYMBOLS = [
     "mfem_b200_solve", "mfem_b200_apply_K", "mfem_b200_spmv", "mfem_b200_const_strain_load",
     "mfem_b200_avg_strain_stress", "mfem_b200_get_volumes", "mfem_b200_get_timer", "mfem_b200_reset_timers",
     "mfem_b200_launch_count", "mfem_b200_time_spmv", "mfem_b200_set_matrix_triplets", "mfem_b200_comm_share",
+    "mfem_b200_apply_preconditioner", "mfem_b200_get_coarse_array",
 ]
 
 STATUS_NAMES = {
@@ -91,6 +92,8 @@ def load_library():
     lib.mfem_b200_launch_count.argtypes = [c_void_p]
     lib.mfem_b200_launch_count.restype = c_int64
     lib.mfem_b200_time_spmv.argtypes = [c_void_p, c_int, dp]
+    lib.mfem_b200_apply_preconditioner.argtypes = [c_void_p, dp, dp, dp]
+    lib.mfem_b200_get_coarse_array.argtypes = [c_void_p, c_char_p, dp, c_int64, lp]
     lib.mfem_b200_set_matrix_triplets.argtypes = [c_void_p, c_int, c_int64, c_int64, lp, lp, dp, c_int]
     for name in SYMBOLS:
         fn = getattr(lib, name)
@@ -331,6 +334,22 @@ class Handle:
 
     def launch_count(self):
         return self.lib.mfem_b200_launch_count(self._h)
+
+    def apply_preconditioner(self, r):
+        """(M^-1 r, r.M^-1 r) for the preconditioner the next solve would use (diagnostics / parity tests)."""
+        r = _f64(r)
+        z = np.zeros_like(r)
+        rz = c_double()
+        self._check(self.lib.mfem_b200_apply_preconditioner(self._h, _dptr(r), _dptr(z), ctypes.byref(rz)))
+        return z, rz.value
+
+    def coarse_array(self, name):
+        """Named array of the aggregation levels (diagnostics; see mfem_b200_get_coarse_array)."""
+        n = c_int64()
+        self._check(self.lib.mfem_b200_get_coarse_array(self._h, name.encode(), None, 0, ctypes.byref(n)))
+        out = np.zeros(n.value)
+        self._check(self.lib.mfem_b200_get_coarse_array(self._h, name.encode(), _dptr(out), n.value, ctypes.byref(n)))
+        return out
 
     def time_spmv(self, iters=20):
         s = c_double()

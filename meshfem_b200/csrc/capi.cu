@@ -104,13 +104,17 @@ int mfem_b200_set_option(mfem_b200_handle h, const char *name, int64_t value) {
         MFEM_REQUIRE(value >= 0 && value <= 4, MFEM_B200_ERR_INVALID, "spmv_kernel must be 0 (auto), 1 (direct loads), 2 (TMA ring), 3 (index-pipelined) or 4 (symmetric)");
         h->opt_spmv_kernel = (int)value;
     } else if (n == "coarse_aggregates") {
-        MFEM_REQUIRE(value >= 0 && value <= 5461, MFEM_B200_ERR_INVALID, "coarse_aggregates must be 0 (block-Jacobi only) .. 5461");
+        MFEM_REQUIRE(value >= -1 && value <= 5461, MFEM_B200_ERR_INVALID,
+                     "coarse_aggregates must be -1 (automatic), 0 (block-Jacobi only) or 1 .. 5461 large aggregates");
         h->opt_coarse = (int)value;
         h->precondValid = false;
-    } else if (n == "coarse_shape") {
-        MFEM_REQUIRE(value == 0 || value == 1, MFEM_B200_ERR_INVALID, "coarse_shape must be 0 (boxes) or 1 (runs of the internal numbering)");
-        h->opt_coarse_shape = (int)value;
+    } else if (n == "coarse_fine_nodes") {
+        MFEM_REQUIRE(value >= 0 && value <= 100000, MFEM_B200_ERR_INVALID,
+                     "coarse_fine_nodes must be 0 (no level 1) or the number of nodes per small aggregate");
+        h->opt_coarse_fine = (int)value;
         h->precondValid = false;
+    } else if (n == "coarse_shape") {
+        MFEM_REQUIRE(value == 0, MFEM_B200_ERR_INVALID, "coarse_shape: only 0 (nested box grids) is supported");
     } else if (n == "spmv_lanes") {
         MFEM_REQUIRE(value == 0 || value == 8 || value == 16 || value == 32, MFEM_B200_ERR_INVALID,
                      "spmv_lanes must be 0 (auto), 8, 16 or 32");
@@ -134,6 +138,7 @@ int mfem_b200_set_node_positions(mfem_b200_handle h, const double *nodes) {
     MFEM_CUDA(cudaMemcpyAsync(h->nodes, nodes, h->nodes.bytes(), cudaMemcpyHostToDevice, h->stream));
     compute_geometry(h);
     h->precondValid = false;
+    h->meshVersion++;
     API_END(h)
 }
 
@@ -337,7 +342,7 @@ int mfem_b200_solve(mfem_b200_handle h, int nrhs, const double *f, double *u, do
     const size_t n = (size_t)h->nvar();
     int firstErr = MFEM_B200_OK;
     std::string firstMsg;
-    if (h->opt_batch_rhs && nrhs == flat_len(h->N) && h->opt_coarse == 0) {
+    if (h->opt_batch_rhs && nrhs == flat_len(h->N) && h->opt_coarse <= 0) {
         // the cell-problem case: all right-hand sides in one batched PCG (one matrix stream for all of them)
         DevBuf<double> fext(n), fin(n * nrhs), uin(n * nrhs), uext(n);
         for (int k = 0; k < nrhs; ++k) {
@@ -456,6 +461,27 @@ int mfem_b200_time_spmv(mfem_b200_handle h, int iters, double *seconds_per_launc
     API_BEGIN(h)
     MFEM_REQUIRE(iters > 0 && seconds_per_launch, MFEM_B200_ERR_INVALID, "time_spmv: bad arguments");
     *seconds_per_launch = time_spmv(h, iters);
+    API_END(h)
+}
+
+int mfem_b200_apply_preconditioner(mfem_b200_handle h, const double *r, double *z, double *rz) {
+    API_BEGIN(h)
+    MFEM_REQUIRE(r && z && rz, MFEM_B200_ERR_INVALID, "apply_preconditioner: null argument");
+    const size_t n = (size_t)h->nvar();
+    DevBuf<double> a(n), b(n);
+    MFEM_CUDA(cudaMemcpyAsync(a, r, n * 8, cudaMemcpyHostToDevice, h->stream));
+    permute_to_internal(h, a, b);
+    apply_preconditioner(h, b, a, rz);
+    permute_to_external(h, a, b);
+    MFEM_CUDA(cudaMemcpyAsync(z, b, n * 8, cudaMemcpyDeviceToHost, h->stream));
+    MFEM_CUDA(cudaStreamSynchronize(h->stream));
+    API_END(h)
+}
+
+int mfem_b200_get_coarse_array(mfem_b200_handle h, const char *name, double *out, int64_t capacity, int64_t *n) {
+    API_BEGIN(h)
+    MFEM_REQUIRE(name && n, MFEM_B200_ERR_INVALID, "get_coarse_array: null argument");
+    *n = get_coarse_array(h, name, out, capacity);
     API_END(h)
 }
 

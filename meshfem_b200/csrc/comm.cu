@@ -22,6 +22,13 @@ struct Halo {
     std::vector<int64_t> offsets;        // [nNeighbors+1] into idx
     DevBuf<int32_t> idx;                 // internal DoF ids shared with each neighbour, per-neighbour segments
     DevBuf<uint8_t> owned;               // [nDofs] internal numbering
+    DevBuf<uint8_t> shared;              // [nDofs] 1 = DoF appears in some neighbour's list
+    // receive side, per DISTINCT shared DoF: the slots of recvBuf that carry its partial sums (a DoF on a partition
+    // edge is shared with several neighbours), so that one launch adds everything in a fixed order
+    DevBuf<int32_t> uIdx;                // [nUnique] internal DoF id
+    DevBuf<int64_t> uPtr;                // [nUnique+1] into uPos
+    DevBuf<int32_t> uPos;                // [total] slot in recvBuf (units of `width` doubles)
+    int64_t nUnique = 0;
     DevBuf<double> sendBuf, recvBuf;     // total * maxWidth doubles
     int64_t total = 0;
     int maxWidth = 9;
@@ -42,14 +49,21 @@ __global__ void k_halo_pack(int64_t n, int width, const int32_t *__restrict__ id
     const int c = (int)(t - k * width);
     buf[t] = vec[(int64_t)idx[k] * width + c];
 }
-// one launch per neighbour: inside a neighbour's segment every DoF appears once -> no write conflicts
-__global__ void k_halo_unpack_add(int64_t n, int width, const int32_t *__restrict__ idx, const double *__restrict__ buf,
-                                  double *__restrict__ vec) {
+// one launch for all neighbours: a thread owns one component of one distinct shared DoF and adds its received
+// partial sums in list order (deterministic; no write conflicts)
+__global__ void k_halo_unpack_add(int64_t nUnique, int width, const int32_t *__restrict__ uIdx, const int64_t *__restrict__ uPtr,
+                                  const int32_t *__restrict__ uPos, const double *__restrict__ buf, double *__restrict__ vec) {
     const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (t >= n * width) return;
-    const int64_t k = t / width;
-    const int c = (int)(t - k * width);
-    vec[(int64_t)idx[k] * width + c] += buf[t];
+    if (t >= nUnique * width) return;
+    const int64_t u = t / width;
+    const int c = (int)(t - u * width);
+    double s = 0.0;
+    for (int64_t k = uPtr[u]; k < uPtr[u + 1]; ++k) s += buf[(int64_t)uPos[k] * width + c];
+    vec[(int64_t)uIdx[u] * width + c] += s;
+}
+__global__ void k_mark_shared(int64_t n, const int32_t *__restrict__ idx, uint8_t *__restrict__ shared) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t < n) shared[idx[t]] = 1;
 }
 __global__ void k_map_shared(int64_t n, const int32_t *__restrict__ localIdx, const int32_t *__restrict__ ext2int,
                              int32_t *__restrict__ out) {
@@ -92,11 +106,14 @@ void halo_exchange_add(mfem_b200_ctx *c, double *vec, int width) {
         MFEM_NCCL(ncclRecv(h.recvBuf.p + off, (size_t)cnt, ncclDouble, h.ranks[q], comm, s));
     }
     MFEM_NCCL(ncclGroupEnd());
-    for (size_t q = 0; q < h.ranks.size(); ++q) {
-        const int64_t off = h.offsets[q], cnt = h.offsets[q + 1] - h.offsets[q];
-        k_halo_unpack_add<<<grid_for(cnt * width, 256), 256, 0, s>>>(cnt, width, h.idx.p + off, h.recvBuf.p + off * width, vec);
-        c->launches++;
-    }
+    k_halo_unpack_add<<<grid_for(h.nUnique * width, 256), 256, 0, s>>>(h.nUnique, width, h.uIdx, h.uPtr, h.uPos, h.recvBuf, vec);
+    c->launches++;
+}
+
+const uint8_t *halo_shared(mfem_b200_ctx *c) {
+    MFEM_REQUIRE(c->halo && c->halo->shared.n == (size_t)c->nDofs, MFEM_B200_ERR_INVALID,
+                 "multi-GPU handle without interface description: call mfem_b200_set_interface after set_mesh");
+    return c->halo->shared;
 }
 
 void allreduce_sum(mfem_b200_ctx *c, const double *in, double *out, int n) {
@@ -181,13 +198,37 @@ int mfem_b200_set_interface(mfem_b200_handle h, int n_neighbors, const int32_t *
             MFEM_REQUIRE(shared_local_dofs[k] >= 0 && shared_local_dofs[k] < h->nDofs, MFEM_B200_ERR_INVALID,
                          "set_interface: shared DoF out of range");
         cudaStream_t s = h->stream;
+        H.shared.alloc((size_t)h->nDofs);
+        MFEM_CUDA(cudaMemsetAsync(H.shared, 0, H.shared.bytes(), s));
         if (H.total) {
             DevBuf<int32_t> tmp((size_t)H.total);
             MFEM_CUDA(cudaMemcpyAsync(tmp, shared_local_dofs, tmp.bytes(), cudaMemcpyHostToDevice, s));
             H.idx.alloc((size_t)H.total);
             k_map_shared<<<grid_for(H.total, 256), 256, 0, s>>>(H.total, tmp, h->ext2int, H.idx);
+            k_mark_shared<<<grid_for(H.total, 256), 256, 0, s>>>(H.total, H.idx, H.shared);
             H.sendBuf.alloc((size_t)H.total * H.maxWidth);
             H.recvBuf.alloc((size_t)H.total * H.maxWidth);
+            // distinct shared DoFs (caller's numbering) and the receive slots of each, in slot order
+            std::vector<int32_t> order((size_t)H.total);
+            for (int64_t k = 0; k < H.total; ++k) order[(size_t)k] = (int32_t)k;
+            std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return shared_local_dofs[a] < shared_local_dofs[b]; });
+            std::vector<int32_t> uExt;
+            std::vector<int64_t> uPtr;
+            for (int64_t k = 0; k < H.total; ++k) {
+                const int32_t d = shared_local_dofs[order[(size_t)k]];
+                if (uExt.empty() || uExt.back() != d) { uExt.push_back(d); uPtr.push_back(k); }
+            }
+            uPtr.push_back(H.total);
+            H.nUnique = (int64_t)uExt.size();
+            DevBuf<int32_t> tmpU((size_t)H.nUnique);
+            MFEM_CUDA(cudaMemcpyAsync(tmpU, uExt.data(), tmpU.bytes(), cudaMemcpyHostToDevice, s));
+            H.uIdx.alloc((size_t)H.nUnique);
+            k_map_shared<<<grid_for(H.nUnique, 256), 256, 0, s>>>(H.nUnique, tmpU, h->ext2int, H.uIdx);
+            H.uPtr.alloc(uPtr.size());
+            H.uPos.alloc((size_t)H.total);
+            MFEM_CUDA(cudaMemcpyAsync(H.uPtr, uPtr.data(), H.uPtr.bytes(), cudaMemcpyHostToDevice, s));
+            MFEM_CUDA(cudaMemcpyAsync(H.uPos, order.data(), H.uPos.bytes(), cudaMemcpyHostToDevice, s));
+            h->launches += 3;
             MFEM_CUDA(cudaStreamSynchronize(s));
         }
         DevBuf<uint8_t> oext((size_t)h->nDofs);
@@ -198,6 +239,7 @@ int mfem_b200_set_interface(mfem_b200_handle h, int n_neighbors, const int32_t *
         MFEM_CUDA(cudaStreamSynchronize(s));
         MFEM_CUDA(cudaGetLastError());
         h->precondValid = false;
+        h->meshVersion++;
         return MFEM_B200_OK;
     } catch (const CudaError &e) {
         h->err = e.what();

@@ -70,7 +70,8 @@ struct PcgWork {
     DevBuf<double> x, r, z, p, Ap, b, ufix;
     DevBuf<double> partials;     // per-CTA partial sums, 4 slots
     DevBuf<double> scal;         // device scalars (see solver.cu)
-    DevBuf<double> dotLoc;       // multi-GPU: this rank's partial sums before the all-reduce
+    DevBuf<double> dotLoc;       // multi-GPU (batched solver): this rank's partial sums before the all-reduce
+    DevBuf<double> red;          // [2 + 32768] r.z, r.r and the coarse residuals c2: ONE all-reduce per PCG iteration
     DevBuf<unsigned> ticket;     // last-block tickets
     DevBuf<int> status;          // [0]=iterations done, [1]=state (0 running, 1 converged, 2 breakdown, 3 nan)
 };
@@ -94,8 +95,10 @@ struct mfem_b200_ctx {
     int opt_spmm_kernel = 0;               // batched PCG: 0/1 full-warp SpMM, 2 half-warp split SpMM (even batch sizes)
     int opt_batch_rhs = 1;                 // solve flatLen(N) right-hand sides as one batched PCG (SpMM)
     int opt_spmv_lanes = 0;                // lanes per block row in the SpMV (0 = choose from the mean row length)
-    int opt_coarse = 0;                    // aggregates of the two-level preconditioner (0 = block-Jacobi only)
-    int opt_coarse_shape = 0;              // 0 = near-cubic boxes (default), 1 = contiguous runs of the internal numbering
+    int opt_coarse = -1;                   // large aggregates of the multilevel preconditioner: -1 automatic (from the
+                                           // problem size; block-Jacobi only below 30k DoFs), 0 = block-Jacobi only
+    int opt_coarse_fine = 32;              // DoFs (nodes) per small (level-1) aggregate; 0 = no level 1 (two-level method)
+    int64_t meshVersion = 0;               // bumped by everything that changes DoFs, positions or the interface
 
     // mesh
     int N = 0, deg = 0, npe = 0;
@@ -242,10 +245,13 @@ bool pcg_solve_multi(mfem_b200_ctx *c, int nrhs, const double *f_int, double *u_
 void free_work_multi(mfem_b200_ctx *c);
 void free_coarse_space(mfem_b200_ctx *c);
 double time_spmv(mfem_b200_ctx *c, int iters);
+int64_t get_coarse_array(mfem_b200_ctx *c, const std::string &name, double *out, int64_t capacity);
+void apply_preconditioner(mfem_b200_ctx *c, const double *r_int, double *z_int, double *rz);
 // comm.cu
 void halo_exchange_add(mfem_b200_ctx *c, double *vec_int, int width);   // no-op on one rank
 void allreduce_sum(mfem_b200_ctx *c, const double *in, double *out, int n);
 const uint8_t *halo_owned(mfem_b200_ctx *c);
+const uint8_t *halo_shared(mfem_b200_ctx *c);      // [nDofs] 1 = DoF shared with another rank
 // aux.cu
 void permute_to_internal(mfem_b200_ctx *c, const double *ext, double *in);   // per-DoF vectors
 void permute_to_external(mfem_b200_ctx *c, const double *in, double *ext);

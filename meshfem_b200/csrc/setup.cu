@@ -476,8 +476,11 @@ void upload_external_bsr(mfem_b200_ctx *c, int dim, int64_t nb, const std::vecto
     c->externalMatrix = true;
     c->geomValid = c->haveMaterial = false;
     c->precondValid = c->workValid = false;
+    c->meshVersion++;
     c->fixedHost.assign((size_t)nb * dim, 0);
     c->nFixed = 0;
+    // a re-set system starts without constraints on the device too (ensure_work re-zeroes only on a size change)
+    c->fixedMask.free(); c->fixedVals.free();
     c->nnzb = (int64_t)colidx.size();
     c->rowptr.alloc((size_t)nb + 1 + 2);
     c->colidx.alloc((size_t)c->nnzb + 4);
@@ -515,9 +518,12 @@ void setup_mesh(mfem_b200_ctx *c, int dim, int degree, int64_t nNodes, const dou
     c->nDofs = c->periodic ? nDofs : nNodes;
     MFEM_REQUIRE(c->nDofs > 0 && c->nDofs <= nNodes, MFEM_B200_ERR_INVALID, "bad n_dofs");
     c->patternValid = c->valuesValid = c->geomValid = c->precondValid = c->workValid = false;
+    c->meshVersion++;
     c->externalMatrix = false;
     c->fixedHost.assign((size_t)c->nDofs * dim, 0);
     c->nFixed = 0;
+    // a re-set mesh starts without constraints on the device too (ensure_work re-zeroes only on a size change)
+    c->fixedMask.free(); c->fixedVals.free();
 
     const int npe = c->npe;
     c->nodes.alloc((size_t)nNodes * dim);

@@ -936,128 +936,122 @@ __global__ void k_jacobi_setup(int64_t nb, const int64_t *__restrict__ rowptr, c
         for (int c = 0; c < N; ++c) Minv[row * NN + r * N + c] = inv[r][c];
 }
 
+static int sm_count(mfem_b200_ctx *c);
+
+#include "coarse.inl"
+
 // ---------------------------------------------------------------------------
 // K4  fused vector kernels (one thread per DoF block, grid-stride)
 // ---------------------------------------------------------------------------
-// init: r = mask(b); z = Minv r; p = z; x = 0; partial sums of r.z and r.r over owned DoFs
-template <int N>
+// update (INIT: start-up): alpha = rz/pAp; x += alpha p; r -= alpha Ap  (INIT: x = 0, r = mask(b));  z = Minv r;
+// partial sums of r.z and r.r over owned DoFs -> red[0], red[1]; with a coarse space also c1 += P1^T r over owned
+// DoFs (coarse.inl).  A warp holds 32 consecutive DoFs, which is what the segmented restriction needs.
+template <int N, bool INIT>
 __global__ void __launch_bounds__(kVecThreads)
-k_pcg_init(int64_t nb, const double *__restrict__ b, const uint8_t *__restrict__ fixedMask,
-           const uint8_t *__restrict__ owned, const double *__restrict__ Minv, double *__restrict__ x,
-           double *__restrict__ r, double *__restrict__ z, double *__restrict__ p, double *partials, unsigned *ticket,
-           double *dotOut /* [2]: rz, rr */) {
+k_pcg_update(int64_t nb, const double *__restrict__ b, const uint8_t *__restrict__ fixedMask, const double *__restrict__ Minv,
+             const uint8_t *__restrict__ owned, const double *__restrict__ p, const double *__restrict__ Ap, double *__restrict__ x,
+             double *__restrict__ r, double *__restrict__ z, double *partials, unsigned *ticket, const double *__restrict__ scal,
+             double *red /* [0] = r.z, [1] = r.r */, const int *status, const int32_t *__restrict__ agg1,
+             const double *__restrict__ Y1, double *c1) {
     constexpr int NN = N * N;
+    if (!INIT && status[ST_STATE] != 0) return;
+    const double alpha = INIT ? 0.0 : scal[S_RZ] / scal[S_PAP];
+    const int lane = threadIdx.x & 31;
     double acc[2] = {0.0, 0.0};
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nb; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t base = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) & ~31ll; base < nb; base += stride) {
+        const int64_t i = base + lane;
+        const bool active = i < nb;
         double rv[N], zv[N];
+        bool mine = false;
+        if (active) {
 #pragma unroll
-        for (int k = 0; k < N; ++k) rv[k] = fixedMask[i * N + k] ? 0.0 : b[i * N + k];
+            for (int k = 0; k < N; ++k) {
+                if (INIT) {
+                    x[i * N + k] = 0.0;
+                    rv[k] = fixedMask[i * N + k] ? 0.0 : b[i * N + k];
+                } else {
+                    x[i * N + k] += alpha * p[i * N + k];
+                    rv[k] = r[i * N + k] - alpha * Ap[i * N + k];
+                }
+            }
 #pragma unroll
-        for (int k = 0; k < N; ++k) {
-            double s = 0.0;
+            for (int k = 0; k < N; ++k) {
+                double s = 0.0;
 #pragma unroll
-            for (int m = 0; m < N; ++m) s += Minv[i * NN + k * N + m] * rv[m];
-            zv[k] = s;
+                for (int m = 0; m < N; ++m) s += Minv[i * NN + k * N + m] * rv[m];
+                zv[k] = s;
+            }
+            mine = !(owned && !owned[i]);
+            const double wgt = mine ? 1.0 : 0.0;
+#pragma unroll
+            for (int k = 0; k < N; ++k) {
+                r[i * N + k] = rv[k]; z[i * N + k] = zv[k];
+                acc[0] += wgt * rv[k] * zv[k];
+                acc[1] += wgt * rv[k] * rv[k];
+            }
         }
-        const double wgt = (owned && !owned[i]) ? 0.0 : 1.0;
+        if (c1) {                       // kernel-uniform
+            if (!mine) {
 #pragma unroll
-        for (int k = 0; k < N; ++k) {
-            x[i * N + k] = 0.0; r[i * N + k] = rv[k]; z[i * N + k] = zv[k]; p[i * N + k] = zv[k];
-            acc[0] += wgt * rv[k] * zv[k];
-            acc[1] += wgt * rv[k] * rv[k];
+                for (int k = 0; k < N; ++k) rv[k] = 0.0;
+            }
+            coarse_restrict_warp<N>(active, i, rv, agg1, Y1, c1, lane);
         }
     }
     block_reduce_store<2>(acc, partials);
     if (last_block(ticket)) {
         const double rz = final_sum(partials, gridDim.x);
         const double rr = final_sum(partials + gridDim.x, gridDim.x);
-        if (threadIdx.x == 0) { dotOut[0] = rz; dotOut[1] = rr; }
+        if (threadIdx.x == 0) { red[0] = rz; red[1] = rr; }
     }
 }
 
-// after the (all-reduced) initial sums are in scal[S_RZ_NEW], scal[S_RR]
-__global__ void k_pcg_init_finalize(double *scal, int *status, double tol2) {
+// after the start-up sums are in rzrr[0..1] (all-reduced, coarse part included)
+__global__ void k_pcg_init_finalize(double *scal, const double *rzrr, int *status, double tol2) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    const double rr = scal[S_RR];
-    scal[S_RZ] = scal[S_RZ_NEW];
+    const double rr = rzrr[1];
+    scal[S_RZ] = rzrr[0];
+    scal[S_RR] = rr;
     scal[S_BB] = rr;
     scal[S_TOL2] = tol2;
     status[ST_ITERS] = 0;
     status[ST_STATE] = (rr == 0.0) ? 1 : ((rr != rr) ? 3 : 0);
 }
 
-// p.Ap over owned DoFs (multi-GPU only: Ap is complete only after the interface exchange)
+// direction: beta = rz_new/rz; p = z + [mask(R1 (y1 + P2 y2))] + beta p  (INIT: p = z + coarse part).  The last CTA then
+// closes the iteration on the (global) scalars: rotates rz, counts the iteration, decides convergence / breakdown.
+// With a coarse space the kernel also clears c2 (red[2..]) for the next application.
+template <int N, bool INIT>
 __global__ void __launch_bounds__(kVecThreads)
-k_dot_owned(int64_t nb, int N, const double *__restrict__ a, const double *__restrict__ b2,
-            const uint8_t *__restrict__ owned, double *partials, unsigned *ticket, double *dotOut, const int *status) {
-    if (status[ST_STATE] != 0) return;
-    double acc[1] = {0.0};
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nb; i += (int64_t)gridDim.x * blockDim.x) {
-        if (!owned[i]) continue;
-        for (int k = 0; k < N; ++k) acc[0] += a[i * N + k] * b2[i * N + k];
-    }
-    block_reduce_store<1>(acc, partials);
-    if (last_block(ticket)) {
-        const double s = final_sum(partials, gridDim.x);
-        if (threadIdx.x == 0) dotOut[0] = s;
-    }
-}
-
-// update: alpha = rz/pAp; x += alpha p; r -= alpha Ap; z = Minv r; partial sums of r.z and r.r
-template <int N>
-__global__ void __launch_bounds__(kVecThreads)
-k_pcg_update(int64_t nb, const double *__restrict__ Minv, const uint8_t *__restrict__ owned,
-             const double *__restrict__ p, const double *__restrict__ Ap, double *__restrict__ x,
-             double *__restrict__ r, double *__restrict__ z, double *partials, unsigned *ticket,
-             const double *__restrict__ scal, double *dotOut /* [2]: rz_new, rr */, const int *status) {
-    constexpr int NN = N * N;
-    if (status[ST_STATE] != 0) return;
-    const double alpha = scal[S_RZ] / scal[S_PAP];
-    double acc[2] = {0.0, 0.0};
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nb; i += (int64_t)gridDim.x * blockDim.x) {
-        double rv[N], zv[N];
+k_pcg_direction(int64_t nb, const double *__restrict__ z, double *__restrict__ p, double *scal, const double *rzrr, int *status,
+                unsigned *ticket, const uint8_t *__restrict__ fixedMask, const int32_t *__restrict__ agg1,
+                const double *__restrict__ Y1, const double *__restrict__ y1, const double *__restrict__ y2,
+                const double *__restrict__ shift, int64_t S1, int64_t R, int64_t aggBase, bool level1, double *red, int64_t nc2) {
+    if (!INIT && status[ST_STATE] != 0) return;
+    const double beta = INIT ? 0.0 : rzrr[0] / scal[S_RZ];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x, t0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    for (int64_t i = t0; i < nb; i += stride) {
+        double v[N];
+#pragma unroll
+        for (int k = 0; k < N; ++k) v[k] = 0.0;
+        if (agg1) coarse_prolong_dof<N>(i, agg1, Y1, y1, y2, shift, S1, R, aggBase, level1, v);
 #pragma unroll
         for (int k = 0; k < N; ++k) {
-            x[i * N + k] += alpha * p[i * N + k];
-            rv[k] = r[i * N + k] - alpha * Ap[i * N + k];
-        }
-#pragma unroll
-        for (int k = 0; k < N; ++k) {
-            double s = 0.0;
-#pragma unroll
-            for (int m = 0; m < N; ++m) s += Minv[i * NN + k * N + m] * rv[m];
-            zv[k] = s;
-        }
-        const double wgt = (owned && !owned[i]) ? 0.0 : 1.0;
-#pragma unroll
-        for (int k = 0; k < N; ++k) {
-            r[i * N + k] = rv[k]; z[i * N + k] = zv[k];
-            acc[0] += wgt * rv[k] * zv[k];
-            acc[1] += wgt * rv[k] * rv[k];
+            const double zk = z[i * N + k] + ((agg1 && !fixedMask[i * N + k]) ? v[k] : 0.0);
+            p[i * N + k] = INIT ? zk : zk + beta * p[i * N + k];
         }
     }
-    block_reduce_store<2>(acc, partials);
-    if (last_block(ticket)) {
-        const double rz = final_sum(partials, gridDim.x);
-        const double rr = final_sum(partials + gridDim.x, gridDim.x);
-        if (threadIdx.x == 0) { dotOut[0] = rz; dotOut[1] = rr; }
+    if (INIT) {
+        for (int64_t k = t0; k < nc2; k += stride) red[2 + k] = 0.0;
+        return;
     }
-}
-
-// direction: beta = rz_new/rz; p = z + beta p.  The last CTA then closes the iteration on the
-// (global) scalars: rotates rz, counts the iteration, decides convergence / breakdown.
-template <int N>
-__global__ void __launch_bounds__(kVecThreads)
-k_pcg_direction(int64_t n, const double *__restrict__ z, double *__restrict__ p, double *scal, int *status,
-                unsigned *ticket) {
-    if (status[ST_STATE] != 0) return;
-    const double beta = scal[S_RZ_NEW] / scal[S_RZ];
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        p[i] = z[i] + beta * p[i];
+    // rzrr may alias red[0..1] (no coarse space): read the scalars before anything is cleared, by the last CTA only
     if (last_block(ticket)) {
         if (threadIdx.x == 0) {
-            const double pAp = scal[S_PAP], rz = scal[S_RZ_NEW], rr = scal[S_RR];
+            const double pAp = scal[S_PAP], rz = rzrr[0], rr = rzrr[1];
             scal[S_RZ] = rz;
+            scal[S_RR] = rr;
             status[ST_ITERS] += 1;
             int st = 0;
             if (!(pAp > 0.0)) st = 2;
@@ -1066,6 +1060,7 @@ k_pcg_direction(int64_t n, const double *__restrict__ z, double *__restrict__ p,
             status[ST_STATE] = st;     // written last; kernels of later iterations read it first
         }
     }
+    for (int64_t k = t0; k < nc2; k += stride) red[2 + k] = 0.0;      // nobody reads c2 in this kernel
 }
 
 // b = f - K ufix on free rows (ufix carries the fixed values, zero elsewhere); u = x + ufix
@@ -1113,12 +1108,14 @@ void ensure_work(mfem_b200_ctx *c) {
     w.partials.alloc(4 * (size_t)kMaxPartials);
     w.scal.alloc(S_COUNT);
     w.dotLoc.alloc(DL_COUNT);
-    w.ticket.alloc(4);
+    w.red.alloc(2 + 32768);          // (r.z, r.r, coarse residuals c2): one all-reduce per iteration
+    w.ticket.alloc(8);
     w.status.alloc(4);
     MFEM_CUDA(cudaMemsetAsync(w.ticket, 0, w.ticket.bytes(), c->stream));
     MFEM_CUDA(cudaMemsetAsync(w.status, 0, w.status.bytes(), c->stream));
     MFEM_CUDA(cudaMemsetAsync(w.scal, 0, w.scal.bytes(), c->stream));
     MFEM_CUDA(cudaMemsetAsync(w.dotLoc, 0, w.dotLoc.bytes(), c->stream));
+    MFEM_CUDA(cudaMemsetAsync(w.red, 0, w.red.bytes(), c->stream));
     if (c->fixedMask.n != n) {
         c->fixedMask.alloc(n);
         c->fixedVals.alloc(n);
@@ -1241,8 +1238,6 @@ void spmv_plain(mfem_b200_ctx *c, const double *x_int, double *y_int) {
     MFEM_CUDA(cudaGetLastError());
 }
 
-#include "coarse.inl"
-
 void free_coarse_space(mfem_b200_ctx *c) { free_coarse(c); }
 
 void build_preconditioner(mfem_b200_ctx *c) {
@@ -1276,7 +1271,7 @@ void build_preconditioner(mfem_b200_ctx *c) {
     MFEM_REQUIRE(nbad == 0, MFEM_B200_ERR_NOT_SPD,
                  "block-Jacobi: " + std::to_string(nbad) + " diagonal blocks are not positive definite");
     timer.stop();
-    if (c->opt_coarse > 0) build_coarse(c); else free_coarse(c);
+    if (c->opt_coarse != 0) build_coarse(c); else free_coarse(c);
     c->precondValid = true;
 }
 
@@ -1287,30 +1282,65 @@ static void spmv_exchanged(mfem_b200_ctx *c, const double *x, double *y, bool ma
     halo_exchange_add(c, y, N);
 }
 
+// the preconditioner's tail after k_pcg_update left r.z / r.r in red[0..1] and the level-1 residuals in c1:
+// level 1, ONE all-reduce of (r.z, r.r, c2), dense level.  Returns where the final (r.z, r.r) pair lives.
+template <int N>
+static const double *enqueue_precond_tail(mfem_b200_ctx *c, const int *status) {
+    PcgWork &w = c->work;
+    cudaStream_t s = c->stream;
+    const bool multi = c->nRanks > 1;
+    if (!c->coarse) {
+        if (multi) allreduce_sum(c, w.red, w.red, 2);
+        return w.red;
+    }
+    CoarseSpace &cs = *c->coarse;
+    const int g1 = (int)std::max<int64_t>(1, std::min<int64_t>((cs.n1 + kVecThreads - 1) / kVecThreads, (int64_t)sm_count(c) * 8));
+    k_coarse_level1<N><<<g1, kVecThreads, 0, s>>>(cs.S1, cs.n1, cs.R, cs.aggBase, cs.level1, cs.c1, cs.y1, cs.B1inv, cs.shift, w.red, status);
+    if (multi) allreduce_sum(c, w.red, w.red, (int)(2 + cs.nc2));
+    const int gg = (int)std::max<int64_t>(1, std::min<int64_t>((cs.nc2 + 7) / 8, std::min<int64_t>(kMaxPartials, (int64_t)sm_count(c) * 8)));
+    k_coarse_gemv<<<gg, kVecThreads, 0, s>>>(cs.nc2, cs.Einv, w.red, cs.y2, w.partials + 2 * (size_t)kMaxPartials, w.ticket + 3,
+                                             w.scal.p + S_RZ_NEW, status);
+    c->launches += 2;
+    return w.scal.p + S_RZ_NEW;
+}
+
+template <int N, bool INIT>
+static void launch_direction(mfem_b200_ctx *c, const double *rzrr) {
+    PcgWork &w = c->work;
+    CoarseSpace *cs = c->coarse;
+    k_pcg_direction<N, INIT><<<vec_grid(c, c->nDofs), kVecThreads, 0, c->stream>>>(
+        c->nDofs, w.z, w.p, w.scal, rzrr, w.status, w.ticket + 2, c->fixedMask, cs ? cs->agg1.p : nullptr, cs ? cs->Y1.p : nullptr,
+        cs ? cs->y1.p : nullptr, cs ? cs->y2.p : nullptr, cs ? cs->shift.p : nullptr, cs ? cs->S1 : 0, cs ? cs->R : 1,
+        cs ? cs->aggBase : 0, cs ? cs->level1 : false, w.red, cs ? cs->nc2 : 0);
+    c->launches++;
+}
+
+// One PCG iteration.  1 rank: SpMV (+ p.Ap) -> update (+ restriction) -> [level 1 -> dense level] -> direction.
+// N ranks: p.Ap = sum over ranks of p_loc . (K_loc p_loc) -- the LOCAL products before the exchange, over all local
+// rows, because K = sum of the ranks' element matrices -- so the same fused SpMV epilogue serves, and its 1-double
+// all-reduce travels next to the interface exchange; the second (and last) all-reduce of the iteration carries
+// (r.z, r.r, coarse residuals) together.
 template <int N>
 static void enqueue_iteration(mfem_b200_ctx *c) {
     PcgWork &w = c->work;
-    const int64_t nb = c->nDofs, n = c->nvar();
+    const int64_t nb = c->nDofs;
     const int vgrid = vec_grid(c, nb);
     const bool multi = c->nRanks > 1;
     const uint8_t *owned = multi ? halo_owned(c) : nullptr;
-    if (!multi) {
-        launch_spmv<N>(c, w.p, w.Ap, true, true);             // p.Ap fused into the SpMV epilogue
-    } else {
+    CoarseSpace *cs = c->coarse;
+    launch_spmv<N>(c, w.p, w.Ap, true, true);                 // p.Ap fused into the SpMV epilogue -> scal[S_PAP]
+    if (multi) {
         // masked rows stay zero through the exchange: every sharer masks the same DoFs
-        spmv_exchanged<N>(c, w.p, w.Ap, true);
-        k_dot_owned<<<vgrid, kVecThreads, 0, c->stream>>>(nb, N, w.p, w.Ap, owned, w.partials, w.ticket, w.dotLoc.p + DL_PAP,
-                                                         w.status);
-        c->launches++;
-        allreduce_sum(c, w.dotLoc.p + DL_PAP, w.scal.p + S_PAP, 1);
+        halo_exchange_add(c, w.Ap, N);
+        allreduce_sum(c, w.scal.p + S_PAP, w.scal.p + S_PAP, 1);
     }
-    k_pcg_update<N><<<vgrid, kVecThreads, 0, c->stream>>>(nb, c->Minv, owned, w.p, w.Ap, w.x, w.r, w.z, w.partials,
-                                                           w.ticket + 1, w.scal,
-                                                           multi ? w.dotLoc.p + DL_RZ_NEW : w.scal.p + S_RZ_NEW, w.status);
-    if (multi) allreduce_sum(c, w.dotLoc.p + DL_RZ_NEW, w.scal.p + S_RZ_NEW, 2);
-    if (c->coarse) apply_coarse<N>(c, w.r, w.z, nullptr, w.scal.p + S_RZ_NEW, w.status);      // z += Z E^-1 Z^T r
-    k_pcg_direction<N><<<vec_grid(c, n), kVecThreads, 0, c->stream>>>(n, w.z, w.p, w.scal, w.status, w.ticket + 2);
-    c->launches += 2;
+    k_pcg_update<N, false><<<vgrid, kVecThreads, 0, c->stream>>>(nb, nullptr, c->fixedMask, c->Minv, owned, w.p, w.Ap, w.x, w.r, w.z,
+                                                                  w.partials, w.ticket + 1, w.scal, w.red, w.status,
+                                                                  cs ? cs->agg1.p : nullptr, cs ? cs->Y1.p : nullptr,
+                                                                  cs ? cs->c1.p : nullptr);
+    c->launches++;
+    const double *rzrr = enqueue_precond_tail<N>(c, w.status);
+    launch_direction<N, false>(c, rzrr);
 }
 
 template <int N>
@@ -1321,39 +1351,42 @@ static void pcg_impl(mfem_b200_ctx *c, const double *f_int, double *u_int, doubl
     const int64_t nb = c->nDofs, n = c->nvar();
     const bool multi = c->nRanks > 1;
     const uint8_t *owned = multi ? halo_owned(c) : nullptr;
-    // b = f - K ufix  (masked rows are zeroed by the init kernel)
-    if (multi) spmv_exchanged<N>(c, c->fixedVals, w.Ap, false);
-    else launch_spmv<N>(c, c->fixedVals, w.Ap, false, false);
-    k_axpby<<<vec_grid(c, n), kVecThreads, 0, s>>>(n, 1.0, f_int, -1.0, w.Ap, w.b);
-    k_pcg_init<N><<<vec_grid(c, nb), kVecThreads, 0, s>>>(nb, w.b, c->fixedMask, owned, c->Minv, w.x, w.r, w.z, w.p,
-                                                          w.partials, w.ticket + 1,
-                                                          multi ? w.dotLoc.p + DL_RZ_NEW : w.scal.p + S_RZ_NEW);
-    if (multi) allreduce_sum(c, w.dotLoc.p + DL_RZ_NEW, w.scal.p + S_RZ_NEW, 2);
-    if (c->coarse) {
-        MFEM_CUDA(cudaMemsetAsync(c->coarse->cvec, 0, c->coarse->cvec.bytes(), s));
-        apply_coarse<N>(c, w.r, w.z, w.p, w.scal.p + S_RZ_NEW, nullptr);                         // z0, p0 = z0, r.z0
-    }
-    k_pcg_init_finalize<<<1, 32, 0, s>>>(w.scal, w.status, rtol * rtol);
-    c->launches += 3;
-    MFEM_CUDA(cudaGetLastError());
-
+    CoarseSpace *cs = c->coarse;
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0, s);
+    // b = f - K ufix  (masked rows are zeroed by the start-up kernel)
+    if (multi) spmv_exchanged<N>(c, c->fixedVals, w.Ap, false);
+    else launch_spmv<N>(c, c->fixedVals, w.Ap, false, false);
+    k_axpby<<<vec_grid(c, n), kVecThreads, 0, s>>>(n, 1.0, f_int, -1.0, w.Ap, w.b);
+    if (cs) {
+        MFEM_CUDA(cudaMemsetAsync(cs->c1, 0, cs->c1.bytes(), s));
+        MFEM_CUDA(cudaMemsetAsync(w.red, 0, w.red.bytes(), s));
+    }
+    k_pcg_update<N, true><<<vec_grid(c, nb), kVecThreads, 0, s>>>(nb, w.b, c->fixedMask, c->Minv, owned, nullptr, nullptr, w.x, w.r, w.z,
+                                                                   w.partials, w.ticket + 1, w.scal, w.red, nullptr,
+                                                                   cs ? cs->agg1.p : nullptr, cs ? cs->Y1.p : nullptr,
+                                                                   cs ? cs->c1.p : nullptr);
+    const double *rzrr = enqueue_precond_tail<N>(c, nullptr);                                // r.z0 with the coarse part
+    k_pcg_init_finalize<<<1, 32, 0, s>>>(w.scal, rzrr, w.status, rtol * rtol);
+    launch_direction<N, true>(c, rzrr);                                                      // p0 = z0
+    c->launches += 3;
+    MFEM_CUDA(cudaGetLastError());
 
-    // The iteration is captured once into a CUDA graph of kBatch iterations; kernels turn
-    // into no-ops as soon as the device-side state leaves "running", so the host only polls
-    // the 2-int status between graph launches.  (Multi-GPU: direct launches; the NCCL calls sit
-    // on the same stream between the kernels.)
-    const int kBatch = 25;
+    // The iteration is captured once into a CUDA graph of kBatch iterations; kernels turn into no-ops as soon as the
+    // device-side state leaves "running", so the host only polls the 2-int status between graph launches.  The NCCL
+    // calls of a multi-rank iteration (grouped send/recv of the interface, two all-reduces) are captured with it.
+    const int kBatch = multi ? 10 : 25;
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
-    if (c->opt_graph && !multi) {
+    int64_t launchesPerBatch = 0;
+    if (c->opt_graph) {
         const int64_t launchesBefore = c->launches;
-        MFEM_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        MFEM_CUDA(cudaStreamBeginCapture(s, multi ? cudaStreamCaptureModeRelaxed : cudaStreamCaptureModeThreadLocal));
         for (int k = 0; k < kBatch; ++k) enqueue_iteration<N>(c);
         MFEM_CUDA(cudaStreamEndCapture(s, &graph));
         MFEM_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+        launchesPerBatch = c->launches - launchesBefore;
         c->launches = launchesBefore;      // capture does not launch
     }
     int hst[2] = {0, 0};
@@ -1361,7 +1394,7 @@ static void pcg_impl(mfem_b200_ctx *c, const double *f_int, double *u_int, doubl
     while (done < maxIters) {
         if (exec) {
             MFEM_CUDA(cudaGraphLaunch(exec, s));
-            c->launches += (c->coarse ? (c->coarse->indexed ? 7 : 6) : 3) * kBatch;
+            c->launches += launchesPerBatch;
         } else {
             for (int k = 0; k < kBatch; ++k) enqueue_iteration<N>(c);
         }
@@ -1409,6 +1442,68 @@ void pcg_solve(mfem_b200_ctx *c, const double *f_int, double *u_int, double rtol
     build_preconditioner(c);
     if (c->N == 3) pcg_impl<3>(c, f_int, u_int, rtol, maxIters, info);
     else pcg_impl<2>(c, f_int, u_int, rtol, maxIters, info);
+}
+
+// z = M^-1 r and r.z for the preconditioner the next solve would use (block-Jacobi [+ level 1 + dense level]); r is
+// masked on the fixed variables first.  Runs the PCG's own start-up kernels, so what is returned is exactly the operator
+// inside the iteration.  Testing / diagnostics entry (mfem_b200_apply_preconditioner).
+void apply_preconditioner(mfem_b200_ctx *c, const double *r_int, double *z_int, double *rz) {
+    MFEM_REQUIRE(c->valuesValid, MFEM_B200_ERR_INVALID, "apply_preconditioner: matrix not assembled");
+    ensure_work(c);
+    build_preconditioner(c);
+    PcgWork &w = c->work;
+    cudaStream_t s = c->stream;
+    const int64_t nb = c->nDofs;
+    const uint8_t *owned = c->nRanks > 1 ? halo_owned(c) : nullptr;
+    CoarseSpace *cs = c->coarse;
+    if (cs) MFEM_CUDA(cudaMemsetAsync(cs->c1, 0, cs->c1.bytes(), s));
+    MFEM_CUDA(cudaMemsetAsync(w.red, 0, w.red.bytes(), s));
+    const double *rzrr = nullptr;
+    if (c->N == 3) {
+        k_pcg_update<3, true><<<vec_grid(c, nb), kVecThreads, 0, s>>>(nb, r_int, c->fixedMask, c->Minv, owned, nullptr, nullptr, w.x, w.r, w.z,
+                                                                       w.partials, w.ticket + 1, w.scal, w.red, nullptr,
+                                                                       cs ? cs->agg1.p : nullptr, cs ? cs->Y1.p : nullptr, cs ? cs->c1.p : nullptr);
+        rzrr = enqueue_precond_tail<3>(c, nullptr);
+        launch_direction<3, true>(c, rzrr);
+    } else {
+        k_pcg_update<2, true><<<vec_grid(c, nb), kVecThreads, 0, s>>>(nb, r_int, c->fixedMask, c->Minv, owned, nullptr, nullptr, w.x, w.r, w.z,
+                                                                       w.partials, w.ticket + 1, w.scal, w.red, nullptr,
+                                                                       cs ? cs->agg1.p : nullptr, cs ? cs->Y1.p : nullptr, cs ? cs->c1.p : nullptr);
+        rzrr = enqueue_precond_tail<2>(c, nullptr);
+        launch_direction<2, true>(c, rzrr);
+    }
+    c->launches++;
+    MFEM_CUDA(cudaMemcpyAsync(z_int, w.p, sizeof(double) * c->nvar(), cudaMemcpyDeviceToDevice, s));
+    MFEM_CUDA(cudaMemcpyAsync(rz, rzrr, sizeof(double), cudaMemcpyDeviceToHost, s));
+    MFEM_CUDA(cudaStreamSynchronize(s));
+    MFEM_CUDA(cudaGetLastError());
+}
+
+// diagnostics: copy a named array of the coarse space to the host as doubles (internal DoF order); returns its length
+int64_t get_coarse_array(mfem_b200_ctx *c, const std::string &name, double *out, int64_t capacity) {
+    MFEM_REQUIRE(c->coarse, MFEM_B200_ERR_INVALID, "no coarse space (solve or apply_preconditioner first)");
+    CoarseSpace &cs = *c->coarse;
+    std::vector<double> h;
+    auto fromD = [&](const DevBuf<double> &b) { h.resize(b.n); if (b.n) MFEM_CUDA(cudaMemcpy(h.data(), b.p, b.bytes(), cudaMemcpyDeviceToHost)); };
+    if (name == "agg1") {
+        std::vector<int32_t> t(cs.agg1.n);
+        if (cs.agg1.n) MFEM_CUDA(cudaMemcpy(t.data(), cs.agg1.p, cs.agg1.bytes(), cudaMemcpyDeviceToHost));
+        h.assign(t.begin(), t.end());
+    } else if (name == "int2ext") {
+        std::vector<int32_t> t(c->int2ext.n);
+        if (c->int2ext.n) MFEM_CUDA(cudaMemcpy(t.data(), c->int2ext.p, c->int2ext.bytes(), cudaMemcpyDeviceToHost));
+        h.assign(t.begin(), t.end());
+    } else if (name == "Y1") fromD(cs.Y1);
+    else if (name == "shift") fromD(cs.shift);
+    else if (name == "B1inv") fromD(cs.B1inv);
+    else if (name == "D1") fromD(cs.D1);
+    else if (name == "Einv") fromD(cs.Einv);
+    else if (name == "y1") fromD(cs.y1);
+    else if (name == "y2") fromD(cs.y2);
+    else if (name == "sizes") h = {(double)cs.S1, (double)cs.S2, (double)cs.R, (double)cs.n1, (double)cs.aggBase, cs.level1 ? 1.0 : 0.0};
+    else throw CudaError(MFEM_B200_ERR_INVALID, "unknown coarse array " + name);
+    if (out) std::copy(h.begin(), h.begin() + std::min<int64_t>((int64_t)h.size(), capacity), out);
+    return (int64_t)h.size();
 }
 
 #include "solver_multi.inl"

@@ -135,5 +135,17 @@ def test_homogenize_and_probe(pymods, deg):
     wo = orc.solve_orthotropic_cell_problems(sim)
     for i in range(6):
         assert rel_l2(ho.w_ij[i], wo[i]) < 1e-6
-    with pytest.raises(RuntimeError, match="manualPeriodicVerticesFile"):
-        ph.homogenize(V, T, C.D, degree=deg, manualPeriodicVerticesFile="x.txt")
+    # identified node pairs from a file (PeriodicCondition(mesh, pcFile), BoundaryConditions.hh:563-610): the pairs the
+    # matcher finds, written out, reproduce the matcher's tensor; a missing file raises the reference's message
+    import tempfile
+    dof = np.asarray(orc.periodic_condition(m)[0])
+    order = np.argsort(dof, kind="stable")
+    same = dof[order][1:] == dof[order][:-1]
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "pairs.txt")
+        with open(path, "w") as fh:
+            fh.write("".join(f"{a} {b}\n" for a, b in zip(order[:-1][same], order[1:][same])))
+        hm = ph.homogenize(V, T, C.D, degree=deg, manualPeriodicVerticesFile=path, rtol=1e-12)
+    assert np.abs(hm.Ch - gold[f"Eh_deg{deg}"]).max() < 1e-7 * np.abs(hm.Ch).max()
+    with pytest.raises(RuntimeError, match="Couldn't open"):
+        ph.homogenize(V, T, C.D, degree=deg, manualPeriodicVerticesFile="/nonexistent/x.txt")

@@ -18,9 +18,9 @@ def mfem(lib_built):
     return meshfem_b200
 
 
-@pytest.mark.parametrize("shape", [0, 1])       # 0: near-cubic boxes (default; emulated ratios 0.21 / 0.35 / 0.19), 1: runs of the internal order
+@pytest.mark.parametrize("fine", [0, 24])       # 0: large boxes only (two-level; emulated ratios 0.21 / 0.35 / 0.19), 24: + level 1
 @pytest.mark.parametrize("N,deg,sizes,aggregates", [(3, 2, (20, 4, 4), 128), (3, 1, (24, 6, 6), 64), (2, 2, (40, 8), 96)])
-def test_two_level_pcg_matches_direct_solve_with_fewer_iterations(mfem, N, deg, sizes, aggregates, shape):
+def test_two_level_pcg_matches_direct_solve_with_fewer_iterations(mfem, N, deg, sizes, aggregates, fine):
     sim, fixed, vals, f = cantilever_problem(N, deg, sizes)
     u_ref = sim.solve(f)
     with mfem.Handle(0) as h:
@@ -29,7 +29,7 @@ def test_two_level_pcg_matches_direct_solve_with_fewer_iterations(mfem, N, deg, 
         h.assemble()
         h.fix_variables(fixed, vals)
         u0, info0 = h.solve(f, rtol=1e-10, return_info=True)
-        h.set_option("coarse_shape", shape)
+        h.set_option("coarse_fine_nodes", fine)
         h.set_option("coarse_aggregates", aggregates)
         u1, info1 = h.solve(f, rtol=1e-10, return_info=True)
         u2, info2 = h.solve(2.0 * f, rtol=1e-10, return_info=True)          # coarse space reused

@@ -177,6 +177,43 @@ def run(sizes, deg, nodes_per_small, S2, rtol=1e-8, boxes=False):
         cost = 1.0 + k * nnzb1 * 36 / (bs.indices.size * 9)
         print(f"   level 1 by Chebyshev degree {k} (lmax {lmax:.2f}, ratio {ratio:.0f}): {itc} outer iterations x {cost:.2f} fine-SpMV "
               f"equivalents = {itc * cost:.0f}  (block-Jacobi {it0}, two-level {it2}, additive three-level {it3})", flush=True)
+    # level 1-2 V-cycle as the level-1 solver: k damped block-Jacobi (Chebyshev in B1^-1 K1) pre-smoothing steps, exact
+    # dense correction of the level-1 residual, k post-smoothing steps (symmetric => a fixed SPD operator); cost per
+    # outer iteration: 1 fine SpMV + (2k [+1 residual]) SpMVs with K1 + ONE dense GEMV (what the additive method has too)
+    B1 = lambda c: np.einsum("bij,bj->bi", B1inv, c.reshape(-1, 6)).reshape(-1) * live
+    v = rng.standard_normal(6 * S1) * live
+    for _ in range(30):
+        w = B1(K1 @ v); lb = np.linalg.norm(w) / np.linalg.norm(v); v = w / np.linalg.norm(w)
+    lb *= 1.1
+    def cheb_smooth(c, y, k, lmax, ratio):
+        # k Chebyshev steps on K1 y = c preconditioned by B1, eigenvalue window [lmax/ratio, lmax], from the iterate y
+        lmin = lmax / ratio
+        theta, delta = 0.5 * (lmax + lmin), 0.5 * (lmax - lmin)
+        r = c - K1 @ y if y.any() else c.copy()
+        sigma = theta / delta; rho = 1.0 / sigma
+        d = B1(r) / theta
+        for i in range(k):
+            y = y + d
+            if i + 1 < k:
+                r = r - K1 @ d
+                rho_new = 1.0 / (2.0 * sigma - rho)
+                d = rho_new * rho * d + (2.0 * rho_new / delta) * B1(r)
+                rho = rho_new
+        return y
+    for k, ratio in ((1, 4.0), (2, 6.0), (3, 10.0)):
+        def vcycle(c, k=k, ratio=ratio):
+            c = c * live
+            y = cheb_smooth(c, np.zeros_like(c), k, lb, ratio)
+            r = c - K1 @ y
+            y = y + P2 @ (E3inv @ (P2.T @ r))
+            # post-smoothing = the adjoint of the pre-smoothing: run the same polynomial on the new residual
+            r = c - K1 @ y
+            y = y + cheb_smooth(r, np.zeros_like(c), k, lb, ratio)
+            return y * live
+        _, itv = pcg(Kff, b, lambda r: jac(r) + Z1 @ vcycle(Z1.T @ r), rtol, 20000)
+        nk1 = 2 * k + 2 * (k - 1)      # K1 products: residual before the dense level, residual before post-smoothing, k-1 inside each smoother
+        cost = 1.0 + nk1 * nnzb1 * 36 / (bs.indices.size * 9)
+        print(f"   level 1-2 V-cycle, {k} Chebyshev(B1) pre/post steps (lmax {lb:.2f}, ratio {ratio:.0f}): {itv} outer iterations x {cost:.2f} = {itv * cost:.0f}", flush=True)
     # the same with the level-1 term alone (no dense level): how much each level buys
     _, it1 = pcg(Kff, b, lambda r: jac(r) + Z1 @ np.einsum("bij,bj->bi", B1inv, (Z1.T @ r).reshape(-1, 6)).reshape(-1), rtol, 20000)
     print(f"   block-Jacobi + level-1 block-Jacobi only: {it1} iterations", flush=True)
