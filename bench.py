@@ -6,11 +6,13 @@ cantilever of the named size (default: config 5, 220x44x44 hexes -> 10,222,080 q
 tets, 43.96M DoF, isotropic E=200 nu=0.35, examples/cantilever/cantilever.bc), with the PCG
 iteration rate and the SpMV roofline beside it.
 
-One "step" = one numeric assembly of K into the cached block-CSR pattern + one block-Jacobi
-PCG solve to rtol on ||r||/||b||.  `value` times steps with all inputs resident in HBM (CUDA
-events on the library's stream); `e2e` times the same work through the C ABI from HOST
-buffers on a fresh handle (mesh upload, symbolic phase, assembly, constraints, solve, result
-download all inside the timed region).
+One "step" = one numeric assembly of K into the cached block-CSR pattern + the set-up of the
+preconditioner for the new values (block-Jacobi blocks, coarse matrices) + one PCG solve to rtol
+on ||r||/||b||.  `value` times steps with all inputs resident in HBM (CUDA events on the
+library's stream, max over ranks); `e2e` times the same work through the C ABI from HOST buffers
+on a fresh handle (mesh upload, symbolic phase, assembly, constraints, solve, result download all
+inside the timed region).  N GPUs (torchrun, one process per GPU): x-slabs of elements, the
+library's own NCCL communicator for the interface exchange and the all-reduces.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--config cfg5|cfg3|cfg2|GRID:DEG:MAT]
   python bench.py --impl reference ...     # the reference algorithm on the host cores (oracle port)
@@ -35,7 +37,12 @@ import numpy as np  # noqa: E402
 METRIC = "assembly+solve throughput (elements/s), quadratic-tet elasticity cantilever"
 UNIT = "elements/s"
 RTOL = 1e-8
-CPU_SAMPLE_GRID = (60, 12, 12)     # 207,360 quadratic tets: ~10-25 s of CPU work per sample
+# bounded CPU samples of the workload (same cross-section ratio 5:1:1, same material / BCs), with the seconds one
+# assemble+solve took on the 16 host threads of the round-1 GPU box: the reference arm picks the largest one
+# that keeps `steps + warmup` samples within its time budget
+CPU_SAMPLE_GRIDS = [((72, 14, 14), 40.0), ((60, 12, 12), 21.0), ((50, 10, 10), 10.0), ((40, 8, 8), 4.2), ((30, 6, 6), 1.4)]
+CPU_ARM_BUDGET_S = 240.0
+DIRECT_GRID = (24, 5, 5)          # direct-solver leg: 14,400 quadratic tets, 67,767 DoF (SuperLU needs ~8 s on one core)
 
 
 def parse_config(s):
@@ -133,7 +140,7 @@ def pinned_copy(a):
 
 
 # ---------------------------------------------------------------------------------------------
-def cpu_port_sample(deg, mat, rtol, threads=None):
+def cpu_port_sample(grid, deg, mat, rtol, threads=None):
     """The reference algorithm on the host cores, on a bounded sample of the workload:
     perElementStiffness loop nest + serial triplet scatter + sumRepeated (oracle/ref_cpu.cc,
     following LinearElasticity.hh:165-232, 1408-1466 and SparseMatrices.hh:280-374), then a
@@ -141,54 +148,90 @@ def cpu_port_sample(deg, mat, rtol, threads=None):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import ref_cpu
     import workloads as wl
-    m = wl.grid_femmesh(CPU_SAMPLE_GRID, deg)
+    m = wl.grid_femmesh(grid, deg)
     D = wl.material(mat)
     fixed, vals, f = wl.cantilever_inputs(m)
     threads = threads or os.cpu_count() or 1
-    t0 = time.perf_counter()
     A, t_asm = ref_cpu.assemble_upper_csc(3, deg, m.nodes, m.elem_nodes, D, threads=threads)
-    t1 = time.perf_counter()
     u, info = ref_cpu.solve_fixed_pcg(3, A, f, fixed, vals, rtol=rtol, threads=threads)
     t_assemble = t_asm["ke"] + t_asm["scatter"] + t_asm["compress"]
     total = t_assemble + info["seconds"]
     return {
         "value": m.num_elements / total, "unit": UNIT, "cores": threads, "kind": "port",
-        "sample": (f"grid {'x'.join(map(str, CPU_SAMPLE_GRID))} -t, degree {deg}, {m.num_elements} elements, same material/BCs; "
+        "sample": (f"grid {'x'.join(map(str, grid))} -t, degree {deg}, {m.num_elements} elements, same material/BCs; "
                    f"assembly {t_assemble:.2f}s (Ke {t_asm['ke']:.2f} + serial scatter {t_asm['scatter']:.2f} + compress "
                    f"{t_asm['compress']:.2f}), block-Jacobi PCG {info['iters']} it in {info['seconds']:.2f}s "
                    f"(CHOLMOD stand-in; smaller mesh => fewer iterations than the full workload, i.e. favourable to the CPU)"),
         "seconds": total, "elements": m.num_elements, "pcg_iterations": info["iters"],
+        "assembly_seconds": t_assemble, "solve_seconds": info["seconds"],
     }
 
 
-def two_level_trial(cfg, device, expect_min_uy, aggregates=2048, timeout_s=150):
-    """Extra, NOT the headline: the optional two-level preconditioner (coarse_aggregates; csrc/coarse.inl, DESIGN.md
-    section 8 item 0) on the same workload, in a subprocess with a timeout so that nothing it does can touch the
-    numbers above.  Returns the subprocess's JSON (validated there against the block-Jacobi tip deflection and the
-    true residual) or {"error": ...}.  Box aggregates first (the default); if that run fails or does not validate, the
-    first version (runs of the internal numbering) is tried once and reported under "fallback_runs"."""
-    def one(shape, limit):
-        cmd = [sys.executable, os.path.join(ROOT, "tools", "two_level_trial.py"), "--config", cfg, "--aggregates", str(aggregates),
-               "--device", str(device), "--rtol", str(RTOL), "--shape", str(shape)]
-        if expect_min_uy is not None:
-            cmd += ["--expect-min-uy", repr(float(expect_min_uy))]
-        try:
-            r = subprocess.run(cmd, capture_output=True, text=True, timeout=limit, cwd=ROOT)
-            lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
-            if not lines:
-                return {"error": f"no output (exit {r.returncode}): {r.stderr[-300:]}"}
-            return json.loads(lines[-1])
-        except subprocess.TimeoutExpired:
-            return {"error": f"timed out after {limit}s"}
-        except Exception as e:  # noqa: BLE001
-            return {"error": f"{type(e).__name__}: {e}"[:300]}
-
-    out = one(0, timeout_s)
-    if "error" in out or not out.get("valid", False):
-        out["fallback_runs"] = one(1, 100)
-    out["note"] = ("experimental option, reported beside the block-Jacobi headline (the headline stays block-Jacobi until this "
-                   "path has been validated on hardware, on every GPU count)")
+def cpu_direct_sample(deg, mat):
+    """Direct-solver leg of the CPU baseline (the reference's solver class: SPSDSystem::solve -> CholmodFactorizer,
+    SparseMatrices.hh:2002-2024, 2106-2124) on a size where a direct factorisation finishes in seconds: reference-style
+    assembly (oracle/ref_cpu.cc) + sparse factorisation and solve of K_ff.  CHOLMOD is not available; the stand-ins are
+    cuSOLVER's HOST sparse Cholesky with METIS nested dissection (cusolverSpDcsrlsvcholHost, reorder = 3: a CPU routine,
+    the closest thing to CHOLMOD's NESDIS + Cholesky in this image) when libcusolver loads, and SuperLU (scipy splu,
+    MMD on A^T + A, symmetric mode) otherwise / besides.  One thread each."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ctypes
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    import ref_cpu
+    import workloads as wl
+    m = wl.grid_femmesh(DIRECT_GRID, deg)
+    D = wl.material(mat)
+    fixed, vals, f = wl.cantilever_inputs(m)
+    threads = os.cpu_count() or 1
+    A, t_asm = ref_cpu.assemble_upper_csc(3, deg, m.nodes, m.elem_nodes, D, threads=threads)
+    t_assemble = t_asm["ke"] + t_asm["scatter"] + t_asm["compress"]
+    K = (A + sp.triu(A, 1).T).tocsr()
+    n = K.shape[0]
+    free = np.ones(n, dtype=bool); free[np.asarray(fixed)] = False
+    Kff = K[free][:, free].tocsr(); Kff.sort_indices()
+    b = np.asarray(f, float).reshape(-1)[free].copy()
+    out = {"grid": "x".join(map(str, DIRECT_GRID)), "elements": int(m.num_elements), "dofs": int(Kff.shape[0]),
+           "assembly_seconds": round(t_assemble, 3), "legs": {}}
+    try:        # cuSOLVER host sparse Cholesky (CPU code path of libcusolver)
+        lib = ctypes.CDLL("libcusolver.so.11")
+        sparse = ctypes.CDLL("libcusparse.so.12")
+        h, descr = ctypes.c_void_p(), ctypes.c_void_p()
+        if lib.cusolverSpCreate(ctypes.byref(h)) != 0 or sparse.cusparseCreateMatDescr(ctypes.byref(descr)) != 0:
+            raise RuntimeError("cusolverSpCreate failed")
+        x = np.zeros_like(b); sing = ctypes.c_int(0)
+        ip, ix = Kff.indptr.astype(np.int32), Kff.indices.astype(np.int32)
+        t0 = time.perf_counter()
+        st = lib.cusolverSpDcsrlsvcholHost(h, ctypes.c_int(Kff.shape[0]), ctypes.c_int(Kff.nnz), descr,
+                                           Kff.data.ctypes.data_as(ctypes.c_void_p), ip.ctypes.data_as(ctypes.c_void_p),
+                                           ix.ctypes.data_as(ctypes.c_void_p), b.ctypes.data_as(ctypes.c_void_p),
+                                           ctypes.c_double(0.0), ctypes.c_int(3), x.ctypes.data_as(ctypes.c_void_p), ctypes.byref(sing))
+        dt = time.perf_counter() - t0
+        res = float(np.linalg.norm(Kff @ x - b) / np.linalg.norm(b))
+        if st != 0 or sing.value != -1 or not res < 1e-6:
+            raise RuntimeError(f"status {st}, singularity {sing.value}, residual {res:.1e}")
+        out["legs"]["cusolverSp host Cholesky (METIS nested dissection, 1 thread)"] = {
+            "factor_solve_seconds": round(dt, 3), "rel_residual": res, "elements_per_s": m.num_elements / (t_assemble + dt)}
+    except Exception as e:  # noqa: BLE001
+        out["legs"]["cusolverSp host Cholesky"] = {"unavailable": f"{type(e).__name__}: {e}"[:160]}
+    t0 = time.perf_counter()
+    lu = spla.splu(Kff.tocsc(), permc_spec="MMD_AT_PLUS_A", options=dict(SymmetricMode=True))
+    x = lu.solve(b)
+    dt = time.perf_counter() - t0
+    out["legs"]["SuperLU (scipy splu, MMD_AT_PLUS_A, symmetric mode, 1 thread)"] = {
+        "factor_solve_seconds": round(dt, 3), "rel_residual": float(np.linalg.norm(Kff @ x - b) / np.linalg.norm(b)),
+        "factor_nnz": int(lu.L.nnz + lu.U.nnz), "elements_per_s": m.num_elements / (t_assemble + dt)}
+    out["note"] = ("direct sparse factorisation as the reference does it, at a size where it takes seconds: cost grows like "
+                   "n^2 (3D fill), so at the PCG sample's size it would be ~100x slower than the PCG stand-in used for `value`")
     return out
+
+
+def cpu_sample_grid(n_samples):
+    per_step = min(60.0, CPU_ARM_BUDGET_S / max(n_samples, 1))
+    for grid, secs in CPU_SAMPLE_GRIDS:
+        if secs <= per_step:
+            return grid
+    return CPU_SAMPLE_GRIDS[-1][0]
 
 
 def run_reference(args):
@@ -196,31 +239,47 @@ def run_reference(args):
     if rank != 0:
         return
     name, grid, deg, mat = parse_config(args.config)
+    sgrid = cpu_sample_grid(args.steps + args.warmup) if deg == 2 else (50, 10, 10)
     samples = []
     for _ in range(args.warmup):
-        cpu_port_sample(deg, mat, RTOL)
+        cpu_port_sample(sgrid, deg, mat, RTOL)
     for _ in range(args.steps):
-        samples.append(cpu_port_sample(deg, mat, RTOL))
+        samples.append(cpu_port_sample(sgrid, deg, mat, RTOL))
     secs = sum(s["seconds"] for s in samples)
     elems = sum(s["elements"] for s in samples)
     value = elems / secs
     base = dict(samples[-1]); base["value"] = value
-    for k in ("seconds", "elements", "pcg_iterations"):
+    for k in ("seconds", "elements", "pcg_iterations", "assembly_seconds", "solve_seconds"):
         base.pop(k, None)
+    base["pcg"] = {"elements_per_s": value, "grid": "x".join(map(str, sgrid))}
+    if not args.no_direct:
+        base["direct"] = cpu_direct_sample(deg, mat)
+    sample_name = (f"{name} SAMPLE: grid {'x'.join(map(str, sgrid))} -t ({24 * sgrid[0] * sgrid[1] * sgrid[2]} "
+                   f"{'quadratic' if deg == 2 else 'linear'} tets), {mat} material, cantilever.bc")
     out = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(args.steps, 1), "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(name, grid, deg, mat), "rtol": RTOL,
-                   "note": "reference algorithm (oracle port) on host cores, bounded sample per step"},
+        "config": {"workload": sample_name, "full_workload": workload_name(name, grid, deg, mat), "rtol": RTOL,
+                   "same_config": False,
+                   "note": ("reference algorithm (oracle port: perElementStiffness loop nest, serial triplet scatter, sumRepeated; "
+                            "block-Jacobi PCG standing in for CHOLMOD) on the host cores.  The full workload needs ~295 GB of "
+                            "triplets and hours on this host, so every step runs a bounded SAMPLE of it (the grid named in "
+                            "`workload`); throughput in elements/s on the smaller mesh flatters the CPU (fewer PCG iterations).")},
         "cpu_baseline": base,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(out), flush=True)
 
 
-def precond_name(aggregates):
-    return "block-Jacobi 3x3" if not aggregates else f"two-level: block-Jacobi 3x3 + {aggregates} rigid-mode aggregates (additive)"
+def precond_name(aggregates, fine):
+    if not aggregates:
+        return "block-Jacobi 3x3"
+    s = "multilevel aggregation: block-Jacobi 3x3 + "
+    if fine:
+        s += f"level-1 rigid modes of ~{fine}-node boxes (6x6 block solves) + "
+    s += ("dense level of rigid modes of " + (f"<= {aggregates}" if aggregates > 0 else "automatically many") + " large boxes (additive)")
+    return s
 
 
 def workload_name(name, grid, deg, mat):
@@ -230,144 +289,242 @@ def workload_name(name, grid, deg, mat):
 
 # ---------------------------------------------------------------------------------------------
 def run_ours(args):
-    import meshfem_b200
-    from meshfem_b200 import build as mb
-    import workloads as wl
-
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    dist = None
+    dist = device = None
     if world > 1:
         import torch
-        import torch.distributed as dist_mod
+        import torch.distributed as dist
         torch.cuda.set_device(local_rank)
-        dist_mod.init_process_group("nccl")
-        dist = dist_mod
-    mb.build_all()
+        dist.init_process_group("nccl")
+        device = torch.device("cuda", local_rank)
+    # one rank builds (a stale stamp would otherwise start N concurrent nvcc / g++ runs into the same files)
+    from meshfem_b200 import build as mb
+    if rank == 0:
+        mb.build_all()
+    if dist is not None:
+        dist.barrier()
+    import meshfem_b200
+    import workloads as wl
+    from multi_gpu import local_problem, make_handle, max_over_ranks, sum_over_ranks
+
+    def rmax(v):
+        return max_over_ranks(dist, v, device) if dist is not None else float(v)
+
+    def rsum(v):
+        return sum_over_ranks(dist, v, device) if dist is not None else float(v)
+
     name, grid, deg, mat = parse_config(args.config)
     hbm_peak, peak_src = peaks()
-
-    if world > 1:
-        from multi_gpu import run_multi_gpu   # tools/multi_gpu.py
-        return run_multi_gpu(args, dist, world, rank, local_rank, name, grid, deg, mat, hbm_peak, peak_src)
-
     t_gen = time.perf_counter()
     m = wl.grid_femmesh(grid, deg)
     D = wl.material(mat)
     fixed, vals, f = wl.cantilever_inputs(m)
+    n_elems, n_nodes, npe = m.num_elements, m.num_nodes, m.elem_nodes.shape[1]
+    if world > 1:
+        p, fixed, vals, f = local_problem(m, fixed, vals, f, world, rank)
+        nodes, elem_nodes = p.nodes, p.elem_nodes
+    else:
+        p, nodes, elem_nodes = None, m.nodes, m.elem_nodes
+    del m
     t_gen = time.perf_counter() - t_gen
-    nodes_p, _k1 = pinned_copy(m.nodes)
-    elems_p, _k2 = pinned_copy(m.elem_nodes)
-    f_p, _k3 = pinned_copy(f)
-    n_elems = m.num_elements
+    nodes_p, _k1 = pinned_copy(nodes)
+    elems_p, _k2 = pinned_copy(elem_nodes)
+    f_p, _k3 = pinned_copy(np.ascontiguousarray(f))
+    if p is not None:
+        p.nodes, p.elem_nodes = nodes_p, elems_p
+    opts = {"coarse_aggregates": args.coarse_aggregates, "coarse_fine_nodes": args.coarse_fine_nodes}
+
+    def new_handle(parent=None, **over):
+        o = dict(opts); o.update(over)
+        if world > 1:
+            return make_handle(meshfem_b200, dist, world, rank, local_rank, p, D, comm_parent=parent, **o)
+        hh = meshfem_b200.Handle(local_rank, **o)
+        hh.set_mesh(3, deg, nodes_p, elems_p)
+        hh.set_material(D)
+        return hh
 
     sampler = ClockSampler(local_rank)
     # ------------------------------------------------------------------ device-resident steps
-    opts = {"coarse_aggregates": args.coarse_aggregates} if args.coarse_aggregates else {}
-    h = meshfem_b200.Handle(local_rank, **opts)
-    h.set_mesh(3, deg, nodes_p, elems_p)
-    h.set_material(D)
+    h = new_handle()
     h.assemble()                      # symbolic phase (pattern + incidence lists) is cached from here on
     h.fix_variables(fixed, vals)
     nb, nnzb = h.bsr_sizes()
     pattern_s = h.timer("Pattern")
 
-    def step():
-        h.reset_timers()
-        h.assemble()
-        _, info = h.solve(f_p, rtol=RTOL, return_info=True)
-        coarse_s = max(0.0, h.timer("Coarse Space")) if args.coarse_aggregates else 0.0    # E = Z'KZ rebuilt per assembly: counted
-        return h.timer("Assemble System"), info[0]["seconds"] + coarse_s, info[0]["iterations"], info[0]["rel_residual"], \
-            h.launch_count()
+    def step(hh=None, rtol=RTOL):
+        hh = hh or h
+        hh.reset_timers()
+        hh.assemble()
+        u, info = hh.solve(f_p, rtol=rtol, return_info=True)
+        # block-Jacobi blocks + coarse matrices are rebuilt for the new values inside solve(): counted in the step
+        setup = max(0.0, hh.timer("Fix Variables")) + max(0.0, hh.timer("Coarse Space"))
+        return u, hh.timer("Assemble System"), setup, info[0]["seconds"], info[0]["iterations"], info[0]["rel_residual"], hh.launch_count()
 
     for _ in range(args.warmup):
         step()
-    sampler.start()
+    if dist is not None:
+        import torch
+        dist.barrier(); torch.cuda.synchronize()
+    if rank == 0:
+        sampler.start()
     wall0 = time.perf_counter()
-    asm_s, solve_s, iters, launches = 0.0, 0.0, 0, 0
-    relres = None
+    asm_s = setup_s = solve_s = 0.0
+    iters = 0
+    relres, u = None, None
+    launches = 0
     for _ in range(args.steps):
-        a, s, it, relres, nl = step()
-        asm_s += a; solve_s += s; iters += it; launches += nl
+        u, a, su, s, it, relres, nl = step()          # reset_timers() restarts the launch counter: nl is per step
+        asm_s += a; setup_s += su; solve_s += s; iters += it; launches += nl
+    if dist is not None:
+        torch.cuda.synchronize(); dist.barrier()
     wall = time.perf_counter() - wall0
-    # dominant kernel: the PCG SpMV, timed live on the library's stream (inputs: 31 GB matrix >> L2)
+    # dominant kernel: the PCG SpMV (the masked + fused-dot variant the iteration launches), timed live on the
+    # library's stream (inputs: the 31 GB matrix >> L2)
     spmv_s = h.time_spmv(20)
-    clocks = sampler.stop()
-    dev_s = asm_s + solve_s
-    value = args.steps * n_elems / dev_s
-    spmv_bytes = nnzb * 76 + nb * 52
-    roofline = {"bound": "hbm", "kernel": "k_bsr_spmv (PCG SpMV)", "achieved": spmv_bytes / spmv_s / 1e9,
-                "peak": hbm_peak, "unit": "GB/s", "frac": spmv_bytes / spmv_s / 1e9 / hbm_peak,
-                "traffic": measured_traffic(name, "k_bsr_spmv", nnzb),
-                "peak_source": peak_src, "algorithmic_bytes_per_launch": spmv_bytes,
-                "seconds_per_launch": spmv_s}
-    asm_bytes = nnzb * 72 + n_elems * (4 * m.elem_nodes.shape[1] + 96)
-    roofline["assembly"] = {"achieved": asm_bytes / (asm_s / args.steps) / 1e9, "unit": "GB/s",
-                            "frac": asm_bytes / (asm_s / args.steps) / 1e9 / hbm_peak,
-                            "algorithmic_bytes_per_launch": asm_bytes}
-    h.close()
+    clocks = sampler.stop() if rank == 0 else None
+    asm_max, setup_max, solve_max, spmv_max = rmax(asm_s), rmax(setup_s), rmax(solve_s), rmax(spmv_s)
+    nnzb_tot, nb_tot, launches_tot = rsum(nnzb), rsum(nb), rsum(launches)
+    dev_s = rmax(asm_s + setup_s + solve_s)
+    coarse_sizes = None
+    if args.coarse_aggregates:
+        try:
+            cz = h.coarse_array("sizes")
+            coarse_sizes = {"small_boxes_this_rank": int(cz[0]), "large_boxes": int(cz[1]), "small_per_large": int(cz[2])}
+        except Exception:
+            coarse_sizes = None
+
+    # ------------------------------------------------------------------ parity evidence at full size
+    parity = None
+    if not args.no_parity:
+        u = np.asarray(u).reshape(-1)
+        parity = {"rtol": RTOL}
+        # (1) a tighter solve with the same preconditioner: how far is the rtol answer from the converged one
+        u12, *_ = step(rtol=1e-12)
+        u12 = np.asarray(u12).reshape(-1)
+        num, den = rsum(float(np.sum((u - u12) ** 2))), rsum(float(np.sum(u12 ** 2)))
+        parity["rel_l2_rtol_1e-8_vs_1e-12"] = float(np.sqrt(num / den))
+        # (2) an independent preconditioner: block-Jacobi PCG on the same matrix, full vector
+        if args.coarse_aggregates and not args.no_bj_parity:
+            h.set_option("coarse_aggregates", 0)
+            ubj, info = h.solve(f_p, rtol=RTOL, return_info=True)
+            h.set_option("coarse_aggregates", args.coarse_aggregates)
+            ubj = np.asarray(ubj).reshape(-1)
+            num, den = rsum(float(np.sum((u - ubj) ** 2))), rsum(float(np.sum(ubj ** 2)))
+            parity["rel_l2_vs_block_jacobi_pcg"] = float(np.sqrt(num / den))
+            parity["block_jacobi_iterations"] = int(info[0]["iterations"])
+            parity["block_jacobi_solve_ms"] = 1e3 * rmax(info[0]["seconds"])
+        # (3) true residual of the returned vector through an INDEPENDENT code path: the matrix-free element-wise
+        #     K u (mfem_b200_apply_K = applyStiffnessMatrix, LinearElasticity.hh:801-823), free variables only
+        if world == 1:
+            Ku = np.asarray(h.apply_K(u.reshape(-1, 3))).reshape(-1)
+            free = np.ones(u.size, dtype=bool); free[np.asarray(fixed)] = False
+            fr = np.asarray(f_p).reshape(-1)
+            parity["true_rel_residual_elementwise_apply_K"] = float(np.linalg.norm((fr - Ku)[free]) / np.linalg.norm(fr[free]))
+        parity["min_uy"] = -rmax(-float(u.reshape(-1, 3)[:, 1].min()))
+    h_keep = h if world > 1 else None          # N ranks: the e2e handles borrow this one's NCCL communicator
+    if world == 1:
+        h.close()
 
     # ------------------------------------------------------------------ end-to-end steps (host buffers)
     def e2e_step():
+        if dist is not None:
+            dist.barrier()
         t0 = time.perf_counter()
-        with meshfem_b200.Handle(local_rank, **opts) as hh:
-            hh.set_mesh(3, deg, nodes_p, elems_p)
-            hh.set_material(D)
-            hh.assemble()
-            hh.fix_variables(fixed, vals)
-            u = hh.solve(f_p, rtol=RTOL)
-            tip = float(u.reshape(-1, 3)[:, 1].min())
-        return time.perf_counter() - t0, tip
-
-    n_e2e = 1          # one warm-up + one timed end-to-end pass (each is a full solve from host buffers)
-    e2e_step() if args.warmup > 0 else None
-    e2e_s, tip = 0.0, None
+        hh = new_handle(parent=h_keep)
+        t1 = time.perf_counter()
+        hh.assemble()
+        t2 = time.perf_counter()
+        hh.fix_variables(fixed, vals)
+        uu, info = hh.solve(f_p, rtol=RTOL, return_info=True)
+        t3 = time.perf_counter()
+        tip = float(uu.reshape(-1, 3)[:, 1].min())
+        parts = {"create_upload_reorder_s": t1 - t0, "symbolic_pattern_s": hh.timer("Pattern"),
+                 "assemble_call_s": t2 - t1, "numeric_assembly_s": hh.timer("Assemble System"),
+                 "preconditioner_setup_s": max(0.0, hh.timer("Fix Variables")) + max(0.0, hh.timer("Coarse Space")),
+                 "pcg_s": info[0]["seconds"], "fix_solve_download_call_s": t3 - t2}
+        hh.close()
+        if dist is not None:
+            torch.cuda.synchronize(); dist.barrier()
+        return time.perf_counter() - t0, tip, parts
+    if args.warmup > 0:
+        e2e_step()
+    n_e2e = 2 if args.steps >= 2 else 1
+    e2e_s, tip, parts = 0.0, None, None
     for _ in range(n_e2e):
-        s, tip = e2e_step()
+        s, tip, parts = e2e_step()
         e2e_s += s
-    h2d = nodes_p.nbytes + elems_p.nbytes + f_p.nbytes + fixed.nbytes + vals.nbytes
-    d2h = f_p.nbytes
-    e2e = {"value": n_e2e * n_elems / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-           "seconds_per_step": e2e_s / n_e2e, "steps": n_e2e, "min_uy": tip,
-           "includes": "handle creation, mesh upload, DoF reordering, symbolic pattern, assembly, constraints, PCG, result download"}
+    e2e_max = rmax(e2e_s)
+    tip_min = -rmax(-tip)
+    h2d = rsum(nodes_p.nbytes + elems_p.nbytes + f_p.nbytes + np.asarray(fixed).nbytes + np.asarray(vals).nbytes)
+    d2h = rsum(f_p.nbytes)
+    parts = {k: rmax(v) for k, v in parts.items()}
+    if h_keep is not None:
+        h_keep.close()
 
-    two_level = two_level_trial(name, local_rank, tip) if not (args.no_two_level_trial or args.coarse_aggregates) else None
-    cpu = cpu_port_sample(deg, mat, RTOL) if not args.no_cpu_baseline else None
-    if cpu:
-        for k in ("seconds", "elements", "pcg_iterations"):
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_port_sample((60, 12, 12) if deg == 2 else (50, 10, 10), deg, mat, RTOL)
+        cpu["pcg"] = {"elements_per_s": cpu["value"], "assembly_seconds": cpu["assembly_seconds"], "solve_seconds": cpu["solve_seconds"],
+                      "iterations": cpu["pcg_iterations"]}
+        for k in ("seconds", "elements", "pcg_iterations", "assembly_seconds", "solve_seconds"):
             cpu.pop(k, None)
+        if not args.no_direct:
+            cpu["direct"] = cpu_direct_sample(deg, mat)
 
-    out = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(name, grid, deg, mat), "elements": n_elems, "nodes": m.num_nodes,
-                   "dofs": 3 * m.num_nodes, "nnz_blocks": nnzb, "rtol": RTOL, "preconditioner": precond_name(args.coarse_aggregates),
-                   "l2_policy": "inputs larger than L2 (matrix %.1f GB)" % (nnzb * 76 / 1e9)},
-        "assembly_elements_per_s": args.steps * n_elems / asm_s,
-        "pcg_iters_per_s": iters / solve_s, "pcg_iterations_per_solve": iters / args.steps,
-        "pcg_rel_residual": relres, "assembly_ms": 1e3 * asm_s / args.steps, "solve_ms": 1e3 * solve_s / args.steps,
-        "symbolic_pattern_ms": 1e3 * pattern_s, "wall_ms_per_step": 1e3 * wall / args.steps,
-        "mesh_generation_s": t_gen,
-        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-        "two_level_trial": two_level,
-    }
-    print(json.dumps(out), flush=True)
+    if rank == 0:
+        spmv_bytes = nnzb_tot * 76 + nb_tot * 52           # whole-job algorithmic bytes of one (distributed) SpMV
+        asm_bytes = nnzb_tot * 72 + n_elems * (4 * npe + 96)
+        roofline = {"bound": "hbm", "kernel": "k_bsr_spmv<3,32,masked,dot> (the PCG's SpMV" + (", per-rank local part, max over ranks)" if world > 1 else ")"),
+                    "achieved": spmv_bytes / spmv_max / 1e9, "peak": hbm_peak * world, "unit": "GB/s",
+                    "frac": spmv_bytes / spmv_max / 1e9 / (hbm_peak * world),
+                    "traffic": measured_traffic(name, "k_bsr_spmv", nnzb) if world == 1 else None,
+                    "peak_source": peak_src, "algorithmic_bytes_per_launch": spmv_bytes, "seconds_per_launch": spmv_max,
+                    "assembly": {"achieved": asm_bytes / (asm_max / args.steps) / 1e9, "unit": "GB/s",
+                                 "frac": asm_bytes / (asm_max / args.steps) / 1e9 / (hbm_peak * world),
+                                 "algorithmic_bytes_per_launch": asm_bytes}}
+        cfg = {"workload": workload_name(name, grid, deg, mat), "elements": n_elems, "nodes": n_nodes, "dofs": 3 * n_nodes,
+               "nnz_blocks": int(nnzb_tot), "rtol": RTOL, "preconditioner": precond_name(args.coarse_aggregates, args.coarse_fine_nodes),
+               "coarse_space": coarse_sizes, "l2_policy": "inputs larger than L2 (matrix %.1f GB)" % (nnzb_tot * 76 / 1e9 / world)}
+        if world > 1:
+            cfg["partition"] = f"{world} x-slabs of elements, shared interface DoFs, NCCL send/recv sum-exchange + 2 all-reduces per iteration"
+        out = {
+            "metric": METRIC, "value": args.steps * n_elems / dev_s, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+            "assembly_elements_per_s": args.steps * n_elems / asm_max,
+            "pcg_iters_per_s": iters / solve_max, "pcg_iterations_per_solve": iters / args.steps,
+            "pcg_rel_residual": relres, "assembly_ms": 1e3 * asm_max / args.steps,
+            "preconditioner_setup_ms": 1e3 * setup_max / args.steps, "solve_ms": 1e3 * solve_max / args.steps,
+            "symbolic_pattern_ms": 1e3 * pattern_s, "wall_ms_per_step": 1e3 * wall / args.steps, "mesh_generation_s": t_gen,
+            "roofline": roofline, "cpu_baseline": cpu,
+            "e2e": {"value": n_e2e * n_elems / e2e_max, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "seconds_per_step": e2e_max / n_e2e, "steps": n_e2e, "min_uy": tip_min, "breakdown_last_step": parts,
+                    "includes": "handle creation, mesh upload, DoF reordering, symbolic pattern, assembly, constraints, "
+                                "preconditioner set-up, PCG, result download"},
+            "parity": parity, "gpu_launches": int(launches_tot), "clocks": clocks,
+        }
+        print(json.dumps(out), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="cfg5")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-two-level-trial", action="store_true")
-    ap.add_argument("--coarse-aggregates", type=int, default=0,
-                    help="aggregates of the optional two-level preconditioner for EVERY solve of the run (default 0 = "
-                         "block-Jacobi only, the validated configuration; the preconditioner is named in config)")
+    ap.add_argument("--no-direct", action="store_true", help="skip the direct-solver leg of the CPU baseline")
+    ap.add_argument("--no-parity", action="store_true", help="skip the full-size parity evidence (two extra solves)")
+    ap.add_argument("--no-bj-parity", action="store_true", help="skip the block-Jacobi cross-check (48 s on one GPU for cfg5)")
+    ap.add_argument("--coarse-aggregates", type=int, default=2048,
+                    help="large aggregates of the multilevel preconditioner (0 = block-Jacobi only, -1 = automatic)")
+    ap.add_argument("--coarse-fine-nodes", type=int, default=64, help="nodes per small (level-1) aggregate, 0 = none")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -174,6 +174,10 @@ int mfem_b200_get_volumes(mfem_b200_handle h, double *vol);
  * "Pattern", "Assemble System", "Elasticity Solve", "SpMV".  Returns -1.0 if unknown.  */
 double mfem_b200_get_timer(mfem_b200_handle h, const char *section);
 int mfem_b200_reset_timers(mfem_b200_handle h);
+/* Device memory of destroyed handles is kept in a process-wide cache and reused by later handles (cudaMalloc / cudaFree
+ * of multi-GB arrays cost hundreds of milliseconds).  This call returns the cached blocks to the driver; the environment
+ * variable MFEM_B200_POOL=0 disables caching altogether.                                                            */
+int mfem_b200_release_cached_memory(void);
 /* number of kernel launches issued by this handle since creation / last reset          */
 int64_t mfem_b200_launch_count(mfem_b200_handle h);
 

@@ -25,7 +25,7 @@ SYMBOLS = [
     "mfem_b200_solve", "mfem_b200_apply_K", "mfem_b200_spmv", "mfem_b200_const_strain_load",
     "mfem_b200_avg_strain_stress", "mfem_b200_get_volumes", "mfem_b200_get_timer", "mfem_b200_reset_timers",
     "mfem_b200_launch_count", "mfem_b200_time_spmv", "mfem_b200_set_matrix_triplets", "mfem_b200_comm_share",
-    "mfem_b200_apply_preconditioner", "mfem_b200_get_coarse_array",
+    "mfem_b200_apply_preconditioner", "mfem_b200_get_coarse_array", "mfem_b200_release_cached_memory",
 ]
 
 STATUS_NAMES = {

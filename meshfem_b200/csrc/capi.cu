@@ -29,6 +29,100 @@ void comm_destroy(mfem_b200_ctx *c);   // comm.cu
 
 static thread_local std::string g_createError;
 
+// ---------------------------------------------------------------------------------------------------------
+// caching pool behind DevBuf (core.cuh)
+#include <mutex>
+#include <unordered_map>
+namespace mfem {
+namespace {
+struct PoolBlock { void *p; size_t bytes; int device; };
+std::mutex g_poolMutex;
+std::vector<PoolBlock> g_poolFree;                              // cached blocks
+std::unordered_map<void *, PoolBlock> g_poolLive;               // blocks handed out
+bool pool_enabled() {
+    static const bool on = [] { const char *e = getenv("MFEM_B200_POOL"); return !(e && e[0] == '0'); }();
+    return on;
+}
+void pool_release_locked(int device /* -1: all */) {
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (size_t k = 0; k < g_poolFree.size();) {
+        if (device < 0 || g_poolFree[k].device == device) {
+            cudaSetDevice(g_poolFree[k].device);
+            cudaFree(g_poolFree[k].p);
+            g_poolFree[k] = g_poolFree.back();
+            g_poolFree.pop_back();
+        } else ++k;
+    }
+    cudaSetDevice(cur);
+}
+}  // namespace
+
+void *pool_alloc(size_t bytes) {
+    int dev = 0;
+    MFEM_CUDA(cudaGetDevice(&dev));
+    const size_t want = (bytes + 511) & ~size_t(511);
+    std::lock_guard<std::mutex> lock(g_poolMutex);
+    if (pool_enabled()) {
+        // best fit among the cached blocks of this device: at least `want`, at most 12.5 % + 1 MiB larger
+        size_t best = g_poolFree.size();
+        for (size_t k = 0; k < g_poolFree.size(); ++k) {
+            const PoolBlock &b = g_poolFree[k];
+            if (b.device != dev || b.bytes < want || b.bytes > want + want / 8 + (1u << 20)) continue;
+            if (best == g_poolFree.size() || b.bytes < g_poolFree[best].bytes) best = k;
+        }
+        if (best != g_poolFree.size()) {
+            PoolBlock b = g_poolFree[best];
+            g_poolFree[best] = g_poolFree.back();
+            g_poolFree.pop_back();
+            g_poolLive[b.p] = b;
+            return b.p;
+        }
+    }
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {                      // out of memory: give the cached blocks back and try once more
+        cudaGetLastError();
+        pool_release_locked(dev);
+        e = cudaMalloc(&p, want);
+    }
+    if (e != cudaSuccess)
+        throw CudaError(MFEM_B200_ERR_CUDA, std::string("cudaMalloc of ") + std::to_string(want) + " bytes failed: " + cudaGetErrorString(e));
+    g_poolLive[p] = PoolBlock{p, want, dev};
+    return p;
+}
+
+void pool_free(void *p) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lock(g_poolMutex);
+    auto it = g_poolLive.find(p);
+    if (it == g_poolLive.end()) { cudaFree(p); return; }
+    PoolBlock b = it->second;
+    g_poolLive.erase(it);
+    if (pool_enabled()) {
+        // cudaFree synchronises the device, and code that drops a temporary while its last kernel is still in flight
+        // relies on that; keep the guarantee (a block may be handed to a handle on another stream next)
+        int cur = 0;
+        cudaGetDevice(&cur);
+        if (cur != b.device) cudaSetDevice(b.device);
+        cudaDeviceSynchronize();
+        if (cur != b.device) cudaSetDevice(cur);
+        g_poolFree.push_back(b);
+    } else {
+        int cur = 0;
+        cudaGetDevice(&cur);
+        if (cur != b.device) cudaSetDevice(b.device);
+        cudaFree(b.p);
+        if (cur != b.device) cudaSetDevice(cur);
+    }
+}
+
+void pool_release_all() {
+    std::lock_guard<std::mutex> lock(g_poolMutex);
+    pool_release_locked(-1);
+}
+}  // namespace mfem
+
 extern "C" {
 
 int mfem_b200_device_count(void) {
@@ -101,7 +195,7 @@ int mfem_b200_set_option(mfem_b200_handle h, const char *name, int64_t value) {
     } else if (n == "graph") {
         h->opt_graph = value != 0;
     } else if (n == "spmv_kernel") {
-        MFEM_REQUIRE(value >= 0 && value <= 4, MFEM_B200_ERR_INVALID, "spmv_kernel must be 0 (auto), 1 (direct loads), 2 (TMA ring), 3 (index-pipelined) or 4 (symmetric)");
+        MFEM_REQUIRE(value >= 0 && value <= 5, MFEM_B200_ERR_INVALID, "spmv_kernel must be 0 (auto), 1 (direct loads), 2 (TMA ring), 3 (index-pipelined), 4 (symmetric) or 5 (128-bit load timing probe: wrong results)");
         h->opt_spmv_kernel = (int)value;
     } else if (n == "coarse_aggregates") {
         MFEM_REQUIRE(value >= -1 && value <= 5461, MFEM_B200_ERR_INVALID,
@@ -115,6 +209,10 @@ int mfem_b200_set_option(mfem_b200_handle h, const char *name, int64_t value) {
         h->precondValid = false;
     } else if (n == "coarse_shape") {
         MFEM_REQUIRE(value == 0, MFEM_B200_ERR_INVALID, "coarse_shape: only 0 (nested box grids) is supported");
+    } else if (n == "spmv_min_blocks") {
+        h->opt_spmv_min_blocks = (int)value;
+    } else if (n == "spmv_prefetch") {
+        h->opt_spmv_prefetch = value != 0;
     } else if (n == "spmv_lanes") {
         MFEM_REQUIRE(value == 0 || value == 8 || value == 16 || value == 32, MFEM_B200_ERR_INVALID,
                      "spmv_lanes must be 0 (auto), 8, 16 or 32");
@@ -483,6 +581,11 @@ int mfem_b200_get_coarse_array(mfem_b200_handle h, const char *name, double *out
     MFEM_REQUIRE(name && n, MFEM_B200_ERR_INVALID, "get_coarse_array: null argument");
     *n = get_coarse_array(h, name, out, capacity);
     API_END(h)
+}
+
+int mfem_b200_release_cached_memory(void) {
+    mfem::pool_release_all();
+    return MFEM_B200_OK;
 }
 
 }  // extern "C"

@@ -56,7 +56,11 @@ struct CoarseSpace {
     DevBuf<double> B1inv;             // [S1*M*M]
     DevBuf<double> D1;                // [S1*M(M+1)/2] the blocks B1inv was computed from (upper triangles, column by column)
     DevBuf<double> c1, y1;            // [n1*M]
-    DevBuf<double> Einv;              // [nc2*nc2] row-major, symmetric
+    DevBuf<double> Einv;              // [nRowsLoc*nc2] rows rowBase.. of E2^-1 (row-major).  One rank: all of it; N ranks:
+                                      // the rows of the large boxes this rank owns (the dense level is ROW-SPLIT: every
+                                      // rank computes its slice of y2 = E2^-1 c2, one all-gather completes it)
+    DevBuf<double> Efac;              // [nc2*nc2] N ranks only: the assembled / all-reduced / factorised E2
+    int64_t rowBase = 0, nRowsLoc = 0;
     DevBuf<double> y2;                // [nc2]
 };
 
@@ -551,17 +555,18 @@ k_coarse_level1(int64_t S1, int64_t n1, int64_t R, int64_t aggBase, bool level1,
     }
 }
 
-// y2 = Einv c2 (one warp per row); the last CTA adds c2.y2 in a fixed order to the (all-reduced) block-Jacobi + level-1
-// part of r.z: out[0] = red[0] + c2.y2, out[1] = red[1] -- every rank holds the same c2, Einv and grid, hence the same bits
+// y2[rowBase + k] = Einv[k, :] . c2 for the nRows local rows (one warp per row).  One rank (FINAL): the last CTA adds
+// c2.y2 in a fixed order to the block-Jacobi + level-1 part of r.z: out[0] = red[0] + c2.y2, out[1] = red[1].
+template <bool FINAL>
 __global__ void __launch_bounds__(kVecThreads)
-k_coarse_gemv(int64_t nc, const double *__restrict__ Einv, const double *__restrict__ red, double *__restrict__ y2,
-              double *partials, unsigned *ticket, double *out, const int *status) {
+k_coarse_gemv(int64_t nc, int64_t rowBase, int64_t nRows, const double *__restrict__ Einv, const double *__restrict__ red,
+              double *__restrict__ y2, double *partials, unsigned *ticket, double *out, const int *status) {
     if (status && status[ST_STATE] != 0) return;
     const double *c2 = red + 2;
     const int lane = threadIdx.x & 31;
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nWarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     double dot = 0.0;
-    for (int64_t row = warp; row < nc; row += nWarps) {
+    for (int64_t row = warp; row < nRows; row += nWarps) {
         const double *e = Einv + row * nc;
         double s0 = 0.0, s1 = 0.0;
         int64_t k = lane;
@@ -570,14 +575,33 @@ k_coarse_gemv(int64_t nc, const double *__restrict__ Einv, const double *__restr
         double s = s0 + s1;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) { y2[row] = s; dot = fma(s, c2[row], dot); }
+        if (lane == 0) { y2[rowBase + row] = s; dot = fma(s, c2[rowBase + row], dot); }
     }
-    double v1[1] = {dot};
-    block_reduce_store<1>(v1, partials);
-    if (last_block(ticket)) {
-        const double s = final_sum(partials, gridDim.x);
-        if (threadIdx.x == 0) { out[0] = red[0] + s; out[1] = red[1]; }
+    if (FINAL) {
+        double v1[1] = {dot};
+        block_reduce_store<1>(v1, partials);
+        if (last_block(ticket)) {
+            const double s = final_sum(partials, gridDim.x);
+            if (threadIdx.x == 0) { out[0] = red[0] + s; out[1] = red[1]; }
+        }
     }
+}
+// N ranks, after the all-gather of y2: out[0] = red[0] + c2.y2 in a fixed order (one CTA) -- every rank holds the same
+// c2 and y2, hence the same bits; out[1] = red[1]
+__global__ void __launch_bounds__(256) k_coarse_cy(int64_t nc, const double *__restrict__ red, const double *__restrict__ y2,
+                                                   double *out, const int *status) {
+    if (status && status[ST_STATE] != 0) return;
+    __shared__ double sh[256];
+    const double *c2 = red + 2;
+    double s = 0.0;
+    for (int64_t k = threadIdx.x; k < nc; k += 256) s = fma(c2[k], y2[k], s);
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { out[0] = red[0] + sh[0]; out[1] = red[1]; }
 }
 
 // coarse part of z for DoF i: R1_i (y1[slot] + P2 y2[large box])
@@ -615,6 +639,7 @@ struct CusolverApi {
     cusolverStatus_t (*potrf)(cusolverDnHandle_t, cublasFillMode_t, int, double *, int, double *, int, int *) = nullptr;
     cusolverStatus_t (*potriBuf)(cusolverDnHandle_t, cublasFillMode_t, int, double *, int, int *) = nullptr;
     cusolverStatus_t (*potri)(cusolverDnHandle_t, cublasFillMode_t, int, double *, int, double *, int, int *) = nullptr;
+    cusolverStatus_t (*potrs)(cusolverDnHandle_t, cublasFillMode_t, int, int, const double *, int, double *, int, int *) = nullptr;
 };
 static CusolverApi &cusolver_api() {
     static CusolverApi api;
@@ -636,6 +661,7 @@ static CusolverApi &cusolver_api() {
     api.potrf = reinterpret_cast<decltype(api.potrf)>(sym("cusolverDnDpotrf"));
     api.potriBuf = reinterpret_cast<decltype(api.potriBuf)>(sym("cusolverDnDpotri_bufferSize"));
     api.potri = reinterpret_cast<decltype(api.potri)>(sym("cusolverDnDpotri"));
+    api.potrs = reinterpret_cast<decltype(api.potrs)>(sym("cusolverDnDpotrs"));
     return api;
 }
 
@@ -644,13 +670,21 @@ static void free_coarse(mfem_b200_ctx *c) {
     c->coarse = nullptr;
 }
 
-// E (assembled: the row-major upper block triangle, which is all potrf reads) -> regularised -> explicit inverse in place
-// (potrf + potri + mirror).  Returns false when E is not positive definite (the caller falls back to block-Jacobi in
-// automatic mode, throws otherwise).
-static bool invert_coarse_matrix(mfem_b200_ctx *c, CoarseSpace &cs, std::string &why) {
+__global__ void k_coarse_identity_cols(int64_t nc, int64_t rowBase, int64_t nCols, double *B /* [nc x nCols] column-major */) {
+    const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (j < nCols) B[j * nc + rowBase + j] = 1.0;
+}
+
+// E (assembled in `Ebuf`: the row-major upper block triangle, which is all potrf reads) -> regularised -> Cholesky factor.
+// One rank: explicit inverse in place (potri + mirror), Ebuf is cs.Einv.  N ranks: every rank factorises the same
+// all-reduced E and then solves for ITS rows of the (symmetric) inverse only: E X = I[:, own rows] (potrs), so the
+// O(n^3) part of the inversion and the per-iteration GEMV are split N ways.
+// Returns false when E is not positive definite (the caller falls back to block-Jacobi in automatic mode, throws otherwise).
+static bool invert_coarse_matrix(mfem_b200_ctx *c, CoarseSpace &cs, double *Ebuf, std::string &why) {
     cudaStream_t s = c->stream;
     const int64_t nc = cs.nc2;
-    k_coarse_regularize<<<grid_for(nc, 256), 256, 0, s>>>(nc, cs.Einv, 1e-8);
+    const bool multi = c->nRanks > 1;
+    k_coarse_regularize<<<grid_for(nc, 256), 256, 0, s>>>(nc, Ebuf, 1e-8);
     c->launches++;
     MFEM_CUDA(cudaGetLastError());
     CusolverApi &api = cusolver_api();
@@ -661,23 +695,38 @@ static bool invert_coarse_matrix(mfem_b200_ctx *c, CoarseSpace &cs, std::string 
     if (!h) MFEM_REQUIRE(api.create(&h) == CUSOLVER_STATUS_SUCCESS, MFEM_B200_ERR_CUDA, "cusolverDnCreate failed");
     MFEM_REQUIRE(api.setStream(h, s) == CUSOLVER_STATUS_SUCCESS, MFEM_B200_ERR_CUDA, "cusolverDnSetStream failed");
     int lw1 = 0, lw2 = 0;
-    MFEM_REQUIRE(api.potrfBuf(h, CUBLAS_FILL_MODE_LOWER, (int)nc, cs.Einv, (int)nc, &lw1) == CUSOLVER_STATUS_SUCCESS, MFEM_B200_ERR_CUDA, "potrf_bufferSize failed");
-    MFEM_REQUIRE(api.potriBuf(h, CUBLAS_FILL_MODE_LOWER, (int)nc, cs.Einv, (int)nc, &lw2) == CUSOLVER_STATUS_SUCCESS, MFEM_B200_ERR_CUDA, "potri_bufferSize failed");
+    MFEM_REQUIRE(api.potrfBuf(h, CUBLAS_FILL_MODE_LOWER, (int)nc, Ebuf, (int)nc, &lw1) == CUSOLVER_STATUS_SUCCESS, MFEM_B200_ERR_CUDA, "potrf_bufferSize failed");
+    if (!multi)
+        MFEM_REQUIRE(api.potriBuf(h, CUBLAS_FILL_MODE_LOWER, (int)nc, Ebuf, (int)nc, &lw2) == CUSOLVER_STATUS_SUCCESS, MFEM_B200_ERR_CUDA, "potri_bufferSize failed");
     DevBuf<double> wbuf((size_t)std::max(lw1, lw2) + 1);
     DevBuf<int> info(1);
     int hinfo = 0;
-    MFEM_REQUIRE(api.potrf(h, CUBLAS_FILL_MODE_LOWER, (int)nc, cs.Einv, (int)nc, wbuf, lw1, info) == CUSOLVER_STATUS_SUCCESS, MFEM_B200_ERR_CUDA, "potrf failed");
+    MFEM_REQUIRE(api.potrf(h, CUBLAS_FILL_MODE_LOWER, (int)nc, Ebuf, (int)nc, wbuf, lw1, info) == CUSOLVER_STATUS_SUCCESS, MFEM_B200_ERR_CUDA, "potrf failed");
     MFEM_CUDA(cudaMemcpyAsync(&hinfo, info, sizeof(int), cudaMemcpyDeviceToHost, s));
     MFEM_CUDA(cudaStreamSynchronize(s));
     if (hinfo != 0) {
         why = "coarse matrix is not positive definite (leading minor " + std::to_string(hinfo) + "): fewer aggregates, or a singular system";
         return false;
     }
-    MFEM_REQUIRE(api.potri(h, CUBLAS_FILL_MODE_LOWER, (int)nc, cs.Einv, (int)nc, wbuf, lw2, info) == CUSOLVER_STATUS_SUCCESS, MFEM_B200_ERR_CUDA, "potri failed");
+    if (multi) {
+        // rows rowBase .. rowBase + nRowsLoc of E^-1 = columns of the solution of E X = I[:, those columns]
+        // (column-major nc x nRowsLoc == row-major nRowsLoc x nc)
+        MFEM_CUDA(cudaMemsetAsync(cs.Einv, 0, cs.Einv.bytes(), s));
+        k_coarse_identity_cols<<<grid_for(cs.nRowsLoc, 256), 256, 0, s>>>(nc, cs.rowBase, cs.nRowsLoc, cs.Einv);
+        c->launches++;
+        MFEM_REQUIRE(api.potrs(h, CUBLAS_FILL_MODE_LOWER, (int)nc, (int)cs.nRowsLoc, Ebuf, (int)nc, cs.Einv, (int)nc, info) == CUSOLVER_STATUS_SUCCESS,
+                     MFEM_B200_ERR_CUDA, "potrs failed");
+        MFEM_CUDA(cudaMemcpyAsync(&hinfo, info, sizeof(int), cudaMemcpyDeviceToHost, s));
+        MFEM_CUDA(cudaStreamSynchronize(s));
+        if (hinfo != 0) { why = "coarse matrix solve failed (" + std::to_string(hinfo) + ")"; return false; }
+        MFEM_CUDA(cudaGetLastError());
+        return true;
+    }
+    MFEM_REQUIRE(api.potri(h, CUBLAS_FILL_MODE_LOWER, (int)nc, Ebuf, (int)nc, wbuf, lw2, info) == CUSOLVER_STATUS_SUCCESS, MFEM_B200_ERR_CUDA, "potri failed");
     MFEM_CUDA(cudaMemcpyAsync(&hinfo, info, sizeof(int), cudaMemcpyDeviceToHost, s));
     MFEM_CUDA(cudaStreamSynchronize(s));
     if (hinfo != 0) { why = "coarse matrix inversion failed (" + std::to_string(hinfo) + ")"; return false; }
-    k_coarse_symmetrize<<<dim3((unsigned)grid_for(nc, 256), (unsigned)nc), 256, 0, s>>>(nc, cs.Einv);
+    k_coarse_symmetrize<<<dim3((unsigned)grid_for(nc, 256), (unsigned)nc), 256, 0, s>>>(nc, Ebuf);
     c->launches++;
     MFEM_CUDA(cudaStreamSynchronize(s));
     MFEM_CUDA(cudaGetLastError());
@@ -817,26 +866,31 @@ static bool build_coarse_values(mfem_b200_ctx *c, std::string &why) {
     CoarseSpace &cs = *c->coarse;
     const int64_t nb = c->nDofs, nc = cs.nc2;
     const bool multi = c->nRanks > 1;
-    if (cs.Einv.n != (size_t)nc * nc) cs.Einv.alloc((size_t)nc * nc);
+    // one rank: E is assembled, factorised and inverted in cs.Einv; N ranks: in cs.Efac, and cs.Einv gets this rank's rows
+    cs.rowBase = multi ? cs.aggBase * M : 0;
+    cs.nRowsLoc = multi ? nc / c->nRanks : nc;
+    if (cs.Einv.n != (size_t)cs.nRowsLoc * nc) cs.Einv.alloc((size_t)cs.nRowsLoc * nc);
+    if (multi && cs.Efac.n != (size_t)nc * nc) cs.Efac.alloc((size_t)nc * nc);
+    double *Ebuf = multi ? cs.Efac.p : cs.Einv.p;
     const int grid = (int)std::min<int64_t>((nb + 7) / 8, (int64_t)sm_count(c) * 8);
     {
         ScopedTimer t(c, "Coarse Matrix");
-        MFEM_CUDA(cudaMemsetAsync(cs.Einv, 0, cs.Einv.bytes(), s));
-        if (cs.meshVersion == -2) MFEM_CUDA(cudaMemsetAsync(cs.Einv, 0xff, sizeof(double), s));   // NaN in E[0]: the inversion fails on all ranks
+        MFEM_CUDA(cudaMemsetAsync(Ebuf, 0, sizeof(double) * nc * nc, s));
+        if (cs.meshVersion == -2) MFEM_CUDA(cudaMemsetAsync(Ebuf, 0xff, sizeof(double), s));   // NaN in E[0]: the inversion fails on all ranks
         k_coarse_matrix<N><<<grid, 256, 0, s>>>(nb, cs.S2, cs.S1, cs.R, cs.aggBase, cs.agg1, cs.Y1, cs.shift, c->rowptr, c->colidx, c->vals,
-                                                c->fixedMask, cs.Einv);
+                                                c->fixedMask, Ebuf);
         c->launches++;
         MFEM_CUDA(cudaGetLastError());
         if (multi) {
             // one all-reduce of the partial coarse matrices (chunked: keep single calls moderate)
             const size_t total = (size_t)nc * nc, chunk = (size_t)1 << 27;
             for (size_t off = 0; off < total; off += chunk)
-                allreduce_sum(c, cs.Einv.p + off, cs.Einv.p + off, (int)std::min(chunk, total - off));
+                allreduce_sum(c, Ebuf + off, Ebuf + off, (int)std::min(chunk, total - off));
         }
     }
     {
         ScopedTimer t(c, "Coarse Inverse");
-        if (!invert_coarse_matrix(c, cs, why)) return false;
+        if (!invert_coarse_matrix(c, cs, Ebuf, why)) return false;
     }
     if (cs.level1) {
         ScopedTimer t(c, "Coarse Level 1");

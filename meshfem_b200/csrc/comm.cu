@@ -124,6 +124,12 @@ void allreduce_sum(mfem_b200_ctx *c, const double *in, double *out, int n) {
     MFEM_NCCL(ncclAllReduce(in, out, (size_t)n, ncclDouble, ncclSum, static_cast<ncclComm_t>(c->ncclComm), c->stream));
 }
 
+// every rank contributes buf[rank*count .. (rank+1)*count) and receives all slices (in place)
+void allgather_inplace(mfem_b200_ctx *c, double *buf, int count) {
+    if (c->nRanks <= 1) return;
+    MFEM_NCCL(ncclAllGather(buf + (size_t)c->rank * count, buf, (size_t)count, ncclDouble, static_cast<ncclComm_t>(c->ncclComm), c->stream));
+}
+
 }  // namespace mfem
 
 using namespace mfem;

@@ -33,7 +33,15 @@ struct CudaError : std::runtime_error {
         if (!(cond)) throw mfem::CudaError((status), (msg));  \
     } while (0)
 
-// Owning device buffer (plain cudaMalloc; lifetime = handle or a setup scope).
+// Device memory comes from a small process-wide caching pool (capi.cu): cudaMalloc / cudaFree of the multi-GB arrays
+// of a handle cost hundreds of milliseconds (page-table work, a device-wide synchronisation per cudaFree), which a
+// long-lived process that creates handle after handle (an optimisation loop, bench.py's end-to-end steps) would pay
+// every time.  A freed block is kept and handed to the next request of a similar size on the same device; the pool is
+// emptied when an allocation fails, on mfem_b200_release_cached_memory(), or never used with MFEM_B200_POOL=0.
+void *pool_alloc(size_t bytes);
+void pool_free(void *p);
+
+// Owning device buffer (lifetime = handle or a setup scope).
 template <class T>
 struct DevBuf {
     T *p = nullptr;
@@ -51,10 +59,10 @@ struct DevBuf {
     void alloc(size_t count) {
         free();
         n = count;
-        if (count) MFEM_CUDA(cudaMalloc(reinterpret_cast<void **>(&p), count * sizeof(T)));
+        if (count) p = static_cast<T *>(pool_alloc(count * sizeof(T)));
     }
     void free() {
-        if (p) cudaFree(p);
+        if (p) pool_free(p);
         p = nullptr; n = 0;
     }
     size_t bytes() const { return n * sizeof(T); }
@@ -94,10 +102,12 @@ struct mfem_b200_ctx {
     int opt_spmv_kernel = 0;               // 0 auto, 1 direct-load kernel, 2 TMA-ring kernel, 3 index-pipelined, 4 symmetric (upper tails + atomics)
     int opt_spmm_kernel = 0;               // batched PCG: 0/1 full-warp SpMM, 2 half-warp split SpMM (even batch sizes)
     int opt_batch_rhs = 1;                 // solve flatLen(N) right-hand sides as one batched PCG (SpMM)
+    int opt_spmv_min_blocks = 0;           // SpMV occupancy experiment: 3 or 5 CTAs per SM instead of 4 (N = 3, 32 lanes)
+    int opt_spmv_prefetch = 0;             // SpMV: L2 prefetch of the row a warp streams next (one prefetch instruction per lane and row)
     int opt_spmv_lanes = 0;                // lanes per block row in the SpMV (0 = choose from the mean row length)
     int opt_coarse = -1;                   // large aggregates of the multilevel preconditioner: -1 automatic (from the
                                            // problem size; block-Jacobi only below 30k DoFs), 0 = block-Jacobi only
-    int opt_coarse_fine = 32;              // DoFs (nodes) per small (level-1) aggregate; 0 = no level 1 (two-level method)
+    int opt_coarse_fine = 64;              // DoFs (nodes) per small (level-1) aggregate; 0 = no level 1 (two-level method)
     int64_t meshVersion = 0;               // bumped by everything that changes DoFs, positions or the interface
 
     // mesh
@@ -250,6 +260,7 @@ void apply_preconditioner(mfem_b200_ctx *c, const double *r_int, double *z_int, 
 // comm.cu
 void halo_exchange_add(mfem_b200_ctx *c, double *vec_int, int width);   // no-op on one rank
 void allreduce_sum(mfem_b200_ctx *c, const double *in, double *out, int n);
+void allgather_inplace(mfem_b200_ctx *c, double *buf, int count);   // slices of `count` doubles in rank order
 const uint8_t *halo_owned(mfem_b200_ctx *c);
 const uint8_t *halo_shared(mfem_b200_ctx *c);      // [nDofs] 1 = DoF shared with another rank
 // aux.cu

@@ -251,8 +251,15 @@ __device__ __forceinline__ void gather3(const double *x0, const double *x1, cons
         : "memory");
 }
 
-template <int N, int LPR, bool MASKED, bool DOT>
-__global__ void __launch_bounds__(kSpmvThreads, 4)   // <= 64 registers: 32 resident warps per SM
+// PF = true: every lane also issues ONE `prefetch.global.L2` per row iteration for the row this warp will stream in
+// its NEXT iteration (its extent is fetched two iterations ahead): lane l touches the l-th 128-byte line of that row's
+// values (32 lines = 4 KB = 56 blocks; longer rows lose their tail) and lanes 0..2 a line of its column indices.
+// The prefetch needs no destination registers, so the DRAM round trip of row k+1 overlaps all of row k's work at no
+// occupancy cost; the streaming loads then hit L2.
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+template <int N, int LPR, bool MASKED, bool DOT, bool PF, int MINB = 4>
+__global__ void __launch_bounds__(kSpmvThreads, MINB)   // MINB = 4: <= 64 registers, 32 resident warps per SM
 k_bsr_spmv(int64_t nb, const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
            const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y,
            const uint8_t *__restrict__ fixedMask, double *partials, unsigned *ticket, double *dotOut,
@@ -280,18 +287,33 @@ k_bsr_spmv(int64_t nb, const int64_t *__restrict__ rowptr, const int32_t *__rest
         cc[u] = f - jj[u] * N;
     }
     double dot = 0.0;
-    // software pipeline over rows: the next row's extent is fetched while this one is computed
+    // software pipeline over rows: the next row's extent is fetched while this one is computed (PF: two rows ahead)
     int64_t row = warpGlobal * RPW + sub;
     const int64_t rowStride = nWarps * RPW;
-    int64_t nb0 = 0, nb1 = 0;
+    int64_t nb0 = 0, nb1 = 0, pb0 = 0;
+    int pn = 0;
     if (row < nb) { nb0 = rowptr[row]; nb1 = rowptr[row + 1]; }
+    if (PF && row + rowStride < nb) { pb0 = rowptr[row + rowStride]; pn = (int)(rowptr[row + rowStride + 1] - pb0); }
     for (int64_t rowBase = warpGlobal * RPW; rowBase < nb; rowBase += rowStride) {
         const int64_t b0 = nb0;
         const int L = (int)(nb1 - nb0) * N;
         const int64_t thisRow = row;
         row += rowStride;
-        nb0 = nb1 = 0;
-        if (row < nb) { nb0 = rowptr[row]; nb1 = rowptr[row + 1]; }
+        if (PF) {
+            // row k+1: extent known since the previous iteration -> prefetch its lines now; row k+2: fetch the extent
+            nb0 = pb0; nb1 = pb0 + pn;
+            if (pn > 0) {
+                const char *pv = reinterpret_cast<const char *>(vals + pb0 * NN) + sl * 128 * (32 / LPR);
+                if (sl * 128 * (32 / LPR) < pn * NN * 8) prefetch_l2(pv);
+                if (LPR < 32 && sl * 128 * (32 / LPR) + 128 < pn * NN * 8) prefetch_l2(pv + 128);
+                if (sl * 128 < pn * 4) prefetch_l2(reinterpret_cast<const char *>(colidx + pb0) + sl * 128);
+            }
+            pb0 = 0; pn = 0;
+            if (row + rowStride < nb) { pb0 = rowptr[row + rowStride]; pn = (int)(rowptr[row + rowStride + 1] - pb0); }
+        } else {
+            nb0 = nb1 = 0;
+            if (row < nb) { nb0 = rowptr[row]; nb1 = rowptr[row + 1]; }
+        }
         const double *v = vals + b0 * NN + sl;        // plane 0, this lane's first scalar
         const int32_t *ci = colidx + b0;
         double acc[N];
@@ -609,6 +631,126 @@ k_bsr_spmv_sym(int64_t nb, const int64_t *__restrict__ rowptr, const int32_t *__
         }
         const double out0 = fold_reduce<N, LPR>(acc, sl);
         if (comp >= 0 && thisRow < nb) red_add_f64(y + (thisRow * N + comp), out0);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K3v  bsr_spmv_v2 (N = 3): 128-bit matrix loads.  16 lanes per block row, two rows per warp; lane l of a row owns the
+// scalar PAIRS (32u + 2l, 32u + 2l + 1), u = 0..2, of each of the three planes of a 96-scalar chunk: 9 v2.f64 streaming
+// loads, 6 column indices, 6 gathered x values, 18 FMAs per lane and chunk -- 10.5 load instructions per row chunk
+// instead of 15, twice the bytes in flight per warp, and the fold / row bookkeeping shared by two rows.
+// Needs 16-byte aligned planes: ALIGNED = true is for a value layout whose planes start on even indices (not the
+// current one); ALIGNED = false rounds every address down to 16 bytes, which reads the wrong doubles whenever a plane
+// starts on an odd index -- option spmv_kernel = 5 is a TIMING PROBE of the memory pipeline, not a usable SpMV.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void ld_stream_v2(const double *p, uint64_t pol, int pred, double &a, double &b) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %3, 0;\n\t"
+        "mov.f64 %0, 0d0000000000000000; mov.f64 %1, 0d0000000000000000;\n\t"
+        "@q ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0, %1}, [%2], %4;\n\t}"
+        : "=d"(a), "=d"(b)
+        : "l"(p), "r"(pred), "l"(pol)
+        : "memory");
+}
+__device__ __forceinline__ int ld_stream_s32_pred(const int32_t *p, uint64_t pol, int pred) {
+    int v;
+    asm volatile(
+        "{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %2, 0;\n\tmov.b32 %0, 0;\n\t"
+        "@q ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %3;\n\t}"
+        : "=r"(v)
+        : "l"(p), "r"(pred), "l"(pol)
+        : "memory");
+    return v;
+}
+__device__ __forceinline__ double ld_keep_f64_v(const double *p, uint64_t pol) {
+    double v;
+    asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol) : "memory");
+    return v;
+}
+
+template <bool MASKED, bool DOT, bool ALIGNED>
+__global__ void __launch_bounds__(kSpmvThreads, 3)
+k_bsr_spmv_v2(int64_t nb, const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
+              const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y,
+              const uint8_t *__restrict__ fixedMask, double *partials, unsigned *ticket, double *dotOut, const int *status) {
+    constexpr int N = 3, NN = 9, LPR = 16, RPW = 2, U = 3, CH = U * 2 * LPR;     // 96 scalars of a plane per chunk
+    if (status && status[ST_STATE] != 0) return;
+    const int lane = threadIdx.x & 31;
+    const int sub = lane / LPR, sl = lane % LPR;
+    const int64_t warpGlobal = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nWarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int comp = owner_component<N, LPR>(sl);
+    const unsigned groupMask = ((1u << LPR) - 1u) << (sub * LPR);
+    const uint64_t polStream = l2_policy_evict_first(), polKeep = l2_policy_evict_last();
+    int j0[U], c0[U], j1[U], c1[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int f = 2 * LPR * u + 2 * sl;
+        j0[u] = f / N; c0[u] = f - j0[u] * N;
+        j1[u] = (f + 1) / N; c1[u] = f + 1 - j1[u] * N;
+    }
+    double dot = 0.0;
+    int64_t row = warpGlobal * RPW + sub;
+    const int64_t rowStride = nWarps * RPW;
+    int64_t nb0 = 0, nb1 = 0;
+    if (row < nb) { nb0 = rowptr[row]; nb1 = rowptr[row + 1]; }
+    for (int64_t rowBase = warpGlobal * RPW; rowBase < nb; rowBase += rowStride) {
+        const int64_t b0 = nb0;
+        const int L = (int)(nb1 - nb0) * N;
+        const int64_t thisRow = row;
+        row += rowStride;
+        nb0 = nb1 = 0;
+        if (row < nb) { nb0 = rowptr[row]; nb1 = rowptr[row + 1]; }
+        const double *v = vals + b0 * NN + 2 * sl;
+        const int32_t *ci = colidx + b0;
+        double acc[N] = {0.0, 0.0, 0.0};
+        // the two half-warps may have rows of different lengths: loop to the longer one (shorter one is predicated off)
+        const int Lmax = max(L, __shfl_xor_sync(0xffffffffu, L, LPR));
+        for (int base = 0; base < Lmax; base += CH, v += CH, ci += CH / N) {
+            const int rem = L - base - 2 * sl;        // pair u is valid iff 32u < rem (second scalar iff 32u + 1 < rem)
+            int col0[U], col1[U];
+            double a0[U][N], a1[U][N];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                col0[u] = ld_stream_s32_pred(ci + j0[u], polStream, 2 * LPR * u < rem);
+                col1[u] = ld_stream_s32_pred(ci + j1[u], polStream, 2 * LPR * u + 1 < rem);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int r = 0; r < N; ++r) {
+                    const double *q = v + r * L + 2 * LPR * u;
+                    if (!ALIGNED) q = reinterpret_cast<const double *>(reinterpret_cast<uintptr_t>(q) & ~uintptr_t(15));
+                    ld_stream_v2(q, polStream, 2 * LPR * u < rem, a0[u][r], a1[u][r]);
+                }
+            __syncwarp(groupMask);
+            double x0[U], x1[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                x0[u] = ld_keep_f64_v(x + (col0[u] * N + c0[u]), polKeep);
+                x1[u] = ld_keep_f64_v(x + (col1[u] * N + c1[u]), polKeep);
+            }
+            __syncwarp(groupMask);
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int r = 0; r < N; ++r) acc[r] = fma(a1[u][r], x1[u], fma(a0[u][r], x0[u], acc[r]));
+        }
+        const double out0 = fold_reduce<N, LPR>(acc, sl);
+        if (comp >= 0 && thisRow < nb) {
+            double out = out0;
+            if (MASKED && fixedMask[thisRow * N + comp]) out = 0.0;
+            y[thisRow * N + comp] = out;
+            if (DOT) dot += out * x[thisRow * N + comp];
+        }
+    }
+    if (DOT) {
+        double v1[1] = {dot};
+        block_reduce_store<1>(v1, partials);
+        if (last_block(ticket)) {
+            const double s = final_sum(partials, gridDim.x);
+            if (threadIdx.x == 0) dotOut[0] = s;
+        }
     }
 }
 
@@ -1125,19 +1267,41 @@ void ensure_work(mfem_b200_ctx *c) {
     c->workValid = true;
 }
 
-template <int N, int LPR>
-static void launch_spmv_l(mfem_b200_ctx *c, const double *x, double *y, bool masked, bool dot) {
+template <int N, int LPR, bool PF>
+static void launch_spmv_lp(mfem_b200_ctx *c, const double *x, double *y, bool masked, bool dot) {
     PcgWork &w = c->work;
     if (masked && dot)
-        k_bsr_spmv<N, LPR, true, true><<<spmv_grid(c, LPR, k_bsr_spmv<N, LPR, true, true>), kSpmvThreads, 0, c->stream>>>(
+        k_bsr_spmv<N, LPR, true, true, PF><<<spmv_grid(c, LPR, k_bsr_spmv<N, LPR, true, true, PF>), kSpmvThreads, 0, c->stream>>>(
             c->nDofs, c->rowptr, c->colidx, c->vals, x, y, c->fixedMask, w.partials, w.ticket, w.scal.p + S_PAP, w.status);
     else if (masked)
-        k_bsr_spmv<N, LPR, true, false><<<spmv_grid(c, LPR, k_bsr_spmv<N, LPR, true, false>), kSpmvThreads, 0, c->stream>>>(
+        k_bsr_spmv<N, LPR, true, false, PF><<<spmv_grid(c, LPR, k_bsr_spmv<N, LPR, true, false, PF>), kSpmvThreads, 0, c->stream>>>(
             c->nDofs, c->rowptr, c->colidx, c->vals, x, y, c->fixedMask, nullptr, nullptr, nullptr, nullptr);
     else
-        k_bsr_spmv<N, LPR, false, false><<<spmv_grid(c, LPR, k_bsr_spmv<N, LPR, false, false>), kSpmvThreads, 0, c->stream>>>(
+        k_bsr_spmv<N, LPR, false, false, PF><<<spmv_grid(c, LPR, k_bsr_spmv<N, LPR, false, false, PF>), kSpmvThreads, 0, c->stream>>>(
             c->nDofs, c->rowptr, c->colidx, c->vals, x, y, nullptr, nullptr, nullptr, nullptr, nullptr);
     c->launches++;
+}
+// occupancy experiment (option spmv_min_blocks = 3 / 5, N = 3 with 32 lanes only): the same kernel compiled for 3 CTAs
+// per SM (80 registers: ptxas keeps the lane constants instead of recomputing them per row) or 5 (48 registers)
+template <int MINB>
+static void launch_spmv_occ(mfem_b200_ctx *c, const double *x, double *y, bool masked, bool dot) {
+    PcgWork &w = c->work;
+    if (masked && dot)
+        k_bsr_spmv<3, 32, true, true, false, MINB><<<spmv_grid(c, 32, k_bsr_spmv<3, 32, true, true, false, MINB>), kSpmvThreads, 0, c->stream>>>(
+            c->nDofs, c->rowptr, c->colidx, c->vals, x, y, c->fixedMask, w.partials, w.ticket, w.scal.p + S_PAP, w.status);
+    else
+        k_bsr_spmv<3, 32, false, false, false, MINB><<<spmv_grid(c, 32, k_bsr_spmv<3, 32, false, false, false, MINB>), kSpmvThreads, 0, c->stream>>>(
+            c->nDofs, c->rowptr, c->colidx, c->vals, x, y, nullptr, nullptr, nullptr, nullptr, nullptr);
+    c->launches++;
+}
+template <int N, int LPR>
+static void launch_spmv_l(mfem_b200_ctx *c, const double *x, double *y, bool masked, bool dot) {
+    if (N == 3 && LPR == 32 && (masked == dot) && (c->opt_spmv_min_blocks == 3 || c->opt_spmv_min_blocks == 5)) {
+        if (c->opt_spmv_min_blocks == 3) launch_spmv_occ<3>(c, x, y, masked, dot); else launch_spmv_occ<5>(c, x, y, masked, dot);
+        return;
+    }
+    if (c->opt_spmv_prefetch) launch_spmv_lp<N, LPR, true>(c, x, y, masked, dot);
+    else launch_spmv_lp<N, LPR, false>(c, x, y, masked, dot);
 }
 
 template <int N>
@@ -1206,8 +1370,20 @@ static void launch_spmv_tma(mfem_b200_ctx *c, const double *x, double *y, bool m
     c->launches++;
 }
 
+static void launch_spmv_v2probe(mfem_b200_ctx *c, const double *x, double *y, bool masked, bool dot) {
+    PcgWork &w = c->work;
+    if (masked && dot)
+        k_bsr_spmv_v2<true, true, false><<<spmv_grid(c, 16, k_bsr_spmv_v2<true, true, false>), kSpmvThreads, 0, c->stream>>>(
+            c->nDofs, c->rowptr, c->colidx, c->vals, x, y, c->fixedMask, w.partials, w.ticket, w.scal.p + S_PAP, w.status);
+    else
+        k_bsr_spmv_v2<false, false, false><<<spmv_grid(c, 16, k_bsr_spmv_v2<false, false, false>), kSpmvThreads, 0, c->stream>>>(
+            c->nDofs, c->rowptr, c->colidx, c->vals, x, y, nullptr, nullptr, nullptr, nullptr, nullptr);
+    c->launches++;
+}
+
 template <int N>
 static void launch_spmv(mfem_b200_ctx *c, const double *x, double *y, bool masked, bool dot) {
+    if (N == 3 && c->opt_spmv_kernel == 5) { launch_spmv_v2probe(c, x, y, masked, dot); return; }
     if (spmv_use_sym(c)) {
         PcgWork &w = c->work;
         launch_spmv_sym<N>(c, x, y, (masked && dot) ? w.status.p : nullptr);
@@ -1297,9 +1473,17 @@ static const double *enqueue_precond_tail(mfem_b200_ctx *c, const int *status) {
     const int g1 = (int)std::max<int64_t>(1, std::min<int64_t>((cs.n1 + kVecThreads - 1) / kVecThreads, (int64_t)sm_count(c) * 8));
     k_coarse_level1<N><<<g1, kVecThreads, 0, s>>>(cs.S1, cs.n1, cs.R, cs.aggBase, cs.level1, cs.c1, cs.y1, cs.B1inv, cs.shift, w.red, status);
     if (multi) allreduce_sum(c, w.red, w.red, (int)(2 + cs.nc2));
-    const int gg = (int)std::max<int64_t>(1, std::min<int64_t>((cs.nc2 + 7) / 8, std::min<int64_t>(kMaxPartials, (int64_t)sm_count(c) * 8)));
-    k_coarse_gemv<<<gg, kVecThreads, 0, s>>>(cs.nc2, cs.Einv, w.red, cs.y2, w.partials + 2 * (size_t)kMaxPartials, w.ticket + 3,
-                                             w.scal.p + S_RZ_NEW, status);
+    const int gg = (int)std::max<int64_t>(1, std::min<int64_t>((cs.nRowsLoc + 7) / 8, std::min<int64_t>(kMaxPartials, (int64_t)sm_count(c) * 8)));
+    if (!multi) {
+        k_coarse_gemv<true><<<gg, kVecThreads, 0, s>>>(cs.nc2, 0, cs.nRowsLoc, cs.Einv, w.red, cs.y2, w.partials + 2 * (size_t)kMaxPartials,
+                                                       w.ticket + 3, w.scal.p + S_RZ_NEW, status);
+    } else {
+        // row-split dense level: this rank's slice of y2, one in-place all-gather, then c2.y2 in a fixed order
+        k_coarse_gemv<false><<<gg, kVecThreads, 0, s>>>(cs.nc2, cs.rowBase, cs.nRowsLoc, cs.Einv, w.red, cs.y2, nullptr, nullptr, nullptr, status);
+        allgather_inplace(c, cs.y2, (int)cs.nRowsLoc);
+        k_coarse_cy<<<1, 256, 0, s>>>(cs.nc2, w.red, cs.y2, w.scal.p + S_RZ_NEW, status);
+        c->launches++;
+    }
     c->launches += 2;
     return w.scal.p + S_RZ_NEW;
 }
@@ -1497,7 +1681,7 @@ int64_t get_coarse_array(mfem_b200_ctx *c, const std::string &name, double *out,
     else if (name == "shift") fromD(cs.shift);
     else if (name == "B1inv") fromD(cs.B1inv);
     else if (name == "D1") fromD(cs.D1);
-    else if (name == "Einv") fromD(cs.Einv);
+    else if (name == "Einv") fromD(cs.Einv);      // this rank's rows (all of them on one rank)
     else if (name == "y1") fromD(cs.y1);
     else if (name == "y2") fromD(cs.y2);
     else if (name == "sizes") h = {(double)cs.S1, (double)cs.S2, (double)cs.R, (double)cs.n1, (double)cs.aggBase, cs.level1 ? 1.0 : 0.0};
@@ -1508,19 +1692,22 @@ int64_t get_coarse_array(mfem_b200_ctx *c, const std::string &name, double *out,
 
 #include "solver_multi.inl"
 
+// Average duration of the SpMV launch the PCG iteration issues -- masked rows AND the fused p.Ap epilogue
+// (k_bsr_spmv<N, lanes, 1, 1>) -- timed with CUDA events on the library's stream after 3 warm-up launches.
 double time_spmv(mfem_b200_ctx *c, int iters) {
     MFEM_REQUIRE(c->valuesValid, MFEM_B200_ERR_INVALID, "time_spmv: matrix not assembled");
     ensure_work(c);
     PcgWork &w = c->work;
     cudaStream_t s = c->stream;
-    // a non-trivial, reproducible input vector
-    k_axpby<<<vec_grid(c, c->nvar()), kVecThreads, 0, s>>>(c->nvar(), 0.0, w.b, 0.0, w.b, w.p);
+    // a non-trivial, reproducible input vector; status "running" (a finished solve leaves it at "converged", which
+    // turns the in-loop kernels into no-ops)
     MFEM_CUDA(cudaMemsetAsync(w.p, 0x3f, w.p.bytes(), s));   // 0x3f3f.. ~ 4.8e-4, finite
+    MFEM_CUDA(cudaMemsetAsync(w.status, 0, w.status.bytes(), s));
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     auto run = [&]() {
-        if (c->N == 3) launch_spmv<3>(c, w.p, w.Ap, false, false);
-        else launch_spmv<2>(c, w.p, w.Ap, false, false);
+        if (c->N == 3) launch_spmv<3>(c, w.p, w.Ap, true, true);
+        else launch_spmv<2>(c, w.p, w.Ap, true, true);
     };
     for (int k = 0; k < 3; ++k) run();
     cudaEventRecord(e0, s);

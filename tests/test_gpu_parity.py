@@ -71,16 +71,20 @@ def test_assembly_is_bit_reproducible(mfem, N, deg, sizes):
 
 
 @pytest.mark.parametrize("N,deg,sizes", CASES + [(3, 2, (9, 4, 3))])
-@pytest.mark.parametrize("lanes,kernel", [(0, 0), (0, 1), (8, 1), (16, 1), (32, 1), (0, 2), (32, 3), (0, 4), (8, 4), (16, 4), (32, 4)])
+@pytest.mark.parametrize("lanes,kernel", [(0, 0), (0, 1), (8, 1), (16, 1), (32, 1), (0, 2), (32, 3), (0, 4), (8, 4), (16, 4), (32, 4),
+                                          (8, 11), (16, 11), (32, 11)])
 def test_spmv_and_apply_K(mfem, N, deg, sizes, lanes, kernel):
     """kernel 0 = auto, 1 = direct-load SpMV (8/16/32 lanes per row), 2 = TMA-ring SpMV,
-    3 = index-pipelined SpMV (32 lanes), 4 = symmetric SpMV (upper tails + atomic adds)."""
+    3 = index-pipelined SpMV (32 lanes), 4 = symmetric SpMV (upper tails + atomic adds); 11 = kernel 1 with the L2
+    prefetch of the next row (option spmv_prefetch)."""
+    opts = dict(spmv_prefetch=1) if kernel == 11 else dict(spmv_prefetch=0)
+    kernel = 1 if kernel == 11 else kernel
     mesh = grid_mesh(N, deg, sizes)
     D = _material(N, "ortho")
     rng = np.random.default_rng(5)
     x = rng.normal(size=(mesh.num_nodes, N))
     Kref = orc.stiffness_matrix(mesh, D)
-    with _handle(mfem, mesh, D, spmv_lanes=lanes, spmv_kernel=kernel) as h:
+    with _handle(mfem, mesh, D, spmv_lanes=lanes, spmv_kernel=kernel, **opts) as h:
         h.assemble()
         y = h.spmv(x)
         z = h.apply_K(x)
