@@ -293,6 +293,9 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     dist = device = None
+    # stdout carries ONE JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION prints to stdout) out of it
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
     if world > 1:
         import torch
         import torch.distributed as dist
@@ -443,6 +446,8 @@ def run_ours(args):
         parts = {"create_upload_reorder_s": t1 - t0, "symbolic_pattern_s": hh.timer("Pattern"),
                  "assemble_call_s": t2 - t1, "numeric_assembly_s": hh.timer("Assemble System"),
                  "preconditioner_setup_s": max(0.0, hh.timer("Fix Variables")) + max(0.0, hh.timer("Coarse Space")),
+                 "coarse_structure_s": max(0.0, hh.timer("Coarse Structure")), "coarse_matrix_s": max(0.0, hh.timer("Coarse Matrix")),
+                 "coarse_inverse_s": max(0.0, hh.timer("Coarse Inverse")), "coarse_level1_s": max(0.0, hh.timer("Coarse Level 1")),
                  "pcg_s": info[0]["seconds"], "fix_solve_download_call_s": t3 - t2}
         hh.close()
         if dist is not None:

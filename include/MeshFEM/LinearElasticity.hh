@@ -235,6 +235,11 @@ public:
         namespace SD = ShapeDerivatives;
         if (u.domainSize() != m_mesh.numNodes()) throw std::runtime_error("applyDeltaStiffnessMatrix: per-node displacement expected");
         if (deltaP.domainSize() != m_mesh.numVertices()) throw std::runtime_error("applyDeltaStiffnessMatrix: per-vertex perturbation expected");
+        if (!m_hostOnly) {        // device element kernel (csrc/shape.cu k_apply_delta_K); the loop below is the host-only mirror
+            VField load(numDoFs());
+            mfemCheck(h(), mfem_b200_apply_delta_K(h(), u.data().data(), deltaP.data().data(), (int64_t)m_mesh.numVertices(), load.data().data()));
+            return load;
+        }
         constexpr size_t npe = _Mesh::nodesPerElement;
         const SD::ElementQuadrature<K, Degree> quad;
         VField load(numDoFs());
@@ -276,6 +281,13 @@ public:
     VField deltaConstantStrainLoad(const _SymMat &cstrain, const VField &deltaP) const {
         namespace SD = ShapeDerivatives;
         if (deltaP.domainSize() != m_mesh.numVertices()) throw std::runtime_error("deltaConstantStrainLoad: per-vertex perturbation expected");
+        if (!m_hostOnly) {        // device element kernel (csrc/shape.cu k_delta_const_strain_load)
+            VField dload(numDoFs());
+            Real eps[flatLen(N)];
+            for (size_t kf = 0; kf < flatLen(N); ++kf) eps[kf] = cstrain[kf];
+            mfemCheck(h(), mfem_b200_delta_const_strain_load(h(), eps, deltaP.data().data(), (int64_t)m_mesh.numVertices(), dload.data().data()));
+            return dload;
+        }
         constexpr size_t npe = _Mesh::nodesPerElement;
         VField dload(numDoFs());
         Real centroid[K + 1];
@@ -308,6 +320,12 @@ public:
         namespace SD = ShapeDerivatives;
         if (u.domainSize() != m_mesh.numNodes() || deltaU.domainSize() != m_mesh.numNodes()) throw std::runtime_error("deltaAverageStrainField: per-node fields expected");
         if (deltaP.domainSize() != m_mesh.numVertices()) throw std::runtime_error("deltaAverageStrainField: per-vertex perturbation expected");
+        if (!m_hostOnly) {        // device element kernel (csrc/shape.cu k_delta_avg_strain)
+            SMField ds(m_mesh.numElements());
+            mfemCheck(h(), mfem_b200_delta_avg_strain(h(), u.data().data(), deltaU.data().data(), deltaP.data().data(),
+                                                      (int64_t)m_mesh.numVertices(), ds.data().data()));
+            return ds;
+        }
         constexpr size_t npe = _Mesh::nodesPerElement;
         SMField ds(m_mesh.numElements());
         Real centroid[K + 1];

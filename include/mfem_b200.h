@@ -169,6 +169,18 @@ int mfem_b200_avg_strain_stress(mfem_b200_handle h, const double *u_nodes, doubl
 /* Per-element volumes and negative-volume count (Simulator ctor check).                */
 int mfem_b200_get_volumes(mfem_b200_handle h, double *vol);
 
+/* ---- discrete shape derivatives (csrc/shape.cu) ------------------------------------ */
+/* Replace Simulator::applyDeltaStiffnessMatrix (LinearElasticity.hh:1301-1330), deltaConstantStrainLoad (:1333-1348)
+ * and deltaAverageStrainField (:1365-1375): the change of K u, of constantStrainLoad(eps) and of the element-averaged
+ * strain under a perturbation delta_p of the VERTEX positions [n_vertices*dim] (the first n_vertices nodes are the
+ * vertices, FEMMesh.inl:17-37).  u_nodes / delta_u_nodes: per node [n_nodes*dim]; out_dofs: per DoF [n_dofs*dim];
+ * strain: [n_elems*flat].  One element loop each on the device (FP64 atomics for the per-DoF sums).               */
+int mfem_b200_apply_delta_K(mfem_b200_handle h, const double *u_nodes, const double *delta_p, int64_t n_vertices, double *out_dofs);
+int mfem_b200_delta_const_strain_load(mfem_b200_handle h, const double *eps_flat, const double *delta_p, int64_t n_vertices,
+                                      double *out_dofs);
+int mfem_b200_delta_avg_strain(mfem_b200_handle h, const double *u_nodes, const double *delta_u_nodes, const double *delta_p,
+                               int64_t n_vertices, double *strain);
+
 /* ---- timers (BENCHMARK_REPORT sections, GlobalBenchmark.hh:8-58) ------------------ */
 /* Seconds of device time (CUDA events) accumulated under a section name, e.g.
  * "Pattern", "Assemble System", "Elasticity Solve", "SpMV".  Returns -1.0 if unknown.  */

@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(ROOT, "csrc")
 LIBDIR = os.path.join(ROOT, "lib")
 LIB = os.path.join(LIBDIR, "libmfem_b200.so")
-SOURCES = ["setup.cu", "assemble.cu", "solver.cu", "aux.cu", "comm.cu", "capi.cu"]
+SOURCES = ["setup.cu", "assemble.cu", "solver.cu", "aux.cu", "shape.cu", "comm.cu", "capi.cu"]
 HEADERS = ["core.cuh", "elem_math.cuh", "solver_multi.inl", "coarse.inl", os.path.join("..", "..", "include", "mfem_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [

@@ -26,6 +26,7 @@ SYMBOLS = [
     "mfem_b200_avg_strain_stress", "mfem_b200_get_volumes", "mfem_b200_get_timer", "mfem_b200_reset_timers",
     "mfem_b200_launch_count", "mfem_b200_time_spmv", "mfem_b200_set_matrix_triplets", "mfem_b200_comm_share",
     "mfem_b200_apply_preconditioner", "mfem_b200_get_coarse_array", "mfem_b200_release_cached_memory",
+    "mfem_b200_apply_delta_K", "mfem_b200_delta_const_strain_load", "mfem_b200_delta_avg_strain",
 ]
 
 STATUS_NAMES = {
@@ -94,6 +95,9 @@ def load_library():
     lib.mfem_b200_time_spmv.argtypes = [c_void_p, c_int, dp]
     lib.mfem_b200_apply_preconditioner.argtypes = [c_void_p, dp, dp, dp]
     lib.mfem_b200_get_coarse_array.argtypes = [c_void_p, c_char_p, dp, c_int64, lp]
+    lib.mfem_b200_apply_delta_K.argtypes = [c_void_p, dp, dp, c_int64, dp]
+    lib.mfem_b200_delta_const_strain_load.argtypes = [c_void_p, dp, dp, c_int64, dp]
+    lib.mfem_b200_delta_avg_strain.argtypes = [c_void_p, dp, dp, dp, c_int64, dp]
     lib.mfem_b200_set_matrix_triplets.argtypes = [c_void_p, c_int, c_int64, c_int64, lp, lp, dp, c_int]
     for name in SYMBOLS:
         fn = getattr(lib, name)
@@ -319,6 +323,25 @@ class Handle:
         stress = np.zeros((self.n_elems, F))
         self._check(self.lib.mfem_b200_avg_strain_stress(self._h, _dptr(u), _dptr(strain), _dptr(stress)))
         return strain, stress
+
+    # ---- discrete shape derivatives (per-vertex perturbation delta_p[n_vertices, dim]) ---------------------
+    def apply_delta_K(self, u_nodes, delta_p):
+        u, dpv = _f64(u_nodes), _f64(delta_p)
+        out = np.zeros((self.n_dofs, self.dim))
+        self._check(self.lib.mfem_b200_apply_delta_K(self._h, _dptr(u), _dptr(dpv), dpv.size // self.dim, _dptr(out)))
+        return out
+
+    def delta_const_strain_load(self, eps_flat, delta_p):
+        e, dpv = _f64(eps_flat), _f64(delta_p)
+        out = np.zeros((self.n_dofs, self.dim))
+        self._check(self.lib.mfem_b200_delta_const_strain_load(self._h, _dptr(e), _dptr(dpv), dpv.size // self.dim, _dptr(out)))
+        return out
+
+    def delta_avg_strain(self, u_nodes, delta_u_nodes, delta_p):
+        u, du, dpv = _f64(u_nodes), _f64(delta_u_nodes), _f64(delta_p)
+        out = np.zeros((self.n_elems, flat_len(self.dim)))
+        self._check(self.lib.mfem_b200_delta_avg_strain(self._h, _dptr(u), _dptr(du), _dptr(dpv), dpv.size // self.dim, _dptr(out)))
+        return out
 
     def volumes(self):
         v = np.zeros(self.n_elems)

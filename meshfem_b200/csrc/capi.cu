@@ -583,6 +583,74 @@ int mfem_b200_get_coarse_array(mfem_b200_handle h, const char *name, double *out
     API_END(h)
 }
 
+// ---- discrete shape derivatives (csrc/shape.cu)
+static __global__ void k_max_vertex_node(int64_t nElems, int npe, int nv, const int32_t *__restrict__ elemNodes, int *out) {
+    const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= nElems) return;
+    int m = 0;
+    for (int k = 0; k < nv; ++k) m = max(m, elemNodes[e * npe + k]);
+    atomicMax(out, m);
+}
+// delta_p arrives per VERTEX (the first n_vertices nodes); returns a device copy after checking that no element
+// reads past it
+static void upload_delta_p(mfem_b200_handle h, const double *delta_p, int64_t n_vertices, DevBuf<double> &dp) {
+    MFEM_REQUIRE(h->nElems > 0 && !h->externalMatrix, MFEM_B200_ERR_INVALID, "shape derivatives need a mesh");
+    MFEM_REQUIRE(delta_p && n_vertices > 0 && n_vertices <= h->nNodes, MFEM_B200_ERR_INVALID, "shape derivatives: bad delta_p / n_vertices");
+    if (h->maxVertexNodeVersion != h->meshVersion) {
+        DevBuf<int> m(1);
+        MFEM_CUDA(cudaMemsetAsync(m, 0, sizeof(int), h->stream));
+        k_max_vertex_node<<<grid_for(h->nElems, 256), 256, 0, h->stream>>>(h->nElems, h->npe, h->N + 1, h->elemNodes, m);
+        int hm = 0;
+        MFEM_CUDA(cudaMemcpyAsync(&hm, m, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        MFEM_CUDA(cudaStreamSynchronize(h->stream));
+        h->maxVertexNode = hm;
+        h->maxVertexNodeVersion = h->meshVersion;
+        h->launches++;
+    }
+    MFEM_REQUIRE(h->maxVertexNode < n_vertices, MFEM_B200_ERR_INVALID, "shape derivatives: per-vertex perturbation expected (an element vertex lies beyond n_vertices)");
+    dp.alloc((size_t)n_vertices * h->N);
+    MFEM_CUDA(cudaMemcpyAsync(dp, delta_p, dp.bytes(), cudaMemcpyHostToDevice, h->stream));
+}
+
+int mfem_b200_apply_delta_K(mfem_b200_handle h, const double *u_nodes, const double *delta_p, int64_t n_vertices, double *out_dofs) {
+    API_BEGIN(h)
+    MFEM_REQUIRE(u_nodes && out_dofs, MFEM_B200_ERR_INVALID, "apply_delta_K: null argument");
+    DevBuf<double> dp, u((size_t)h->nNodes * h->N), out((size_t)h->nvar());
+    upload_delta_p(h, delta_p, n_vertices, dp);
+    MFEM_CUDA(cudaMemcpyAsync(u, u_nodes, u.bytes(), cudaMemcpyHostToDevice, h->stream));
+    apply_delta_K(h, u, dp, out);
+    MFEM_CUDA(cudaMemcpyAsync(out_dofs, out, out.bytes(), cudaMemcpyDeviceToHost, h->stream));
+    MFEM_CUDA(cudaStreamSynchronize(h->stream));
+    API_END(h)
+}
+
+int mfem_b200_delta_const_strain_load(mfem_b200_handle h, const double *eps_flat, const double *delta_p, int64_t n_vertices,
+                                      double *out_dofs) {
+    API_BEGIN(h)
+    MFEM_REQUIRE(eps_flat && out_dofs, MFEM_B200_ERR_INVALID, "delta_const_strain_load: null argument");
+    DevBuf<double> dp, out((size_t)h->nvar());
+    upload_delta_p(h, delta_p, n_vertices, dp);
+    delta_const_strain_load(h, eps_flat, dp, out);
+    MFEM_CUDA(cudaMemcpyAsync(out_dofs, out, out.bytes(), cudaMemcpyDeviceToHost, h->stream));
+    MFEM_CUDA(cudaStreamSynchronize(h->stream));
+    API_END(h)
+}
+
+int mfem_b200_delta_avg_strain(mfem_b200_handle h, const double *u_nodes, const double *delta_u_nodes, const double *delta_p,
+                               int64_t n_vertices, double *strain) {
+    API_BEGIN(h)
+    MFEM_REQUIRE(u_nodes && delta_u_nodes && strain, MFEM_B200_ERR_INVALID, "delta_avg_strain: null argument");
+    const size_t nn = (size_t)h->nNodes * h->N;
+    DevBuf<double> dp, u(nn), du(nn), out((size_t)h->nElems * flat_len(h->N));
+    upload_delta_p(h, delta_p, n_vertices, dp);
+    MFEM_CUDA(cudaMemcpyAsync(u, u_nodes, u.bytes(), cudaMemcpyHostToDevice, h->stream));
+    MFEM_CUDA(cudaMemcpyAsync(du, delta_u_nodes, du.bytes(), cudaMemcpyHostToDevice, h->stream));
+    delta_avg_strain(h, u, du, dp, out);
+    MFEM_CUDA(cudaMemcpyAsync(strain, out, out.bytes(), cudaMemcpyDeviceToHost, h->stream));
+    MFEM_CUDA(cudaStreamSynchronize(h->stream));
+    API_END(h)
+}
+
 int mfem_b200_release_cached_memory(void) {
     mfem::pool_release_all();
     return MFEM_B200_OK;

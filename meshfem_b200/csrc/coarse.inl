@@ -762,11 +762,13 @@ static void coarse_choose_refinement(int N, const double *L, const int *b, int64
         if (L[k] > 0.0) r[k] = (int)std::max<int64_t>(1, std::llround(L[k] / b[k] / h1));
 }
 
-// requested number of large boxes: explicit (> 0), or automatic (-1): one per ~3500 DoFs, 16..2048, none below 30k DoFs
+// requested number of large boxes: explicit (> 0), or automatic (-1): one per ~400 DoFs (nodes), 16..2048, none below
+// 30k DoFs.  Measured: 92,785 nodes: 26 boxes 414 iterations, 256 boxes 170 (block-Jacobi 1240); cfg5 (14.65 M nodes):
+// 1024 / 2048 / 4096 boxes 307 / 254 / 213 iterations, but the dense inverse grows like boxes^3 (37 / 131 / 738 ms).
 static int64_t coarse_budget(mfem_b200_ctx *c, int64_t nDofsGlobal) {
     if (c->opt_coarse > 0) return c->opt_coarse;
     if (c->opt_coarse == 0 || nDofsGlobal < 30000) return 0;
-    return std::max<int64_t>(16, std::min<int64_t>(2048, nDofsGlobal / 3500));
+    return std::max<int64_t>(16, std::min<int64_t>(2048, nDofsGlobal / 400));
 }
 
 // Box grids, slots, centred positions (1..N ranks; on one rank the exchange is a no-op).

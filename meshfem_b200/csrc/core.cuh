@@ -108,6 +108,7 @@ struct mfem_b200_ctx {
     int opt_coarse = -1;                   // large aggregates of the multilevel preconditioner: -1 automatic (from the
                                            // problem size; block-Jacobi only below 30k DoFs), 0 = block-Jacobi only
     int opt_coarse_fine = 64;              // DoFs (nodes) per small (level-1) aggregate; 0 = no level 1 (two-level method)
+    int64_t maxVertexNode = -1, maxVertexNodeVersion = -1;   // largest node id in a vertex slot of elemNodes (shape derivatives)
     int64_t meshVersion = 0;               // bumped by everything that changes DoFs, positions or the interface
 
     // mesh
@@ -270,5 +271,9 @@ void apply_K_nodes(mfem_b200_ctx *c, const double *u_nodes_dev, double *Ku_nodes
 void const_strain_load(mfem_b200_ctx *c, const double *epsFlatHost, double *f_ext_dev);
 void avg_strain_stress(mfem_b200_ctx *c, const double *u_nodes_dev, double *strain_dev, double *stress_dev);
 void export_bsr(mfem_b200_ctx *c, int64_t *rowptr, int32_t *colidx, double *vals);
+// shape.cu (discrete shape derivatives; device pointers, per node / per DoF in the caller's numbering)
+void apply_delta_K(mfem_b200_ctx *c, const double *u_nodes, const double *deltaP_nodes, double *out_dofs);
+void delta_const_strain_load(mfem_b200_ctx *c, const double *epsFlatHost, const double *deltaP_nodes, double *out_dofs);
+void delta_avg_strain(mfem_b200_ctx *c, const double *u_nodes, const double *du_nodes, const double *deltaP_nodes, double *out);
 
 }  // namespace mfem

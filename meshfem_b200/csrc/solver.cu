@@ -251,12 +251,13 @@ __device__ __forceinline__ void gather3(const double *x0, const double *x1, cons
         : "memory");
 }
 
-// PF = true: every lane also issues ONE `prefetch.global.L2` per row iteration for the row this warp will stream in
-// its NEXT iteration (its extent is fetched two iterations ahead): lane l touches the l-th 128-byte line of that row's
-// values (32 lines = 4 KB = 56 blocks; longer rows lose their tail) and lanes 0..2 a line of its column indices.
-// The prefetch needs no destination registers, so the DRAM round trip of row k+1 overlaps all of row k's work at no
-// occupancy cost; the streaming loads then hit L2.
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// PF = true: the first lane of a row also issues two bulk L2 prefetches (cp.async.bulk.prefetch.L2: values, column
+// indices) per row iteration for the row this warp will stream in its NEXT iteration (its extent is fetched two
+// iterations ahead).  The prefetch needs no destination registers, so the DRAM round trip of row k+1 overlaps all of
+// row k's work at no occupancy cost; the streaming loads then hit L2.
+__device__ __forceinline__ void bulk_prefetch_l2(const void *p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 
 template <int N, int LPR, bool MASKED, bool DOT, bool PF, int MINB = 4>
 __global__ void __launch_bounds__(kSpmvThreads, MINB)   // MINB = 4: <= 64 registers, 32 resident warps per SM
@@ -302,11 +303,16 @@ k_bsr_spmv(int64_t nb, const int64_t *__restrict__ rowptr, const int32_t *__rest
         if (PF) {
             // row k+1: extent known since the previous iteration -> prefetch its lines now; row k+2: fetch the extent
             nb0 = pb0; nb1 = pb0 + pn;
-            if (pn > 0) {
-                const char *pv = reinterpret_cast<const char *>(vals + pb0 * NN) + sl * 128 * (32 / LPR);
-                if (sl * 128 * (32 / LPR) < pn * NN * 8) prefetch_l2(pv);
-                if (LPR < 32 && sl * 128 * (32 / LPR) + 128 < pn * NN * 8) prefetch_l2(pv + 128);
-                if (sl * 128 < pn * 4) prefetch_l2(reinterpret_cast<const char *>(colidx + pb0) + sl * 128);
+            if (pn > 0 && sl == 0) {
+                // ONE bulk L2 prefetch per array and row, issued by the row's first lane: handled by the copy engine, no
+                // L1 wavefronts (a per-lane prefetch.global.L2 of 32 lines costs 32 L1 transactions per row and made
+                // the kernel 10 % slower)
+                const uintptr_t v0 = reinterpret_cast<uintptr_t>(vals + pb0 * NN) & ~uintptr_t(15);
+                const uintptr_t v1 = (reinterpret_cast<uintptr_t>(vals + (pb0 + pn) * NN) + 15) & ~uintptr_t(15);
+                const uintptr_t c0 = reinterpret_cast<uintptr_t>(colidx + pb0) & ~uintptr_t(15);
+                const uintptr_t c1 = (reinterpret_cast<uintptr_t>(colidx + pb0 + pn) + 15) & ~uintptr_t(15);
+                bulk_prefetch_l2(reinterpret_cast<const void *>(v0), (uint32_t)(v1 - v0));
+                bulk_prefetch_l2(reinterpret_cast<const void *>(c0), (uint32_t)(c1 - c0));
             }
             pb0 = 0; pn = 0;
             if (row + rowStride < nb) { pb0 = rowptr[row + rowStride]; pn = (int)(rowptr[row + rowStride + 1] - pb0); }

@@ -91,71 +91,117 @@ def main():
         rz = rzn
     u = (x + ufix).reshape(-1, N)
 
-    # ---- two-level variant, exactly the multi-GPU algorithm of csrc/coarse.inl (build_coarse_indexed_impl): box aggregates
-    # over the OWNED DoFs of each rank, owner's
-    # aggregate id and centred position sent to the sharers by a sum-exchange in which only the owner contributes,
-    # E = all-reduce of Z_loc' K_loc Z_loc, restriction over owned DoFs + all-reduce, replicated coarse solve,
-    # prolongation on every local DoF, r.z corrected by c.y after its all-reduce.
-    Sr, M = 8, 6
-    S = Sr * world
+    # ---- multilevel variant, exactly the multi-GPU algorithm of csrc/coarse.inl + solver.cu (enqueue_iteration):
+    # nested box grids over the OWNED DoFs of each rank; DoFs shared between ranks take no part in level 1 and hang on
+    # their OWNER's large box ("pass-through" slots; owner's large id and centred position sent to the sharers by a
+    # sum-exchange in which only the owner contributes); E2 = all-reduce of Z2_loc' K_loc Z2_loc; the dense level is
+    # ROW-SPLIT (every rank holds the rows of E2^-1 of its own large boxes, computes its slice of y2, one all-gather);
+    # per iteration TWO all-reduces: p.Ap = sum over ranks of the LOCAL products p_loc.(K_loc p_loc) over all local
+    # rows, and (r.z, r.r, c2) together.
+    import scipy.sparse as sp
+    import emulate_multilevel as em
+    Sr, M, fine = 8, 6, 10
+    S2 = Sr * world
     X = p.nodes
     own_n = p.owned.astype(bool)
-    # near-cubic boxes over the bounding box of the OWNED nodes, at most Sr of them (coarse_choose_boxes / k_coarse_box_agg)
+    shared_n = np.zeros(p.num_nodes, bool)
+    for q_ in p.neighbor_ranks:
+        shared_n[p.shared[int(q_)]] = True
     lo, hi = X[own_n].min(0), X[own_n].max(0)
     L = hi - lo
-    h = (np.prod(L[L > 0]) / Sr) ** (1.0 / (L > 0).sum())
-    bx = [int(max(1, np.floor(l / h + 0.5))) if l > 0 else 1 for l in L]
-    while np.prod(bx) > Sr:
-        k = int(np.argmax(bx))
-        if bx[k] == 1:
-            break
-        bx[k] -= 1
-    scale = np.where(L > 0, np.array(bx) / np.where(L > 0, L, 1.0), 0.0)
-    q = np.clip(np.floor((X - lo) * scale).astype(np.int64), 0, np.array(bx) - 1)
-    box = (q[:, 0] * bx[1] + q[:, 1]) * bx[2] + q[:, 2]
-    agg = np.where(own_n, rank * Sr + box, -1)
+    bgrid = np.array(em.choose_boxes(L, Sr))
+    rgrid = np.array(em.choose_refinement(L, bgrid, int(own_n.sum()), fine))
+    scale1 = np.where(L > 0, bgrid * rgrid / np.where(L > 0, L, 1.0), 0.0)
+    qq = np.clip(np.floor((X - lo) * scale1).astype(np.int64), 0, bgrid * rgrid - 1)
+    big = np.zeros(p.num_nodes, np.int64); loc = np.zeros(p.num_nodes, np.int64)
+    for k in range(3):
+        big = big * bgrid[k] + qq[:, k] // rgrid[k]
+        loc = loc * rgrid[k] + qq[:, k] % rgrid[k]
+    Rr = int(np.prod(rgrid)); nBoxes = int(np.prod(bgrid))
+    assert Rr > 1 and nBoxes <= Sr
+    S1 = nBoxes * Rr
+    aggBase = rank * Sr
+    elig = own_n & ~shared_n                                 # level 1: owned, not shared
     T = np.zeros((p.num_nodes, 4))
-    cen = np.zeros((Sr, 4))
-    np.add.at(cen, agg[own_n] - rank * Sr, np.hstack([X[own_n], np.ones((int(own_n.sum()), 1))]))
-    T[own_n, 0] = agg[own_n] + 1
-    T[own_n, 1:] = X[own_n] - (cen[:, :3] / np.maximum(cen[:, 3:], 1))[agg[own_n] - rank * Sr]
+    cen2 = np.zeros((Sr, 4))
+    np.add.at(cen2, big[own_n], np.hstack([X[own_n], np.ones((int(own_n.sum()), 1))]))
+    c2pos = cen2[:, :3] / np.maximum(cen2[:, 3:], 1)
+    T[own_n, 0] = aggBase + big[own_n] + 1
+    T[own_n, 1:] = X[own_n] - c2pos[big[own_n]]
     T = exchange_add(T.reshape(-1).copy(), 4).reshape(p.num_nodes, 4)
-    agg = np.rint(T[:, 0]).astype(np.int64) - 1
-    assert agg.min() >= 0 and agg.max() < S
-    Y = T[:, 1:]
-    R = np.zeros((p.num_nodes, N, M))
-    R[:, 0, 0] = R[:, 1, 1] = R[:, 2, 2] = 1.0
-    R[:, 1, 3], R[:, 2, 3] = -Y[:, 2], Y[:, 1]
-    R[:, 0, 4], R[:, 2, 4] = Y[:, 2], -Y[:, 0]
-    R[:, 0, 5], R[:, 1, 5] = -Y[:, 1], Y[:, 0]
-    import scipy.sparse as sp
+    agg2 = np.rint(T[:, 0]).astype(np.int64) - 1
+    assert agg2.min() >= 0 and agg2.max() < S2
+    Y2 = T[:, 1:]
+    slot_small = big * Rr + loc
+    cen1 = np.zeros((S1, 4))
+    np.add.at(cen1, slot_small[elig], np.hstack([X[elig], np.ones((int(elig.sum()), 1))]))
+    has1 = cen1[:, 3] > 0
+    shift = np.where((has1 & (cen2[np.arange(S1) // Rr, 3] > 0))[:, None],
+                     cen1[:, :3] / np.maximum(cen1[:, 3:], 1) - c2pos[np.arange(S1) // Rr], 0.0)
+    slot = np.where(elig, slot_small, S1 + agg2)
+    Y1 = np.where(elig[:, None], Y2 - shift[np.minimum(slot_small, S1 - 1)], Y2)
+    n1 = S1 + S2
+    fm6 = np.repeat(free, M)
     rows = np.repeat(np.arange(n), M)
-    cols = (M * np.repeat(agg, N)[:, None] + np.arange(M)[None, :]).reshape(-1)
-    Z = sp.csr_matrix((R.reshape(-1) * np.repeat(free, M), (rows, cols)), shape=(n, M * S))
-    Et = torch.from_numpy((Z.T @ K @ Z).toarray())
+    P1 = sp.csr_matrix((em.rigid(Y1).reshape(-1) * fm6, (rows, (M * np.repeat(slot, N)[:, None] + np.arange(M)[None, :]).reshape(-1))),
+                       shape=(n, M * n1))
+    # P2: level-1 slots -> large boxes (global ids); small slots through the shift, pass-through slots by identity
+    blocks = np.zeros((n1, M, M))
+    for mm in range(M):
+        e = np.zeros((S1, M)); e[:, mm] = 1.0
+        blocks[:S1, :, mm] = em.shift_prolong(shift, e)
+    blocks[S1:] = np.eye(M)
+    parent = np.concatenate([aggBase + np.arange(S1) // Rr, np.arange(S2)])
+    P2 = sp.csr_matrix((blocks.reshape(-1), (np.repeat(np.arange(M * n1), M), (M * np.repeat(parent, M)[:, None] + np.arange(M)[None, :]).reshape(-1))),
+                       shape=(M * n1, M * S2))
+    Z2 = (P1 @ P2).tocsr()
+    # the rows of Z2 must agree on all sharers: the large boxes' rigid modes at the owner's centred positions
+    rows2 = np.repeat(np.arange(n), M)
+    Z2direct = sp.csr_matrix((em.rigid(Y2).reshape(-1) * fm6, (rows2, (M * np.repeat(agg2, N)[:, None] + np.arange(M)[None, :]).reshape(-1))),
+                             shape=(n, M * S2))
+    assert abs(Z2 - Z2direct).max() < 1e-12
+    Et = torch.from_numpy((Z2.T @ K @ Z2).toarray())
     dist.all_reduce(Et)
     E = Et.numpy()
     d = np.diag(E).copy()
     E[np.diag_indices_from(E)] = np.where(d == 0.0, 1.0, d * (1 + 1e-8))
-    Einv = np.linalg.inv(E)
-    Zown = sp.diags(owned.astype(float)) @ Z
+    EinvRows = np.linalg.inv(E)[aggBase * M:(aggBase + Sr) * M]           # row-split dense level
+    K1 = (P1.T @ K @ P1).tobsr((M, M)); K1.sort_indices()
+    B1inv = np.zeros((n1, M, M))
+    for s_ in range(S1):
+        cols = K1.indices[K1.indptr[s_]:K1.indptr[s_ + 1]]
+        k = np.searchsorted(cols, s_)
+        if k < cols.size and cols[k] == s_:
+            blk = K1.data[K1.indptr[s_] + k]
+            B1inv[s_] = em.dropping_cholesky_inverse(0.5 * (blk + blk.T))
 
-    def coarse(rv):
-        ct = torch.from_numpy(Zown.T @ rv); dist.all_reduce(ct)
-        cv = ct.numpy(); yv = Einv @ cv
-        return Z @ yv, float(cv @ yv)
+    def precond(rv):
+        """(z, r.z, r.r) with ONE all-reduce of (r.z_local, r.r_local, c2) and one all-gather of y2."""
+        zB = apply_M(rv)
+        c1 = (P1.T @ (rv * owned)).reshape(n1, M)
+        y1 = np.einsum("sab,sb->sa", B1inv, c1)
+        red = np.concatenate([[rv[owned] @ zB[owned] + float((c1 * y1).sum()), rv[owned] @ rv[owned]], P2.T @ c1.reshape(-1)])
+        t = torch.from_numpy(red); dist.all_reduce(t)
+        red = t.numpy()
+        c2v = red[2:]
+        y2loc = torch.from_numpy(EinvRows @ c2v)
+        parts = [torch.zeros_like(y2loc) for _ in range(world)]
+        dist.all_gather(parts, y2loc)
+        y2 = np.concatenate([x_.numpy() for x_ in parts])
+        qv = y1.reshape(-1) + P2 @ y2
+        return zB + P1 @ qv, red[0] + float(c2v @ y2), red[1]
 
-    x = np.zeros(n); r = b.copy(); z = apply_M(r)
-    rz = gsum(r[owned] @ z[owned]); zc, cy = coarse(r); z = z + zc; rz += cy
+    x = np.zeros(n); r = b.copy()
+    z, rz, _ = precond(r)
     pvec = z.copy()
     its2 = 0
     while its2 < 5000:
-        Ap = spmv(pvec)
-        alpha = rz / gsum(pvec[owned] @ Ap[owned])
+        Aloc = (K @ pvec) * free                               # local product, before the exchange
+        pAp = gsum(float(pvec @ Aloc))                         # all local rows, no owner mask: K = sum of the ranks' K_loc
+        Ap = exchange_add(Aloc.copy(), N)
+        alpha = rz / pAp
         x += alpha * pvec; r -= alpha * Ap
-        z = apply_M(r)
-        rzn = gsum(r[owned] @ z[owned]); rr = gsum(r[owned] @ r[owned])
-        zc, cy = coarse(r); z = z + zc; rzn += cy
+        z, rzn, rr = precond(r)
         its2 += 1
         if rr <= 1e-24 * bb:
             break
@@ -168,7 +214,7 @@ def main():
     err = float(np.linalg.norm(u - u_ref) / np.linalg.norm(u_ref))
     err2 = float(np.linalg.norm(u2 - u_ref) / np.linalg.norm(u_ref))
     t2 = torch.tensor([err2], dtype=torch.float64); dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-    assert t2.item() < 1e-8 and its2 < 0.8 * its, (t2.item(), its, its2)
+    assert t2.item() < 1e-8 and its2 < 0.6 * its, (t2.item(), its, its2)
     t = torch.tensor([err], dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX)
     nowned = gsum(float(p.owned.sum()))
     if rank == 0:

@@ -127,12 +127,36 @@ def test_box_grid_choice():
                 assert edges[multi].max() / edges[multi].min() < 2.5
 
 
-def test_emulated_two_level_pcg_needs_far_fewer_iterations():
-    """tools/emulate_two_level.py: the device algorithm (box aggregates, masked rigid modes, regularised dense E,
-    additive correction with r.z += c.y) restated in numpy, on a small linear-tet cantilever."""
+def test_emulated_multilevel_pcg_needs_far_fewer_iterations():
+    """tools/emulate_multilevel.py: the device algorithm (nested box grids, masked rigid modes, level-1 6x6 blocks with
+    dropped dead modes, regularised dense E, additive terms with r.z = r.B0^-1 r + c1.y1 + c2.y2, level 1 <-> 2 through
+    the shift formulas) restated in numpy, on a small linear-tet cantilever: large boxes alone, then with level 1."""
     import os
     import sys
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
-    from emulate_two_level import run
-    it0, it1 = run(3, 1, (16, 4, 4), 32, verbose=False)
-    assert it1 < 0.5 * it0, (it0, it1)
+    from emulate_multilevel import run
+    it0, it2, it3 = run(3, 1, (16, 4, 4), 8, 12, verbose=False)
+    assert it2 < 0.6 * it0 and it3 < it2, (it0, it2, it3)
+
+
+def test_level_transfer_formulas_compose_to_the_large_box_modes():
+    """coarse_shift_prolong / coarse_shift_restrict (restated in tools/emulate_multilevel.py): the rigid modes of a large
+    box are exact combinations of the modes of its small boxes, R1(y1) P2(d) = R2(y1 + d), and the restriction is the
+    transpose; the dropping Cholesky inverse (k_coarse_invert1) inverts the live principal submatrix."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import emulate_multilevel as em
+    rng = np.random.default_rng(3)
+    for N, M in ((3, 6), (2, 3)):
+        y1, d, Yc, v = rng.standard_normal((5, N)), rng.standard_normal((5, N)), rng.standard_normal((5, M)), rng.standard_normal((5, N))
+        q = em.shift_prolong(d, Yc)
+        R1, R2 = em.rigid(y1), em.rigid(y1 + d)
+        assert np.allclose(np.einsum("ncm,nm->nc", R1, q), np.einsum("ncm,nm->nc", R2, Yc))
+        c1 = np.einsum("ncm,nc->nm", R1, v)
+        assert np.allclose(em.shift_restrict(d, c1), np.einsum("ncm,nc->nm", R2, v))
+    G = rng.standard_normal((6, 6)); S = G @ G.T + 0.1 * np.eye(6)
+    assert np.abs(em.dropping_cholesky_inverse(S) @ S - np.eye(6)).max() < 1e-12
+    S[2, :] = 0; S[:, 2] = 0
+    B = em.dropping_cholesky_inverse(S); live = [0, 1, 3, 4, 5]
+    assert np.abs(B[np.ix_(live, live)] @ S[np.ix_(live, live)] - np.eye(5)).max() < 1e-12 and np.abs(B[2]).max() == 0.0
