@@ -67,6 +67,16 @@ int mfem_b200_comm_init(mfem_b200_handle h, int n_ranks, int rank, const void *n
 /* Put h on the communicator of `parent` (same process, same device) instead of creating another one:
  * a long-lived parent handle plays the role of the process group; parent must outlive h.      */
 int mfem_b200_comm_share(mfem_b200_handle h, mfem_b200_handle parent);
+/* Peer window (one NVSwitch box, <= 8 ranks): after comm_init every rank allocates a window of device memory
+ * (comm_window_handle returns its 64-byte CUDA IPC handle), the caller gathers the handles of all ranks in rank order
+ * and every rank maps them (comm_window_open).  From then on the small collectives of the PCG iteration -- the interface
+ * sum-exchange, the all-reduces of the dot products / coarse residuals, the all-gather of the row-split dense level --
+ * are single kernels of this library that store into the peers' windows over NVLink and synchronise through flag words
+ * (csrc/comm.cu), not NCCL calls; NCCL keeps the large set-up all-reduce and is the fallback if IPC mapping is refused
+ * on any rank (comm_uses_peer_window then returns 0) or option "comm_p2p" is 0.                                  */
+int mfem_b200_comm_window_handle(mfem_b200_handle h, void *out64);
+int mfem_b200_comm_window_open(mfem_b200_handle h, const void *handles_rank_order);
+int mfem_b200_comm_uses_peer_window(mfem_b200_handle h);
 
 /* ---- options (before set_mesh) --------------------------------------------------- */
 /* "reorder": 1 (default) renumbers DoFs along a space-filling curve inside the handle;

@@ -26,6 +26,7 @@ SYMBOLS = [
     "mfem_b200_avg_strain_stress", "mfem_b200_get_volumes", "mfem_b200_get_timer", "mfem_b200_reset_timers",
     "mfem_b200_launch_count", "mfem_b200_time_spmv", "mfem_b200_set_matrix_triplets", "mfem_b200_comm_share",
     "mfem_b200_apply_preconditioner", "mfem_b200_get_coarse_array", "mfem_b200_release_cached_memory",
+    "mfem_b200_comm_window_handle", "mfem_b200_comm_window_open", "mfem_b200_comm_uses_peer_window",
     "mfem_b200_apply_delta_K", "mfem_b200_delta_const_strain_load", "mfem_b200_delta_avg_strain",
 ]
 
@@ -69,6 +70,9 @@ def load_library():
     lib.mfem_b200_comm_unique_id.argtypes = [c_void_p]
     lib.mfem_b200_comm_init.argtypes = [c_void_p, c_int, c_int, c_void_p]
     lib.mfem_b200_comm_share.argtypes = [c_void_p, c_void_p]
+    lib.mfem_b200_comm_window_handle.argtypes = [c_void_p, c_void_p]
+    lib.mfem_b200_comm_window_open.argtypes = [c_void_p, c_void_p]
+    lib.mfem_b200_comm_uses_peer_window.argtypes = [c_void_p]
     lib.mfem_b200_set_option.argtypes = [c_void_p, c_char_p, c_int64]
     lib.mfem_b200_set_mesh.argtypes = [c_void_p, c_int, c_int, c_int64, dp, c_int64, ip, lp, c_int64]
     lib.mfem_b200_set_interface.argtypes = [c_void_p, c_int, ip, lp, ip, POINTER(ctypes.c_uint8)]
@@ -175,6 +179,20 @@ class Handle:
         """Use the communicator of `parent` (a long-lived handle of this process) instead of creating one."""
         self._check(self.lib.mfem_b200_comm_share(self._h, parent._h))
         self._comm_parent = parent          # keep it alive
+
+    def comm_window_handle(self) -> bytes:
+        """Allocate this rank's peer window and return its 64-byte CUDA IPC handle (after comm_init)."""
+        buf = ctypes.create_string_buffer(64)
+        self._check(self.lib.mfem_b200_comm_window_handle(self._h, buf))
+        return buf.raw
+
+    def comm_window_open(self, handles_rank_order: bytes):
+        """Map the windows of all ranks (their IPC handles concatenated in rank order)."""
+        buf = ctypes.create_string_buffer(handles_rank_order, len(handles_rank_order))
+        self._check(self.lib.mfem_b200_comm_window_open(self._h, buf))
+
+    def comm_uses_peer_window(self) -> bool:
+        return bool(self.lib.mfem_b200_comm_uses_peer_window(self._h))
 
     @staticmethod
     def comm_unique_id() -> bytes:

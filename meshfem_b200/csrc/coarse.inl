@@ -604,6 +604,59 @@ __global__ void __launch_bounds__(256) k_coarse_cy(int64_t nc, const double *__r
     if (threadIdx.x == 0) { out[0] = red[0] + sh[0]; out[1] = red[1]; }
 }
 
+// N ranks with the peer window: this rank's rows of y2 = E2^-1 c2, every row stored straight into ALL ranks' windows
+// (lane q of the row's warp stores to rank q); the last CTA publishes the sequence number to the peers.
+__global__ void __launch_bounds__(kVecThreads)
+k_coarse_gemv_ship(PeerWin w, int64_t nc, int64_t rowBase, int64_t nRows, const double *__restrict__ Einv, const double *__restrict__ red,
+                   unsigned *ticket, const int *status) {
+    if (status && status[ST_STATE] != 0) return;
+    const double *c2 = red + 2;
+    const unsigned long long sq = *w.seq(SET_AG) + 1;
+    const int phase = (int)(sq & 1);
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nWarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t row = warp; row < nRows; row += nWarps) {
+        const double *e = Einv + row * nc;
+        double s0 = 0.0, s1 = 0.0;
+        int64_t k = lane;
+        for (; k + 32 < nc; k += 64) { s0 = fma(e[k], c2[k], s0); s1 = fma(e[k + 32], c2[k + 32], s1); }
+        if (k < nc) s0 = fma(e[k], c2[k], s0);
+        double s = s0 + s1;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane < w.R) w.ag(lane, phase)[rowBase + row] = s;
+    }
+    __threadfence_system();
+    if (last_block(ticket)) {
+        if ((int)threadIdx.x < w.R) peer_publish(w.flags(threadIdx.x, SET_AG) + w.rank, sq);
+    }
+}
+// one CTA: wait for every rank's rows, copy the gathered y2 out of the window, out[0] = red[0] + c2.y2 in a fixed order
+// (every rank holds the same c2 and y2, hence the same bits), out[1] = red[1]; advances the all-gather sequence number
+__global__ void __launch_bounds__(1024)
+k_coarse_cy_gather(PeerWin w, int64_t nc, const double *__restrict__ red, double *__restrict__ y2, double *out, const int *status) {
+    if (status && status[ST_STATE] != 0) return;
+    __shared__ double sh[1024];
+    const unsigned long long sq = *w.seq(SET_AG) + 1;
+    const int phase = (int)(sq & 1);
+    if ((int)threadIdx.x < w.R && !peer_wait(w.flags(w.rank, SET_AG) + threadIdx.x, sq)) *w.err() = 1;
+    __syncthreads();
+    const double *c2 = red + 2, *g = w.ag(w.rank, phase);
+    double s = 0.0;
+    for (int64_t k = threadIdx.x; k < nc; k += 1024) {
+        const double y = g[k];
+        y2[k] = y;
+        s = fma(c2[k], y, s);
+    }
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 512; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { out[0] = red[0] + sh[0]; out[1] = red[1]; *w.seq(SET_AG) = sq; }
+}
+
 // coarse part of z for DoF i: R1_i (y1[slot] + P2 y2[large box])
 template <int N>
 __device__ __forceinline__ void coarse_prolong_dof(int64_t i, const int32_t *__restrict__ agg1, const double *__restrict__ Y1,

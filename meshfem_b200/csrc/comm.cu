@@ -14,6 +14,7 @@
 #include <algorithm>
 
 #include "core.cuh"
+#include "peer.cuh"
 
 namespace mfem {
 
@@ -32,6 +33,11 @@ struct Halo {
     DevBuf<double> sendBuf, recvBuf;     // total * maxWidth doubles
     int64_t total = 0;
     int maxWidth = 9;
+    // peer-window path
+    DevBuf<int32_t> nbrRankDev;          // [nNeighbors]
+    DevBuf<int64_t> offsetsDev;          // [nNeighbors+1]
+    DevBuf<int64_t> uWin;                // [total] sender * kHaloSegCap + slot inside the sender's segment, in uPtr order
+    bool p2pFits = false;                // every neighbour segment fits its window slot
 };
 
 #define MFEM_NCCL(call)                                                                              \
@@ -40,6 +46,198 @@ struct Halo {
         if (r_ != ncclSuccess)                                                                       \
             throw mfem::CudaError(MFEM_B200_ERR_COMM, std::string(#call) + ": " + ncclGetErrorString(r_)); \
     } while (0)
+
+// ---------------------------------------------------------------------------------------------------------------
+// Peer window: the small collectives of the PCG iteration done by OUR kernels over NVLink peer memory instead of NCCL.
+//
+// Every rank owns one device buffer (the "window") that all other ranks of the box map through CUDA IPC
+// (mfem_b200_comm_window_handle / _open).  A collective is ONE kernel per rank: it stores this rank's contribution
+// straight into the peers' windows (P2P stores over NVLink / NVSwitch), publishes a sequence number in the peers' flag
+// words (system-scope fence before it), waits until the flags of the ranks it depends on show the same sequence number,
+// and finishes from LOCAL memory -- sums the R slots in rank order (all-reduce: every rank adds the same numbers in the
+// same order, so all ranks hold the same bits), copies them (all-gather), or adds the neighbours' interface values
+// (halo).  No launch of a communication library, no proxy thread, no ring: two NVLink hops of latency per collective.
+// Data slots are double-buffered by the parity of the sequence number: a rank can run at most one collective ahead of a
+// peer (it needs that peer's next flag to go further), so a slot is never overwritten while it is still being read.
+// A spin that lasts longer than ~2 s sets the window's error word (the host turns it into MFEM_B200_ERR_COMM).
+// NCCL stays underneath for everything large (the coarse-matrix all-reduce at set-up) and as the fallback when the
+// window is not available (option comm_p2p = 0, IPC refused, a message larger than its region).
+struct PeerWinOwner {                             // host side: owns the local allocation and the IPC mappings
+    PeerWin w;
+    void *local = nullptr;
+    void *mapped[kPeerMax] = {};
+    bool open = false;
+    ~PeerWinOwner() {
+        for (int r = 0; r < kPeerMax; ++r) if (mapped[r]) cudaIpcCloseMemHandle(mapped[r]);
+        if (local) cudaFree(local);
+    }
+};
+
+// all-reduce (sum) of n <= kArCap doubles; grid = R blocks: block q ships my vector to rank q, then (after everybody's
+// flag arrived) reduces the q-th slice of the result.  in == out allowed.
+__global__ void __launch_bounds__(1024)
+k_peer_allreduce(PeerWin w, const double *in, double *out, int n, unsigned *ticket, const int *status) {
+    if (status && status[1] != 0) return;
+    const int q = blockIdx.x;
+    const unsigned long long s = *w.seq(SET_AR) + 1;
+    const int phase = (int)(s & 1);
+    double *dst = w.ar(q, phase, w.rank);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = in[i];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        peer_publish(w.flags(q, SET_AR) + w.rank, s);
+        atomicAdd(w.arrive(), 1ull);              // this block is done reading `in` (which may alias `out`)
+    }
+    // everybody's contribution has landed here, and all MY blocks have read `in`: R blocks per call, s calls so far
+    if ((int)threadIdx.x < w.R && !peer_wait(w.flags(w.rank, SET_AR) + threadIdx.x, s)) *w.err() = 1;
+    if ((int)threadIdx.x == w.R && !peer_wait(w.arrive(), (unsigned long long)w.R * s)) *w.err() = 1;
+    __syncthreads();
+    const int per = (n + w.R - 1) / w.R, lo = q * per, hi = min(n, lo + per);
+    for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        double t = 0.0;
+        for (int r = 0; r < w.R; ++r) t += w.ar(w.rank, phase, r)[i];
+        out[i] = t;
+    }
+    peer_finish(w, SET_AR, s, ticket);
+}
+
+// in-place all-gather: rank r owns buf[r*count .. (r+1)*count); grid = R blocks
+__global__ void __launch_bounds__(1024)
+k_peer_allgather(PeerWin w, double *buf, int count, unsigned *ticket, const int *status) {
+    if (status && status[1] != 0) return;
+    const int q = blockIdx.x;
+    const unsigned long long s = *w.seq(SET_AG) + 1;
+    const int phase = (int)(s & 1);
+    double *dst = w.ag(q, phase) + (size_t)w.rank * count;
+    const double *src = buf + (size_t)w.rank * count;
+    for (int i = threadIdx.x; i < count; i += blockDim.x) dst[i] = src[i];
+    __syncthreads();
+    if (threadIdx.x == 0) peer_publish(w.flags(q, SET_AG) + w.rank, s);
+    if ((int)threadIdx.x < w.R && !peer_wait(w.flags(w.rank, SET_AG) + threadIdx.x, s)) *w.err() = 1;
+    __syncthreads();
+    if (q != w.rank) {
+        const double *g = w.ag(w.rank, phase) + (size_t)q * count;
+        for (int i = threadIdx.x; i < count; i += blockDim.x) buf[(size_t)q * count + i] = g[i];
+    }
+    peer_finish(w, SET_AG, s, ticket);
+}
+
+// interface exchange, sender side: block b packs the values of the DoFs shared with neighbour b straight into that
+// neighbour's window (slot of sender = my rank) and publishes the sequence number there
+__global__ void __launch_bounds__(1024)
+k_peer_halo_send(PeerWin w, int nNbr, const int32_t *__restrict__ nbrRank, const int64_t *__restrict__ offsets, int width,
+                 const int32_t *__restrict__ idx, const double *__restrict__ vec, unsigned *ticket, const int *status) {
+    if (status && status[1] != 0) return;
+    const int b = blockIdx.x;
+    const unsigned long long s = *w.seq(SET_HALO) + 1;
+    const int phase = (int)(s & 1);
+    const int q = nbrRank[b];
+    const int64_t off = offsets[b], cnt = (offsets[b + 1] - off) * width;
+    double *dst = w.halo(q, phase, w.rank);
+    for (int64_t t = threadIdx.x; t < cnt; t += blockDim.x) {
+        const int64_t k = t / width;
+        dst[t] = vec[(int64_t)idx[off + k] * width + (t - k * width)];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) peer_publish(w.flags(q, SET_HALO) + w.rank, s);
+    (void)nNbr;
+    (void)ticket;
+}
+// receiver side: wait for every neighbour's flag, then add the received partial sums of every distinct shared DoF in
+// list order; the last block advances the sequence number
+__global__ void __launch_bounds__(256)
+k_peer_halo_recv(PeerWin w, int nNbr, const int32_t *__restrict__ nbrRank, int64_t nUnique, int width,
+                 const int32_t *__restrict__ uIdx, const int64_t *__restrict__ uPtr, const int64_t *__restrict__ uWin /* sender * kHaloSegCap + local slot */,
+                 double *__restrict__ vec, unsigned *ticket, const int *status) {
+    if (status && status[1] != 0) return;
+    const unsigned long long s = *w.seq(SET_HALO) + 1;
+    const int phase = (int)(s & 1);
+    if ((int)threadIdx.x < nNbr && !peer_wait(w.flags(w.rank, SET_HALO) + nbrRank[threadIdx.x], s)) *w.err() = 1;
+    __syncthreads();
+    const double *base = w.halo(w.rank, phase, 0);
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t < nUnique * width) {
+        const int64_t u = t / width;
+        const int c = (int)(t - u * width);
+        double acc = 0.0;
+        for (int64_t k = uPtr[u]; k < uPtr[u + 1]; ++k) {
+            const int64_t wpos = uWin[k];
+            const int64_t sender = wpos / kHaloSegCap, slot = wpos - sender * kHaloSegCap;
+            acc += base[sender * kHaloSegCap + slot * width + c];
+        }
+        vec[(int64_t)uIdx[u] * width + c] += acc;
+    }
+    peer_finish(w, SET_HALO, s, ticket);
+}
+
+// The multi-rank PCG iteration's first communication step as ONE kernel: the interface sum-exchange of Ap AND the
+// all-reduce of the scalar p.Ap.  Blocks [0, nNbr) are the senders (as k_peer_halo_send), block nNbr all-reduces the
+// scalar over the window's all-reduce slots (one double per rank, summed in rank order), the remaining blocks are the
+// receivers (as k_peer_halo_recv).  Senders never wait on receivers, so residency order cannot deadlock.
+__global__ void __launch_bounds__(256)
+k_peer_halo_fused(PeerWin w, int nNbr, const int32_t *__restrict__ nbrRank, const int64_t *__restrict__ offsets, int width,
+                  const int32_t *__restrict__ idx, int64_t nUnique, const int32_t *__restrict__ uIdx, const int64_t *__restrict__ uPtr,
+                  const int64_t *__restrict__ uWin, double *__restrict__ vec, double *scalar, unsigned *ticket) {
+    const unsigned long long s = *w.seq(SET_HALO) + 1;
+    const int phase = (int)(s & 1);
+    if ((int)blockIdx.x < nNbr) {
+        const int b = blockIdx.x, q = nbrRank[b];
+        const int64_t off = offsets[b], cnt = (offsets[b + 1] - off) * width;
+        double *dst = w.halo(q, phase, w.rank);
+        for (int64_t t = threadIdx.x; t < cnt; t += blockDim.x) {
+            const int64_t k = t / width;
+            dst[t] = vec[(int64_t)idx[off + k] * width + (t - k * width)];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            peer_publish(w.flags(q, SET_HALO) + w.rank, s);
+            atomicAdd(w.sendDone(), 1ull);        // this block no longer reads vec (the receivers below update it)
+        }
+    } else if ((int)blockIdx.x == nNbr) {
+        const unsigned long long sa = *w.seq(SET_AR) + 1;
+        const int pa = (int)(sa & 1);
+        __shared__ double part[kPeerMax];
+        if ((int)threadIdx.x < w.R) {
+            const int q = threadIdx.x;
+            w.ar(q, pa, w.rank)[0] = scalar[0];
+            peer_publish(w.flags(q, SET_AR) + w.rank, sa);
+            if (!peer_wait(w.flags(w.rank, SET_AR) + q, sa)) *w.err() = 1;
+            part[q] = w.ar(w.rank, pa, q)[0];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int r = 0; r < w.R; ++r) t += part[r];
+            scalar[0] = t;
+            atomicAdd(w.arrive(), (unsigned long long)w.R);      // keeps k_peer_allreduce's "R blocks per call" count
+            *w.seq(SET_AR) = sa;
+        }
+    } else {
+        // the neighbours' values have landed AND all of MY sender blocks are done reading vec (they share this launch)
+        if ((int)threadIdx.x < nNbr && !peer_wait(w.flags(w.rank, SET_HALO) + nbrRank[threadIdx.x], s)) *w.err() = 1;
+        if ((int)threadIdx.x == nNbr && !peer_wait(w.sendDone(), *w.fusedCalls() + (unsigned long long)nNbr)) *w.err() = 1;
+        __syncthreads();
+        const double *base = w.halo(w.rank, phase, 0);
+        const int64_t t = (blockIdx.x - nNbr - 1) * (int64_t)blockDim.x + threadIdx.x;
+        if (t < nUnique * width) {
+            const int64_t u = t / width;
+            const int c = (int)(t - u * width);
+            double acc = 0.0;
+            for (int64_t k = uPtr[u]; k < uPtr[u + 1]; ++k) {
+                const int64_t wpos = uWin[k];
+                const int64_t sender = wpos / kHaloSegCap, slot = wpos - sender * kHaloSegCap;
+                acc += base[sender * kHaloSegCap + slot * width + c];
+            }
+            vec[(int64_t)uIdx[u] * width + c] += acc;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned t = atomicAdd(ticket, 1u);
+        if (t == gridDim.x - 1) { *ticket = 0u; *w.seq(SET_HALO) = s; *w.fusedCalls() = *w.sendDone(); }      // snapshot: all nNbr senders of this call are in
+    }
+}
 
 __global__ void k_halo_pack(int64_t n, int width, const int32_t *__restrict__ idx, const double *__restrict__ vec,
                             double *__restrict__ buf) {
@@ -76,9 +274,20 @@ __global__ void k_map_owned(int64_t n, const uint8_t *__restrict__ ownedExt, con
     if (t < n) out[t] = ownedExt[int2ext[t]];
 }
 
+static PeerWinOwner *peer_of(mfem_b200_ctx *c) { return static_cast<PeerWinOwner *>(c->peerWin); }
+static bool peer_active(mfem_b200_ctx *c) { return c->peerWin && peer_of(c)->open && c->opt_comm_p2p; }
+
 void comm_destroy(mfem_b200_ctx *c) {
     delete c->halo;
     c->halo = nullptr;
+    if (c->peerWin && c->ownsWin) {
+        // nobody may still be spinning on this window: the ranks leave together
+        if (c->ncclComm) {
+            cudaStreamSynchronize(c->stream);
+        }
+        delete peer_of(c);
+    }
+    c->peerWin = nullptr;
     if (c->ncclComm && c->ownsComm) ncclCommDestroy(static_cast<ncclComm_t>(c->ncclComm));
     c->ncclComm = nullptr;
 }
@@ -96,6 +305,16 @@ void halo_exchange_add(mfem_b200_ctx *c, double *vec, int width) {
     if (h.total == 0) return;
     MFEM_REQUIRE(width <= h.maxWidth, MFEM_B200_ERR_INVALID, "halo width too large");
     cudaStream_t s = c->stream;
+    if (peer_active(c) && h.p2pFits) {
+        // our own kernels over NVLink peer memory: the sender packs straight into the neighbours' windows
+        const PeerWin &w = peer_of(c)->w;
+        const int nNbr = (int)h.ranks.size();
+        k_peer_halo_send<<<nNbr, 1024, 0, s>>>(w, nNbr, h.nbrRankDev, h.offsetsDev, width, h.idx, vec, w.ticket(SET_HALO), nullptr);
+        k_peer_halo_recv<<<grid_for(h.nUnique * width, 256), 256, 0, s>>>(w, nNbr, h.nbrRankDev, h.nUnique, width, h.uIdx, h.uPtr, h.uWin, vec,
+                                                                           w.ticket(SET_HALO), nullptr);
+        c->launches += 2;
+        return;
+    }
     ncclComm_t comm = static_cast<ncclComm_t>(c->ncclComm);
     k_halo_pack<<<grid_for(h.total * width, 256), 256, 0, s>>>(h.total, width, h.idx, vec, h.sendBuf);
     c->launches++;
@@ -110,6 +329,21 @@ void halo_exchange_add(mfem_b200_ctx *c, double *vec, int width) {
     c->launches++;
 }
 
+// vec += interface partial sums of the neighbours AND *scalar = sum over ranks, in one kernel over the peer window;
+// false (nothing done) when the window path is not available for this exchange
+bool halo_exchange_add_allreduce1(mfem_b200_ctx *c, double *vec, int width, double *scalar) {
+    if (c->nRanks <= 1 || !c->halo || !peer_active(c) || !c->halo->p2pFits || c->halo->total == 0) return false;
+    Halo &h = *c->halo;
+    const PeerWin &w = peer_of(c)->w;
+    const int nNbr = (int)h.ranks.size();
+    const int grid = nNbr + 1 + grid_for(h.nUnique * width, 256);
+    k_peer_halo_fused<<<grid, 256, 0, c->stream>>>(w, nNbr, h.nbrRankDev, h.offsetsDev, width, h.idx, h.nUnique, h.uIdx, h.uPtr, h.uWin, vec, scalar,
+                                                   w.ticket(SET_HALO));
+    c->launches++;
+    return true;
+}
+const PeerWin *comm_peer_window(mfem_b200_ctx *c) { return peer_active(c) ? &peer_of(c)->w : nullptr; }
+
 const uint8_t *halo_shared(mfem_b200_ctx *c) {
     MFEM_REQUIRE(c->halo && c->halo->shared.n == (size_t)c->nDofs, MFEM_B200_ERR_INVALID,
                  "multi-GPU handle without interface description: call mfem_b200_set_interface after set_mesh");
@@ -121,12 +355,32 @@ void allreduce_sum(mfem_b200_ctx *c, const double *in, double *out, int n) {
         if (in != out) MFEM_CUDA(cudaMemcpyAsync(out, in, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
         return;
     }
+    if (peer_active(c) && n <= kArCap) {
+        const PeerWin &w = peer_of(c)->w;
+        k_peer_allreduce<<<w.R, 1024, 0, c->stream>>>(w, in, out, n, w.ticket(SET_AR), nullptr);
+        c->launches++;
+        return;
+    }
     MFEM_NCCL(ncclAllReduce(in, out, (size_t)n, ncclDouble, ncclSum, static_cast<ncclComm_t>(c->ncclComm), c->stream));
 }
+
+int comm_peer_error(mfem_b200_ctx *c) {
+    if (!c->peerWin || !peer_of(c)->open) return 0;
+    int e = 0;
+    cudaMemcpy(&e, peer_of(c)->w.err(), sizeof(int), cudaMemcpyDeviceToHost);
+    return e;
+}
+bool comm_uses_peer_window(mfem_b200_ctx *c) { return peer_active(c); }
 
 // every rank contributes buf[rank*count .. (rank+1)*count) and receives all slices (in place)
 void allgather_inplace(mfem_b200_ctx *c, double *buf, int count) {
     if (c->nRanks <= 1) return;
+    if (peer_active(c) && (int64_t)count * c->nRanks <= kAgCap) {
+        const PeerWin &w = peer_of(c)->w;
+        k_peer_allgather<<<w.R, 1024, 0, c->stream>>>(w, buf, count, w.ticket(SET_AG), nullptr);
+        c->launches++;
+        return;
+    }
     MFEM_NCCL(ncclAllGather(buf + (size_t)c->rank * count, buf, (size_t)count, ncclDouble, static_cast<ncclComm_t>(c->ncclComm), c->stream));
 }
 
@@ -180,8 +434,77 @@ int mfem_b200_comm_share(mfem_b200_handle h, mfem_b200_handle parent) {
     h->ownsComm = false;
     h->nRanks = parent->nRanks;
     h->rank = parent->rank;
+    h->peerWin = parent->peerWin;          // the peer window is process-level state like the communicator
+    h->ownsWin = false;
     return MFEM_B200_OK;
 }
+
+// Peer window, step 1: allocate this rank's window and return its 64-byte CUDA IPC handle; the caller gathers the handles
+// of all ranks (torch.distributed / MPI) and passes them to mfem_b200_comm_window_open.  After comm_init.
+int mfem_b200_comm_window_handle(mfem_b200_handle h, void *out64) {
+    if (!h || !out64) return MFEM_B200_ERR_INVALID;
+    try {
+        MFEM_CUDA(cudaSetDevice(h->device));
+        MFEM_REQUIRE(h->nRanks > 1 && h->ncclComm && h->ownsComm, MFEM_B200_ERR_INVALID, "comm_window_handle: call comm_init first");
+        MFEM_REQUIRE(h->nRanks <= kPeerMax, MFEM_B200_ERR_INVALID, "comm_window: at most 8 ranks (one NVSwitch box)");
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+        if (!h->peerWin) {
+            auto *o = new PeerWinOwner();
+            h->peerWin = o;
+            h->ownsWin = true;
+            MFEM_CUDA(cudaMalloc(&o->local, PeerWin::bytes));
+            MFEM_CUDA(cudaMemset(o->local, 0, PeerWin::offAr));          // flags, sequence numbers, error word, tickets
+        }
+        cudaIpcMemHandle_t ih;
+        MFEM_CUDA(cudaIpcGetMemHandle(&ih, peer_of(h)->local));
+        memcpy(out64, &ih, sizeof(ih));
+        return MFEM_B200_OK;
+    } catch (const CudaError &e) {
+        h->err = e.what();
+        return e.status;
+    }
+}
+
+// step 2: map the windows of all ranks (handles in rank order, 64 bytes each).  The caller must put a barrier between
+// this call and the first collective (every rank has to have opened the windows it will write to -- the NCCL
+// collectives of set_interface / the first set-up provide it anyway, mfem_b200_comm_window_open ends with an all-reduce).
+int mfem_b200_comm_window_open(mfem_b200_handle h, const void *handles) {
+    if (!h || !handles) return MFEM_B200_ERR_INVALID;
+    try {
+        MFEM_CUDA(cudaSetDevice(h->device));
+        MFEM_REQUIRE(h->peerWin && h->ownsWin, MFEM_B200_ERR_INVALID, "comm_window_open: call comm_window_handle first");
+        PeerWinOwner &o = *peer_of(h);
+        o.w.R = h->nRanks; o.w.rank = h->rank;
+        bool ok = true;
+        std::string why;
+        for (int r = 0; r < h->nRanks && ok; ++r) {
+            if (r == h->rank) { o.w.peer[r] = static_cast<char *>(o.local); continue; }
+            cudaIpcMemHandle_t ih;
+            memcpy(&ih, static_cast<const char *>(handles) + 64 * (size_t)r, sizeof(ih));
+            const cudaError_t e = cudaIpcOpenMemHandle(&o.mapped[r], ih, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) { ok = false; why = cudaGetErrorString(e); cudaGetLastError(); break; }
+            o.w.peer[r] = static_cast<char *>(o.mapped[r]);
+        }
+        // all ranks agree on whether the window is usable (one refusal disables it everywhere) -- and this all-reduce is
+        // the barrier that orders "everybody has mapped everything" before the first peer store
+        DevBuf<double> flag(1);
+        const double mine = ok ? 0.0 : 1.0;
+        MFEM_CUDA(cudaMemcpyAsync(flag, &mine, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        MFEM_NCCL(ncclAllReduce(flag.p, flag.p, 1, ncclDouble, ncclSum, static_cast<ncclComm_t>(h->ncclComm), h->stream));
+        double bad = 0.0;
+        MFEM_CUDA(cudaMemcpyAsync(&bad, flag, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        MFEM_CUDA(cudaStreamSynchronize(h->stream));
+        o.open = bad == 0.0;
+        if (!o.open) { h->err = "peer window unavailable (" + (why.empty() ? std::string("refused on another rank") : why) + "): NCCL path"; return MFEM_B200_OK; }
+        return MFEM_B200_OK;
+    } catch (const CudaError &e) {
+        h->err = e.what();
+        return e.status;
+    }
+}
+
+// 1 if the small collectives of this handle run over the peer window, 0 if over NCCL
+int mfem_b200_comm_uses_peer_window(mfem_b200_handle h) { return (h && comm_uses_peer_window(h)) ? 1 : 0; }
 
 int mfem_b200_set_interface(mfem_b200_handle h, int n_neighbors, const int32_t *neighbor_ranks,
                             const int64_t *neighbor_offsets, const int32_t *shared_local_dofs, const uint8_t *owned) {
@@ -234,6 +557,21 @@ int mfem_b200_set_interface(mfem_b200_handle h, int n_neighbors, const int32_t *
             H.uPos.alloc((size_t)H.total);
             MFEM_CUDA(cudaMemcpyAsync(H.uPtr, uPtr.data(), H.uPtr.bytes(), cudaMemcpyHostToDevice, s));
             MFEM_CUDA(cudaMemcpyAsync(H.uPos, order.data(), H.uPos.bytes(), cudaMemcpyHostToDevice, s));
+            // peer-window path: neighbour table on the device and, per receive slot, (sender rank, slot in its segment)
+            std::vector<int32_t> nbr(H.ranks.begin(), H.ranks.end());
+            std::vector<int64_t> uWin((size_t)H.total);
+            H.p2pFits = true;
+            for (int q = 0; q < n_neighbors; ++q)
+                if ((H.offsets[q + 1] - H.offsets[q]) * H.maxWidth > kHaloSegCap) H.p2pFits = false;
+            for (int64_t k = 0; k < H.total; ++k) {
+                const int64_t pos = order[(size_t)k];
+                const int q = (int)(std::upper_bound(H.offsets.begin(), H.offsets.end(), pos) - H.offsets.begin()) - 1;
+                uWin[(size_t)k] = (int64_t)H.ranks[q] * kHaloSegCap + (pos - H.offsets[q]);
+            }
+            H.nbrRankDev.alloc(nbr.size()); H.offsetsDev.alloc(H.offsets.size()); H.uWin.alloc(uWin.size());
+            MFEM_CUDA(cudaMemcpyAsync(H.nbrRankDev, nbr.data(), H.nbrRankDev.bytes(), cudaMemcpyHostToDevice, s));
+            MFEM_CUDA(cudaMemcpyAsync(H.offsetsDev, H.offsets.data(), H.offsetsDev.bytes(), cudaMemcpyHostToDevice, s));
+            MFEM_CUDA(cudaMemcpyAsync(H.uWin, uWin.data(), H.uWin.bytes(), cudaMemcpyHostToDevice, s));
             h->launches += 3;
             MFEM_CUDA(cudaStreamSynchronize(s));
         }

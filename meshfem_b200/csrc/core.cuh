@@ -183,6 +183,9 @@ struct mfem_b200_ctx {
     void *ncclComm = nullptr;
     bool ownsComm = false;                 // false: borrowed from another handle (mfem_b200_comm_share)
     mfem::Halo *halo = nullptr;
+    void *peerWin = nullptr;               // PeerWinOwner (comm.cu): window mapped by all ranks for the small collectives
+    bool ownsWin = false;
+    int opt_comm_p2p = 1;                  // 1: small collectives over the peer window when it is open, 0: always NCCL
 
     // bookkeeping
     std::map<std::string, double> timers;
@@ -255,13 +258,19 @@ bool pcg_solve_multi(mfem_b200_ctx *c, int nrhs, const double *f_int, double *u_
                      mfem_b200_solve_info *info);
 void free_work_multi(mfem_b200_ctx *c);
 void free_coarse_space(mfem_b200_ctx *c);
+bool will_use_coarse(mfem_b200_ctx *c);
 double time_spmv(mfem_b200_ctx *c, int iters);
 int64_t get_coarse_array(mfem_b200_ctx *c, const std::string &name, double *out, int64_t capacity);
 void apply_preconditioner(mfem_b200_ctx *c, const double *r_int, double *z_int, double *rz);
 // comm.cu
 void halo_exchange_add(mfem_b200_ctx *c, double *vec_int, int width);   // no-op on one rank
 void allreduce_sum(mfem_b200_ctx *c, const double *in, double *out, int n);
-void allgather_inplace(mfem_b200_ctx *c, double *buf, int count);   // slices of `count` doubles in rank order
+void allgather_inplace(mfem_b200_ctx *c, double *buf, int count);
+int comm_peer_error(mfem_b200_ctx *c);                             // non-zero after a peer-window spin timed out
+bool comm_uses_peer_window(mfem_b200_ctx *c);
+bool halo_exchange_add_allreduce1(mfem_b200_ctx *c, double *vec_int, int width, double *scalar);   // fused; false = not available
+struct PeerWin;
+const PeerWin *comm_peer_window(mfem_b200_ctx *c);                 // nullptr when the collectives go through NCCL   // slices of `count` doubles in rank order
 const uint8_t *halo_owned(mfem_b200_ctx *c);
 const uint8_t *halo_shared(mfem_b200_ctx *c);      // [nDofs] 1 = DoF shared with another rank
 // aux.cu

@@ -11,6 +11,7 @@
 // All reductions are two-stage with a fixed order (per-CTA partials, then the last CTA to
 // finish sums them in index order): results are bit-reproducible run to run.
 #include "core.cuh"
+#include "peer.cuh"
 
 #include <cusolverDn.h>   // types only: the library is loaded with dlopen by coarse.inl (optional two-level preconditioner)
 #include <dlfcn.h>
@@ -45,7 +46,7 @@ enum { ST_ITERS = 0, ST_STATE = 1 };   // state: 0 running, 1 converged, 2 break
 // ---------------------------------------------------------------------------
 template <int NV>
 __device__ __forceinline__ void block_reduce_store(double (&v)[NV], double *partials /* [NV][gridDim.x] */) {
-    __shared__ double red[NV][kVecThreads / 32];
+    __shared__ double red[NV][32];                  // up to 1024 threads per block
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
@@ -260,7 +261,9 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void *p, uint32_t bytes) 
 }
 
 template <int N, int LPR, bool MASKED, bool DOT, bool PF, int MINB = 4>
-__global__ void __launch_bounds__(kSpmvThreads, MINB)   // MINB = 4: <= 64 registers, 32 resident warps per SM
+__global__ void __launch_bounds__(MINB == 1 ? 1024 : kSpmvThreads, MINB)   // MINB = 4: <= 64 registers, 32 resident warps per SM;
+                                                                          // MINB = 1: ONE 1024-thread CTA per SM (same registers and
+                                                                          // occupancy), so the 32 warps of an SM work on 32 consecutive rows
 k_bsr_spmv(int64_t nb, const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
            const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y,
            const uint8_t *__restrict__ fixedMask, double *partials, unsigned *ticket, double *dotOut,
@@ -1292,18 +1295,28 @@ static void launch_spmv_lp(mfem_b200_ctx *c, const double *x, double *y, bool ma
 template <int MINB>
 static void launch_spmv_occ(mfem_b200_ctx *c, const double *x, double *y, bool masked, bool dot) {
     PcgWork &w = c->work;
+    const int threads = MINB == 1 ? 1024 : kSpmvThreads;
+    int grid;
+    if (MINB == 1) {
+        const int64_t ctas = (c->nDofs + 31) / 32;
+        grid = (int)std::max<int64_t>(1, std::min<int64_t>(ctas, sm_count(c)));
+    } else {
+        grid = spmv_grid(c, 32, k_bsr_spmv<3, 32, true, true, false, MINB>);
+    }
     if (masked && dot)
-        k_bsr_spmv<3, 32, true, true, false, MINB><<<spmv_grid(c, 32, k_bsr_spmv<3, 32, true, true, false, MINB>), kSpmvThreads, 0, c->stream>>>(
+        k_bsr_spmv<3, 32, true, true, false, MINB><<<grid, threads, 0, c->stream>>>(
             c->nDofs, c->rowptr, c->colidx, c->vals, x, y, c->fixedMask, w.partials, w.ticket, w.scal.p + S_PAP, w.status);
     else
-        k_bsr_spmv<3, 32, false, false, false, MINB><<<spmv_grid(c, 32, k_bsr_spmv<3, 32, false, false, false, MINB>), kSpmvThreads, 0, c->stream>>>(
+        k_bsr_spmv<3, 32, false, false, false, MINB><<<grid, threads, 0, c->stream>>>(
             c->nDofs, c->rowptr, c->colidx, c->vals, x, y, nullptr, nullptr, nullptr, nullptr, nullptr);
     c->launches++;
 }
 template <int N, int LPR>
 static void launch_spmv_l(mfem_b200_ctx *c, const double *x, double *y, bool masked, bool dot) {
-    if (N == 3 && LPR == 32 && (masked == dot) && (c->opt_spmv_min_blocks == 3 || c->opt_spmv_min_blocks == 5)) {
-        if (c->opt_spmv_min_blocks == 3) launch_spmv_occ<3>(c, x, y, masked, dot); else launch_spmv_occ<5>(c, x, y, masked, dot);
+    if (N == 3 && LPR == 32 && (masked == dot) && (c->opt_spmv_min_blocks == 3 || c->opt_spmv_min_blocks == 5 || c->opt_spmv_min_blocks == 1)) {
+        if (c->opt_spmv_min_blocks == 3) launch_spmv_occ<3>(c, x, y, masked, dot);
+        else if (c->opt_spmv_min_blocks == 5) launch_spmv_occ<5>(c, x, y, masked, dot);
+        else launch_spmv_occ<1>(c, x, y, masked, dot);
         return;
     }
     if (c->opt_spmv_prefetch) launch_spmv_lp<N, LPR, true>(c, x, y, masked, dot);
@@ -1422,6 +1435,13 @@ void spmv_plain(mfem_b200_ctx *c, const double *x_int, double *y_int) {
 
 void free_coarse_space(mfem_b200_ctx *c) { free_coarse(c); }
 
+// will the next solve use the aggregation levels (explicit option, or the automatic rule on a large enough problem)?
+bool will_use_coarse(mfem_b200_ctx *c) {
+    if (c->opt_coarse == 0) return false;
+    if (c->opt_coarse > 0) return true;
+    return coarse_budget(c, coarse_global_dofs(c)) > 0;
+}
+
 void build_preconditioner(mfem_b200_ctx *c) {
     if (c->precondValid) return;
     MFEM_REQUIRE(c->valuesValid, MFEM_B200_ERR_INVALID, "preconditioner: matrix not assembled");
@@ -1485,9 +1505,17 @@ static const double *enqueue_precond_tail(mfem_b200_ctx *c, const int *status) {
                                                        w.ticket + 3, w.scal.p + S_RZ_NEW, status);
     } else {
         // row-split dense level: this rank's slice of y2, one in-place all-gather, then c2.y2 in a fixed order
-        k_coarse_gemv<false><<<gg, kVecThreads, 0, s>>>(cs.nc2, cs.rowBase, cs.nRowsLoc, cs.Einv, w.red, cs.y2, nullptr, nullptr, nullptr, status);
-        allgather_inplace(c, cs.y2, (int)cs.nRowsLoc);
-        k_coarse_cy<<<1, 256, 0, s>>>(cs.nc2, w.red, cs.y2, w.scal.p + S_RZ_NEW, status);
+        const PeerWin *pw = comm_peer_window(c);
+        if (pw && cs.nc2 <= kAgCap) {
+            // the GEMV stores its rows of y2 straight into every rank's window; the 1-CTA kernel that adds c2.y2 waits for
+            // everybody's rows and copies the gathered vector out: the all-gather costs no launch of its own
+            k_coarse_gemv_ship<<<gg, kVecThreads, 0, s>>>(*pw, cs.nc2, cs.rowBase, cs.nRowsLoc, cs.Einv, w.red, w.ticket + 4, status);
+            k_coarse_cy_gather<<<1, 1024, 0, s>>>(*pw, cs.nc2, w.red, cs.y2, w.scal.p + S_RZ_NEW, status);
+        } else {
+            k_coarse_gemv<false><<<gg, kVecThreads, 0, s>>>(cs.nc2, cs.rowBase, cs.nRowsLoc, cs.Einv, w.red, cs.y2, nullptr, nullptr, nullptr, status);
+            allgather_inplace(c, cs.y2, (int)cs.nRowsLoc);
+            k_coarse_cy<<<1, 256, 0, s>>>(cs.nc2, w.red, cs.y2, w.scal.p + S_RZ_NEW, status);
+        }
         c->launches++;
     }
     c->launches += 2;
@@ -1521,8 +1549,10 @@ static void enqueue_iteration(mfem_b200_ctx *c) {
     launch_spmv<N>(c, w.p, w.Ap, true, true);                 // p.Ap fused into the SpMV epilogue -> scal[S_PAP]
     if (multi) {
         // masked rows stay zero through the exchange: every sharer masks the same DoFs
-        halo_exchange_add(c, w.Ap, N);
-        allreduce_sum(c, w.scal.p + S_PAP, w.scal.p + S_PAP, 1);
+        if (!halo_exchange_add_allreduce1(c, w.Ap, N, w.scal.p + S_PAP)) {      // one kernel over the peer window, or NCCL
+            halo_exchange_add(c, w.Ap, N);
+            allreduce_sum(c, w.scal.p + S_PAP, w.scal.p + S_PAP, 1);
+        }
     }
     k_pcg_update<N, false><<<vgrid, kVecThreads, 0, c->stream>>>(nb, nullptr, c->fixedMask, c->Minv, owned, w.p, w.Ap, w.x, w.r, w.z,
                                                                   w.partials, w.ticket + 1, w.scal, w.red, w.status,
@@ -1616,6 +1646,8 @@ static void pcg_impl(mfem_b200_ctx *c, const double *f_int, double *u_int, doubl
         info->seconds = ms * 1e-3;
         info->spmv_seconds = 0.0;
     }
+    if (multi && comm_peer_error(c))
+        throw CudaError(MFEM_B200_ERR_COMM, "PCG: a peer-window collective timed out (a rank stopped responding)");
     if (hst[ST_STATE] == 2)
         throw CudaError(MFEM_B200_ERR_NOT_SPD, "PCG breakdown: p'Ap <= 0 (matrix is not positive definite)");
     if (hst[ST_STATE] == 3) throw CudaError(MFEM_B200_ERR_NAN, "PCG: NaN encountered");

@@ -54,6 +54,12 @@ def make_handle(dist, world, rank, local_rank, p, D, comm_parent=None, **options
         dev = torch.device("cuda", local_rank) if dist.get_backend() == "nccl" else None
         uid = broadcast_bytes(dist, uid, 128, dev)
         h.comm_init(world, rank, uid)
+        if dev is not None and world <= 8 and options.get("comm_p2p", 1):
+            # peer window: the IPC handles of all ranks, gathered in rank order (csrc/comm.cu)
+            mine = torch.frombuffer(bytearray(h.comm_window_handle()), dtype=torch.uint8).to(dev)
+            parts = [torch.zeros(64, dtype=torch.uint8, device=dev) for _ in range(world)]
+            dist.all_gather(parts, mine)
+            h.comm_window_open(b"".join(bytes(t.cpu().numpy().tobytes()) for t in parts))
     h.set_mesh(p.N, p.deg, p.nodes, p.elem_nodes, dof_for_node=p.dof_for_node,
                n_dofs=p.num_dofs if p.dof_for_node is not None else None)
     h.set_interface(p.neighbor_ranks, p.neighbor_offsets, p.shared_local, p.owned)

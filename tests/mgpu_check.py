@@ -36,7 +36,7 @@ def main():
         h = make_handle(meshfem_b200, dist, world, rank, local_rank, p, D)
         h.assemble()
         h.fix_variables(lfixed, lvals)
-        u, info = h.solve(lf, rtol=1e-12, return_info=True)
+        u, info = h.solve(lf, rtol=1e-12, max_iters=4000, return_info=True)
         h.close()
         err = float(np.linalg.norm(u.reshape(-1, 3) - u_ref[p.nodes_global]) / np.linalg.norm(u_ref[p.nodes_global]))
         err = max_over_ranks(dist, err, device)
@@ -59,7 +59,7 @@ def main():
             h = make_handle(meshfem_b200, dist, world, rank, local_rank, p, D, coarse_aggregates=coarse, coarse_fine_nodes=fine)
             h.assemble()
             h.fix_variables(lfixed, lvals)
-            u, info = h.solve(lf, rtol=1e-11, return_info=True)
+            u, info = h.solve(lf, rtol=1e-11, max_iters=4000, return_info=True)
             h.close()
             err = max_over_ranks(dist, float(np.linalg.norm(u.reshape(-1, 3) - ref) / np.linalg.norm(ref)), device)
             if rank == 0:

@@ -21,6 +21,7 @@ def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 64
     deg = int(sys.argv[2]) if len(sys.argv) > 2 else 2
     batch = int(os.environ.get("BATCH_RHS", "1"))
+    coarse = int(os.environ.get("COARSE", "-1"))          # -1: automatic multilevel preconditioner (systems one after the other), 0: batched block-Jacobi PCG
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -39,7 +40,7 @@ def main():
     raw = hostlib.perforated_cell(3, n, n // 2)
     t_mesh = time.perf_counter() - t0
     t0 = time.perf_counter()
-    Eh, extra = distributed.homogenize(raw, deg, D, dist=dist, local_rank=local_rank, rtol=1e-8, return_fields=True, batch_rhs=batch)
+    Eh, extra = distributed.homogenize(raw, deg, D, dist=dist, local_rank=local_rank, rtol=1e-8, return_fields=True, batch_rhs=batch, coarse_aggregates=coarse)
     wall = time.perf_counter() - t0
     solve_s = sum(s["seconds"] for s in extra["solves"])
     if dist is not None:
@@ -52,7 +53,7 @@ def main():
         out = {
             "workload": f"cfg4: {n}^3 voxel cell minus centred {n // 2}^3 block, degree {deg}, periodic, {6} cell problems",
             "n_gpus": world, "elements": int(m.num_elements), "nodes": int(m.num_nodes), "dofs": 3 * int(extra["dof_for_node"].max() + 1),
-            "batched": bool(batch), "iterations": [s["iterations"] for s in extra["solves"]],
+            "batched": bool(batch) and coarse == 0, "coarse_aggregates": coarse, "iterations": [s["iterations"] for s in extra["solves"]],
             "solve_device_s": solve_s, "homogenize_wall_s": wall, "mesh_generation_s": t_mesh,
             "elements_per_s_solve": 6 * m.num_elements / solve_s,
             "Eh_diag": [float(Eh[i, i]) for i in range(6)], "Eh_01": float(Eh[0, 1]),
