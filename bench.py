@@ -336,7 +336,7 @@ def run_ours(args):
     f_p, _k3 = pinned_copy(np.ascontiguousarray(f))
     if p is not None:
         p.nodes, p.elem_nodes = nodes_p, elems_p
-    opts = {"coarse_aggregates": args.coarse_aggregates, "coarse_fine_nodes": args.coarse_fine_nodes}
+    opts = {"coarse_aggregates": args.coarse_aggregates, "coarse_fine_nodes": args.coarse_fine_nodes, "matrix_free": args.matrix_free}
     if world > 1:
         opts["comm_p2p"] = args.comm_p2p
 
@@ -388,8 +388,12 @@ def run_ours(args):
     # dominant kernel: the PCG SpMV (the masked + fused-dot variant the iteration launches), timed live on the
     # library's stream (inputs: the 31 GB matrix >> L2)
     spmv_s = h.time_spmv(20)
+    # ... and the product the iteration actually launches: the mesh-based operator (csrc/matfree.inl) where option
+    # matrix_free selects it (3D quadratic elements by default), its two kernels also timed alone
+    op_s, op_parts, mf_used = h.time_operator(20)
     clocks = sampler.stop() if rank == 0 else None
     asm_max, setup_max, solve_max, spmv_max = rmax(asm_s), rmax(setup_s), rmax(solve_s), rmax(spmv_s)
+    op_max, op_elem_max, op_gather_max = rmax(op_s), rmax(op_parts[0]), rmax(op_parts[1])
     nnzb_tot, nb_tot, launches_tot = rsum(nnzb), rsum(nb), rsum(launches)
     dev_s = rmax(asm_s + setup_s + solve_s)
     coarse_sizes = None
@@ -420,6 +424,17 @@ def run_ours(args):
             parity["rel_l2_vs_block_jacobi_pcg"] = float(np.sqrt(num / den))
             parity["block_jacobi_iterations"] = int(info[0]["iterations"])
             parity["block_jacobi_solve_ms"] = 1e3 * rmax(info[0]["seconds"])
+        # (2b) an independent operator: the same PCG multiplying with the STORED matrix (block-CSR SpMV) instead of the
+        #      mesh-based operator, full vector
+        if mf_used:
+            h.set_option("matrix_free", 0)
+            ust, info = h.solve(f_p, rtol=RTOL, return_info=True)
+            h.set_option("matrix_free", args.matrix_free)
+            ust = np.asarray(ust).reshape(-1)
+            num, den = rsum(float(np.sum((u - ust) ** 2))), rsum(float(np.sum(ust ** 2)))
+            parity["rel_l2_vs_stored_matrix_pcg"] = float(np.sqrt(num / den))
+            parity["stored_matrix_iterations"] = int(info[0]["iterations"])
+            parity["stored_matrix_solve_ms"] = 1e3 * rmax(info[0]["seconds"])
         # (3) true residual of the returned vector through an INDEPENDENT code path: the matrix-free element-wise
         #     K u (mfem_b200_apply_K = applyStiffnessMatrix, LinearElasticity.hh:801-823), free variables only
         if world == 1:
@@ -483,17 +498,44 @@ def run_ours(args):
     if rank == 0:
         spmv_bytes = nnzb_tot * 76 + nb_tot * 52           # whole-job algorithmic bytes of one (distributed) SpMV
         asm_bytes = nnzb_tot * 72 + n_elems * (4 * npe + 96)
-        roofline = {"bound": "hbm", "kernel": "k_bsr_spmv<3,32,masked,dot> (the PCG's SpMV" + (", per-rank local part, max over ranks)" if world > 1 else ")"),
-                    "achieved": spmv_bytes / spmv_max / 1e9, "peak": hbm_peak * world, "unit": "GB/s",
-                    "frac": spmv_bytes / spmv_max / 1e9 / (hbm_peak * world),
-                    "traffic": measured_traffic(name, "k_bsr_spmv", nnzb) if world == 1 else None,
-                    "peak_source": peak_src, "algorithmic_bytes_per_launch": spmv_bytes, "seconds_per_launch": spmv_max,
-                    "assembly": {"achieved": asm_bytes / (asm_max / args.steps) / 1e9, "unit": "GB/s",
-                                 "frac": asm_bytes / (asm_max / args.steps) / 1e9 / (hbm_peak * world),
-                                 "algorithmic_bytes_per_launch": asm_bytes}}
+        peak_all = hbm_peak * world
+        rank_note = ", per-rank local part, max over ranks)" if world > 1 else ")"
+        spmv_roof = {"kernel": "k_bsr_spmv<3,32,masked,dot> (block-CSR SpMV on the stored matrix" + rank_note,
+                     "achieved": spmv_bytes / spmv_max / 1e9, "unit": "GB/s", "frac": spmv_bytes / spmv_max / 1e9 / peak_all,
+                     "traffic": measured_traffic(name, "k_bsr_spmv", nnzb) if world == 1 else None,
+                     "algorithmic_bytes_per_launch": spmv_bytes, "seconds_per_launch": spmv_max}
+        asm_roof = {"achieved": asm_bytes / (asm_max / args.steps) / 1e9, "unit": "GB/s",
+                    "frac": asm_bytes / (asm_max / args.steps) / 1e9 / peak_all, "algorithmic_bytes_per_launch": asm_bytes}
+        if mf_used:
+            # the iteration multiplies with the mesh-based operator: k_mf_elements (one thread per element: DoF ids 4*npe,
+            # packed geometry 128, the element's npe result blocks 24*npe; the x blocks once per DoF) then k_mf_gather
+            # (per incidence one 4-byte slot id + 24 bytes; per DoF row: extent 8, x 24, y 24, mask 3)
+            n_inc = n_elems * npe
+            elem_bytes = n_elems * (4 * npe + 128 + 24 * npe) + nb_tot * 24
+            gather_bytes = n_inc * 28 + nb_tot * 59
+            roofline = {"bound": "hbm", "kernel": "k_mf_elements<3,2> (element kernel of the PCG's mesh-based operator" + rank_note,
+                        "achieved": elem_bytes / op_elem_max / 1e9, "peak": peak_all, "unit": "GB/s",
+                        "frac": elem_bytes / op_elem_max / 1e9 / peak_all,
+                        "traffic": measured_traffic(name, "k_mf_elements", nnzb) if world == 1 else None,
+                        "peak_source": peak_src, "algorithmic_bytes_per_launch": elem_bytes, "seconds_per_launch": op_elem_max,
+                        "gather_kernel": {"kernel": "k_mf_gather<3,masked,dot>", "achieved": gather_bytes / op_gather_max / 1e9, "unit": "GB/s",
+                                          "frac": gather_bytes / op_gather_max / 1e9 / peak_all,
+                                          "traffic": measured_traffic(name, "k_mf_gather", nnzb) if world == 1 else None,
+                                          "algorithmic_bytes_per_launch": gather_bytes, "seconds_per_launch": op_gather_max},
+                        "operator_seconds_per_product": op_max,
+                        "equivalent_stored_matrix_bandwidth": {"achieved": spmv_bytes / op_max / 1e9, "unit": "GB/s",
+                                                               "frac": spmv_bytes / op_max / 1e9 / peak_all,
+                                                               "note": "bytes the stored-matrix SpMV would have to stream for the same product / operator time"},
+                        "stored_matrix_spmv": spmv_roof, "assembly": asm_roof}
+        else:
+            roofline = dict(spmv_roof)
+            roofline.update({"bound": "hbm", "peak": peak_all, "peak_source": peak_src, "assembly": asm_roof})
+            roofline["kernel"] = roofline["kernel"].replace("block-CSR SpMV on the stored matrix", "the PCG's SpMV")
         cfg = {"workload": workload_name(name, grid, deg, mat), "elements": n_elems, "nodes": n_nodes, "dofs": 3 * n_nodes,
                "nnz_blocks": int(nnzb_tot), "rtol": RTOL, "preconditioner": precond_name(args.coarse_aggregates, args.coarse_fine_nodes),
-               "coarse_space": coarse_sizes, "l2_policy": "inputs larger than L2 (matrix %.1f GB)" % (nnzb_tot * 76 / 1e9 / world)}
+               "coarse_space": coarse_sizes,
+               "pcg_operator": ("mesh-based (matrix-free): element kernel + per-DoF gather, csrc/matfree.inl" if mf_used
+                                else "stored block-CSR matrix (SpMV)"), "l2_policy": "inputs larger than L2 (matrix %.1f GB)" % (nnzb_tot * 76 / 1e9 / world)}
         if world > 1:
             cfg["partition"] = (f"{world} x-slabs of elements, shared interface DoFs; per iteration one interface sum-exchange, two all-reduces "
                                 f"and one all-gather, " + ("by the library's own kernels over NVLink peer memory (CUDA IPC window)" if uses_window
@@ -527,6 +569,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="cfg5")
+    ap.add_argument("--matrix-free", type=int, default=-1,
+                    help="PCG operator: -1 automatic (mesh-based for 3D quadratic elements), 0 stored-matrix SpMV, 1 mesh-based")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-direct", action="store_true", help="skip the direct-solver leg of the CPU baseline")
     ap.add_argument("--no-parity", action="store_true", help="skip the full-size parity evidence (two extra solves)")

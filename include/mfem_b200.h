@@ -208,6 +208,12 @@ int64_t mfem_b200_launch_count(mfem_b200_handle h);
  * vectors and return the mean device seconds per launch (CUDA events on the handle's
  * stream).  Used by bench.py for the roofline of the dominant kernel.                  */
 int mfem_b200_time_spmv(mfem_b200_handle h, int iters, double *seconds_per_launch);
+/* The same for the product the PCG actually launches per iteration, y = mask(K p) with the fused p.y: the mesh-based
+ * (matrix-free) operator of csrc/matfree.inl where option "matrix_free" selects it (*matrix_free = 1; seconds_parts[0..1]
+ * = its element kernel and its gather kernel timed alone), else the stored-matrix SpMV (*matrix_free = 0, parts 0).
+ * seconds_parts and matrix_free may be NULL.                                                                         */
+int mfem_b200_time_operator(mfem_b200_handle h, int iters, double *seconds_per_product, double *seconds_parts,
+                            int *matrix_free);
 /* Diagnostics: z = M^-1 r and *rz = r.z for the preconditioner the next solve would use (block-Jacobi alone, or with the
  * aggregation levels of "coarse_aggregates" / "coarse_fine_nodes"), r masked on the fixed variables first; per-DoF
  * vectors in the caller's numbering.  Runs the PCG's own start-up kernels, so the parity tests can compare the operator

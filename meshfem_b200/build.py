@@ -14,7 +14,7 @@ CSRC = os.path.join(ROOT, "csrc")
 LIBDIR = os.path.join(ROOT, "lib")
 LIB = os.path.join(LIBDIR, "libmfem_b200.so")
 SOURCES = ["setup.cu", "assemble.cu", "solver.cu", "aux.cu", "shape.cu", "comm.cu", "capi.cu"]
-HEADERS = ["core.cuh", "elem_math.cuh", "solver_multi.inl", "coarse.inl", os.path.join("..", "..", "include", "mfem_b200.h")]
+HEADERS = ["core.cuh", "elem_math.cuh", "solver_multi.inl", "coarse.inl", "matfree.inl", "peer.cuh", os.path.join("..", "..", "include", "mfem_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

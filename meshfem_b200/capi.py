@@ -24,7 +24,7 @@ SYMBOLS = [
     "mfem_b200_set_node_positions", "mfem_b200_fix_variables", "mfem_b200_clear_fixed_variables",
     "mfem_b200_solve", "mfem_b200_apply_K", "mfem_b200_spmv", "mfem_b200_const_strain_load",
     "mfem_b200_avg_strain_stress", "mfem_b200_get_volumes", "mfem_b200_get_timer", "mfem_b200_reset_timers",
-    "mfem_b200_launch_count", "mfem_b200_time_spmv", "mfem_b200_set_matrix_triplets", "mfem_b200_comm_share",
+    "mfem_b200_launch_count", "mfem_b200_time_spmv", "mfem_b200_time_operator", "mfem_b200_set_matrix_triplets", "mfem_b200_comm_share",
     "mfem_b200_apply_preconditioner", "mfem_b200_get_coarse_array", "mfem_b200_release_cached_memory",
     "mfem_b200_comm_window_handle", "mfem_b200_comm_window_open", "mfem_b200_comm_uses_peer_window",
     "mfem_b200_apply_delta_K", "mfem_b200_delta_const_strain_load", "mfem_b200_delta_avg_strain",
@@ -97,6 +97,7 @@ def load_library():
     lib.mfem_b200_launch_count.argtypes = [c_void_p]
     lib.mfem_b200_launch_count.restype = c_int64
     lib.mfem_b200_time_spmv.argtypes = [c_void_p, c_int, dp]
+    lib.mfem_b200_time_operator.argtypes = [c_void_p, c_int, dp, dp, ctypes.POINTER(c_int)]
     lib.mfem_b200_apply_preconditioner.argtypes = [c_void_p, dp, dp, dp]
     lib.mfem_b200_get_coarse_array.argtypes = [c_void_p, c_char_p, dp, c_int64, lp]
     lib.mfem_b200_apply_delta_K.argtypes = [c_void_p, dp, dp, c_int64, dp]
@@ -396,3 +397,11 @@ class Handle:
         s = c_double()
         self._check(self.lib.mfem_b200_time_spmv(self._h, iters, ctypes.byref(s)))
         return s.value
+
+    def time_operator(self, iters=20):
+        """Seconds per K*p product as the PCG launches it: (seconds, [element kernel, gather kernel], matrix_free)."""
+        s = c_double()
+        parts = (c_double * 2)()
+        mf = c_int(0)
+        self._check(self.lib.mfem_b200_time_operator(self._h, iters, ctypes.byref(s), parts, ctypes.byref(mf)))
+        return s.value, [parts[0], parts[1]], bool(mf.value)

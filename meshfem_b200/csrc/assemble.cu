@@ -503,6 +503,16 @@ k_assemble_blocks(int64_t nnzb, const int32_t *__restrict__ chunkRow, const int6
     }
 }
 
+void ensure_packed_geometry(mfem_b200_ctx *c) {
+    if (c->geomPValid) return;
+    MFEM_REQUIRE(c->geomValid, MFEM_B200_ERR_INVALID, "packed geometry: no mesh geometry");
+    if (c->geomP.n != (size_t)c->nElems * 16) c->geomP.alloc((size_t)c->nElems * 16);
+    if (c->N == 3) k_pack_geom<3><<<grid_for(c->nElems * 4, 256), 256, 0, c->stream>>>(c->nElems, c->geom, c->geomP);
+    else k_pack_geom<2><<<grid_for(c->nElems * 4, 256), 256, 0, c->stream>>>(c->nElems, c->geom, c->geomP);
+    c->launches++;
+    c->geomPValid = true;
+}
+
 template <int N, int DEG>
 static void launch_assemble_blocks(mfem_b200_ctx *c) {
     cudaStream_t s = c->stream;
@@ -517,12 +527,7 @@ static void launch_assemble_blocks(mfem_b200_ctx *c) {
         c->pairTabKey = N * 10 + DEG;
     }
     static_assert(PP <= 100, "pair table sized for at most 10 nodes per element");
-    if (!c->geomPValid) {
-        if (c->geomP.n != (size_t)c->nElems * 16) c->geomP.alloc((size_t)c->nElems * 16);
-        k_pack_geom<N><<<grid_for(c->nElems * 4, 256), 256, 0, s>>>(c->nElems, c->geom, c->geomP);
-        c->launches++;
-        c->geomPValid = true;
-    }
+    ensure_packed_geometry(c);
     const int64_t nChunks = (c->nnzb + kBlkChunk - 1) / kBlkChunk;
     // orthotropic sparsity pattern of the constant tensor (isotropic included)?
     constexpr int F = flat_len(N);

@@ -195,8 +195,12 @@ int mfem_b200_set_option(mfem_b200_handle h, const char *name, int64_t value) {
     } else if (n == "graph") {
         h->opt_graph = value != 0;
     } else if (n == "spmv_kernel") {
-        MFEM_REQUIRE(value >= 0 && value <= 5, MFEM_B200_ERR_INVALID, "spmv_kernel must be 0 (auto), 1 (direct loads), 2 (TMA ring), 3 (index-pipelined), 4 (symmetric) or 5 (128-bit load timing probe: wrong results)");
+        MFEM_REQUIRE(value >= 0 && value <= 6, MFEM_B200_ERR_INVALID, "spmv_kernel must be 0 (auto), 1 (direct loads), 2 (TMA ring), 3 (index-pipelined), 4 (symmetric), 5 (128-bit load timing probe: wrong results) or 6 (mfem_b200_spmv evaluates the mesh-based operator instead of the stored matrix)");
         h->opt_spmv_kernel = (int)value;
+    } else if (n == "matrix_free") {
+        MFEM_REQUIRE(value >= -1 && value <= 1, MFEM_B200_ERR_INVALID,
+                     "matrix_free must be -1 (automatic: 3D quadratic elements), 0 (stored-matrix SpMV) or 1 (mesh-based operator whenever a mesh is set)");
+        h->opt_matrix_free = (int)value;
     } else if (n == "coarse_aggregates") {
         MFEM_REQUIRE(value >= -1 && value <= 5461, MFEM_B200_ERR_INVALID,
                      "coarse_aggregates must be -1 (automatic), 0 (block-Jacobi only) or 1 .. 5461 large aggregates");
@@ -564,6 +568,14 @@ int mfem_b200_time_spmv(mfem_b200_handle h, int iters, double *seconds_per_launc
     API_BEGIN(h)
     MFEM_REQUIRE(iters > 0 && seconds_per_launch, MFEM_B200_ERR_INVALID, "time_spmv: bad arguments");
     *seconds_per_launch = time_spmv(h, iters);
+    API_END(h)
+}
+
+int mfem_b200_time_operator(mfem_b200_handle h, int iters, double *seconds_per_product, double *seconds_parts,
+                            int *matrix_free) {
+    API_BEGIN(h)
+    MFEM_REQUIRE(iters > 0 && seconds_per_product, MFEM_B200_ERR_INVALID, "time_operator: bad arguments");
+    *seconds_per_product = time_operator(h, iters, matrix_free, seconds_parts);
     API_END(h)
 }
 

@@ -105,6 +105,7 @@ struct mfem_b200_ctx {
     int opt_spmv_min_blocks = 0;           // SpMV occupancy experiment: 3 or 5 CTAs per SM instead of 4 (N = 3, 32 lanes)
     int opt_spmv_prefetch = 0;             // SpMV: L2 prefetch of the row a warp streams next (one prefetch instruction per lane and row)
     int opt_spmv_lanes = 0;                // lanes per block row in the SpMV (0 = choose from the mean row length)
+    int opt_matrix_free = -1;              // PCG operator: -1 auto (mesh-based for 3D quadratic elements), 0 assembled SpMV, 1 mesh-based whenever possible
     int opt_coarse = -1;                   // large aggregates of the multilevel preconditioner: -1 automatic (from the
                                            // problem size; block-Jacobi only below 30k DoFs), 0 = block-Jacobi only
     int opt_coarse_fine = 64;              // DoFs (nodes) per small (level-1) aggregate; 0 = no level 1 (two-level method)
@@ -125,6 +126,7 @@ struct mfem_b200_ctx {
     bool geomValid = false;
     mfem::DevBuf<double> geomP;            // [nElems*16] packed (G_a, vol) slots for the block-owner assembly
     bool geomPValid = false;
+    mfem::DevBuf<double> elemY;            // [nElems*npe*N] per-element results of the matrix-free operator (matfree.inl)
 
     // material
     bool haveMaterial = false, perElemD = false;
@@ -248,6 +250,7 @@ void upload_external_bsr(mfem_b200_ctx *c, int dim, int64_t nb, const std::vecto
 void build_coloring(mfem_b200_ctx *c);
 // assemble.cu
 void assemble_values(mfem_b200_ctx *c);
+void ensure_packed_geometry(mfem_b200_ctx *c);     // geomP from geom (128-byte records)
 // solver.cu
 void spmv_plain(mfem_b200_ctx *c, const double *x_int, double *y_int);
 void build_preconditioner(mfem_b200_ctx *c);
@@ -260,6 +263,7 @@ void free_work_multi(mfem_b200_ctx *c);
 void free_coarse_space(mfem_b200_ctx *c);
 bool will_use_coarse(mfem_b200_ctx *c);
 double time_spmv(mfem_b200_ctx *c, int iters);
+double time_operator(mfem_b200_ctx *c, int iters, int *matrixFree, double *secondsParts);   // what the PCG launches per iteration for K*p
 int64_t get_coarse_array(mfem_b200_ctx *c, const std::string &name, double *out, int64_t capacity);
 void apply_preconditioner(mfem_b200_ctx *c, const double *r_int, double *z_int, double *rz);
 // comm.cu

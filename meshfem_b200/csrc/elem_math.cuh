@@ -13,6 +13,7 @@
 // Everything is FP64.  Functions are __host__ __device__ so the CPU unit test
 // (tests/test_elem_math_host.py) can check them against the oracle without a GPU.
 #pragma once
+#include <cmath>
 #include <cstdint>
 
 #ifdef __CUDACC__
@@ -266,6 +267,153 @@ MFEM_HD void ke_row_slice_rot(const ElemGeom<N> &g, const double *D, int i, int 
                 emit(col, blk);
             }
         }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Matrix-free element operator  ye = Ke * xe  without forming Ke (the PCG's operator for quadratic
+// elements, csrc/matfree.inl).  Same quantity as perElementStiffness (LinearElasticity.hh:165-232)
+// applied to a vector, i.e. what Simulator::applyStiffnessMatrix (LinearElasticity.hh:801-823) sums,
+// evaluated as  ye[i] = vol sum_q w_q sigma(q) grad phi_i(q),  sigma(q) = C : grad u(q),
+// on the (N+1)-point degree-2 rule of w_coeff() -- exact for the quadratic integrand, so it equals
+// Ke*xe up to rounding.  The rule's q-th point has lambda_b(q) = c1 + (c0 - c1) [b == q]; with
+//   k0 = 4 c1 - 1, k1 = 4 c1, kd = 4 (c0 - c1)
+// the coefficient of grad lambda_a in grad phi at point q is k0 + kd [a == q] (vertex function a) and
+// k1 + kd [e == q] (edge function (a, e)), which leaves per element: one "base" displacement
+// gradient, N+1 rank-one corrections, N+1 stress evaluations and 2 small contractions per output node
+// (~700 FMA for a quadratic tet instead of the 900 multiply-adds of a dense 30x30 product, and
+// 40 + 128 bytes of input instead of 7200).
+// Ga[a][r] = d lambda_a / d x_r (ElemGeom::G transposed: the packed 32-byte slots of geomP).
+// ---------------------------------------------------------------------------
+template <int N>
+MFEM_HD constexpr int edge_between(int a, int b) {       // local edge index of the edge {a, b}, a != b
+    const int lo = a < b ? a : b, hi = a < b ? b : a;
+    if (N == 2) return hi - lo == 1 ? lo : 2;            // (0,1)->0 (1,2)->1 (0,2)->2
+    return hi == 3 ? (lo == 0 ? 3 : (lo == 1 ? 5 : 4))   // (0,3)->3 (1,3)->5 (2,3)->4
+                   : (hi - lo == 1 ? lo : 2);            // (0,1)->0 (1,2)->1 (0,2)->2
+}
+
+// sigma_flat = scale * D * (shear-doubled flat strain of the displacement gradient H[d][t] = d u_d / d x_t)
+template <int N>
+MFEM_HD void stress_flat(const double *D, const double H[N][N], double scale, double sig[flat_len(N)]) {
+    constexpr int F = flat_len(N);
+    double e[F];
+#pragma unroll
+    for (int d = 0; d < N; ++d) e[d] = H[d][d];
+    if (N == 2) e[2] = H[0][1] + H[1][0];
+    else { e[3] = H[1][2] + H[2][1]; e[4] = H[0][2] + H[2][0]; e[5] = H[0][1] + H[1][0]; }
+#pragma unroll
+    for (int i = 0; i < F; ++i) {
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < F; ++j) s = fma(D[i * F + j], e[j], s);
+        sig[i] = scale * s;
+    }
+}
+
+// out[c] = sum_r sigma_{rc} g[r]
+template <int N>
+MFEM_HD void sig_dot(const double sig[flat_len(N)], const double g[N], double out[N]) {
+#pragma unroll
+    for (int c = 0; c < N; ++c) {
+        double s = 0.0;
+#pragma unroll
+        for (int r = 0; r < N; ++r) s = fma(sig[flat_idx<N>(r, c)], g[r], s);
+        out[c] = s;
+    }
+}
+
+template <int N, int DEG, class GetX, class PutY>
+MFEM_HD void elem_apply(const double Ga[N + 1][N], double vol, const double *D, GetX &&getx, PutY &&puty) {
+    constexpr int F = flat_len(N);
+    if (DEG == 1) {
+        double H[N][N];
+#pragma unroll
+        for (int d = 0; d < N; ++d)
+#pragma unroll
+            for (int t = 0; t < N; ++t) H[d][t] = 0.0;
+#pragma unroll
+        for (int a = 0; a <= N; ++a)
+#pragma unroll
+            for (int d = 0; d < N; ++d) {
+                const double xv = getx(a, d);
+#pragma unroll
+                for (int t = 0; t < N; ++t) H[d][t] = fma(xv, Ga[a][t], H[d][t]);
+            }
+        double sig[F];
+        stress_flat<N>(D, H, vol, sig);
+#pragma unroll
+        for (int a = 0; a <= N; ++a) {
+            double o[N];
+            sig_dot<N>(sig, Ga[a], o);
+#pragma unroll
+            for (int c = 0; c < N; ++c) puty(a, c, o[c]);
+        }
+        return;
+    }
+    constexpr double c0 = (N == 3) ? 0.58541019662496845446 : 2.0 / 3.0;
+    constexpr double c1 = (N == 3) ? 0.13819660112501051518 : 1.0 / 6.0;
+    constexpr double k0 = 4.0 * c1 - 1.0, k1 = 4.0 * c1, kd = 4.0 * (c0 - c1);
+    const double wv = vol / (N + 1);
+    // base gradient: coefficient vectors with lambda == c1 everywhere
+    double Hb[N][N];
+#pragma unroll
+    for (int d = 0; d < N; ++d)
+#pragma unroll
+        for (int t = 0; t < N; ++t) Hb[d][t] = 0.0;
+#pragma unroll
+    for (int a = 0; a <= N; ++a)
+#pragma unroll
+        for (int d = 0; d < N; ++d) {
+            double es = 0.0;
+#pragma unroll
+            for (int b = 0; b <= N; ++b)
+                if (b != a) es += getx(N + 1 + edge_between<N>(a, b), d);
+            const double bv = fma(k1, es, k0 * getx(a, d));
+#pragma unroll
+            for (int t = 0; t < N; ++t) Hb[d][t] = fma(bv, Ga[a][t], Hb[d][t]);
+        }
+    double sig[N + 1][F], ssum[F];
+#pragma unroll
+    for (int i = 0; i < F; ++i) ssum[i] = 0.0;
+#pragma unroll
+    for (int q = 0; q <= N; ++q) {
+        double H[N][N];
+#pragma unroll
+        for (int d = 0; d < N; ++d)
+#pragma unroll
+            for (int t = 0; t < N; ++t) H[d][t] = Hb[d][t];
+#pragma unroll
+        for (int a = 0; a <= N; ++a)
+#pragma unroll
+            for (int d = 0; d < N; ++d) {
+                const double xv = kd * getx(a == q ? a : N + 1 + edge_between<N>(a, q), d);
+#pragma unroll
+                for (int t = 0; t < N; ++t) H[d][t] = fma(xv, Ga[a][t], H[d][t]);
+            }
+        stress_flat<N>(D, H, wv, sig[q]);
+#pragma unroll
+        for (int i = 0; i < F; ++i) ssum[i] += sig[q][i];
+    }
+    double T[N + 1][N];
+#pragma unroll
+    for (int a = 0; a <= N; ++a) sig_dot<N>(ssum, Ga[a], T[a]);
+#pragma unroll
+    for (int a = 0; a <= N; ++a) {
+        double o[N];
+        sig_dot<N>(sig[a], Ga[a], o);
+#pragma unroll
+        for (int c = 0; c < N; ++c) puty(a, c, fma(kd, o[c], k0 * T[a][c]));
+    }
+    constexpr int NE = N * (N + 1) / 2;
+#pragma unroll
+    for (int k = 0; k < NE; ++k) {
+        const int s = edge_start(k), e = edge_end(k);
+        double o1[N], o2[N];
+        sig_dot<N>(sig[e], Ga[s], o1);
+        sig_dot<N>(sig[s], Ga[e], o2);
+#pragma unroll
+        for (int c = 0; c < N; ++c) puty(N + 1 + k, c, fma(kd, o1[c] + o2[c], k1 * (T[s][c] + T[e][c])));
     }
 }
 

@@ -1,0 +1,175 @@
+// K9: the PCG's operator WITHOUT the assembled matrix (quadratic elements).
+//
+// y = mask(K x) [, x.y] evaluated from the mesh: the quantity Simulator::applyStiffnessMatrix
+// (LinearElasticity.hh:801-823) sums element by element, with the per-element product
+// perElementStiffness * x (LinearElasticity.hh:165-232) evaluated by elem_apply (elem_math.cuh)
+// on the degree-2 rule instead of through a stored 30x30 matrix.  Why: the block-CSR SpMV streams
+// 76 bytes per 3x3 block -- 2060 bytes per node of a quadratic-tet mesh, 30.9 GB per product on the
+// 10.2 M-element workload -- and is HBM-bound at 6.8 ms.  The mesh-based operator reads 40 bytes of
+// DoF ids + 128 bytes of packed geometry per element and moves the 30 element results once through
+// HBM: ~0.65 KB per element, ~7 GB per product.
+//
+// Two kernels, no atomics, bit-reproducible:
+//   k_mf_elements  one thread per element: gather the 10 x blocks (L2-resident, evict-last), ~700
+//                  FMA, store the element's 30 results into its own slots elemY[e*npe + i][c];
+//   k_mf_gather    4 lanes per DoF row: sum the row's slots in the fixed order of the incidence
+//                  list (incPtr / incList of the symbolic phase, (element, local node) order), apply
+//                  the Dirichlet mask, write y and accumulate x.y (same two-stage deterministic
+//                  reduction as the SpMV epilogue, same scal slot).
+// The assembled matrix stays what the preconditioner set-up, the b = f - K u_fix product of
+// non-eligible cases, export and the C-ABI spmv read; the operator is used where the Krylov loop
+// multiplies (option `matrix_free`: -1 auto = quadratic elements of a mesh, 0 never, 1 whenever a
+// mesh + material are present).
+//
+// Included by solver.cu (needs its reduction helpers and load wrappers).
+
+constexpr int kMfThreads = 128;
+
+__device__ __forceinline__ void ld_slot4(const double *p, uint64_t pol, double &a, double &b, double &c, double &d) {
+    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f64 {%0,%1,%2,%3}, [%4], %5;"
+        : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p), "l"(pol));
+}
+
+template <int N, int DEG, bool PER_ELEM_D>
+__global__ void __launch_bounds__(kMfThreads, 3)
+k_mf_elements(int64_t nElems, const int32_t *__restrict__ elemDof, const double *__restrict__ geomP, const MatD Dc,
+              const double *__restrict__ Delem, const double *__restrict__ x, double *__restrict__ elemY,
+              const int *status) {
+    constexpr int NPE = nodes_per_elem(N, DEG);
+    constexpr int F = flat_len(N);
+    if (status && status[ST_STATE] != 0) return;
+    const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= nElems) return;
+    const uint64_t polStream = l2_policy_evict_first(), polKeep = l2_policy_evict_last();
+    int32_t nd[NPE];
+#pragma unroll
+    for (int j = 0; j < NPE; ++j) nd[j] = ld_stream_s32(elemDof + e * NPE + j, polStream);
+    double Ga[N + 1][N], vol = 0.0;
+#pragma unroll
+    for (int a = 0; a <= N; ++a) {
+        double g0, g1, g2, v;
+        ld_slot4(geomP + e * 16 + a * 4, polStream, g0, g1, g2, v);
+        Ga[a][0] = g0; Ga[a][1] = g1;
+        if (N == 3) Ga[a][2] = g2;
+        vol = v;
+    }
+    double xe[NPE][N];
+#pragma unroll
+    for (int j = 0; j < NPE; ++j)
+#pragma unroll
+        for (int d = 0; d < N; ++d) xe[j][d] = ld_keep_f64(x + (int64_t)nd[j] * N + d, polKeep);
+    const double *D = PER_ELEM_D ? Delem + e * (F * F) : Dc.d;
+    double ye[NPE * N];
+    elem_apply<N, DEG>(Ga, vol, D, [&](int j, int d) { return xe[j][d]; },
+                       [&](int i, int c, double v) { ye[i * N + c] = v; });
+    // the element's record is 16-byte aligned (NPE * N is even): 128-bit stores
+    static_assert((NPE * N) % 2 == 0, "element record must hold an even number of doubles");
+    double2 *out = reinterpret_cast<double2 *>(elemY + e * (NPE * N));
+#pragma unroll
+    for (int k = 0; k < NPE * N / 2; ++k) out[k] = make_double2(ye[2 * k], ye[2 * k + 1]);
+}
+
+template <int N, bool MASKED, bool DOT>
+__global__ void __launch_bounds__(kVecThreads)
+k_mf_gather(int64_t nb, const int64_t *__restrict__ incPtr, const int32_t *__restrict__ incList,
+            const double *__restrict__ elemY, const double *__restrict__ x, double *__restrict__ y,
+            const uint8_t *__restrict__ fixedMask, double *partials, unsigned *ticket, double *dotOut,
+            const int *status) {
+    constexpr int LPR = 4;                      // lanes per DoF row
+    constexpr unsigned FULL = 0xffffffffu;
+    if (status && status[ST_STATE] != 0) return;
+    const uint64_t polStream = l2_policy_evict_first();
+    const int sl = threadIdx.x & (LPR - 1);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x / LPR;
+    double dot = 0.0;
+    for (int64_t rowBase = ((int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31)) / LPR; rowBase < nb; rowBase += stride) {
+        const int64_t row = rowBase + ((threadIdx.x & 31) / LPR);
+        int64_t k0 = 0, k1 = 0;
+        if (row < nb) { k0 = incPtr[row]; k1 = incPtr[row + 1]; }
+        double acc[N];
+#pragma unroll
+        for (int c = 0; c < N; ++c) acc[c] = 0.0;
+        int64_t k = k0 + sl;
+        for (; k + LPR < k1; k += 2 * LPR) {     // two incidences per lane in flight
+            const int s0 = ld_stream_s32(incList + k, polStream), s1 = ld_stream_s32(incList + k + LPR, polStream);
+            const double *p0 = elemY + (int64_t)s0 * N, *p1 = elemY + (int64_t)s1 * N;
+            double a0[N], a1[N];
+#pragma unroll
+            for (int c = 0; c < N; ++c) { a0[c] = ld_stream_f64(p0 + c, polStream); a1[c] = ld_stream_f64(p1 + c, polStream); }
+#pragma unroll
+            for (int c = 0; c < N; ++c) acc[c] = (acc[c] + a0[c]) + a1[c];
+        }
+        if (k < k1) {
+            const int s0 = ld_stream_s32(incList + k, polStream);
+            const double *p0 = elemY + (int64_t)s0 * N;
+#pragma unroll
+            for (int c = 0; c < N; ++c) acc[c] += ld_stream_f64(p0 + c, polStream);
+        }
+        // fixed-shape tree over the 4 lanes (the same value in every lane of the group)
+#pragma unroll
+        for (int c = 0; c < N; ++c) {
+            acc[c] += __shfl_xor_sync(FULL, acc[c], 1);
+            acc[c] += __shfl_xor_sync(FULL, acc[c], 2);
+        }
+        if (row < nb && sl < N) {
+            double out = sl == 0 ? acc[0] : (sl == 1 ? acc[1] : acc[N - 1]);
+            if (MASKED && fixedMask[row * N + sl]) out = 0.0;
+            y[row * N + sl] = out;
+            if (DOT) dot = fma(out, x[row * N + sl], dot);
+        }
+    }
+    if (DOT) {
+        double v1[1] = {dot};
+        block_reduce_store<1>(v1, partials);
+        if (last_block(ticket)) {
+            const double s = final_sum(partials, gridDim.x);
+            if (threadIdx.x == 0) dotOut[0] = s;
+        }
+    }
+}
+
+// is the mesh-based operator usable / chosen for this handle?
+static bool matrix_free_eligible(mfem_b200_ctx *c) {
+    return !c->externalMatrix && c->nElems > 0 && c->patternValid && c->geomValid && c->haveMaterial && c->elemDof.p && c->incPtr.p &&
+           c->incList.p && c->totalInc == c->nElems * (int64_t)c->npe;
+}
+static bool use_matrix_free(mfem_b200_ctx *c) {
+    if (c->opt_matrix_free == 0 || !matrix_free_eligible(c)) return false;
+    if (c->opt_matrix_free > 0) return true;
+    return c->deg == 2 && c->N == 3;            // auto: where the stored matrix is 5x the mesh (27 blocks per row)
+}
+
+template <int N, int DEG>
+static void launch_matrix_free_nd(mfem_b200_ctx *c, const double *x, double *y, bool masked, bool dot, int phases) {
+    PcgWork &w = c->work;
+    cudaStream_t s = c->stream;
+    ensure_packed_geometry(c);
+    const size_t need = (size_t)c->nElems * c->npe * N;
+    if (c->elemY.n != need) c->elemY.alloc(need);
+    const int *status = (masked && dot) ? w.status.p : nullptr;      // in-loop launches turn into no-ops once the solve left "running"
+    const int grid = grid_for(c->nElems, kMfThreads);
+    if (!(phases & 1)) {}
+    else if (c->perElemD)
+        k_mf_elements<N, DEG, true><<<grid, kMfThreads, 0, s>>>(c->nElems, c->elemDof, c->geomP, c->Dconst, c->Delem, x, c->elemY, status);
+    else
+        k_mf_elements<N, DEG, false><<<grid, kMfThreads, 0, s>>>(c->nElems, c->elemDof, c->geomP, c->Dconst, nullptr, x, c->elemY, status);
+    const int64_t ctas = (c->nDofs * 4 + kVecThreads - 1) / kVecThreads;
+    const int ggrid = (int)std::max<int64_t>(1, std::min<int64_t>(ctas, std::min<int64_t>(kMaxPartials, (int64_t)sm_count(c) * 8)));
+    if (!(phases & 2)) {}
+    else if (masked && dot)
+        k_mf_gather<N, true, true><<<ggrid, kVecThreads, 0, s>>>(c->nDofs, c->incPtr, c->incList, c->elemY, x, y, c->fixedMask,
+                                                                 w.partials, w.ticket, w.scal.p + S_PAP, status);
+    else if (masked)
+        k_mf_gather<N, true, false><<<ggrid, kVecThreads, 0, s>>>(c->nDofs, c->incPtr, c->incList, c->elemY, x, y, c->fixedMask,
+                                                                  nullptr, nullptr, nullptr, nullptr);
+    else
+        k_mf_gather<N, false, false><<<ggrid, kVecThreads, 0, s>>>(c->nDofs, c->incPtr, c->incList, c->elemY, x, y, nullptr,
+                                                                   nullptr, nullptr, nullptr, nullptr);
+    c->launches += (phases & 1) + ((phases >> 1) & 1);
+}
+
+template <int N>
+static void launch_matrix_free(mfem_b200_ctx *c, const double *x, double *y, bool masked, bool dot, int phases = 3) {
+    if (c->deg == 2) launch_matrix_free_nd<N, 2>(c, x, y, masked, dot, phases);
+    else launch_matrix_free_nd<N, 1>(c, x, y, masked, dot, phases);
+}

@@ -1228,6 +1228,8 @@ static int sm_count(mfem_b200_ctx *c) {
     return n > 0 ? n : 148;
 }
 
+#include "matfree.inl"
+
 static int spmv_lanes(mfem_b200_ctx *c) {
     if (c->opt_spmv_lanes == 8 || c->opt_spmv_lanes == 16 || c->opt_spmv_lanes == 32) return c->opt_spmv_lanes;
     const double meanL = c->nDofs ? double(c->nnzb) * c->N / double(c->nDofs) : 0.0;   // scalars per scalar row
@@ -1426,9 +1428,21 @@ static void launch_spmv(mfem_b200_ctx *c, const double *x, double *y, bool maske
     }
 }
 
+// what the Krylov loops multiply with: the mesh-based operator (matfree.inl) where it is chosen, else the stored matrix
+template <int N>
+static void launch_operator(mfem_b200_ctx *c, const double *x, double *y, bool masked, bool dot) {
+    if (use_matrix_free(c)) launch_matrix_free<N>(c, x, y, masked, dot);
+    else launch_spmv<N>(c, x, y, masked, dot);
+}
+
 void spmv_plain(mfem_b200_ctx *c, const double *x_int, double *y_int) {
     MFEM_REQUIRE(c->valuesValid, MFEM_B200_ERR_INVALID, "spmv: matrix not assembled");
-    if (c->N == 3) launch_spmv<3>(c, x_int, y_int, false, false);
+    if (c->opt_spmv_kernel == 6) {      // the mesh-based operator on request (parity tests compare it with the stored matrix)
+        MFEM_REQUIRE(matrix_free_eligible(c), MFEM_B200_ERR_INVALID, "spmv_kernel 6: the matrix-free operator needs a mesh and a material");
+        ensure_work(c);
+        if (c->N == 3) launch_matrix_free<3>(c, x_int, y_int, false, false);
+        else launch_matrix_free<2>(c, x_int, y_int, false, false);
+    } else if (c->N == 3) launch_spmv<3>(c, x_int, y_int, false, false);
     else launch_spmv<2>(c, x_int, y_int, false, false);
     MFEM_CUDA(cudaGetLastError());
 }
@@ -1480,7 +1494,7 @@ void build_preconditioner(mfem_b200_ctx *c) {
 // y = mask(K x) completed across ranks: local SpMV, then the interface sum-exchange
 template <int N>
 static void spmv_exchanged(mfem_b200_ctx *c, const double *x, double *y, bool masked) {
-    launch_spmv<N>(c, x, y, masked, false);
+    launch_operator<N>(c, x, y, masked, false);
     halo_exchange_add(c, y, N);
 }
 
@@ -1546,7 +1560,7 @@ static void enqueue_iteration(mfem_b200_ctx *c) {
     const bool multi = c->nRanks > 1;
     const uint8_t *owned = multi ? halo_owned(c) : nullptr;
     CoarseSpace *cs = c->coarse;
-    launch_spmv<N>(c, w.p, w.Ap, true, true);                 // p.Ap fused into the SpMV epilogue -> scal[S_PAP]
+    launch_operator<N>(c, w.p, w.Ap, true, true);             // p.Ap fused into the epilogue -> scal[S_PAP]
     if (multi) {
         // masked rows stay zero through the exchange: every sharer masks the same DoFs
         if (!halo_exchange_add_allreduce1(c, w.Ap, N, w.scal.p + S_PAP)) {      // one kernel over the peer window, or NCCL
@@ -1577,7 +1591,7 @@ static void pcg_impl(mfem_b200_ctx *c, const double *f_int, double *u_int, doubl
     cudaEventRecord(e0, s);
     // b = f - K ufix  (masked rows are zeroed by the start-up kernel)
     if (multi) spmv_exchanged<N>(c, c->fixedVals, w.Ap, false);
-    else launch_spmv<N>(c, c->fixedVals, w.Ap, false, false);
+    else launch_operator<N>(c, c->fixedVals, w.Ap, false, false);
     k_axpby<<<vec_grid(c, n), kVecThreads, 0, s>>>(n, 1.0, f_int, -1.0, w.Ap, w.b);
     if (cs) {
         MFEM_CUDA(cudaMemsetAsync(cs->c1, 0, cs->c1.bytes(), s));
@@ -1759,6 +1773,46 @@ double time_spmv(mfem_b200_ctx *c, int iters) {
     const double sec = ms * 1e-3 / iters;
     c->timers["SpMV"] += ms * 1e-3;
     return sec;
+}
+
+// the product the PCG launches per iteration (mesh-based operator or the stored-matrix SpMV), masked + fused dot;
+// secondsParts[0..1]: the operator's two kernels timed alone (0 for the SpMV)
+double time_operator(mfem_b200_ctx *c, int iters, int *matrixFree, double *secondsParts) {
+    MFEM_REQUIRE(c->valuesValid, MFEM_B200_ERR_INVALID, "time_operator: matrix not assembled");
+    if (secondsParts) secondsParts[0] = secondsParts[1] = 0.0;
+    if (!use_matrix_free(c)) {
+        if (matrixFree) *matrixFree = 0;
+        return time_spmv(c, iters);
+    }
+    if (matrixFree) *matrixFree = 1;
+    ensure_work(c);
+    PcgWork &w = c->work;
+    cudaStream_t s = c->stream;
+    MFEM_CUDA(cudaMemsetAsync(w.p, 0x3f, w.p.bytes(), s));
+    MFEM_CUDA(cudaMemsetAsync(w.status, 0, w.status.bytes(), s));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    double sec[3] = {0, 0, 0};
+    const int phases[3] = {3, 1, 2};
+    for (int t = 0; t < 3; ++t) {
+        auto run = [&]() {
+            if (c->N == 3) launch_matrix_free<3>(c, w.p, w.Ap, true, true, phases[t]);
+            else launch_matrix_free<2>(c, w.p, w.Ap, true, true, phases[t]);
+        };
+        for (int k = 0; k < 3; ++k) run();
+        cudaEventRecord(e0, s);
+        for (int k = 0; k < iters; ++k) run();
+        cudaEventRecord(e1, s);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        sec[t] = ms * 1e-3 / iters;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    MFEM_CUDA(cudaGetLastError());
+    if (secondsParts) { secondsParts[0] = sec[1]; secondsParts[1] = sec[2]; }
+    c->timers["Matrix-free Operator"] += sec[0] * iters;
+    return sec[0];
 }
 
 }  // namespace mfem

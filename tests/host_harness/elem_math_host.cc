@@ -72,3 +72,24 @@ extern "C" int harness_int_grads(int N, int deg, const double *pts, double *out)
     else return 1;
     return 0;
 }
+
+// ye = Ke * xe through the matrix-free element operator (elem_apply)
+template <int N, int DEG>
+static void apply_elem(const double *pts, const double *D, const double *xe, double *ye) {
+    double p[N + 1][N];
+    for (int v = 0; v <= N; ++v) for (int r = 0; r < N; ++r) p[v][r] = pts[v * N + r];
+    ElemGeom<N> g;
+    embed(p, g);
+    double Ga[N + 1][N];
+    for (int a = 0; a <= N; ++a) for (int r = 0; r < N; ++r) Ga[a][r] = g.G[r][a];
+    elem_apply<N, DEG>(Ga, g.vol, D, [&](int j, int d) { return xe[j * N + d]; },
+                       [&](int i, int c, double v) { ye[i * N + c] = v; });
+}
+extern "C" int harness_elem_apply(int N, int deg, const double *pts, const double *D, const double *xe, double *ye) {
+    if (N == 2 && deg == 1) apply_elem<2, 1>(pts, D, xe, ye);
+    else if (N == 2 && deg == 2) apply_elem<2, 2>(pts, D, xe, ye);
+    else if (N == 3 && deg == 1) apply_elem<3, 1>(pts, D, xe, ye);
+    else if (N == 3 && deg == 2) apply_elem<3, 2>(pts, D, xe, ye);
+    else return 1;
+    return 0;
+}

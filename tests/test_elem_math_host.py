@@ -24,6 +24,7 @@ def harness(tmp_path_factory):
     lib.harness_ke.argtypes = [ctypes.c_int, ctypes.c_int, dp, dp, dp, dp]
     lib.harness_ke_rot.argtypes = [ctypes.c_int, ctypes.c_int, dp, dp, dp, ctypes.c_int]
     lib.harness_int_grads.argtypes = [ctypes.c_int, ctypes.c_int, dp, dp]
+    lib.harness_elem_apply.argtypes = [ctypes.c_int, ctypes.c_int, dp, dp, dp, dp]
     return lib
 
 
@@ -92,3 +93,29 @@ def test_integrated_shape_function_gradients(harness, N, deg):
     ref = vol[0] * np.einsum("iva,ra->ir", T, G[0]) / T.shape[1]
     assert np.abs(out - ref).max() <= 1e-13 * np.abs(ref).max()
     assert np.abs(out.sum(axis=0)).max() <= 1e-12 * np.abs(ref).max()        # partition of unity: gradients sum to zero
+
+
+@pytest.mark.parametrize("N", [2, 3])
+@pytest.mark.parametrize("deg", [1, 2])
+def test_matrix_free_element_operator_equals_Ke_times_x(harness, N, deg):
+    """elem_apply (the PCG's matrix-free operator, csrc/matfree.inl) == perElementStiffness (LinearElasticity.hh:165-232)
+    applied to a vector, on badly shaped simplices and isotropic / orthotropic / fully anisotropic tensors."""
+    rng = np.random.default_rng(900 + 10 * N + deg)
+    nn = orc.num_nodes(N, deg)
+    for trial in range(6):
+        P = _simplex(N, rng)
+        vol, G = orc.embed_simplices(P[None])
+        for D in _materials(N, rng):
+            D = np.ascontiguousarray(D)
+            ref = orc.per_element_stiffness(N, deg, vol, G, D)[0]
+            for _ in range(3):
+                xe = np.ascontiguousarray(rng.standard_normal(N * nn))
+                ye = np.zeros(N * nn)
+                assert harness.harness_elem_apply(N, deg, _ptr(np.ascontiguousarray(P)), _ptr(D), _ptr(xe), _ptr(ye)) == 0
+                want = ref @ xe
+                assert np.abs(ye - want).max() <= 1e-13 * np.abs(ref).max() * np.abs(xe).max() * N * nn
+            # rigid translations are in the kernel of Ke
+            ye = np.zeros(N * nn)
+            xe = np.ascontiguousarray(np.tile(rng.standard_normal(N), nn))
+            harness.harness_elem_apply(N, deg, _ptr(np.ascontiguousarray(P)), _ptr(D), _ptr(xe), _ptr(ye))
+            assert np.abs(ye).max() <= 1e-12 * np.abs(ref).max()

@@ -1,0 +1,43 @@
+"""Stored-matrix SpMV vs the mesh-based (matrix-free) operator on the GPU box, plus one solve with each:
+python tools/time_operator.py <cfg>"""
+import json, os, sys, time
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tools"))
+import meshfem_b200
+import workloads as wl
+
+cfg = sys.argv[1]
+grid, deg, mat = wl.CONFIGS[cfg]
+m = wl.grid_femmesh(grid, deg)
+fixed, vals, f = wl.cantilever_inputs(m)
+peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+h = meshfem_b200.Handle(0, coarse_aggregates=-1 if cfg != "cfg5" else 2048)
+h.set_mesh(3, deg, m.nodes, m.elem_nodes)
+h.set_material(wl.material(mat))
+h.assemble()
+h.fix_variables(fixed, vals)
+nb, nnzb = h.bsr_sizes()
+ne, npe = m.num_elements, m.elem_nodes.shape[1]
+t = min(h.time_spmv(20) for _ in range(2))
+by = nnzb * 76 + nb * 52
+print(json.dumps(dict(cfg=cfg, what="stored-matrix SpMV", ms=round(t * 1e3, 4), GBs=round(by / t / 1e9, 1), frac=round(by / t / 1e9 / peak, 4))), flush=True)
+h.set_option("matrix_free", 1)
+h.time_operator(3)
+r = [h.time_operator(20) for _ in range(2)]
+top = min(x[0] for x in r); te = min(x[1][0] for x in r); tg = min(x[1][1] for x in r)
+be = ne * (4 * npe + 128 + 24 * npe) + nb * 24
+bg = ne * npe * (24 + 4) + nb * (8 + 24 + 24 + 3)
+print(json.dumps(dict(cfg=cfg, what="matrix-free operator", ms=round(top * 1e3, 4), elements_ms=round(te * 1e3, 4), gather_ms=round(tg * 1e3, 4),
+                      elements_GBs=round(be / te / 1e9, 1), elements_frac=round(be / te / 1e9 / peak, 4),
+                      gather_GBs=round(bg / tg / 1e9, 1), gather_frac=round(bg / tg / 1e9 / peak, 4), speedup=round(t / top, 3))), flush=True)
+us = {}
+for mf in (0, 1):
+    h.set_option("matrix_free", mf)
+    for rep in range(2):
+        u, info = h.solve(f, rtol=1e-8, return_info=True)
+    us[mf] = np.asarray(u).reshape(-1)
+    print(json.dumps(dict(cfg=cfg, matrix_free=mf, iterations=info[0]["iterations"], solve_s=round(info[0]["seconds"], 4),
+                          ms_per_iteration=round(1e3 * info[0]["seconds"] / info[0]["iterations"], 4), rel_residual=info[0]["rel_residual"])), flush=True)
+print(json.dumps(dict(cfg=cfg, rel_l2_matrix_free_vs_stored=float(np.linalg.norm(us[1] - us[0]) / np.linalg.norm(us[0])))), flush=True)
+h.close()
