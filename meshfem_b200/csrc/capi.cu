@@ -201,6 +201,16 @@ int mfem_b200_set_option(mfem_b200_handle h, const char *name, int64_t value) {
         MFEM_REQUIRE(value >= -1 && value <= 1, MFEM_B200_ERR_INVALID,
                      "matrix_free must be -1 (automatic: 3D quadratic elements), 0 (stored-matrix SpMV) or 1 (mesh-based operator whenever a mesh is set)");
         h->opt_matrix_free = (int)value;
+    } else if (n == "mf_slot_pad") {
+        h->opt_mf_slot_pad = value != 0;
+    } else if (n == "mf_gather_lanes") {
+        MFEM_REQUIRE(value == 4 || value == 8, MFEM_B200_ERR_INVALID, "mf_gather_lanes must be 4 or 8");
+        h->opt_mf_gather_lanes = (int)value;
+    } else if (n == "mf_elem_order") {
+        h->opt_mf_elem_order = value != 0;
+    } else if (n == "mf_gather_policy") {
+        MFEM_REQUIRE(value >= 0 && value <= 3, MFEM_B200_ERR_INVALID, "mf_gather_policy must be 0 (evict_first), 1 (evict_last), 2 (evict_normal) or 3 (evict_last + L1 allocation)");
+        h->opt_mf_gather_policy = (int)value;
     } else if (n == "coarse_aggregates") {
         MFEM_REQUIRE(value >= -1 && value <= 5461, MFEM_B200_ERR_INVALID,
                      "coarse_aggregates must be -1 (automatic), 0 (block-Jacobi only) or 1 .. 5461 large aggregates");

@@ -106,6 +106,10 @@ struct mfem_b200_ctx {
     int opt_spmv_prefetch = 0;             // SpMV: L2 prefetch of the row a warp streams next (one prefetch instruction per lane and row)
     int opt_spmv_lanes = 0;                // lanes per block row in the SpMV (0 = choose from the mean row length)
     int opt_matrix_free = -1;              // PCG operator: -1 auto (mesh-based for 3D quadratic elements), 0 assembled SpMV, 1 mesh-based whenever possible
+    int opt_mf_slot_pad = 0;               // matrix-free operator, 3D: 32-byte (padded) result slots; 0 = packed 24-byte slots (A/B)
+    int opt_mf_gather_lanes = 8;           // matrix-free operator: lanes per DoF row in the gather kernel (4 or 8; the in-loop launch only)
+    int opt_mf_elem_order = 0;             // matrix-free operator: 1 = elements processed in the order of their DoFs (build_mf_plan), 0 = caller's order (A/B)
+    int opt_mf_gather_policy = 3;          // slot loads of the gather kernel: 0 evict_first, 1 evict_last, 2 evict_normal, 3 evict_last + L1 allocation (A/B)
     int opt_coarse = -1;                   // large aggregates of the multilevel preconditioner: -1 automatic (from the
                                            // problem size; block-Jacobi only below 30k DoFs), 0 = block-Jacobi only
     int opt_coarse_fine = 64;              // DoFs (nodes) per small (level-1) aggregate; 0 = no level 1 (two-level method)
@@ -126,7 +130,14 @@ struct mfem_b200_ctx {
     bool geomValid = false;
     mfem::DevBuf<double> geomP;            // [nElems*16] packed (G_a, vol) slots for the block-owner assembly
     bool geomPValid = false;
-    mfem::DevBuf<double> elemY;            // [nElems*npe*N] per-element results of the matrix-free operator (matfree.inl)
+    mfem::DevBuf<double> elemY;            // [nElems*npe*slot] per-element results of the matrix-free operator (matfree.inl)
+    // matrix-free operator plan (setup.cu build_mf_plan): the elements in the order of their DoFs (internal DoF ids follow
+    // a Morton curve), so that the rows the gather kernel sweeps find their slots in one moving window of elemY
+    bool mfPlanValid = false, mfGeomValid = false;
+    mfem::DevBuf<int32_t> mfPerm;          // [nElems] element handled by thread k
+    mfem::DevBuf<int32_t> mfElemDof;       // [nElems*npe] elemDof in that order
+    mfem::DevBuf<double> mfGeomP;          // [nElems*16]  geomP in that order
+    mfem::DevBuf<int32_t> mfIncList;       // [totalInc]   k*npe + i sorted by DoF (same extents as incPtr)
 
     // material
     bool haveMaterial = false, perElemD = false;
@@ -248,6 +259,7 @@ void finish_pattern(mfem_b200_ctx *c);
 void upload_external_bsr(mfem_b200_ctx *c, int dim, int64_t nb, const std::vector<int64_t> &rowptr,
                          const std::vector<int32_t> &colidx, const std::vector<double> &blocks);
 void build_coloring(mfem_b200_ctx *c);
+void build_mf_plan(mfem_b200_ctx *c);               // element order + incidence list of the matrix-free operator
 // assemble.cu
 void assemble_values(mfem_b200_ctx *c);
 void ensure_packed_geometry(mfem_b200_ctx *c);     // geomP from geom (128-byte records)

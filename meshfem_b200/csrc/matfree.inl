@@ -11,7 +11,10 @@
 //
 // Two kernels, no atomics, bit-reproducible:
 //   k_mf_elements  one thread per element: gather the 10 x blocks (L2-resident, evict-last), ~700
-//                  FMA, store the element's 30 results into its own slots elemY[e*npe + i][c];
+//                  FMA, store the element's 30 results into its own slots elemY[e*npe + i][c]
+//                  (3D: slots padded to 32 bytes = one sector, written and read by ONE 256-bit
+//                  access each; unpadded 24-byte slots cost the gather three 8-byte requests per
+//                  incidence, measured 2.54 ms instead of ... on the 10.2 M-element workload);
 //   k_mf_gather    4 lanes per DoF row: sum the row's slots in the fixed order of the incidence
 //                  list (incPtr / incList of the symbolic phase, (element, local node) order), apply
 //                  the Dirichlet mask, write y and accumulate x.y (same two-stage deterministic
@@ -30,11 +33,18 @@ __device__ __forceinline__ void ld_slot4(const double *p, uint64_t pol, double &
         : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p), "l"(pol));
 }
 
-template <int N, int DEG, bool PER_ELEM_D>
+__device__ __forceinline__ void st_slot4(double *p, double a, double b, double c, double d) {
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" :: "l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+// one result slot of elemY: N doubles, or -- PAD, 3D -- a 32-byte aligned record of 4 (one sector, one 256-bit access)
+template <int N, bool PAD>
+struct MfSlot { static constexpr int stride = (N == 3 && PAD) ? 4 : N; };
+
+template <int N, int DEG, bool PER_ELEM_D, bool PAD>
 __global__ void __launch_bounds__(kMfThreads, 3)
 k_mf_elements(int64_t nElems, const int32_t *__restrict__ elemDof, const double *__restrict__ geomP, const MatD Dc,
-              const double *__restrict__ Delem, const double *__restrict__ x, double *__restrict__ elemY,
-              const int *status) {
+              const double *__restrict__ Delem, const int32_t *__restrict__ perm, const double *__restrict__ x,
+              double *__restrict__ elemY, const int *status) {
     constexpr int NPE = nodes_per_elem(N, DEG);
     constexpr int F = flat_len(N);
     if (status && status[ST_STATE] != 0) return;
@@ -58,27 +68,53 @@ k_mf_elements(int64_t nElems, const int32_t *__restrict__ elemDof, const double 
     for (int j = 0; j < NPE; ++j)
 #pragma unroll
         for (int d = 0; d < N; ++d) xe[j][d] = ld_keep_f64(x + (int64_t)nd[j] * N + d, polKeep);
-    const double *D = PER_ELEM_D ? Delem + e * (F * F) : Dc.d;
+    const double *D = PER_ELEM_D ? Delem + (perm ? (int64_t)perm[e] : e) * (F * F) : Dc.d;   // materials keep the caller's element order
     double ye[NPE * N];
     elem_apply<N, DEG>(Ga, vol, D, [&](int j, int d) { return xe[j][d]; },
                        [&](int i, int c, double v) { ye[i * N + c] = v; });
-    // the element's record is 16-byte aligned (NPE * N is even): 128-bit stores
-    static_assert((NPE * N) % 2 == 0, "element record must hold an even number of doubles");
-    double2 *out = reinterpret_cast<double2 *>(elemY + e * (NPE * N));
+    if (N == 3 && PAD) {
+        double *out = elemY + e * (NPE * 4);
 #pragma unroll
-    for (int k = 0; k < NPE * N / 2; ++k) out[k] = make_double2(ye[2 * k], ye[2 * k + 1]);
+        for (int i = 0; i < NPE; ++i) st_slot4(out + 4 * i, ye[i * N], ye[i * N + 1], ye[i * N + N - 1], 0.0);
+    } else {
+        // the element's record is 16-byte aligned (NPE * N is even): 128-bit stores
+        static_assert((NPE * N) % 2 == 0, "element record must hold an even number of doubles");
+        double2 *out = reinterpret_cast<double2 *>(elemY + e * (NPE * N));
+#pragma unroll
+        for (int k = 0; k < NPE * N / 2; ++k) out[k] = make_double2(ye[2 * k], ye[2 * k + 1]);
+    }
 }
 
-template <int N, bool MASKED, bool DOT>
+// one slot of elemY -> a[0..N)
+template <int N, bool PAD>
+__device__ __forceinline__ void ld_result_slot(const double *elemY, int slot, uint64_t pol, bool l1, double (&a)[N]) {
+    if (N == 3 && PAD) {
+        double pad;
+        ld_slot4(elemY + (int64_t)slot * 4, pol, a[0], a[1], a[N - 1], pad);
+    } else if (N == 2) {
+        asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;"
+            : "=d"(a[0]), "=d"(a[1]) : "l"(elemY + (int64_t)slot * 2), "l"(pol));
+    } else {
+#pragma unroll
+        for (int c = 0; c < N; ++c)
+            a[c] = l1 ? ld_keep_f64(elemY + (int64_t)slot * N + c, pol) : ld_stream_f64(elemY + (int64_t)slot * N + c, pol);
+    }
+}
+
+template <int N, bool MASKED, bool DOT, bool PAD, int LPR = 4>
 __global__ void __launch_bounds__(kVecThreads)
 k_mf_gather(int64_t nb, const int64_t *__restrict__ incPtr, const int32_t *__restrict__ incList,
             const double *__restrict__ elemY, const double *__restrict__ x, double *__restrict__ y,
             const uint8_t *__restrict__ fixedMask, double *partials, unsigned *ticket, double *dotOut,
-            const int *status) {
-    constexpr int LPR = 4;                      // lanes per DoF row
+            const int *status, int slotPolicy) {
+    static_assert(LPR >= N && (LPR & (LPR - 1)) == 0, "lanes per DoF row: a power of two >= N");
     constexpr unsigned FULL = 0xffffffffu;
     if (status && status[ST_STATE] != 0) return;
+    // The slots are the only data of this kernel with reuse in L2 (the other slots of a fetched 64/128-byte line belong
+    // to rows swept a little later): they must outlive the pure streams (lists, extents, x, y).
     const uint64_t polStream = l2_policy_evict_first();
+    const uint64_t polSlot = (slotPolicy == 1 || slotPolicy == 3) ? l2_policy_evict_last() : (slotPolicy == 2 ? l2_policy_evict_normal() : polStream);
+    const bool l1 = slotPolicy == 3;            // packed slots: let the three 8-byte loads of a slot share its L1 line
     const int sl = threadIdx.x & (LPR - 1);
     const int64_t stride = (int64_t)gridDim.x * blockDim.x / LPR;
     double dot = 0.0;
@@ -92,25 +128,23 @@ k_mf_gather(int64_t nb, const int64_t *__restrict__ incPtr, const int32_t *__res
         int64_t k = k0 + sl;
         for (; k + LPR < k1; k += 2 * LPR) {     // two incidences per lane in flight
             const int s0 = ld_stream_s32(incList + k, polStream), s1 = ld_stream_s32(incList + k + LPR, polStream);
-            const double *p0 = elemY + (int64_t)s0 * N, *p1 = elemY + (int64_t)s1 * N;
             double a0[N], a1[N];
-#pragma unroll
-            for (int c = 0; c < N; ++c) { a0[c] = ld_stream_f64(p0 + c, polStream); a1[c] = ld_stream_f64(p1 + c, polStream); }
+            ld_result_slot<N, PAD>(elemY, s0, polSlot, l1, a0);
+            ld_result_slot<N, PAD>(elemY, s1, polSlot, l1, a1);
 #pragma unroll
             for (int c = 0; c < N; ++c) acc[c] = (acc[c] + a0[c]) + a1[c];
         }
         if (k < k1) {
-            const int s0 = ld_stream_s32(incList + k, polStream);
-            const double *p0 = elemY + (int64_t)s0 * N;
+            double a0[N];
+            ld_result_slot<N, PAD>(elemY, ld_stream_s32(incList + k, polStream), polSlot, l1, a0);
 #pragma unroll
-            for (int c = 0; c < N; ++c) acc[c] += ld_stream_f64(p0 + c, polStream);
+            for (int c = 0; c < N; ++c) acc[c] += a0[c];
         }
-        // fixed-shape tree over the 4 lanes (the same value in every lane of the group)
+        // fixed-shape tree over the LPR lanes (the same value in every lane of the group)
 #pragma unroll
-        for (int c = 0; c < N; ++c) {
-            acc[c] += __shfl_xor_sync(FULL, acc[c], 1);
-            acc[c] += __shfl_xor_sync(FULL, acc[c], 2);
-        }
+        for (int c = 0; c < N; ++c)
+#pragma unroll
+            for (int o = 1; o < LPR; o <<= 1) acc[c] += __shfl_xor_sync(FULL, acc[c], o);
         if (row < nb && sl < N) {
             double out = sl == 0 ? acc[0] : (sl == 1 ? acc[1] : acc[N - 1]);
             if (MASKED && fixedMask[row * N + sl]) out = 0.0;
@@ -139,37 +173,54 @@ static bool use_matrix_free(mfem_b200_ctx *c) {
     return c->deg == 2 && c->N == 3;            // auto: where the stored matrix is 5x the mesh (27 blocks per row)
 }
 
-template <int N, int DEG>
+template <int N, int DEG, bool PAD>
 static void launch_matrix_free_nd(mfem_b200_ctx *c, const double *x, double *y, bool masked, bool dot, int phases) {
     PcgWork &w = c->work;
     cudaStream_t s = c->stream;
-    ensure_packed_geometry(c);
-    const size_t need = (size_t)c->nElems * c->npe * N;
+    const bool ordered = c->opt_mf_elem_order != 0;
+    if (ordered) build_mf_plan(c);
+    else ensure_packed_geometry(c);
+    const int32_t *elemDof = ordered ? c->mfElemDof.p : c->elemDof.p;
+    const double *geomP = ordered ? c->mfGeomP.p : c->geomP.p;
+    const int32_t *incList = ordered ? c->mfIncList.p : c->incList.p;
+    const int32_t *perm = ordered ? c->mfPerm.p : nullptr;
+    const size_t need = (size_t)c->nElems * c->npe * MfSlot<N, PAD>::stride;
     if (c->elemY.n != need) c->elemY.alloc(need);
     const int *status = (masked && dot) ? w.status.p : nullptr;      // in-loop launches turn into no-ops once the solve left "running"
     const int grid = grid_for(c->nElems, kMfThreads);
     if (!(phases & 1)) {}
     else if (c->perElemD)
-        k_mf_elements<N, DEG, true><<<grid, kMfThreads, 0, s>>>(c->nElems, c->elemDof, c->geomP, c->Dconst, c->Delem, x, c->elemY, status);
+        k_mf_elements<N, DEG, true, PAD><<<grid, kMfThreads, 0, s>>>(c->nElems, elemDof, geomP, c->Dconst, c->Delem, perm, x, c->elemY, status);
     else
-        k_mf_elements<N, DEG, false><<<grid, kMfThreads, 0, s>>>(c->nElems, c->elemDof, c->geomP, c->Dconst, nullptr, x, c->elemY, status);
-    const int64_t ctas = (c->nDofs * 4 + kVecThreads - 1) / kVecThreads;
+        k_mf_elements<N, DEG, false, PAD><<<grid, kMfThreads, 0, s>>>(c->nElems, elemDof, geomP, c->Dconst, nullptr, nullptr, x, c->elemY, status);
+    const int lpr = c->opt_mf_gather_lanes == 8 ? 8 : 4;
+    const int pol = c->opt_mf_gather_policy;
+    const int64_t ctas = (c->nDofs * lpr + kVecThreads - 1) / kVecThreads;
     const int ggrid = (int)std::max<int64_t>(1, std::min<int64_t>(ctas, std::min<int64_t>(kMaxPartials, (int64_t)sm_count(c) * 8)));
     if (!(phases & 2)) {}
+    else if (masked && dot && lpr == 8)
+        k_mf_gather<N, true, true, PAD, 8><<<ggrid, kVecThreads, 0, s>>>(c->nDofs, c->incPtr, incList, c->elemY, x, y, c->fixedMask,
+                                                                         w.partials, w.ticket, w.scal.p + S_PAP, status, pol);
     else if (masked && dot)
-        k_mf_gather<N, true, true><<<ggrid, kVecThreads, 0, s>>>(c->nDofs, c->incPtr, c->incList, c->elemY, x, y, c->fixedMask,
-                                                                 w.partials, w.ticket, w.scal.p + S_PAP, status);
+        k_mf_gather<N, true, true, PAD><<<ggrid, kVecThreads, 0, s>>>(c->nDofs, c->incPtr, incList, c->elemY, x, y, c->fixedMask,
+                                                                      w.partials, w.ticket, w.scal.p + S_PAP, status, pol);
     else if (masked)
-        k_mf_gather<N, true, false><<<ggrid, kVecThreads, 0, s>>>(c->nDofs, c->incPtr, c->incList, c->elemY, x, y, c->fixedMask,
-                                                                  nullptr, nullptr, nullptr, nullptr);
+        k_mf_gather<N, true, false, PAD><<<ggrid, kVecThreads, 0, s>>>(c->nDofs, c->incPtr, incList, c->elemY, x, y, c->fixedMask,
+                                                                       nullptr, nullptr, nullptr, nullptr, pol);
     else
-        k_mf_gather<N, false, false><<<ggrid, kVecThreads, 0, s>>>(c->nDofs, c->incPtr, c->incList, c->elemY, x, y, nullptr,
-                                                                   nullptr, nullptr, nullptr, nullptr);
+        k_mf_gather<N, false, false, PAD><<<ggrid, kVecThreads, 0, s>>>(c->nDofs, c->incPtr, incList, c->elemY, x, y, nullptr,
+                                                                        nullptr, nullptr, nullptr, nullptr, pol);
     c->launches += (phases & 1) + ((phases >> 1) & 1);
 }
 
 template <int N>
 static void launch_matrix_free(mfem_b200_ctx *c, const double *x, double *y, bool masked, bool dot, int phases = 3) {
-    if (c->deg == 2) launch_matrix_free_nd<N, 2>(c, x, y, masked, dot, phases);
-    else launch_matrix_free_nd<N, 1>(c, x, y, masked, dot, phases);
+    const bool pad = N == 3 && c->opt_mf_slot_pad != 0;
+    if (c->deg == 2) {
+        if (pad) launch_matrix_free_nd<N, 2, N == 3>(c, x, y, masked, dot, phases);
+        else launch_matrix_free_nd<N, 2, false>(c, x, y, masked, dot, phases);
+    } else {
+        if (pad) launch_matrix_free_nd<N, 1, N == 3>(c, x, y, masked, dot, phases);
+        else launch_matrix_free_nd<N, 1, false>(c, x, y, masked, dot, phases);
+    }
 }
