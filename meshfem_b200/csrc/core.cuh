@@ -107,9 +107,12 @@ struct mfem_b200_ctx {
     int opt_spmv_lanes = 0;                // lanes per block row in the SpMV (0 = choose from the mean row length)
     int opt_matrix_free = -1;              // PCG operator: -1 auto (mesh-based for 3D quadratic elements), 0 assembled SpMV, 1 mesh-based whenever possible
     int opt_mf_slot_pad = 0;               // matrix-free operator, 3D: 32-byte (padded) result slots; 0 = packed 24-byte slots (A/B)
-    int opt_mf_gather_lanes = 8;           // matrix-free operator: lanes per DoF row in the gather kernel (4 or 8; the in-loop launch only)
+    int opt_mf_gather_lanes = 0;           // matrix-free operator: lanes per DoF row in the gather kernel (4 or 8, the in-loop launch only; 0 = 4 for chunk partials, 8 for slots)
     int opt_mf_elem_order = 0;             // matrix-free operator: 1 = elements processed in the order of their DoFs (build_mf_plan), 0 = caller's order (A/B)
     int opt_mf_gather_policy = 3;          // slot loads of the gather kernel: 0 evict_first, 1 evict_last, 2 evict_normal, 3 evict_last + L1 allocation (A/B)
+    int opt_mf_chunked = 1;                // matrix-free operator: 1 = per-chunk partial sums in shared memory (build_mf_chunks), 0 = one slot per (element, node)
+    int opt_mf_chunk_elems = 64;           // elements per chunk (= threads per CTA) of the chunked operator: 32, 64 or 128
+    int opt_mf_chunk_warps = 16;           // chunked operator: resident warps per SM the element kernel is compiled for (12 or 16)
     int opt_coarse = -1;                   // large aggregates of the multilevel preconditioner: -1 automatic (from the
                                            // problem size; block-Jacobi only below 30k DoFs), 0 = block-Jacobi only
     int opt_coarse_fine = 64;              // DoFs (nodes) per small (level-1) aggregate; 0 = no level 1 (two-level method)
@@ -138,6 +141,18 @@ struct mfem_b200_ctx {
     mfem::DevBuf<int32_t> mfElemDof;       // [nElems*npe] elemDof in that order
     mfem::DevBuf<double> mfGeomP;          // [nElems*16]  geomP in that order
     mfem::DevBuf<int32_t> mfIncList;       // [totalInc]   k*npe + i sorted by DoF (same extents as incPtr)
+    // chunked variant (setup.cu build_mf_chunks): opt_mf_chunk_elems consecutive elements = one CTA, which sums the results of its
+    // elements per DISTINCT DoF in shared memory and writes one partial per (chunk, DoF) instead of one slot per (element, node)
+    bool mfChunksValid = false;
+    int mfChunkElems = 0;                  // elements per chunk the tables were built for
+    int64_t mfPartials = 0;                // total (chunk, DoF) partials
+    mfem::DevBuf<int32_t> mfChunkBase;     // [nChunks+1] first partial of each chunk
+    mfem::DevBuf<int32_t> mfChunkDof;      // [nChunks*S] DoF of each chunk-local index (ascending DoF id), fixed stride, 0 beyond the chunk's count
+    mfem::DevBuf<uint16_t> mfLocalIdx;     // [nChunks*S] chunk-local DoF index of slot i*chunk + t   (S = chunk*npe)
+    mfem::DevBuf<uint16_t> mfCsrPtr;       // [nChunks*(S+1)] extents of each chunk-local DoF in the sorted slot order
+    mfem::DevBuf<uint16_t> mfCsrList;      // [nChunks*S] rank of slot i*chunk + t in the order sorted by chunk-local DoF ((element, local node) inside)
+    mfem::DevBuf<int64_t> mfIncPtr2;       // [nDofs+1]   DoF row -> its partials
+    mfem::DevBuf<int32_t> mfIncList2;      // [mfPartials]
 
     // material
     bool haveMaterial = false, perElemD = false;
@@ -260,6 +275,7 @@ void upload_external_bsr(mfem_b200_ctx *c, int dim, int64_t nb, const std::vecto
                          const std::vector<int32_t> &colidx, const std::vector<double> &blocks);
 void build_coloring(mfem_b200_ctx *c);
 void build_mf_plan(mfem_b200_ctx *c);               // element order + incidence list of the matrix-free operator
+void build_mf_chunks(mfem_b200_ctx *c);             // chunk-local DoF tables of the matrix-free operator
 // assemble.cu
 void assemble_values(mfem_b200_ctx *c);
 void ensure_packed_geometry(mfem_b200_ctx *c);     // geomP from geom (128-byte records)

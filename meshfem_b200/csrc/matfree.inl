@@ -85,6 +85,111 @@ k_mf_elements(int64_t nElems, const int32_t *__restrict__ elemDof, const double 
     }
 }
 
+// Chunked element kernel: one CTA = CH = 32 / 64 / 128 consecutive elements (tables: setup.cu build_mf_chunks).
+//   1. the chunk's DISTINCT x blocks are staged in shared memory once (buf[c][u], u = chunk-local DoF index);
+//   2. every thread (element) picks its npe blocks through the 16-bit local indices, evaluates elem_apply and puts its
+//      npe results back into the same buffer, at their rank in the order sorted by chunk-local DoF;
+//   3. the results are summed per chunk-local DoF -- a contiguous range, (element, local node) order inside -- and written as
+//      ONE partial per (chunk, DoF), contiguous per chunk -- 2.2-3x fewer bytes than one slot per (element, node), for
+//      this kernel's stores and for the gather kernel's loads alike.
+template <int N, int DEG, bool PER_ELEM_D, int kMfChunk, int WARPS = 12>      // WARPS resident per SM: 12 (<= 168 registers) or 16 (128, a few spills)
+__global__ void __launch_bounds__(kMfChunk, WARPS * 32 / kMfChunk)
+k_mf_chunk(int64_t nElems, const int32_t *__restrict__ chunkBase, const int32_t *__restrict__ chunkDof,
+           const uint16_t *__restrict__ localIdx, const uint16_t *__restrict__ csrPtr, const uint16_t *__restrict__ rankOfSlot,
+           const double *__restrict__ geomP, const MatD Dc, const double *__restrict__ Delem,
+           const double *__restrict__ x, double *__restrict__ partialY, const int *status) {
+    constexpr int NPE = nodes_per_elem(N, DEG);
+    constexpr int F = flat_len(N);
+    constexpr int S = kMfChunk * NPE;
+    __shared__ double buf[N * S];
+    if (status && status[ST_STATE] != 0) return;
+    const int64_t b = blockIdx.x;
+    const int t = threadIdx.x;
+    const int64_t e = b * kMfChunk + t;
+    const bool valid = e < nElems;
+    const uint64_t polStream = l2_policy_evict_first(), polKeep = l2_policy_evict_last();
+    // Loads are issued in program order and a warp stalls at the first USE of a pending result, so everything that does
+    // not depend on the chunk's extent goes out first (geometry, the 16-bit tables), then the extent, then -- in one
+    // batch per dependency level -- the DoF ids, the x blocks and the extents of the final sums.
+    double Ga[N + 1][N], vol = 0.0;
+    uint32_t lr[NPE];                           // chunk-local DoF index | rank of the result << 16
+    if (valid) {
+#pragma unroll
+        for (int a = 0; a <= N; ++a) {
+            double g0, g1, g2, v;
+            ld_slot4(geomP + e * 16 + a * 4, polStream, g0, g1, g2, v);
+            Ga[a][0] = g0; Ga[a][1] = g1;
+            if (N == 3) Ga[a][2] = g2;
+            vol = v;
+        }
+#pragma unroll
+        for (int i = 0; i < NPE; ++i)
+            lr[i] = (uint32_t)localIdx[b * S + i * kMfChunk + t] | ((uint32_t)rankOfSlot[b * S + i * kMfChunk + t] << 16);
+    }
+    // the chunk's fixed-stride tables are read without knowing its DoF count (entries past it are 0 = valid)
+    const uint16_t *ptr = csrPtr + b * (S + 1);
+    const int32_t *dofs = chunkDof + b * S;
+    constexpr int UB = 3;                       // chunk-local DoFs per thread handled in one batch (typical count / chunk = 2.5)
+    int pf0[UB], pf1[UB];
+    int64_t d[UB];
+#pragma unroll
+    for (int j = 0; j < UB; ++j) {
+        const int u = t + j * kMfChunk;
+        d[j] = u < S ? dofs[u] : 0;
+        pf0[j] = u < S ? ptr[u] : 0;
+        pf1[j] = u < S ? ptr[u + 1] : 0;
+    }
+    const int base = chunkBase[b], nu = chunkBase[b + 1] - base;
+    {
+        double xv[UB][N];
+#pragma unroll
+        for (int j = 0; j < UB; ++j)
+#pragma unroll
+            for (int c = 0; c < N; ++c) xv[j][c] = ld_keep_f64(x + d[j] * N + c, polKeep);
+#pragma unroll
+        for (int j = 0; j < UB; ++j)
+            if (t + j * kMfChunk < nu) {
+#pragma unroll
+                for (int c = 0; c < N; ++c) buf[c * S + t + j * kMfChunk] = xv[j][c];
+            }
+    }
+    for (int u = t + UB * kMfChunk; u < nu; u += kMfChunk) {      // rare: more than UB distinct DoFs per element of the chunk
+        const int64_t du = dofs[u];
+#pragma unroll
+        for (int c = 0; c < N; ++c) buf[c * S + u] = ld_keep_f64(x + du * N + c, polKeep);
+    }
+    __syncthreads();
+    double xe[NPE][N];
+    if (valid) {
+#pragma unroll
+        for (int i = 0; i < NPE; ++i)
+#pragma unroll
+            for (int c = 0; c < N; ++c) xe[i][c] = buf[c * S + (lr[i] & 0xffffu)];
+    }
+    __syncthreads();                            // everyone holds its x blocks: the buffer now takes the results
+    if (valid) {
+        const double *D = PER_ELEM_D ? Delem + e * (F * F) : Dc.d;
+        elem_apply<N, DEG>(Ga, vol, D, [&](int j, int d) { return xe[j][d]; },
+                           [&](int i, int c, double v) { buf[c * S + (lr[i] >> 16)] = v; });
+    }
+    __syncthreads();
+    // results sit in the order sorted by chunk-local DoF: DoF u owns the contiguous range ptr[u] .. ptr[u+1]
+    auto reduce_one = [&](int u, int k0, int k1) {
+        double acc[N];
+#pragma unroll
+        for (int c = 0; c < N; ++c) acc[c] = 0.0;
+        for (int k = k0; k < k1; ++k)
+#pragma unroll
+            for (int c = 0; c < N; ++c) acc[c] += buf[c * S + k];
+#pragma unroll
+        for (int c = 0; c < N; ++c) partialY[(int64_t)(base + u) * N + c] = acc[c];
+    };
+#pragma unroll
+    for (int j = 0; j < UB; ++j)
+        if (t + j * kMfChunk < nu) reduce_one(t + j * kMfChunk, pf0[j], pf1[j]);
+    for (int u = t + UB * kMfChunk; u < nu; u += kMfChunk) reduce_one(u, ptr[u], ptr[u + 1]);
+}
+
 // one slot of elemY -> a[0..N)
 template <int N, bool PAD>
 __device__ __forceinline__ void ld_result_slot(const double *elemY, int slot, uint64_t pol, bool l1, double (&a)[N]) {
@@ -177,45 +282,71 @@ template <int N, int DEG, bool PAD>
 static void launch_matrix_free_nd(mfem_b200_ctx *c, const double *x, double *y, bool masked, bool dot, int phases) {
     PcgWork &w = c->work;
     cudaStream_t s = c->stream;
-    const bool ordered = c->opt_mf_elem_order != 0;
-    if (ordered) build_mf_plan(c);
+    const bool chunked = c->opt_mf_chunked != 0;
+    const bool ordered = !chunked && c->opt_mf_elem_order != 0;
+    if (chunked) { build_mf_chunks(c); ensure_packed_geometry(c); }
+    else if (ordered) build_mf_plan(c);
     else ensure_packed_geometry(c);
     const int32_t *elemDof = ordered ? c->mfElemDof.p : c->elemDof.p;
     const double *geomP = ordered ? c->mfGeomP.p : c->geomP.p;
-    const int32_t *incList = ordered ? c->mfIncList.p : c->incList.p;
+    const int32_t *incList = chunked ? c->mfIncList2.p : (ordered ? c->mfIncList.p : c->incList.p);
+    const int64_t *incPtr = chunked ? c->mfIncPtr2.p : c->incPtr.p;
     const int32_t *perm = ordered ? c->mfPerm.p : nullptr;
-    const size_t need = (size_t)c->nElems * c->npe * MfSlot<N, PAD>::stride;
+    const size_t need = chunked ? (size_t)c->mfPartials * N : (size_t)c->nElems * c->npe * MfSlot<N, PAD>::stride;
     if (c->elemY.n != need) c->elemY.alloc(need);
     const int *status = (masked && dot) ? w.status.p : nullptr;      // in-loop launches turn into no-ops once the solve left "running"
     const int grid = grid_for(c->nElems, kMfThreads);
     if (!(phases & 1)) {}
+    else if (chunked) {
+        const int ch = c->mfChunkElems;
+        const unsigned nChunks = (unsigned)((c->nElems + ch - 1) / ch);
+#define MFEM_CHUNK(PE_, CH_, DELEM_)                                                                                        \
+    do {                                                                                                                    \
+        if (c->opt_mf_chunk_warps == 16)                                                                                    \
+            k_mf_chunk<N, DEG, PE_, CH_, 16><<<nChunks, CH_, 0, s>>>(c->nElems, c->mfChunkBase, c->mfChunkDof, c->mfLocalIdx, c->mfCsrPtr, \
+                                                                     c->mfCsrList, c->geomP, c->Dconst, DELEM_, x, c->elemY, status); \
+        else                                                                                                                \
+            k_mf_chunk<N, DEG, PE_, CH_, 12><<<nChunks, CH_, 0, s>>>(c->nElems, c->mfChunkBase, c->mfChunkDof, c->mfLocalIdx, c->mfCsrPtr, \
+                                                                     c->mfCsrList, c->geomP, c->Dconst, DELEM_, x, c->elemY, status); \
+    } while (0)
+        if (c->perElemD) {
+            if (ch == 32) MFEM_CHUNK(true, 32, c->Delem.p);
+            else if (ch == 64) MFEM_CHUNK(true, 64, c->Delem.p);
+            else MFEM_CHUNK(true, 128, c->Delem.p);
+        } else {
+            if (ch == 32) MFEM_CHUNK(false, 32, nullptr);
+            else if (ch == 64) MFEM_CHUNK(false, 64, nullptr);
+            else MFEM_CHUNK(false, 128, nullptr);
+        }
+#undef MFEM_CHUNK
+    }
     else if (c->perElemD)
         k_mf_elements<N, DEG, true, PAD><<<grid, kMfThreads, 0, s>>>(c->nElems, elemDof, geomP, c->Dconst, c->Delem, perm, x, c->elemY, status);
     else
         k_mf_elements<N, DEG, false, PAD><<<grid, kMfThreads, 0, s>>>(c->nElems, elemDof, geomP, c->Dconst, nullptr, nullptr, x, c->elemY, status);
-    const int lpr = c->opt_mf_gather_lanes == 8 ? 8 : 4;
+    const int lpr = c->opt_mf_gather_lanes == 8 ? 8 : (c->opt_mf_gather_lanes == 4 ? 4 : (chunked ? 4 : 8));   // 0 = auto
     const int pol = c->opt_mf_gather_policy;
     const int64_t ctas = (c->nDofs * lpr + kVecThreads - 1) / kVecThreads;
     const int ggrid = (int)std::max<int64_t>(1, std::min<int64_t>(ctas, std::min<int64_t>(kMaxPartials, (int64_t)sm_count(c) * 8)));
     if (!(phases & 2)) {}
     else if (masked && dot && lpr == 8)
-        k_mf_gather<N, true, true, PAD, 8><<<ggrid, kVecThreads, 0, s>>>(c->nDofs, c->incPtr, incList, c->elemY, x, y, c->fixedMask,
+        k_mf_gather<N, true, true, PAD, 8><<<ggrid, kVecThreads, 0, s>>>(c->nDofs, incPtr, incList, c->elemY, x, y, c->fixedMask,
                                                                          w.partials, w.ticket, w.scal.p + S_PAP, status, pol);
     else if (masked && dot)
-        k_mf_gather<N, true, true, PAD><<<ggrid, kVecThreads, 0, s>>>(c->nDofs, c->incPtr, incList, c->elemY, x, y, c->fixedMask,
+        k_mf_gather<N, true, true, PAD><<<ggrid, kVecThreads, 0, s>>>(c->nDofs, incPtr, incList, c->elemY, x, y, c->fixedMask,
                                                                       w.partials, w.ticket, w.scal.p + S_PAP, status, pol);
     else if (masked)
-        k_mf_gather<N, true, false, PAD><<<ggrid, kVecThreads, 0, s>>>(c->nDofs, c->incPtr, incList, c->elemY, x, y, c->fixedMask,
+        k_mf_gather<N, true, false, PAD><<<ggrid, kVecThreads, 0, s>>>(c->nDofs, incPtr, incList, c->elemY, x, y, c->fixedMask,
                                                                        nullptr, nullptr, nullptr, nullptr, pol);
     else
-        k_mf_gather<N, false, false, PAD><<<ggrid, kVecThreads, 0, s>>>(c->nDofs, c->incPtr, incList, c->elemY, x, y, nullptr,
+        k_mf_gather<N, false, false, PAD><<<ggrid, kVecThreads, 0, s>>>(c->nDofs, incPtr, incList, c->elemY, x, y, nullptr,
                                                                         nullptr, nullptr, nullptr, nullptr, pol);
     c->launches += (phases & 1) + ((phases >> 1) & 1);
 }
 
 template <int N>
 static void launch_matrix_free(mfem_b200_ctx *c, const double *x, double *y, bool masked, bool dot, int phases = 3) {
-    const bool pad = N == 3 && c->opt_mf_slot_pad != 0;
+    const bool pad = N == 3 && c->opt_mf_slot_pad != 0 && !c->opt_mf_chunked;      // chunk partials are always packed
     if (c->deg == 2) {
         if (pad) launch_matrix_free_nd<N, 2, N == 3>(c, x, y, masked, dot, phases);
         else launch_matrix_free_nd<N, 2, false>(c, x, y, masked, dot, phases);

@@ -518,7 +518,7 @@ void setup_mesh(mfem_b200_ctx *c, int dim, int degree, int64_t nNodes, const dou
     c->nDofs = c->periodic ? nDofs : nNodes;
     MFEM_REQUIRE(c->nDofs > 0 && c->nDofs <= nNodes, MFEM_B200_ERR_INVALID, "bad n_dofs");
     c->patternValid = c->valuesValid = c->geomValid = c->precondValid = c->workValid = false;
-    c->mfPlanValid = c->mfGeomValid = false;
+    c->mfPlanValid = c->mfGeomValid = c->mfChunksValid = false;
     c->meshVersion++;
     c->externalMatrix = false;
     c->fixedHost.assign((size_t)c->nDofs * dim, 0);
@@ -712,6 +712,153 @@ void build_mf_plan(mfem_b200_ctx *c) {
         c->mfGeomValid = true;
     }
     MFEM_CUDA(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------
+// Chunk tables of the matrix-free operator (matfree.inl k_mf_chunk).  A chunk = kMfChunk consecutive elements = one CTA.
+// Neighbouring elements share most of their DoFs (a quadratic-tet mesh has 1.4 DoFs per element but 10 (element, node)
+// slots), so the CTA reads each distinct x block once, sums its elements' results per distinct DoF in shared memory
+// and writes ONE partial per (chunk, DoF).  Per chunk, by one CTA-wide radix sort of its (DoF, slot) pairs:
+//   mfChunkDof    the distinct DoFs, ascending, fixed stride        (x staging, and the keys of the rows' partial lists)
+//   mfLocalIdx    chunk-local DoF index of every slot               (element threads read x / nothing else)
+//   mfCsrPtr/List extents of the chunk-local DoFs in the sorted order / rank of every slot in that order, which keeps
+//                 (element, local node) order inside a DoF (fixed-order sums: bit-reproducible)
+// and per DoF row the list of its partials (mfIncPtr2 / mfIncList2) for the unchanged gather kernel.
+// ---------------------------------------------------------------------------
+template <int NPE, int kMfChunk>
+__global__ void __launch_bounds__(kMfChunk)
+k_mf_chunk_tables(int64_t nElems, const int32_t *__restrict__ elemDof, uint16_t *__restrict__ localIdx,
+                  uint16_t *__restrict__ csrPtr, uint16_t *__restrict__ csrList, int32_t *__restrict__ uniqueDof,
+                  int32_t *__restrict__ nUnique) {
+    constexpr int S = kMfChunk * NPE;
+    using Sort = cub::BlockRadixSort<uint32_t, kMfChunk, NPE, uint32_t>;
+    using Disc = cub::BlockDiscontinuity<uint32_t, kMfChunk>;
+    using Scan = cub::BlockScan<int, kMfChunk>;
+    __shared__ union { typename Sort::TempStorage sort; typename Disc::TempStorage disc; typename Scan::TempStorage scan; } tmp;
+    const int64_t b = blockIdx.x;
+    const int t = threadIdx.x;
+    const int64_t e = b * kMfChunk + t;
+    uint32_t keys[NPE], vals[NPE];
+#pragma unroll
+    for (int i = 0; i < NPE; ++i) {
+        keys[i] = e < nElems ? (uint32_t)elemDof[e * NPE + i] : 0xffffffffu;     // padding of the last chunk sorts to the end
+        vals[i] = (uint32_t)(i * kMfChunk + t);
+    }
+    Sort(tmp.sort).Sort(keys, vals);            // blocked arrangement: thread t holds sorted positions t*NPE ..
+    __syncthreads();
+    int heads[NPE];
+    Disc(tmp.disc).FlagHeads(heads, keys, cub::Inequality());
+    __syncthreads();
+    int flag[NPE], idx[NPE], total = 0;
+#pragma unroll
+    for (int i = 0; i < NPE; ++i) flag[i] = (heads[i] && keys[i] != 0xffffffffu) ? 1 : 0;
+    Scan(tmp.scan).ExclusiveSum(flag, idx, total);
+    int nValid = 0;
+#pragma unroll
+    for (int i = 0; i < NPE; ++i) {
+        const int pos = t * NPE + i;
+        if (keys[i] == 0xffffffffu) continue;
+        ++nValid;
+        const int u = idx[i] + flag[i] - 1;     // chunk-local DoF index of this sorted position
+        localIdx[b * S + vals[i]] = (uint16_t)u;
+        csrList[b * S + vals[i]] = (uint16_t)pos;      // rank of the slot: its position in the order sorted by chunk-local DoF
+        if (flag[i]) {
+            csrPtr[b * (S + 1) + u] = (uint16_t)pos;
+            uniqueDof[b * S + u] = (int32_t)keys[i];
+        }
+    }
+    // number of valid sorted positions = end of the last extent
+    __shared__ int sValid;
+    if (t == 0) sValid = 0;
+    __syncthreads();
+    if (nValid) atomicAdd(&sValid, nValid);
+    __syncthreads();
+    if (t == 0) {
+        csrPtr[b * (S + 1) + total] = (uint16_t)sValid;
+        nUnique[b] = total;
+    }
+}
+
+__global__ void k_mf_partial_dofs(int64_t nChunks, int S, const int32_t *__restrict__ chunkBase, const int32_t *__restrict__ uniqueDof,
+                                  int32_t *__restrict__ partialDof) {
+    const int64_t b = blockIdx.x;
+    const int base = chunkBase[b], nu = chunkBase[b + 1] - base;
+    for (int u = threadIdx.x; u < nu; u += blockDim.x) partialDof[base + u] = uniqueDof[b * S + u];
+}
+
+void build_mf_chunks(mfem_b200_ctx *c) {
+    if (c->mfChunksValid && c->mfChunkElems == c->opt_mf_chunk_elems) return;
+    MFEM_REQUIRE(c->nElems > 0 && c->elemDof.p, MFEM_B200_ERR_INVALID, "matrix-free chunks: no mesh");
+    ScopedTimer timer(c, "Matrix-free Plan");
+    cudaStream_t s = c->stream;
+    const int kMfChunk = c->opt_mf_chunk_elems;
+    c->mfChunkElems = kMfChunk;
+    const int npe = c->npe, S = kMfChunk * npe;
+    const int64_t nChunks = (c->nElems + kMfChunk - 1) / kMfChunk;
+    c->mfLocalIdx.alloc((size_t)nChunks * S);
+    c->mfCsrPtr.alloc((size_t)nChunks * (S + 1));
+    c->mfCsrList.alloc((size_t)nChunks * S);
+    c->mfChunkBase.alloc((size_t)nChunks + 1);
+    c->mfChunkDof.alloc((size_t)nChunks * S);
+    int32_t *uniqueDof = c->mfChunkDof.p;
+    DevBuf<int32_t> nUnique((size_t)nChunks + 1);
+    MFEM_CUDA(cudaMemsetAsync(nUnique, 0, nUnique.bytes(), s));
+    // the element kernel reads the fixed-stride tables before it knows the chunk's count: entries past it must be valid
+    MFEM_CUDA(cudaMemsetAsync(c->mfChunkDof, 0, c->mfChunkDof.bytes(), s));
+    MFEM_CUDA(cudaMemsetAsync(c->mfCsrPtr, 0, c->mfCsrPtr.bytes(), s));
+#define MFEM_TABLES(NPE_, CH_)                                                                                      \
+    k_mf_chunk_tables<NPE_, CH_><<<(unsigned)nChunks, CH_, 0, s>>>(c->nElems, c->elemDof, c->mfLocalIdx, c->mfCsrPtr, \
+                                                                    c->mfCsrList, uniqueDof, nUnique)
+#define MFEM_TABLES_CH(NPE_)                                                                                       \
+    do {                                                                                                           \
+        if (kMfChunk == 32) MFEM_TABLES(NPE_, 32);                                                                 \
+        else if (kMfChunk == 64) MFEM_TABLES(NPE_, 64);                                                            \
+        else MFEM_TABLES(NPE_, 128);                                                                               \
+    } while (0)
+    switch (npe) {
+        case 3: MFEM_TABLES_CH(3); break;
+        case 4: MFEM_TABLES_CH(4); break;
+        case 6: MFEM_TABLES_CH(6); break;
+        default: MFEM_TABLES_CH(10); break;
+    }
+#undef MFEM_TABLES_CH
+#undef MFEM_TABLES
+    c->launches++;
+    {
+        size_t tmpBytes = 0;
+        MFEM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, nUnique.p, c->mfChunkBase.p, nChunks + 1, s));
+        DevBuf<uint8_t> tmp(tmpBytes);
+        MFEM_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmpBytes, nUnique.p, c->mfChunkBase.p, nChunks + 1, s));
+        c->launches++;
+        int32_t total = 0;
+        MFEM_CUDA(cudaMemcpyAsync(&total, c->mfChunkBase.p + nChunks, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        MFEM_CUDA(cudaStreamSynchronize(s));
+        MFEM_REQUIRE(total > 0, MFEM_B200_ERR_INVALID, "matrix-free chunks: empty plan");
+        c->mfPartials = total;
+        c->timers["Matrix-free Partials"] = (double)total;     // diagnostic, not a time
+    }
+    const int64_t nP = c->mfPartials;
+    DevBuf<int32_t> partialDof((size_t)nP);        // compact copy: the keys of the rows' partial lists
+    k_mf_partial_dofs<<<(unsigned)nChunks, 128, 0, s>>>(nChunks, S, c->mfChunkBase, uniqueDof, partialDof);
+    c->launches++;
+    {   // per DoF row: its partials (stable sort: ascending chunk order inside a row)
+        DevBuf<uint32_t> keysOut((size_t)nP);
+        DevBuf<int32_t> ids((size_t)nP);
+        c->mfIncList2.alloc((size_t)nP);
+        k_iota<<<grid_for(nP, 256), 256, 0, s>>>(nP, ids);
+        size_t tmpBytes = 0;
+        const int dofBits = bits_for(c->nDofs + 1);
+        const uint32_t *kin = reinterpret_cast<const uint32_t *>(partialDof.p);
+        MFEM_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmpBytes, kin, keysOut.p, ids.p, c->mfIncList2.p, nP, 0, dofBits, s));
+        DevBuf<uint8_t> tmp(tmpBytes);
+        MFEM_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmpBytes, kin, keysOut.p, ids.p, c->mfIncList2.p, nP, 0, dofBits, s));
+        c->mfIncPtr2.alloc((size_t)c->nDofs + 1);
+        k_rowptr_from_keys32<<<grid_for(c->nDofs + 1, 256), 256, 0, s>>>(c->nDofs, nP, keysOut, c->mfIncPtr2);
+        c->launches += 3;
+        MFEM_CUDA(cudaStreamSynchronize(s));
+    }
+    MFEM_CUDA(cudaGetLastError());
+    c->mfChunksValid = true;
 }
 
 // Symbolic phase: sorted unique (row, col) block keys -> rowptr / colidx, and the

@@ -45,23 +45,34 @@ def test_operator_matches_oracle_matrix(mfem, N, deg, sizes, mat, reorder):
         h.assemble()
         y = h.spmv(x)
         y2 = h.spmv(x)
-        h.set_option("mf_elem_order", 0)              # elements in the caller's order instead of DoF order
+        ych = []
+        for ch in (32, 64):                           # chunk sizes other than the default 128
+            h.set_option("mf_chunk_elems", ch)
+            ych.append(h.spmv(x))
+        h.set_option("mf_chunked", 0)                 # one slot per (element, node) instead of per-chunk partial sums
         y3 = h.spmv(x)
+        h.set_option("mf_elem_order", 1)              # ... with the elements in DoF order instead of the caller's
+        y4 = h.spmv(x)
         h.set_option("spmv_kernel", 0)
         ys = h.spmv(x)
     assert rel_l2(y, yref) < 1e-13
     assert rel_l2(y3, yref) < 1e-13
+    assert rel_l2(y4, yref) < 1e-13
+    assert rel_l2(ych[0], yref) < 1e-13 and rel_l2(ych[1], yref) < 1e-13
     assert rel_l2(y, ys) < 1e-13
     assert np.array_equal(y, y2)                      # no atomics: bit-reproducible
 
 
-@pytest.mark.parametrize("pad,lanes,order,policy", [(1, 4, 1, 1), (0, 4, 1, 1), (1, 8, 1, 1), (0, 8, 1, 1), (1, 4, 0, 1), (0, 8, 0, 0), (1, 8, 1, 2)])
-def test_operator_layout_variants_in_a_solve(mfem, pad, lanes, order, policy):
-    """A/B variants of the operator (packed 24-byte or padded 32-byte result slots; 4 or 8 lanes per DoF row in the
-    in-loop gather; elements in DoF order or in the caller's order; L2 policy of the slot loads): same solution."""
+@pytest.mark.parametrize("chunked,pad,lanes,order,policy", [(1, 0, 0, 0, 3), (1, 1, 8, 1, 1), (1, 0, 4, 0, 0), (0, 1, 4, 1, 1), (0, 0, 4, 1, 1),
+                                                            (0, 1, 8, 1, 1), (0, 0, 8, 1, 3), (0, 1, 4, 0, 1), (0, 0, 8, 0, 0), (0, 1, 8, 1, 2)])
+def test_operator_layout_variants_in_a_solve(mfem, chunked, pad, lanes, order, policy):
+    """A/B variants of the operator (per-chunk partial sums or one slot per (element, node); packed 24-byte or padded
+    32-byte slots; 4 or 8 lanes per DoF row in the in-loop gather; elements in DoF order or in the caller's order; L2
+    policy of the slot loads): same solution."""
     sim, fixed, vals, f = cantilever_problem(3, 2, (9, 3, 2), D=orc.material_from_json(3, ORTHO))
     u_ref = sim.solve(f)
-    with mfem.Handle(0, matrix_free=1, mf_slot_pad=pad, mf_gather_lanes=lanes, mf_elem_order=order, mf_gather_policy=policy) as h:
+    with mfem.Handle(0, matrix_free=1, mf_chunked=chunked, mf_slot_pad=pad, mf_gather_lanes=lanes, mf_elem_order=order,
+                     mf_gather_policy=policy) as h:
         h.set_mesh(3, 2, sim.mesh.nodes, sim.mesh.elem_nodes)
         h.set_material(sim.D)
         h.assemble()
