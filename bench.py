@@ -334,6 +334,7 @@ def run_ours(args):
     nodes_p, _k1 = pinned_copy(nodes)
     elems_p, _k2 = pinned_copy(elem_nodes)
     f_p, _k3 = pinned_copy(np.ascontiguousarray(f))
+    u_p, _k4 = pinned_copy(np.zeros_like(np.ascontiguousarray(f)))      # page-locked result buffer, reused by every solve
     if p is not None:
         p.nodes, p.elem_nodes = nodes_p, elems_p
     opts = {"coarse_aggregates": args.coarse_aggregates, "coarse_fine_nodes": args.coarse_fine_nodes, "matrix_free": args.matrix_free}
@@ -394,6 +395,8 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     asm_max, setup_max, solve_max, spmv_max = rmax(asm_s), rmax(setup_s), rmax(solve_s), rmax(spmv_s)
     op_max, op_elem_max, op_gather_max = rmax(op_s), rmax(op_parts[0]), rmax(op_parts[1])
+    n_partials = rsum(max(0.0, h.timer("Matrix-free Partials")))       # chunked operator: (chunk, DoF) partial sums; 0 = one slot per (element, node)
+    mf_plan_s = rmax(max(0.0, h.timer("Matrix-free Plan")))
     nnzb_tot, nb_tot, launches_tot = rsum(nnzb), rsum(nb), rsum(launches)
     dev_s = rmax(asm_s + setup_s + solve_s)
     coarse_sizes = None
@@ -457,7 +460,7 @@ def run_ours(args):
         hh.assemble()
         t2 = time.perf_counter()
         hh.fix_variables(fixed, vals)
-        uu, info = hh.solve(f_p, rtol=RTOL, return_info=True)
+        uu, info = hh.solve(f_p, rtol=RTOL, return_info=True, out=u_p)
         t3 = time.perf_counter()
         tip = float(uu.reshape(-1, 3)[:, 1].min())
         parts = {"create_upload_reorder_s": t1 - t0, "symbolic_pattern_s": hh.timer("Pattern"),
@@ -511,18 +514,26 @@ def run_ours(args):
             # packed geometry 128, the element's npe result blocks 24*npe; the x blocks once per DoF) then k_mf_gather
             # (per incidence one 4-byte slot id + 24 bytes; per DoF row: extent 8, x 24, y 24, mask 3)
             n_inc = n_elems * npe
-            elem_bytes = n_elems * (4 * npe + 128 + 24 * npe) + nb_tot * 24
-            gather_bytes = n_inc * 28 + nb_tot * 59
-            roofline = {"bound": "hbm", "kernel": "k_mf_elements<3,2> (element kernel of the PCG's mesh-based operator" + rank_note,
+            if n_partials > 0:
+                # chunked: per element the packed geometry (128) and two 16-bit tables per slot (4*npe); per (chunk, DoF)
+                # partial its extent (2), DoF id (4) and result (24); the x blocks once per DoF
+                elem_bytes = n_elems * (128 + 4 * npe) + n_partials * 30 + nb_tot * 24
+                gather_bytes = n_partials * 28 + nb_tot * 59
+                elem_kernel = "k_mf_chunk<3,2> (element kernel of the PCG's mesh-based operator: one CTA per 64 elements, per-chunk partial sums"
+            else:
+                elem_bytes = n_elems * (4 * npe + 128 + 24 * npe) + nb_tot * 24
+                gather_bytes = n_inc * 28 + nb_tot * 59
+                elem_kernel = "k_mf_elements<3,2> (element kernel of the PCG's mesh-based operator"
+            roofline = {"bound": "hbm", "kernel": elem_kernel + rank_note,
                         "achieved": elem_bytes / op_elem_max / 1e9, "peak": peak_all, "unit": "GB/s",
                         "frac": elem_bytes / op_elem_max / 1e9 / peak_all,
-                        "traffic": measured_traffic(name, "k_mf_elements", nnzb) if world == 1 else None,
+                        "traffic": measured_traffic(name, "k_mf_chunk" if n_partials > 0 else "k_mf_elements", nnzb) if world == 1 else None,
                         "peak_source": peak_src, "algorithmic_bytes_per_launch": elem_bytes, "seconds_per_launch": op_elem_max,
                         "gather_kernel": {"kernel": "k_mf_gather<3,masked,dot>", "achieved": gather_bytes / op_gather_max / 1e9, "unit": "GB/s",
                                           "frac": gather_bytes / op_gather_max / 1e9 / peak_all,
                                           "traffic": measured_traffic(name, "k_mf_gather", nnzb) if world == 1 else None,
                                           "algorithmic_bytes_per_launch": gather_bytes, "seconds_per_launch": op_gather_max},
-                        "operator_seconds_per_product": op_max,
+                        "operator_seconds_per_product": op_max, "partials": int(n_partials), "operator_plan_s_once_per_mesh": mf_plan_s,
                         "equivalent_stored_matrix_bandwidth": {"achieved": spmv_bytes / op_max / 1e9, "unit": "GB/s",
                                                                "frac": spmv_bytes / op_max / 1e9 / peak_all,
                                                                "note": "bytes the stored-matrix SpMV would have to stream for the same product / operator time"},

@@ -303,12 +303,18 @@ class Handle:
     def clear_fixed_variables(self):
         self._check(self.lib.mfem_b200_clear_fixed_variables(self._h))
 
-    def solve(self, f, rtol=1e-10, max_iters=100000, return_info=False):
+    def solve(self, f, rtol=1e-10, max_iters=100000, return_info=False, out=None):
+        """`out`: optional result array (same size as f, C-contiguous float64), e.g. page-locked memory reused across
+        solves -- a fresh pageable array costs its page faults plus a staged device-to-host copy (~0.1 s per 350 MB)."""
         n = self.n_dofs * self.dim
         f = _f64(f)
         nrhs = f.size // n
         assert f.size == nrhs * n and nrhs >= 1
-        u = np.zeros_like(f)
+        if out is None:
+            u = np.empty_like(f)
+        else:
+            assert isinstance(out, np.ndarray) and out.dtype == np.float64 and out.flags.c_contiguous and out.size == f.size
+            u = out
         info = (SolveInfo * nrhs)()
         st = self.lib.mfem_b200_solve(self._h, nrhs, _dptr(f), _dptr(u), rtol, max_iters, info)
         self.last_info = [dict(iterations=i.iterations, converged=bool(i.converged), rel_residual=i.rel_residual,

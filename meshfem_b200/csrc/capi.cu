@@ -204,7 +204,7 @@ int mfem_b200_set_option(mfem_b200_handle h, const char *name, int64_t value) {
     } else if (n == "mf_slot_pad") {
         h->opt_mf_slot_pad = value != 0;
     } else if (n == "mf_gather_lanes") {
-        MFEM_REQUIRE(value == 0 || value == 4 || value == 8, MFEM_B200_ERR_INVALID, "mf_gather_lanes must be 0 (automatic), 4 or 8");
+        MFEM_REQUIRE(value == 0 || value == 1 || value == 4 || value == 8, MFEM_B200_ERR_INVALID, "mf_gather_lanes must be 0 (automatic), 1, 4 or 8");
         h->opt_mf_gather_lanes = (int)value;
     } else if (n == "mf_elem_order") {
         h->opt_mf_elem_order = value != 0;
@@ -217,7 +217,7 @@ int mfem_b200_set_option(mfem_b200_handle h, const char *name, int64_t value) {
         MFEM_REQUIRE(value == 32 || value == 64 || value == 128, MFEM_B200_ERR_INVALID, "mf_chunk_elems must be 32, 64 or 128");
         h->opt_mf_chunk_elems = (int)value;
     } else if (n == "mf_chunk_warps") {
-        MFEM_REQUIRE(value == 12 || value == 16, MFEM_B200_ERR_INVALID, "mf_chunk_warps must be 12 or 16");
+        MFEM_REQUIRE(value == 12 || value == 16 || value == 20, MFEM_B200_ERR_INVALID, "mf_chunk_warps must be 12, 16 or 20");
         h->opt_mf_chunk_warps = (int)value;
     } else if (n == "coarse_aggregates") {
         MFEM_REQUIRE(value >= -1 && value <= 5461, MFEM_B200_ERR_INVALID,

@@ -107,7 +107,7 @@ struct mfem_b200_ctx {
     int opt_spmv_lanes = 0;                // lanes per block row in the SpMV (0 = choose from the mean row length)
     int opt_matrix_free = -1;              // PCG operator: -1 auto (mesh-based for 3D quadratic elements), 0 assembled SpMV, 1 mesh-based whenever possible
     int opt_mf_slot_pad = 0;               // matrix-free operator, 3D: 32-byte (padded) result slots; 0 = packed 24-byte slots (A/B)
-    int opt_mf_gather_lanes = 0;           // matrix-free operator: lanes per DoF row in the gather kernel (4 or 8, the in-loop launch only; 0 = 4 for chunk partials, 8 for slots)
+    int opt_mf_gather_lanes = 0;           // matrix-free operator: lanes per DoF row in the gather kernel (4 or 8, the in-loop launch only; 0 = 1 for chunk partials, 8 for slots)
     int opt_mf_elem_order = 0;             // matrix-free operator: 1 = elements processed in the order of their DoFs (build_mf_plan), 0 = caller's order (A/B)
     int opt_mf_gather_policy = 3;          // slot loads of the gather kernel: 0 evict_first, 1 evict_last, 2 evict_normal, 3 evict_last + L1 allocation (A/B)
     int opt_mf_chunked = 1;                // matrix-free operator: 1 = per-chunk partial sums in shared memory (build_mf_chunks), 0 = one slot per (element, node)

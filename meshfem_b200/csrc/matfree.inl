@@ -92,7 +92,7 @@ k_mf_elements(int64_t nElems, const int32_t *__restrict__ elemDof, const double 
 //   3. the results are summed per chunk-local DoF -- a contiguous range, (element, local node) order inside -- and written as
 //      ONE partial per (chunk, DoF), contiguous per chunk -- 2.2-3x fewer bytes than one slot per (element, node), for
 //      this kernel's stores and for the gather kernel's loads alike.
-template <int N, int DEG, bool PER_ELEM_D, int kMfChunk, int WARPS = 12>      // WARPS resident per SM: 12 (<= 168 registers) or 16 (128, a few spills)
+template <int N, int DEG, bool PER_ELEM_D, int kMfChunk, int WARPS = 12>      // WARPS resident per SM: 12 (<= 168 registers), 16 (128, a few spills) or 20 (96, ~600 bytes of spills)
 __global__ void __launch_bounds__(kMfChunk, WARPS * 32 / kMfChunk)
 k_mf_chunk(int64_t nElems, const int32_t *__restrict__ chunkBase, const int32_t *__restrict__ chunkDof,
            const uint16_t *__restrict__ localIdx, const uint16_t *__restrict__ csrPtr, const uint16_t *__restrict__ rankOfSlot,
@@ -212,7 +212,7 @@ k_mf_gather(int64_t nb, const int64_t *__restrict__ incPtr, const int32_t *__res
             const double *__restrict__ elemY, const double *__restrict__ x, double *__restrict__ y,
             const uint8_t *__restrict__ fixedMask, double *partials, unsigned *ticket, double *dotOut,
             const int *status, int slotPolicy) {
-    static_assert(LPR >= N && (LPR & (LPR - 1)) == 0, "lanes per DoF row: a power of two >= N");
+    static_assert((LPR >= N || LPR == 1) && (LPR & (LPR - 1)) == 0, "lanes per DoF row: 1, or a power of two >= N");
     constexpr unsigned FULL = 0xffffffffu;
     if (status && status[ST_STATE] != 0) return;
     // The slots are the only data of this kernel with reuse in L2 (the other slots of a fetched 64/128-byte line belong
@@ -250,7 +250,17 @@ k_mf_gather(int64_t nb, const int64_t *__restrict__ incPtr, const int32_t *__res
         for (int c = 0; c < N; ++c)
 #pragma unroll
             for (int o = 1; o < LPR; o <<= 1) acc[c] += __shfl_xor_sync(FULL, acc[c], o);
-        if (row < nb && sl < N) {
+        if (LPR == 1) {
+            if (row < nb) {
+#pragma unroll
+                for (int c = 0; c < N; ++c) {
+                    double out = acc[c];
+                    if (MASKED && fixedMask[row * N + c]) out = 0.0;
+                    y[row * N + c] = out;
+                    if (DOT) dot = fma(out, x[row * N + c], dot);
+                }
+            }
+        } else if (row < nb && sl < N) {
             double out = sl == 0 ? acc[0] : (sl == 1 ? acc[1] : acc[N - 1]);
             if (MASKED && fixedMask[row * N + sl]) out = 0.0;
             y[row * N + sl] = out;
@@ -302,7 +312,10 @@ static void launch_matrix_free_nd(mfem_b200_ctx *c, const double *x, double *y, 
         const unsigned nChunks = (unsigned)((c->nElems + ch - 1) / ch);
 #define MFEM_CHUNK(PE_, CH_, DELEM_)                                                                                        \
     do {                                                                                                                    \
-        if (c->opt_mf_chunk_warps == 16)                                                                                    \
+        if (c->opt_mf_chunk_warps == 20)                                                                                    \
+            k_mf_chunk<N, DEG, PE_, CH_, 20><<<nChunks, CH_, 0, s>>>(c->nElems, c->mfChunkBase, c->mfChunkDof, c->mfLocalIdx, c->mfCsrPtr, \
+                                                                     c->mfCsrList, c->geomP, c->Dconst, DELEM_, x, c->elemY, status); \
+        else if (c->opt_mf_chunk_warps == 16)                                                                               \
             k_mf_chunk<N, DEG, PE_, CH_, 16><<<nChunks, CH_, 0, s>>>(c->nElems, c->mfChunkBase, c->mfChunkDof, c->mfLocalIdx, c->mfCsrPtr, \
                                                                      c->mfCsrList, c->geomP, c->Dconst, DELEM_, x, c->elemY, status); \
         else                                                                                                                \
@@ -324,11 +337,14 @@ static void launch_matrix_free_nd(mfem_b200_ctx *c, const double *x, double *y, 
         k_mf_elements<N, DEG, true, PAD><<<grid, kMfThreads, 0, s>>>(c->nElems, elemDof, geomP, c->Dconst, c->Delem, perm, x, c->elemY, status);
     else
         k_mf_elements<N, DEG, false, PAD><<<grid, kMfThreads, 0, s>>>(c->nElems, elemDof, geomP, c->Dconst, nullptr, nullptr, x, c->elemY, status);
-    const int lpr = c->opt_mf_gather_lanes == 8 ? 8 : (c->opt_mf_gather_lanes == 4 ? 4 : (chunked ? 4 : 8));   // 0 = auto
+    const int lpr = c->opt_mf_gather_lanes == 8 ? 8 : (c->opt_mf_gather_lanes == 4 ? 4 : (c->opt_mf_gather_lanes == 1 ? 1 : (chunked ? 1 : 8)));   // 0 = auto
     const int pol = c->opt_mf_gather_policy;
     const int64_t ctas = (c->nDofs * lpr + kVecThreads - 1) / kVecThreads;
     const int ggrid = (int)std::max<int64_t>(1, std::min<int64_t>(ctas, std::min<int64_t>(kMaxPartials, (int64_t)sm_count(c) * 8)));
     if (!(phases & 2)) {}
+    else if (masked && dot && lpr == 1)
+        k_mf_gather<N, true, true, PAD, 1><<<ggrid, kVecThreads, 0, s>>>(c->nDofs, incPtr, incList, c->elemY, x, y, c->fixedMask,
+                                                                         w.partials, w.ticket, w.scal.p + S_PAP, status, pol);
     else if (masked && dot && lpr == 8)
         k_mf_gather<N, true, true, PAD, 8><<<ggrid, kVecThreads, 0, s>>>(c->nDofs, incPtr, incList, c->elemY, x, y, c->fixedMask,
                                                                          w.partials, w.ticket, w.scal.p + S_PAP, status, pol);

@@ -63,7 +63,7 @@ def test_operator_matches_oracle_matrix(mfem, N, deg, sizes, mat, reorder):
     assert np.array_equal(y, y2)                      # no atomics: bit-reproducible
 
 
-@pytest.mark.parametrize("chunked,pad,lanes,order,policy", [(1, 0, 0, 0, 3), (1, 1, 8, 1, 1), (1, 0, 4, 0, 0), (0, 1, 4, 1, 1), (0, 0, 4, 1, 1),
+@pytest.mark.parametrize("chunked,pad,lanes,order,policy", [(1, 0, 0, 0, 3), (1, 1, 8, 1, 1), (1, 0, 4, 0, 0), (1, 0, 1, 0, 3), (0, 0, 1, 0, 3), (0, 1, 4, 1, 1), (0, 0, 4, 1, 1),
                                                             (0, 1, 8, 1, 1), (0, 0, 8, 1, 3), (0, 1, 4, 0, 1), (0, 0, 8, 0, 0), (0, 1, 8, 1, 2)])
 def test_operator_layout_variants_in_a_solve(mfem, chunked, pad, lanes, order, policy):
     """A/B variants of the operator (per-chunk partial sums or one slot per (element, node); packed 24-byte or padded
@@ -72,7 +72,8 @@ def test_operator_layout_variants_in_a_solve(mfem, chunked, pad, lanes, order, p
     sim, fixed, vals, f = cantilever_problem(3, 2, (9, 3, 2), D=orc.material_from_json(3, ORTHO))
     u_ref = sim.solve(f)
     with mfem.Handle(0, matrix_free=1, mf_chunked=chunked, mf_slot_pad=pad, mf_gather_lanes=lanes, mf_elem_order=order,
-                     mf_gather_policy=policy) as h:
+                     mf_gather_policy=policy, mf_chunk_warps=(12, 16, 20)[(lanes + policy) % 3],
+                     mf_chunk_elems=(32, 64, 128)[(pad + lanes + order) % 3]) as h:
         h.set_mesh(3, 2, sim.mesh.nodes, sim.mesh.elem_nodes)
         h.set_material(sim.D)
         h.assemble()
