@@ -1817,6 +1817,8 @@ double time_operator(mfem_b200_ctx *c, int iters, int *matrixFree, double *secon
     MFEM_CUDA(cudaGetLastError());
     if (secondsParts) { secondsParts[0] = sec[1]; secondsParts[1] = sec[2]; }
     c->timers["Matrix-free Operator"] += sec[0] * iters;
+    // diagnostics for the caller's byte accounting (reset_timers() drops the copy written when the tables were built)
+    c->timers["Matrix-free Partials"] = (c->opt_mf_chunked && c->mfChunksValid) ? (double)c->mfPartials : 0.0;
     return sec[0];
 }
 
