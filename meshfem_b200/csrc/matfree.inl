@@ -1,27 +1,29 @@
-// K9: the PCG's operator WITHOUT the assembled matrix (quadratic elements).
+// K10: the PCG's operator WITHOUT the assembled matrix (quadratic elements).
 //
 // y = mask(K x) [, x.y] evaluated from the mesh: the quantity Simulator::applyStiffnessMatrix
 // (LinearElasticity.hh:801-823) sums element by element, with the per-element product
 // perElementStiffness * x (LinearElasticity.hh:165-232) evaluated by elem_apply (elem_math.cuh)
 // on the degree-2 rule instead of through a stored 30x30 matrix.  Why: the block-CSR SpMV streams
 // 76 bytes per 3x3 block -- 2060 bytes per node of a quadratic-tet mesh, 30.9 GB per product on the
-// 10.2 M-element workload -- and is HBM-bound at 6.8 ms.  The mesh-based operator reads 40 bytes of
-// DoF ids + 128 bytes of packed geometry per element and moves the 30 element results once through
-// HBM: ~0.65 KB per element, ~7 GB per product.
+// 10.2 M-element workload -- and is HBM-bound at 6.8 ms.  The mesh-based operator reads 128 bytes of
+// packed geometry + 40 bytes of 16-bit tables per element and moves one partial sum per (chunk, DoF)
+// once through HBM: 4.4 GB per product in all.
 //
-// Two kernels, no atomics, bit-reproducible:
-//   k_mf_elements  one thread per element: gather the 10 x blocks (L2-resident, evict-last), ~700
-//                  FMA, store the element's 30 results into its own slots elemY[e*npe + i][c]
-//                  (3D: slots padded to 32 bytes = one sector, written and read by ONE 256-bit
-//                  access each; unpadded 24-byte slots cost the gather three 8-byte requests per
-//                  incidence, measured 2.54 ms instead of ... on the 10.2 M-element workload);
-//   k_mf_gather    4 lanes per DoF row: sum the row's slots in the fixed order of the incidence
-//                  list (incPtr / incList of the symbolic phase, (element, local node) order), apply
-//                  the Dirichlet mask, write y and accumulate x.y (same two-stage deterministic
-//                  reduction as the SpMV epilogue, same scal slot).
-// The assembled matrix stays what the preconditioner set-up, the b = f - K u_fix product of
-// non-eligible cases, export and the C-ABI spmv read; the operator is used where the Krylov loop
-// multiplies (option `matrix_free`: -1 auto = quadratic elements of a mesh, 0 never, 1 whenever a
+// Two kernels, no atomics, bit-reproducible.  Default (option mf_chunked = 1):
+//   k_mf_chunk     one CTA per chunk of 64 consecutive elements (tables: setup.cu build_mf_chunks): stage the chunk's
+//                  DISTINCT x blocks in shared memory, one thread per element evaluates elem_apply (~770 FP64
+//                  instructions) and puts its results back into shared memory, the CTA sums them per distinct DoF
+//                  in a fixed order and writes ONE partial per (chunk, DoF) -- 25.6 M partials instead of 102 M
+//                  (element, node) slots on the 10.2 M-element workload;
+//   k_mf_gather    one thread per DoF row: sum the row's partials in the fixed order of a per-row list, apply the
+//                  Dirichlet mask, write y and accumulate x.y (same two-stage deterministic reduction as the SpMV
+//                  epilogue, same scal slot).
+// Measured on that workload: 1.15 + 0.33 ms per product against 6.8 ms for the SpMV.
+// A/B variant (mf_chunked = 0): k_mf_elements, one thread per element writing its 30 results into its own slots
+// elemY[e*npe + i][c] (packed, or padded to one 32-byte sector), gathered by 4 or 8 lanes per row through the
+// incidence list of the symbolic phase -- 1.11 + 1.47 ms.
+// The assembled matrix stays what the preconditioner set-up, export and the C-ABI spmv read; the operator is used where
+// the Krylov loop multiplies (option `matrix_free`: -1 auto = quadratic tetrahedra of a mesh, 0 never, 1 whenever a
 // mesh + material are present).
 //
 // Included by solver.cu (needs its reduction helpers and load wrappers).
