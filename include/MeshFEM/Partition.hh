@@ -3,9 +3,14 @@
 // every rank that touches them (owner = lowest rank).  Each rank assembles only its own elements,
 // so interface rows of its local K hold partial sums; one sum-exchange per SpMV completes them.
 //
-// Partitioner: equal-count slabs of element centroids along the longest bounding-box axis
-// (METIS is not available offline; for the bar-shaped benchmark meshes slabs are also the
-// minimum-interface cut).
+// Partitioners (METIS is not available offline):
+//   slabPartition  equal-count slabs of element centroids along the longest bounding-box axis -- the default; for the
+//                  bar-shaped benchmark meshes slabs are also the minimum-interface cut;
+//   rcbPartition   recursive coordinate bisection of the centroids for compact domains (a cube cut into 8 slabs has
+//                  7 interfaces of a full cross-section each, into 2x2x2 boxes 12 quarter-sections: less interface
+//                  per rank, but up to 7 neighbours instead of 2).  Opt-in (MESHFEM_PARTITIONER=rcb / partition(...,
+//                  method="rcb")): the device path with more than two neighbours per rank is covered on CPU by the
+//                  gloo emulation only (tests/test_multirank_cpu.py).
 #ifndef MESHFEM_B200_PARTITION_HH
 #define MESHFEM_B200_PARTITION_HH
 #include <algorithm>
@@ -37,6 +42,54 @@ inline std::vector<int32_t> slabPartition(int dim, int64_t nNodes, const double 
     std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return key[(size_t)a] < key[(size_t)b]; });
     std::vector<int32_t> part((size_t)nElems);
     for (int64_t k = 0; k < nElems; ++k) part[(size_t)order[(size_t)k]] = (int32_t)std::min<int64_t>(nParts - 1, k * nParts / nElems);
+    return part;
+}
+
+// Recursive coordinate bisection: the part range [p0, p1) is split into floor / ceil halves, the elements -- ordered by
+// their centroid coordinate along the longest extent of THIS subset, ties by element id -- in the same proportion.
+inline std::vector<int32_t> rcbPartition(int dim, int64_t nNodes, const double *nodes, int64_t nElems, int npe,
+                                         const int32_t *elemNodes, int nParts) {
+    if (nParts < 1 || nParts > 64) throw std::runtime_error("rcbPartition: 1..64 parts supported");
+    (void)nNodes;
+    const int nv = dim + 1;
+    std::vector<double> cen((size_t)nElems * 3, 0.0);
+    for (int64_t e = 0; e < nElems; ++e)
+        for (int r = 0; r < dim; ++r) {
+            double c = 0;
+            for (int v = 0; v < nv; ++v) c += nodes[(int64_t)elemNodes[e * npe + v] * dim + r];
+            cen[(size_t)e * 3 + r] = c / nv;
+        }
+    std::vector<int32_t> part((size_t)nElems, 0);
+    std::vector<int64_t> ids((size_t)nElems);
+    std::iota(ids.begin(), ids.end(), 0);
+    struct Job { int64_t b, e; int p0, p1; };
+    std::vector<Job> stack{{0, nElems, 0, nParts}};
+    while (!stack.empty()) {
+        const Job j = stack.back();
+        stack.pop_back();
+        const int np = j.p1 - j.p0;
+        if (np <= 1 || j.e - j.b == 0) {
+            for (int64_t k = j.b; k < j.e; ++k) part[(size_t)ids[(size_t)k]] = (int32_t)j.p0;
+            continue;
+        }
+        double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
+        for (int64_t k = j.b; k < j.e; ++k)
+            for (int r = 0; r < dim; ++r) {
+                const double c = cen[(size_t)ids[(size_t)k] * 3 + r];
+                mn[r] = std::min(mn[r], c); mx[r] = std::max(mx[r], c);
+            }
+        int axis = 0;
+        for (int r = 1; r < dim; ++r) if (mx[r] - mn[r] > mx[axis] - mn[axis]) axis = r;
+        const int npL = np / 2;
+        const int64_t nL = (j.e - j.b) * npL / np;
+        auto less = [&](int64_t a, int64_t b) {
+            const double ca = cen[(size_t)a * 3 + axis], cb = cen[(size_t)b * 3 + axis];
+            return ca < cb || (ca == cb && a < b);
+        };
+        std::nth_element(ids.begin() + j.b, ids.begin() + j.b + nL, ids.begin() + j.e, less);
+        stack.push_back({j.b, j.b + nL, j.p0, j.p0 + npL});
+        stack.push_back({j.b + nL, j.e, j.p0 + npL, j.p1});
+    }
     return part;
 }
 

@@ -52,6 +52,7 @@ def load_library():
         lib.mfemhost_closest_isotropic.argtypes = [c_int, POINTER(c_double), POINTER(c_double)]
         lib.mfemhost_partition.argtypes = [c_int, c_int64, POINTER(c_double), c_int64, c_int, POINTER(c_int32), c_int, c_int,
                                            POINTER(c_int64), c_int64, POINTER(c_int64)]
+        lib.mfemhost_set_partitioner.argtypes = [c_int]
         lib.mfemhost_partition_copy.argtypes = [POINTER(c_int64), POINTER(c_int64), POINTER(c_int32),
                                                 ctypes.POINTER(ctypes.c_uint8), POINTER(c_int32), POINTER(c_int64),
                                                 POINTER(c_int32), POINTER(c_int64), POINTER(c_int64)]
@@ -312,14 +313,17 @@ def from_arrays(dim, V, E) -> RawMesh:
     return RawMesh(p, dim)
 
 
-def partition(m, n_parts, rank, dof_for_node=None):
-    """Slab element partition of FEMMesh data `m` (from RawMesh.femmesh): this rank's local sub-mesh
+def partition(m, n_parts, rank, dof_for_node=None, method=None):
+    """Element partition of FEMMesh data `m` (from RawMesh.femmesh) -- method "slab" (default) or "rcb" (recursive
+    coordinate bisection; None = slabs unless MESHFEM_PARTITIONER=rcb) --: this rank's local sub-mesh
     and interface description (include/MeshFEM/Partition.hh).  Returns a SimpleNamespace with
     elems, nodes_global, elem_nodes (local node ids), local node coordinates, and -- in terms of
     DoFs, which are the nodes unless `dof_for_node` (periodic identification) is given --
     dofs_global, dof_for_node (local, or None), owned mask, neighbor_ranks and shared[q] = local DoF
     ids shared with rank q (ascending global id)."""
     lib = load_library()
+    assert method in (None, "slab", "rcb")
+    lib.mfemhost_set_partitioner(-1 if method is None else (1 if method == "rcb" else 0))
     nodes = np.ascontiguousarray(m.nodes, dtype=np.float64)
     en = np.ascontiguousarray(m.elem_nodes, dtype=np.int32)
     sz = (c_int64 * 6)()

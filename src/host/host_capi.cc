@@ -14,6 +14,7 @@
 #include <MeshFEM/filters/hex_tet_subdiv.hh>
 #include <MeshFEM/filters/quad_tri_subdiv.hh>
 
+#include <cstdlib>
 #include <cstring>
 #include <sstream>
 #include <string>
@@ -592,12 +593,21 @@ int mfemhost_save_mesh(void *m, const char *path) {
 
 // ---- element partitioning (include/MeshFEM/Partition.hh) for the multi-GPU bench and tests
 namespace { thread_local Partition::LocalPart g_part; }
+static int g_partitioner = -1;          // -1: from the environment
 extern "C" {
+int mfemhost_set_partitioner(int method) { g_partitioner = method; return 0; }
 // sizes5: [nLocalElems, nLocalNodes, nNeighbors, nSharedTotal, nOwned]
 int mfemhost_partition(int dim, int64_t nNodes, const double *nodes, int64_t nElems, int npe, const int32_t *elemNodes,
                        int nParts, int rank, const int64_t *dofForNode, int64_t nDofs, int64_t *sizes6) {
     try {
-        auto part = Partition::slabPartition(dim, nNodes, nodes, nElems, npe, elemNodes, nParts);
+        // 0 = slabs (default), 1 = recursive coordinate bisection; mfemhost_set_partitioner or MESHFEM_PARTITIONER=rcb
+        int method = g_partitioner;
+        if (method < 0) {
+            const char *env = std::getenv("MESHFEM_PARTITIONER");
+            method = (env && std::string(env) == "rcb") ? 1 : 0;
+        }
+        auto part = method == 1 ? Partition::rcbPartition(dim, nNodes, nodes, nElems, npe, elemNodes, nParts)
+                                : Partition::slabPartition(dim, nNodes, nodes, nElems, npe, elemNodes, nParts);
         g_part = Partition::extractPart(rank, nParts, nNodes, nElems, npe, elemNodes, part, dofForNode, nDofs);
         sizes6[0] = (int64_t)g_part.elems.size(); sizes6[1] = (int64_t)g_part.nodes.size();
         sizes6[2] = (int64_t)g_part.neighborRanks.size(); sizes6[3] = (int64_t)g_part.sharedLocal.size();

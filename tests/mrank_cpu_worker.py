@@ -21,7 +21,7 @@ def main():
     from multi_gpu import local_problem
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
-    grid, deg = (10, 2, 2), 2
+    grid, deg = tuple(int(v) for v in os.environ.get("MRANK_GRID", "10,2,2").split(",")), 2      # MESHFEM_PARTITIONER=rcb: see Partition.hh
     m = wl.grid_femmesh(grid, deg)
     D = wl.material("ortho")
     fixed, vals, f = wl.cantilever_inputs(m)
