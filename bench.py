@@ -534,6 +534,15 @@ def run_ours(args):
                                           "traffic": measured_traffic(name, "k_mf_gather", nnzb) if world == 1 else None,
                                           "algorithmic_bytes_per_launch": gather_bytes, "seconds_per_launch": op_gather_max},
                         "operator_seconds_per_product": op_max, "partials": int(n_partials), "operator_plan_s_once_per_mesh": mf_plan_s,
+                        # the element kernel is not HBM-bound (ncu, profiles/r2_ncu_full_cfg5_matrix_free_pcg_kernels.txt: DRAM 30 %, L1 /
+                        # shared memory 82.6 %, FP64 pipe 44.5 %): its FP64 rate beside the byte rate.  769 FP64 instructions per
+                        # element in the SASS of k_mf_chunk<3,2> (546 DFMA + 126 DADD + 97 DMUL) = 1315 flop
+                        "fp64": {"flop_per_launch": 1315 * n_elems, "achieved_tflops": 1315 * n_elems / op_elem_max / 1e12,
+                                 "peak_tflops": 37.0 * world, "peak_source": "NVIDIA spec (FP64 vector), not in MEASURED_PEAKS.json",
+                                 "frac": 1315 * n_elems / op_elem_max / 1e12 / (37.0 * world)},
+                        "note": "the PCG multiplies with the mesh-based operator, so the dominant kernel of the step is its element kernel, "
+                                "not the SpMV; SURVEY 8(d)'s SpMV figure (nnzb*76 + nb*52 bytes) is reported under stored_matrix_spmv, and "
+                                "the same bytes over the operator's time under equivalent_stored_matrix_bandwidth",
                         "equivalent_stored_matrix_bandwidth": {"achieved": spmv_bytes / op_max / 1e9, "unit": "GB/s",
                                                                "frac": spmv_bytes / op_max / 1e9 / peak_all,
                                                                "note": "bytes the stored-matrix SpMV would have to stream for the same product / operator time"},
