@@ -57,6 +57,18 @@ def main():
         dist.all_reduce(t)
         return float(t.item())
 
+    # the PCG's matrix-free operator on this rank's elements (numpy restatement of csrc/matfree.inl, tools/emulate_matrix_free.py):
+    # equal to the local matrix, and the identity the N-rank iteration relies on -- sum over ranks of the LOCAL products
+    # x_loc.(K_loc x_loc) == x.(K x) over owned DoFs after the interface exchange -- holds with it
+    import emulate_matrix_free as emf
+    tab = emf.build_chunk_tables(p.elem_nodes.astype(np.int64), p.num_nodes, 64)
+    Ke = orc.per_element_stiffness(3, deg, vol, G, D)
+    xr = np.cos(0.37 * (np.arange(N)[None, :] + 1) * (p.nodes_global[:, None] + 1.0))        # the same values on every sharer
+    y_mf, dot_loc = emf.apply_operator(tab, Ke, xr, N)
+    assert np.abs(y_mf.reshape(-1) - K @ xr.reshape(-1)).max() <= 1e-12 * np.abs(y_mf).max()
+    y_full = exchange_add(y_mf.reshape(-1).copy(), N)
+    lhs, rhs = gsum(dot_loc), gsum(xr.reshape(-1)[owned] @ y_full[owned])
+    assert abs(lhs - rhs) <= 1e-12 * abs(rhs), (lhs, rhs)
     free = np.ones(n, bool); free[lfixed] = False
     ufix = np.zeros(n); ufix[lfixed] = lvals
     # block-Jacobi on the COMPLETED diagonal blocks
