@@ -78,19 +78,29 @@ int mfem_b200_comm_window_handle(mfem_b200_handle h, void *out64);
 int mfem_b200_comm_window_open(mfem_b200_handle h, const void *handles_rank_order);
 int mfem_b200_comm_uses_peer_window(mfem_b200_handle h);
 
-/* ---- options (before set_mesh) --------------------------------------------------- */
+/* ---- options ("reorder" before set_mesh; the others at any time between solves) ------- */
 /* "reorder": 1 (default) renumbers DoFs along a space-filling curve inside the handle;
  *            every ABI function still speaks the caller's numbering.
  * "assembly": 0 = block-owner (default: every BSR block summed by one thread from its sorted
  *                 contribution list and written exactly once, coalesced),
  *             1 = graph-coloured element scatter (read-modify-write, no atomics),
  *             2 = owner-gather by DoF row (first-generation kernel, kept for A/B).
- * "coarse_aggregates": S > 0 adds an aggregation coarse space (rigid-body modes of at most S aggregates: near-cubic
- *             boxes over the bounding box of the DoFs; "coarse_shape" = 1 selects contiguous runs of the internal
- *             DoF numbering instead, one GPU only) to the block-Jacobi preconditioner, M^-1 = B^-1 + Z (Z'KZ)^-1 Z'
- *             (csrc/coarse.inl; single right-hand side; on several GPUs every rank aggregates the DoFs it owns and the coarse
- *             matrix / residuals are all-reduced -- set the same value on every rank; default 0 = off; may be changed
- *             between solves). */
+ * "coarse_aggregates": -1 (default) = multilevel aggregation preconditioner sized from the problem (block-Jacobi alone
+ *             below 30 k DoFs or when the coarse matrix is not SPD), 0 = block-Jacobi only, S > 0 = at most S large
+ *             aggregates (near-cubic boxes over the bounding box of the DoFs, rigid-body modes, dense level inverted
+ *             explicitly); "coarse_fine_nodes": nodes per small (level-1) aggregate, default 64, 0 = none
+ *             (csrc/coarse.inl; on several GPUs set the same values on every rank; may be changed between solves).
+ * "matrix_free": what the Krylov loop multiplies with.  -1 (default) = for quadratic tetrahedra of a mesh given through
+ *             set_mesh the product K*p is evaluated from the mesh (csrc/matfree.inl: what applyStiffnessMatrix,
+ *             LinearElasticity.hh:801-823, computes; no atomics, bit-reproducible), the stored block-CSR matrix
+ *             otherwise; 0 = always the stored matrix; 1 = the mesh-based operator for every element type.  Matrices from
+ *             set_matrix_triplets are always multiplied as stored.  A/B variants of the operator: "mf_chunked" (1 = per-chunk
+ *             partial sums, default; 0 = one slot per (element, node)), "mf_chunk_elems" (32 / 64 / 128), "mf_chunk_warps"
+ *             (12 / 16 / 20), "mf_gather_lanes" (0 auto / 1 / 4 / 8), "mf_gather_policy" (0..3), "mf_slot_pad", "mf_elem_order".
+ * "spmv_kernel", "spmv_lanes", "spmv_prefetch", "spmv_min_blocks": A/B variants of the stored-matrix SpMV (spmv_kernel 6:
+ *             mfem_b200_spmv evaluates the mesh-based operator instead -- parity tests); "graph" (CUDA graph of the
+ *             iteration, default 1), "batch_rhs" (flatLen(N) right-hand sides as one batched PCG when the levels are
+ *             off), "comm_p2p" (N ranks: peer-window collectives, default 1). */
 int mfem_b200_set_option(mfem_b200_handle h, const char *name, int64_t value);
 
 /* ---- mesh ------------------------------------------------------------------------ */
