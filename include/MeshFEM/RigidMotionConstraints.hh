@@ -17,9 +17,10 @@
 //   reference's augmented matrix (SparseMatrices.hh:2389-2500).
 //
 // Z is found, not assumed: among the candidate rigid modes (translations; infinitesimal rotations when
-// nodes and DoFs coincide) the combinations that vanish on every fixed variable.  If their number
-// differs from the number of rows the configuration is not one the reference can solve either
-// (its matrix is singular) or needs a Schur-complement solve on a non-singular K_ff, and we throw.
+// nodes and DoFs coincide) the combinations that vanish on every fixed variable.  More rows than free
+// modes (down to none: Dirichlet conditions that already make K_ff definite, with no_rigid_motion on top) is
+// the same saddle point with a Schur complement for the surplus rows -- m - k extra SPSD solves, see solve();
+// fewer rows than free modes is singular for the reference too, and we throw.
 #ifndef MESHFEM_B200_RIGIDMOTIONCONSTRAINTS_HH
 #define MESHFEM_B200_RIGIDMOTIONCONSTRAINTS_HH
 #include <algorithm>
@@ -156,6 +157,15 @@ inline std::vector<Vec> freeRigidModes(size_t n, std::vector<Vec> modes, const s
 // Solve the saddle-point systems for the right-hand sides fs (see the header comment).
 //   solveSPSD(rhs) -> u: solves K_ff u_f = rhs_f - K_fc u_c for every right-hand side and returns the full
 //   vectors with the fixed values in place (the device PCG; K_ff may be singular, the systems are consistent).
+//
+// General form (k = free rigid modes, m = rows, k <= m): with W = C_f Z (m x k, full column rank) the multipliers are
+//   l = l0 + Nn mu,   l0 = W (W^T W)^-1 Z^T f  (the part the null space of K_ff dictates),  Nn = null(W^T)  (m x (m-k)),
+// and with  K_ff u_p = f - C^T l0 - K_fc u_c  and  K_ff y_j = C_f^T Nn_j  (m-k more consistent solves, shared by all
+// right-hand sides)
+//   u = u_p - sum_j mu_j y_j + Z a,     [ -C y_1 .. -C y_(m-k) | W ] (mu; a) = d - C u_p .
+// k = m (the rows remove exactly the null space -- every configuration the no-rigid-motion rows were made for): Nn is
+// empty and this is the three-line recipe of the header.  k = 0 (Dirichlet conditions already make K_ff definite, rows
+// on top: the reference solves that saddle point too): the classical Schur complement S = C K_ff^-1 C^T.
 template <class SolveFn>
 std::vector<Vec> solve(size_t n, const Rows &C, const std::vector<size_t> &fixedVars, const std::vector<Vec> &candidateModes,
                        const std::vector<Vec> &fs, SolveFn &&solveSPSD, std::vector<Vec> *multipliers = nullptr) {
@@ -164,40 +174,109 @@ std::vector<Vec> solve(size_t n, const Rows &C, const std::vector<size_t> &fixed
     for (const auto &r : C.rows) if (r.size() != n) throw std::runtime_error("Bad constraint rows");
     for (const auto &f : fs) if (f.size() != n) throw std::runtime_error("Bad RHS");
     std::vector<Vec> Z = freeRigidModes(n, candidateModes, fixedVars);
-    if (Z.size() != m)
+    const size_t k = Z.size();
+    if (k > m)
         throw std::runtime_error("Unsupported constrained system: " + std::to_string(m) + " Lagrange-multiplier row(s) but the fixed variables leave " +
-                                 std::to_string(Z.size()) + " rigid mode(s) free (the rows must remove exactly the null space of the stiffness matrix)");
+                                 std::to_string(k) + " rigid mode(s) free (the rows must remove the null space of the stiffness matrix)");
     std::vector<uint8_t> isFixed(n, 0);
     for (size_t v : fixedVars) isFixed[v] = 1;
-    // W = C_f Z
-    std::vector<Real> W(m * m), Wt(m * m);
+    // W = C_f Z  (m x k)
+    std::vector<Real> W(m * k);
     for (size_t i = 0; i < m; ++i)
-        for (size_t j = 0; j < m; ++j) {
+        for (size_t j = 0; j < k; ++j) {
             long double s = 0.0L;
             for (size_t q = 0; q < n; ++q) if (!isFixed[q]) s += (long double)C.rows[i][q] * Z[j][q];
-            W[i * m + j] = (Real)s;
-            Wt[j * m + i] = (Real)s;
+            W[i * k + j] = (Real)s;
         }
+    // Nn = null(W^T): eigenvectors of W W^T (m x m) with vanishing eigenvalue; exactly m - k of them iff W has full column rank
+    const size_t e = m - k;
+    std::vector<Vec> Nn;
+    if (e > 0) {
+        std::vector<Real> G(m * m, 0.0), V;
+        Real trace = 0.0;
+        for (size_t i = 0; i < m; ++i)
+            for (size_t j = 0; j < m; ++j) {
+                Real s = 0.0;
+                for (size_t t = 0; t < k; ++t) s += W[i * k + t] * W[j * k + t];
+                G[i * m + j] = s;
+                if (i == j) trace += s;
+            }
+        Vec evals;
+        symmetricEigen(m, G, evals, V);
+        for (size_t j = 0; j < m; ++j) {
+            if (std::abs(evals[j]) > 1e-10 * std::max(trace, Real(1e-300)) && k > 0) continue;
+            Vec v(m);
+            for (size_t i = 0; i < m; ++i) v[i] = V[i * m + j];
+            Nn.push_back(std::move(v));
+        }
+        if (Nn.size() != e) throw std::runtime_error("Singular constraint system: constraint rows do not control the free rigid modes");
+    }
+    // W^T W (k x k) for the least-norm multipliers
+    std::vector<Real> WtW(k * k, 0.0);
+    for (size_t a = 0; a < k; ++a)
+        for (size_t b = 0; b < k; ++b)
+            for (size_t i = 0; i < m; ++i) WtW[a * k + b] += W[i * k + a] * W[i * k + b];
     std::vector<Vec> lambdas, rhs;
     for (const auto &f : fs) {
-        Vec ztf(m);
-        for (size_t j = 0; j < m; ++j) ztf[j] = dot(Z[j], f);          // Z vanishes on the fixed variables
-        Vec l = denseSolve(m, Wt, ztf, "constraint rows do not control the free rigid modes");
+        Vec l(m, 0.0);
+        if (k > 0) {
+            Vec ztf(k);
+            for (size_t j = 0; j < k; ++j) ztf[j] = dot(Z[j], f);      // Z vanishes on the fixed variables
+            if (k == m) {                                               // square W: W^T l = Z^T f directly
+                std::vector<Real> Wt(m * m);
+                for (size_t i = 0; i < m; ++i)
+                    for (size_t j = 0; j < m; ++j) Wt[j * m + i] = W[i * m + j];
+                l = denseSolve(m, Wt, ztf, "constraint rows do not control the free rigid modes");
+            } else {
+                const Vec c = denseSolve(k, WtW, ztf, "constraint rows do not control the free rigid modes");
+                for (size_t i = 0; i < m; ++i)
+                    for (size_t j = 0; j < k; ++j) l[i] += W[i * k + j] * c[j];
+            }
+        }
         Vec b = f;
         for (size_t i = 0; i < m; ++i)
             if (l[i] != 0.0) for (size_t q = 0; q < n; ++q) b[q] -= l[i] * C.rows[i][q];
         lambdas.push_back(std::move(l));
         rhs.push_back(std::move(b));
     }
+    // the extra systems K_ff y_j = C_f^T Nn_j ride on the first right-hand side: y_j = u(rhs_0 + C^T Nn_j) - u(rhs_0)
+    // (the solver keeps the fixed values in place; they cancel in the difference)
+    const size_t nf = fs.size();
+    if (e > 0 && nf == 0) return {};
+    for (size_t j = 0; j < e; ++j) {
+        Vec b = rhs[0];
+        for (size_t i = 0; i < m; ++i)
+            if (Nn[j][i] != 0.0) for (size_t q = 0; q < n; ++q) b[q] += Nn[j][i] * C.rows[i][q];
+        rhs.push_back(std::move(b));
+    }
     std::vector<Vec> us = solveSPSD(rhs);
-    if (us.size() != fs.size()) throw std::runtime_error("constrained solve: solver returned the wrong number of solutions");
-    for (auto &u : us) {
+    if (us.size() != nf + e) throw std::runtime_error("constrained solve: solver returned the wrong number of solutions");
+    for (auto &u : us)
         if (u.size() != n) throw std::runtime_error("constrained solve: solver returned a vector of the wrong size");
+    std::vector<Vec> Y(e);
+    for (size_t j = 0; j < e; ++j) {
+        Y[j] = us[nf + j];
+        for (size_t q = 0; q < n; ++q) Y[j][q] -= us[0][q];
+    }
+    us.resize(nf);
+    // M = [ -C y_1 .. -C y_e | W ]  (m x m)
+    std::vector<Real> M(m * m, 0.0);
+    for (size_t i = 0; i < m; ++i) {
+        for (size_t j = 0; j < e; ++j) M[i * m + j] = -dot(C.rows[i], Y[j]);
+        for (size_t j = 0; j < k; ++j) M[i * m + e + j] = W[i * k + j];
+    }
+    for (size_t r = 0; r < nf; ++r) {
+        Vec &u = us[r];
         Vec d(m);
         for (size_t i = 0; i < m; ++i) d[i] = C.rhs[i] - dot(C.rows[i], u);     // fixed columns included: C u = d
-        const Vec a = denseSolve(m, W, d, "constraint rows do not control the free rigid modes");
-        for (size_t j = 0; j < m; ++j)
-            if (a[j] != 0.0) for (size_t q = 0; q < n; ++q) u[q] += a[j] * Z[j][q];
+        const Vec x = denseSolve(m, M, d, "constraint rows do not control the free rigid modes");
+        for (size_t j = 0; j < e; ++j) {
+            if (x[j] == 0.0) continue;
+            for (size_t q = 0; q < n; ++q) u[q] -= x[j] * Y[j][q];
+            for (size_t i = 0; i < m; ++i) lambdas[r][i] += x[j] * Nn[j][i];
+        }
+        for (size_t j = 0; j < k; ++j)
+            if (x[e + j] != 0.0) for (size_t q = 0; q < n; ++q) u[q] += x[e + j] * Z[j][q];
     }
     if (multipliers) *multipliers = lambdas;
     return us;

@@ -167,3 +167,38 @@ def test_rigid_motion_constraint_with_rhs_oracle():
     with pytest.raises(RuntimeError, match="Invalid rigid motion RHS"):
         sim.rigid_motion_rhs = np.zeros(2)
         sim.constraints()
+
+
+def test_rows_on_top_of_a_definite_system_schur_complement(hostlib):
+    """no_rigid_motion together with a clamped face: the Dirichlet conditions already remove every rigid mode (k = 0), the
+    three rotation rows + three translation rows come on top -- the reference factorises that saddle point as well
+    (SparseMatrices.hh:2332-2348); here the six rows are resolved by a Schur complement, six extra SPSD solves."""
+    bc = {"no_rigid_motion": True, "regions": [{"type": "dirichlet", "value": [0, 0, 0], "box%": FACE_MIN_X},
+                                               {"type": "force", "value": [0.5, -2.0, 1.0], "box%": FACE_MAX_X}]}
+    sim, U, lam = _check(hostlib, 3, 1, (3, 2, 2), bc, nrows=6, extra_rhs=1)
+    assert np.abs(lam[0]).max() > 1e-4
+    # and the constrained solution is NOT the plain clamped-cantilever solution: the rows act
+    fixed, vals, C, d = sim.constraints()
+    u_plain = orc.solve_fixed(sim.stiffness(), sim.neumann_load().reshape(-1), fixed, vals)
+    assert np.abs(U[0] - u_plain).max() > 1e-3 * np.abs(u_plain).max()
+
+
+def test_more_rows_than_free_rigid_modes_mixed_case(hostlib):
+    """2D, y fixed on the bottom edge (removes the y translation and the rotation, leaves the x translation: k = 1) and
+    no_rigid_motion on top (one rotation row + two translation rows: m = 3): one multiplier direction is dictated by the
+    null space, the other two by the Schur complement."""
+    bc = {"no_rigid_motion": True,
+          "regions": [{"type": "dirichlety", "value": [0, 0, 0], "box%": {"minCorner": [-0.01, -0.001], "maxCorner": [1.01, 0.001]}},
+                      {"type": "force", "value": [1.0, -2.0, 0], "box%": {"minCorner": [-0.01, 0.999], "maxCorner": [1.01, 1.001]}}]}
+    _check(hostlib, 2, 2, (5, 3), bc, nrows=3, extra_rhs=1)
+
+
+def test_too_few_rows_is_still_rejected(hostlib):
+    """Fewer rows than free rigid modes: singular for the reference too."""
+    sim = _oracle_sim(3, 1, (2, 2, 2), {"no_rigid_motion": True, "regions": []})
+    fixed, vals, C, d = sim.constraints()
+    r = hostlib.grid([2, 2, 2]).apply_bc(1, json.dumps({"no_rigid_motion": True, "regions": []}))
+    K = sim.stiffness().tocsr()
+    with pytest.raises(RuntimeError, match="rigid mode"):
+        hostlib.constrained_solve(r["constraint_rows"][:3], r["constraint_rhs"][:3], r["fixed_vars"], r["rigid_modes"],
+                                  np.ones((1, K.shape[0])), _spsd_solver(K, fixed, vals, None))
